@@ -1,0 +1,190 @@
+"""ctypes binding of libd2b200.so (the C-ABI declared in include/d2b200.h).
+
+There is NO fallback: if the shared library is missing or an entry point fails,
+the operators raise.  torch is used only for device memory and streams.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libd2b200.so")
+
+MAX_LEVELS = 8
+DTYPE_F32, DTYPE_BF16 = 0, 1
+TOPK_IDENTITY, TOPK_SIGMOID = 0, 1
+MNMS_GAUSSIAN, MNMS_LINEAR = 0, 1
+
+_vp = C.c_void_p
+_i32 = C.c_int32
+_i64 = C.c_int64
+_f32 = C.c_float
+
+
+class RoiAlignParams(C.Structure):
+    _fields_ = [
+        ("features", _vp * MAX_LEVELS), ("height", _i32 * MAX_LEVELS), ("width", _i32 * MAX_LEVELS),
+        ("scale", _f32 * MAX_LEVELS), ("num_levels", _i32), ("num_images", _i32), ("channels", _i32),
+        ("feature_dtype", _i32), ("boxes", _vp), ("batch_idx", _vp), ("batch_idx_is_int64", _i32),
+        ("batch_idx_stride", _i64), ("num_rois", _i64), ("output_h", _i32), ("output_w", _i32),
+        ("sampling_ratio", _i32), ("aligned", _i32), ("pad_border", _i32), ("min_level", _i32),
+        ("canonical_box_size", _i32), ("canonical_level", _i32), ("out", _vp), ("out_dtype", _i32),
+        ("level_counts", _vp), ("level_assignments", _vp),
+    ]
+
+
+class ApplyDeltasParams(C.Structure):
+    _fields_ = [("deltas", _vp), ("boxes", _vp), ("n", _i64), ("k", _i32), ("weights", _f32 * 4),
+                ("scale_clamp", _f32), ("out", _vp)]
+
+
+class SegmentedTopkParams(C.Structure):
+    _fields_ = [("scores", _vp * MAX_LEVELS), ("row_len", _i64 * MAX_LEVELS), ("k_limit", _i32 * MAX_LEVELS),
+                ("num_groups", _i32), ("rows_per_group", _i32), ("k", _i32), ("transform", _i32),
+                ("out_values", _vp), ("out_indices", _vp), ("out_counts", _vp)]
+
+
+class BatchedNmsParams(C.Structure):
+    _fields_ = [("boxes", _vp), ("scores", _vp), ("counts", _vp), ("num_segments", _i32), ("n", _i32),
+                ("max_output_size", _i32), ("iou_threshold", _f32), ("keep", _vp), ("num_keep", _vp)]
+
+
+class RpnProposalsParams(C.Structure):
+    _fields_ = [("logits", _vp * MAX_LEVELS), ("proposals", _vp * MAX_LEVELS), ("deltas", _vp * MAX_LEVELS),
+                ("anchors", _vp * MAX_LEVELS), ("hwa", _i64 * MAX_LEVELS), ("num_levels", _i32),
+                ("num_images", _i32), ("image_shapes", _vp), ("nms_thresh", _f32), ("pre_nms_topk", _i32),
+                ("post_nms_topk", _i32), ("min_box_side_len", _f32), ("weights", _f32 * 4),
+                ("scale_clamp", _f32), ("out_boxes", _vp), ("out_logits", _vp), ("out_valid", _vp),
+                ("out_num_valid", _vp), ("out_nms_boxes_in", _vp)]
+
+
+class FastRcnnParams(C.Structure):
+    _fields_ = [("boxes", _vp), ("scores", _vp), ("indices", _vp), ("num_preds", _i64), ("num_images", _i32),
+                ("rmax", _i32), ("num_bbox_reg_classes", _i32), ("num_classes", _i32), ("image_shapes", _vp),
+                ("score_thresh", _f32), ("nms_thresh", _f32), ("topk_per_image", _i32),
+                ("nms_cls_agnostic", _i32), ("out_boxes", _vp), ("out_scores", _vp), ("out_classes", _vp),
+                ("out_valid", _vp), ("out_roi_index", _vp), ("out_num", _vp), ("out_nms_boxes_in", _vp)]
+
+
+class RetinanetParams(C.Structure):
+    _fields_ = [("box_cls", _vp * MAX_LEVELS), ("box_delta", _vp * MAX_LEVELS), ("anchors", _vp * MAX_LEVELS),
+                ("hwa", _i64 * MAX_LEVELS), ("num_levels", _i32), ("num_images", _i32), ("num_classes", _i32),
+                ("topk_candidates", _i32), ("score_thresh", _f32), ("nms_thresh", _f32),
+                ("max_detections", _i32), ("weights", _f32 * 4), ("scale_clamp", _f32), ("out_boxes", _vp),
+                ("out_scores", _vp), ("out_classes", _vp), ("out_valid", _vp), ("out_num", _vp),
+                ("out_nms_boxes_in", _vp)]
+
+
+class MatrixNmsParams(C.Structure):
+    _fields_ = [("masks", _vp), ("classes", _vp), ("scores", _vp), ("sum_masks", _vp), ("counts", _vp),
+                ("batch", _i32), ("n", _i32), ("hw", _i64), ("kernel", _i32), ("sigma", _f32), ("out", _vp)]
+
+
+# op name -> params struct; every op exports d2b_<op> and d2b_<op>_workspace_bytes
+OPS = {
+    "roi_align_multilevel": RoiAlignParams,
+    "apply_deltas": ApplyDeltasParams,
+    "segmented_topk": SegmentedTopkParams,
+    "batched_nms": BatchedNmsParams,
+    "rpn_proposals": RpnProposalsParams,
+    "fast_rcnn_postprocess": FastRcnnParams,
+    "retinanet_postprocess": RetinanetParams,
+    "matrix_nms": MatrixNmsParams,
+}
+EXPORTS = ["d2b_version", "d2b_status_string", "d2b_last_error"] + \
+          [f"d2b_{op}{sfx}" for op in OPS for sfx in ("", "_workspace_bytes")]
+
+
+class D2BError(RuntimeError):
+    pass
+
+
+_lib = None
+launch_count = 0  # C-ABI op calls issued by this process (bench.py reports it)
+
+
+def lib():
+    """Load libd2b200.so; raises if it has not been built (no CPU fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise D2BError(f"{LIB_PATH} not found: build it with `python -m detectron2_tensorflow_b200.build` "
+                           "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.d2b_version.restype = C.c_int
+        L.d2b_status_string.restype = C.c_char_p
+        L.d2b_status_string.argtypes = [C.c_int]
+        L.d2b_last_error.restype = C.c_char_p
+        for op, st in OPS.items():
+            f = getattr(L, f"d2b_{op}")
+            f.restype = C.c_int
+            f.argtypes = [C.POINTER(st), _vp, C.c_size_t, _vp]
+            w = getattr(L, f"d2b_{op}_workspace_bytes")
+            w.restype = C.c_size_t
+            w.argtypes = [C.POINTER(st)]
+        _lib = L
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    return t.data_ptr()
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    """Grow-only per-(device, stream) scratch buffer owned by the host layer (the C library never allocates)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def call(op, params, device):
+    """Run d2b_<op> on torch's current stream of `device`."""
+    global launch_count
+    L = lib()
+    with torch.cuda.device(device):
+        nbytes = getattr(L, f"d2b_{op}_workspace_bytes")(C.byref(params))
+        ws = _workspace(nbytes, device) if nbytes else None
+        stream = torch.cuda.current_stream(device).cuda_stream
+        rc = getattr(L, f"d2b_{op}")(C.byref(params), ws.data_ptr() if ws is not None else None,
+                                     nbytes, C.c_void_p(stream))
+    launch_count += 1
+    if rc != 0:
+        msg = f"d2b_{op}: {L.d2b_status_string(rc).decode()}: {L.d2b_last_error().decode()}"
+        if rc == -1:
+            raise ValueError(msg)
+        raise D2BError(msg)
+
+
+def to_device(t, device, dtype=None):
+    """Host->device staging used by every operator: accepts torch tensors (any device) or array-likes."""
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    return t.contiguous()
+
+
+def default_device():
+    if not torch.cuda.is_available():
+        raise D2BError("no CUDA device: libd2b200 has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def device_of(*tensors):
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            return t.device
+    return default_device()

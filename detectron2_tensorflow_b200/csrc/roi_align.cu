@@ -1,0 +1,337 @@
+// roi_align.cu -- multi-level ROIAlign (ROIPooler.call) as ONE gather kernel.
+//
+// Replaces, per reference call of ROIPooler.call (lib/modeling/poolers.py:134-180):
+//   assign_boxes_to_levels (poolers.py:11-49)  -> computed in the CTA prologue
+//   tf.where/gather per level (:166-169)       -> gone: every ROI knows its level
+//   tf.pad SYMMETRIC (functional.py:125)       -> gone: border rule = index clamp
+//   tf.image.crop_and_resize (functional.py:164) + avg_pool (roi_align.py:59-65)
+//                                              -> fused gather + register accumulate
+//   concat + invert_permutation + gather (:175-178) -> gone: ROI i writes row i
+//
+// Layout: one CTA per ROI.  The prologue computes, once per ROI and in exactly
+// the reference's fp32 operation order, the sample coordinates of every crop
+// row and column (top/bottom index, lerp weight, validity) into shared memory.
+// Main loop: one warp per output bin, lanes own contiguous 16-byte channel
+// groups (NHWC => 512 B coalesced per warp request), the 4 corner vectors of
+// each sample are loaded with ld.global.nc and the result is written with a
+// streaming store so the output stream does not evict feature maps from L2.
+// HBM-bound gather: no contraction, so no tensor cores.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace d2b {
+namespace {
+
+constexpr int kMaxSamples = 128;  // max crop rows / cols per ROI (output * sampling_ratio)
+constexpr int kThreads = 256;
+
+struct Level {
+  const void* ptr;
+  int H, W;
+  float scale;
+};
+
+struct RoiAlignArgs {
+  Level lv[D2B_MAX_LEVELS];
+  int L, N, C;
+  const float* boxes;
+  const void* bidx;
+  int bidx64;
+  long long bidx_stride;
+  long long M;
+  int oh, ow, sr, aligned, pad;
+  int min_level, max_level;
+  float canon_size, canon_level;
+  void* out;
+  int* level_counts;
+  int64_t* level_out;
+};
+
+struct Tap {   // one crop row (or column) of one ROI
+  int i0, i1;  // clamped un-padded indices of the two neighbours
+  float w;     // lerp weight toward i1
+  int valid;   // 0 => extrapolation (zeros)
+};
+
+// assign_boxes_to_levels, poolers.py:37-49 (one rounding per op)
+__device__ __forceinline__ int level_of(float y1, float x1, float y2, float x2, int min_level,
+                                        int max_level, float canon_size, float canon_level) {
+  const float eps = 2.220446049250313e-16f;
+  const float ln2 = 0.6931471805599453f;
+  float hh = y2 - y1;
+  float ww = x2 - x1;
+  float area = hh * ww;
+  float s = sqrtf(area);
+  float t = s / canon_size;
+  t = t + eps;
+  float v = d2b_logf(t);
+  v = v / ln2;
+  v = canon_level + v;
+  v = floorf(v);
+  int lvl;
+  if (v != v) lvl = min_level;
+  else if (v <= (float)min_level) lvl = min_level;
+  else if (v >= (float)max_level) lvl = max_level;
+  else lvl = (int)v;
+  return lvl - min_level;
+}
+
+// functional.py:128-160 + TF CropAndResize coordinate rule for sample `s` of `cs`
+// along an axis of (padded) extent P; lo/hi are the scaled (+pad) box edges.
+__device__ __forceinline__ Tap make_tap(float lo, float hi, int s, int cs, int P, int pad,
+                                        int dim, int aligned) {
+  float n1, n2;
+  if (aligned) {
+    float sp = (hi - lo) / (float)cs;
+    float im = (float)(P - 1);
+    float a = sp / 2.0f;
+    a = lo + a;
+    a = a - 0.5f;
+    n1 = a / im;
+    float nl = sp * (float)(cs - 1);
+    nl = nl / im;
+    n2 = n1 + nl;
+  } else {
+    n1 = lo / (float)P;
+    n2 = hi / (float)P;
+  }
+  float in;
+  if (cs > 1) {
+    const float step = (n2 - n1) * (float)(P - 1) / (float)(cs - 1);
+    in = n1 * (float)(P - 1) + (float)s * step;
+  } else {
+    in = 0.5f * (n1 + n2) * (float)(P - 1);
+  }
+  Tap t;
+  t.valid = (in >= 0.0f && in <= (float)(P - 1)) ? 1 : 0;
+  const float f = floorf(in);
+  const int i0 = (int)f, i1 = (int)ceilf(in);
+  t.w = in - f;
+  // padded index p holds un-padded pixel clamp(p - pad, 0, dim-1)  (SYMMETRIC pad of 1)
+  t.i0 = min(max(i0 - pad, 0), dim - 1);
+  t.i1 = min(max(i1 - pad, 0), dim - 1);
+  return t;
+}
+
+template <typename T>
+struct Vec;  // 16-byte channel group
+template <>
+struct Vec<float> {
+  static constexpr int kElems = 4;
+  float v[4];
+  __device__ __forceinline__ static Vec load(const float* p) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(p));
+    Vec o; o.v[0] = r.x; o.v[1] = r.y; o.v[2] = r.z; o.v[3] = r.w;
+    return o;
+  }
+};
+template <>
+struct Vec<__nv_bfloat16> {
+  static constexpr int kElems = 8;
+  float v[8];
+  __device__ __forceinline__ static Vec load(const __nv_bfloat16* p) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    Vec o;
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      o.v[2 * i] = __uint_as_float(w[i] << 16);
+      o.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+    return o;
+  }
+};
+
+template <int E>
+__device__ __forceinline__ void store_out(float* p, const float (&v)[E]) {
+#pragma unroll
+  for (int i = 0; i < E; i += 4) __stcs(reinterpret_cast<float4*>(p + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+}
+template <int E>
+__device__ __forceinline__ void store_out(__nv_bfloat16* p, const float (&v)[E]) {
+  static_assert(E == 8, "bf16 output groups are 8 wide");
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  __stcs(reinterpret_cast<uint4*>(p), make_uint4(w[0], w[1], w[2], w[3]));
+}
+
+// TIn: feature element type; TOut: output element type; GROUPS: 16-byte groups
+// each lane owns per bin (0 => runtime loop for any channel count).
+template <typename TIn, typename TOut, int GROUPS>
+__global__ void __launch_bounds__(kThreads) roi_align_kernel(const RoiAlignArgs a) {
+  constexpr int E = Vec<TIn>::kElems;
+  __shared__ Tap ty[kMaxSamples];
+  __shared__ Tap tx[kMaxSamples];
+  __shared__ int s_level;
+  __shared__ int s_img;
+
+  const long long roi = blockIdx.x;
+  const int s1 = a.sr > 0 ? a.sr : 1;
+  const int ch = a.oh * s1, cw = a.ow * s1;
+  const int tid = threadIdx.x;
+
+  // ---- prologue: every participating thread derives the ROI frame redundantly
+  if (tid < ch + cw || tid == kThreads - 1) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(a.boxes) + roi);
+    int lvl = 0;
+    if (a.L > 1) lvl = level_of(b.x, b.y, b.z, b.w, a.min_level, a.max_level, a.canon_size, a.canon_level);
+    const Level L = a.lv[lvl];
+    const float padf = a.pad ? 1.0f : 0.0f;
+    if (tid < ch) {
+      const float lo = b.x * L.scale + padf, hi = b.z * L.scale + padf;
+      ty[tid] = make_tap(lo, hi, tid, ch, L.H + 2 * a.pad, a.pad, L.H, a.aligned);
+    } else if (tid < ch + cw) {
+      const float lo = b.y * L.scale + padf, hi = b.w * L.scale + padf;
+      tx[tid - ch] = make_tap(lo, hi, tid - ch, cw, L.W + 2 * a.pad, a.pad, L.W, a.aligned);
+    }
+    if (tid == kThreads - 1) {
+      long long img = a.bidx64 ? reinterpret_cast<const long long*>(a.bidx)[roi * a.bidx_stride]
+                               : (long long)reinterpret_cast<const int*>(a.bidx)[roi * a.bidx_stride];
+      s_level = lvl;
+      s_img = (img >= 0 && img < a.N) ? (int)img : -1;
+      if (a.level_counts) atomicAdd(a.level_counts + lvl, 1);
+      if (a.level_out) a.level_out[roi] = lvl;
+    }
+  }
+  __syncthreads();
+
+  const int lvl = s_level;
+  const int img = s_img;
+  const Level L = a.lv[lvl];
+  const int C = a.C;
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kThreads / 32;
+  const TIn* base = reinterpret_cast<const TIn*>(L.ptr) + (size_t)(img < 0 ? 0 : img) * L.H * L.W * C;
+  TOut* obase = reinterpret_cast<TOut*>(a.out) + (size_t)roi * a.oh * a.ow * C;
+  const float cnt = (float)(s1 * s1);
+  const int groups_total = C / E;  // 16-byte groups per pixel
+
+  for (int bin = warp; bin < a.oh * a.ow; bin += kWarps) {
+    const int oy = bin / a.ow, ox = bin - oy * a.ow;
+    TOut* o = obase + (size_t)bin * C;
+    auto do_group = [&](int g) {
+      const int c = g * E;
+      float acc[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[e] = 0.0f;
+      for (int dy = 0; dy < s1; ++dy) {
+        const Tap y = ty[oy * s1 + dy];
+        for (int dx = 0; dx < s1; ++dx) {
+          const Tap x = tx[ox * s1 + dx];
+          float val[E];
+          if (y.valid && x.valid && img >= 0) {
+            const TIn* r0 = base + (size_t)y.i0 * L.W * C + c;
+            const TIn* r1 = base + (size_t)y.i1 * L.W * C + c;
+            const Vec<TIn> tl = Vec<TIn>::load(r0 + (size_t)x.i0 * C);
+            const Vec<TIn> tr = Vec<TIn>::load(r0 + (size_t)x.i1 * C);
+            const Vec<TIn> bl = Vec<TIn>::load(r1 + (size_t)x.i0 * C);
+            const Vec<TIn> br = Vec<TIn>::load(r1 + (size_t)x.i1 * C);
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+              float t = tr.v[e] - tl.v[e]; t = t * x.w; t = tl.v[e] + t;
+              float bb = br.v[e] - bl.v[e]; bb = bb * x.w; bb = bl.v[e] + bb;
+              float r = bb - t; r = r * y.w; r = t + r;
+              val[e] = r;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) val[e] = 0.0f;
+          }
+          if (s1 == 1) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[e] = val[e];
+          } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[e] = acc[e] + val[e];
+          }
+        }
+      }
+      if (s1 > 1) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[e] = acc[e] / cnt;
+      }
+      store_out<E>(o + c, acc);
+    };
+    if (GROUPS > 0) {
+#pragma unroll
+      for (int j = 0; j < GROUPS; ++j) do_group(lane + 32 * j);
+    } else {
+      for (int g = lane; g < groups_total; g += 32) do_group(g);
+    }
+  }
+}
+
+template <typename TIn, typename TOut>
+int launch(const RoiAlignArgs& a, cudaStream_t st) {
+  constexpr int E = Vec<TIn>::kElems;
+  const dim3 grid((unsigned)a.M), block(kThreads);
+  const int g = a.C / E;
+  if (g == 32) roi_align_kernel<TIn, TOut, 1><<<grid, block, 0, st>>>(a);
+  else if (g == 64) roi_align_kernel<TIn, TOut, 2><<<grid, block, 0, st>>>(a);
+  else roi_align_kernel<TIn, TOut, 0><<<grid, block, 0, st>>>(a);
+  D2B_LAUNCH_CHECK();
+  return D2B_OK;
+}
+
+}  // namespace
+}  // namespace d2b
+
+using namespace d2b;
+
+extern "C" size_t d2b_roi_align_multilevel_workspace_bytes(const d2b_roi_align_params*) { return 0; }
+
+extern "C" int d2b_roi_align_multilevel(const d2b_roi_align_params* p, void* /*workspace*/,
+                                        size_t /*workspace_bytes*/, d2b_stream_t stream) {
+  D2B_REQUIRE(p != nullptr, "params is NULL");
+  // poolers.py:148-150 asserts len(x) == len(scales); unknown pooler types raise ValueError (:118)
+  D2B_REQUIRE(p->num_levels >= 1 && p->num_levels <= D2B_MAX_LEVELS, "num_levels=%d out of [1,%d]",
+              p->num_levels, D2B_MAX_LEVELS);
+  D2B_REQUIRE(p->num_rois >= 0 && p->num_rois < (1ll << 31), "num_rois=%lld out of range", (long long)p->num_rois);
+  D2B_REQUIRE(p->output_h > 0 && p->output_w > 0, "output size must be positive");
+  D2B_REQUIRE(p->sampling_ratio >= 0, "sampling_ratio must be >= 0");
+  const int s1 = p->sampling_ratio > 0 ? p->sampling_ratio : 1;
+  D2B_REQUIRE(p->output_h * s1 <= kMaxSamples && p->output_w * s1 <= kMaxSamples &&
+                  (p->output_h + p->output_w) * s1 < kThreads,
+              "output_size*sampling_ratio too large (max %d per axis)", kMaxSamples);
+  D2B_REQUIRE(p->feature_dtype == D2B_DTYPE_F32 || p->feature_dtype == D2B_DTYPE_BF16, "bad feature_dtype");
+  D2B_REQUIRE(p->out_dtype == D2B_DTYPE_F32 || (p->out_dtype == D2B_DTYPE_BF16 && p->feature_dtype == D2B_DTYPE_BF16),
+              "bad out_dtype");
+  const int E = p->feature_dtype == D2B_DTYPE_F32 ? 4 : 8;
+  D2B_REQUIRE(p->channels > 0 && p->channels % E == 0, "channels=%d must be a multiple of %d", p->channels, E);
+  D2B_REQUIRE(p->num_images > 0, "num_images must be positive");
+  if (p->num_rois == 0) return D2B_OK;
+  D2B_REQUIRE(p->boxes && p->batch_idx && p->out, "boxes/batch_idx/out must be non-NULL");
+
+  RoiAlignArgs a;
+  for (int l = 0; l < p->num_levels; ++l) {
+    D2B_REQUIRE(p->features[l] != nullptr && p->height[l] > 0 && p->width[l] > 0, "level %d: bad feature map", l);
+    a.lv[l].ptr = p->features[l];
+    a.lv[l].H = p->height[l];
+    a.lv[l].W = p->width[l];
+    a.lv[l].scale = p->scale[l];
+  }
+  for (int l = p->num_levels; l < D2B_MAX_LEVELS; ++l) a.lv[l] = a.lv[0];
+  a.L = p->num_levels; a.N = p->num_images; a.C = p->channels;
+  a.boxes = p->boxes; a.bidx = p->batch_idx; a.bidx64 = p->batch_idx_is_int64;
+  a.bidx_stride = p->batch_idx_stride > 0 ? p->batch_idx_stride : 1;
+  a.M = p->num_rois;
+  a.oh = p->output_h; a.ow = p->output_w; a.sr = p->sampling_ratio; a.aligned = p->aligned ? 1 : 0;
+  a.pad = p->pad_border ? 1 : 0;
+  a.min_level = p->min_level; a.max_level = p->min_level + p->num_levels - 1;
+  a.canon_size = (float)p->canonical_box_size; a.canon_level = (float)p->canonical_level;
+  a.out = p->out; a.level_counts = p->level_counts; a.level_out = p->level_assignments;
+  if (p->num_levels > 1) {
+    D2B_REQUIRE(p->min_level > 0 && p->canonical_box_size > 0, "min_level and canonical_box_size must be positive");
+  }
+
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->level_counts) D2B_CUDA(cudaMemsetAsync(p->level_counts, 0, sizeof(int32_t) * p->num_levels, st));
+  if (p->feature_dtype == D2B_DTYPE_F32) return launch<float, float>(a, st);
+  if (p->out_dtype == D2B_DTYPE_F32) return launch<__nv_bfloat16, float>(a, st);
+  return launch<__nv_bfloat16, __nv_bfloat16>(a, st);
+}

@@ -1,0 +1,282 @@
+/*
+ * d2b200.h -- C-ABI of libd2b200.so: B200 (sm_100a) kernels for the detection
+ * post-backbone hot path of SimeonZhang/detectron2_tensorflow.
+ *
+ * The reference has no FFI boundary of its own (it is pure Python over stock
+ * TensorFlow ops).  Each entry point below replaces the TF-op chain behind one
+ * reference Python operator; the cited file:line is that operator.  A TF
+ * custom-op shim (csrc/tf_ops) or the ctypes host layer
+ * (detectron2_tensorflow_b200/_native.py) binds exactly these symbols.
+ *
+ * Conventions:
+ *  - all pointers are DEVICE pointers unless marked "host"; the caller owns all
+ *    memory (inputs, outputs, workspace); the library never allocates, frees or
+ *    keeps a pointer after the call returns; no global mutable state.
+ *  - every op has  size_t d2b_<op>_workspace_bytes(const params*)  and
+ *    int d2b_<op>(const params*, void* workspace, size_t workspace_bytes, d2b_stream_t).
+ *    All work is enqueued on the caller's stream; nothing synchronises the host.
+ *  - outputs are fixed-size and zero-padded like the reference's
+ *    pad_or_clip_tensor (lib/utils/shape_utils.py:80-99) with explicit counts.
+ *  - return 0 on success, a negative D2B_E* code otherwise; never throws/exits.
+ *  - boxes are [ymin, xmin, ymax, xmax] fp32 absolute pixels
+ *    (lib/structures/box_list.py:46-49); features are NHWC
+ *    (lib/layers/roi_align.py:48); deltas are (dy,dx,dh,dw)
+ *    (lib/modeling/box_regression.py:101-106); image shapes are (h, w) int32.
+ */
+#ifndef D2B200_H_
+#define D2B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define D2B_API __attribute__((visibility("default")))
+#else
+#define D2B_API
+#endif
+
+typedef void* d2b_stream_t; /* a cudaStream_t */
+
+enum {
+  D2B_OK = 0,
+  D2B_EINVAL = -1,     /* shape / attribute violation (reference: ValueError / assert) */
+  D2B_EWORKSPACE = -2, /* workspace NULL or smaller than *_workspace_bytes() */
+  D2B_ECUDA = -3,      /* a CUDA runtime call or launch failed */
+  D2B_EUNSUPPORTED = -4
+};
+
+#define D2B_MAX_LEVELS 8
+#define D2B_DTYPE_F32 0
+#define D2B_DTYPE_BF16 1
+
+D2B_API int d2b_version(void);
+D2B_API const char* d2b_status_string(int status);
+/* thread-local detail of the last non-zero status returned on this thread */
+D2B_API const char* d2b_last_error(void);
+
+/* ------------------------------------------------------------------------
+ * Multi-level ROIAlign == ROIPooler.call          lib/modeling/poolers.py:134-180
+ *   level assignment                               lib/modeling/poolers.py:11-49
+ *   ROIAlign.call                                  lib/layers/roi_align.py:45-66
+ *   crop_and_resize (aligned / pad_border)         lib/layers/functional.py:100-166
+ * One launch: level computed in-kernel, every ROI written to its final row
+ * (no per-level gather, no SYMMETRIC pad copy, no inverse-permutation pass).
+ * With num_levels == 1 it is ROIAlign.call / crop_and_resize on one map.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const void* features[D2B_MAX_LEVELS]; /* level l: [num_images, height[l], width[l], channels] */
+  int32_t height[D2B_MAX_LEVELS];
+  int32_t width[D2B_MAX_LEVELS];
+  float scale[D2B_MAX_LEVELS]; /* spatial_scale of level l (1/stride) */
+  int32_t num_levels;          /* 1..D2B_MAX_LEVELS */
+  int32_t num_images;
+  int32_t channels;
+  int32_t feature_dtype; /* D2B_DTYPE_F32 | D2B_DTYPE_BF16 */
+  const float* boxes;    /* [num_rois, 4] */
+  const void* batch_idx; /* image of each ROI; element i at batch_idx[i*batch_idx_stride] */
+  int32_t batch_idx_is_int64; /* 1: int64 (SparseBoxList.indices[:,0]); 0: int32 (box_ind) */
+  int64_t batch_idx_stride;   /* in elements (2 when pointing at SparseBoxList.indices) */
+  int64_t num_rois;
+  int32_t output_h, output_w;
+  int32_t sampling_ratio;     /* 0 => one sample per bin (reference default) */
+  int32_t aligned;            /* 1: "ROIAlignV2"; 0: "ROIAlign" */
+  int32_t pad_border;         /* functional.crop_and_resize pad_border (ROIAlign: always 1) */
+  int32_t min_level;          /* -log2(scale[0]); used only when num_levels > 1 */
+  int32_t canonical_box_size; /* 224 */
+  int32_t canonical_level;    /* 4 */
+  void* out;                  /* [num_rois, output_h, output_w, channels] */
+  int32_t out_dtype;          /* D2B_DTYPE_F32 (or BF16 when feature_dtype is BF16) */
+  int32_t* level_counts;      /* optional [num_levels]: 'roi_align/num_roi_level_k' (poolers.py:173) */
+  int64_t* level_assignments; /* optional [num_rois]: assign_boxes_to_levels output */
+} d2b_roi_align_params;
+
+D2B_API size_t d2b_roi_align_multilevel_workspace_bytes(const d2b_roi_align_params* p);
+D2B_API int d2b_roi_align_multilevel(const d2b_roi_align_params* p, void* workspace,
+                                     size_t workspace_bytes, d2b_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Box2BoxTransform.apply_deltas               lib/modeling/box_regression.py:76-123
+ * deltas [n, k*4], boxes [n, 4] -> out [n, k*4]
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* deltas;
+  const float* boxes;
+  int64_t n;
+  int32_t k;
+  float weights[4]; /* (wy, wx, wh, ww) */
+  float scale_clamp;
+  float* out;
+} d2b_apply_deltas_params;
+D2B_API size_t d2b_apply_deltas_workspace_bytes(const d2b_apply_deltas_params* p);
+D2B_API int d2b_apply_deltas(const d2b_apply_deltas_params* p, void* workspace,
+                             size_t workspace_bytes, d2b_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Segmented top-k == tf.nn.top_k per (image, level) row
+ *   lib/modeling/proposal_generator/rpn_outputs.py:70,106
+ *   lib/modeling/single_stage_heads/retinanet.py:321-326 (transform = sigmoid)
+ * Rows are described per group (level): group g holds rows_per_group rows of
+ * row_len[g] contiguous fp32 each.  Row r = image * num_groups + g.
+ * Output per row: the k_r = min(k, row_len[g]) largest in (value desc, index asc)
+ * order, zero/-1 padded to k.  NaN ranks lowest.
+ * ---------------------------------------------------------------------- */
+#define D2B_TOPK_IDENTITY 0
+#define D2B_TOPK_SIGMOID 1
+typedef struct {
+  const float* scores[D2B_MAX_LEVELS]; /* group g: [rows_per_group, row_len[g]] */
+  int64_t row_len[D2B_MAX_LEVELS];
+  int32_t k_limit[D2B_MAX_LEVELS];     /* per-group cap on k (0 => k); RetinaNet: #anchors (retinanet.py:325) */
+  int32_t num_groups;
+  int32_t rows_per_group;
+  int32_t k;
+  int32_t transform;   /* D2B_TOPK_* applied to every score before ranking */
+  float* out_values;   /* [rows, k]  transformed values */
+  int32_t* out_indices; /* [rows, k]  index within the row, -1 padding */
+  int32_t* out_counts;  /* [rows] */
+} d2b_segmented_topk_params;
+D2B_API size_t d2b_segmented_topk_workspace_bytes(const d2b_segmented_topk_params* p);
+D2B_API int d2b_segmented_topk(const d2b_segmented_topk_params* p, void* workspace,
+                               size_t workspace_bytes, d2b_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Batched hard NMS == tf.image.non_max_suppression per segment
+ *   lib/layers/nms.py:6-26 (batch_nms), rpn_outputs.py:90, fast_rcnn.py:145,
+ *   retinanet.py:353.  IoU in the TF CPU kernel's op order (division form,
+ *   strict '>'), candidates ordered (score desc, index asc), scores of -inf/NaN
+ *   never selected, stop at max_output_size.
+ * boxes [S, n, 4], scores [S, n], optional counts [S] (valid prefix per segment).
+ * keep [S, max_output_size] (indices into the segment, selection order, -1 pad).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* boxes;
+  const float* scores;
+  const int32_t* counts; /* optional */
+  int32_t num_segments;
+  int32_t n;
+  int32_t max_output_size;
+  float iou_threshold;
+  int32_t* keep;
+  int32_t* num_keep; /* [S] */
+} d2b_batched_nms_params;
+D2B_API size_t d2b_batched_nms_workspace_bytes(const d2b_batched_nms_params* p);
+D2B_API int d2b_batched_nms(const d2b_batched_nms_params* p, void* workspace,
+                            size_t workspace_bytes, d2b_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * RPN proposal stage == RPNOutputs.predict_proposals + find_top_rpn_proposals
+ *   lib/modeling/proposal_generator/rpn_outputs.py:403-426, 29-132
+ * Either `proposals` (already decoded, the reference signature) or
+ * `deltas`+`anchors` (decode fused; only the top-k winners are decoded, which
+ * is value-identical because decoding is elementwise).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* logits[D2B_MAX_LEVELS];    /* [N, hwa[l]] */
+  const float* proposals[D2B_MAX_LEVELS]; /* [N, hwa[l], 4] or NULL */
+  const float* deltas[D2B_MAX_LEVELS];    /* [N, hwa[l], 4] or NULL */
+  const float* anchors[D2B_MAX_LEVELS];   /* [hwa[l], 4]    or NULL */
+  int64_t hwa[D2B_MAX_LEVELS];
+  int32_t num_levels;
+  int32_t num_images;
+  const int32_t* image_shapes; /* [N, 2] (h, w) */
+  float nms_thresh;
+  int32_t pre_nms_topk;
+  int32_t post_nms_topk;
+  float min_box_side_len;
+  float weights[4]; /* RPN.BBOX_REG_WEIGHTS */
+  float scale_clamp;
+  float* out_boxes;      /* [N, post, 4] */
+  float* out_logits;     /* [N, post] */
+  uint8_t* out_valid;    /* [N, post] */
+  int32_t* out_num_valid; /* optional [N] */
+  int64_t* out_nms_boxes_in; /* optional [1]: total boxes that entered NMS (metric bookkeeping) */
+} d2b_rpn_proposals_params;
+D2B_API size_t d2b_rpn_proposals_workspace_bytes(const d2b_rpn_proposals_params* p);
+D2B_API int d2b_rpn_proposals(const d2b_rpn_proposals_params* p, void* workspace,
+                              size_t workspace_bytes, d2b_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * fast_rcnn_inference                      lib/modeling/roi_heads/fast_rcnn.py:28-187
+ * boxes [M, Kb*4] (Kb = K or 1), scores [M, K+1] (last column = background),
+ * indices [M, 2] int64 (image, slot) with dense shape [N, Rmax].
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* boxes;
+  const float* scores;
+  const int64_t* indices;
+  int64_t num_preds; /* M */
+  int32_t num_images, rmax;
+  int32_t num_bbox_reg_classes; /* Kb */
+  int32_t num_classes;          /* K */
+  const int32_t* image_shapes;  /* [N, 2] */
+  float score_thresh, nms_thresh;
+  int32_t topk_per_image;
+  int32_t nms_cls_agnostic;
+  float* out_boxes;       /* [N, topk, 4] */
+  float* out_scores;      /* [N, topk] */
+  int64_t* out_classes;   /* [N, topk] */
+  uint8_t* out_valid;     /* [N, topk] */
+  int32_t* out_roi_index; /* optional [N, topk]: slot of the source ROI, -1 pad (kept_indices) */
+  int32_t* out_num;       /* optional [N] */
+  int64_t* out_nms_boxes_in; /* optional [1] */
+} d2b_fast_rcnn_params;
+D2B_API size_t d2b_fast_rcnn_postprocess_workspace_bytes(const d2b_fast_rcnn_params* p);
+D2B_API int d2b_fast_rcnn_postprocess(const d2b_fast_rcnn_params* p, void* workspace,
+                                      size_t workspace_bytes, d2b_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * RetinaNetHead.inference        lib/modeling/single_stage_heads/retinanet.py:285-387
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* box_cls[D2B_MAX_LEVELS];   /* [N, hwa[l], K] logits */
+  const float* box_delta[D2B_MAX_LEVELS]; /* [N, hwa[l], 4] */
+  const float* anchors[D2B_MAX_LEVELS];   /* [hwa[l], 4] */
+  int64_t hwa[D2B_MAX_LEVELS];
+  int32_t num_levels, num_images, num_classes;
+  int32_t topk_candidates;
+  float score_thresh, nms_thresh;
+  int32_t max_detections;
+  float weights[4];
+  float scale_clamp;
+  float* out_boxes;     /* [N, max_det, 4] */
+  float* out_scores;    /* [N, max_det] */
+  int32_t* out_classes; /* [N, max_det] */
+  uint8_t* out_valid;   /* [N, max_det] */
+  int32_t* out_num;     /* optional [N] */
+  int64_t* out_nms_boxes_in; /* optional [1] */
+} d2b_retinanet_params;
+D2B_API size_t d2b_retinanet_postprocess_workspace_bytes(const d2b_retinanet_params* p);
+D2B_API int d2b_retinanet_postprocess(const d2b_retinanet_params* p, void* workspace,
+                                      size_t workspace_bytes, d2b_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * matrix_nms (SOLOv2)                                   lib/layers/nms.py:29-83
+ * masks [B, n, hw] fp32 in {0,1} (B independent images per call; the reference
+ * is called once per image inside tf.map_fn, solo_v2.py:587), classes [B, n]
+ * int64, scores [B, n] sorted descending, sum_masks [B, n] or NULL.
+ * ---------------------------------------------------------------------- */
+#define D2B_MNMS_GAUSSIAN 0
+#define D2B_MNMS_LINEAR 1
+typedef struct {
+  const float* masks;
+  const int64_t* classes;
+  const float* scores;
+  const float* sum_masks; /* optional */
+  const int32_t* counts;  /* optional [B]: valid prefix length per image (<= n) */
+  int32_t batch, n;
+  int64_t hw;
+  int32_t kernel;
+  float sigma;
+  float* out; /* [B, n] */
+} d2b_matrix_nms_params;
+D2B_API size_t d2b_matrix_nms_workspace_bytes(const d2b_matrix_nms_params* p);
+D2B_API int d2b_matrix_nms(const d2b_matrix_nms_params* p, void* workspace, size_t workspace_bytes,
+                           d2b_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D2B200_H_ */

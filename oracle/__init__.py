@@ -1,0 +1,280 @@
+"""CPU oracle for the post-backbone hot path -- TEST INFRASTRUCTURE ONLY.
+
+numpy-in / numpy-out ctypes bindings over ``oracle/liboracle.so`` (built from
+``oracle/d2b_oracle.c`` by ``oracle/Makefile``).  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs may import this package; the product package never does.
+
+Parity status: *unpinned at the TF boundary* (the reference ships no tests and
+TensorFlow cannot be installed here); pinned against the reference's own numpy
+NMS and torchvision/torch -- see ``tests/golden/make_golden.py``.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+
+SCALE_CLAMP = float(np.log(1000.0 / 16))  # lib/modeling/box_regression.py:10
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "d2b_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "liboracle.so"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_expf.restype = C.c_float
+        _lib.orc_expf.argtypes = [C.c_float]
+        _lib.orc_logf.restype = C.c_float
+        _lib.orc_logf.argtypes = [C.c_float]
+        _lib.orc_sigmoidf.restype = C.c_float
+        _lib.orc_sigmoidf.argtypes = [C.c_float]
+        _lib.orc_nms.restype = C.c_int32
+        _lib.orc_get_max_threads.restype = C.c_int
+    return _lib
+
+
+def set_num_threads(n):
+    lib().orc_set_num_threads(C.c_int(int(n)))
+
+
+def max_threads():
+    return int(lib().orc_get_max_threads())
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _ptr_array(arrs):
+    return (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+def expf(x):
+    x = _f32(x)
+    return np.array([lib().orc_expf(float(v)) for v in x.ravel()], np.float32).reshape(x.shape)
+
+
+def logf(x):
+    x = _f32(x)
+    return np.array([lib().orc_logf(float(v)) for v in x.ravel()], np.float32).reshape(x.shape)
+
+
+def sigmoidf(x):
+    x = _f32(x)
+    return np.array([lib().orc_sigmoidf(float(v)) for v in x.ravel()], np.float32).reshape(x.shape)
+
+
+def assign_boxes_to_levels(boxes, min_level, max_level, canonical_box_size=224, canonical_level=4):
+    boxes = _f32(boxes).reshape(-1, 4)
+    out = np.empty(boxes.shape[0], np.int64)
+    lib().orc_assign_boxes_to_levels(_p(boxes), C.c_int64(boxes.shape[0]), int(min_level), int(max_level),
+                                     int(canonical_box_size), int(canonical_level), _p(out))
+    return out
+
+
+def crop_and_resize(image, boxes, box_ind, crop_size, aligned=True, pad_border=True):
+    image = _f32(image)
+    N, H, W, Cc = image.shape
+    boxes = _f32(boxes).reshape(-1, 4)
+    box_ind = np.ascontiguousarray(box_ind, np.int32)
+    M = boxes.shape[0]
+    ch, cw = int(crop_size[0]), int(crop_size[1])
+    out = np.zeros((M, ch, cw, Cc), np.float32)
+    rc = lib().orc_crop_and_resize(_p(image), N, H, W, Cc, _p(boxes), _p(box_ind), C.c_int64(M), ch, cw,
+                                   int(bool(aligned)), int(bool(pad_border)), _p(out))
+    assert rc == 0
+    return out
+
+
+def roi_align(image, boxes, box_ind, output_size, spatial_scale, sampling_ratio, aligned=True):
+    image = _f32(image)
+    N, H, W, Cc = image.shape
+    boxes = _f32(boxes).reshape(-1, 4)
+    box_ind = np.ascontiguousarray(box_ind, np.int32)
+    M = boxes.shape[0]
+    oh, ow = int(output_size[0]), int(output_size[1])
+    out = np.zeros((M, oh, ow, Cc), np.float32)
+    rc = lib().orc_roi_align(_p(image), N, H, W, Cc, _p(boxes), _p(box_ind), C.c_int64(M), oh, ow,
+                             C.c_float(spatial_scale), int(sampling_ratio), int(bool(aligned)), _p(out))
+    assert rc == 0
+    return out
+
+
+def roi_pooler(feats, scales, boxes, batch_idx, output_size, sampling_ratio, aligned=True,
+               canonical_box_size=224, canonical_level=4):
+    feats = [_f32(f) for f in feats]
+    L = len(feats)
+    N, _, _, Cc = feats[0].shape
+    Hs = np.array([f.shape[1] for f in feats], np.int32)
+    Ws = np.array([f.shape[2] for f in feats], np.int32)
+    sc = _f32(scales)
+    boxes = _f32(boxes).reshape(-1, 4)
+    batch_idx = np.ascontiguousarray(batch_idx, np.int64)
+    M = boxes.shape[0]
+    oh, ow = int(output_size[0]), int(output_size[1])
+    out = np.zeros((M, oh, ow, Cc), np.float32)
+    counts = np.zeros(L, np.int32)
+    rc = lib().orc_roi_pooler(_ptr_array(feats), _p(Hs), _p(Ws), L, N, Cc, _p(sc), _p(boxes), _p(batch_idx),
+                              C.c_int64(M), oh, ow, int(sampling_ratio), int(bool(aligned)),
+                              int(canonical_box_size), int(canonical_level), _p(out), _p(counts))
+    assert rc == 0
+    return out, counts
+
+
+def apply_deltas(deltas, boxes, weights, scale_clamp=SCALE_CLAMP):
+    boxes = _f32(boxes).reshape(-1, 4)
+    n = boxes.shape[0]
+    deltas = _f32(deltas).reshape(n, -1)
+    k = deltas.shape[1] // 4
+    w = _f32(weights)
+    out = np.empty_like(deltas)
+    lib().orc_apply_deltas(_p(deltas), _p(boxes), C.c_int64(n), k, _p(w), C.c_float(scale_clamp), _p(out))
+    return out
+
+
+def top_k(x, k):
+    x = _f32(x).ravel()
+    k = min(int(k), x.size)
+    vals = np.empty(k, np.float32)
+    idx = np.empty(k, np.int32)
+    lib().orc_top_k(_p(x), C.c_int64(x.size), C.c_int64(k), _p(vals), _p(idx))
+    return vals, idx
+
+
+def box_iou(a, b):
+    a = _f32(a)
+    b = _f32(b)
+    f = lib().orc_box_iou
+    f.restype = C.c_float
+    return float(f(_p(a), _p(b)))
+
+
+def nms(boxes, scores, max_output_size, iou_threshold):
+    boxes = _f32(boxes).reshape(-1, 4)
+    scores = _f32(scores).ravel()
+    keep = np.empty(max(int(max_output_size), 1), np.int32)
+    c = lib().orc_nms(_p(boxes), _p(scores), C.c_int64(boxes.shape[0]), C.c_int32(int(max_output_size)),
+                      C.c_float(iou_threshold), _p(keep))
+    return keep[:c].copy()
+
+
+def batch_nms(boxes, scores, max_output_size, iou_threshold=0.5):
+    boxes = _f32(boxes)
+    scores = _f32(scores)
+    B, n = scores.shape
+    keep = np.empty((B, max_output_size), np.int32)
+    num = np.empty(B, np.int32)
+    lib().orc_batch_nms(_p(boxes), _p(scores), B, C.c_int64(n), C.c_int32(max_output_size),
+                        C.c_float(iou_threshold), _p(keep), _p(num))
+    return keep, num
+
+
+def rpn_predict_proposals(deltas, anchors, weights=(1.0, 1.0, 1.0, 1.0), scale_clamp=SCALE_CLAMP):
+    """deltas [N, HWA, 4], anchors [HWA, 4] -> [N, HWA, 4] (rpn_outputs.py:403-426)."""
+    deltas = _f32(deltas)
+    anchors = _f32(anchors)
+    N, hwa, _ = deltas.shape
+    out = np.empty_like(deltas)
+    w = _f32(weights)
+    lib().orc_rpn_predict_proposals(_p(deltas), _p(anchors), N, C.c_int64(hwa), _p(w), C.c_float(scale_clamp),
+                                    _p(out))
+    return out
+
+
+def find_top_rpn_proposals(proposals, logits, image_shapes, nms_thresh, pre_nms_topk, post_nms_topk,
+                           min_box_side_len):
+    proposals = [_f32(p) for p in proposals]
+    logits = [_f32(x) for x in logits]
+    L = len(proposals)
+    N = logits[0].shape[0]
+    hwa = np.array([x.shape[1] for x in logits], np.int64)
+    shapes = np.ascontiguousarray(image_shapes, np.int32).reshape(N, 2)
+    ob = np.zeros((N, post_nms_topk, 4), np.float32)
+    ol = np.zeros((N, post_nms_topk), np.float32)
+    ov = np.zeros((N, post_nms_topk), np.uint8)
+    on = np.zeros(N, np.int32)
+    lib().orc_find_top_rpn_proposals(_ptr_array(proposals), _ptr_array(logits), _p(hwa), L, N, _p(shapes),
+                                     C.c_float(nms_thresh), int(pre_nms_topk), int(post_nms_topk),
+                                     C.c_float(min_box_side_len), _p(ob), _p(ol), _p(ov), _p(on))
+    return ob, ol, ov.astype(bool), on
+
+
+def fast_rcnn_inference(boxes, scores, indices, dense_shape, image_shapes, score_thresh, nms_thresh,
+                        topk_per_image, nms_cls_agnostic=False):
+    scores = _f32(scores)
+    M, K1 = scores.shape
+    K = K1 - 1
+    boxes = _f32(boxes).reshape(M, -1)
+    Kb = boxes.shape[1] // 4
+    indices = np.ascontiguousarray(indices, np.int64).reshape(M, 2)
+    N, Rmax = int(dense_shape[0]), int(dense_shape[1])
+    shapes = np.ascontiguousarray(image_shapes, np.int32).reshape(N, 2)
+    T = int(topk_per_image)
+    ob = np.zeros((N, T, 4), np.float32)
+    os_ = np.zeros((N, T), np.float32)
+    oc = np.zeros((N, T), np.int64)
+    ov = np.zeros((N, T), np.uint8)
+    orr = np.zeros((N, T), np.int32)
+    on = np.zeros(N, np.int32)
+    lib().orc_fast_rcnn_inference(_p(boxes), _p(scores), _p(indices), C.c_int64(M), N, Rmax, Kb, K, _p(shapes),
+                                  C.c_float(score_thresh), C.c_float(nms_thresh), T, int(bool(nms_cls_agnostic)),
+                                  _p(ob), _p(os_), _p(oc), _p(ov), _p(orr), _p(on))
+    return ob, os_, oc, ov.astype(bool), orr, on
+
+
+def retinanet_inference(box_cls, box_delta, anchors, num_classes, topk_candidates, score_thresh, nms_thresh,
+                        max_det, weights=(1.0, 1.0, 1.0, 1.0), scale_clamp=SCALE_CLAMP):
+    box_cls = [_f32(x) for x in box_cls]
+    box_delta = [_f32(x) for x in box_delta]
+    anchors = [_f32(x) for x in anchors]
+    L = len(box_cls)
+    N = box_cls[0].shape[0]
+    hwa = np.array([a.shape[0] for a in anchors], np.int64)
+    T = int(max_det)
+    ob = np.zeros((N, T, 4), np.float32)
+    os_ = np.zeros((N, T), np.float32)
+    oc = np.zeros((N, T), np.int32)
+    ov = np.zeros((N, T), np.uint8)
+    on = np.zeros(N, np.int32)
+    w = _f32(weights)
+    lib().orc_retinanet_inference(_ptr_array(box_cls), _ptr_array(box_delta), _ptr_array(anchors), _p(hwa), L, N,
+                                  int(num_classes), int(topk_candidates), C.c_float(score_thresh),
+                                  C.c_float(nms_thresh), T, _p(w), C.c_float(scale_clamp), _p(ob), _p(os_), _p(oc),
+                                  _p(ov), _p(on))
+    return ob, os_, oc, ov.astype(bool), on
+
+
+def matrix_nms(masks, classes, scores, sum_masks=None, kernel="gaussian", sigma=2.0):
+    masks = _f32(masks)
+    n = masks.shape[0]
+    hw = int(np.prod(masks.shape[1:]))
+    classes = np.ascontiguousarray(classes, np.int64)
+    scores = _f32(scores)
+    kid = {"gaussian": 0, "linear": 1}.get(kernel, -1)
+    if kid < 0:
+        raise NotImplementedError(f"NMS kernel {kernel} not implemented yet.")
+    sm = None if sum_masks is None else _f32(sum_masks)
+    out = np.zeros(n, np.float32)
+    rc = lib().orc_matrix_nms(_p(masks), _p(classes), _p(scores), None if sm is None else _p(sm), n,
+                              C.c_int64(hw), kid, C.c_float(sigma), _p(out))
+    assert rc == 0
+    return out
