@@ -116,15 +116,25 @@ def lib():
         L.d2b_status_string.restype = C.c_char_p
         L.d2b_status_string.argtypes = [C.c_int]
         L.d2b_last_error.restype = C.c_char_p
-        for op, st in OPS.items():
-            f = getattr(L, f"d2b_{op}")
-            f.restype = C.c_int
-            f.argtypes = [C.POINTER(st), _vp, C.c_size_t, _vp]
-            w = getattr(L, f"d2b_{op}_workspace_bytes")
-            w.restype = C.c_size_t
-            w.argtypes = [C.POINTER(st)]
         _lib = L
     return _lib
+
+
+_bound = set()
+
+
+def _bind(op):
+    L = lib()
+    if op not in _bound:
+        st = OPS[op]
+        f = getattr(L, f"d2b_{op}")
+        f.restype = C.c_int
+        f.argtypes = [C.POINTER(st), _vp, C.c_size_t, _vp]
+        w = getattr(L, f"d2b_{op}_workspace_bytes")
+        w.restype = C.c_size_t
+        w.argtypes = [C.POINTER(st)]
+        _bound.add(op)
+    return L
 
 
 def ptr(t):
@@ -151,7 +161,7 @@ def _workspace(nbytes, device):
 def call(op, params, device):
     """Run d2b_<op> on torch's current stream of `device`."""
     global launch_count
-    L = lib()
+    L = _bind(op)
     with torch.cuda.device(device):
         nbytes = getattr(L, f"d2b_{op}_workspace_bytes")(C.byref(params))
         ws = _workspace(nbytes, device) if nbytes else None

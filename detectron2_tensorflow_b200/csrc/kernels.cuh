@@ -1,0 +1,41 @@
+// kernels.cuh -- internal (non-ABI) interfaces shared by the pipeline translation units.
+#pragma once
+#include "common.cuh"
+
+namespace d2b {
+
+// ---------------------------------------------------------------- segmented top-k (topk.cu)
+// Row r = image * G + g;  row pointer = scores[g] + image * row_len[g].
+struct TopkDesc {
+  const float* scores[D2B_MAX_LEVELS];
+  long long row_len[D2B_MAX_LEVELS];
+  int k_limit[D2B_MAX_LEVELS];  // 0 => no extra cap
+  int G;
+  int rows_per_group;
+  int k;
+  int transform;  // D2B_TOPK_*
+};
+constexpr int kTopkMaxK = 16384;
+size_t topk_workspace_bytes(const TopkDesc& d);
+// Writes, per row, the k_r winners sorted (value desc, index asc):
+//   out_keys [rows, P] u64 composites (key32<<32 | ~index), zero padded, P = topk_padded_k(k)
+//   optional out_values/out_indices [rows, k] (-1 / 0 padded), out_counts [rows] (always written)
+int topk_run(const TopkDesc& d, unsigned long long* out_keys, float* out_values, int32_t* out_indices,
+             int32_t* out_counts, void* ws, cudaStream_t st);
+int topk_padded_k(int k);
+
+// ---------------------------------------------------------------- segment sort (sort.cu)
+// Sort each of S segments of P (power of two) u64 keys in DESCENDING order in place.
+// seg_len (optional, device [S]): only the first seg_len[s] entries are live; the rest are
+// overwritten with 0 before sorting (0 sorts last).
+int sort_segments_desc(unsigned long long* keys, int S, int P, const int32_t* seg_len, cudaStream_t st);
+
+// ---------------------------------------------------------------- NMS (nms.cu)
+// Boxes of every segment are already in candidate order (score desc, index asc).
+// boxes [S, n, 4]; counts [S] (device, live prefix per segment; NULL => n).
+// keep [S, max_out] positions into the segment (selection order, -1 padded), num_keep [S].
+size_t nms_sorted_workspace_bytes(int S, int n, int max_out);
+int nms_sorted(const float* boxes, const int32_t* counts, int S, int n, int max_out, float thr, int32_t* keep,
+               int32_t* num_keep, void* ws, cudaStream_t st);
+
+}  // namespace d2b

@@ -1,0 +1,328 @@
+// topk.cu -- segmented radix-select top-k over (image, level) rows.
+//
+// Replaces tf.nn.top_k at rpn_outputs.py:70,106 and retinanet.py:326 (with the
+// sigmoid of retinanet.py:322 fused into the key load).  Tie rule of TF's TopKV2:
+// among equal values the lower index wins -- realised by ranking 64-bit
+// composites (order-preserving value key << 32 | ~index), which are unique.
+//
+// All rows of all levels are processed by the same launches (no per-image loop):
+//   1. radix-select passes over the composite, most significant digit first
+//      (11/11/10 bits of the value key, then 11/11/10 bits of ~index).  A pass is
+//      one streaming read of the live rows: shared-memory histogram per CTA chunk,
+//      merged into a per-row global histogram; the last CTA of a row to finish
+//      locates the digit that holds the k-th largest element.  A row stops as soon
+//      as its boundary bucket is taken whole, so the index passes only ever run
+//      for rows whose k-th value is tied (CTAs of finished rows exit at once).
+//   2. collect: one more streaming read gathers every element with composite >=
+//      the row's threshold (exactly k_r of them) through a warp-aggregated slot
+//      counter.
+//   3. sort the k_r winners (sort.cu) and emit values / indices.
+// HBM-bound scan (4 B per candidate score per pass); no tensor cores.
+#include "kernels.cuh"
+
+namespace d2b {
+namespace {
+
+typedef unsigned long long u64;
+
+constexpr int kBins = 2048;
+constexpr int kPasses = 6;
+constexpr int kHistThreads = 256;
+constexpr int kChunk = 16384;  // elements per CTA per pass
+
+__constant__ int c_shift[kPasses] = {53, 42, 32, 21, 10, 0};
+__constant__ int c_bits[kPasses] = {11, 11, 10, 11, 11, 10};
+
+struct RowState {
+  u64 prefix;        // digits resolved so far (right-aligned)
+  u64 threshold;     // final: take every composite >= threshold
+  unsigned k_rem;    // winners still to be found inside the current prefix
+  unsigned active;   // 1 while more passes are needed
+  unsigned k_r;      // min(k, len, k_limit)
+  unsigned out_count;  // collect slot counter
+  unsigned done[kPasses];
+};
+
+struct TopkArgs {
+  TopkDesc d;
+  int chunks[D2B_MAX_LEVELS];      // CTAs per row in group g
+  int cta_begin[D2B_MAX_LEVELS + 1];  // first CTA of group g
+  RowState* state;
+  unsigned* hist;  // [rows][kPasses][kBins]
+  int P;           // padded k
+};
+
+__device__ __forceinline__ bool locate(const TopkArgs& a, int cta, int& g, int& img, int& chunk) {
+  g = 0;
+  while (g + 1 < a.d.G && cta >= a.cta_begin[g + 1]) ++g;
+  const int rem = cta - a.cta_begin[g];
+  img = rem / a.chunks[g];
+  chunk = rem - img * a.chunks[g];
+  return img < a.d.rows_per_group;
+}
+
+__device__ __forceinline__ u64 composite(float x, unsigned idx, int transform) {
+  if (transform == D2B_TOPK_SIGMOID) x = d2b_sigmoidf(x);
+  return ((u64)float_to_key(x) << 32) | (u64)(0xffffffffu - idx);
+}
+
+__global__ void topk_init(TopkArgs a, int rows) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int g = r % a.d.G;
+  long long kr = a.d.k;
+  if (a.d.row_len[g] < kr) kr = a.d.row_len[g];
+  if (a.d.k_limit[g] > 0 && a.d.k_limit[g] < kr) kr = a.d.k_limit[g];
+  if (kr < 0) kr = 0;
+  RowState s;
+  s.prefix = 0; s.k_rem = (unsigned)kr; s.k_r = (unsigned)kr; s.out_count = 0;
+  for (int p = 0; p < kPasses; ++p) s.done[p] = 0;
+  if (kr == 0) { s.active = 0; s.threshold = ~0ull; }            // take nothing
+  else if (kr == a.d.row_len[g]) { s.active = 0; s.threshold = 0ull; }  // take the whole row
+  else { s.active = 1; s.threshold = 0ull; }
+  a.state[r] = s;
+}
+
+__global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass) {
+  __shared__ unsigned sh[kBins];
+  __shared__ int s_last;
+  int g, img, chunk;
+  if (!locate(a, blockIdx.x, g, img, chunk)) return;
+  const int row = img * a.d.G + g;
+  RowState* st = a.state + row;
+  if (!st->active) return;  // uniform per CTA
+  const u64 prefix = st->prefix;
+  const int shift = c_shift[pass], bits = c_bits[pass];
+  const unsigned mask = (1u << bits) - 1u;
+  for (int i = threadIdx.x; i < kBins; i += kHistThreads) sh[i] = 0;
+  __syncthreads();
+  const long long len = a.d.row_len[g];
+  const float* x = a.d.scores[g] + (size_t)img * len;
+  const long long beg = (long long)chunk * kChunk;
+  const long long end = beg + kChunk < len ? beg + kChunk : len;
+  const int hi_shift = shift + bits;  // bits above the current digit
+#pragma unroll 4
+  for (long long i = beg + threadIdx.x; i < end; i += kHistThreads) {
+    const u64 c = composite(__ldg(x + i), (unsigned)i, a.d.transform);
+    const bool in = (pass == 0) || ((c >> hi_shift) == prefix);
+    if (in) atomicAdd(&sh[(unsigned)(c >> shift) & mask], 1u);
+  }
+  __syncthreads();
+  unsigned* gh = a.hist + ((size_t)row * kPasses + pass) * kBins;
+  for (int i = threadIdx.x; i < kBins; i += kHistThreads)
+    if (sh[i]) atomicAdd(gh + i, sh[i]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(&st->done[pass], 1u);
+    s_last = (t == (unsigned)a.chunks[g] - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- last CTA of the row: find the digit holding the k_rem-th largest element
+  const unsigned k_rem = st->k_rem;
+  constexpr int kPer = kBins / kHistThreads;  // 8 bins per thread, thread t owns the t-th highest group
+  unsigned loc[kPer];
+  unsigned sum = 0;
+  const int top = kBins - 1 - threadIdx.x * kPer;  // this thread's highest bin
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    loc[j] = __ldcg(gh + (top - j));
+    sum += loc[j];
+  }
+  __shared__ unsigned scan[kHistThreads];
+  scan[threadIdx.x] = sum;
+  __syncthreads();
+  for (int off = 1; off < kHistThreads; off <<= 1) {  // inclusive scan from the top bins down
+    unsigned v = threadIdx.x >= off ? scan[threadIdx.x - off] : 0;
+    __syncthreads();
+    scan[threadIdx.x] += v;
+    __syncthreads();
+  }
+  const unsigned incl = scan[threadIdx.x], excl = incl - sum;
+  if (excl < k_rem && k_rem <= incl) {
+    unsigned above = excl;
+    for (int j = 0; j < kPer; ++j) {
+      if (above + loc[j] >= k_rem) {
+        const unsigned digit = (unsigned)(top - j);
+        const unsigned need = k_rem - above;
+        const u64 np = (prefix << bits) | digit;
+        st->prefix = np;
+        st->k_rem = need;
+        if (loc[j] == need || pass == kPasses - 1) {  // bucket taken whole: row resolved
+          st->threshold = np << shift;
+          st->active = 0;
+        }
+        break;
+      }
+      above += loc[j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kHistThreads) topk_collect(TopkArgs a, u64* out_keys) {
+  int g, img, chunk;
+  if (!locate(a, blockIdx.x, g, img, chunk)) return;
+  const int row = img * a.d.G + g;
+  RowState* st = a.state + row;
+  if (st->k_r == 0) return;
+  const u64 thr = st->threshold;
+  const long long len = a.d.row_len[g];
+  const float* x = a.d.scores[g] + (size_t)img * len;
+  const long long beg = (long long)chunk * kChunk;
+  const long long end = beg + kChunk < len ? beg + kChunk : len;
+  u64* out = out_keys + (size_t)row * a.P;
+  const int lane = threadIdx.x & 31;
+  for (long long i0 = beg + (threadIdx.x & ~31); i0 < end; i0 += kHistThreads) {
+    const long long i = i0 + lane;
+    u64 c = 0;
+    bool take = false;
+    if (i < end) {
+      c = composite(__ldg(x + i), (unsigned)i, a.d.transform);
+      take = c >= thr;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    if (m) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(&st->out_count, (unsigned)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (take) {
+        const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
+        if (slot < (unsigned)a.P) out[slot] = c;
+      }
+    }
+  }
+}
+
+__global__ void topk_emit(TopkArgs a, const u64* keys, float* out_values, int32_t* out_indices,
+                          int32_t* out_counts, int rows) {
+  const int row = blockIdx.y;
+  const unsigned kr = a.state[row].k_r;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && out_counts) out_counts[row] = (int32_t)kr;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.d.k) return;
+  float v = 0.0f;
+  int32_t idx = -1;
+  if ((unsigned)j < kr) {
+    const u64 c = keys[(size_t)row * a.P + j];
+    v = key_to_float((uint32_t)(c >> 32));
+    idx = (int32_t)(0xffffffffu - (uint32_t)c);
+  }
+  if (out_values) out_values[(size_t)row * a.d.k + j] = v;
+  if (out_indices) out_indices[(size_t)row * a.d.k + j] = idx;
+}
+
+__global__ void topk_counts(TopkArgs a, int32_t* seg_len, int rows) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) seg_len[r] = (int32_t)a.state[r].k_r;
+}
+
+int fill_args(const TopkDesc& d, TopkArgs& a) {
+  a.d = d;
+  int cta = 0;
+  for (int g = 0; g < d.G; ++g) {
+    a.chunks[g] = (int)((d.row_len[g] + kChunk - 1) / kChunk);
+    if (a.chunks[g] < 1) a.chunks[g] = 1;
+    a.cta_begin[g] = cta;
+    cta += a.chunks[g] * d.rows_per_group;
+  }
+  for (int g = d.G; g <= D2B_MAX_LEVELS; ++g) a.cta_begin[g] = cta;
+  a.P = topk_padded_k(d.k);
+  return cta;
+}
+
+}  // namespace
+
+int topk_padded_k(int k) {
+  int P = 1;
+  while (P < k) P <<= 1;
+  return P;
+}
+
+size_t topk_workspace_bytes(const TopkDesc& d) {
+  const size_t rows = (size_t)d.G * d.rows_per_group;
+  return ws_slice(rows * sizeof(RowState)) + ws_slice(rows * kPasses * kBins * sizeof(unsigned)) +
+         ws_slice(rows * sizeof(int32_t));
+}
+
+int topk_run(const TopkDesc& d, unsigned long long* out_keys, float* out_values, int32_t* out_indices,
+             int32_t* out_counts, void* ws, cudaStream_t st) {
+  D2B_REQUIRE(d.G >= 1 && d.G <= D2B_MAX_LEVELS, "top-k: num_groups=%d out of range", d.G);
+  D2B_REQUIRE(d.k >= 0 && d.k <= kTopkMaxK, "top-k: k=%d out of [0,%d]", d.k, kTopkMaxK);
+  D2B_REQUIRE(d.rows_per_group >= 0, "top-k: negative rows_per_group");
+  for (int g = 0; g < d.G; ++g)
+    D2B_REQUIRE(d.row_len[g] >= 0 && d.row_len[g] < (1ll << 32) - 1, "top-k: row_len[%d] out of range", g);
+  const int rows = d.G * d.rows_per_group;
+  if (rows == 0 || d.k == 0) return D2B_OK;
+  TopkArgs a;
+  const int ctas = fill_args(d, a);
+  Workspace w(ws);
+  a.state = w.take<RowState>(rows);
+  a.hist = w.take<unsigned>((size_t)rows * kPasses * kBins);
+  int32_t* seg_len = w.take<int32_t>(rows);
+  D2B_CUDA(cudaMemsetAsync(a.hist, 0, (size_t)rows * kPasses * kBins * sizeof(unsigned), st));
+  topk_init<<<(rows + 127) / 128, 128, 0, st>>>(a, rows);
+  D2B_LAUNCH_CHECK();
+  for (int p = 0; p < kPasses; ++p) {
+    topk_hist<<<ctas, kHistThreads, 0, st>>>(a, p);
+    D2B_LAUNCH_CHECK();
+  }
+  topk_collect<<<ctas, kHistThreads, 0, st>>>(a, out_keys);
+  D2B_LAUNCH_CHECK();
+  topk_counts<<<(rows + 127) / 128, 128, 0, st>>>(a, seg_len, rows);
+  D2B_LAUNCH_CHECK();
+  int rc = sort_segments_desc(out_keys, rows, a.P, seg_len, st);
+  if (rc != D2B_OK) return rc;
+  if (out_values || out_indices || out_counts) {
+    const dim3 grid((d.k + 255) / 256, rows);
+    topk_emit<<<grid, 256, 0, st>>>(a, out_keys, out_values, out_indices, out_counts, rows);
+    D2B_LAUNCH_CHECK();
+  }
+  return D2B_OK;
+}
+
+}  // namespace d2b
+
+using namespace d2b;
+
+static int to_desc(const d2b_segmented_topk_params* p, TopkDesc& d) {
+  D2B_REQUIRE(p != nullptr, "params is NULL");
+  D2B_REQUIRE(p->num_groups >= 1 && p->num_groups <= D2B_MAX_LEVELS, "num_groups=%d out of range", p->num_groups);
+  D2B_REQUIRE(p->transform == D2B_TOPK_IDENTITY || p->transform == D2B_TOPK_SIGMOID, "unknown transform");
+  for (int g = 0; g < D2B_MAX_LEVELS; ++g) {
+    d.scores[g] = g < p->num_groups ? p->scores[g] : nullptr;
+    d.row_len[g] = g < p->num_groups ? p->row_len[g] : 0;
+    d.k_limit[g] = g < p->num_groups ? p->k_limit[g] : 0;
+  }
+  d.G = p->num_groups;
+  d.rows_per_group = p->rows_per_group;
+  d.k = p->k;
+  d.transform = p->transform;
+  return D2B_OK;
+}
+
+extern "C" size_t d2b_segmented_topk_workspace_bytes(const d2b_segmented_topk_params* p) {
+  TopkDesc d;
+  if (!p || to_desc(p, d) != D2B_OK) return 0;
+  const size_t rows = (size_t)d.G * d.rows_per_group;
+  return topk_workspace_bytes(d) + ws_slice(rows * (size_t)topk_padded_k(d.k) * sizeof(unsigned long long));
+}
+
+extern "C" int d2b_segmented_topk(const d2b_segmented_topk_params* p, void* workspace, size_t workspace_bytes,
+                                  d2b_stream_t stream) {
+  TopkDesc d;
+  int rc = to_desc(p, d);
+  if (rc != D2B_OK) return rc;
+  const int rows = d.G * d.rows_per_group;
+  if (rows == 0 || d.k == 0) return D2B_OK;
+  for (int g = 0; g < d.G; ++g) D2B_REQUIRE(d.scores[g] != nullptr || d.row_len[g] == 0, "scores[%d] is NULL", g);
+  if (workspace == nullptr || workspace_bytes < d2b_segmented_topk_workspace_bytes(p)) {
+    set_last_error("segmented_topk needs %zu workspace bytes", d2b_segmented_topk_workspace_bytes(p));
+    return D2B_EWORKSPACE;
+  }
+  Workspace w(workspace);
+  unsigned long long* keys = w.take<unsigned long long>((size_t)rows * topk_padded_k(d.k));
+  return topk_run(d, keys, p->out_values, p->out_indices, p->out_counts, w.base + w.off,
+                  static_cast<cudaStream_t>(stream));
+}
