@@ -1,0 +1,654 @@
+// pipelines.cu -- the three fused post-processing stages, each a fixed chain of
+// launches over ALL (image, level) segments with no host synchronisation:
+//   d2b_rpn_proposals          rpn_outputs.py:403-426 + 29-132
+//   d2b_fast_rcnn_postprocess  fast_rcnn.py:28-187
+//   d2b_retinanet_postprocess  retinanet.py:285-387
+// The reference runs them as tf.map_fn over images with a CPU NMS per segment.
+#include "kernels.cuh"
+
+namespace d2b {
+namespace {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 make_key(float score, unsigned idx) {
+  return ((u64)float_to_key(score) << 32) | (u64)(0xffffffffu - idx);
+}
+__device__ __forceinline__ unsigned key_index(u64 k) { return 0xffffffffu - (unsigned)k; }
+
+int pad_pow2(long long n) {
+  int P = 1;
+  while (P < n) P <<= 1;
+  return P;
+}
+
+// Ordered block compaction helper: returns this thread's output slot (or -1) and adds the
+// block total to `base` (shared), preserving thread order.  All threads must call it.
+template <int THREADS>
+__device__ __forceinline__ int block_compact(bool flag, int& base_reg, int* s_warp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned m = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) s_warp[warp] = __popc(m);
+  __syncthreads();
+  int before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; ++w) {
+    const int c = s_warp[w];
+    if (w < warp) before += c;
+    total += c;
+  }
+  const int slot = flag ? base_reg + before + __popc(m & ((1u << lane) - 1u)) : -1;
+  base_reg += total;
+  __syncthreads();
+  return slot;
+}
+
+// =====================================================================================
+// RPN
+// =====================================================================================
+struct RpnArgs {
+  const float* logits[D2B_MAX_LEVELS];
+  const float4* proposals[D2B_MAX_LEVELS];
+  const float4* deltas[D2B_MAX_LEVELS];
+  const float4* anchors[D2B_MAX_LEVELS];
+  long long hwa[D2B_MAX_LEVELS];
+  int L, N;
+  const int32_t* shapes;
+  float min_len;
+  float w[4];
+  float clampv;
+  int k, P, post, P2;
+};
+
+constexpr int kRpnThreads = 256;
+
+// one CTA per (image, level) row: gather/decode the sorted top-k winners, clip, prune (ordered)
+__global__ void __launch_bounds__(kRpnThreads) rpn_decode_kernel(RpnArgs a, const u64* keys, const int32_t* k_r,
+                                                                  float4* seg_boxes, float* seg_scores,
+                                                                  int32_t* seg_count, u64* nms_in_total) {
+  __shared__ int s_warp[kRpnThreads / 32];
+  const int row = blockIdx.x;
+  const int n = row / a.L, l = row - n * a.L;
+  const int kr = k_r[row];
+  const float h = (float)a.shapes[2 * n], w = (float)a.shapes[2 * n + 1];
+  const size_t rbase = (size_t)n * a.hwa[l];
+  int base = 0;
+  for (int j0 = 0; j0 < kr; j0 += kRpnThreads) {
+    const int j = j0 + threadIdx.x;
+    bool ok = false;
+    float4 box = make_float4(0, 0, 0, 0);
+    float score = 0.0f;
+    if (j < kr) {
+      const unsigned idx = key_index(keys[(size_t)row * a.P + j]);
+      score = __ldg(a.logits[l] + rbase + idx);
+      if (a.proposals[l]) box = __ldg(a.proposals[l] + rbase + idx);
+      else box = d2b_decode(__ldg(a.deltas[l] + rbase + idx), __ldg(a.anchors[l] + idx), a.w[0], a.w[1], a.w[2], a.w[3], a.clampv);
+      box = d2b_clip(box, h, w);  // rpn_outputs.py:77-80
+      ok = true;
+      if (a.min_len > 0.0f) {     // prune_small_boxes, :83-87
+        const float bh = box.z - box.x, bw = box.w - box.y;
+        ok = (bw >= a.min_len) && (bh >= a.min_len);
+      }
+    }
+    const int slot = block_compact<kRpnThreads>(ok, base, s_warp);
+    if (slot >= 0) {
+      seg_boxes[(size_t)row * a.k + slot] = box;
+      seg_scores[(size_t)row * a.k + slot] = score;
+    }
+  }
+  if (threadIdx.x == 0) {
+    seg_count[row] = base;
+    if (nms_in_total) atomicAdd(nms_in_total, (u64)base);
+  }
+}
+
+// one CTA per image: concat the per-level NMS survivors (level-major) and key them for the final top-k
+__global__ void __launch_bounds__(256) rpn_merge_prep_kernel(RpnArgs a, const float* seg_scores, const int32_t* keep,
+                                                             const int32_t* num_keep, u64* keys2, int32_t* off,
+                                                             int32_t* total) {
+  const int n = blockIdx.x;
+  __shared__ int s_off[D2B_MAX_LEVELS + 1];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int l = 0; l < a.L; ++l) { s_off[l] = acc; acc += num_keep[n * a.L + l]; }
+    s_off[a.L] = acc;
+    for (int l = 0; l <= a.L; ++l) off[n * (D2B_MAX_LEVELS + 1) + l] = s_off[l];
+    total[n] = acc;
+  }
+  __syncthreads();
+  for (int l = 0; l < a.L; ++l) {
+    const int row = n * a.L + l;
+    const int cnt = s_off[l + 1] - s_off[l];
+    for (int q = threadIdx.x; q < cnt; q += blockDim.x) {
+      const int pos = keep[(size_t)row * a.post + q];
+      keys2[(size_t)n * a.P2 + s_off[l] + q] = make_key(seg_scores[(size_t)row * a.k + pos], (unsigned)(s_off[l] + q));
+    }
+  }
+}
+
+__global__ void rpn_emit_kernel(RpnArgs a, const u64* keys2, const int32_t* off, const int32_t* total,
+                                const float4* seg_boxes, const float* seg_scores, const int32_t* keep,
+                                float4* out_boxes, float* out_logits, uint8_t* out_valid, int32_t* out_num) {
+  const int n = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.post) return;
+  const int kk = min(total[n], a.post);  // rpn_outputs.py:105
+  if (j == 0 && out_num) out_num[n] = kk;
+  float4 box = make_float4(0, 0, 0, 0);
+  float logit = 0.0f;
+  uint8_t valid = 0;
+  if (j < kk) {
+    const int ci = (int)key_index(keys2[(size_t)n * a.P2 + j]);
+    const int32_t* o = off + n * (D2B_MAX_LEVELS + 1);
+    int l = 0;
+    while (l + 1 < a.L && ci >= o[l + 1]) ++l;
+    const int row = n * a.L + l;
+    const int pos = keep[(size_t)row * a.post + (ci - o[l])];
+    box = seg_boxes[(size_t)row * a.k + pos];
+    logit = seg_scores[(size_t)row * a.k + pos];
+    valid = 1;
+  }
+  out_boxes[(size_t)n * a.post + j] = box;
+  out_logits[(size_t)n * a.post + j] = logit;
+  out_valid[(size_t)n * a.post + j] = valid;
+}
+
+struct RpnPlan {
+  TopkDesc td;
+  RpnArgs a;
+  int rows;
+  size_t bytes;
+  // offsets
+  size_t o_topk, o_keys, o_kr, o_boxes, o_scores, o_count, o_keep, o_nkeep, o_nms, o_keys2, o_off, o_total;
+};
+
+int rpn_plan(const d2b_rpn_proposals_params* p, RpnPlan& pl) {
+  D2B_REQUIRE(p != nullptr, "params is NULL");
+  D2B_REQUIRE(p->num_levels >= 1 && p->num_levels <= D2B_MAX_LEVELS, "num_levels=%d out of range", p->num_levels);
+  D2B_REQUIRE(p->num_images >= 0, "num_images must be >= 0");
+  D2B_REQUIRE(p->pre_nms_topk >= 1 && p->pre_nms_topk <= kTopkMaxK, "pre_nms_topk=%d out of [1,%d]", p->pre_nms_topk, kTopkMaxK);
+  D2B_REQUIRE(p->post_nms_topk >= 1 && p->post_nms_topk <= kTopkMaxK, "post_nms_topk=%d out of [1,%d]", p->post_nms_topk, kTopkMaxK);
+  RpnArgs& a = pl.a;
+  TopkDesc& td = pl.td;
+  long long maxlen = 0;
+  for (int l = 0; l < D2B_MAX_LEVELS; ++l) {
+    const bool in = l < p->num_levels;
+    a.logits[l] = in ? p->logits[l] : nullptr;
+    a.proposals[l] = in ? reinterpret_cast<const float4*>(p->proposals[l]) : nullptr;
+    a.deltas[l] = in ? reinterpret_cast<const float4*>(p->deltas[l]) : nullptr;
+    a.anchors[l] = in ? reinterpret_cast<const float4*>(p->anchors[l]) : nullptr;
+    a.hwa[l] = in ? p->hwa[l] : 0;
+    td.scores[l] = a.logits[l];
+    td.row_len[l] = a.hwa[l];
+    td.k_limit[l] = 0;
+    if (in) {
+      D2B_REQUIRE(p->hwa[l] >= 0, "hwa[%d] negative", l);
+      if (p->num_images > 0 && p->hwa[l] > 0) {
+        D2B_REQUIRE(p->logits[l] != nullptr, "logits[%d] is NULL", l);
+        D2B_REQUIRE(p->proposals[l] != nullptr || (p->deltas[l] != nullptr && p->anchors[l] != nullptr),
+                    "level %d: need proposals or deltas+anchors", l);
+      }
+      if (p->hwa[l] > maxlen) maxlen = p->hwa[l];
+    }
+  }
+  a.L = p->num_levels; a.N = p->num_images; a.shapes = p->image_shapes; a.min_len = p->min_box_side_len;
+  for (int i = 0; i < 4; ++i) a.w[i] = p->weights[i];
+  a.clampv = p->scale_clamp;
+  // k = min(pre, longest row): no row can yield more (rpn_outputs.py:67-68)
+  a.k = (int)(p->pre_nms_topk < maxlen ? p->pre_nms_topk : (maxlen > 0 ? maxlen : 1));
+  a.P = topk_padded_k(a.k);
+  a.post = p->post_nms_topk;
+  a.P2 = pad_pow2((long long)a.L * (a.post < a.k ? a.post : a.k));
+  td.G = a.L; td.rows_per_group = a.N; td.k = a.k; td.transform = D2B_TOPK_IDENTITY;
+  pl.rows = a.L * a.N;
+  const size_t rows = pl.rows, N = a.N;
+  size_t o = 0;
+  pl.o_topk = o; o += topk_workspace_bytes(td);
+  pl.o_keys = o; o += ws_slice(rows * a.P * sizeof(u64));
+  pl.o_kr = o; o += ws_slice(rows * sizeof(int32_t));
+  pl.o_boxes = o; o += ws_slice(rows * a.k * sizeof(float4));
+  pl.o_scores = o; o += ws_slice(rows * a.k * sizeof(float));
+  pl.o_count = o; o += ws_slice(rows * sizeof(int32_t));
+  pl.o_keep = o; o += ws_slice(rows * a.post * sizeof(int32_t));
+  pl.o_nkeep = o; o += ws_slice(rows * sizeof(int32_t));
+  pl.o_nms = o; o += nms_sorted_workspace_bytes(pl.rows, a.k, a.post);
+  pl.o_keys2 = o; o += ws_slice(N * a.P2 * sizeof(u64));
+  pl.o_off = o; o += ws_slice(N * (D2B_MAX_LEVELS + 1) * sizeof(int32_t));
+  pl.o_total = o; o += ws_slice(N * sizeof(int32_t));
+  pl.bytes = o;
+  return D2B_OK;
+}
+
+// =====================================================================================
+// detection tail shared by Fast R-CNN and RetinaNet:
+//   sorted candidate keys -> class-offset boxes -> NMS -> padded outputs
+// =====================================================================================
+struct FrcnnFetch {
+  const float4* boxes;    // [M, Kb]
+  const float* scores;    // [M, K+1]
+  const int32_t* slot_map;  // [N, Rmax] -> pred row
+  const int32_t* shapes;
+  int Rmax, Kb, K;
+  __device__ __forceinline__ void get(int n, unsigned ci, float4& box, float& score, int& cls, int& roi) const {
+    cls = (int)(ci / (unsigned)Rmax);
+    roi = (int)(ci - (unsigned)cls * (unsigned)Rmax);
+    const int i = slot_map[(size_t)n * Rmax + roi];
+    const float h = (float)shapes[2 * n], w = (float)shapes[2 * n + 1];
+    box = d2b_clip(__ldg(boxes + (size_t)i * Kb + (Kb == 1 ? 0 : cls)), h, w);
+    score = __ldg(scores + (size_t)i * (K + 1) + cls);
+  }
+};
+
+struct RetinaFetch {
+  const float4* cand_boxes;  // [N, stride]
+  const float* cand_scores;
+  const int32_t* cand_cls;
+  int stride;
+  __device__ __forceinline__ void get(int n, unsigned ci, float4& box, float& score, int& cls, int& roi) const {
+    const size_t o = (size_t)n * stride + ci;
+    box = cand_boxes[o];
+    score = cand_scores[o];
+    cls = cand_cls[o];
+    roi = (int)ci;
+  }
+};
+
+template <typename F>
+__global__ void det_gather_kernel(F f, const u64* keys, const int32_t* count, const float* max_coord, int P,
+                                  int stride, int agnostic, float4* nms_boxes, u64* nms_in_total) {
+  const int n = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cnt = min(count[n], stride);
+  if (j == 0 && nms_in_total) atomicAdd(nms_in_total, (u64)cnt);
+  if (j >= cnt) return;
+  float4 box; float score; int cls, roi;
+  f.get(n, key_index(keys[(size_t)n * P + j]), box, score, cls, roi);
+  if (!agnostic) {  // fast_rcnn.py:141-143 / retinanet.py:349-351: fp32 class offset on every coordinate
+    const float mc1 = max_coord[n] + 1.0f;
+    const float off = (float)cls * mc1;
+    box.x = box.x + off; box.y = box.y + off; box.z = box.z + off; box.w = box.w + off;
+  }
+  nms_boxes[(size_t)n * stride + j] = box;
+}
+
+template <typename F, typename TCls>
+__global__ void det_emit_kernel(F f, const u64* keys, int P, const int32_t* keep, const int32_t* num_keep, int topk,
+                                float4* out_boxes, float* out_scores, TCls* out_classes, uint8_t* out_valid,
+                                int32_t* out_roi, int32_t* out_num) {
+  const int n = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= topk) return;
+  const int nk = num_keep[n];
+  if (q == 0 && out_num) out_num[n] = nk;
+  float4 box = make_float4(0, 0, 0, 0);
+  float score = 0.0f;
+  int cls = 0, roi = -1;
+  uint8_t valid = 0;
+  if (q < nk) {
+    const int j = keep[(size_t)n * topk + q];
+    f.get(n, key_index(keys[(size_t)n * P + j]), box, score, cls, roi);
+    valid = 1;
+  }
+  const size_t o = (size_t)n * topk + q;
+  out_boxes[o] = box;
+  out_scores[o] = score;
+  out_classes[o] = (TCls)cls;
+  out_valid[o] = valid;
+  if (out_roi) out_roi[o] = roi;
+}
+
+// ------------------------------------------------------------------ Fast R-CNN front
+// one thread per (prediction row, class): threshold -> candidate key; also the dense slot map
+// and max_coord over ALL clipped boxes of the image (fast_rcnn.py:109-116,141).
+__global__ void frcnn_prep_kernel(const float4* boxes, const float* scores, const long long* indices, long long M,
+                                  int N, int Rmax, int Kb, int K, const int32_t* shapes, float thresh, int P,
+                                  u64* keys, int32_t* count, int32_t* slot_map, int* max_coord_bits) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M * K) return;
+  const long long i = t / K;
+  const int k = (int)(t - i * K);
+  const long long n = indices[2 * i], r = indices[2 * i + 1];
+  if (n < 0 || n >= N || r < 0 || r >= Rmax) return;
+  if (k == 0) slot_map[n * Rmax + r] = (int32_t)i;
+  if (k < Kb) {
+    const float h = (float)shapes[2 * n], w = (float)shapes[2 * n + 1];
+    const float4 b = d2b_clip(__ldg(boxes + i * Kb + k), h, w);
+    const float m = fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w));  // >= 0 after clipping
+    atomicMax(max_coord_bits + n, __float_as_int(m));
+  }
+  const float s = __ldg(scores + i * (K + 1) + k);
+  if (s > thresh) {
+    const int slot = atomicAdd(count + n, 1);
+    if (slot < P) keys[(size_t)n * P + slot] = make_key(s, (unsigned)(k * Rmax + (int)r));
+  }
+}
+
+// ------------------------------------------------------------------ RetinaNet front
+struct RetinaArgs {
+  const float4* deltas[D2B_MAX_LEVELS];
+  const float4* anchors[D2B_MAX_LEVELS];
+  long long hwa[D2B_MAX_LEVELS];
+  int L, N, K;
+  float thresh;
+  float w[4];
+  float clampv;
+  int k, P, stride, P3;
+};
+constexpr int kRetThreads = 256;
+
+// one CTA per image: per level keep p > thresh (ordered), decode, append to the image's candidate list
+__global__ void __launch_bounds__(kRetThreads) retina_decode_kernel(RetinaArgs a, const u64* keys, const int32_t* k_r,
+                                                                    float4* cand_boxes, float* cand_scores,
+                                                                    int32_t* cand_cls, u64* keys3, int32_t* count,
+                                                                    float* max_coord) {
+  __shared__ int s_warp[kRetThreads / 32];
+  __shared__ float s_max[kRetThreads / 32];
+  const int n = blockIdx.x;
+  int base = 0;
+  float mx = __int_as_float(0xff800000);  // -inf
+  for (int l = 0; l < a.L; ++l) {
+    const int row = n * a.L + l;
+    const int kr = k_r[row];
+    const size_t rbase = (size_t)n * a.hwa[l];
+    for (int j0 = 0; j0 < kr; j0 += kRetThreads) {
+      const int j = j0 + threadIdx.x;
+      bool ok = false;
+      float p = 0.0f;
+      unsigned idx = 0;
+      if (j < kr) {
+        const u64 c = keys[(size_t)row * a.P + j];
+        p = key_to_float((uint32_t)(c >> 32));
+        idx = key_index(c);
+        ok = p > a.thresh;  // retinanet.py:329-331
+      }
+      const int slot = block_compact<kRetThreads>(ok, base, s_warp);
+      if (slot >= 0) {
+        const unsigned anc = idx / (unsigned)a.K;       // :333
+        const int cls = (int)(idx - anc * (unsigned)a.K);  // :334
+        const float4 box = d2b_decode(__ldg(a.deltas[l] + rbase + anc), __ldg(a.anchors[l] + anc), a.w[0], a.w[1],
+                                      a.w[2], a.w[3], a.clampv);
+        const size_t o = (size_t)n * a.stride + slot;
+        cand_boxes[o] = box;
+        cand_scores[o] = p;
+        cand_cls[o] = cls;
+        keys3[(size_t)n * a.P3 + slot] = make_key(p, (unsigned)slot);
+        mx = fmaxf(mx, fmaxf(fmaxf(box.x, box.y), fmaxf(box.z, box.w)));
+      }
+    }
+  }
+  // block max (retinanet.py:349)
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = s_max[0];
+    for (int w = 1; w < kRetThreads / 32; ++w) m = fmaxf(m, s_max[w]);
+    max_coord[n] = m;
+    count[n] = base;
+  }
+}
+
+}  // namespace
+}  // namespace d2b
+
+using namespace d2b;
+
+// =====================================================================================
+extern "C" size_t d2b_rpn_proposals_workspace_bytes(const d2b_rpn_proposals_params* p) {
+  RpnPlan pl;
+  if (rpn_plan(p, pl) != D2B_OK) return 0;
+  return pl.bytes;
+}
+
+extern "C" int d2b_rpn_proposals(const d2b_rpn_proposals_params* p, void* workspace, size_t workspace_bytes,
+                                 d2b_stream_t stream) {
+  RpnPlan pl;
+  int rc = rpn_plan(p, pl);
+  if (rc != D2B_OK) return rc;
+  if (p->num_images == 0) return D2B_OK;
+  D2B_REQUIRE(p->image_shapes && p->out_boxes && p->out_logits && p->out_valid, "rpn_proposals: NULL pointer");
+  if (workspace == nullptr || workspace_bytes < pl.bytes) {
+    set_last_error("rpn_proposals needs %zu workspace bytes", pl.bytes);
+    return D2B_EWORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  const RpnArgs& a = pl.a;
+  u64* keys = reinterpret_cast<u64*>(ws + pl.o_keys);
+  int32_t* kr = reinterpret_cast<int32_t*>(ws + pl.o_kr);
+  float4* seg_boxes = reinterpret_cast<float4*>(ws + pl.o_boxes);
+  float* seg_scores = reinterpret_cast<float*>(ws + pl.o_scores);
+  int32_t* seg_count = reinterpret_cast<int32_t*>(ws + pl.o_count);
+  int32_t* keep = reinterpret_cast<int32_t*>(ws + pl.o_keep);
+  int32_t* nkeep = reinterpret_cast<int32_t*>(ws + pl.o_nkeep);
+  u64* keys2 = reinterpret_cast<u64*>(ws + pl.o_keys2);
+  int32_t* off = reinterpret_cast<int32_t*>(ws + pl.o_off);
+  int32_t* total = reinterpret_cast<int32_t*>(ws + pl.o_total);
+  u64* nms_in = reinterpret_cast<u64*>(p->out_nms_boxes_in);
+  if (nms_in) D2B_CUDA(cudaMemsetAsync(nms_in, 0, sizeof(u64), st));
+
+  rc = topk_run(pl.td, keys, nullptr, nullptr, kr, ws + pl.o_topk, st);  // rpn_outputs.py:70
+  if (rc != D2B_OK) return rc;
+  rpn_decode_kernel<<<pl.rows, kRpnThreads, 0, st>>>(a, keys, kr, seg_boxes, seg_scores, seg_count, nms_in);
+  D2B_LAUNCH_CHECK();
+  rc = nms_sorted(reinterpret_cast<const float*>(seg_boxes), seg_count, pl.rows, a.k, a.post, p->nms_thresh, keep,
+                  nkeep, ws + pl.o_nms, st);  // :90-94
+  if (rc != D2B_OK) return rc;
+  rpn_merge_prep_kernel<<<a.N, 256, 0, st>>>(a, seg_scores, keep, nkeep, keys2, off, total);
+  D2B_LAUNCH_CHECK();
+  rc = sort_segments_desc(keys2, a.N, a.P2, total, st);  // :105-107
+  if (rc != D2B_OK) return rc;
+  rpn_emit_kernel<<<dim3((a.post + 255) / 256, a.N), 256, 0, st>>>(
+      a, keys2, off, total, seg_boxes, seg_scores, keep, reinterpret_cast<float4*>(p->out_boxes), p->out_logits,
+      p->out_valid, p->out_num_valid);
+  D2B_LAUNCH_CHECK();
+  return D2B_OK;
+}
+
+// =====================================================================================
+namespace {
+struct FrcnnPlan {
+  int P, stride;
+  size_t bytes, o_keys, o_count, o_slot, o_max, o_nmsb, o_keep, o_nkeep, o_nms;
+};
+int frcnn_plan(const d2b_fast_rcnn_params* p, FrcnnPlan& pl) {
+  D2B_REQUIRE(p != nullptr, "params is NULL");
+  D2B_REQUIRE(p->num_images >= 0 && p->rmax >= 0 && p->num_preds >= 0, "fast_rcnn: negative sizes");
+  D2B_REQUIRE(p->num_classes >= 1, "fast_rcnn: num_classes must be >= 1");
+  D2B_REQUIRE(p->num_bbox_reg_classes == 1 || p->num_bbox_reg_classes == p->num_classes,
+              "fast_rcnn: boxes must be [M,4] or [M,K*4] (Kb=%d, K=%d)", p->num_bbox_reg_classes, p->num_classes);
+  D2B_REQUIRE(p->topk_per_image >= 1, "fast_rcnn: topk_per_image must be >= 1");
+  const long long cmax = (long long)p->rmax * p->num_classes;
+  D2B_REQUIRE(cmax < (1ll << 30), "fast_rcnn: Rmax*K too large");
+  pl.stride = (int)(cmax > 0 ? cmax : 1);
+  pl.P = pad_pow2(pl.stride);
+  const size_t N = p->num_images;
+  size_t o = 0;
+  pl.o_keys = o; o += ws_slice(N * pl.P * sizeof(u64));
+  pl.o_count = o; o += ws_slice(N * sizeof(int32_t));
+  pl.o_slot = o; o += ws_slice(N * (size_t)(p->rmax > 0 ? p->rmax : 1) * sizeof(int32_t));
+  pl.o_max = o; o += ws_slice(N * sizeof(float));
+  pl.o_nmsb = o; o += ws_slice(N * pl.stride * sizeof(float4));
+  pl.o_keep = o; o += ws_slice(N * p->topk_per_image * sizeof(int32_t));
+  pl.o_nkeep = o; o += ws_slice(N * sizeof(int32_t));
+  pl.o_nms = o; o += nms_sorted_workspace_bytes(p->num_images, pl.stride, p->topk_per_image);
+  pl.bytes = o;
+  return D2B_OK;
+}
+}  // namespace
+
+extern "C" size_t d2b_fast_rcnn_postprocess_workspace_bytes(const d2b_fast_rcnn_params* p) {
+  FrcnnPlan pl;
+  if (frcnn_plan(p, pl) != D2B_OK) return 0;
+  return pl.bytes;
+}
+
+extern "C" int d2b_fast_rcnn_postprocess(const d2b_fast_rcnn_params* p, void* workspace, size_t workspace_bytes,
+                                         d2b_stream_t stream) {
+  FrcnnPlan pl;
+  int rc = frcnn_plan(p, pl);
+  if (rc != D2B_OK) return rc;
+  if (p->num_images == 0) return D2B_OK;
+  D2B_REQUIRE(p->image_shapes && p->out_boxes && p->out_scores && p->out_classes && p->out_valid,
+              "fast_rcnn: NULL pointer");
+  D2B_REQUIRE(p->num_preds == 0 || (p->boxes && p->scores && p->indices), "fast_rcnn: NULL input");
+  if (workspace == nullptr || workspace_bytes < pl.bytes) {
+    set_last_error("fast_rcnn_postprocess needs %zu workspace bytes", pl.bytes);
+    return D2B_EWORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  const int N = p->num_images, T = p->topk_per_image;
+  u64* keys = reinterpret_cast<u64*>(ws + pl.o_keys);
+  int32_t* count = reinterpret_cast<int32_t*>(ws + pl.o_count);
+  int32_t* slot_map = reinterpret_cast<int32_t*>(ws + pl.o_slot);
+  float* max_coord = reinterpret_cast<float*>(ws + pl.o_max);
+  float4* nms_boxes = reinterpret_cast<float4*>(ws + pl.o_nmsb);
+  int32_t* keep = reinterpret_cast<int32_t*>(ws + pl.o_keep);
+  int32_t* nkeep = reinterpret_cast<int32_t*>(ws + pl.o_nkeep);
+  u64* nms_in = reinterpret_cast<u64*>(p->out_nms_boxes_in);
+  if (nms_in) D2B_CUDA(cudaMemsetAsync(nms_in, 0, sizeof(u64), st));
+  D2B_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t) * N, st));
+  D2B_CUDA(cudaMemsetAsync(max_coord, 0, sizeof(float) * N, st));  // clipped coords are >= 0; padding rows are 0
+  const long long MK = p->num_preds * p->num_classes;
+  if (MK > 0) {
+    frcnn_prep_kernel<<<(unsigned)((MK + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(p->boxes), p->scores, reinterpret_cast<const long long*>(p->indices),
+        p->num_preds, N, p->rmax, p->num_bbox_reg_classes, p->num_classes, p->image_shapes, p->score_thresh, pl.P,
+        keys, count, slot_map, reinterpret_cast<int*>(max_coord));
+    D2B_LAUNCH_CHECK();
+  }
+  rc = sort_segments_desc(keys, N, pl.P, count, st);
+  if (rc != D2B_OK) return rc;
+  FrcnnFetch f{reinterpret_cast<const float4*>(p->boxes), p->scores, slot_map, p->image_shapes, p->rmax,
+               p->num_bbox_reg_classes, p->num_classes};
+  det_gather_kernel<FrcnnFetch><<<dim3((pl.stride + 255) / 256, N), 256, 0, st>>>(
+      f, keys, count, max_coord, pl.P, pl.stride, p->nms_cls_agnostic ? 1 : 0, nms_boxes, nms_in);
+  D2B_LAUNCH_CHECK();
+  rc = nms_sorted(reinterpret_cast<const float*>(nms_boxes), count, N, pl.stride, T, p->nms_thresh, keep, nkeep,
+                  ws + pl.o_nms, st);  // fast_rcnn.py:145-146
+  if (rc != D2B_OK) return rc;
+  det_emit_kernel<FrcnnFetch, int64_t><<<dim3((T + 127) / 128, N), 128, 0, st>>>(
+      f, keys, pl.P, keep, nkeep, T, reinterpret_cast<float4*>(p->out_boxes), p->out_scores, p->out_classes,
+      p->out_valid, p->out_roi_index, p->out_num);
+  D2B_LAUNCH_CHECK();
+  return D2B_OK;
+}
+
+// =====================================================================================
+namespace {
+struct RetinaPlan {
+  TopkDesc td;
+  RetinaArgs a;
+  int rows;
+  size_t bytes, o_topk, o_keys, o_kr, o_cb, o_cs, o_cc, o_keys3, o_count, o_max, o_nmsb, o_keep, o_nkeep, o_nms;
+};
+int retina_plan(const d2b_retinanet_params* p, RetinaPlan& pl) {
+  D2B_REQUIRE(p != nullptr, "params is NULL");
+  D2B_REQUIRE(p->num_levels >= 1 && p->num_levels <= D2B_MAX_LEVELS, "num_levels=%d out of range", p->num_levels);
+  D2B_REQUIRE(p->num_images >= 0 && p->num_classes >= 1, "retinanet: bad sizes");
+  D2B_REQUIRE(p->topk_candidates >= 1 && p->topk_candidates <= kTopkMaxK, "topk_candidates=%d out of [1,%d]",
+              p->topk_candidates, kTopkMaxK);
+  D2B_REQUIRE(p->max_detections >= 1, "max_detections must be >= 1");
+  RetinaArgs& a = pl.a;
+  TopkDesc& td = pl.td;
+  long long maxhwa = 0;
+  for (int l = 0; l < D2B_MAX_LEVELS; ++l) {
+    const bool in = l < p->num_levels;
+    a.deltas[l] = in ? reinterpret_cast<const float4*>(p->box_delta[l]) : nullptr;
+    a.anchors[l] = in ? reinterpret_cast<const float4*>(p->anchors[l]) : nullptr;
+    a.hwa[l] = in ? p->hwa[l] : 0;
+    td.scores[l] = in ? p->box_cls[l] : nullptr;
+    td.row_len[l] = in ? p->hwa[l] * p->num_classes : 0;
+    td.k_limit[l] = in ? (int)(p->hwa[l] < p->topk_candidates ? p->hwa[l] : p->topk_candidates) : 0;
+    if (in) {
+      D2B_REQUIRE(p->hwa[l] >= 0 && p->hwa[l] * p->num_classes < (1ll << 32) - 1, "hwa[%d] out of range", l);
+      if (p->num_images > 0 && p->hwa[l] > 0)
+        D2B_REQUIRE(p->box_cls[l] && p->box_delta[l] && p->anchors[l], "level %d: NULL input", l);
+      if (p->hwa[l] > maxhwa) maxhwa = p->hwa[l];
+      if (td.k_limit[l] == 0 && p->hwa[l] == 0) td.row_len[l] = 0;
+    }
+  }
+  a.L = p->num_levels; a.N = p->num_images; a.K = p->num_classes; a.thresh = p->score_thresh;
+  for (int i = 0; i < 4; ++i) a.w[i] = p->weights[i];
+  a.clampv = p->scale_clamp;
+  a.k = (int)(p->topk_candidates < maxhwa ? p->topk_candidates : (maxhwa > 0 ? maxhwa : 1));
+  a.P = topk_padded_k(a.k);
+  a.stride = a.L * a.k;
+  a.P3 = pad_pow2(a.stride);
+  td.G = a.L; td.rows_per_group = a.N; td.k = a.k; td.transform = D2B_TOPK_SIGMOID;
+  pl.rows = a.L * a.N;
+  const size_t rows = pl.rows, N = a.N;
+  size_t o = 0;
+  pl.o_topk = o; o += topk_workspace_bytes(td);
+  pl.o_keys = o; o += ws_slice(rows * a.P * sizeof(u64));
+  pl.o_kr = o; o += ws_slice(rows * sizeof(int32_t));
+  pl.o_cb = o; o += ws_slice(N * a.stride * sizeof(float4));
+  pl.o_cs = o; o += ws_slice(N * a.stride * sizeof(float));
+  pl.o_cc = o; o += ws_slice(N * a.stride * sizeof(int32_t));
+  pl.o_keys3 = o; o += ws_slice(N * a.P3 * sizeof(u64));
+  pl.o_count = o; o += ws_slice(N * sizeof(int32_t));
+  pl.o_max = o; o += ws_slice(N * sizeof(float));
+  pl.o_nmsb = o; o += ws_slice(N * a.stride * sizeof(float4));
+  pl.o_keep = o; o += ws_slice(N * p->max_detections * sizeof(int32_t));
+  pl.o_nkeep = o; o += ws_slice(N * sizeof(int32_t));
+  pl.o_nms = o; o += nms_sorted_workspace_bytes(a.N, a.stride, p->max_detections);
+  pl.bytes = o;
+  return D2B_OK;
+}
+}  // namespace
+
+extern "C" size_t d2b_retinanet_postprocess_workspace_bytes(const d2b_retinanet_params* p) {
+  RetinaPlan pl;
+  if (retina_plan(p, pl) != D2B_OK) return 0;
+  return pl.bytes;
+}
+
+extern "C" int d2b_retinanet_postprocess(const d2b_retinanet_params* p, void* workspace, size_t workspace_bytes,
+                                         d2b_stream_t stream) {
+  RetinaPlan pl;
+  int rc = retina_plan(p, pl);
+  if (rc != D2B_OK) return rc;
+  if (p->num_images == 0) return D2B_OK;
+  D2B_REQUIRE(p->out_boxes && p->out_scores && p->out_classes && p->out_valid, "retinanet: NULL output");
+  if (workspace == nullptr || workspace_bytes < pl.bytes) {
+    set_last_error("retinanet_postprocess needs %zu workspace bytes", pl.bytes);
+    return D2B_EWORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  const RetinaArgs& a = pl.a;
+  const int N = a.N, T = p->max_detections;
+  u64* keys = reinterpret_cast<u64*>(ws + pl.o_keys);
+  int32_t* kr = reinterpret_cast<int32_t*>(ws + pl.o_kr);
+  float4* cb = reinterpret_cast<float4*>(ws + pl.o_cb);
+  float* cs = reinterpret_cast<float*>(ws + pl.o_cs);
+  int32_t* cc = reinterpret_cast<int32_t*>(ws + pl.o_cc);
+  u64* keys3 = reinterpret_cast<u64*>(ws + pl.o_keys3);
+  int32_t* count = reinterpret_cast<int32_t*>(ws + pl.o_count);
+  float* max_coord = reinterpret_cast<float*>(ws + pl.o_max);
+  float4* nms_boxes = reinterpret_cast<float4*>(ws + pl.o_nmsb);
+  int32_t* keep = reinterpret_cast<int32_t*>(ws + pl.o_keep);
+  int32_t* nkeep = reinterpret_cast<int32_t*>(ws + pl.o_nkeep);
+  u64* nms_in = reinterpret_cast<u64*>(p->out_nms_boxes_in);
+  if (nms_in) D2B_CUDA(cudaMemsetAsync(nms_in, 0, sizeof(u64), st));
+
+  rc = topk_run(pl.td, keys, nullptr, nullptr, kr, ws + pl.o_topk, st);  // retinanet.py:321-326
+  if (rc != D2B_OK) return rc;
+  retina_decode_kernel<<<N, kRetThreads, 0, st>>>(a, keys, kr, cb, cs, cc, keys3, count, max_coord);
+  D2B_LAUNCH_CHECK();
+  rc = sort_segments_desc(keys3, N, a.P3, count, st);
+  if (rc != D2B_OK) return rc;
+  RetinaFetch f{cb, cs, cc, a.stride};
+  det_gather_kernel<RetinaFetch><<<dim3((a.stride + 255) / 256, N), 256, 0, st>>>(f, keys3, count, max_coord, a.P3,
+                                                                                    a.stride, 0, nms_boxes, nms_in);
+  D2B_LAUNCH_CHECK();
+  rc = nms_sorted(reinterpret_cast<const float*>(nms_boxes), count, N, a.stride, T, p->nms_thresh, keep, nkeep,
+                  ws + pl.o_nms, st);  // :353-355
+  if (rc != D2B_OK) return rc;
+  det_emit_kernel<RetinaFetch, int32_t><<<dim3((T + 127) / 128, N), 128, 0, st>>>(
+      f, keys3, a.P3, keep, nkeep, T, reinterpret_cast<float4*>(p->out_boxes), p->out_scores, p->out_classes,
+      p->out_valid, nullptr, p->out_num);
+  D2B_LAUNCH_CHECK();
+  return D2B_OK;
+}

@@ -1,1 +1,5 @@
 from .poolers import ROIPooler, assign_boxes_to_levels
+from .box_regression import Box2BoxTransform
+from .proposal_generator.rpn_outputs import find_top_rpn_proposals, RPNOutputs
+from .roi_heads.fast_rcnn import fast_rcnn_inference, FastRCNNOutputs
+from .single_stage_heads.retinanet import RetinaNetInference

@@ -1,0 +1,271 @@
+"""GPU parity for top-k / decode / NMS / RPN / Fast R-CNN / RetinaNet / Matrix-NMS vs the CPU oracle.
+
+Bar (BASELINE.json north_star): kept indices and counts bit-exact; box/score values are produced by
+the same fp32 op order (no FMA) so they are compared for exact equality too.
+"""
+import numpy as np
+import pytest
+import torch
+
+from detectron2_tensorflow_b200.layers import batch_nms, matrix_nms, segmented_top_k
+from detectron2_tensorflow_b200.modeling import (Box2BoxTransform, RPNOutputs, RetinaNetInference, fast_rcnn_inference,
+                                                 find_top_rpn_proposals)
+from detectron2_tensorflow_b200.structures import BoxList, ImageList, SparseBoxList
+from detectron2_tensorflow_b200.utils import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def T(x, dev):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+def rand_boxes(rng, n, H=800, W=1333, smin=8, smax=400):
+    cy, cx = rng.uniform(0, H, n), rng.uniform(0, W, n)
+    h, w = rng.uniform(smin, smax, n), rng.uniform(smin, smax, n)
+    return np.stack([cy - h / 2, cx - w / 2, cy + h / 2, cx + w / 2], 1).astype(np.float32)
+
+
+def clustered_boxes(rng, n, k=12):
+    c = rand_boxes(rng, k)
+    b = c[rng.integers(0, k, n)] + rng.normal(0, 6, (n, 4)).astype(np.float32)
+    return b.astype(np.float32)
+
+
+# ------------------------------------------------------------------ decode
+def test_apply_deltas(cuda, oracle_lib):
+    rng = np.random.default_rng(0)
+    n, k = 3000, 5
+    boxes = rand_boxes(rng, n)
+    deltas = rng.standard_normal((n, k * 4)).astype(np.float32)
+    deltas[::7, 2] = 50.0  # hits the scale clamp
+    deltas[::11, 3] = -30.0
+    for w in ((1., 1., 1., 1.), (10., 10., 5., 5.)):
+        want = oracle_lib.apply_deltas(deltas, boxes, w)
+        got = Box2BoxTransform(w).apply_deltas(T(deltas, cuda), T(boxes, cuda)).cpu().numpy()
+        assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------ top-k
+@pytest.mark.parametrize("variant", ["gaussian", "ties", "heavy_ties", "special"])
+def test_segmented_topk(cuda, oracle_lib, variant):
+    rng = np.random.default_rng(1)
+    lens = [40000, 5000, 819, 33, 1]
+    N, k = 3, 1000
+    rows = []
+    for ln in lens:
+        x = (rng.standard_normal((N, ln)) * 2).astype(np.float32)
+        if variant == "ties":
+            x = (np.round(x * 64) / 64).astype(np.float32)
+        elif variant == "heavy_ties":
+            x = np.round(x).astype(np.float32)  # a dozen distinct values: boundary bucket is huge
+        elif variant == "special":
+            x[:, ::5] = 0.0
+            x[:, 1::50] = -0.0
+            x[:, 2::97] = np.nan
+            x[:, 3::89] = -np.inf
+            x[:, 4::101] = np.inf
+        rows.append(x)
+    vals, idx, cnt = segmented_top_k([T(x, cuda) for x in rows], k)
+    vals, idx, cnt = vals.cpu().numpy(), idx.cpu().numpy(), cnt.cpu().numpy()
+    for n in range(N):
+        for l, x in enumerate(rows):
+            wv, wi = oracle_lib.top_k(x[n], k)
+            kr = len(wi)
+            assert cnt[n, l] == kr == min(k, x.shape[1])
+            assert np.array_equal(idx[n, l, :kr], wi), (variant, n, l)
+            assert np.array_equal(vals[n, l, :kr], wv, equal_nan=True)
+            assert np.all(idx[n, l, kr:] == -1) and np.all(vals[n, l, kr:] == 0)
+
+
+def test_segmented_topk_sigmoid_and_limit(cuda, oracle_lib):
+    rng = np.random.default_rng(2)
+    K = 7
+    hwa = [900, 60, 5]
+    rows = [(rng.standard_normal((2, h * K)) * 6).astype(np.float32) for h in hwa]  # saturates -> ties
+    k = 100
+    vals, idx, cnt = segmented_top_k([T(x, cuda) for x in rows], k, sigmoid=True, k_limits=hwa)
+    for n in range(2):
+        for l, x in enumerate(rows):
+            p = oracle_lib.sigmoidf(x[n])
+            wv, wi = oracle_lib.top_k(p, min(k, hwa[l]))
+            kr = len(wi)
+            assert cnt[n, l].item() == kr
+            assert np.array_equal(idx[n, l, :kr].cpu().numpy(), wi)
+            assert np.array_equal(vals[n, l, :kr].cpu().numpy(), wv)
+
+
+# ------------------------------------------------------------------ NMS
+@pytest.mark.parametrize("n,max_out,thr,kind", [
+    (1000, 1000, 0.7, "random"), (2000, 1000, 0.7, "clustered"), (777, 50, 0.5, "clustered"),
+    (5000, 100, 0.5, "clustered"),   # capped lazy sweep (cap << n)
+    (4500, 4500, 0.6, "random"),     # bitmask, several words per lane
+    (300, 300, 0.3, "ties"), (64, 64, 0.5, "degenerate"), (1, 5, 0.5, "random"), (0, 5, 0.5, "random")])
+def test_batched_nms(cuda, oracle_lib, n, max_out, thr, kind):
+    rng = np.random.default_rng(n + max_out)
+    B = 3
+    boxes = np.zeros((B, n, 4), np.float32)
+    scores = np.zeros((B, n), np.float32)
+    for b in range(B):
+        bx = clustered_boxes(rng, n) if kind in ("clustered", "ties") else rand_boxes(rng, n)
+        sc = rng.standard_normal(n).astype(np.float32)
+        if kind == "ties":
+            sc = np.round(sc * 4).astype(np.float32) / 4
+            bx[n // 2:] = bx[:n - n // 2]  # exact duplicates
+        if kind == "degenerate" and n:
+            bx[::4, 2] = bx[::4, 0]            # zero height
+            bx[1::8] = bx[1::8][:, [2, 3, 0, 1]]  # inverted corners
+            sc[::9] = -np.inf
+            sc[5::13] = np.nan
+        boxes[b], scores[b] = bx, sc
+    keep, num = batch_nms(T(boxes, cuda), T(scores, cuda), max_out, axis=1, iou_threshold=thr)
+    keep, num = keep.cpu().numpy(), num.cpu().numpy()
+    for b in range(B):
+        want = oracle_lib.nms(boxes[b], scores[b], max_out, thr)
+        assert num[b] == len(want)
+        assert np.array_equal(keep[b, :len(want)], want), (kind, b)
+        assert np.all(keep[b, len(want):] == -1)
+
+
+def test_batch_nms_axis0_and_idempotence(cuda, oracle_lib):
+    rng = np.random.default_rng(7)
+    n, B = 400, 2
+    boxes = np.stack([clustered_boxes(rng, n) for _ in range(B)])
+    scores = rng.standard_normal((B, n)).astype(np.float32)
+    k1, n1 = batch_nms(T(boxes.transpose(1, 0, 2), cuda), T(scores.T, cuda), n, axis=0, iou_threshold=0.5)
+    k2, n2 = batch_nms(T(boxes, cuda), T(scores, cuda), n, axis=1, iou_threshold=0.5)
+    assert torch.equal(k1, k2) and torch.equal(n1, n2)
+    # idempotence: NMS of the survivors keeps all of them
+    for b in range(B):
+        kept = k2[b, :n2[b]].long().cpu().numpy()
+        k3, n3 = batch_nms(T(boxes[b][kept][None], cuda), T(scores[b][kept][None], cuda), n, axis=1, iou_threshold=0.5)
+        assert n3[0].item() == len(kept)
+
+
+# ------------------------------------------------------------------ RPN
+def _small_rpn(seed, variant, N=2):
+    padded = (160, 224)
+    anchors = syn.rpn_anchors(padded_hw=padded)
+    rng = np.random.default_rng(seed)
+    logits, deltas = [], []
+    for a in anchors:
+        lg = (rng.standard_normal((N, a.shape[0])) * 2).astype(np.float32)
+        if variant == "ties":
+            lg = (np.round(lg * 8) / 8).astype(np.float32)
+        d = (rng.standard_normal((N, a.shape[0], 4)) * np.array([0.5, 0.5, 0.25, 0.25])).astype(np.float32)
+        if variant == "clustered":
+            d *= 0.05
+        logits.append(lg)
+        deltas.append(d)
+    shapes = np.array([[150, 200], [160, 224]][:N], np.int32)
+    return anchors, logits, deltas, shapes
+
+
+@pytest.mark.parametrize("variant,pre,post,min_len", [("gaussian", 300, 200, 0.0), ("ties", 200, 150, 0.0),
+                                                      ("clustered", 500, 100, 0.0), ("gaussian", 300, 200, 12.0),
+                                                      ("clustered", 2000, 1000, 4.0)])
+def test_rpn_proposals(cuda, oracle_lib, variant, pre, post, min_len):
+    anchors, logits, deltas, shapes = _small_rpn(11, variant)
+    props = [oracle_lib.rpn_predict_proposals(d, a) for d, a in zip(deltas, anchors)]
+    wb, wl, wv, wn = oracle_lib.find_top_rpn_proposals(props, logits, shapes, 0.7, pre, post, min_len)
+    images = ImageList(None, T(shapes, cuda))
+    # (1) reference signature: decoded proposals in
+    res = find_top_rpn_proposals([T(p, cuda) for p in props], [T(x, cuda) for x in logits], images, 0.7, pre, post,
+                                 min_len)
+    # (2) fused: deltas + anchors, only the winners are decoded
+    outs = RPNOutputs(Box2BoxTransform((1., 1., 1., 1.)), images,
+                      [T(x, cuda) for x in logits], [T(d, cuda) for d in deltas], [T(a, cuda) for a in anchors])
+    res2 = outs.find_top_proposals(0.7, pre, post, min_len)
+    for r in (res, res2):
+        assert np.array_equal(r.get_field("is_valid").cpu().numpy(), wv)
+        assert np.array_equal(r.boxes.cpu().numpy(), wb)
+        assert np.array_equal(r.get_field("objectness_logits").cpu().numpy(), wl)
+    # the decode-all path of the reference is also available and bit-exact
+    pp = outs.predict_proposals()
+    for a, b in zip(pp, props):
+        assert np.array_equal(a.cpu().numpy(), b)
+
+
+def test_rpn_full_size_one_image(cuda, oracle_lib):
+    """Config 1 shapes: one 800x1333 image, 268,569 anchors, 1000 pre / 1000 post (test-time FPN settings)."""
+    anchors = syn.rpn_anchors()
+    logits, deltas = syn.rpn_inputs(1, seed=2, variant="clustered", anchors=anchors)
+    shapes = syn.image_shapes(1)
+    props = [oracle_lib.rpn_predict_proposals(d, a) for d, a in zip(deltas, anchors)]
+    wb, wl, wv, wn = oracle_lib.find_top_rpn_proposals(props, logits, shapes, 0.7, 1000, 1000, 0.0)
+    outs = RPNOutputs(Box2BoxTransform((1., 1., 1., 1.)), ImageList(None, T(shapes, cuda)),
+                      [T(x, cuda) for x in logits], [T(d, cuda) for d in deltas], [T(a, cuda) for a in anchors])
+    r = outs.find_top_proposals(0.7, 1000, 1000, 0.0)
+    assert np.array_equal(r.get_field("is_valid").cpu().numpy(), wv)
+    assert np.array_equal(r.boxes.cpu().numpy(), wb)
+    assert np.array_equal(r.get_field("objectness_logits").cpu().numpy(), wl)
+
+
+# ------------------------------------------------------------------ Fast R-CNN
+@pytest.mark.parametrize("agnostic_reg,agnostic_nms,R,K,topk", [(False, False, 120, 20, 100), (True, False, 80, 10, 30),
+                                                                (False, True, 60, 8, 100), (False, False, 1000, 80, 100)])
+def test_fast_rcnn_inference(cuda, oracle_lib, agnostic_reg, agnostic_nms, R, K, topk):
+    rng = np.random.default_rng(R + K)
+    N = 2
+    # ragged: image 1 has fewer valid proposals
+    valid = np.ones((N, R), bool)
+    valid[1, R // 2:] = False
+    idx = np.argwhere(valid).astype(np.int64)
+    M = idx.shape[0]
+    prop = clustered_boxes(rng, M, k=15)
+    Kb = 1 if agnostic_reg else K
+    deltas = (rng.standard_normal((M, Kb * 4)) * 0.5).astype(np.float32)
+    boxes = oracle_lib.apply_deltas(deltas, prop, (10., 10., 5., 5.))
+    lg = rng.standard_normal((M, K + 1)) * 3
+    e = np.exp(lg - lg.max(1, keepdims=True))
+    scores = (e / e.sum(1, keepdims=True)).astype(np.float32)
+    shapes = np.array([[800, 1333], [750, 1200]], np.int32)
+    wb, ws, wc, wv, wr, wn = oracle_lib.fast_rcnn_inference(boxes, scores, idx, (N, R), shapes, 0.05, 0.5, topk,
+                                                            agnostic_nms)
+    inst = SparseBoxList(T(idx, cuda), BoxList(T(prop, cuda)), (N, R))
+    inst.set_tracking('image_shape', T(shapes, cuda))
+    res, kept = fast_rcnn_inference(T(boxes, cuda), T(scores, cuda), inst, 0.05, 0.5, topk, agnostic_nms)
+    assert np.array_equal(res.get_field('is_valid').cpu().numpy(), wv)
+    assert np.array_equal(res.get_field('pred_classes').cpu().numpy(), wc)
+    assert res.get_field('pred_classes').dtype == torch.int64
+    assert np.array_equal(res.get_field('scores').cpu().numpy(), ws)
+    assert np.array_equal(res.boxes.cpu().numpy(), wb)
+    assert np.array_equal(kept.cpu().numpy(), wr)
+
+
+# ------------------------------------------------------------------ RetinaNet
+def test_retinanet_inference(cuda, oracle_lib):
+    rng = np.random.default_rng(21)
+    N, K = 2, 12
+    anchors = syn.retinanet_anchors(padded_hw=(256, 320))
+    cls = [(rng.standard_normal((N, a.shape[0], K)) * 1.5 - 2.5).astype(np.float32) for a in anchors]
+    dl = [(rng.standard_normal((N, a.shape[0], 4)) * 0.3).astype(np.float32) for a in anchors]
+    wb, ws, wc, wv, wn = oracle_lib.retinanet_inference(cls, dl, anchors, K, 300, 0.05, 0.5, 100)
+    head = RetinaNetInference(num_classes=K, topk_candidates=300)
+    res = head.inference([T(x, cuda) for x in cls], [T(x, cuda) for x in dl], [T(a, cuda) for a in anchors])
+    assert np.array_equal(res.get_field('is_valid').cpu().numpy(), wv)
+    assert np.array_equal(res.get_field('pred_classes').cpu().numpy(), wc)
+    assert res.get_field('pred_classes').dtype == torch.int32
+    assert np.array_equal(res.get_field('scores').cpu().numpy(), ws)
+    assert np.array_equal(res.boxes.cpu().numpy(), wb)
+    assert wn.sum() > 0
+
+
+# ------------------------------------------------------------------ Matrix NMS
+@pytest.mark.parametrize("kernel", ["gaussian", "linear"])
+def test_matrix_nms(cuda, oracle_lib, kernel):
+    masks, classes, scores = syn.solo_masks(120, hw=(50, 84), num_classes=6, seed=7)
+    want = oracle_lib.matrix_nms(masks, classes, scores, None, kernel, 2.0)
+    got = matrix_nms(T(masks, cuda), T(classes, cuda), T(scores, cuda), kernel=kernel, sigma=2.0).cpu().numpy()
+    assert np.array_equal(got, want, equal_nan=True)
+    sm = masks.reshape(120, -1).sum(1)
+    got2 = matrix_nms(T(masks, cuda), T(classes, cuda), T(scores, cuda), sum_masks=T(sm, cuda), kernel=kernel).cpu().numpy()
+    assert np.array_equal(got2, want, equal_nan=True)
+    # batched launch == per-image launches
+    m2, c2, s2 = syn.solo_masks(120, hw=(50, 84), num_classes=6, seed=8)
+    gb = matrix_nms(T(np.stack([masks, m2]), cuda), T(np.stack([classes, c2]), cuda), T(np.stack([scores, s2]), cuda),
+                    kernel=kernel).cpu().numpy()
+    assert np.array_equal(gb[0], want, equal_nan=True)
+    assert np.array_equal(gb[1], oracle_lib.matrix_nms(m2, c2, s2, None, kernel, 2.0), equal_nan=True)
+    with pytest.raises(NotImplementedError):
+        matrix_nms(T(masks, cuda), T(classes, cuda), T(scores, cuda), kernel="cosine")
