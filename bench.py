@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of BASELINE.json on the Mask R-CNN R50-FPN batch-16 config.
+
+One STEP = one pass of the post-backbone hot path over one batch of 16 synthetic 800x1333 images
+(BASELINE.json configs[1]; training-time RPN settings 2000 pre / 1000 post):
+    RPN proposal stage   (top-k 2000/level -> fused decode+clip -> NMS 0.7 -> per-image top-1000)
+    box ROIAlign 7x7     (16,000 ROIs over P2..P5, C=256, fp32)
+    Fast R-CNN post      (decode 80 classes -> clip -> score>0.05 -> class-offset NMS 0.5 -> top-100)
+    mask ROIAlign 14x14  (the 1,600 detections)
+Every rank of an N-GPU run processes its own batch of 16 images (images are independent: weak scaling,
+no data-path collective).  `value` = ROIs pooled by all ranks / max-over-ranks step time.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMAGES_PER_RANK = 16
+ROIS_PER_IMAGE = 1000
+DETS_PER_IMAGE = 100
+PRE_NMS, POST_NMS, RPN_THR = 2000, 1000, 0.7
+NUM_CLASSES = 80
+SCORE_THR, NMS_THR = 0.05, 0.5
+CHANNELS = 256
+METRIC = "ROIAlign ROIs/s + NMS boxes/s (Mask R-CNN R50-FPN batch-16 post-backbone path)"
+WORKLOAD = ("configs[1]: Mask R-CNN R50-FPN, 16 synthetic 800x1333 images/GPU: RPN 2000 pre/1000 post NMS 0.7, "
+            "box ROIAlign 7x7 on 16000 ROIs, Fast R-CNN per-class NMS, mask ROIAlign 14x14 on 1600 dets")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------- synthetic inputs (host, numpy)
+def make_host_inputs(n_images, seed_offset=0):
+    from detectron2_tensorflow_b200.utils import synthetic as syn
+    anchors = syn.rpn_anchors()
+    logits, deltas = syn.rpn_inputs(n_images, seed=2 + seed_offset, variant="gaussian", anchors=anchors)
+    feats = syn.fpn_features(n_images, CHANNELS, seed=0 + seed_offset)
+    scores, cls_deltas = syn.fast_rcnn_inputs(n_images, ROIS_PER_IMAGE, NUM_CLASSES, seed=5 + seed_offset)
+    cls_deltas = (cls_deltas.reshape(-1, NUM_CLASSES, 4) * 0.5).reshape(-1, NUM_CLASSES * 4).astype(np.float32)
+    return dict(anchors=anchors, logits=logits, deltas=deltas, feats=feats, scores=scores, cls_deltas=cls_deltas,
+                shapes=syn.image_shapes(n_images))
+
+
+def algorithmic_bytes_box_pool(n_images):
+    """output write + compulsory feature read (each pixel once, never more than gathered) + boxes."""
+    from detectron2_tensorflow_b200.utils import synthetic as syn
+    M = n_images * ROIS_PER_IMAGE
+    feat = sum(n_images * h * w * CHANNELS * 4 for h, w in (syn.level_hw(s) for s in syn.FPN_STRIDES))
+    gathered = M * 7 * 7 * 4 * CHANNELS * 4
+    return M * 7 * 7 * CHANNELS * 4 + min(feat, gathered) + M * 24
+
+
+# --------------------------------------------------------------------------- the step through the public API
+class HotPath(object):
+    """The reference-facing operators wired as GeneralizedRCNN.inference wires them (rcnn.py:92-144)."""
+
+    def __init__(self, n_images, dev=None):
+        import torch
+        from detectron2_tensorflow_b200.modeling import Box2BoxTransform, ROIPooler
+        self.torch = torch
+        self.n = n_images
+        self.rpn_tf = Box2BoxTransform((1.0, 1.0, 1.0, 1.0))
+        self.box_tf = Box2BoxTransform((10.0, 10.0, 5.0, 5.0))
+        scales = [1 / 4., 1 / 8., 1 / 16., 1 / 32.]
+        self.box_pooler = ROIPooler(7, scales, 0, "ROIAlignV2")
+        self.mask_pooler = ROIPooler(14, scales, 0, "ROIAlignV2")
+        # static instance grids (every slot of the padded dense outputs): no tf.where-style host sync
+        img = np.repeat(np.arange(n_images, dtype=np.int64), ROIS_PER_IMAGE)
+        slot = np.tile(np.arange(ROIS_PER_IMAGE, dtype=np.int64), n_images)
+        self.roi_idx = torch.from_numpy(np.stack([img, slot], 1))
+        img = np.repeat(np.arange(n_images, dtype=np.int64), DETS_PER_IMAGE)
+        slot = np.tile(np.arange(DETS_PER_IMAGE, dtype=np.int64), n_images)
+        self.det_idx = torch.from_numpy(np.stack([img, slot], 1))
+        if dev is not None:
+            self.roi_idx = self.roi_idx.to(dev)
+            self.det_idx = self.det_idx.to(dev)
+
+    def step(self, x, events=None):
+        """x: dict of torch tensors (all on the device, or all on the host).  Returns the outputs dict."""
+        from detectron2_tensorflow_b200.modeling import RPNOutputs, fast_rcnn_inference
+        from detectron2_tensorflow_b200.structures import BoxList, ImageList, SparseBoxList
+        torch = self.torch
+        n = self.n
+
+        def mark(i):
+            if events is not None:
+                events[i].record()
+        mark(0)
+        outs = RPNOutputs(self.rpn_tf, ImageList(None, x["shapes"]), x["logits"], x["deltas"], x["anchors"])
+        props = outs.find_top_proposals(RPN_THR, PRE_NMS, POST_NMS, 0.0)
+        mark(1)
+        inst = SparseBoxList(self.roi_idx, BoxList(props.boxes.reshape(-1, 4)), (n, ROIS_PER_IMAGE))
+        inst.set_tracking("image_shape", x["shapes"])
+        box_feats = self.box_pooler(x["feats"], inst)
+        mark(2)
+        boxes = self.box_tf.apply_deltas(x["cls_deltas"], inst.data.boxes)
+        dets, _ = fast_rcnn_inference(boxes, x["scores"], inst, SCORE_THR, NMS_THR, DETS_PER_IMAGE, False)
+        mark(3)
+        dinst = SparseBoxList(self.det_idx, BoxList(dets.boxes.reshape(-1, 4)), (n, DETS_PER_IMAGE))
+        mask_feats = self.mask_pooler(x["feats"], dinst)
+        mark(4)
+        return dict(proposals=props, box_feats=box_feats, dets=dets, mask_feats=mask_feats)
+
+
+def to_torch(host, dev=None, pin=False):
+    import torch
+    out = {}
+    for k, v in host.items():
+        def conv(a):
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            if dev is not None:
+                return t.to(dev)
+            return t.pin_memory() if pin else t
+        out[k] = [conv(a) for a in v] if isinstance(v, list) else conv(v)
+    return out
+
+
+def nbytes(obj):
+    import torch
+    if isinstance(obj, torch.Tensor):
+        return obj.numel() * obj.element_size()
+    if isinstance(obj, (list, tuple)):
+        return sum(nbytes(o) for o in obj)
+    if isinstance(obj, dict):
+        return sum(nbytes(o) for o in obj.values())
+    if hasattr(obj, "data") and isinstance(obj.data, dict):
+        return sum(nbytes(o) for o in obj.data.values())
+    return 0
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons DURING the timed region (NVML every ~2 ms; nvidia-smi fallback)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = False
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(i):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip() != ""]
+            if i < len(ids) and ids[i].strip().isdigit():
+                return int(ids[i])
+        return i
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        bits = int(get(self.h))
+        for bit, name in self.REASONS.items():
+            if bits & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        o = subprocess.check_output(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                     "--format=csv,noheader,nounits"], timeout=5).decode().strip()
+        f = [x.strip() for x in o.split(",")]
+        self.sm.append(float(f[0]))
+        self.max_mhz = float(f[1])
+        for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[2:6]):
+            if v == "Active":
+                self.reasons.add(name)
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
+
+
+# --------------------------------------------------------------------------- CPU arm (oracle = port of the reference's TF CPU path)
+def cpu_step(host, n_images):
+    """The same step on the CPU oracle for the first `n_images` images, following the reference's own
+    data movement (decode ALL anchors, per-level pad/crop/unpermute).  Returns (rois, nms_boxes_in)."""
+    import oracle
+    sl = slice(0, n_images)
+    props = [oracle.rpn_predict_proposals(d[sl], a) for d, a in zip(host["deltas"], host["anchors"])]
+    pb, pl, pv, pn = oracle.find_top_rpn_proposals(props, [x[sl] for x in host["logits"]], host["shapes"][sl], RPN_THR,
+                                                   PRE_NMS, POST_NMS, 0.0)
+    M = n_images * ROIS_PER_IMAGE
+    idx = np.stack([np.repeat(np.arange(n_images), ROIS_PER_IMAGE), np.tile(np.arange(ROIS_PER_IMAGE), n_images)], 1)
+    boxes = pb.reshape(-1, 4)
+    scales = [1 / 4., 1 / 8., 1 / 16., 1 / 32.]
+    feats = [f[sl] for f in host["feats"]]
+    box_feats, _ = oracle.roi_pooler(feats, scales, boxes, idx[:, 0], (7, 7), 0)
+    pred = oracle.apply_deltas(host["cls_deltas"][:M], boxes, (10., 10., 5., 5.))
+    db, ds, dc, dv, dr, dn = oracle.fast_rcnn_inference(pred, host["scores"][:M], idx, (n_images, ROIS_PER_IMAGE),
+                                                        host["shapes"][sl], SCORE_THR, NMS_THR, DETS_PER_IMAGE, False)
+    didx = np.repeat(np.arange(n_images), DETS_PER_IMAGE)
+    mask_feats, _ = oracle.roi_pooler(feats, scales, db.reshape(-1, 4), didx, (14, 14), 0)
+    return dict(proposals=(pb, pl, pv), box_feats=box_feats, dets=(db, ds, dc, dv), mask_feats=mask_feats)
+
+
+def time_cpu(host, n_images, steps, warmup):
+    import oracle
+    oracle.build()
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        cpu_step(host, n_images)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            ts.append(dt)
+    rois = n_images * (ROIS_PER_IMAGE + DETS_PER_IMAGE)
+    return rois / float(np.mean(ts)), float(np.mean(ts)), oracle.max_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_img = 2
+    host = make_host_inputs(n_img)
+    steps, warmup = max(min(args.steps, 20), 1), max(min(args.warmup, 2), 1)  # bounded: each step ~0.3-1 s of CPU
+    v, sec, cores = time_cpu(host, n_img, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "ROIs/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{n_img} of the 16 images per step"},
+        "cpu_baseline": {"value": v, "unit": "ROIs/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_img} images/step x {steps} steps, OpenMP over all host threads; oracle/ = C "
+                                   "restatement of the reference's TF-CPU path (TensorFlow is not installable here)"},
+        "e2e": {"value": v, "unit": "ROIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from detectron2_tensorflow_b200 import _native as nv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nv.lib()
+
+    n = IMAGES_PER_RANK
+    host = make_host_inputs(n, seed_offset=0)
+    x = to_torch(host, dev=dev)
+    hp = HotPath(n, dev)
+    K, W = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for _ in range(W):
+        out = hp.step(x)
+    barrier()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = nv.kernel_launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(K):
+        out = hp.step(x, evs[s])
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = nv.kernel_launch_count() - l0
+    clocks = sampler.summary()
+    dev_ms = evs[0][0].elapsed_time(evs[-1][4])  # first event of step 0 -> last event of step K-1
+    stage = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in evs])  # rpn, boxpool, frcnn, maskpool
+    st = stage.mean(0)
+    if world > 1:
+        t = torch.tensor([dev_ms, wall * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms = float(t[0]), float(t[1])
+    else:
+        wall_ms = wall * 1e3
+    ms_per_step = dev_ms / K  # CUDA events on the launching stream, max over ranks
+    rois_rank = n * (ROIS_PER_IMAGE + DETS_PER_IMAGE)
+    value = rois_rank * world / (ms_per_step * 1e-3)
+
+    # NMS bookkeeping: boxes entering NMS (RPN segments + Fast R-CNN candidates), counted by the kernels
+    from detectron2_tensorflow_b200.modeling.proposal_generator import rpn_outputs as ro
+    r = ro._rpn_call([t_.reshape(n, -1) for t_ in x["logits"]], None, x["deltas"], x["anchors"], x["shapes"], RPN_THR,
+                     PRE_NMS, POST_NMS, 0.0, count_nms_in=True)
+    rpn_nms_in = int(r.get_tracking("nms_boxes_in").item())
+    cand = int((x["scores"][:, :-1] > SCORE_THR).sum().item())
+
+    hbm_peak, peak_src = peaks()
+    alg = algorithmic_bytes_box_pool(n)
+    ach = alg / (st[1] * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "ROIs/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "images_per_gpu": n, "rois_per_step_per_gpu": rois_rank,
+                   "cache": "inputs larger than L2 (1.46 GB features + 0.8 GB outputs per step vs 126 MB L2)",
+                   "sharding": "images by batch index, no collective"},
+        "wall_ms_per_step": wall_ms / K,
+        "stages_ms": {"rpn_proposals": st[0], "box_roi_align_7x7": st[1], "fast_rcnn_post": st[2],
+                      "mask_roi_align_14x14": st[3]},
+        "roi_align": {"rois_per_s": rois_rank * world / ((st[1] + st[3]) * 1e-3), "unit": "ROIs/s"},
+        "nms": {"boxes_per_s": (rpn_nms_in + cand) * world / ((st[0] + st[2]) * 1e-3), "unit": "boxes/s",
+                "boxes_in_per_step_per_gpu": rpn_nms_in + cand,
+                "note": "boxes entering NMS / time of the full proposal + Fast R-CNN post stages"},
+        "roofline": {"kernel": "roi_align_kernel<float,float,2> (box pooler 7x7, 16000 ROIs)", "bound": "hbm",
+                     "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                     "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+
+    # ---- end-to-end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    hx = to_torch(host, dev=None, pin=True)
+    hp_h = HotPath(n, None)
+    for _ in range(2):
+        ho = hp_h.step(hx)
+    barrier()
+    Ke = max(2, min(K, 5))
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        ho = hp_h.step(hx)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    h2d = nbytes(hx["feats"]) * 2 + nbytes(hx["logits"]) + nbytes(hx["deltas"]) + nbytes(hx["anchors"]) + \
+        nbytes(hx["scores"]) + nbytes(hx["cls_deltas"]) + 3 * nbytes(hx["shapes"])
+    d2h = nbytes(ho["proposals"]) + nbytes(ho["box_feats"]) + nbytes(ho["dets"]) + nbytes(ho["mask_feats"])
+    line["e2e"] = {"value": rois_rank * world / (e2e_s / Ke), "unit": "ROIs/s", "ms_per_step": e2e_s / Ke * 1e3,
+                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": Ke,
+                   "note": "host tensors in (pinned), host tensors out; feature maps are uploaded by each pooler call"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
+    if world == 1 and not args.no_cpu:
+        v, sec, cores = time_cpu(host, 2, 2, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "ROIs/s", "cores": cores, "kind": "port",
+                                "sample": "first 2 of the 16 images, 2 timed steps after 1 warm-up, OpenMP all threads",
+                                "ms_per_step": sec * 1e3}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="d2b200", choices=["d2b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -92,7 +92,7 @@ OPS = {
     "retinanet_postprocess": RetinanetParams,
     "matrix_nms": MatrixNmsParams,
 }
-EXPORTS = ["d2b_version", "d2b_status_string", "d2b_last_error"] + \
+EXPORTS = ["d2b_version", "d2b_status_string", "d2b_last_error", "d2b_kernel_launch_count"] + \
           [f"d2b_{op}{sfx}" for op in OPS for sfx in ("", "_workspace_bytes")]
 
 
@@ -116,6 +116,7 @@ def lib():
         L.d2b_status_string.restype = C.c_char_p
         L.d2b_status_string.argtypes = [C.c_int]
         L.d2b_last_error.restype = C.c_char_p
+        L.d2b_kernel_launch_count.restype = C.c_uint64
         _lib = L
     return _lib
 
@@ -135,6 +136,21 @@ def _bind(op):
         w.argtypes = [C.POINTER(st)]
         _bound.add(op)
     return L
+
+
+def kernel_launch_count():
+    """CUDA kernels launched by libd2b200 in this process."""
+    return int(lib().d2b_kernel_launch_count())
+
+
+def to_host(t):
+    """Device->host through the caching pinned-host allocator (one async copy + stream sync)."""
+    if not t.is_cuda:
+        return t
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return out
 
 
 def ptr(t):

@@ -11,7 +11,11 @@ void set_last_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 }  // namespace d2b
+
+extern "C" uint64_t d2b_kernel_launch_count(void) { return __atomic_load_n(&d2b::g_launches, __ATOMIC_RELAXED); }
 
 extern "C" int d2b_version(void) { return 100; /* 0.1.0 */ }
 

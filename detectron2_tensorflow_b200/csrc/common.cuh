@@ -11,6 +11,7 @@
 namespace d2b {
 
 void set_last_error(const char* fmt, ...);
+void count_launch();  // every kernel launch of the library bumps d2b_kernel_launch_count()
 
 #define D2B_REQUIRE(cond, ...)              \
   do {                                      \
@@ -32,6 +33,7 @@ void set_last_error(const char* fmt, ...);
 
 #define D2B_LAUNCH_CHECK()                                                               \
   do {                                                                                   \
+    ::d2b::count_launch();                                                               \
     cudaError_t _e = cudaGetLastError();                                                 \
     if (_e != cudaSuccess) {                                                             \
       ::d2b::set_last_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),  \

@@ -66,7 +66,7 @@ def _roi_align_call(features, scales, boxes, batch_idx, bidx_stride, output_size
     p.level_assignments = nv.ptr(levels)
     nv.call("roi_align_multilevel", p, dev)
     if host_out:
-        out = out.cpu()
+        out = nv.to_host(out)
     if want_levels:
         return out, counts, levels
     return out

@@ -32,7 +32,7 @@ def batch_nms(boxes, scores, max_output_size, axis=0, iou_threshold=0.5, scope=N
     p.keep, p.num_keep = keep.data_ptr(), num.data_ptr()
     nv.call("batched_nms", p, dev)
     if host:
-        return keep.cpu(), num.cpu()
+        return nv.to_host(keep), nv.to_host(num)
     return keep, num
 
 
@@ -81,4 +81,4 @@ def matrix_nms(masks, classes, scores, sum_masks=None, kernel="gaussian", sigma=
     nv.call("matrix_nms", p, dev)
     if not batched:
         out = out[0]
-    return out.cpu() if host else out
+    return nv.to_host(out) if host else out

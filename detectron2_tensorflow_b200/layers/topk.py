@@ -24,5 +24,5 @@ def segmented_top_k(rows_per_level, k, sigmoid=False, k_limits=None):
     p.out_values, p.out_indices, p.out_counts = vals.data_ptr(), idx.data_ptr(), cnt.data_ptr()
     nv.call("segmented_topk", p, dev)
     if host:
-        return vals.cpu(), idx.cpu(), cnt.cpu()
+        return nv.to_host(vals), nv.to_host(idx), nv.to_host(cnt)
     return vals, idx, cnt

@@ -43,4 +43,4 @@ class Box2BoxTransform(object):
         p.out = out.data_ptr()
         nv.call("apply_deltas", p, dev)
         out = out.reshape(d.shape)
-        return out.cpu() if host else out
+        return nv.to_host(out) if host else out

@@ -33,7 +33,7 @@ def assign_boxes_to_levels(boxlist, min_level, max_level, canonical_box_size, ca
     _, _, levels = _roi_align_call(dummy, [2.0 ** -(min_level + l) for l in range(L)], b, bidx, 1, (1, 1), 0, True,
                                    True, min_level=min_level, canonical_box_size=canonical_box_size,
                                    canonical_level=canonical_level, want_levels=True)
-    return levels.cpu() if host else levels
+    return nv.to_host(levels) if host else levels
 
 
 class ROIPooler(Layer):

@@ -50,7 +50,7 @@ def _rpn_call(logits, proposals, deltas, anchors, image_shapes, nms_thresh, pre_
     p.out_nms_boxes_in = nv.ptr(nms_in)
     nv.call("rpn_proposals", p, dev)
     if host:
-        out_boxes, out_logits, out_valid = out_boxes.cpu(), out_logits.cpu(), out_valid.cpu()
+        out_boxes, out_logits, out_valid = nv.to_host(out_boxes), nv.to_host(out_logits), nv.to_host(out_valid)
     results = BoxList(out_boxes)
     results.add_field("objectness_logits", out_logits)
     results.add_field("is_valid", out_valid)

@@ -49,7 +49,7 @@ def fast_rcnn_inference(boxes, scores, proposals, score_thresh, nms_thresh, topk
     p.out_nms_boxes_in = None
     nv.call("fast_rcnn_postprocess", p, dev)
     if host:
-        ob, os_, oc, ov, oroi = ob.cpu(), os_.cpu(), oc.cpu(), ov.cpu(), oroi.cpu()
+        ob, os_, oc, ov, oroi = nv.to_host(ob), nv.to_host(os_), nv.to_host(oc), nv.to_host(ov), nv.to_host(oroi)
     result = BoxList(ob)
     result.add_field('scores', os_)
     result.add_field('pred_classes', oc)

@@ -57,7 +57,7 @@ class RetinaNetInference(object):
         p.out_nms_boxes_in = None
         nv.call("retinanet_postprocess", p, dev)
         if host:
-            ob, os_, oc, ov = ob.cpu(), os_.cpu(), oc.cpu(), ov.cpu()
+            ob, os_, oc, ov = nv.to_host(ob), nv.to_host(os_), nv.to_host(oc), nv.to_host(ov)
         result = BoxList(ob)
         result.add_field('scores', os_)
         result.add_field('pred_classes', oc)

@@ -57,6 +57,8 @@ D2B_API int d2b_version(void);
 D2B_API const char* d2b_status_string(int status);
 /* thread-local detail of the last non-zero status returned on this thread */
 D2B_API const char* d2b_last_error(void);
+/* number of CUDA kernels this library has launched in the process (monotonic; bench bookkeeping) */
+D2B_API uint64_t d2b_kernel_launch_count(void);
 
 /* ------------------------------------------------------------------------
  * Multi-level ROIAlign == ROIPooler.call          lib/modeling/poolers.py:134-180

@@ -1,0 +1,98 @@
+"""CPU: libd2b200.so builds for sm_100a, loads, and exports every symbol include/d2b200.h declares.
+No compute is launched (there is no GPU here); argument validation paths that return before any CUDA
+call are exercised through the C-ABI."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from detectron2_tensorflow_b200 import build, _native
+    build.build()
+    return _native.lib()
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "d2b200.h")).read()
+    return sorted(set(re.findall(r"D2B_API\s+[\w\s\*]+?\b(d2b_\w+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    from detectron2_tensorflow_b200 import _native
+    syms = _declared_symbols()
+    assert len(syms) == 4 + 2 * len(_native.OPS)
+    assert sorted(_native.EXPORTS) == syms
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert lib.d2b_version() >= 100
+    assert lib.d2b_status_string(0) == b"ok"
+    assert b"invalid" in lib.d2b_status_string(-1)
+
+
+def test_struct_layout_matches_header(lib, tmp_path):
+    """sizeof of every ctypes params struct equals the C compiler's sizeof of the header struct."""
+    from detectron2_tensorflow_b200 import _native
+    names = {"roi_align_multilevel": "d2b_roi_align_params", "apply_deltas": "d2b_apply_deltas_params",
+             "segmented_topk": "d2b_segmented_topk_params", "batched_nms": "d2b_batched_nms_params",
+             "rpn_proposals": "d2b_rpn_proposals_params", "fast_rcnn_postprocess": "d2b_fast_rcnn_params",
+             "retinanet_postprocess": "d2b_retinanet_params", "matrix_nms": "d2b_matrix_nms_params"}
+    prog = '#include <stdio.h>\n#include "d2b200.h"\nint main(){' + "".join(
+        f'printf("{op} %zu\\n", sizeof({st}));' for op, st in names.items()) + "return 0;}"
+    src = tmp_path / "sz.c"
+    src.write_text(prog)
+    exe = tmp_path / "sz"
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    sizes = dict(zip(out[0::2], map(int, out[1::2])))
+    for op, st in _native.OPS.items():
+        assert C.sizeof(st) == sizes[op], op
+
+
+def test_argument_validation_without_gpu(lib):
+    """EINVAL paths return before touching CUDA (reference: ValueError / assert / NotImplementedError)."""
+    from detectron2_tensorflow_b200 import _native as nv
+    p = nv.RoiAlignParams()
+    p.num_levels = 0
+    nv._bind("roi_align_multilevel")
+    assert lib.d2b_roi_align_multilevel(C.byref(p), None, 0, None) == -1
+    assert b"num_levels" in lib.d2b_last_error()
+    p.num_levels, p.num_images, p.channels, p.output_h, p.output_w = 1, 1, 6, 7, 7
+    assert lib.d2b_roi_align_multilevel(C.byref(p), None, 0, None) == -1  # channels % 4
+    m = nv.MatrixNmsParams()
+    m.kernel = 5
+    nv._bind("matrix_nms")
+    assert lib.d2b_matrix_nms(C.byref(m), None, 0, None) == -1
+    assert b"not implemented" in lib.d2b_last_error()
+    r = nv.RpnProposalsParams()
+    r.num_levels, r.pre_nms_topk, r.post_nms_topk = 1, 0, 10
+    nv._bind("rpn_proposals")
+    assert lib.d2b_rpn_proposals(C.byref(r), None, 0, None) == -1
+    # workspace queries are pure host arithmetic
+    t = nv.SegmentedTopkParams()
+    t.num_groups, t.rows_per_group, t.k = 2, 4, 1000
+    t.row_len[0], t.row_len[1] = 5000, 800
+    nv._bind("segmented_topk")
+    assert lib.d2b_segmented_topk_workspace_bytes(C.byref(t)) > 8 * 1024 * 8
+
+
+def test_no_cpu_fallback_in_product():
+    """The product package must not import the oracle or fall back to CPU compute."""
+    pkg = os.path.join(ROOT, "detectron2_tensorflow_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                s = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in s and "from oracle" not in s and "liboracle" not in s, f
+    import torch
+    if not torch.cuda.is_available():
+        from detectron2_tensorflow_b200 import _native as nv
+        from detectron2_tensorflow_b200.layers import ROIAlign
+        with pytest.raises(nv.D2BError):
+            ROIAlign((7, 7), 0.25, 0)(torch.zeros(1, 8, 8, 4), torch.zeros(1, 4), torch.zeros(1, dtype=torch.int32))
