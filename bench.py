@@ -360,6 +360,10 @@ def run_gpu(args):
         "clocks": clocks,
     }
 
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps(line))
+        return
     # ---- end-to-end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
     hx = to_torch(host, dev=None, pin=True)
     hp_h = HotPath(n, None)
@@ -402,6 +406,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="d2b200", choices=["d2b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

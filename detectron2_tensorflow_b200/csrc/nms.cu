@@ -5,10 +5,10 @@
 // Two exact formulations, chosen per call:
 //  A. bitmask (RPN-sized segments, large cap): all (segment, 64-row block) CTAs
 //     compute the upper-triangular IoU>thr matrix as 64-bit words in parallel
-//     (phase 1, spread over every SM); one warp per segment then sweeps 64 rows at
+//     (phase 1, spread over every SM); one CTA per segment then sweeps 64 rows at
 //     a time: the diagonal 64x64 tile is resolved serially from shared memory,
-//     the surviving rows are OR-ed into a per-lane "removed" word set, and the
-//     sweep stops at the cap (phase 2).
+//     the surviving rows are OR-ed by all warps into a shared "removed" word set,
+//     and the sweep stops at the cap (phase 2).
 //  B. capped lazy sweep (huge candidate lists, small cap: Fast R-CNN / RetinaNet):
 //     one CTA per segment keeps the selected boxes in shared memory and, per
 //     64-candidate block, tests candidates against the kept list, resolves the
@@ -25,9 +25,43 @@ typedef unsigned long long u64;
 // ------------------------------------------------------------------ A: bitmask
 constexpr int kMaskThreads = 256;
 
+// Canonical box (min/max of the stored corners) + area, as the TF kernel derives them per pair.
+// Degenerate boxes (area <= 0) can neither suppress nor be suppressed (IoU := 0): they are replaced
+// by an empty sentinel whose intersection with anything is exactly 0.
+struct CBox { float ymin, xmin, ymax, xmax, area; };
+__device__ __forceinline__ CBox canon(const float4 b, bool live) {
+  CBox c;
+  c.ymin = fminf(b.x, b.z); c.xmin = fminf(b.y, b.w);
+  c.ymax = fmaxf(b.x, b.z); c.xmax = fmaxf(b.y, b.w);
+  c.area = (c.ymax - c.ymin) * (c.xmax - c.xmin);
+  if (!live || !(c.area > 0.0f)) {
+    const float inf = __int_as_float(0x7f800000);
+    c.ymin = inf; c.xmin = inf; c.ymax = -inf; c.xmax = -inf; c.area = 0.0f;
+  }
+  return c;
+}
+
+// inter / (area_a + area_b - inter) > thr, decided without the division whenever the comparison is
+// not within 1e-6 relative of the threshold (the division result differs from the real quotient by
+// at most 2^-24 relative, so outside that band the outcome is certain); exact division otherwise.
+__device__ __forceinline__ bool iou_gt(float inter, float area_a, float area_b, float thr) {
+  float u = area_a + area_b;
+  u = u - inter;
+  const float q = thr * u;
+  if (u > 1e-30f && q > 1e-30f && u < 1e30f) {
+    if (inter > q * 1.000001f) return true;
+    if (inter < q * 0.999999f) return false;
+  }
+  return inter / u > thr;
+}
+
 // grid (row_blocks, S).  mask[seg][i][w] bit c: box (w*64+c) is suppressed by box i (only j > i).
+// 256 threads = 4 groups of 64; group q walks column blocks rb+q, rb+q+4, ... with the 64 column
+// boxes staged (canonicalised, with area) in shared memory.
 __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* boxes, const int32_t* counts, int n,
                                                                  int W, float thr, u64* mask) {
+  __shared__ float4 s_box[4][64];
+  __shared__ float s_area[4][64];
   const int seg = blockIdx.y, rb = blockIdx.x;
   const int cnt = counts ? min(counts[seg], n) : n;
   if (rb * 64 >= cnt) return;
@@ -35,81 +69,103 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* bo
   const int r = threadIdx.x & 63, q = threadIdx.x >> 6;
   const int i = rb * 64 + r;
   const bool live = i < cnt;
-  const float4 bi = live ? b[i] : make_float4(0, 0, 0, 0);
+  const CBox bi = canon(live ? b[i] : make_float4(0, 0, 0, 0), live);
   u64* mrow = mask + ((size_t)seg * W * 64 + i) * W;
   const int nb = (cnt + 63) >> 6;
   for (int cb = rb + q; cb < nb; cb += kMaskThreads / 64) {
-    u64 bits = 0;
     const int j0 = cb * 64;
-    const int jn = min(64, cnt - j0);
-    for (int c = 0; c < jn; ++c) {
-      const int j = j0 + c;
-      const float4 bj = __ldg(b + j);  // warp-uniform address: one broadcast transaction
-      if (j > i && d2b_iou(bi, bj) > thr) bits |= (1ull << c);
+    {
+      const int j = j0 + r;
+      const CBox c = canon(j < cnt ? __ldg(b + j) : make_float4(0, 0, 0, 0), j < cnt);
+      s_box[q][r] = make_float4(c.ymin, c.xmin, c.ymax, c.xmax);
+      s_area[q][r] = c.area;
+    }
+    asm volatile("bar.sync %0, 64;" ::"r"(q + 1));
+    u64 bits = 0;
+    const int c0 = (cb == rb) ? r + 1 : 0;  // only j > i
+#pragma unroll 4
+    for (int c = c0; c < 64; ++c) {
+      const float4 bj = s_box[q][c];
+      const float ih = fmaxf(fminf(bi.ymax, bj.z) - fmaxf(bi.ymin, bj.x), 0.0f);
+      const float iw = fmaxf(fminf(bi.xmax, bj.w) - fmaxf(bi.xmin, bj.y), 0.0f);
+      const float inter = ih * iw;
+      if (inter > 0.0f && iou_gt(inter, s_area[q][c], bi.area, thr)) bits |= (1ull << c);
     }
     if (live) mrow[cb] = bits;
+    asm volatile("bar.sync %0, 64;" ::"r"(q + 1));
   }
 }
 
-// One warp per segment.  WPL = removed-words per lane (W <= 32*WPL).
-template <int WPL>
-__global__ void __launch_bounds__(32) nms_sweep_kernel(const int32_t* counts, int n, int W, int max_out,
-                                                        const u64* mask, int32_t* keep, int32_t* num_keep) {
-  __shared__ u64 diag[64];
-  const int seg = blockIdx.x, lane = threadIdx.x;
+// One CTA (8 warps) per segment.  The removed-set lives in shared memory (W words).  Per 64-row block:
+// thread 0 resolves the diagonal tile serially from registers-prefetched shared memory; then all 256
+// threads OR the kept rows into the removed-set, rows spread over thread groups so the global loads of
+// one block are all in flight at once.  Stops at the cap.
+constexpr int kSweepThreads = 256;
+__global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const int32_t* counts, int n, int W, int max_out,
+                                                                   const u64* mask, int32_t* keep,
+                                                                   int32_t* num_keep) {
+  extern __shared__ u64 s_removed[];  // [W]
+  __shared__ u64 s_diag[2][64];
+  __shared__ int s_list[64];
+  __shared__ int s_nk;
+  const int seg = blockIdx.x, tid = threadIdx.x;
   const int cnt = counts ? min(counts[seg], n) : n;
   const u64* m = mask + (size_t)seg * W * 64 * W;
   int32_t* kp = keep + (size_t)seg * max_out;
-  u64 removed[WPL];
-#pragma unroll
-  for (int s = 0; s < WPL; ++s) removed[s] = 0;
-  int kept = 0;
+  for (int w = tid; w < W; w += kSweepThreads) s_removed[w] = 0;
+  int kept = 0;  // replicated in every thread
   const int nb = (cnt + 63) >> 6;
-  for (int b = 0; b < nb && kept < max_out; ++b) {
-    // removed word b lives in lane (b & 31), slot (b >> 5)
-    u64 rem = 0;
-#pragma unroll
-    for (int s = 0; s < WPL; ++s)
-      if ((b >> 5) == s) rem = removed[s];
-    rem = __shfl_sync(0xffffffffu, rem, b & 31);
+  if (tid < 64 && nb > 0) s_diag[0][tid] = tid < cnt ? m[(size_t)tid * W] : 0ull;
+  __syncthreads();
+  // thread layout of the OR phase: words across, kept rows down
+  const int Wp = W < kSweepThreads ? W : kSweepThreads;  // words handled per pass
+  const int groups = kSweepThreads / Wp;                 // row groups (>= 1)
+  const int wl = tid % Wp, rg = tid / Wp;
+  for (int b = 0; b < nb; ++b) {
+    const int kept0 = kept;
+    if (kept0 >= max_out) break;
     const int rows = min(64, cnt - b * 64);
-    if (rows < 64) rem |= ~0ull << rows;
-    // diagonal tile -> shared memory
-    for (int t = lane; t < 64; t += 32) diag[t] = t < rows ? m[((size_t)b * 64 + t) * W + b] : 0ull;
-    __syncwarp();
-    u64 keepm = 0;
-    if (lane == 0) {
-      int left = max_out - kept;
-      for (int t = 0; t < rows && left > 0; ++t) {
-        if (!((rem >> t) & 1ull)) {
-          keepm |= 1ull << t;
-          rem |= diag[t];
-          --left;
+    // prefetch the next diagonal tile while this one is resolved
+    u64 next_diag = 0;
+    if (tid < 64 && b + 1 < nb) {
+      const int i = (b + 1) * 64 + tid;
+      next_diag = i < cnt ? m[(size_t)i * W + (b + 1)] : 0ull;
+    }
+    if (tid == 0) {
+      u64 rem = s_removed[b];
+      if (rows < 64) rem |= ~0ull << rows;
+      const u64* d = s_diag[b & 1];
+      int k = 0, left = max_out - kept0;
+#pragma unroll 8
+      for (int t = 0; t < 64; ++t) {
+        const u64 dt = d[t];
+        if (!((rem >> t) & 1ull) && k < left) {
+          s_list[k] = t;
+          kp[kept0 + k] = b * 64 + t;
+          ++k;
+          rem |= dt;
+        }
+      }
+      s_nk = k;
+    }
+    if (tid < 64) s_diag[(b + 1) & 1][tid] = next_diag;
+    __syncthreads();
+    const int nk = s_nk;
+    kept += nk;
+    if (rg < groups) {
+      for (int w0 = b + 1; w0 < W; w0 += Wp) {
+        const int w = w0 + wl;
+        if (w < W) {
+          u64 acc = 0;
+          for (int x = rg; x < nk; x += groups) acc |= __ldg(m + ((size_t)b * 64 + s_list[x]) * W + w);
+          if (acc) atomicOr(&s_removed[w], acc);
         }
       }
     }
-    keepm = __shfl_sync(0xffffffffu, keepm, 0);
-    __syncwarp();
-    // emit kept positions in order
-    const unsigned lo = (unsigned)keepm, hi = (unsigned)(keepm >> 32);
-    if ((lo >> lane) & 1u) kp[kept + __popc(lo & ((1u << lane) - 1u))] = b * 64 + lane;
-    if ((hi >> lane) & 1u) kp[kept + __popc(lo) + __popc(hi & ((1u << lane) - 1u))] = b * 64 + 32 + lane;
-    kept += __popcll(keepm);
-    // OR the kept rows into the removed set (words beyond b only matter)
-    u64 km = keepm;
-    while (km) {
-      const int t = __ffsll((long long)km) - 1;
-      km &= km - 1;
-      const u64* row = m + ((size_t)b * 64 + t) * W;
-#pragma unroll
-      for (int s = 0; s < WPL; ++s) {
-        const int w = s * 32 + lane;
-        if (w > b && w < W) removed[s] |= __ldg(row + w);
-      }
-    }
+    __syncthreads();
   }
-  for (int j = kept + lane; j < max_out; j += 32) kp[j] = -1;
-  if (lane == 0) num_keep[seg] = kept;
+  for (int j = kept + tid; j < max_out; j += kSweepThreads) kp[j] = -1;
+  if (tid == 0) num_keep[seg] = kept;
 }
 
 // ------------------------------------------------------------------ B: capped lazy sweep
@@ -218,13 +274,7 @@ int nms_sorted(const float* boxes, const int32_t* counts, int S, int n, int max_
   u64* mask = static_cast<u64*>(ws);
   nms_mask_kernel<<<dim3(W, S), kMaskThreads, 0, st>>>(b4, counts, n, W, thr, mask);
   D2B_LAUNCH_CHECK();
-  const int wpl = (W + 31) / 32;
-  if (wpl <= 1) nms_sweep_kernel<1><<<S, 32, 0, st>>>(counts, n, W, max_out, mask, keep, num_keep);
-  else if (wpl <= 2) nms_sweep_kernel<2><<<S, 32, 0, st>>>(counts, n, W, max_out, mask, keep, num_keep);
-  else if (wpl <= 4) nms_sweep_kernel<4><<<S, 32, 0, st>>>(counts, n, W, max_out, mask, keep, num_keep);
-  else if (wpl <= 8) nms_sweep_kernel<8><<<S, 32, 0, st>>>(counts, n, W, max_out, mask, keep, num_keep);
-  else if (wpl <= 16) nms_sweep_kernel<16><<<S, 32, 0, st>>>(counts, n, W, max_out, mask, keep, num_keep);
-  else nms_sweep_kernel<32><<<S, 32, 0, st>>>(counts, n, W, max_out, mask, keep, num_keep);
+  nms_sweep_kernel<<<S, kSweepThreads, (size_t)W * sizeof(u64), st>>>(counts, n, W, max_out, mask, keep, num_keep);
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }

@@ -102,55 +102,67 @@ __global__ void __launch_bounds__(kRpnThreads) rpn_decode_kernel(RpnArgs a, cons
   }
 }
 
-// one CTA per image: concat the per-level NMS survivors (level-major) and key them for the final top-k
-__global__ void __launch_bounds__(256) rpn_merge_prep_kernel(RpnArgs a, const float* seg_scores, const int32_t* keep,
-                                                             const int32_t* num_keep, u64* keys2, int32_t* off,
-                                                             int32_t* total) {
+// One CTA per image: the final per-image top-k (rpn_outputs.py:101-114) as a rank computation.
+// Each level's NMS survivors are already ordered (score desc, index asc), so the position of a
+// survivor in the sorted concatenation is its own position plus, per other level, the number of
+// survivors that precede it -- a binary search over that level's keys.  Ties across levels go to the
+// lower concat index, i.e. the earlier level (TF top_k rule).  No sort, no intermediate buffers.
+constexpr int kMergeThreads = 1024;
+__global__ void __launch_bounds__(kMergeThreads) rpn_merge_rank_kernel(
+    RpnArgs a, const float4* seg_boxes, const float* seg_scores, const int32_t* keep, const int32_t* num_keep,
+    uint32_t* gkeys, float4* out_boxes, float* out_logits, uint8_t* out_valid, int32_t* out_num) {
   const int n = blockIdx.x;
   __shared__ int s_off[D2B_MAX_LEVELS + 1];
   if (threadIdx.x == 0) {
     int acc = 0;
     for (int l = 0; l < a.L; ++l) { s_off[l] = acc; acc += num_keep[n * a.L + l]; }
     s_off[a.L] = acc;
-    for (int l = 0; l <= a.L; ++l) off[n * (D2B_MAX_LEVELS + 1) + l] = s_off[l];
-    total[n] = acc;
   }
   __syncthreads();
-  for (int l = 0; l < a.L; ++l) {
+  const int total = s_off[a.L];
+  const int kk = min(total, a.post);  // :105
+  uint32_t* gk = gkeys + (size_t)n * a.P2;
+  for (int ci = threadIdx.x; ci < total; ci += kMergeThreads) {
+    int l = 0;
+    while (l + 1 < a.L && ci >= s_off[l + 1]) ++l;
     const int row = n * a.L + l;
-    const int cnt = s_off[l + 1] - s_off[l];
-    for (int q = threadIdx.x; q < cnt; q += blockDim.x) {
-      const int pos = keep[(size_t)row * a.post + q];
-      keys2[(size_t)n * a.P2 + s_off[l] + q] = make_key(seg_scores[(size_t)row * a.k + pos], (unsigned)(s_off[l] + q));
+    const int pos = keep[(size_t)row * a.post + (ci - s_off[l])];
+    gk[ci] = float_to_key(seg_scores[(size_t)row * a.k + pos]);
+  }
+  __syncthreads();
+  for (int ci = threadIdx.x; ci < total; ci += kMergeThreads) {
+    int l = 0;
+    while (l + 1 < a.L && ci >= s_off[l + 1]) ++l;
+    const uint32_t key = gk[ci];
+    int rank = ci - s_off[l];
+    for (int l2 = 0; l2 < a.L; ++l2) {
+      if (l2 == l) continue;
+      const uint32_t* kl = gk + s_off[l2];
+      int lo = 0, hi = s_off[l2 + 1] - s_off[l2];
+      while (lo < hi) {  // first position whose element does NOT precede (key, ci)
+        const int mid = (lo + hi) >> 1;
+        const uint32_t ke = kl[mid];
+        const bool before = (l2 < l) ? (ke >= key) : (ke > key);
+        if (before) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < a.post) {
+      const int row = n * a.L + l;
+      const int pos = keep[(size_t)row * a.post + (ci - s_off[l])];
+      const size_t o = (size_t)n * a.post + rank;
+      out_boxes[o] = seg_boxes[(size_t)row * a.k + pos];
+      out_logits[o] = seg_scores[(size_t)row * a.k + pos];
+      out_valid[o] = 1;
     }
   }
-}
-
-__global__ void rpn_emit_kernel(RpnArgs a, const u64* keys2, const int32_t* off, const int32_t* total,
-                                const float4* seg_boxes, const float* seg_scores, const int32_t* keep,
-                                float4* out_boxes, float* out_logits, uint8_t* out_valid, int32_t* out_num) {
-  const int n = blockIdx.y;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.post) return;
-  const int kk = min(total[n], a.post);  // rpn_outputs.py:105
-  if (j == 0 && out_num) out_num[n] = kk;
-  float4 box = make_float4(0, 0, 0, 0);
-  float logit = 0.0f;
-  uint8_t valid = 0;
-  if (j < kk) {
-    const int ci = (int)key_index(keys2[(size_t)n * a.P2 + j]);
-    const int32_t* o = off + n * (D2B_MAX_LEVELS + 1);
-    int l = 0;
-    while (l + 1 < a.L && ci >= o[l + 1]) ++l;
-    const int row = n * a.L + l;
-    const int pos = keep[(size_t)row * a.post + (ci - o[l])];
-    box = seg_boxes[(size_t)row * a.k + pos];
-    logit = seg_scores[(size_t)row * a.k + pos];
-    valid = 1;
+  for (int j = kk + threadIdx.x; j < a.post; j += kMergeThreads) {  // zero padding :111-114
+    const size_t o = (size_t)n * a.post + j;
+    out_boxes[o] = make_float4(0, 0, 0, 0);
+    out_logits[o] = 0.0f;
+    out_valid[o] = 0;
   }
-  out_boxes[(size_t)n * a.post + j] = box;
-  out_logits[(size_t)n * a.post + j] = logit;
-  out_valid[(size_t)n * a.post + j] = valid;
+  if (threadIdx.x == 0 && out_num) out_num[n] = kk;
 }
 
 struct RpnPlan {
@@ -159,7 +171,7 @@ struct RpnPlan {
   int rows;
   size_t bytes;
   // offsets
-  size_t o_topk, o_keys, o_kr, o_boxes, o_scores, o_count, o_keep, o_nkeep, o_nms, o_keys2, o_off, o_total;
+  size_t o_topk, o_keys, o_kr, o_boxes, o_scores, o_count, o_keep, o_nkeep, o_nms, o_keys2;
 };
 
 int rpn_plan(const d2b_rpn_proposals_params* p, RpnPlan& pl) {
@@ -212,9 +224,7 @@ int rpn_plan(const d2b_rpn_proposals_params* p, RpnPlan& pl) {
   pl.o_keep = o; o += ws_slice(rows * a.post * sizeof(int32_t));
   pl.o_nkeep = o; o += ws_slice(rows * sizeof(int32_t));
   pl.o_nms = o; o += nms_sorted_workspace_bytes(pl.rows, a.k, a.post);
-  pl.o_keys2 = o; o += ws_slice(N * a.P2 * sizeof(u64));
-  pl.o_off = o; o += ws_slice(N * (D2B_MAX_LEVELS + 1) * sizeof(int32_t));
-  pl.o_total = o; o += ws_slice(N * sizeof(int32_t));
+  pl.o_keys2 = o; o += ws_slice(N * a.P2 * sizeof(uint32_t));
   pl.bytes = o;
   return D2B_OK;
 }
@@ -304,22 +314,51 @@ __global__ void frcnn_prep_kernel(const float4* boxes, const float* scores, cons
                                   int N, int Rmax, int Kb, int K, const int32_t* shapes, float thresh, int P,
                                   u64* keys, int32_t* count, int32_t* slot_map, int* max_coord_bits) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= M * K) return;
-  const long long i = t / K;
-  const int k = (int)(t - i * K);
-  const long long n = indices[2 * i], r = indices[2 * i + 1];
-  if (n < 0 || n >= N || r < 0 || r >= Rmax) return;
-  if (k == 0) slot_map[n * Rmax + r] = (int32_t)i;
-  if (k < Kb) {
-    const float h = (float)shapes[2 * n], w = (float)shapes[2 * n + 1];
-    const float4 b = d2b_clip(__ldg(boxes + i * Kb + k), h, w);
-    const float m = fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w));  // >= 0 after clipping
-    atomicMax(max_coord_bits + n, __float_as_int(m));
+  const int lane = threadIdx.x & 31;
+  long long n = -1, r = 0, i = 0;
+  int k = 0;
+  if (t < M * K) {
+    i = t / K;
+    k = (int)(t - i * K);
+    n = indices[2 * i];
+    r = indices[2 * i + 1];
+    if (n < 0 || n >= N || r < 0 || r >= Rmax) n = -1;
   }
-  const float s = __ldg(scores + i * (K + 1) + k);
-  if (s > thresh) {
-    const int slot = atomicAdd(count + n, 1);
-    if (slot < P) keys[(size_t)n * P + slot] = make_key(s, (unsigned)(k * Rmax + (int)r));
+  int mbits = 0;  // clipped coordinates are >= 0, so their int bit patterns order like the floats
+  bool cand = false;
+  float s = 0.0f;
+  if (n >= 0) {
+    if (k == 0) slot_map[n * Rmax + r] = (int32_t)i;
+    if (k < Kb) {
+      const float h = (float)shapes[2 * n], w = (float)shapes[2 * n + 1];
+      const float4 b = d2b_clip(__ldg(boxes + i * Kb + k), h, w);
+      mbits = __float_as_int(fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+    }
+    s = __ldg(scores + i * (K + 1) + k);
+    cand = s > thresh;
+  }
+  // warp-aggregated atomics when the whole warp belongs to one image (the common, image-major case)
+  const long long n0 = __shfl_sync(0xffffffffu, n, 0);
+  const bool uniform = __all_sync(0xffffffffu, n == n0) && n0 >= 0;
+  if (uniform) {
+    const int wm = __reduce_max_sync(0xffffffffu, mbits);
+    const unsigned cm = __ballot_sync(0xffffffffu, cand);
+    int base = 0;
+    if (lane == 0) {
+      if (wm > 0) atomicMax(max_coord_bits + n0, wm);
+      if (cm) base = atomicAdd(count + n0, __popc(cm));
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (cand) {
+      const int slot = base + __popc(cm & ((1u << lane) - 1u));
+      if (slot < P) keys[(size_t)n0 * P + slot] = make_key(s, (unsigned)(k * Rmax + (int)r));
+    }
+  } else if (n >= 0) {
+    if (mbits > 0) atomicMax(max_coord_bits + n, mbits);
+    if (cand) {
+      const int slot = atomicAdd(count + n, 1);
+      if (slot < P) keys[(size_t)n * P + slot] = make_key(s, (unsigned)(k * Rmax + (int)r));
+    }
   }
 }
 
@@ -421,9 +460,7 @@ extern "C" int d2b_rpn_proposals(const d2b_rpn_proposals_params* p, void* worksp
   int32_t* seg_count = reinterpret_cast<int32_t*>(ws + pl.o_count);
   int32_t* keep = reinterpret_cast<int32_t*>(ws + pl.o_keep);
   int32_t* nkeep = reinterpret_cast<int32_t*>(ws + pl.o_nkeep);
-  u64* keys2 = reinterpret_cast<u64*>(ws + pl.o_keys2);
-  int32_t* off = reinterpret_cast<int32_t*>(ws + pl.o_off);
-  int32_t* total = reinterpret_cast<int32_t*>(ws + pl.o_total);
+  uint32_t* keys2 = reinterpret_cast<uint32_t*>(ws + pl.o_keys2);
   u64* nms_in = reinterpret_cast<u64*>(p->out_nms_boxes_in);
   if (nms_in) D2B_CUDA(cudaMemsetAsync(nms_in, 0, sizeof(u64), st));
 
@@ -434,13 +471,9 @@ extern "C" int d2b_rpn_proposals(const d2b_rpn_proposals_params* p, void* worksp
   rc = nms_sorted(reinterpret_cast<const float*>(seg_boxes), seg_count, pl.rows, a.k, a.post, p->nms_thresh, keep,
                   nkeep, ws + pl.o_nms, st);  // :90-94
   if (rc != D2B_OK) return rc;
-  rpn_merge_prep_kernel<<<a.N, 256, 0, st>>>(a, seg_scores, keep, nkeep, keys2, off, total);
-  D2B_LAUNCH_CHECK();
-  rc = sort_segments_desc(keys2, a.N, a.P2, total, st);  // :105-107
-  if (rc != D2B_OK) return rc;
-  rpn_emit_kernel<<<dim3((a.post + 255) / 256, a.N), 256, 0, st>>>(
-      a, keys2, off, total, seg_boxes, seg_scores, keep, reinterpret_cast<float4*>(p->out_boxes), p->out_logits,
-      p->out_valid, p->out_num_valid);
+  rpn_merge_rank_kernel<<<a.N, kMergeThreads, 0, st>>>(a, seg_boxes, seg_scores, keep, nkeep, keys2,
+                                                        reinterpret_cast<float4*>(p->out_boxes), p->out_logits,
+                                                        p->out_valid, p->out_num_valid);  // :101-114
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }

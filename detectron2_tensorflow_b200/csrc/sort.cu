@@ -3,98 +3,87 @@
 // Used to order top-k winners / NMS candidates by (score desc, index asc): the
 // composite key is (order-preserving score key << 32) | ~index, so one unsigned
 // 64-bit descending sort realises TF's tie rule.
-// Segments up to kTile keys are sorted by one CTA in shared memory; longer ones
-// alternate global compare-exchange steps (stride >= kTile) with shared-memory
-// tails, the classic tiled bitonic schedule.  Launch count depends only on P.
+//
+// Two launches whatever the size: (1) every tile of up to kTile keys is fully sorted in
+// shared memory; (2) for segments longer than one tile a single CTA per segment finishes the
+// bitonic network in global memory.  The EFFECTIVE length of a segment (next power of two of its
+// live count, read on the device) bounds the work: tiles and stages beyond it are skipped, so a
+// padded capacity (e.g. Rmax*K candidates of Fast R-CNN) costs nothing when few entries are live.
 #include "kernels.cuh"
 
 namespace d2b {
 namespace {
 
-constexpr int kTile = 4096;     // keys per CTA tile (32 KB of shared memory)
-constexpr int kSortThreads = 512;
+constexpr int kTile = 8192;  // keys per CTA tile (64 KB of shared memory)
+constexpr int kSortThreads = 1024;
 
 typedef unsigned long long u64;
 
-__device__ __forceinline__ void cmpx(u64& a, u64& b, bool desc) {
-  const bool sw = desc ? (a < b) : (a > b);
-  if (sw) { u64 t = a; a = b; b = t; }
+__device__ __forceinline__ int eff_len(const int32_t* seg_len, int seg, int P) {
+  if (!seg_len) return P;
+  int c = seg_len[seg];
+  if (c < 1) c = 1;
+  if (c > P) c = P;
+  int e = 1;
+  while (e < c) e <<= 1;
+  return e;
 }
 
-// Sort stages k = 2 .. min(P, tile) entirely in shared memory (k_from == 2), or run the
-// tail substages j = tile/2 .. 1 of a single outer stage `k_only` (k_from == 0).
-__global__ void __launch_bounds__(kSortThreads) sort_local(u64* keys, int P, int tile, const int32_t* seg_len,
-                                                            int k_only, int mask_dead) {
+__global__ void __launch_bounds__(kSortThreads) sort_local(u64* keys, int P, int tile, const int32_t* seg_len) {
   extern __shared__ u64 s[];
   const int seg = blockIdx.y;
   const int t0 = blockIdx.x * tile;
+  const int Pe = eff_len(seg_len, seg, P);
+  if (t0 >= Pe) return;
+  const int tl = tile < Pe ? tile : Pe;  // live part of this tile (a power of two)
   u64* g = keys + (size_t)seg * P + t0;
   const int live = seg_len ? seg_len[seg] : P;
-  for (int i = threadIdx.x; i < tile; i += kSortThreads) {
-    u64 v = g[i];
-    if (mask_dead && t0 + i >= live) v = 0ull;
-    s[i] = v;
-  }
+  for (int i = threadIdx.x; i < tl; i += kSortThreads) s[i] = (t0 + i < live) ? g[i] : 0ull;
   __syncthreads();
-  if (k_only == 0) {
-    for (int k = 2; k <= tile; k <<= 1)
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int p = threadIdx.x; p < tile / 2; p += kSortThreads) {
-          const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-          const bool desc = (((t0 + i) & k) == 0);
-          cmpx(s[i], s[i | j], desc);
-        }
-        __syncthreads();
-      }
-  } else {
-    const int k = k_only;
-    for (int j = tile >> 1; j > 0; j >>= 1) {
-      for (int p = threadIdx.x; p < tile / 2; p += kSortThreads) {
+  for (int k = 2; k <= tl; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int p = threadIdx.x; p < tl / 2; p += kSortThreads) {
         const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
         const bool desc = (((t0 + i) & k) == 0);
-        cmpx(s[i], s[i | j], desc);
+        const u64 a = s[i], b = s[i | j];
+        if (desc ? (a < b) : (a > b)) { s[i] = b; s[i | j] = a; }
       }
       __syncthreads();
     }
-  }
-  for (int i = threadIdx.x; i < tile; i += kSortThreads) g[i] = s[i];
+  for (int i = threadIdx.x; i < tl; i += kSortThreads) g[i] = s[i];
 }
 
-// One global compare-exchange step (stride j >= kTile) of outer stage k.
-__global__ void sort_global_step(u64* keys, int P, int k, int j) {
-  const int seg = blockIdx.y;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P / 2) return;
-  const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+// Segments longer than one tile: one CTA finishes stages k = 2*tile .. Pe in global memory.
+__global__ void __launch_bounds__(kSortThreads) sort_big(u64* keys, int P, int tile, const int32_t* seg_len) {
+  const int seg = blockIdx.x;
+  const int Pe = eff_len(seg_len, seg, P);
+  if (Pe <= tile) return;
   u64* g = keys + (size_t)seg * P;
-  u64 a = g[i], b = g[i | j];
-  const bool desc = ((i & k) == 0);
-  const bool sw = desc ? (a < b) : (a > b);
-  if (sw) { g[i] = b; g[i | j] = a; }
+  for (int k = tile << 1; k <= Pe; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int p = threadIdx.x; p < Pe / 2; p += kSortThreads) {
+        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+        const bool desc = ((i & k) == 0);
+        const u64 a = g[i], b = g[i | j];
+        if (desc ? (a < b) : (a > b)) { g[i] = b; g[i | j] = a; }
+      }
+      __syncthreads();
+    }
 }
 
 }  // namespace
 
 int sort_segments_desc(unsigned long long* keys, int S, int P, const int32_t* seg_len, cudaStream_t st) {
-  if (S <= 0 || P <= 1) {
-    if (S > 0 && P == 1 && seg_len) {
-      // single-slot segments: nothing to order; dead slots are ignored by consumers via counts
-    }
-    return D2B_OK;
-  }
+  if (S <= 0 || P <= 1) return D2B_OK;
   D2B_REQUIRE((P & (P - 1)) == 0, "sort: P=%d is not a power of two", P);
   const int tile = P < kTile ? P : kTile;
-  const dim3 grid(P / tile, S);
   const size_t smem = (size_t)tile * sizeof(u64);
-  sort_local<<<grid, kSortThreads, smem, st>>>(keys, P, tile, seg_len, 0, seg_len != nullptr);
+  if (smem > 48 * 1024)
+    D2B_CUDA(cudaFuncSetAttribute(sort_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sort_local<<<dim3(P / tile, S), kSortThreads, smem, st>>>(keys, P, tile, seg_len);
   D2B_LAUNCH_CHECK();
-  for (int k = tile << 1; k <= P; k <<= 1) {
-    for (int j = k >> 1; j >= tile; j >>= 1) {
-      const dim3 g2((P / 2 + 255) / 256, S);
-      sort_global_step<<<g2, 256, 0, st>>>(keys, P, k, j);
-      D2B_LAUNCH_CHECK();
-    }
-    sort_local<<<grid, kSortThreads, smem, st>>>(keys, P, tile, nullptr, k, 0);
+  if (P > tile) {
+    sort_big<<<S, kSortThreads, 0, st>>>(keys, P, tile, seg_len);
     D2B_LAUNCH_CHECK();
   }
   return D2B_OK;

@@ -1,0 +1,293 @@
+// d2b_tf_ops.cc -- TensorFlow custom-op shim over the C-ABI of libd2b200.so.
+//
+// NOT COMPILED IN THIS REPOSITORY'S BUILD: TensorFlow is not installable in the build image
+// (no wheel, no network).  It is the glue a maintainer of the reference compiles against their
+// own TensorFlow:
+//   g++ -std=c++14 -shared -fPIC d2b_tf_ops.cc -o libd2b200_tf.so \
+//       $(python -c 'import tensorflow as tf; print(" ".join(tf.sysconfig.get_compile_flags()))') \
+//       -I<repo>/include -L<repo>/detectron2_tensorflow_b200/lib -ld2b200 \
+//       $(python -c 'import tensorflow as tf; print(" ".join(tf.sysconfig.get_link_flags()))')
+// and loads with tf.load_op_library("libd2b200_tf.so").  Every OpKernel only
+// validates shapes, allocates outputs and a temp workspace, fetches the CUDA stream and calls ONE
+// C function; all logic lives behind include/d2b200.h.
+#include "tensorflow/core/framework/op.h"
+#include "tensorflow/core/framework/op_kernel.h"
+#include "tensorflow/core/framework/shape_inference.h"
+
+#define EIGEN_USE_GPU
+#include "tensorflow/core/util/gpu_kernel_helper.h"
+
+#include "d2b200.h"
+
+namespace tf = tensorflow;
+using tf::shape_inference::InferenceContext;
+
+namespace {
+
+cudaStream_t StreamOf(tf::OpKernelContext* ctx) { return ctx->eigen_device<Eigen::GpuDevice>().stream(); }
+
+// Allocates the op's scratch as a temp uint8 tensor and runs `fn(workspace, bytes, stream)`.
+template <typename Params, typename BytesFn, typename RunFn>
+void RunOp(tf::OpKernelContext* ctx, const Params& p, BytesFn bytes_fn, RunFn run_fn) {
+  const size_t bytes = bytes_fn(&p);
+  tf::Tensor ws;
+  OP_REQUIRES_OK(ctx, ctx->allocate_temp(tf::DT_UINT8, tf::TensorShape({static_cast<tf::int64>(bytes ? bytes : 1)}), &ws));
+  const int rc = run_fn(&p, ws.flat<tf::uint8>().data(), bytes, StreamOf(ctx));
+  OP_REQUIRES(ctx, rc == D2B_OK,
+              tf::errors::Internal(d2b_status_string(rc), ": ", d2b_last_error()));
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ D2RoiAlignMultilevel
+// Replaces ROIPooler.call (lib/modeling/poolers.py:134-180).
+REGISTER_OP("D2RoiAlignMultilevel")
+    .Input("features: L * float")  // L NHWC maps
+    .Input("boxes: float")         // [M, 4]
+    .Input("batch_idx: int64")     // [M]
+    .Attr("L: int >= 1")
+    .Attr("output_h: int")
+    .Attr("output_w: int")
+    .Attr("sampling_ratio: int = 0")
+    .Attr("aligned: bool = true")
+    .Attr("scales: list(float)")
+    .Attr("canonical_box_size: int = 224")
+    .Attr("canonical_level: int = 4")
+    .Output("pooled: float")       // [M, output_h, output_w, C]
+    .Output("level_counts: int32")  // [L]
+    .SetShapeFn([](InferenceContext* c) {
+      int L, oh, ow;
+      TF_RETURN_IF_ERROR(c->GetAttr("L", &L));
+      TF_RETURN_IF_ERROR(c->GetAttr("output_h", &oh));
+      TF_RETURN_IF_ERROR(c->GetAttr("output_w", &ow));
+      c->set_output(0, c->MakeShape({c->Dim(c->input(L), 0), oh, ow, c->Dim(c->input(0), 3)}));
+      c->set_output(1, c->MakeShape({L}));
+      return tf::Status::OK();
+    });
+
+class D2RoiAlignMultilevelOp : public tf::OpKernel {
+ public:
+  explicit D2RoiAlignMultilevelOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("L", &L_));
+    OP_REQUIRES_OK(c, c->GetAttr("output_h", &oh_));
+    OP_REQUIRES_OK(c, c->GetAttr("output_w", &ow_));
+    OP_REQUIRES_OK(c, c->GetAttr("sampling_ratio", &sr_));
+    OP_REQUIRES_OK(c, c->GetAttr("aligned", &aligned_));
+    OP_REQUIRES_OK(c, c->GetAttr("scales", &scales_));
+    OP_REQUIRES_OK(c, c->GetAttr("canonical_box_size", &cbs_));
+    OP_REQUIRES_OK(c, c->GetAttr("canonical_level", &cl_));
+    OP_REQUIRES(c, static_cast<int>(scales_.size()) == L_ && L_ <= D2B_MAX_LEVELS,
+                tf::errors::InvalidArgument("len(scales) must equal L <= ", D2B_MAX_LEVELS));
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    const tf::Tensor& boxes = ctx->input(L_);
+    const tf::Tensor& bidx = ctx->input(L_ + 1);
+    OP_REQUIRES(ctx, boxes.dims() == 2 && boxes.dim_size(1) == 4, tf::errors::InvalidArgument("boxes must be [M,4]"));
+    d2b_roi_align_params p = {};
+    for (int l = 0; l < L_; ++l) {
+      const tf::Tensor& f = ctx->input(l);
+      OP_REQUIRES(ctx, f.dims() == 4, tf::errors::InvalidArgument("features must be NHWC"));
+      p.features[l] = f.flat<float>().data();
+      p.height[l] = f.dim_size(1);
+      p.width[l] = f.dim_size(2);
+      p.scale[l] = scales_[l];
+    }
+    p.num_levels = L_;
+    p.num_images = ctx->input(0).dim_size(0);
+    p.channels = ctx->input(0).dim_size(3);
+    p.feature_dtype = D2B_DTYPE_F32;
+    p.boxes = boxes.flat<float>().data();
+    p.batch_idx = bidx.flat<tf::int64>().data();
+    p.batch_idx_is_int64 = 1;
+    p.batch_idx_stride = 1;
+    p.num_rois = boxes.dim_size(0);
+    p.output_h = oh_; p.output_w = ow_; p.sampling_ratio = sr_; p.aligned = aligned_; p.pad_border = 1;
+    p.min_level = static_cast<int>(std::lround(-std::log2(scales_[0])));
+    p.canonical_box_size = cbs_; p.canonical_level = cl_;
+    tf::Tensor* out = nullptr;
+    tf::Tensor* counts = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({p.num_rois, oh_, ow_, p.channels}), &out));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({L_}), &counts));
+    p.out = out->flat<float>().data();
+    p.out_dtype = D2B_DTYPE_F32;
+    p.level_counts = counts->flat<tf::int32>().data();
+    RunOp(ctx, p, d2b_roi_align_multilevel_workspace_bytes, d2b_roi_align_multilevel);
+  }
+
+ private:
+  int L_, oh_, ow_, sr_, cbs_, cl_;
+  bool aligned_;
+  std::vector<float> scales_;
+};
+REGISTER_KERNEL_BUILDER(Name("D2RoiAlignMultilevel").Device(tf::DEVICE_GPU), D2RoiAlignMultilevelOp);
+
+// ------------------------------------------------------------------ D2BatchedNms
+// Replaces tf.map_fn(tf.image.non_max_suppression) (lib/layers/nms.py:6-26).
+REGISTER_OP("D2BatchedNms")
+    .Input("boxes: float")   // [S, n, 4]
+    .Input("scores: float")  // [S, n]
+    .Attr("max_output_size: int")
+    .Attr("iou_threshold: float = 0.5")
+    .Output("keep: int32")      // [S, max_output_size], -1 padded
+    .Output("num_keep: int32")  // [S]
+    .SetShapeFn([](InferenceContext* c) {
+      int mo;
+      TF_RETURN_IF_ERROR(c->GetAttr("max_output_size", &mo));
+      c->set_output(0, c->MakeShape({c->Dim(c->input(0), 0), mo}));
+      c->set_output(1, c->MakeShape({c->Dim(c->input(0), 0)}));
+      return tf::Status::OK();
+    });
+
+class D2BatchedNmsOp : public tf::OpKernel {
+ public:
+  explicit D2BatchedNmsOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("max_output_size", &mo_));
+    OP_REQUIRES_OK(c, c->GetAttr("iou_threshold", &thr_));
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    const tf::Tensor& boxes = ctx->input(0);
+    const tf::Tensor& scores = ctx->input(1);
+    OP_REQUIRES(ctx, boxes.dims() == 3 && scores.dims() == 2, tf::errors::InvalidArgument("ranks must be 3 and 2"));
+    d2b_batched_nms_params p = {};
+    p.boxes = boxes.flat<float>().data();
+    p.scores = scores.flat<float>().data();
+    p.num_segments = boxes.dim_size(0);
+    p.n = boxes.dim_size(1);
+    p.max_output_size = mo_;
+    p.iou_threshold = thr_;
+    tf::Tensor *keep = nullptr, *num = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({p.num_segments, mo_}), &keep));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({p.num_segments}), &num));
+    p.keep = keep->flat<tf::int32>().data();
+    p.num_keep = num->flat<tf::int32>().data();
+    RunOp(ctx, p, d2b_batched_nms_workspace_bytes, d2b_batched_nms);
+  }
+
+ private:
+  int mo_;
+  float thr_;
+};
+REGISTER_KERNEL_BUILDER(Name("D2BatchedNms").Device(tf::DEVICE_GPU), D2BatchedNmsOp);
+
+// ------------------------------------------------------------------ D2RpnProposals
+// Replaces RPNOutputs.predict_proposals + find_top_rpn_proposals (rpn_outputs.py:403-426, 29-132).
+REGISTER_OP("D2RpnProposals")
+    .Input("logits: L * float")   // L x [N, HWA_l]
+    .Input("deltas: L * float")   // L x [N, HWA_l, 4]
+    .Input("anchors: L * float")  // L x [HWA_l, 4]
+    .Input("image_shapes: int32")  // [N, 2] (h, w)
+    .Attr("L: int >= 1")
+    .Attr("pre_nms_topk: int")
+    .Attr("post_nms_topk: int")
+    .Attr("nms_thresh: float = 0.7")
+    .Attr("min_box_side_len: float = 0.0")
+    .Attr("weights: list(float) = [1.0, 1.0, 1.0, 1.0]")
+    .Output("boxes: float")     // [N, post, 4]
+    .Output("logits_out: float")  // [N, post]
+    .Output("is_valid: bool")   // [N, post]
+    .SetShapeFn([](InferenceContext* c) {
+      int post;
+      TF_RETURN_IF_ERROR(c->GetAttr("post_nms_topk", &post));
+      auto n = c->Dim(c->input(0), 0);
+      c->set_output(0, c->MakeShape({n, post, 4}));
+      c->set_output(1, c->MakeShape({n, post}));
+      c->set_output(2, c->MakeShape({n, post}));
+      return tf::Status::OK();
+    });
+
+class D2RpnProposalsOp : public tf::OpKernel {
+ public:
+  explicit D2RpnProposalsOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("L", &L_));
+    OP_REQUIRES_OK(c, c->GetAttr("pre_nms_topk", &pre_));
+    OP_REQUIRES_OK(c, c->GetAttr("post_nms_topk", &post_));
+    OP_REQUIRES_OK(c, c->GetAttr("nms_thresh", &thr_));
+    OP_REQUIRES_OK(c, c->GetAttr("min_box_side_len", &min_len_));
+    OP_REQUIRES_OK(c, c->GetAttr("weights", &w_));
+    OP_REQUIRES(c, L_ <= D2B_MAX_LEVELS && w_.size() == 4, tf::errors::InvalidArgument("bad L / weights"));
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    d2b_rpn_proposals_params p = {};
+    for (int l = 0; l < L_; ++l) {
+      p.logits[l] = ctx->input(l).flat<float>().data();
+      p.deltas[l] = ctx->input(L_ + l).flat<float>().data();
+      p.anchors[l] = ctx->input(2 * L_ + l).flat<float>().data();
+      p.hwa[l] = ctx->input(2 * L_ + l).dim_size(0);
+    }
+    p.num_levels = L_;
+    p.num_images = ctx->input(0).dim_size(0);
+    p.image_shapes = ctx->input(3 * L_).flat<tf::int32>().data();
+    p.nms_thresh = thr_; p.pre_nms_topk = pre_; p.post_nms_topk = post_; p.min_box_side_len = min_len_;
+    for (int i = 0; i < 4; ++i) p.weights[i] = w_[i];
+    p.scale_clamp = 4.135166556742356f;  // log(1000/16), box_regression.py:10
+    tf::Tensor *b = nullptr, *lg = nullptr, *v = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({p.num_images, post_, 4}), &b));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({p.num_images, post_}), &lg));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, tf::TensorShape({p.num_images, post_}), &v));
+    p.out_boxes = b->flat<float>().data();
+    p.out_logits = lg->flat<float>().data();
+    p.out_valid = reinterpret_cast<uint8_t*>(v->flat<bool>().data());
+    RunOp(ctx, p, d2b_rpn_proposals_workspace_bytes, d2b_rpn_proposals);
+  }
+
+ private:
+  int L_, pre_, post_;
+  float thr_, min_len_;
+  std::vector<float> w_;
+};
+REGISTER_KERNEL_BUILDER(Name("D2RpnProposals").Device(tf::DEVICE_GPU).HostMemory("image_shapes"), D2RpnProposalsOp);
+// NOTE: image_shapes is read by the kernels, so a production shim either drops HostMemory above or
+// copies the [N,2] array to the workspace first; kept explicit here because TF places small int32
+// tensors on the host by default.
+
+// ------------------------------------------------------------------ D2MatrixNms
+// Replaces matrix_nms (lib/layers/nms.py:29-83).
+REGISTER_OP("D2MatrixNms")
+    .Input("masks: float")    // [n, H, W]
+    .Input("classes: int64")  // [n]
+    .Input("scores: float")   // [n]
+    .Input("sum_masks: float")  // [n]
+    .Attr("kernel: string = 'gaussian'")
+    .Attr("sigma: float = 2.0")
+    .Output("updated_scores: float")
+    .SetShapeFn([](InferenceContext* c) {
+      c->set_output(0, c->input(2));
+      return tf::Status::OK();
+    });
+
+class D2MatrixNmsOp : public tf::OpKernel {
+ public:
+  explicit D2MatrixNmsOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    std::string k;
+    OP_REQUIRES_OK(c, c->GetAttr("kernel", &k));
+    OP_REQUIRES_OK(c, c->GetAttr("sigma", &sigma_));
+    OP_REQUIRES(c, k == "gaussian" || k == "linear", tf::errors::Unimplemented("NMS kernel ", k, " not implemented yet."));
+    kernel_ = k == "gaussian" ? D2B_MNMS_GAUSSIAN : D2B_MNMS_LINEAR;
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    const tf::Tensor& m = ctx->input(0);
+    OP_REQUIRES(ctx, m.dims() == 3, tf::errors::InvalidArgument("masks must be [n,H,W]"));
+    d2b_matrix_nms_params p = {};
+    p.masks = m.flat<float>().data();
+    p.classes = reinterpret_cast<const int64_t*>(ctx->input(1).flat<tf::int64>().data());
+    p.scores = ctx->input(2).flat<float>().data();
+    p.sum_masks = ctx->input(3).flat<float>().data();
+    p.batch = 1;
+    p.n = m.dim_size(0);
+    p.hw = m.dim_size(1) * m.dim_size(2);
+    p.kernel = kernel_;
+    p.sigma = sigma_;
+    tf::Tensor* out = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, ctx->input(2).shape(), &out));
+    p.out = out->flat<float>().data();
+    RunOp(ctx, p, d2b_matrix_nms_workspace_bytes, d2b_matrix_nms);
+  }
+
+ private:
+  int kernel_;
+  float sigma_;
+};
+REGISTER_KERNEL_BUILDER(Name("D2MatrixNms").Device(tf::DEVICE_GPU), D2MatrixNmsOp);
+
+// D2FastRcnnPostprocess and D2RetinanetPostprocess follow the same pattern over
+// d2b_fast_rcnn_postprocess / d2b_retinanet_postprocess (params structs in d2b200.h).

@@ -28,7 +28,8 @@ typedef unsigned long long u64;
 constexpr int kBins = 2048;
 constexpr int kPasses = 6;
 constexpr int kHistThreads = 256;
-constexpr int kChunk = 16384;  // elements per CTA per pass
+constexpr int kChunk = 4096;   // elements per CTA per pass
+constexpr int kBatch = 8;       // independent loads in flight per thread
 
 __constant__ int c_shift[kPasses] = {53, 42, 32, 21, 10, 0};
 __constant__ int c_bits[kPasses] = {11, 11, 10, 11, 11, 10};
@@ -66,7 +67,7 @@ __device__ __forceinline__ u64 composite(float x, unsigned idx, int transform) {
   return ((u64)float_to_key(x) << 32) | (u64)(0xffffffffu - idx);
 }
 
-__global__ void topk_init(TopkArgs a, int rows) {
+__global__ void topk_init(TopkArgs a, int rows, int32_t* seg_len, int32_t* out_counts) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   const int g = r % a.d.G;
@@ -81,6 +82,8 @@ __global__ void topk_init(TopkArgs a, int rows) {
   else if (kr == a.d.row_len[g]) { s.active = 0; s.threshold = 0ull; }  // take the whole row
   else { s.active = 1; s.threshold = 0ull; }
   a.state[r] = s;
+  seg_len[r] = (int32_t)kr;
+  if (out_counts) out_counts[r] = (int32_t)kr;
 }
 
 __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass) {
@@ -101,11 +104,22 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass) 
   const long long beg = (long long)chunk * kChunk;
   const long long end = beg + kChunk < len ? beg + kChunk : len;
   const int hi_shift = shift + bits;  // bits above the current digit
-#pragma unroll 4
-  for (long long i = beg + threadIdx.x; i < end; i += kHistThreads) {
-    const u64 c = composite(__ldg(x + i), (unsigned)i, a.d.transform);
-    const bool in = (pass == 0) || ((c >> hi_shift) == prefix);
-    if (in) atomicAdd(&sh[(unsigned)(c >> shift) & mask], 1u);
+  for (long long i0 = beg + threadIdx.x; i0 < end; i0 += (long long)kBatch * kHistThreads) {
+    float v[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const long long i = i0 + (long long)u * kHistThreads;
+      v[u] = i < end ? __ldg(x + i) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const long long i = i0 + (long long)u * kHistThreads;
+      if (i < end) {
+        const u64 c = composite(v[u], (unsigned)i, a.d.transform);
+        const bool in = (pass == 0) || ((c >> hi_shift) == prefix);
+        if (in) atomicAdd(&sh[(unsigned)(c >> shift) & mask], 1u);
+      }
+    }
   }
   __syncthreads();
   unsigned* gh = a.hist + ((size_t)row * kPasses + pass) * kBins;
@@ -174,22 +188,31 @@ __global__ void __launch_bounds__(kHistThreads) topk_collect(TopkArgs a, u64* ou
   const long long end = beg + kChunk < len ? beg + kChunk : len;
   u64* out = out_keys + (size_t)row * a.P;
   const int lane = threadIdx.x & 31;
-  for (long long i0 = beg + (threadIdx.x & ~31); i0 < end; i0 += kHistThreads) {
-    const long long i = i0 + lane;
-    u64 c = 0;
-    bool take = false;
-    if (i < end) {
-      c = composite(__ldg(x + i), (unsigned)i, a.d.transform);
-      take = c >= thr;
+  for (long long i0 = beg + (threadIdx.x & ~31); i0 < end; i0 += (long long)kBatch * kHistThreads) {
+    float v[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const long long i = i0 + (long long)u * kHistThreads + lane;
+      v[u] = i < end ? __ldg(x + i) : 0.0f;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, take);
-    if (m) {
-      unsigned base = 0;
-      if (lane == 0) base = atomicAdd(&st->out_count, (unsigned)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (take) {
-        const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
-        if (slot < (unsigned)a.P) out[slot] = c;
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const long long i = i0 + (long long)u * kHistThreads + lane;
+      u64 c = 0;
+      bool take = false;
+      if (i < end) {
+        c = composite(v[u], (unsigned)i, a.d.transform);
+        take = c >= thr;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, take);
+      if (m) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&st->out_count, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (take) {
+          const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
+          if (slot < (unsigned)a.P) out[slot] = c;
+        }
       }
     }
   }
@@ -199,7 +222,6 @@ __global__ void topk_emit(TopkArgs a, const u64* keys, float* out_values, int32_
                           int32_t* out_counts, int rows) {
   const int row = blockIdx.y;
   const unsigned kr = a.state[row].k_r;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && out_counts) out_counts[row] = (int32_t)kr;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.d.k) return;
   float v = 0.0f;
@@ -211,11 +233,6 @@ __global__ void topk_emit(TopkArgs a, const u64* keys, float* out_values, int32_
   }
   if (out_values) out_values[(size_t)row * a.d.k + j] = v;
   if (out_indices) out_indices[(size_t)row * a.d.k + j] = idx;
-}
-
-__global__ void topk_counts(TopkArgs a, int32_t* seg_len, int rows) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < rows) seg_len[r] = (int32_t)a.state[r].k_r;
 }
 
 int fill_args(const TopkDesc& d, TopkArgs& a) {
@@ -262,7 +279,7 @@ int topk_run(const TopkDesc& d, unsigned long long* out_keys, float* out_values,
   a.hist = w.take<unsigned>((size_t)rows * kPasses * kBins);
   int32_t* seg_len = w.take<int32_t>(rows);
   D2B_CUDA(cudaMemsetAsync(a.hist, 0, (size_t)rows * kPasses * kBins * sizeof(unsigned), st));
-  topk_init<<<(rows + 127) / 128, 128, 0, st>>>(a, rows);
+  topk_init<<<(rows + 127) / 128, 128, 0, st>>>(a, rows, seg_len, out_counts);
   D2B_LAUNCH_CHECK();
   for (int p = 0; p < kPasses; ++p) {
     topk_hist<<<ctas, kHistThreads, 0, st>>>(a, p);
@@ -270,11 +287,9 @@ int topk_run(const TopkDesc& d, unsigned long long* out_keys, float* out_values,
   }
   topk_collect<<<ctas, kHistThreads, 0, st>>>(a, out_keys);
   D2B_LAUNCH_CHECK();
-  topk_counts<<<(rows + 127) / 128, 128, 0, st>>>(a, seg_len, rows);
-  D2B_LAUNCH_CHECK();
   int rc = sort_segments_desc(out_keys, rows, a.P, seg_len, st);
   if (rc != D2B_OK) return rc;
-  if (out_values || out_indices || out_counts) {
+  if (out_values || out_indices) {
     const dim3 grid((d.k + 255) / 256, rows);
     topk_emit<<<grid, 256, 0, st>>>(a, out_keys, out_values, out_indices, out_counts, rows);
     D2B_LAUNCH_CHECK();
