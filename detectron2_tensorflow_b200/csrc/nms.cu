@@ -83,86 +83,130 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* bo
     asm volatile("bar.sync %0, 64;" ::"r"(q + 1));
     u64 bits = 0;
     const int c0 = (cb == rb) ? r + 1 : 0;  // only j > i
-#pragma unroll 4
+#pragma unroll 8
     for (int c = c0; c < 64; ++c) {
       const float4 bj = s_box[q][c];
-      const float ih = fmaxf(fminf(bi.ymax, bj.z) - fmaxf(bi.ymin, bj.x), 0.0f);
-      const float iw = fmaxf(fminf(bi.xmax, bj.w) - fmaxf(bi.xmin, bj.y), 0.0f);
-      const float inter = ih * iw;
-      if (inter > 0.0f && iou_gt(inter, s_area[q][c], bi.area, thr)) bits |= (1ull << c);
+      // inter > 0  <=>  the open intervals overlap on both axes (sentinel boxes never do)
+      if (bi.ymax > bj.x && bj.z > bi.ymin && bi.xmax > bj.y && bj.w > bi.xmin) {
+        const float ih = fmaxf(fminf(bi.ymax, bj.z) - fmaxf(bi.ymin, bj.x), 0.0f);
+        const float iw = fmaxf(fminf(bi.xmax, bj.w) - fmaxf(bi.xmin, bj.y), 0.0f);
+        const float inter = ih * iw;
+        if (iou_gt(inter, s_area[q][c], bi.area, thr)) bits |= (1ull << c);
+      }
     }
     if (live) mrow[cb] = bits;
     asm volatile("bar.sync %0, 64;" ::"r"(q + 1));
   }
 }
 
-// One CTA (8 warps) per segment.  The removed-set lives in shared memory (W words).  Per 64-row block:
-// thread 0 resolves the diagonal tile serially from registers-prefetched shared memory; then all 256
-// threads OR the kept rows into the removed-set, rows spread over thread groups so the global loads of
-// one block are all in flight at once.  Stops at the cap.
+// One CTA (8 warps) per segment; the removed-set lives in shared memory (W words).  Per 64-row block b:
+//   thread 0     resolves the diagonal tile: the 64 diagonal words sit in registers and the greedy chain
+//                is 64 fully unrolled test/OR steps (no memory access on the serial path);
+//   warps 0-1    prefetch, a block ahead, the diagonal word and the NEXT word of each of their 64 rows, so
+//                the contribution of block b to removed[b+1] (all the next resolve needs) is a register
+//                select + warp OR right after the resolve;
+//   warps 2-7    OR the kept rows of block b-1 into the remaining words concurrently with the resolve.
+// The sweep stops at the cap.
 constexpr int kSweepThreads = 256;
+constexpr int kOrThreads = kSweepThreads - 64;
 __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const int32_t* counts, int n, int W, int max_out,
                                                                    const u64* mask, int32_t* keep,
                                                                    int32_t* num_keep) {
   extern __shared__ u64 s_removed[];  // [W]
   __shared__ u64 s_diag[2][64];
-  __shared__ int s_list[64];
-  __shared__ int s_nk;
-  const int seg = blockIdx.x, tid = threadIdx.x;
+  __shared__ u64 s_keepm[2];
+  __shared__ int s_list[2][64];
+  const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int cnt = counts ? min(counts[seg], n) : n;
   const u64* m = mask + (size_t)seg * W * 64 * W;
   int32_t* kp = keep + (size_t)seg * max_out;
   for (int w = tid; w < W; w += kSweepThreads) s_removed[w] = 0;
-  int kept = 0;  // replicated in every thread
   const int nb = (cnt + 63) >> 6;
-  if (tid < 64 && nb > 0) s_diag[0][tid] = tid < cnt ? m[(size_t)tid * W] : 0ull;
+  u64 pre_next = 0;  // threads 0..63: word b+1 of row b*64+tid
+  if (tid < 64) {
+    u64 d = 0;
+    if (tid < cnt) {
+      d = m[(size_t)tid * W];
+      if (1 < W) pre_next = m[(size_t)tid * W + 1];
+    }
+    s_diag[0][tid] = d;
+  }
   __syncthreads();
-  // thread layout of the OR phase: words across, kept rows down
-  const int Wp = W < kSweepThreads ? W : kSweepThreads;  // words handled per pass
-  const int groups = kSweepThreads / Wp;                 // row groups (>= 1)
-  const int wl = tid % Wp, rg = tid / Wp;
+  int kept = 0;
   for (int b = 0; b < nb; ++b) {
-    const int kept0 = kept;
-    if (kept0 >= max_out) break;
-    const int rows = min(64, cnt - b * 64);
-    // prefetch the next diagonal tile while this one is resolved
-    u64 next_diag = 0;
-    if (tid < 64 && b + 1 < nb) {
-      const int i = (b + 1) * 64 + tid;
-      next_diag = i < cnt ? m[(size_t)i * W + (b + 1)] : 0ull;
-    }
-    if (tid == 0) {
-      u64 rem = s_removed[b];
-      if (rows < 64) rem |= ~0ull << rows;
-      const u64* d = s_diag[b & 1];
-      int k = 0, left = max_out - kept0;
-#pragma unroll 8
-      for (int t = 0; t < 64; ++t) {
-        const u64 dt = d[t];
-        if (!((rem >> t) & 1ull) && k < left) {
-          s_list[k] = t;
-          kp[kept0 + k] = b * 64 + t;
-          ++k;
-          rem |= dt;
+    const int par = b & 1;
+    u64 nd = 0, nn = 0;
+    if (tid < 64) {
+      if (b + 1 < nb) {  // prefetch for block b+1 (independent of the resolve)
+        const int i = (b + 1) * 64 + tid;
+        if (i < cnt) {
+          nd = m[(size_t)i * W + (b + 1)];
+          if (b + 2 < W) nn = m[(size_t)i * W + (b + 2)];
         }
       }
-      s_nk = k;
-    }
-    if (tid < 64) s_diag[(b + 1) & 1][tid] = next_diag;
-    __syncthreads();
-    const int nk = s_nk;
-    kept += nk;
-    if (rg < groups) {
-      for (int w0 = b + 1; w0 < W; w0 += Wp) {
-        const int w = w0 + wl;
-        if (w < W) {
-          u64 acc = 0;
-          for (int x = rg; x < nk; x += groups) acc |= __ldg(m + ((size_t)b * 64 + s_list[x]) * W + w);
-          if (acc) atomicOr(&s_removed[w], acc);
+      if (tid == 0) {
+        const int rows = min(64, cnt - b * 64);
+        u64 rem = s_removed[b];
+        if (rows < 64) rem |= ~0ull << rows;
+        u64 dd[64];
+#pragma unroll
+        for (int t = 0; t < 64; ++t) dd[t] = s_diag[par][t];
+        asm volatile("" ::: "memory");  // all 64 words in registers before the serial chain starts
+        u64 km = 0;
+#pragma unroll
+        for (int t = 0; t < 64; ++t) {
+          if (!((rem >> t) & 1ull)) {
+            km |= 1ull << t;
+            rem |= dd[t];
+          }
+        }
+        int c = __popcll(km);
+        const int left = max_out - kept;
+        while (c > left) {  // cap reached inside this block: keep only the first `left`
+          km &= ~(1ull << (63 - __clzll((long long)km)));
+          --c;
+        }
+        s_keepm[par] = km;
+      }
+    } else if (b > 0) {
+      // OR the kept rows of block b-1 into words >= b+1 (word b was done right after its resolve)
+      const int t = tid - 64;
+      const u64 pk = s_keepm[par ^ 1];
+      const int nk = __popcll(pk);
+      const int wrem = W - (b + 1);
+      if (wrem > 0 && nk > 0) {
+        const int Wp = wrem < kOrThreads ? wrem : kOrThreads;
+        const int groups = kOrThreads / Wp;
+        const int wl = t % Wp, rg = t / Wp;
+        if (rg < groups) {
+          for (int w = b + 1 + wl; w < W; w += Wp) {
+            u64 acc = 0;
+            for (int x = rg; x < nk; x += groups)
+              acc |= __ldg(m + ((size_t)(b - 1) * 64 + s_list[par ^ 1][x]) * W + w);
+            if (acc) atomicOr(&s_removed[w], acc);
+          }
         }
       }
     }
-    __syncthreads();
+    __syncthreads();  // keep-mask of block b published; OR-rest of block b-1 complete
+    const u64 km = s_keepm[par];
+    if (tid < 64) {
+      const bool mine = (km >> tid) & 1ull;
+      if (mine) {
+        const int rank = __popcll(km & ((1ull << tid) - 1ull));
+        kp[kept + rank] = b * 64 + tid;
+        s_list[par][rank] = tid;
+      }
+      u64 v = mine ? pre_next : 0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && v && b + 1 < W) atomicOr(&s_removed[b + 1], v);
+      s_diag[par ^ 1][tid] = nd;
+      pre_next = nn;
+    }
+    kept += __popcll(km);
+    if (kept >= max_out) break;
+    __syncthreads();  // removed[b+1], diag(b+1) and the kept list of block b are visible
   }
   for (int j = kept + tid; j < max_out; j += kSweepThreads) kp[j] = -1;
   if (tid == 0) num_keep[seg] = kept;

@@ -49,7 +49,7 @@ struct RoiAlignArgs {
 };
 
 struct Tap {   // one crop row (or column) of one ROI
-  int i0, i1;  // clamped un-padded indices of the two neighbours
+  int i0, i1;  // ELEMENT offsets of the two (clamped, un-padded) neighbours inside one image's map
   float w;     // lerp weight toward i1
   int valid;   // 0 => extrapolation (zeros)
 };
@@ -80,7 +80,7 @@ __device__ __forceinline__ int level_of(float y1, float x1, float y2, float x2, 
 // functional.py:128-160 + TF CropAndResize coordinate rule for sample `s` of `cs`
 // along an axis of (padded) extent P; lo/hi are the scaled (+pad) box edges.
 __device__ __forceinline__ Tap make_tap(float lo, float hi, int s, int cs, int P, int pad,
-                                        int dim, int aligned) {
+                                        int dim, int aligned, int stride) {
   float n1, n2;
   if (aligned) {
     float sp = (hi - lo) / (float)cs;
@@ -109,8 +109,8 @@ __device__ __forceinline__ Tap make_tap(float lo, float hi, int s, int cs, int P
   const int i0 = (int)f, i1 = (int)ceilf(in);
   t.w = in - f;
   // padded index p holds un-padded pixel clamp(p - pad, 0, dim-1)  (SYMMETRIC pad of 1)
-  t.i0 = min(max(i0 - pad, 0), dim - 1);
-  t.i1 = min(max(i1 - pad, 0), dim - 1);
+  t.i0 = min(max(i0 - pad, 0), dim - 1) * stride;
+  t.i1 = min(max(i1 - pad, 0), dim - 1) * stride;
   return t;
 }
 
@@ -162,7 +162,7 @@ __device__ __forceinline__ void store_out(__nv_bfloat16* p, const float (&v)[E])
 
 // TIn: feature element type; TOut: output element type; GROUPS: 16-byte groups
 // each lane owns per bin (0 => runtime loop for any channel count).
-template <typename TIn, typename TOut, int GROUPS>
+template <typename TIn, typename TOut, int GROUPS, bool ONE>
 __global__ void __launch_bounds__(kThreads) roi_align_kernel(const RoiAlignArgs a) {
   constexpr int E = Vec<TIn>::kElems;
   __shared__ Tap ty[kMaxSamples];
@@ -184,10 +184,10 @@ __global__ void __launch_bounds__(kThreads) roi_align_kernel(const RoiAlignArgs 
     const float padf = a.pad ? 1.0f : 0.0f;
     if (tid < ch) {
       const float lo = b.x * L.scale + padf, hi = b.z * L.scale + padf;
-      ty[tid] = make_tap(lo, hi, tid, ch, L.H + 2 * a.pad, a.pad, L.H, a.aligned);
+      ty[tid] = make_tap(lo, hi, tid, ch, L.H + 2 * a.pad, a.pad, L.H, a.aligned, L.W * a.C);
     } else if (tid < ch + cw) {
       const float lo = b.y * L.scale + padf, hi = b.w * L.scale + padf;
-      tx[tid - ch] = make_tap(lo, hi, tid - ch, cw, L.W + 2 * a.pad, a.pad, L.W, a.aligned);
+      tx[tid - ch] = make_tap(lo, hi, tid - ch, cw, L.W + 2 * a.pad, a.pad, L.W, a.aligned, a.C);
     }
     if (tid == kThreads - 1) {
       long long img = a.bidx64 ? reinterpret_cast<const long long*>(a.bidx)[roi * a.bidx_stride]
@@ -211,6 +211,50 @@ __global__ void __launch_bounds__(kThreads) roi_align_kernel(const RoiAlignArgs 
   const float cnt = (float)(s1 * s1);
   const int groups_total = C / E;  // 16-byte groups per pixel
 
+  if (ONE && GROUPS > 0) {
+    // sampling_ratio 0/1 (the reference default): one bilinear sample per bin, fully unrolled channel
+    // groups, corner addresses formed once per bin from the precomputed element offsets.
+    for (int bin = warp; bin < a.oh * a.ow; bin += kWarps) {
+      const int oy = bin / a.ow, ox = bin - oy * a.ow;
+      TOut* o = obase + (size_t)bin * C + lane * E;
+      const Tap y = ty[oy];
+      const Tap x = tx[ox];
+      if (y.valid && x.valid && img >= 0) {
+        const TIn* p00 = base + (y.i0 + x.i0) + lane * E;
+        const TIn* p01 = base + (y.i0 + x.i1) + lane * E;
+        const TIn* p10 = base + (y.i1 + x.i0) + lane * E;
+        const TIn* p11 = base + (y.i1 + x.i1) + lane * E;
+        constexpr int G = GROUPS > 0 ? GROUPS : 1;
+        Vec<TIn> tl[G], tr[G], bl[G], br[G];
+#pragma unroll
+        for (int j = 0; j < GROUPS; ++j) {
+          tl[j] = Vec<TIn>::load(p00 + j * 32 * E);
+          tr[j] = Vec<TIn>::load(p01 + j * 32 * E);
+          bl[j] = Vec<TIn>::load(p10 + j * 32 * E);
+          br[j] = Vec<TIn>::load(p11 + j * 32 * E);
+        }
+#pragma unroll
+        for (int j = 0; j < GROUPS; ++j) {
+          float val[E];
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            float t = tr[j].v[e] - tl[j].v[e]; t = t * x.w; t = tl[j].v[e] + t;
+            float bb = br[j].v[e] - bl[j].v[e]; bb = bb * x.w; bb = bl[j].v[e] + bb;
+            float r = bb - t; r = r * y.w; r = t + r;
+            val[e] = r;
+          }
+          store_out<E>(o + j * 32 * E, val);
+        }
+      } else {
+        float val[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) val[e] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < GROUPS; ++j) store_out<E>(o + j * 32 * E, val);
+      }
+    }
+    return;
+  }
   for (int bin = warp; bin < a.oh * a.ow; bin += kWarps) {
     const int oy = bin / a.ow, ox = bin - oy * a.ow;
     TOut* o = obase + (size_t)bin * C;
@@ -225,12 +269,12 @@ __global__ void __launch_bounds__(kThreads) roi_align_kernel(const RoiAlignArgs 
           const Tap x = tx[ox * s1 + dx];
           float val[E];
           if (y.valid && x.valid && img >= 0) {
-            const TIn* r0 = base + (size_t)y.i0 * L.W * C + c;
-            const TIn* r1 = base + (size_t)y.i1 * L.W * C + c;
-            const Vec<TIn> tl = Vec<TIn>::load(r0 + (size_t)x.i0 * C);
-            const Vec<TIn> tr = Vec<TIn>::load(r0 + (size_t)x.i1 * C);
-            const Vec<TIn> bl = Vec<TIn>::load(r1 + (size_t)x.i0 * C);
-            const Vec<TIn> br = Vec<TIn>::load(r1 + (size_t)x.i1 * C);
+            const TIn* r0 = base + y.i0 + c;
+            const TIn* r1 = base + y.i1 + c;
+            const Vec<TIn> tl = Vec<TIn>::load(r0 + x.i0);
+            const Vec<TIn> tr = Vec<TIn>::load(r0 + x.i1);
+            const Vec<TIn> bl = Vec<TIn>::load(r1 + x.i0);
+            const Vec<TIn> br = Vec<TIn>::load(r1 + x.i1);
 #pragma unroll
             for (int e = 0; e < E; ++e) {
               float t = tr.v[e] - tl.v[e]; t = t * x.w; t = tl.v[e] + t;
@@ -271,9 +315,12 @@ int launch(const RoiAlignArgs& a, cudaStream_t st) {
   constexpr int E = Vec<TIn>::kElems;
   const dim3 grid((unsigned)a.M), block(kThreads);
   const int g = a.C / E;
-  if (g == 32) roi_align_kernel<TIn, TOut, 1><<<grid, block, 0, st>>>(a);
-  else if (g == 64) roi_align_kernel<TIn, TOut, 2><<<grid, block, 0, st>>>(a);
-  else roi_align_kernel<TIn, TOut, 0><<<grid, block, 0, st>>>(a);
+  const bool one = a.sr <= 1;
+  if (g == 32 && one) roi_align_kernel<TIn, TOut, 1, true><<<grid, block, 0, st>>>(a);
+  else if (g == 64 && one) roi_align_kernel<TIn, TOut, 2, true><<<grid, block, 0, st>>>(a);
+  else if (g == 32) roi_align_kernel<TIn, TOut, 1, false><<<grid, block, 0, st>>>(a);
+  else if (g == 64) roi_align_kernel<TIn, TOut, 2, false><<<grid, block, 0, st>>>(a);
+  else roi_align_kernel<TIn, TOut, 0, false><<<grid, block, 0, st>>>(a);
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }
@@ -310,6 +357,7 @@ extern "C" int d2b_roi_align_multilevel(const d2b_roi_align_params* p, void* /*w
   RoiAlignArgs a;
   for (int l = 0; l < p->num_levels; ++l) {
     D2B_REQUIRE(p->features[l] != nullptr && p->height[l] > 0 && p->width[l] > 0, "level %d: bad feature map", l);
+    D2B_REQUIRE((long long)p->height[l] * p->width[l] * p->channels < (1ll << 31), "level %d: H*W*C must fit in int32", l);
     a.lv[l].ptr = p->features[l];
     a.lv[l].H = p->height[l];
     a.lv[l].W = p->width[l];
