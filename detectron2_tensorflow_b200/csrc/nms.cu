@@ -56,17 +56,19 @@ __device__ __forceinline__ bool iou_gt(float inter, float area_a, float area_b, 
 }
 
 // grid (row_blocks, S).  mask[seg][i][w] bit c: box (w*64+c) is suppressed by box i (only j > i).
-// 256 threads = 4 groups of 64; group q walks column blocks rb+q, rb+q+4, ... with the 64 column
-// boxes staged (canonicalised, with area) in shared memory.
+// 8 independent warps per CTA: warp = (column group q, row half); it owns 32 rows of the 64-row block
+// and walks column blocks rb+q, rb+q+4, ...  The 64 column boxes of a block are staged (canonicalised,
+// with area) in a warp-private shared-memory slice, so only __syncwarp is needed.
 __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* boxes, const int32_t* counts, int n,
                                                                  int W, float thr, u64* mask) {
-  __shared__ float4 s_box[4][64];
-  __shared__ float s_area[4][64];
+  __shared__ float4 s_box[kMaskThreads / 32][64];
+  __shared__ float s_area[kMaskThreads / 32][64];
   const int seg = blockIdx.y, rb = blockIdx.x;
   const int cnt = counts ? min(counts[seg], n) : n;
   if (rb * 64 >= cnt) return;
   const float4* b = boxes + (size_t)seg * n;
-  const int r = threadIdx.x & 63, q = threadIdx.x >> 6;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = warp >> 1, r = (warp & 1) * 32 + lane;
   const int i = rb * 64 + r;
   const bool live = i < cnt;
   const CBox bi = canon(live ? b[i] : make_float4(0, 0, 0, 0), live);
@@ -74,28 +76,31 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* bo
   const int nb = (cnt + 63) >> 6;
   for (int cb = rb + q; cb < nb; cb += kMaskThreads / 64) {
     const int j0 = cb * 64;
-    {
-      const int j = j0 + r;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = j0 + h * 32 + lane;
       const CBox c = canon(j < cnt ? __ldg(b + j) : make_float4(0, 0, 0, 0), j < cnt);
-      s_box[q][r] = make_float4(c.ymin, c.xmin, c.ymax, c.xmax);
-      s_area[q][r] = c.area;
+      s_box[warp][h * 32 + lane] = make_float4(c.ymin, c.xmin, c.ymax, c.xmax);
+      s_area[warp][h * 32 + lane] = c.area;
     }
-    asm volatile("bar.sync %0, 64;" ::"r"(q + 1));
-    u64 bits = 0;
+    __syncwarp();
+    unsigned lo = 0, hi = 0;
     const int c0 = (cb == rb) ? r + 1 : 0;  // only j > i
 #pragma unroll 8
-    for (int c = c0; c < 64; ++c) {
-      const float4 bj = s_box[q][c];
+    for (int c = 0; c < 64; ++c) {
+      const float4 bj = s_box[warp][c];
       // inter > 0  <=>  the open intervals overlap on both axes (sentinel boxes never do)
-      if (bi.ymax > bj.x && bj.z > bi.ymin && bi.xmax > bj.y && bj.w > bi.xmin) {
+      if (c >= c0 && bi.ymax > bj.x && bj.z > bi.ymin && bi.xmax > bj.y && bj.w > bi.xmin) {
         const float ih = fmaxf(fminf(bi.ymax, bj.z) - fmaxf(bi.ymin, bj.x), 0.0f);
         const float iw = fmaxf(fminf(bi.xmax, bj.w) - fmaxf(bi.xmin, bj.y), 0.0f);
         const float inter = ih * iw;
-        if (iou_gt(inter, s_area[q][c], bi.area, thr)) bits |= (1ull << c);
+        if (iou_gt(inter, s_area[warp][c], bi.area, thr)) {
+          if (c < 32) lo |= 1u << c; else hi |= 1u << (c - 32);
+        }
       }
     }
-    if (live) mrow[cb] = bits;
-    asm volatile("bar.sync %0, 64;" ::"r"(q + 1));
+    if (live) mrow[cb] = ((u64)hi << 32) | lo;
+    __syncwarp();
   }
 }
 
@@ -148,18 +153,31 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const int32_t*
         const int rows = min(64, cnt - b * 64);
         u64 rem = s_removed[b];
         if (rows < 64) rem |= ~0ull << rows;
-        u64 dd[64];
-#pragma unroll
-        for (int t = 0; t < 64; ++t) dd[t] = s_diag[par][t];
-        asm volatile("" ::: "memory");  // all 64 words in registers before the serial chain starts
-        u64 km = 0;
+        unsigned dl[64], dh[64];
 #pragma unroll
         for (int t = 0; t < 64; ++t) {
-          if (!((rem >> t) & 1ull)) {
-            km |= 1ull << t;
-            rem |= dd[t];
+          const u64 v = s_diag[par][t];
+          dl[t] = (unsigned)v;
+          dh[t] = (unsigned)(v >> 32);
+        }
+        asm volatile("" ::: "memory");  // all 64 words in registers before the serial chain starts
+        unsigned rl = (unsigned)rem, rh = (unsigned)(rem >> 32), kl = 0, kh = 0;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {  // rows 0..31 can suppress both halves
+          if (!(rl & (1u << t))) {
+            kl |= 1u << t;
+            rl |= dl[t];
+            rh |= dh[t];
           }
         }
+#pragma unroll
+        for (int t = 32; t < 64; ++t) {  // rows 32..63 only matter for the high half (j > i)
+          if (!(rh & (1u << (t - 32)))) {
+            kh |= 1u << (t - 32);
+            rh |= dh[t];
+          }
+        }
+        u64 km = ((u64)kh << 32) | kl;
         int c = __popcll(km);
         const int left = max_out - kept;
         while (c > left) {  // cap reached inside this block: keep only the first `left`

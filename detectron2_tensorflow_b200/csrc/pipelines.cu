@@ -60,7 +60,7 @@ struct RpnArgs {
   int k, P, post, P2;
 };
 
-constexpr int kRpnThreads = 256;
+constexpr int kRpnThreads = 1024;
 
 // one CTA per (image, level) row: gather/decode the sorted top-k winners, clip, prune (ordered)
 __global__ void __launch_bounds__(kRpnThreads) rpn_decode_kernel(RpnArgs a, const u64* keys, const int32_t* k_r,

@@ -25,6 +25,7 @@ namespace {
 
 constexpr int kMaxSamples = 128;  // max crop rows / cols per ROI (output * sampling_ratio)
 constexpr int kThreads = 256;
+constexpr int kBinsPerCta = 56;  // 7 bins per warp; larger outputs are split over blockIdx.y
 
 struct Level {
   const void* ptr;
@@ -194,8 +195,10 @@ __global__ void __launch_bounds__(kThreads) roi_align_kernel(const RoiAlignArgs 
                                : (long long)reinterpret_cast<const int*>(a.bidx)[roi * a.bidx_stride];
       s_level = lvl;
       s_img = (img >= 0 && img < a.N) ? (int)img : -1;
-      if (a.level_counts) atomicAdd(a.level_counts + lvl, 1);
-      if (a.level_out) a.level_out[roi] = lvl;
+      if (blockIdx.y == 0) {
+        if (a.level_counts) atomicAdd(a.level_counts + lvl, 1);
+        if (a.level_out) a.level_out[roi] = lvl;
+      }
     }
   }
   __syncthreads();
@@ -210,11 +213,13 @@ __global__ void __launch_bounds__(kThreads) roi_align_kernel(const RoiAlignArgs 
   TOut* obase = reinterpret_cast<TOut*>(a.out) + (size_t)roi * a.oh * a.ow * C;
   const float cnt = (float)(s1 * s1);
   const int groups_total = C / E;  // 16-byte groups per pixel
+  const int bin_begin = blockIdx.y * kBinsPerCta;
+  const int bin_end = min(bin_begin + kBinsPerCta, a.oh * a.ow);
 
   if (ONE && GROUPS > 0) {
     // sampling_ratio 0/1 (the reference default): one bilinear sample per bin, fully unrolled channel
     // groups, corner addresses formed once per bin from the precomputed element offsets.
-    for (int bin = warp; bin < a.oh * a.ow; bin += kWarps) {
+    for (int bin = bin_begin + warp; bin < bin_end; bin += kWarps) {
       const int oy = bin / a.ow, ox = bin - oy * a.ow;
       TOut* o = obase + (size_t)bin * C + lane * E;
       const Tap y = ty[oy];
@@ -255,7 +260,7 @@ __global__ void __launch_bounds__(kThreads) roi_align_kernel(const RoiAlignArgs 
     }
     return;
   }
-  for (int bin = warp; bin < a.oh * a.ow; bin += kWarps) {
+  for (int bin = bin_begin + warp; bin < bin_end; bin += kWarps) {
     const int oy = bin / a.ow, ox = bin - oy * a.ow;
     TOut* o = obase + (size_t)bin * C;
     auto do_group = [&](int g) {
@@ -313,7 +318,7 @@ __global__ void __launch_bounds__(kThreads) roi_align_kernel(const RoiAlignArgs 
 template <typename TIn, typename TOut>
 int launch(const RoiAlignArgs& a, cudaStream_t st) {
   constexpr int E = Vec<TIn>::kElems;
-  const dim3 grid((unsigned)a.M), block(kThreads);
+  const dim3 grid((unsigned)a.M, (unsigned)((a.oh * a.ow + kBinsPerCta - 1) / kBinsPerCta)), block(kThreads);
   const int g = a.C / E;
   const bool one = a.sr <= 1;
   if (g == 32 && one) roi_align_kernel<TIn, TOut, 1, true><<<grid, block, 0, st>>>(a);

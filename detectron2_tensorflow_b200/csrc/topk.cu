@@ -30,6 +30,7 @@ constexpr int kPasses = 6;
 constexpr int kHistThreads = 256;
 constexpr int kChunk = 4096;   // elements per CTA per pass
 constexpr int kBatch = 8;       // independent loads in flight per thread
+constexpr int kCopies = 4;      // replicated shared histograms (lane & 3) to spread same-bin atomics
 
 __constant__ int c_shift[kPasses] = {53, 42, 32, 21, 10, 0};
 __constant__ int c_bits[kPasses] = {11, 11, 10, 11, 11, 10};
@@ -87,7 +88,7 @@ __global__ void topk_init(TopkArgs a, int rows, int32_t* seg_len, int32_t* out_c
 }
 
 __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass) {
-  __shared__ unsigned sh[kBins];
+  __shared__ unsigned sh[kCopies][kBins];
   __shared__ int s_last;
   int g, img, chunk;
   if (!locate(a, blockIdx.x, g, img, chunk)) return;
@@ -97,8 +98,9 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass) 
   const u64 prefix = st->prefix;
   const int shift = c_shift[pass], bits = c_bits[pass];
   const unsigned mask = (1u << bits) - 1u;
-  for (int i = threadIdx.x; i < kBins; i += kHistThreads) sh[i] = 0;
+  for (int i = threadIdx.x; i < kCopies * kBins; i += kHistThreads) (&sh[0][0])[i] = 0;
   __syncthreads();
+  unsigned* my = sh[threadIdx.x & (kCopies - 1)];
   const long long len = a.d.row_len[g];
   const float* x = a.d.scores[g] + (size_t)img * len;
   const long long beg = (long long)chunk * kChunk;
@@ -117,14 +119,18 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass) 
       if (i < end) {
         const u64 c = composite(v[u], (unsigned)i, a.d.transform);
         const bool in = (pass == 0) || ((c >> hi_shift) == prefix);
-        if (in) atomicAdd(&sh[(unsigned)(c >> shift) & mask], 1u);
+        if (in) atomicAdd(&my[(unsigned)(c >> shift) & mask], 1u);
       }
     }
   }
   __syncthreads();
   unsigned* gh = a.hist + ((size_t)row * kPasses + pass) * kBins;
-  for (int i = threadIdx.x; i < kBins; i += kHistThreads)
-    if (sh[i]) atomicAdd(gh + i, sh[i]);
+  for (int i = threadIdx.x; i < kBins; i += kHistThreads) {
+    unsigned v = 0;
+#pragma unroll
+    for (int c = 0; c < kCopies; ++c) v += sh[c][i];
+    if (v) atomicAdd(gh + i, v);
+  }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
