@@ -37,7 +37,7 @@ struct MnmsArgs {
 
 __device__ __forceinline__ int rows_of(const MnmsArgs& a, int b) { return a.counts ? min(a.counts[b], a.n) : a.n; }
 
-// grid (ceil(Wd/8), n, B); 256 threads: warp w packs word (blockIdx.x*8 + w)
+// Scalar fallback (hw % 4 != 0): grid (ceil(Wd/8), n, B); 256 threads: warp w packs word (blockIdx.x*8 + w)
 __global__ void __launch_bounds__(256) mnms_pack_kernel(MnmsArgs a) {
   const int b = blockIdx.z, i = blockIdx.y;
   if (i >= rows_of(a, b)) return;
@@ -55,6 +55,41 @@ __global__ void __launch_bounds__(256) mnms_pack_kernel(MnmsArgs a) {
     const unsigned c = __popc(lo) + __popc(hi);
     if (c) atomicAdd(a.isum + (size_t)b * a.n + i, c);
   }
+}
+
+// Vector path (hw % 4 == 0): the one streaming read of the fp32 masks.  A warp packs 2 words per step
+// (lane = one float4 = 4 pixels; 16 lanes = 64 pixels = one word) and keeps kPackSteps independent
+// 16-byte loads in flight per lane.  grid (ceil(Wd / 128), n, B), 256 threads = 128 words per CTA.
+constexpr int kPackSteps = 8;
+__global__ void __launch_bounds__(256) mnms_pack4_kernel(MnmsArgs a) {
+  const int b = blockIdx.z, i = blockIdx.y;
+  if (i >= rows_of(a, b)) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float4* m = reinterpret_cast<const float4*>(a.masks + ((size_t)b * a.n + i) * a.hw);
+  const long long nvec = a.hw >> 2;
+  const int w_first = blockIdx.x * (8 * kPackSteps * 2) + warp * (kPackSteps * 2);
+  float4 v[kPackSteps];
+#pragma unroll
+  for (int s = 0; s < kPackSteps; ++s) {
+    const long long q = (long long)(w_first + 2 * s) * 16 + lane;  // float4 index
+    v[s] = q < nvec ? __ldcs(m + q) : make_float4(0, 0, 0, 0);
+  }
+  unsigned total = 0;
+#pragma unroll
+  for (int s = 0; s < kPackSteps; ++s) {
+    const unsigned nib = (v[s].x != 0.0f ? 1u : 0u) | (v[s].y != 0.0f ? 2u : 0u) | (v[s].z != 0.0f ? 4u : 0u) |
+                         (v[s].w != 0.0f ? 8u : 0u);
+    u64 w = (u64)nib << (4 * (lane & 15));
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) w |= __shfl_xor_sync(0xffffffffu, w, o);
+    const int word = w_first + 2 * s + (lane >> 4);
+    if ((lane & 15) == 0 && word < a.Wd) {
+      a.packed[((size_t)b * a.n + i) * a.Wd + word] = w;
+      total += __popcll(w);
+    }
+  }
+  total += __shfl_xor_sync(0xffffffffu, total, 16);
+  if (lane == 0 && total) atomicAdd(a.isum + (size_t)b * a.n + i, total);
 }
 
 __device__ __forceinline__ float sum_of(const MnmsArgs& a, int b, int i) {
@@ -179,7 +214,10 @@ extern "C" int d2b_matrix_nms(const d2b_matrix_nms_params* p, void* workspace, s
   a.cmax = reinterpret_cast<float*>(ws + o_cmax);
   a.out = p->out;
   D2B_CUDA(cudaMemsetAsync(a.isum, 0, sizeof(unsigned) * (size_t)a.B * a.n, st));
-  mnms_pack_kernel<<<dim3((a.Wd + 7) / 8, a.n, a.B), 256, 0, st>>>(a);
+  if (a.hw % 4 == 0 && (reinterpret_cast<uintptr_t>(a.masks) & 15) == 0)
+    mnms_pack4_kernel<<<dim3((a.Wd + 8 * kPackSteps * 2 - 1) / (8 * kPackSteps * 2), a.n, a.B), 256, 0, st>>>(a);
+  else
+    mnms_pack_kernel<<<dim3((a.Wd + 7) / 8, a.n, a.B), 256, 0, st>>>(a);
   D2B_LAUNCH_CHECK();
   mnms_iou_kernel<<<dim3((a.n + 7) / 8, a.n, a.B), 256, 0, st>>>(a);
   D2B_LAUNCH_CHECK();

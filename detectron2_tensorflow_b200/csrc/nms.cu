@@ -58,20 +58,30 @@ __device__ __forceinline__ bool iou_gt(float inter, float area_a, float area_b, 
 // grid (row_blocks, S).  mask[seg][i][w] bit c: box (w*64+c) is suppressed by box i (only j > i).
 // 8 independent warps per CTA: warp = (column group q, row half); it owns 32 rows of the 64-row block
 // and walks column blocks rb+q, rb+q+4, ...  The 64 column boxes of a block are staged (canonicalised,
-// with area) in a warp-private shared-memory slice, so only __syncwarp is needed.
+// with area and pre-scaled extents) in a warp-private shared-memory slice, so only __syncwarp is needed.
+//
+// Pair filter: IoU > thr implies  ih >= thr*max(h_i,h_j)  and  iw >= thr*max(w_i,w_j)  (the intersection
+// can be neither taller nor wider than either box, and inter >= thr*max(area)).  The test uses
+// 0.999*thr, three orders of magnitude more slack than fp32 rounding needs, so it never rejects a pair
+// the exact rule would accept; it rejects >99% of the merely-overlapping pairs, which keeps the exact
+// (divergent) IoU evaluation rare.
 __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* boxes, const int32_t* counts, int n,
                                                                  int W, float thr, u64* mask) {
   __shared__ float4 s_box[kMaskThreads / 32][64];
-  __shared__ float s_area[kMaskThreads / 32][64];
+  __shared__ float4 s_aux[kMaskThreads / 32][64];  // (area, kf*h, kf*w, -)
   const int seg = blockIdx.y, rb = blockIdx.x;
   const int cnt = counts ? min(counts[seg], n) : n;
   if (rb * 64 >= cnt) return;
+  const float kf = thr * 0.999f;
+  const float inf = __int_as_float(0x7f800000);
   const float4* b = boxes + (size_t)seg * n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = warp >> 1, r = (warp & 1) * 32 + lane;
   const int i = rb * 64 + r;
   const bool live = i < cnt;
   const CBox bi = canon(live ? b[i] : make_float4(0, 0, 0, 0), live);
+  const float ty_i = bi.area > 0.0f ? kf * (bi.ymax - bi.ymin) : inf;
+  const float tx_i = bi.area > 0.0f ? kf * (bi.xmax - bi.xmin) : inf;
   u64* mrow = mask + ((size_t)seg * W * 64 + i) * W;
   const int nb = (cnt + 63) >> 6;
   for (int cb = rb + q; cb < nb; cb += kMaskThreads / 64) {
@@ -81,7 +91,8 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* bo
       const int j = j0 + h * 32 + lane;
       const CBox c = canon(j < cnt ? __ldg(b + j) : make_float4(0, 0, 0, 0), j < cnt);
       s_box[warp][h * 32 + lane] = make_float4(c.ymin, c.xmin, c.ymax, c.xmax);
-      s_area[warp][h * 32 + lane] = c.area;
+      s_aux[warp][h * 32 + lane] = make_float4(c.area, c.area > 0.0f ? kf * (c.ymax - c.ymin) : inf,
+                                               c.area > 0.0f ? kf * (c.xmax - c.xmin) : inf, 0.0f);
     }
     __syncwarp();
     unsigned lo = 0, hi = 0;
@@ -89,12 +100,12 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* bo
 #pragma unroll 8
     for (int c = 0; c < 64; ++c) {
       const float4 bj = s_box[warp][c];
-      // inter > 0  <=>  the open intervals overlap on both axes (sentinel boxes never do)
-      if (c >= c0 && bi.ymax > bj.x && bj.z > bi.ymin && bi.xmax > bj.y && bj.w > bi.xmin) {
-        const float ih = fmaxf(fminf(bi.ymax, bj.z) - fmaxf(bi.ymin, bj.x), 0.0f);
-        const float iw = fmaxf(fminf(bi.xmax, bj.w) - fmaxf(bi.xmin, bj.y), 0.0f);
-        const float inter = ih * iw;
-        if (iou_gt(inter, s_area[warp][c], bi.area, thr)) {
+      const float4 aj = s_aux[warp][c];
+      const float ih = fminf(bi.ymax, bj.z) - fmaxf(bi.ymin, bj.x);
+      const float iw = fminf(bi.xmax, bj.w) - fmaxf(bi.xmin, bj.y);
+      if (c >= c0 && ih >= fmaxf(ty_i, aj.y) && iw >= fmaxf(tx_i, aj.z)) {
+        const float inter = fmaxf(ih, 0.0f) * fmaxf(iw, 0.0f);
+        if (iou_gt(inter, aj.x, bi.area, thr)) {
           if (c < 32) lo |= 1u << c; else hi |= 1u << (c - 32);
         }
       }
@@ -312,6 +323,7 @@ int nms_sorted(const float* boxes, const int32_t* counts, int S, int n, int max_
                int32_t* num_keep, void* ws, cudaStream_t st) {
   if (S <= 0) return D2B_OK;
   D2B_REQUIRE(max_out >= 0 && n >= 0, "nms: negative sizes");
+  D2B_REQUIRE(thr >= 0.0f && thr <= 1.0f, "iou_threshold must be in [0, 1]");  // as tf.image.non_max_suppression
   if (max_out == 0) {
     D2B_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int32_t) * S, st));
     return D2B_OK;
