@@ -55,33 +55,48 @@ __device__ __forceinline__ bool iou_gt(float inter, float area_a, float area_b, 
   return inter / u > thr;
 }
 
+// Centre-distance pair filter.  IoU > thr implies ih >= thr*max(h_i,h_j) (the intersection cannot be
+// taller than either box and inter >= thr*max(area)), and ih <= (h_i+h_j)/2 - |cy_i-cy_j|, hence
+//     |cy_i - cy_j| <= (1-thr)*(h_i+h_j)/2 ,   likewise in x.
+// Each box carries r = (1-0.999*thr)*extent/2 * 1.001 + 4e-7*(|lo|+|hi|): slack three orders of magnitude
+// above fp32 rounding of the centre, so the filter never rejects a pair the exact rule accepts.  It costs one
+// 16-byte shared load + 4 adds + 2 compares per pair and rejects all but a fraction of a percent of pairs,
+// so the exact (divergent) IoU evaluation is rare.  Degenerate boxes get r = -inf (never pass, IoU := 0).
+struct FBox { float cy, cx, ry, rx; };
+__device__ __forceinline__ FBox filter_box(const CBox c, float kf) {
+  FBox f;
+  if (c.area > 0.0f) {
+    f.cy = 0.5f * (c.ymin + c.ymax);
+    f.cx = 0.5f * (c.xmin + c.xmax);
+    f.ry = 0.5f * (1.0f - kf) * (c.ymax - c.ymin) * 1.001f + 4e-7f * (fabsf(c.ymin) + fabsf(c.ymax));
+    f.rx = 0.5f * (1.0f - kf) * (c.xmax - c.xmin) * 1.001f + 4e-7f * (fabsf(c.xmin) + fabsf(c.xmax));
+  } else {
+    f.cy = 0.0f; f.cx = 0.0f;
+    f.ry = __int_as_float(0xff800000); f.rx = __int_as_float(0xff800000);
+  }
+  return f;
+}
+
 // grid (row_blocks, S).  mask[seg][i][w] bit c: box (w*64+c) is suppressed by box i (only j > i).
 // 8 independent warps per CTA: warp = (column group q, row half); it owns 32 rows of the 64-row block
-// and walks column blocks rb+q, rb+q+4, ...  The 64 column boxes of a block are staged (canonicalised,
-// with area and pre-scaled extents) in a warp-private shared-memory slice, so only __syncwarp is needed.
-//
-// Pair filter: IoU > thr implies  ih >= thr*max(h_i,h_j)  and  iw >= thr*max(w_i,w_j)  (the intersection
-// can be neither taller nor wider than either box, and inter >= thr*max(area)).  The test uses
-// 0.999*thr, three orders of magnitude more slack than fp32 rounding needs, so it never rejects a pair
-// the exact rule would accept; it rejects >99% of the merely-overlapping pairs, which keeps the exact
-// (divergent) IoU evaluation rare.
+// and walks column blocks rb+q, rb+q+4, ...  The 64 column boxes of a block are staged in a warp-private
+// shared-memory slice (filter record, canonical box, area), so only __syncwarp is needed.
 __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* boxes, const int32_t* counts, int n,
                                                                  int W, float thr, u64* mask) {
+  __shared__ float4 s_flt[kMaskThreads / 32][64];  // (cy, cx, ry, rx)
   __shared__ float4 s_box[kMaskThreads / 32][64];
-  __shared__ float4 s_aux[kMaskThreads / 32][64];  // (area, kf*h, kf*w, -)
+  __shared__ float s_area[kMaskThreads / 32][64];
   const int seg = blockIdx.y, rb = blockIdx.x;
   const int cnt = counts ? min(counts[seg], n) : n;
   if (rb * 64 >= cnt) return;
   const float kf = thr * 0.999f;
-  const float inf = __int_as_float(0x7f800000);
   const float4* b = boxes + (size_t)seg * n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = warp >> 1, r = (warp & 1) * 32 + lane;
   const int i = rb * 64 + r;
   const bool live = i < cnt;
   const CBox bi = canon(live ? b[i] : make_float4(0, 0, 0, 0), live);
-  const float ty_i = bi.area > 0.0f ? kf * (bi.ymax - bi.ymin) : inf;
-  const float tx_i = bi.area > 0.0f ? kf * (bi.xmax - bi.xmin) : inf;
+  const FBox fi = filter_box(bi, kf);
   u64* mrow = mask + ((size_t)seg * W * 64 + i) * W;
   const int nb = (cnt + 63) >> 6;
   for (int cb = rb + q; cb < nb; cb += kMaskThreads / 64) {
@@ -90,27 +105,34 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* bo
     for (int h = 0; h < 2; ++h) {
       const int j = j0 + h * 32 + lane;
       const CBox c = canon(j < cnt ? __ldg(b + j) : make_float4(0, 0, 0, 0), j < cnt);
+      const FBox f = filter_box(c, kf);
+      s_flt[warp][h * 32 + lane] = make_float4(f.cy, f.cx, f.ry, f.rx);
       s_box[warp][h * 32 + lane] = make_float4(c.ymin, c.xmin, c.ymax, c.xmax);
-      s_aux[warp][h * 32 + lane] = make_float4(c.area, c.area > 0.0f ? kf * (c.ymax - c.ymin) : inf,
-                                               c.area > 0.0f ? kf * (c.xmax - c.xmin) : inf, 0.0f);
+      s_area[warp][h * 32 + lane] = c.area;
     }
     __syncwarp();
-    unsigned lo = 0, hi = 0;
-    const int c0 = (cb == rb) ? r + 1 : 0;  // only j > i
-#pragma unroll 8
+    // (1) branch-free filter over the 64 columns -> candidate bits (fully unrolled: immediates only)
+    unsigned clo = 0, chi = 0;
+#pragma unroll
     for (int c = 0; c < 64; ++c) {
-      const float4 bj = s_box[warp][c];
-      const float4 aj = s_aux[warp][c];
-      const float ih = fminf(bi.ymax, bj.z) - fmaxf(bi.ymin, bj.x);
-      const float iw = fminf(bi.xmax, bj.w) - fmaxf(bi.xmin, bj.y);
-      if (c >= c0 && ih >= fmaxf(ty_i, aj.y) && iw >= fmaxf(tx_i, aj.z)) {
-        const float inter = fmaxf(ih, 0.0f) * fmaxf(iw, 0.0f);
-        if (iou_gt(inter, aj.x, bi.area, thr)) {
-          if (c < 32) lo |= 1u << c; else hi |= 1u << (c - 32);
-        }
-      }
+      const float4 fj = s_flt[warp][c];
+      const bool pass = (fabsf(fi.cy - fj.x) <= fi.ry + fj.z) && (fabsf(fi.cx - fj.y) <= fi.rx + fj.w);
+      if (c < 32) clo |= pass ? (1u << c) : 0u; else chi |= pass ? (1u << (c - 32)) : 0u;
     }
-    if (live) mrow[cb] = ((u64)hi << 32) | lo;
+    u64 cand = ((u64)chi << 32) | clo;
+    if (cb == rb) cand &= (r == 63) ? 0ull : (~0ull << (r + 1));  // only j > i
+    // (2) exact rule on the rare candidates
+    u64 bits = 0;
+    while (cand) {
+      const int c = __ffsll((long long)cand) - 1;
+      cand &= cand - 1;
+      const float4 bj = s_box[warp][c];
+      const float ih = fmaxf(fminf(bi.ymax, bj.z) - fmaxf(bi.ymin, bj.x), 0.0f);
+      const float iw = fmaxf(fminf(bi.xmax, bj.w) - fmaxf(bi.xmin, bj.y), 0.0f);
+      const float inter = ih * iw;
+      if (iou_gt(inter, s_area[warp][c], bi.area, thr)) bits |= 1ull << c;
+    }
+    if (live) mrow[cb] = bits;
     __syncwarp();
   }
 }

@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(kRpnThreads) rpn_decode_kernel(RpnArgs a, cons
 constexpr int kMergeThreads = 1024;
 __global__ void __launch_bounds__(kMergeThreads) rpn_merge_rank_kernel(
     RpnArgs a, const float4* seg_boxes, const float* seg_scores, const int32_t* keep, const int32_t* num_keep,
-    uint32_t* gkeys, float4* out_boxes, float* out_logits, uint8_t* out_valid, int32_t* out_num) {
+    uint32_t* gkeys, int use_smem, float4* out_boxes, float* out_logits, uint8_t* out_valid, int32_t* out_num) {
+  extern __shared__ uint32_t s_keys[];
   const int n = blockIdx.x;
   __shared__ int s_off[D2B_MAX_LEVELS + 1];
   if (threadIdx.x == 0) {
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(kMergeThreads) rpn_merge_rank_kernel(
   __syncthreads();
   const int total = s_off[a.L];
   const int kk = min(total, a.post);  // :105
-  uint32_t* gk = gkeys + (size_t)n * a.P2;
+  uint32_t* gk = use_smem ? s_keys : gkeys + (size_t)n * a.P2;
   for (int ci = threadIdx.x; ci < total; ci += kMergeThreads) {
     int l = 0;
     while (l + 1 < a.L && ci >= s_off[l + 1]) ++l;
@@ -471,9 +472,13 @@ extern "C" int d2b_rpn_proposals(const d2b_rpn_proposals_params* p, void* worksp
   rc = nms_sorted(reinterpret_cast<const float*>(seg_boxes), seg_count, pl.rows, a.k, a.post, p->nms_thresh, keep,
                   nkeep, ws + pl.o_nms, st);  // :90-94
   if (rc != D2B_OK) return rc;
-  rpn_merge_rank_kernel<<<a.N, kMergeThreads, 0, st>>>(a, seg_boxes, seg_scores, keep, nkeep, keys2,
-                                                        reinterpret_cast<float4*>(p->out_boxes), p->out_logits,
-                                                        p->out_valid, p->out_num_valid);  // :101-114
+  const size_t merge_smem = (size_t)a.P2 * sizeof(uint32_t);
+  const int merge_in_smem = merge_smem <= 160 * 1024;
+  if (merge_in_smem && merge_smem > 48 * 1024)
+    D2B_CUDA(cudaFuncSetAttribute(rpn_merge_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem));
+  rpn_merge_rank_kernel<<<a.N, kMergeThreads, merge_in_smem ? merge_smem : 0, st>>>(
+      a, seg_boxes, seg_scores, keep, nkeep, keys2, merge_in_smem, reinterpret_cast<float4*>(p->out_boxes),
+      p->out_logits, p->out_valid, p->out_num_valid);  // :101-114
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }

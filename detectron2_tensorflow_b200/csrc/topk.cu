@@ -28,9 +28,9 @@ typedef unsigned long long u64;
 constexpr int kBins = 2048;
 constexpr int kPasses = 6;
 constexpr int kHistThreads = 256;
-constexpr int kChunk = 4096;   // elements per CTA per pass
+constexpr int kChunk = 8192;   // elements per CTA per pass
 constexpr int kBatch = 8;       // independent loads in flight per thread
-constexpr int kCopies = 4;      // replicated shared histograms (lane & 3) to spread same-bin atomics
+constexpr int kCopies = 2;      // replicated shared histograms (lane & 1) to spread same-bin atomics
 
 __constant__ int c_shift[kPasses] = {53, 42, 32, 21, 10, 0};
 __constant__ int c_bits[kPasses] = {11, 11, 10, 11, 11, 10};
@@ -42,6 +42,7 @@ struct RowState {
   unsigned active;   // 1 while more passes are needed
   unsigned k_r;      // min(k, len, k_limit)
   unsigned out_count;  // collect slot counter
+  unsigned cached;     // 1 when pass 0 ran for this row and filled its slice of the key cache
   unsigned done[kPasses];
 };
 
@@ -52,6 +53,8 @@ struct TopkArgs {
   RowState* state;
   unsigned* hist;  // [rows][kPasses][kBins]
   int P;           // padded k
+  uint32_t* key_cache;                    // SIGMOID only: transformed keys written by pass 0, read afterwards
+  long long cache_off[D2B_MAX_LEVELS];    // element offset of group g inside key_cache
 };
 
 __device__ __forceinline__ bool locate(const TopkArgs& a, int cta, int& g, int& img, int& chunk) {
@@ -63,9 +66,12 @@ __device__ __forceinline__ bool locate(const TopkArgs& a, int cta, int& g, int& 
   return img < a.d.rows_per_group;
 }
 
-__device__ __forceinline__ u64 composite(float x, unsigned idx, int transform) {
+__device__ __forceinline__ uint32_t value_key(float x, int transform) {
   if (transform == D2B_TOPK_SIGMOID) x = d2b_sigmoidf(x);
-  return ((u64)float_to_key(x) << 32) | (u64)(0xffffffffu - idx);
+  return float_to_key(x);
+}
+__device__ __forceinline__ u64 composite_of(uint32_t key, unsigned idx) {
+  return ((u64)key << 32) | (u64)(0xffffffffu - idx);
 }
 
 __global__ void topk_init(TopkArgs a, int rows, int32_t* seg_len, int32_t* out_counts) {
@@ -82,6 +88,7 @@ __global__ void topk_init(TopkArgs a, int rows, int32_t* seg_len, int32_t* out_c
   if (kr == 0) { s.active = 0; s.threshold = ~0ull; }            // take nothing
   else if (kr == a.d.row_len[g]) { s.active = 0; s.threshold = 0ull; }  // take the whole row
   else { s.active = 1; s.threshold = 0ull; }
+  s.cached = (s.active && a.key_cache != nullptr) ? 1u : 0u;
   a.state[r] = s;
   seg_len[r] = (int32_t)kr;
   if (out_counts) out_counts[r] = (int32_t)kr;
@@ -98,38 +105,53 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass) 
   const u64 prefix = st->prefix;
   const int shift = c_shift[pass], bits = c_bits[pass];
   const unsigned mask = (1u << bits) - 1u;
-  for (int i = threadIdx.x; i < kCopies * kBins; i += kHistThreads) (&sh[0][0])[i] = 0;
-  __syncthreads();
-  unsigned* my = sh[threadIdx.x & (kCopies - 1)];
+  // pass 0 sees every element: shared-memory histogram.  Later passes only count the few elements
+  // inside the current prefix: they go straight to the row's global histogram.
+  const bool use_smem = (pass == 0);
+  unsigned* gh = a.hist + ((size_t)row * kPasses + pass) * kBins;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < kCopies * kBins; i += kHistThreads) (&sh[0][0])[i] = 0;
+    __syncthreads();
+  }
+  unsigned* my = use_smem ? sh[threadIdx.x & (kCopies - 1)] : gh;
   const long long len = a.d.row_len[g];
   const float* x = a.d.scores[g] + (size_t)img * len;
   const long long beg = (long long)chunk * kChunk;
   const long long end = beg + kChunk < len ? beg + kChunk : len;
   const int hi_shift = shift + bits;  // bits above the current digit
+  uint32_t* kc = (st->cached) ? a.key_cache + a.cache_off[g] + (size_t)img * len : nullptr;
+  const bool from_cache = kc != nullptr && pass > 0;
+  const uint32_t* src = from_cache ? kc : reinterpret_cast<const uint32_t*>(x);
   for (long long i0 = beg + threadIdx.x; i0 < end; i0 += (long long)kBatch * kHistThreads) {
-    float v[kBatch];
+    uint32_t v[kBatch];
 #pragma unroll
     for (int u = 0; u < kBatch; ++u) {
       const long long i = i0 + (long long)u * kHistThreads;
-      v[u] = i < end ? __ldg(x + i) : 0.0f;
+      v[u] = i < end ? __ldg(src + i) : 0u;
     }
 #pragma unroll
     for (int u = 0; u < kBatch; ++u) {
       const long long i = i0 + (long long)u * kHistThreads;
       if (i < end) {
-        const u64 c = composite(v[u], (unsigned)i, a.d.transform);
+        uint32_t key = v[u];
+        if (!from_cache) {
+          key = value_key(__uint_as_float(v[u]), a.d.transform);
+          if (kc) kc[i] = key;  // pass 0 of a SIGMOID row: the transform is evaluated exactly once per element
+        }
+        const u64 c = composite_of(key, (unsigned)i);
         const bool in = (pass == 0) || ((c >> hi_shift) == prefix);
         if (in) atomicAdd(&my[(unsigned)(c >> shift) & mask], 1u);
       }
     }
   }
   __syncthreads();
-  unsigned* gh = a.hist + ((size_t)row * kPasses + pass) * kBins;
-  for (int i = threadIdx.x; i < kBins; i += kHistThreads) {
-    unsigned v = 0;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < kBins; i += kHistThreads) {
+      unsigned v = 0;
 #pragma unroll
-    for (int c = 0; c < kCopies; ++c) v += sh[c][i];
-    if (v) atomicAdd(gh + i, v);
+      for (int c = 0; c < kCopies; ++c) v += sh[c][i];
+      if (v) atomicAdd(gh + i, v);
+    }
   }
   __threadfence();
   __syncthreads();
@@ -194,12 +216,14 @@ __global__ void __launch_bounds__(kHistThreads) topk_collect(TopkArgs a, u64* ou
   const long long end = beg + kChunk < len ? beg + kChunk : len;
   u64* out = out_keys + (size_t)row * a.P;
   const int lane = threadIdx.x & 31;
+  const uint32_t* kc = (st->cached) ? a.key_cache + a.cache_off[g] + (size_t)img * len : nullptr;
+  const uint32_t* src = kc ? kc : reinterpret_cast<const uint32_t*>(x);
   for (long long i0 = beg + (threadIdx.x & ~31); i0 < end; i0 += (long long)kBatch * kHistThreads) {
-    float v[kBatch];
+    uint32_t v[kBatch];
 #pragma unroll
     for (int u = 0; u < kBatch; ++u) {
       const long long i = i0 + (long long)u * kHistThreads + lane;
-      v[u] = i < end ? __ldg(x + i) : 0.0f;
+      v[u] = i < end ? __ldg(src + i) : 0u;
     }
 #pragma unroll
     for (int u = 0; u < kBatch; ++u) {
@@ -207,7 +231,8 @@ __global__ void __launch_bounds__(kHistThreads) topk_collect(TopkArgs a, u64* ou
       u64 c = 0;
       bool take = false;
       if (i < end) {
-        c = composite(v[u], (unsigned)i, a.d.transform);
+        const uint32_t key = kc ? v[u] : value_key(__uint_as_float(v[u]), a.d.transform);
+        c = composite_of(key, (unsigned)i);
         take = c >= thr;
       }
       const unsigned m = __ballot_sync(0xffffffffu, take);
@@ -252,6 +277,12 @@ int fill_args(const TopkDesc& d, TopkArgs& a) {
   }
   for (int g = d.G; g <= D2B_MAX_LEVELS; ++g) a.cta_begin[g] = cta;
   a.P = topk_padded_k(d.k);
+  a.key_cache = nullptr;
+  long long off = 0;
+  for (int g = 0; g < D2B_MAX_LEVELS; ++g) {
+    a.cache_off[g] = off;
+    if (g < d.G) off += d.row_len[g] * (long long)d.rows_per_group;
+  }
   return cta;
 }
 
@@ -263,10 +294,17 @@ int topk_padded_k(int k) {
   return P;
 }
 
+static size_t cache_elems(const TopkDesc& d) {
+  if (d.transform != D2B_TOPK_SIGMOID) return 0;
+  size_t e = 0;
+  for (int g = 0; g < d.G; ++g) e += (size_t)d.row_len[g] * d.rows_per_group;
+  return e;
+}
+
 size_t topk_workspace_bytes(const TopkDesc& d) {
   const size_t rows = (size_t)d.G * d.rows_per_group;
   return ws_slice(rows * sizeof(RowState)) + ws_slice(rows * kPasses * kBins * sizeof(unsigned)) +
-         ws_slice(rows * sizeof(int32_t));
+         ws_slice(rows * sizeof(int32_t)) + ws_slice(cache_elems(d) * sizeof(uint32_t));
 }
 
 int topk_run(const TopkDesc& d, unsigned long long* out_keys, float* out_values, int32_t* out_indices,
@@ -284,6 +322,7 @@ int topk_run(const TopkDesc& d, unsigned long long* out_keys, float* out_values,
   a.state = w.take<RowState>(rows);
   a.hist = w.take<unsigned>((size_t)rows * kPasses * kBins);
   int32_t* seg_len = w.take<int32_t>(rows);
+  if (cache_elems(d) > 0) a.key_cache = w.take<uint32_t>(cache_elems(d));
   D2B_CUDA(cudaMemsetAsync(a.hist, 0, (size_t)rows * kPasses * kBins * sizeof(unsigned), st));
   topk_init<<<(rows + 127) / 128, 128, 0, st>>>(a, rows, seg_len, out_counts);
   D2B_LAUNCH_CHECK();
