@@ -39,6 +39,7 @@ class MaskRCNNPostBackbone(object):
         self._grids = {}
         self._streams = {}
         self._host_out = {}
+        self._dev_in = {}
 
     # ------------------------------------------------------------------ helpers
     def _grid(self, n, per, dev):
@@ -89,43 +90,88 @@ class MaskRCNNPostBackbone(object):
     def run_host(self, x, device=None, chunk_images=2):
         """x: dict of HOST tensors (pinned for full PCIe rate).  Returns a dict of pinned host tensors
         (flatten_outputs keys) for the whole batch, byte-identical to the un-chunked device step.  The
-        returned buffers are owned by this object and are overwritten by the next `run_host` call."""
+        returned buffers are owned by this object and are overwritten by the next `run_host` call.
+
+        Three streams: `up` carries only host->device copies, `run` only kernels, `down` only device->host
+        copies, chained per chunk by events; device input buffers are double-buffered by chunk parity."""
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         N = x["shapes"].shape[0]
-        R, D = self.R, self.D
+        R = self.R
         key = str(dev)
         if key not in self._streams:
-            self._streams[key] = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-        streams = self._streams[key]
+            self._streams[key] = [torch.cuda.Stream(dev) for _ in range(3)]
+        up, run, down = self._streams[key]
         cur = torch.cuda.current_stream(dev)
-        for s in streams:
+        for s in (up, run, down):
             s.wait_stream(cur)
-        anchors = [a.to(dev, non_blocking=True) for a in x["anchors"]]
-        ev_anchor = torch.cuda.Event()
-        ev_anchor.record(cur)
+        with torch.cuda.stream(up):
+            anchors = [a.to(dev, non_blocking=True) for a in x["anchors"]]
+        sets = self._device_inputs(x, dev, chunk_images)
+        free_ev = [None, None]  # kernels that last read input set p have finished
         host_out = None
+        pending = []
         for ci, b in enumerate(range(0, N, chunk_images)):
             e = min(b + chunk_images, N)
-            s = streams[ci % 2]
-            with torch.cuda.stream(s):
-                s.wait_event(ev_anchor)
+            n = e - b
+            p = ci % 2
+            bufs = sets[p]
+            with torch.cuda.stream(up):
+                if free_ev[p] is not None:
+                    up.wait_event(free_ev[p])
                 xd = {"anchors": anchors}
                 for k in PER_IMAGE_KEYS:
                     v = x[k]
-                    xd[k] = [t[b:e].to(dev, non_blocking=True) for t in v] if isinstance(v, (list, tuple)) \
-                        else v[b:e].to(dev, non_blocking=True)
+                    if isinstance(v, (list, tuple)):
+                        xd[k] = []
+                        for dst, src in zip(bufs[k], v):
+                            dst[:n].copy_(src[b:e], non_blocking=True)
+                            xd[k].append(dst[:n])
+                    else:
+                        bufs[k][:n].copy_(v[b:e], non_blocking=True)
+                        xd[k] = bufs[k][:n]
                 for k in PER_ROI_KEYS:
-                    xd[k] = x[k][b * R:e * R].to(dev, non_blocking=True)
+                    bufs[k][:n * R].copy_(x[k][b * R:e * R], non_blocking=True)
+                    xd[k] = bufs[k][:n * R]
+                up_done = torch.cuda.Event()
+                up_done.record(up)
+            with torch.cuda.stream(run):
+                run.wait_event(up_done)
                 out = self.flatten_outputs(self(xd))
+                run_done = torch.cuda.Event()
+                run_done.record(run)
+                free_ev[p] = run_done
+            with torch.cuda.stream(down):
+                down.wait_event(run_done)
                 if host_out is None:
-                    host_out = self._host_buffers(out, N, e - b)
+                    host_out = self._host_buffers(out, N, n)
                 for k, t in out.items():
-                    per = t.shape[0] // (e - b)
+                    per = t.shape[0] // n
                     host_out[k][b * per:e * per].copy_(t, non_blocking=True)
-        for s in streams:
+                    t.record_stream(down)  # allocated on `run`, read on `down`
+            pending.append(out)
+        for s in (up, run, down):
             cur.wait_stream(s)
         cur.synchronize()
         return host_out
+
+    def _device_inputs(self, x, dev, chunk_images):
+        """Two sets of device input buffers (double buffering), cached across calls."""
+        def shape_sig(v):
+            return tuple((tuple(t.shape[1:]), t.dtype) for t in v) if isinstance(v, (list, tuple)) \
+                else (tuple(v.shape[1:]), v.dtype)
+        sig = (str(dev), chunk_images, self.R) + tuple((k, shape_sig(x[k])) for k in PER_IMAGE_KEYS + PER_ROI_KEYS)
+        if self._dev_in.get("sig") != sig:
+            def alloc(v, rows):
+                if isinstance(v, (list, tuple)):
+                    return [torch.empty((rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev) for t in v]
+                return torch.empty((rows,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
+            sets = []
+            for _ in range(2):
+                d = {k: alloc(x[k], chunk_images) for k in PER_IMAGE_KEYS}
+                d.update({k: alloc(x[k], chunk_images * self.R) for k in PER_ROI_KEYS})
+                sets.append(d)
+            self._dev_in = {"sig": sig, "sets": sets}
+        return self._dev_in["sets"]
 
     def _host_buffers(self, out, N, n_chunk):
         sig = tuple((k, tuple(t.shape[1:]), t.dtype, t.shape[0] // n_chunk) for k, t in out.items()) + (N,)
