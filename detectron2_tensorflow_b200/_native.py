@@ -81,6 +81,11 @@ class MatrixNmsParams(C.Structure):
                 ("batch", _i32), ("n", _i32), ("hw", _i64), ("kernel", _i32), ("sigma", _f32), ("out", _vp)]
 
 
+class PasteMasksParams(C.Structure):
+    _fields_ = [("box_masks", _vp), ("boxes", _vp), ("num_masks", _i64), ("mask_h", _i32), ("mask_w", _i32),
+                ("image_h", _i32), ("image_w", _i32), ("mask_threshold", _f32), ("out", _vp)]
+
+
 # op name -> params struct; every op exports d2b_<op> and d2b_<op>_workspace_bytes
 OPS = {
     "roi_align_multilevel": RoiAlignParams,
@@ -91,6 +96,7 @@ OPS = {
     "fast_rcnn_postprocess": FastRcnnParams,
     "retinanet_postprocess": RetinanetParams,
     "matrix_nms": MatrixNmsParams,
+    "paste_masks": PasteMasksParams,
 }
 EXPORTS = ["d2b_version", "d2b_status_string", "d2b_last_error", "d2b_kernel_launch_count"] + \
           [f"d2b_{op}{sfx}" for op in OPS for sfx in ("", "_workspace_bytes")]

@@ -135,7 +135,7 @@ __device__ __forceinline__ float d2b_logf(float x0) {
 __device__ __forceinline__ float d2b_sigmoidf(float x) {
   float e = d2b_expf(-x);
   float d = 1.0f + e;
-  return 1.0f / d;
+  return __frcp_rn(d);  // correctly rounded reciprocal == IEEE 1.0f / d
 }
 
 // Order-preserving fp32 -> u32 key: larger float <=> larger key; -0 == +0;

@@ -96,61 +96,78 @@ __device__ __forceinline__ float sum_of(const MnmsArgs& a, int b, int i) {
   return a.sum_in ? a.sum_in[(size_t)b * a.n + i] : (float)a.isum[(size_t)b * a.n + i];
 }
 
-// one warp per (i, j); grid (ceil(n/8), n, B) with 8 warps per CTA over j
+// One CTA per row i: the row of the decayed-IoU matrix is first filled with its "no overlap" value
+// (coalesced), then each warp takes the few columns j > i of the same class and does the AND+POPC
+// reduction over the packed words.  grid (n, B), 256 threads.
 __global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a) {
-  const int b = blockIdx.z, i = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int b = blockIdx.y, i = blockIdx.x;
   const int nb = rows_of(a, b);
-  if (i >= nb || j >= nb) return;
-  const float si = sum_of(a, b, i), sj = sum_of(a, b, j);
-  const bool same = a.classes[(size_t)b * a.n + i] == a.classes[(size_t)b * a.n + j];
-  float v;
-  if (j > i && same) {
-    const u64* pi = a.packed + ((size_t)b * a.n + i) * a.Wd;
+  if (i >= nb) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float si = sum_of(a, b, i);
+  const long long ci = a.classes[(size_t)b * a.n + i];
+  float* row = a.iou + ((size_t)b * a.n + i) * a.n;
+  const u64* pi = a.packed + ((size_t)b * a.n + i) * a.Wd;
+  // lower triangle / other class: (x - x) resp. (x * 0) of the reference -- zero unless the union is
+  // empty (0/0), which propagates NaN exactly like the TF graph would.
+  for (int j = threadIdx.x; j < nb; j += 256) {
+    const float u = sum_of(a, b, j) + si;
+    row[j] = (u == 0.0f) ? __int_as_float(0x7fc00000) : 0.0f;
+  }
+  __syncthreads();
+  for (int j = i + 1 + warp; j < nb; j += 8) {
+    if (a.classes[(size_t)b * a.n + j] != ci) continue;  // warp-uniform
     const u64* pj = a.packed + ((size_t)b * a.n + j) * a.Wd;
     unsigned c = 0;
     for (int w = lane; w < a.Wd; w += 32) c += __popcll(pi[w] & pj[w]);
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    const float inter = (float)c;
-    float u = sj + si;       // nms.py:51-52
-    u = u - inter;
-    v = inter / u;           // :54
-  } else {
-    // lower triangle / other class: (x - x) resp. (x * 0) of the reference -- zero unless the
-    // union is empty (0/0), which propagates NaN exactly like the TF graph would.
-    float u = sj + si;
-    v = (u == 0.0f) ? __int_as_float(0x7fc00000) : 0.0f;
+    if (lane == 0) {
+      const float inter = (float)c;
+      float u = sum_of(a, b, j) + si;  // nms.py:51-52
+      u = u - inter;
+      row[j] = inter / u;  // :54
+    }
   }
-  if (lane == 0) a.iou[((size_t)b * a.n + i) * a.n + j] = v;
 }
 
-// compensate_iou = reduce_max(iou, axis=0)  (:67)
-__global__ void mnms_cmax_kernel(MnmsArgs a) {
+// compensate_iou = reduce_max(iou, axis=0) (:67): one warp per column, `(v > m) ? v : m` semantics
+// (NaNs are skipped unless the first row is NaN).
+__global__ void __launch_bounds__(256) mnms_cmax_kernel(MnmsArgs a) {
   const int b = blockIdx.y;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   const int nb = rows_of(a, b);
   if (j >= nb) return;
   const float* io = a.iou + (size_t)b * a.n * a.n;
-  float m = io[j];
-  for (int i = 1; i < nb; ++i) {
+  const float first = io[j];
+  float m = __int_as_float(0xff800000);
+  for (int i = lane; i < nb; i += 32) {
     const float v = io[(size_t)i * a.n + j];
     m = (v > m) ? v : m;
   }
-  a.cmax[(size_t)b * a.n + j] = m;
+  for (int o = 16; o > 0; o >>= 1) {
+    const float v = __shfl_xor_sync(0xffffffffu, m, o);
+    m = (v > m) ? v : m;
+  }
+  if (first != first) m = first;
+  if (lane == 0) a.cmax[(size_t)b * a.n + j] = m;
 }
 
-// decay + reduce_min(axis=0) + score update (:72-82)
-__global__ void mnms_decay_kernel(MnmsArgs a) {
+// decay + reduce_min(axis=0) + score update (:72-82): one warp per column, `(d < m) ? d : m` semantics.
+__global__ void __launch_bounds__(256) mnms_decay_kernel(MnmsArgs a) {
   const int b = blockIdx.y;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (j >= a.n) return;
   const int nb = rows_of(a, b);
-  if (j >= nb) { a.out[(size_t)b * a.n + j] = 0.0f; return; }
+  if (j >= nb) {
+    if (lane == 0) a.out[(size_t)b * a.n + j] = 0.0f;
+    return;
+  }
   const float* io = a.iou + (size_t)b * a.n * a.n;
   const float* cm = a.cmax + (size_t)b * a.n;
   float m = __int_as_float(0x7f800000);
-  for (int i = 0; i < nb; ++i) {
+  for (int i = lane; i < nb; i += 32) {
     const float v = io[(size_t)i * a.n + j];
     const float ci = cm[i];
     float d;
@@ -161,7 +178,11 @@ __global__ void mnms_decay_kernel(MnmsArgs a) {
     }
     m = (d < m) ? d : m;
   }
-  a.out[(size_t)b * a.n + j] = a.scores[(size_t)b * a.n + j] * m;
+  for (int o = 16; o > 0; o >>= 1) {
+    const float v = __shfl_xor_sync(0xffffffffu, m, o);
+    m = (v < m) ? v : m;
+  }
+  if (lane == 0) a.out[(size_t)b * a.n + j] = a.scores[(size_t)b * a.n + j] * m;
 }
 
 size_t mnms_bytes(const d2b_matrix_nms_params* p, size_t* o_packed, size_t* o_isum, size_t* o_iou, size_t* o_cmax) {
@@ -219,11 +240,11 @@ extern "C" int d2b_matrix_nms(const d2b_matrix_nms_params* p, void* workspace, s
   else
     mnms_pack_kernel<<<dim3((a.Wd + 7) / 8, a.n, a.B), 256, 0, st>>>(a);
   D2B_LAUNCH_CHECK();
-  mnms_iou_kernel<<<dim3((a.n + 7) / 8, a.n, a.B), 256, 0, st>>>(a);
+  mnms_iou_kernel<<<dim3(a.n, a.B), 256, 0, st>>>(a);
   D2B_LAUNCH_CHECK();
-  mnms_cmax_kernel<<<dim3((a.n + 127) / 128, a.B), 128, 0, st>>>(a);
+  mnms_cmax_kernel<<<dim3((a.n + 7) / 8, a.B), 256, 0, st>>>(a);
   D2B_LAUNCH_CHECK();
-  mnms_decay_kernel<<<dim3((a.n + 127) / 128, a.B), 128, 0, st>>>(a);
+  mnms_decay_kernel<<<dim3((a.n + 7) / 8, a.B), 256, 0, st>>>(a);
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }

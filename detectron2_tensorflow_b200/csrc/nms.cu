@@ -138,126 +138,111 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* bo
 }
 
 // One CTA (8 warps) per segment; the removed-set lives in shared memory (W words).  Per 64-row block b:
-//   thread 0     resolves the diagonal tile: the 64 diagonal words sit in registers and the greedy chain
-//                is 64 fully unrolled test/OR steps (no memory access on the serial path);
-//   warps 0-1    prefetch, a block ahead, the diagonal word and the NEXT word of each of their 64 rows, so
-//                the contribution of block b to removed[b+1] (all the next resolve needs) is a register
-//                select + warp OR right after the resolve;
-//   warps 2-7    OR the kept rows of block b-1 into the remaining words concurrently with the resolve.
-// The sweep stops at the cap.
+//   warp 0      resolves the diagonal 64x64 tile with a warp-parallel fixpoint instead of a 64-step serial
+//               chain: lane l holds the diagonal words of rows l and l+32 in registers; each round ORs
+//               (REDUX) the words of the still-undecided rows, keeps every undecided row no earlier
+//               undecided row can suppress, and removes the rows those suppress.  The result equals the
+//               greedy scan (a row is kept iff no earlier kept row suppresses it); sparse tiles converge
+//               in 2-3 rounds.  The same warp prefetches, a block ahead, the diagonal word and the NEXT
+//               word of its rows, so folding block b into removed[b+1] is a register select + REDUX.
+//   warps 1-7   OR the kept rows of block b-1 into the remaining words (>= b+1) meanwhile.
+// One CTA-wide barrier per block.  The sweep stops at the cap.
 constexpr int kSweepThreads = 256;
-constexpr int kOrThreads = kSweepThreads - 64;
+constexpr int kOrThreads = kSweepThreads - 32;
+
+__device__ __forceinline__ u64 warp_or64(u64 v) {
+  const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+  const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+  return ((u64)hi << 32) | lo;
+}
+
 __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const int32_t* counts, int n, int W, int max_out,
                                                                    const u64* mask, int32_t* keep,
                                                                    int32_t* num_keep) {
   extern __shared__ u64 s_removed[];  // [W]
-  __shared__ u64 s_diag[2][64];
   __shared__ u64 s_keepm[2];
-  __shared__ int s_list[2][64];
   const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int cnt = counts ? min(counts[seg], n) : n;
   const u64* m = mask + (size_t)seg * W * 64 * W;
   int32_t* kp = keep + (size_t)seg * max_out;
   for (int w = tid; w < W; w += kSweepThreads) s_removed[w] = 0;
   const int nb = (cnt + 63) >> 6;
-  u64 pre_next = 0;  // threads 0..63: word b+1 of row b*64+tid
-  if (tid < 64) {
-    u64 d = 0;
-    if (tid < cnt) {
-      d = m[(size_t)tid * W];
-      if (1 < W) pre_next = m[(size_t)tid * W + 1];
-    }
-    s_diag[0][tid] = d;
+  // warp 0, lane l: rows (b*64 + l) and (b*64 + 32 + l): diagonal word b and next word b+1
+  u64 dA = 0, dB = 0, nA = 0, nB = 0;
+  if (tid < 32 && nb > 0) {
+    const int i0 = lane, i1 = 32 + lane;
+    if (i0 < cnt) { dA = m[(size_t)i0 * W]; if (1 < W) nA = m[(size_t)i0 * W + 1]; }
+    if (i1 < cnt) { dB = m[(size_t)i1 * W]; if (1 < W) nB = m[(size_t)i1 * W + 1]; }
   }
   __syncthreads();
   int kept = 0;
   for (int b = 0; b < nb; ++b) {
     const int par = b & 1;
-    u64 nd = 0, nn = 0;
-    if (tid < 64) {
-      if (b + 1 < nb) {  // prefetch for block b+1 (independent of the resolve)
-        const int i = (b + 1) * 64 + tid;
-        if (i < cnt) {
-          nd = m[(size_t)i * W + (b + 1)];
-          if (b + 2 < W) nn = m[(size_t)i * W + (b + 2)];
-        }
+    if (tid < 32) {
+      // prefetch block b+1 (independent of the resolve)
+      u64 pdA = 0, pdB = 0, pnA = 0, pnB = 0;
+      if (b + 1 < nb) {
+        const int i0 = (b + 1) * 64 + lane, i1 = i0 + 32;
+        if (i0 < cnt) { pdA = m[(size_t)i0 * W + (b + 1)]; if (b + 2 < W) pnA = m[(size_t)i0 * W + (b + 2)]; }
+        if (i1 < cnt) { pdB = m[(size_t)i1 * W + (b + 1)]; if (b + 2 < W) pnB = m[(size_t)i1 * W + (b + 2)]; }
       }
-      if (tid == 0) {
-        const int rows = min(64, cnt - b * 64);
-        u64 rem = s_removed[b];
-        if (rows < 64) rem |= ~0ull << rows;
-        unsigned dl[64], dh[64];
-#pragma unroll
-        for (int t = 0; t < 64; ++t) {
-          const u64 v = s_diag[par][t];
-          dl[t] = (unsigned)v;
-          dh[t] = (unsigned)(v >> 32);
-        }
-        asm volatile("" ::: "memory");  // all 64 words in registers before the serial chain starts
-        unsigned rl = (unsigned)rem, rh = (unsigned)(rem >> 32), kl = 0, kh = 0;
-#pragma unroll
-        for (int t = 0; t < 32; ++t) {  // rows 0..31 can suppress both halves
-          if (!(rl & (1u << t))) {
-            kl |= 1u << t;
-            rl |= dl[t];
-            rh |= dh[t];
-          }
-        }
-#pragma unroll
-        for (int t = 32; t < 64; ++t) {  // rows 32..63 only matter for the high half (j > i)
-          if (!(rh & (1u << (t - 32)))) {
-            kh |= 1u << (t - 32);
-            rh |= dh[t];
-          }
-        }
-        u64 km = ((u64)kh << 32) | kl;
-        int c = __popcll(km);
-        const int left = max_out - kept;
-        while (c > left) {  // cap reached inside this block: keep only the first `left`
-          km &= ~(1ull << (63 - __clzll((long long)km)));
-          --c;
-        }
-        s_keepm[par] = km;
+      const int rows = min(64, cnt - b * 64);
+      u64 rem = s_removed[b];
+      if (rows < 64) rem |= ~0ull << rows;
+      u64 U = ~rem, K = 0;
+      const u64 bitA = 1ull << lane, bitB = 1ull << (lane + 32);
+      while (U) {  // warp-uniform
+        const u64 blocked = warp_or64(((U & bitA) ? dA : 0ull) | ((U & bitB) ? dB : 0ull));
+        const u64 nk = U & ~blocked;  // never empty: the first undecided row cannot be blocked
+        K |= nk;
+        U &= ~nk;
+        U &= ~warp_or64(((nk & bitA) ? dA : 0ull) | ((nk & bitB) ? dB : 0ull));
       }
+      int c = __popcll(K);
+      const int left = max_out - kept;
+      while (c > left) {  // cap reached inside this block: keep only the first `left`
+        K &= ~(1ull << (63 - __clzll((long long)K)));
+        --c;
+      }
+      if (K & bitA) kp[kept + __popcll(K & (bitA - 1ull))] = b * 64 + lane;
+      if (K & bitB) kp[kept + __popcll(K & (bitB - 1ull))] = b * 64 + 32 + lane;
+      const u64 fold = warp_or64(((K & bitA) ? nA : 0ull) | ((K & bitB) ? nB : 0ull));
+      if (lane == 0) {
+        s_keepm[par] = K;
+        if (fold && b + 1 < W) atomicOr(&s_removed[b + 1], fold);
+      }
+      dA = pdA; dB = pdB; nA = pnA; nB = pnB;
     } else if (b > 0) {
-      // OR the kept rows of block b-1 into words >= b+1 (word b was done right after its resolve)
-      const int t = tid - 64;
+      // OR the kept rows of block b-1 into words >= b+1 (word b was folded in right after its resolve).
+      // Threads are laid out words-across x row-groups-down; each scans its share of the 64 rows.
+      const int t = tid - 32;
       const u64 pk = s_keepm[par ^ 1];
-      const int nk = __popcll(pk);
       const int wrem = W - (b + 1);
-      if (wrem > 0 && nk > 0) {
+      if (wrem > 0 && pk) {
         const int Wp = wrem < kOrThreads ? wrem : kOrThreads;
         const int groups = kOrThreads / Wp;
         const int wl = t % Wp, rg = t / Wp;
         if (rg < groups) {
           for (int w = b + 1 + wl; w < W; w += Wp) {
             u64 acc = 0;
-            for (int x = rg; x < nk; x += groups)
-              acc |= __ldg(m + ((size_t)(b - 1) * 64 + s_list[par ^ 1][x]) * W + w);
+            for (int x0 = rg; x0 < 64; x0 += groups * 8) {
+              u64 v[8];  // independent (predicated) loads: all in flight before the first use
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int x = x0 + u * groups;
+                v[u] = (x < 64 && ((pk >> x) & 1ull)) ? __ldg(m + ((size_t)(b - 1) * 64 + x) * W + w) : 0ull;
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) acc |= v[u];
+            }
             if (acc) atomicOr(&s_removed[w], acc);
           }
         }
       }
     }
-    __syncthreads();  // keep-mask of block b published; OR-rest of block b-1 complete
-    const u64 km = s_keepm[par];
-    if (tid < 64) {
-      const bool mine = (km >> tid) & 1ull;
-      if (mine) {
-        const int rank = __popcll(km & ((1ull << tid) - 1ull));
-        kp[kept + rank] = b * 64 + tid;
-        s_list[par][rank] = tid;
-      }
-      u64 v = mine ? pre_next : 0ull;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && v && b + 1 < W) atomicOr(&s_removed[b + 1], v);
-      s_diag[par ^ 1][tid] = nd;
-      pre_next = nn;
-    }
-    kept += __popcll(km);
+    __syncthreads();  // block b resolved and folded into removed[b+1]; OR-rest of block b-1 complete
+    kept += __popcll(s_keepm[par]);
     if (kept >= max_out) break;
-    __syncthreads();  // removed[b+1], diag(b+1) and the kept list of block b are visible
   }
   for (int j = kept + tid; j < max_out; j += kSweepThreads) kp[j] = -1;
   if (tid == 0) num_keep[seg] = kept;

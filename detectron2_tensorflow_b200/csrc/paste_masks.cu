@@ -1,0 +1,156 @@
+// paste_masks.cu -- mask paste-back (SURVEY.md 8f "next" #1):
+//   reframe_box_masks_to_image_masks   lib/structures/mask_ops.py:7-56
+//   (called by detector_postprocess    lib/modeling/postprocessing.py:9-59)
+// The reference crops every box mask to the FULL image with tf.image.crop_and_resize on inverted boxes,
+// materialising [M, H, W, 1] fp32 (430 MB per 100 detections at 800x1344), then thresholds to uint8.
+// Here the bilinear sample and the threshold are fused and only the uint8 plane is written: the op is
+// bound by that write (1 B/pixel).  Pixels outside the box are zeros by the extrapolation rule, so a CTA
+// whose rows miss the box stores zeros without touching the mask.
+#include "kernels.cuh"
+
+namespace d2b {
+namespace {
+
+constexpr int kPasteThreads = 256;
+constexpr int kPx = 16;      // output pixels (bytes) per thread per iteration: one 16-byte store
+constexpr int kIters = 4;    // iterations per CTA
+constexpr int kMaxMaskSmem = 16384;  // floats
+
+struct PasteArgs {
+  const float* masks;  // [M, mh, mw]
+  const float* boxes;  // [M, 4] absolute yxyx in output-image pixels
+  long long M;
+  int mh, mw, H, W;
+  float thr;
+  uint8_t* out;  // [M, H, W]
+  int vec;       // 16-byte stores allowed
+  int smem_mask;
+};
+
+struct Axis {  // tf.image.crop_and_resize coordinate rule along one axis
+  float n1, step, mid;
+  int crop, dim;
+  __device__ __forceinline__ float at(int i) const { return crop > 1 ? n1 * (float)(dim - 1) + (float)i * step : mid; }
+};
+__device__ __forceinline__ Axis make_axis(float lo, float hi, int crop, int dim) {
+  Axis a;
+  a.crop = crop; a.dim = dim;
+  // reverse box: ([0,1] - min) / (max - min)   mask_ops.py:44-49
+  const float n1 = (0.0f - lo) / (hi - lo);
+  const float n2 = (1.0f - lo) / (hi - lo);
+  a.n1 = n1;
+  a.step = crop > 1 ? (n2 - n1) * (float)(dim - 1) / (float)(crop - 1) : 0.0f;
+  a.mid = 0.5f * (n1 + n2) * (float)(dim - 1);
+  return a;
+}
+
+__global__ void __launch_bounds__(kPasteThreads) paste_masks_kernel(PasteArgs a) {
+  extern __shared__ float s_mask[];
+  const long long m = blockIdx.y;
+  const long long plane = (long long)a.H * a.W;
+  const long long cta_first = (long long)blockIdx.x * (kPasteThreads * kPx * kIters);
+  if (cta_first >= plane) return;
+  const long long cta_last = min(plane, cta_first + (long long)kPasteThreads * kPx * kIters) - 1;
+  const float4 bx = __ldg(reinterpret_cast<const float4*>(a.boxes) + m);
+  // to_normalized_coordinates: scale by 1/height, 1/width (box_list_ops.py:829-839)
+  const float ys = 1.0f / (float)a.H, xs = 1.0f / (float)a.W;
+  const Axis ay = make_axis(ys * bx.x, ys * bx.z, a.H, a.mh);
+  const Axis ax = make_axis(xs * bx.y, xs * bx.w, a.W, a.mw);
+  const float ymax_in = (float)(a.mh - 1), xmax_in = (float)(a.mw - 1);
+  // does any output row of this CTA fall inside the mask?
+  const int yA = (int)(cta_first / a.W), yB = (int)(cta_last / a.W);
+  bool any = false;
+  for (int y = yA; y <= yB; ++y) {
+    const float in_y = ay.at(y);
+    any = any || (in_y >= 0.0f && in_y <= ymax_in);
+  }
+  const float* mk = a.masks + (size_t)m * a.mh * a.mw;
+  if (any && a.smem_mask) {  // block-uniform
+    for (int i = threadIdx.x; i < a.mh * a.mw; i += kPasteThreads) s_mask[i] = __ldg(mk + i);
+    __syncthreads();
+    mk = s_mask;
+  }
+  uint8_t* o = a.out + (size_t)m * plane;
+  for (int it = 0; it < kIters; ++it) {
+    const long long p0 = cta_first + ((long long)it * kPasteThreads + threadIdx.x) * kPx;
+    if (p0 >= plane) break;
+    int y = (int)(p0 / a.W), x = (int)(p0 - (long long)y * a.W);
+    unsigned pk[4] = {0u, 0u, 0u, 0u};
+    if (any) {
+      int top = 0, bot = 0;
+      float ly = 0.0f;
+      bool vy = false;
+      int cur_y = -1;
+#pragma unroll
+      for (int j = 0; j < kPx; ++j) {
+        if (p0 + j < plane) {
+          if (y != cur_y) {
+            const float in_y = ay.at(y);
+            vy = in_y >= 0.0f && in_y <= ymax_in;
+            const float f = floorf(in_y);
+            top = (int)f; bot = (int)ceilf(in_y);
+            ly = in_y - f;
+            cur_y = y;
+          }
+          if (vy) {
+            const float in_x = ax.at(x);
+            if (in_x >= 0.0f && in_x <= xmax_in) {
+              const float f = floorf(in_x);
+              const int left = (int)f, right = (int)ceilf(in_x);
+              const float lx = in_x - f;
+              const float tl = mk[top * a.mw + left], tr = mk[top * a.mw + right];
+              const float bl = mk[bot * a.mw + left], br = mk[bot * a.mw + right];
+              float t = tr - tl; t = t * lx; t = tl + t;
+              float bb = br - bl; bb = bb * lx; bb = bl + bb;
+              float r = bb - t; r = r * ly; r = t + r;
+              if (r > a.thr) pk[j >> 2] |= 1u << (8 * (j & 3));
+            }
+          }
+          if (++x == a.W) { x = 0; ++y; }
+        }
+      }
+    }
+    if (a.vec && p0 + kPx <= plane) {
+      __stcs(reinterpret_cast<uint4*>(o + p0), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+    } else {
+      for (int j = 0; j < kPx && p0 + j < plane; ++j) o[p0 + j] = (uint8_t)((pk[j >> 2] >> (8 * (j & 3))) & 0xffu);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace d2b
+
+using namespace d2b;
+
+extern "C" size_t d2b_paste_masks_workspace_bytes(const d2b_paste_masks_params*) { return 0; }
+
+extern "C" int d2b_paste_masks(const d2b_paste_masks_params* p, void*, size_t, d2b_stream_t stream) {
+  D2B_REQUIRE(p != nullptr, "params is NULL");
+  D2B_REQUIRE(p->num_masks >= 0 && p->num_masks <= 65535ll * 16, "paste_masks: num_masks=%lld out of range",
+              (long long)p->num_masks);
+  D2B_REQUIRE(p->mask_h >= 1 && p->mask_w >= 1 && p->image_h >= 1 && p->image_w >= 1, "paste_masks: bad sizes");
+  if (p->num_masks == 0) return D2B_OK;  // mask_ops.py:25-28: zeros [0, H, W]
+  D2B_REQUIRE(p->box_masks && p->boxes && p->out, "paste_masks: NULL pointer");
+  PasteArgs a;
+  a.masks = p->box_masks; a.boxes = p->boxes; a.mh = p->mask_h; a.mw = p->mask_w;
+  a.H = p->image_h; a.W = p->image_w; a.thr = p->mask_threshold;
+  const long long plane = (long long)a.H * a.W;
+  a.vec = (plane % 16 == 0) && ((reinterpret_cast<uintptr_t>(p->out) & 15) == 0);
+  a.smem_mask = (a.mh * a.mw <= kMaxMaskSmem);
+  const size_t smem = a.smem_mask ? sizeof(float) * a.mh * a.mw : 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (smem > 48 * 1024)
+    D2B_CUDA(cudaFuncSetAttribute(paste_masks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned gx = (unsigned)((plane + kPasteThreads * kPx * kIters - 1) / (kPasteThreads * kPx * kIters));
+  for (long long m0 = 0; m0 < p->num_masks; m0 += 65535) {  // grid.y limit
+    const long long cnt = p->num_masks - m0 < 65535 ? p->num_masks - m0 : 65535;
+    a.masks = p->box_masks + (size_t)m0 * a.mh * a.mw;
+    a.boxes = p->boxes + 4 * m0;
+    a.out = p->out + (size_t)m0 * plane;
+    a.M = cnt;
+    paste_masks_kernel<<<dim3(gx, (unsigned)cnt), kPasteThreads, smem, st>>>(a);
+    D2B_LAUNCH_CHECK();
+  }
+  return D2B_OK;
+}

@@ -1,2 +1,3 @@
 from .box_list import BoxList, SparseBoxList
 from .image_list import ImageList
+from .mask_ops import reframe_box_masks_to_image_masks

@@ -278,6 +278,25 @@ D2B_API size_t d2b_matrix_nms_workspace_bytes(const d2b_matrix_nms_params* p);
 D2B_API int d2b_matrix_nms(const d2b_matrix_nms_params* p, void* workspace, size_t workspace_bytes,
                            d2b_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Mask paste-back == reframe_box_masks_to_image_masks   lib/structures/mask_ops.py:7-56
+ * (the crop_and_resize-to-full-image + threshold inside detector_postprocess,
+ * lib/modeling/postprocessing.py:9-59).  box_masks [M, mh, mw] fp32, boxes [M, 4]
+ * absolute yxyx in output-image pixels -> out [M, image_h, image_w] uint8 {0,1}.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* box_masks;
+  const float* boxes;
+  int64_t num_masks;
+  int32_t mask_h, mask_w;
+  int32_t image_h, image_w;
+  float mask_threshold;
+  uint8_t* out;
+} d2b_paste_masks_params;
+D2B_API size_t d2b_paste_masks_workspace_bytes(const d2b_paste_masks_params* p);
+D2B_API int d2b_paste_masks(const d2b_paste_masks_params* p, void* workspace, size_t workspace_bytes,
+                            d2b_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

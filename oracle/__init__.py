@@ -278,3 +278,14 @@ def matrix_nms(masks, classes, scores, sum_masks=None, kernel="gaussian", sigma=
                               C.c_int64(hw), kid, C.c_float(sigma), _p(out))
     assert rc == 0
     return out
+
+
+def reframe_box_masks_to_image_masks(box_masks, boxes, image_shape, mask_threshold=0.5):
+    """lib/structures/mask_ops.py:7-56 -> uint8 [M, H, W]."""
+    box_masks = _f32(box_masks)
+    M, mh, mw = box_masks.shape
+    boxes = _f32(boxes).reshape(M, 4)
+    H, W = int(image_shape[0]), int(image_shape[1])
+    out = np.zeros((M, H, W), np.uint8)
+    lib().orc_reframe_box_masks(_p(box_masks), _p(boxes), C.c_int64(M), mh, mw, H, W, C.c_float(mask_threshold), _p(out))
+    return out

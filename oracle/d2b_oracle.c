@@ -756,3 +756,59 @@ ORC_API int orc_matrix_nms(const float* masks, const int64_t* classes, const flo
   free(cmax); free(iou); free(sum_masks);
   return 0;
 }
+
+/* ------------------------------------------------------------------ mask paste-back (SURVEY.md 8f "next" #1) */
+/* lib/structures/mask_ops.py:7-56 reframe_box_masks_to_image_masks:
+ *   boxes -> to_normalized_coordinates (box_list_ops.py:806-839: scale by 1/height, 1/width)
+ *   reverse_boxes = ([0,0,1,1] - min_corner) / (max_corner - min_corner)           (:40-52)
+ *   tf.image.crop_and_resize(box_masks[..., None], reverse_boxes, range(M), image_shape)  (:53-59)
+ *   cast(image_masks > mask_threshold, uint8)                                        (:29-30)
+ * box_masks [M, mh, mw] fp32, boxes [M,4] absolute yxyx, out [M, H, W] uint8. */
+ORC_API void orc_reframe_box_masks(const float* box_masks, const float* boxes, int64_t M, int mh, int mw,
+                                   int H, int W, float thr, uint8_t* out) {
+  const float ys = 1.0f / (float)H, xs = 1.0f / (float)W;
+#pragma omp parallel for num_threads(ORC_NT) schedule(dynamic, 1)
+  for (int64_t b = 0; b < M; ++b) {
+    const float ymin = ys * boxes[4 * b + 0], xmin = xs * boxes[4 * b + 1];
+    const float ymax = ys * boxes[4 * b + 2], xmax = xs * boxes[4 * b + 3];
+    float nb[4];
+    nb[0] = (0.0f - ymin) / (ymax - ymin);
+    nb[1] = (0.0f - xmin) / (xmax - xmin);
+    nb[2] = (1.0f - ymin) / (ymax - ymin);
+    nb[3] = (1.0f - xmin) / (xmax - xmin);
+    float* tmp = (float*)malloc(sizeof(float) * (size_t)H * W);
+    memset(tmp, 0, sizeof(float) * (size_t)H * W);
+    const int32_t zero = 0;
+    /* one box against its own mask: image = mask b as a [1, mh, mw, 1] tensor */
+    const int saved = g_threads;
+    (void)saved;
+    {
+      const float* image = box_masks + (size_t)b * mh * mw;
+      const float y1 = nb[0], x1 = nb[1], y2 = nb[2], x2 = nb[3];
+      const float hs = (H > 1) ? (y2 - y1) * (float)(mh - 1) / (float)(H - 1) : 0.0f;
+      const float ws = (W > 1) ? (x2 - x1) * (float)(mw - 1) / (float)(W - 1) : 0.0f;
+      (void)zero;
+      for (int y = 0; y < H; ++y) {
+        const float in_y = (H > 1) ? y1 * (float)(mh - 1) + (float)y * hs : 0.5f * (y1 + y2) * (float)(mh - 1);
+        if (!(in_y >= 0.0f && in_y <= (float)(mh - 1))) continue;
+        const int top = (int)floorf(in_y), bot = (int)ceilf(in_y);
+        const float ly = in_y - (float)top;
+        for (int x = 0; x < W; ++x) {
+          const float in_x = (W > 1) ? x1 * (float)(mw - 1) + (float)x * ws : 0.5f * (x1 + x2) * (float)(mw - 1);
+          if (!(in_x >= 0.0f && in_x <= (float)(mw - 1))) continue;
+          const int left = (int)floorf(in_x), right = (int)ceilf(in_x);
+          const float lx = in_x - (float)left;
+          const float tl = image[top * mw + left], tr = image[top * mw + right];
+          const float bl = image[bot * mw + left], br = image[bot * mw + right];
+          float t = tr - tl; t = t * lx; t = tl + t;
+          float bb = br - bl; bb = bb * lx; bb = bl + bb;
+          float r = bb - t; r = r * ly; r = t + r;
+          tmp[(size_t)y * W + x] = r;
+        }
+      }
+    }
+    uint8_t* o = out + (size_t)b * H * W;
+    for (size_t p = 0; p < (size_t)H * W; ++p) o[p] = tmp[p] > thr ? 1 : 0;
+    free(tmp);
+  }
+}

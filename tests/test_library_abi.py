@@ -41,7 +41,8 @@ def test_struct_layout_matches_header(lib, tmp_path):
     names = {"roi_align_multilevel": "d2b_roi_align_params", "apply_deltas": "d2b_apply_deltas_params",
              "segmented_topk": "d2b_segmented_topk_params", "batched_nms": "d2b_batched_nms_params",
              "rpn_proposals": "d2b_rpn_proposals_params", "fast_rcnn_postprocess": "d2b_fast_rcnn_params",
-             "retinanet_postprocess": "d2b_retinanet_params", "matrix_nms": "d2b_matrix_nms_params"}
+             "retinanet_postprocess": "d2b_retinanet_params", "matrix_nms": "d2b_matrix_nms_params",
+             "paste_masks": "d2b_paste_masks_params"}
     prog = '#include <stdio.h>\n#include "d2b200.h"\nint main(){' + "".join(
         f'printf("{op} %zu\\n", sizeof({st}));' for op, st in names.items()) + "return 0;}"
     src = tmp_path / "sz.c"
