@@ -37,6 +37,15 @@ WORKLOAD = ("configs[1]: Mask R-CNN R50-FPN, 16 synthetic 800x1333 images/GPU: R
             "box ROIAlign 7x7 on 16000 ROIs, Fast R-CNN per-class NMS, mask ROIAlign 14x14 on 1600 dets")
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/roofline_traffic.json; null when absent)."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("roi_align_box_7x7_dram_bytes_per_launch")
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -171,40 +180,65 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------- CPU arm (oracle = port of the reference's TF CPU path)
-def cpu_step(host, n_images):
+def cpu_step(host, n_images, stage_s=None):
     """The same step on the CPU oracle for the first `n_images` images, following the reference's own
-    data movement (decode ALL anchors, per-level pad/crop/unpermute).  Returns (rois, nms_boxes_in)."""
+    data movement (decode ALL anchors, per-level pad/crop/unpermute).  `stage_s` (list of 4) accumulates
+    the wall time of the four stages."""
     import oracle
     sl = slice(0, n_images)
+    t = [time.perf_counter()]
     props = [oracle.rpn_predict_proposals(d[sl], a) for d, a in zip(host["deltas"], host["anchors"])]
     pb, pl, pv, pn = oracle.find_top_rpn_proposals(props, [x[sl] for x in host["logits"]], host["shapes"][sl], RPN_THR,
                                                    PRE_NMS, POST_NMS, 0.0)
+    t.append(time.perf_counter())
     M = n_images * ROIS_PER_IMAGE
     idx = np.stack([np.repeat(np.arange(n_images), ROIS_PER_IMAGE), np.tile(np.arange(ROIS_PER_IMAGE), n_images)], 1)
     boxes = pb.reshape(-1, 4)
     scales = [1 / 4., 1 / 8., 1 / 16., 1 / 32.]
     feats = [f[sl] for f in host["feats"]]
     box_feats, _ = oracle.roi_pooler(feats, scales, boxes, idx[:, 0], (7, 7), 0)
+    t.append(time.perf_counter())
     pred = oracle.apply_deltas(host["cls_deltas"][:M], boxes, (10., 10., 5., 5.))
     db, ds, dc, dv, dr, dn = oracle.fast_rcnn_inference(pred, host["scores"][:M], idx, (n_images, ROIS_PER_IMAGE),
                                                         host["shapes"][sl], SCORE_THR, NMS_THR, DETS_PER_IMAGE, False)
+    t.append(time.perf_counter())
     didx = np.repeat(np.arange(n_images), DETS_PER_IMAGE)
     mask_feats, _ = oracle.roi_pooler(feats, scales, db.reshape(-1, 4), didx, (14, 14), 0)
+    t.append(time.perf_counter())
+    if stage_s is not None:
+        for i in range(4):
+            stage_s[i] += t[i + 1] - t[i]
     return dict(proposals=(pb, pl, pv), box_feats=box_feats, dets=(db, ds, dc, dv), mask_feats=mask_feats)
 
 
 def time_cpu(host, n_images, steps, warmup):
+    """Returns (ROIs/s, seconds per step, threads, per-stage seconds per step, NMS boxes entering per step)."""
     import oracle
     oracle.build()
     ts = []
+    stage = [0.0, 0.0, 0.0, 0.0]
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        cpu_step(host, n_images)
+        cpu_step(host, n_images, stage if i >= warmup else None)
         dt = time.perf_counter() - t0
         if i >= warmup:
             ts.append(dt)
     rois = n_images * (ROIS_PER_IMAGE + DETS_PER_IMAGE)
-    return rois / float(np.mean(ts)), float(np.mean(ts)), oracle.max_threads()
+    # boxes entering NMS on this sample: min(pre, HWA) per (image, level) + Fast R-CNN candidates
+    nms_in = n_images * sum(min(PRE_NMS, a.shape[0]) for a in host["anchors"]) + \
+        int((host["scores"][:n_images * ROIS_PER_IMAGE, :-1] > SCORE_THR).sum())
+    return rois / float(np.mean(ts)), float(np.mean(ts)), oracle.max_threads(), [x / steps for x in stage], nms_in
+
+
+def cpu_baseline_dict(host, n_images, steps, warmup, sample):
+    v, sec, cores, st, nms_in = time_cpu(host, n_images, steps, warmup)
+    return {"value": v, "unit": "ROIs/s", "cores": cores, "kind": "port", "sample": sample, "ms_per_step": sec * 1e3,
+            "stages_ms": {"rpn_proposals": st[0] * 1e3, "box_roi_align_7x7": st[1] * 1e3, "fast_rcnn_post": st[2] * 1e3,
+                          "mask_roi_align_14x14": st[3] * 1e3},
+            "roi_align_rois_per_s": n_images * (ROIS_PER_IMAGE + DETS_PER_IMAGE) / (st[1] + st[3]),
+            "nms_boxes_per_s": nms_in / (st[0] + st[2]),
+            "note": "oracle/ = C restatement of the reference's TF-CPU path (TensorFlow is not installable here), "
+                    "OpenMP over all host threads"}, v, sec
 
 
 def run_reference(args):
@@ -214,15 +248,13 @@ def run_reference(args):
     n_img = 2
     host = make_host_inputs(n_img)
     steps, warmup = max(min(args.steps, 20), 1), max(min(args.warmup, 2), 1)  # bounded: each step ~0.3-1 s of CPU
-    v, sec, cores = time_cpu(host, n_img, steps, warmup)
+    cb, v, sec = cpu_baseline_dict(host, n_img, steps, warmup, f"{n_img} images/step x {steps} steps")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "ROIs/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": f"{n_img} of the 16 images per step"},
-        "cpu_baseline": {"value": v, "unit": "ROIs/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_img} images/step x {steps} steps, OpenMP over all host threads; oracle/ = C "
-                                   "restatement of the reference's TF-CPU path (TensorFlow is not installable here)"},
+        "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "ROIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -311,7 +343,7 @@ def run_gpu(args):
                 "boxes_in_per_step_per_gpu": rpn_nms_in + cand,
                 "note": "boxes entering NMS / time of the full proposal + Fast R-CNN post stages"},
         "roofline": {"kernel": "roi_align_kernel<float,float,2> (box pooler 7x7, 16000 ROIs)", "bound": "hbm",
-                     "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                     "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": measured_traffic(),
                      "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -346,10 +378,8 @@ def run_gpu(args):
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     if world == 1 and not args.no_cpu:
-        v, sec, cores = time_cpu(host, 2, 2, 1)
-        line["cpu_baseline"] = {"value": v, "unit": "ROIs/s", "cores": cores, "kind": "port",
-                                "sample": "first 2 of the 16 images, 2 timed steps after 1 warm-up, OpenMP all threads",
-                                "ms_per_step": sec * 1e3}
+        cb, _, _ = cpu_baseline_dict(host, 2, 2, 1, "first 2 of the 16 images, 2 timed steps after 1 warm-up")
+        line["cpu_baseline"] = cb
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

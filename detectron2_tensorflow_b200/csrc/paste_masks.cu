@@ -13,7 +13,7 @@ namespace {
 
 constexpr int kPasteThreads = 256;
 constexpr int kPx = 16;      // output pixels (bytes) per thread per iteration: one 16-byte store
-constexpr int kIters = 4;    // iterations per CTA
+constexpr int kIters = 8;    // iterations per CTA
 constexpr int kMaxMaskSmem = 16384;  // floats
 
 struct PasteArgs {
@@ -47,10 +47,10 @@ __device__ __forceinline__ Axis make_axis(float lo, float hi, int crop, int dim)
 __global__ void __launch_bounds__(kPasteThreads) paste_masks_kernel(PasteArgs a) {
   extern __shared__ float s_mask[];
   const long long m = blockIdx.y;
-  const long long plane = (long long)a.H * a.W;
-  const long long cta_first = (long long)blockIdx.x * (kPasteThreads * kPx * kIters);
+  const unsigned plane = (unsigned)a.H * (unsigned)a.W;  // < 2^31 (checked on the host): 32-bit index math
+  const unsigned cta_first = blockIdx.x * (unsigned)(kPasteThreads * kPx * kIters);
   if (cta_first >= plane) return;
-  const long long cta_last = min(plane, cta_first + (long long)kPasteThreads * kPx * kIters) - 1;
+  const unsigned cta_last = min(plane, cta_first + (unsigned)(kPasteThreads * kPx * kIters)) - 1u;
   const float4 bx = __ldg(reinterpret_cast<const float4*>(a.boxes) + m);
   // to_normalized_coordinates: scale by 1/height, 1/width (box_list_ops.py:829-839)
   const float ys = 1.0f / (float)a.H, xs = 1.0f / (float)a.W;
@@ -58,23 +58,22 @@ __global__ void __launch_bounds__(kPasteThreads) paste_masks_kernel(PasteArgs a)
   const Axis ax = make_axis(xs * bx.y, xs * bx.w, a.W, a.mw);
   const float ymax_in = (float)(a.mh - 1), xmax_in = (float)(a.mw - 1);
   // does any output row of this CTA fall inside the mask?
-  const int yA = (int)(cta_first / a.W), yB = (int)(cta_last / a.W);
-  bool any = false;
-  for (int y = yA; y <= yB; ++y) {
-    const float in_y = ay.at(y);
-    any = any || (in_y >= 0.0f && in_y <= ymax_in);
-  }
+  const int yA = (int)(cta_first / (unsigned)a.W), yB = (int)(cta_last / (unsigned)a.W);
+  // at(i) is monotone in i under fp32 rounding (monotone product + monotone sum), so the rows of this
+  // CTA map into [min(at(yA), at(yB)), max(...)]; NaN coordinates compare false -> zeros, as the exact rule.
+  const float e0 = ay.at(yA), e1 = ay.at(yB);
+  const bool any = fminf(e0, e1) <= ymax_in && fmaxf(e0, e1) >= 0.0f && e0 == e0 && e1 == e1;
   const float* mk = a.masks + (size_t)m * a.mh * a.mw;
   if (any && a.smem_mask) {  // block-uniform
     for (int i = threadIdx.x; i < a.mh * a.mw; i += kPasteThreads) s_mask[i] = __ldg(mk + i);
     __syncthreads();
     mk = s_mask;
   }
-  uint8_t* o = a.out + (size_t)m * plane;
+  uint8_t* o = a.out + (size_t)m * (size_t)plane;
   for (int it = 0; it < kIters; ++it) {
-    const long long p0 = cta_first + ((long long)it * kPasteThreads + threadIdx.x) * kPx;
+    const unsigned p0 = cta_first + (unsigned)(it * kPasteThreads + threadIdx.x) * kPx;
     if (p0 >= plane) break;
-    int y = (int)(p0 / a.W), x = (int)(p0 - (long long)y * a.W);
+    int y = (int)(p0 / (unsigned)a.W), x = (int)(p0 - (unsigned)y * (unsigned)a.W);
     unsigned pk[4] = {0u, 0u, 0u, 0u};
     if (any) {
       int top = 0, bot = 0;
@@ -130,6 +129,7 @@ extern "C" int d2b_paste_masks(const d2b_paste_masks_params* p, void*, size_t, d
   D2B_REQUIRE(p->num_masks >= 0 && p->num_masks <= 65535ll * 16, "paste_masks: num_masks=%lld out of range",
               (long long)p->num_masks);
   D2B_REQUIRE(p->mask_h >= 1 && p->mask_w >= 1 && p->image_h >= 1 && p->image_w >= 1, "paste_masks: bad sizes");
+  D2B_REQUIRE((long long)p->image_h * p->image_w < (1ll << 31) - 65536, "paste_masks: image too large");
   if (p->num_masks == 0) return D2B_OK;  // mask_ops.py:25-28: zeros [0, H, W]
   D2B_REQUIRE(p->box_masks && p->boxes && p->out, "paste_masks: NULL pointer");
   PasteArgs a;
