@@ -17,6 +17,11 @@
 //      the row's threshold (exactly k_r of them) through a warp-aggregated slot
 //      counter.
 //   3. sort the k_r winners (sort.cu) and emit values / indices.
+// SIGMOID rows (RetinaNet) first run a histogram over the raw LOGIT keys (no transform) to get a cutoff
+// c <= k-th largest logit; elements below c - margin can never reach the top-k, so the bit-exact sigmoid
+// (ALU-heavy) is evaluated only for the few elements above it.  The margin keeps the computed sigmoid
+// strictly ordered across the gap (true ratio >= 1 + 3e-5 vs <= 4e-7 evaluation error) and the shortcut is
+// disabled in the saturated / underflowing tails (c outside (-80, 8)) where plateaus make index ties matter.
 // HBM-bound scan (4 B per candidate score per pass); no tensor cores.
 #include "kernels.cuh"
 
@@ -28,9 +33,10 @@ typedef unsigned long long u64;
 constexpr int kBins = 2048;
 constexpr int kPasses = 6;
 constexpr int kHistThreads = 256;
-constexpr int kChunk = 8192;   // elements per CTA per pass
+constexpr int kChunk = 8192;        // elements per CTA per pass (rows up to 1 M elements)
+constexpr int kCandCap = 65536;     // candidate-list capacity per SIGMOID row (beyond it the row is re-scanned)
+constexpr int kChunkLong = 65536;   // ... for longer rows (RetinaNet class scores): amortises the per-CTA setup
 constexpr int kBatch = 8;       // independent loads in flight per thread
-constexpr int kCopies = 2;      // replicated shared histograms (lane & 1) to spread same-bin atomics
 
 __constant__ int c_shift[kPasses] = {53, 42, 32, 21, 10, 0};
 __constant__ int c_bits[kPasses] = {11, 11, 10, 11, 11, 10};
@@ -42,19 +48,23 @@ struct RowState {
   unsigned active;   // 1 while more passes are needed
   unsigned k_r;      // min(k, len, k_limit)
   unsigned out_count;  // collect slot counter
-  unsigned cached;     // 1 when pass 0 ran for this row and filled its slice of the key cache
+  unsigned cut_key;    // SIGMOID rows: logit keys below this can never reach the top-k (0 = evaluate all)
+  unsigned pre_done;   // CTAs of the logit pre-histogram that have finished
+  unsigned cand_count; // SIGMOID rows with a cutoff: composites appended to the candidate list by pass 0
+  unsigned compact;    // 1 => the candidate list holds every element that can matter: later passes read it
   unsigned done[kPasses];
 };
 
 struct TopkArgs {
   TopkDesc d;
   int chunks[D2B_MAX_LEVELS];      // CTAs per row in group g
+  int chunk_elems[D2B_MAX_LEVELS]; // elements per CTA in group g (multiple of 4)
   int cta_begin[D2B_MAX_LEVELS + 1];  // first CTA of group g
   RowState* state;
   unsigned* hist;  // [rows][kPasses][kBins]
   int P;           // padded k
-  uint32_t* key_cache;                    // SIGMOID only: transformed keys written by pass 0, read afterwards
-  long long cache_off[D2B_MAX_LEVELS];    // element offset of group g inside key_cache
+  unsigned* prehist;  // SIGMOID only: [rows][kBins] histogram of raw logit keys (top 11 bits)
+  u64* cand;          // SIGMOID only: [rows][kCandCap] composites of the elements above the cutoff
 };
 
 __device__ __forceinline__ bool locate(const TopkArgs& a, int cta, int& g, int& img, int& chunk) {
@@ -74,6 +84,54 @@ __device__ __forceinline__ u64 composite_of(uint32_t key, unsigned idx) {
   return ((u64)key << 32) | (u64)(0xffffffffu - idx);
 }
 
+// Calls f(value, index, valid) for every element of [beg, end) -- and, with valid == false, for the padding
+// slots -- with warp-uniform control flow (f may use warp collectives).  16-byte loads when the chunk is
+// 16-byte aligned, kBatch/4 vectors (or kBatch scalars) in flight per thread.
+template <typename F>
+__device__ __forceinline__ void for_each_elem(const float* x, long long beg, long long end, F f) {
+  const bool vec = ((reinterpret_cast<uintptr_t>(x + beg) & 15) == 0);
+  if (vec) {
+    const long long nvec = (end - beg) >> 2;
+    const float4* xv = reinterpret_cast<const float4*>(x + beg);
+    constexpr int kV = kBatch / 4;
+    for (long long v0 = 0; v0 < nvec; v0 += (long long)kV * kHistThreads) {  // block-uniform trip count
+      float4 q[kV];
+#pragma unroll
+      for (int u = 0; u < kV; ++u) {
+        const long long vi = v0 + (long long)u * kHistThreads + threadIdx.x;
+        q[u] = vi < nvec ? __ldg(xv + vi) : make_float4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < kV; ++u) {
+        const long long vi = v0 + (long long)u * kHistThreads + threadIdx.x;
+        const bool ok = vi < nvec;
+        const long long i = beg + 4 * vi;
+        f(q[u].x, i, ok); f(q[u].y, i + 1, ok); f(q[u].z, i + 2, ok); f(q[u].w, i + 3, ok);
+      }
+    }
+    const long long t0 = beg + 4 * nvec;  // < 4 leftover elements
+    if (t0 < end) {
+      const long long i = t0 + threadIdx.x;
+      const bool ok = i < end;
+      f(ok ? __ldg(x + i) : 0.0f, i, ok);
+    }
+  } else {
+    for (long long i0 = beg; i0 < end; i0 += (long long)kBatch * kHistThreads) {
+      float q[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const long long i = i0 + (long long)u * kHistThreads + threadIdx.x;
+        q[u] = i < end ? __ldg(x + i) : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const long long i = i0 + (long long)u * kHistThreads + threadIdx.x;
+        f(q[u], i, i < end);
+      }
+    }
+  }
+}
+
 __global__ void topk_init(TopkArgs a, int rows, int32_t* seg_len, int32_t* out_counts) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
@@ -88,12 +146,13 @@ __global__ void topk_init(TopkArgs a, int rows, int32_t* seg_len, int32_t* out_c
   if (kr == 0) { s.active = 0; s.threshold = ~0ull; }            // take nothing
   else if (kr == a.d.row_len[g]) { s.active = 0; s.threshold = 0ull; }  // take the whole row
   else { s.active = 1; s.threshold = 0ull; }
-  s.cached = (s.active && a.key_cache != nullptr) ? 1u : 0u;
+  s.cut_key = 0u; s.pre_done = 0u; s.cand_count = 0u; s.compact = 0u;
   a.state[r] = s;
   seg_len[r] = (int32_t)kr;
   if (out_counts) out_counts[r] = (int32_t)kr;
 }
 
+constexpr int kCopies = 4;  // replicated pass-0 histograms (lane & 3) to spread same-bin atomics
 __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass) {
   __shared__ unsigned sh[kCopies][kBins];
   __shared__ int s_last;
@@ -116,33 +175,39 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass) 
   unsigned* my = use_smem ? sh[threadIdx.x & (kCopies - 1)] : gh;
   const long long len = a.d.row_len[g];
   const float* x = a.d.scores[g] + (size_t)img * len;
-  const long long beg = (long long)chunk * kChunk;
-  const long long end = beg + kChunk < len ? beg + kChunk : len;
+  const long long beg = (long long)chunk * a.chunk_elems[g];
+  const long long end = beg + a.chunk_elems[g] < len ? beg + a.chunk_elems[g] : len;
   const int hi_shift = shift + bits;  // bits above the current digit
-  uint32_t* kc = (st->cached) ? a.key_cache + a.cache_off[g] + (size_t)img * len : nullptr;
-  const bool from_cache = kc != nullptr && pass > 0;
-  const uint32_t* src = from_cache ? kc : reinterpret_cast<const uint32_t*>(x);
-  for (long long i0 = beg + threadIdx.x; i0 < end; i0 += (long long)kBatch * kHistThreads) {
-    uint32_t v[kBatch];
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const long long i = i0 + (long long)u * kHistThreads;
-      v[u] = i < end ? __ldg(src + i) : 0u;
+  const unsigned cut = st->cut_key;
+  const int transform = a.d.transform;
+  const bool compact = st->compact != 0;  // set by pass 0; block-uniform
+  unsigned expect = (unsigned)a.chunks[g];
+  if (compact) {
+    // every element that can still matter is in the candidate list: one CTA walks it
+    if (chunk != 0) return;
+    expect = 1u;
+    const u64* cand = a.cand + (size_t)row * kCandCap;
+    const unsigned n = st->cand_count;
+    for (unsigned j = threadIdx.x; j < n; j += kHistThreads) {
+      const u64 c = cand[j];
+      if ((c >> hi_shift) == prefix) atomicAdd(gh + ((unsigned)(c >> shift) & mask), 1u);
     }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const long long i = i0 + (long long)u * kHistThreads;
-      if (i < end) {
-        uint32_t key = v[u];
-        if (!from_cache) {
-          key = value_key(__uint_as_float(v[u]), a.d.transform);
-          if (kc) kc[i] = key;  // pass 0 of a SIGMOID row: the transform is evaluated exactly once per element
+  } else {
+    u64* cand = (pass == 0 && cut != 0u && a.cand) ? a.cand + (size_t)row * kCandCap : nullptr;
+    for_each_elem(x, beg, end, [&](float v, long long i, bool ok) {
+      bool in = ok && float_to_key(v) >= cut;
+      unsigned digit = 0;
+      if (in) {
+        const u64 c = composite_of(value_key(v, transform), (unsigned)i);
+        if (cand) {  // pass 0 of a row with a cutoff: remember the (rare) survivors
+          const unsigned slot = atomicAdd(&st->cand_count, 1u);
+          if (slot < (unsigned)kCandCap) cand[slot] = c;
         }
-        const u64 c = composite_of(key, (unsigned)i);
-        const bool in = (pass == 0) || ((c >> hi_shift) == prefix);
-        if (in) atomicAdd(&my[(unsigned)(c >> shift) & mask], 1u);
+        in = (pass == 0) || ((c >> hi_shift) == prefix);
+        digit = (unsigned)(c >> shift) & mask;
       }
-    }
+      if (in) atomicAdd(my + digit, 1u);
+    });
   }
   __syncthreads();
   if (use_smem) {
@@ -157,11 +222,13 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass) 
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned t = atomicAdd(&st->done[pass], 1u);
-    s_last = (t == (unsigned)a.chunks[g] - 1u);
+    s_last = (t == expect - 1u);
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  if (pass == 0 && threadIdx.x == 0 && cut != 0u && a.cand)
+    st->compact = (*reinterpret_cast<volatile unsigned*>(&st->cand_count) <= (unsigned)kCandCap) ? 1u : 0u;
   // ---- last CTA of the row: find the digit holding the k_rem-th largest element
   const unsigned k_rem = st->k_rem;
   constexpr int kPer = kBins / kHistThreads;  // 8 bins per thread, thread t owns the t-th highest group
@@ -212,41 +279,98 @@ __global__ void __launch_bounds__(kHistThreads) topk_collect(TopkArgs a, u64* ou
   const u64 thr = st->threshold;
   const long long len = a.d.row_len[g];
   const float* x = a.d.scores[g] + (size_t)img * len;
-  const long long beg = (long long)chunk * kChunk;
-  const long long end = beg + kChunk < len ? beg + kChunk : len;
+  const long long beg = (long long)chunk * a.chunk_elems[g];
+  const long long end = beg + a.chunk_elems[g] < len ? beg + a.chunk_elems[g] : len;
   u64* out = out_keys + (size_t)row * a.P;
   const int lane = threadIdx.x & 31;
-  const uint32_t* kc = (st->cached) ? a.key_cache + a.cache_off[g] + (size_t)img * len : nullptr;
-  const uint32_t* src = kc ? kc : reinterpret_cast<const uint32_t*>(x);
-  for (long long i0 = beg + (threadIdx.x & ~31); i0 < end; i0 += (long long)kBatch * kHistThreads) {
-    uint32_t v[kBatch];
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const long long i = i0 + (long long)u * kHistThreads + lane;
-      v[u] = i < end ? __ldg(src + i) : 0u;
-    }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const long long i = i0 + (long long)u * kHistThreads + lane;
-      u64 c = 0;
-      bool take = false;
-      if (i < end) {
-        const uint32_t key = kc ? v[u] : value_key(__uint_as_float(v[u]), a.d.transform);
-        c = composite_of(key, (unsigned)i);
-        take = c >= thr;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, take);
-      if (m) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&st->out_count, (unsigned)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (take) {
-          const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
-          if (slot < (unsigned)a.P) out[slot] = c;
-        }
+  const unsigned cut = st->cut_key;
+  const int transform = a.d.transform;
+  const int P = a.P;
+  auto emit = [&](u64 c, bool take) {  // warp-uniform call
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    if (m) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(&st->out_count, (unsigned)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (take) {
+        const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
+        if (slot < (unsigned)P) out[slot] = c;
       }
     }
+  };
+  if (st->compact) {
+    if (chunk != 0) return;
+    const u64* cand = a.cand + (size_t)row * kCandCap;
+    const unsigned n = st->cand_count;
+    for (unsigned j0 = 0; j0 < n; j0 += kHistThreads) {  // block-uniform trip count
+      const unsigned j = j0 + threadIdx.x;
+      const u64 c = j < n ? cand[j] : 0ull;
+      emit(c, j < n && c >= thr);
+    }
+    return;
   }
+  for_each_elem(x, beg, end, [&](float v, long long i, bool ok) {
+    u64 c = 0;
+    bool take = false;
+    if (ok && float_to_key(v) >= cut) {
+      c = composite_of(value_key(v, transform), (unsigned)i);
+      take = c >= thr;
+    }
+    emit(c, take);
+  });
+}
+
+// SIGMOID rows: histogram of the raw logit keys (top 11 bits), then the cutoff (see the header comment).
+constexpr int kPreBits = 8;             // coarse logit bins: sign + 7 exponent bits (a factor 4 in magnitude)
+constexpr int kPreBins = 1 << kPreBits;
+__global__ void __launch_bounds__(kHistThreads) topk_prehist(TopkArgs a) {
+  // [bin][lane]: every lane owns a bank, so the atomics of a warp never collide however concentrated
+  // the logits are (class logits pile up in 2-3 bins, which serialises a shared histogram 32-way).
+  __shared__ unsigned sh[kPreBins * 32];
+  __shared__ int s_last;
+  int g, img, chunk;
+  if (!locate(a, blockIdx.x, g, img, chunk)) return;
+  const int row = img * a.d.G + g;
+  RowState* st = a.state + row;
+  if (!st->active) return;
+  for (int i = threadIdx.x; i < kPreBins * 32; i += kHistThreads) sh[i] = 0;
+  __syncthreads();
+  const long long len = a.d.row_len[g];
+  const float* x = a.d.scores[g] + (size_t)img * len;
+  const long long beg = (long long)chunk * a.chunk_elems[g];
+  const long long end = beg + a.chunk_elems[g] < len ? beg + a.chunk_elems[g] : len;
+  const int lane = threadIdx.x & 31;
+  for_each_elem(x, beg, end, [&](float v, long long, bool ok) {
+    if (ok) atomicAdd(&sh[(float_to_key(v) >> (32 - kPreBits)) * 32 + lane], 1u);
+  });
+  __syncthreads();
+  unsigned* gh = a.prehist + (size_t)row * kBins;
+  for (int b = threadIdx.x; b < kPreBins; b += kHistThreads) {
+    unsigned v = 0;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) v += sh[b * 32 + ((l + b) & 31)];
+    if (v) atomicAdd(gh + b, v);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&st->pre_done, 1u) == (unsigned)a.chunks[g] - 1u);
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  // thread 0 of the last CTA: walk down from the top bin until k_r elements are covered
+  unsigned acc = 0;
+  int bin = kPreBins - 1;
+  for (; bin > 0; --bin) {
+    acc += __ldcg(gh + bin);
+    if (acc >= st->k_r) break;
+  }
+  const float c = key_to_float((unsigned)bin << (32 - kPreBits));  // lower edge of that bucket: c <= k-th largest logit
+  unsigned cut = 0u;
+  if (c == c && c > -80.0f && c < 8.0f) {
+    const float cm = c - (0.01f * fmaxf(1.0f, fabsf(c)) + 0.01f);
+    cut = float_to_key(cm);
+  }
+  st->cut_key = cut;
 }
 
 __global__ void topk_emit(TopkArgs a, const u64* keys, float* out_values, int32_t* out_indices,
@@ -270,19 +394,17 @@ int fill_args(const TopkDesc& d, TopkArgs& a) {
   a.d = d;
   int cta = 0;
   for (int g = 0; g < d.G; ++g) {
-    a.chunks[g] = (int)((d.row_len[g] + kChunk - 1) / kChunk);
+    a.chunk_elems[g] = d.row_len[g] > (1ll << 20) ? kChunkLong : kChunk;
+    a.chunks[g] = (int)((d.row_len[g] + a.chunk_elems[g] - 1) / a.chunk_elems[g]);
     if (a.chunks[g] < 1) a.chunks[g] = 1;
     a.cta_begin[g] = cta;
     cta += a.chunks[g] * d.rows_per_group;
   }
   for (int g = d.G; g <= D2B_MAX_LEVELS; ++g) a.cta_begin[g] = cta;
+  for (int g = d.G; g < D2B_MAX_LEVELS; ++g) { a.chunks[g] = 1; a.chunk_elems[g] = kChunk; }
   a.P = topk_padded_k(d.k);
-  a.key_cache = nullptr;
-  long long off = 0;
-  for (int g = 0; g < D2B_MAX_LEVELS; ++g) {
-    a.cache_off[g] = off;
-    if (g < d.G) off += d.row_len[g] * (long long)d.rows_per_group;
-  }
+  a.prehist = nullptr;
+  a.cand = nullptr;
   return cta;
 }
 
@@ -294,17 +416,13 @@ int topk_padded_k(int k) {
   return P;
 }
 
-static size_t cache_elems(const TopkDesc& d) {
-  if (d.transform != D2B_TOPK_SIGMOID) return 0;
-  size_t e = 0;
-  for (int g = 0; g < d.G; ++g) e += (size_t)d.row_len[g] * d.rows_per_group;
-  return e;
-}
-
 size_t topk_workspace_bytes(const TopkDesc& d) {
   const size_t rows = (size_t)d.G * d.rows_per_group;
   return ws_slice(rows * sizeof(RowState)) + ws_slice(rows * kPasses * kBins * sizeof(unsigned)) +
-         ws_slice(rows * sizeof(int32_t)) + ws_slice(cache_elems(d) * sizeof(uint32_t));
+         ws_slice(rows * sizeof(int32_t)) +
+         (d.transform == D2B_TOPK_SIGMOID
+              ? ws_slice(rows * kBins * sizeof(unsigned)) + ws_slice(rows * (size_t)kCandCap * sizeof(u64))
+              : 0);
 }
 
 int topk_run(const TopkDesc& d, unsigned long long* out_keys, float* out_values, int32_t* out_indices,
@@ -322,10 +440,18 @@ int topk_run(const TopkDesc& d, unsigned long long* out_keys, float* out_values,
   a.state = w.take<RowState>(rows);
   a.hist = w.take<unsigned>((size_t)rows * kPasses * kBins);
   int32_t* seg_len = w.take<int32_t>(rows);
-  if (cache_elems(d) > 0) a.key_cache = w.take<uint32_t>(cache_elems(d));
+  if (d.transform == D2B_TOPK_SIGMOID) {
+    a.prehist = w.take<unsigned>((size_t)rows * kBins);
+    a.cand = w.take<u64>((size_t)rows * kCandCap);
+    D2B_CUDA(cudaMemsetAsync(a.prehist, 0, (size_t)rows * kBins * sizeof(unsigned), st));
+  }
   D2B_CUDA(cudaMemsetAsync(a.hist, 0, (size_t)rows * kPasses * kBins * sizeof(unsigned), st));
   topk_init<<<(rows + 127) / 128, 128, 0, st>>>(a, rows, seg_len, out_counts);
   D2B_LAUNCH_CHECK();
+  if (d.transform == D2B_TOPK_SIGMOID) {
+    topk_prehist<<<ctas, kHistThreads, 0, st>>>(a);
+    D2B_LAUNCH_CHECK();
+  }
   for (int p = 0; p < kPasses; ++p) {
     topk_hist<<<ctas, kHistThreads, 0, st>>>(a, p);
     D2B_LAUNCH_CHECK();
