@@ -193,13 +193,16 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass) 
       if ((c >> hi_shift) == prefix) atomicAdd(gh + ((unsigned)(c >> shift) & mask), 1u);
     }
   } else {
-    u64* cand = (pass == 0 && cut != 0u && a.cand) ? a.cand + (size_t)row * kCandCap : nullptr;
+    // Candidate list: pass 0 of a row with a logit cutoff remembers every element above the cutoff
+    // (measured: doing the same after pass 1 for rows without a cutoff does not pay at RPN sizes).
+    const bool cand0 = (pass == 0 && cut != 0u);
+    u64* cand = (cand0 && a.cand) ? a.cand + (size_t)row * kCandCap : nullptr;
     for_each_elem(x, beg, end, [&](float v, long long i, bool ok) {
       bool in = ok && float_to_key(v) >= cut;
       unsigned digit = 0;
       if (in) {
         const u64 c = composite_of(value_key(v, transform), (unsigned)i);
-        if (cand) {  // pass 0 of a row with a cutoff: remember the (rare) survivors
+        if (cand) {
           const unsigned slot = atomicAdd(&st->cand_count, 1u);
           if (slot < (unsigned)kCandCap) cand[slot] = c;
         }
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass) 
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (pass == 0 && threadIdx.x == 0 && cut != 0u && a.cand)
+  if (threadIdx.x == 0 && a.cand && !compact && pass == 0 && cut != 0u)
     st->compact = (*reinterpret_cast<volatile unsigned*>(&st->cand_count) <= (unsigned)kCandCap) ? 1u : 0u;
   // ---- last CTA of the row: find the digit holding the k_rem-th largest element
   const unsigned k_rem = st->k_rem;
@@ -421,7 +424,7 @@ size_t topk_workspace_bytes(const TopkDesc& d) {
   return ws_slice(rows * sizeof(RowState)) + ws_slice(rows * kPasses * kBins * sizeof(unsigned)) +
          ws_slice(rows * sizeof(int32_t)) +
          (d.transform == D2B_TOPK_SIGMOID
-              ? ws_slice(rows * kBins * sizeof(unsigned)) + ws_slice(rows * (size_t)kCandCap * sizeof(u64))
+              ? ws_slice(rows * (size_t)kCandCap * sizeof(u64)) + ws_slice(rows * kBins * sizeof(unsigned))
               : 0);
 }
 
@@ -441,8 +444,8 @@ int topk_run(const TopkDesc& d, unsigned long long* out_keys, float* out_values,
   a.hist = w.take<unsigned>((size_t)rows * kPasses * kBins);
   int32_t* seg_len = w.take<int32_t>(rows);
   if (d.transform == D2B_TOPK_SIGMOID) {
-    a.prehist = w.take<unsigned>((size_t)rows * kBins);
     a.cand = w.take<u64>((size_t)rows * kCandCap);
+    a.prehist = w.take<unsigned>((size_t)rows * kBins);
     D2B_CUDA(cudaMemsetAsync(a.prehist, 0, (size_t)rows * kBins * sizeof(unsigned), st));
   }
   D2B_CUDA(cudaMemsetAsync(a.hist, 0, (size_t)rows * kPasses * kBins * sizeof(unsigned), st));

@@ -269,3 +269,32 @@ def test_matrix_nms(cuda, oracle_lib, kernel):
     assert np.array_equal(gb[1], oracle_lib.matrix_nms(m2, c2, s2, None, kernel, 2.0), equal_nan=True)
     with pytest.raises(NotImplementedError):
         matrix_nms(T(masks, cuda), T(classes, cuda), T(scores, cuda), kernel="cosine")
+
+
+# ------------------------------------------------------------------ sigmoid top-k: cutoff / candidate-list paths
+@pytest.mark.parametrize("case", ["typical", "plateau_overflow", "tied_boundary", "negative_tail", "saturated"])
+def test_sigmoid_topk_paths(cuda, oracle_lib, case):
+    """The RetinaNet top-k has a logit pre-histogram cutoff and a candidate list; exercise: the fast path,
+    a candidate list that overflows its capacity (falls back to re-scanning the row), index ties exactly at
+    the k-th value, cutoffs in the negative range, and the saturated regime where the shortcut is disabled."""
+    rng = np.random.default_rng({"typical": 1, "plateau_overflow": 2, "tied_boundary": 3, "negative_tail": 4, "saturated": 5}[case])
+    n, k = 300000, 1000
+    if case == "typical":
+        x = (rng.standard_normal(n) * 1.5 - 4.6).astype(np.float32)
+    elif case == "plateau_overflow":
+        x = np.full(n, 1.0, np.float32)          # > 65536 elements above the cutoff, all tied
+        x[rng.integers(0, n, 500)] = 3.0
+    elif case == "tied_boundary":
+        x = (rng.standard_normal(n) * 1.5 - 4.6).astype(np.float32)
+        kth = np.sort(x)[-k]
+        x[rng.integers(0, n, 400)] = kth         # many exact copies of the k-th value
+    elif case == "negative_tail":
+        x = (rng.standard_normal(n) * 0.5 - 30.0).astype(np.float32)
+    else:
+        x = (rng.standard_normal(n) * 40.0).astype(np.float32)
+    vals, idx, cnt = segmented_top_k([T(x[None], cuda)], k, sigmoid=True)
+    p = oracle_lib.sigmoidf(x)
+    wv, wi = oracle_lib.top_k(p, k)
+    assert cnt[0, 0].item() == k
+    assert np.array_equal(idx[0, 0].cpu().numpy(), wi), case
+    assert np.array_equal(vals[0, 0].cpu().numpy(), wv)
