@@ -338,12 +338,43 @@ __global__ void frcnn_prep_kernel(const float4* boxes, const float* scores, cons
     s = __ldg(scores + i * (K + 1) + k);
     cand = s > thresh;
   }
-  // warp-aggregated atomics when the whole warp belongs to one image (the common, image-major case)
+  // Block-aggregated atomics when the whole CTA belongs to one image (the common, image-major case): one
+  // atomicMax and one atomicAdd per CTA instead of one per warp -- the 16 per-image counters would otherwise
+  // serialise ~40k same-address atomics at L2.
+  __shared__ long long s_n[8];
+  __shared__ int s_max[8], s_cnt[8], s_base;
+  const int warp = threadIdx.x >> 5;
   const long long n0 = __shfl_sync(0xffffffffu, n, 0);
-  const bool uniform = __all_sync(0xffffffffu, n == n0) && n0 >= 0;
-  if (uniform) {
-    const int wm = __reduce_max_sync(0xffffffffu, mbits);
-    const unsigned cm = __ballot_sync(0xffffffffu, cand);
+  const bool wuni = __all_sync(0xffffffffu, n == n0) && n0 >= 0;
+  const int wm = __reduce_max_sync(0xffffffffu, mbits);
+  const unsigned cm = __ballot_sync(0xffffffffu, cand);
+  if (lane == 0) {
+    s_n[warp] = wuni ? n0 : -2;
+    s_max[warp] = wm;
+    s_cnt[warp] = __popc(cm);
+  }
+  __syncthreads();
+  bool buni = true;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) buni = buni && (s_n[w] == s_n[0]);
+  buni = buni && s_n[0] >= 0;
+  if (buni) {
+    if (threadIdx.x == 0) {
+      int bm = 0, tot = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { bm = max(bm, s_max[w]); tot += s_cnt[w]; }
+      if (bm > 0) atomicMax(max_coord_bits + s_n[0], bm);
+      s_base = tot ? atomicAdd(count + s_n[0], tot) : 0;
+    }
+    __syncthreads();
+    if (cand) {
+      int before = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) before += (w < warp) ? s_cnt[w] : 0;
+      const int slot = s_base + before + __popc(cm & ((1u << lane) - 1u));
+      if (slot < P) keys[(size_t)n0 * P + slot] = make_key(s, (unsigned)(k * Rmax + (int)r));
+    }
+  } else if (wuni) {
     int base = 0;
     if (lane == 0) {
       if (wm > 0) atomicMax(max_coord_bits + n0, wm);
