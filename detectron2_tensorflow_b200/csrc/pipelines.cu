@@ -123,38 +123,93 @@ __global__ void __launch_bounds__(kMergeThreads) rpn_merge_rank_kernel(
   const int total = s_off[a.L];
   const int kk = min(total, a.post);  // :105
   uint32_t* gk = use_smem ? s_keys : gkeys + (size_t)n * a.P2;
-  for (int ci = threadIdx.x; ci < total; ci += kMergeThreads) {
-    int l = 0;
-    while (l + 1 < a.L && ci >= s_off[l + 1]) ++l;
-    const int row = n * a.L + l;
-    const int pos = keep[(size_t)row * a.post + (ci - s_off[l])];
-    gk[ci] = float_to_key(seg_scores[(size_t)row * a.k + pos]);
-  }
-  __syncthreads();
-  for (int ci = threadIdx.x; ci < total; ci += kMergeThreads) {
-    int l = 0;
-    while (l + 1 < a.L && ci >= s_off[l + 1]) ++l;
-    const uint32_t key = gk[ci];
-    int rank = ci - s_off[l];
-    for (int l2 = 0; l2 < a.L; ++l2) {
-      if (l2 == l) continue;
-      const uint32_t* kl = gk + s_off[l2];
-      int lo = 0, hi = s_off[l2 + 1] - s_off[l2];
-      while (lo < hi) {  // first position whose element does NOT precede (key, ci)
-        const int mid = (lo + hi) >> 1;
-        const uint32_t ke = kl[mid];
-        const bool before = (l2 < l) ? (ke >= key) : (ke > key);
-        if (before) lo = mid + 1; else hi = mid;
+  constexpr int kPer = 8;  // survivors per thread per sweep: their dependent gathers are issued together
+  for (int base = 0; base < total; base += kPer * kMergeThreads) {
+    int lv[kPer], pos[kPer];
+    float sc[kPer];
+    float4 bx[kPer];
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int ci = base + u * kMergeThreads + threadIdx.x;
+      lv[u] = 0; pos[u] = 0;
+      if (ci < total) {
+        int l = 0;
+        while (l + 1 < a.L && ci >= s_off[l + 1]) ++l;
+        lv[u] = l;
+        pos[u] = keep[(size_t)(n * a.L + l) * a.post + (ci - s_off[l])];
       }
-      rank += lo;
     }
-    if (rank < a.post) {
-      const int row = n * a.L + l;
-      const int pos = keep[(size_t)row * a.post + (ci - s_off[l])];
-      const size_t o = (size_t)n * a.post + rank;
-      out_boxes[o] = seg_boxes[(size_t)row * a.k + pos];
-      out_logits[o] = seg_scores[(size_t)row * a.k + pos];
-      out_valid[o] = 1;
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int ci = base + u * kMergeThreads + threadIdx.x;
+      if (ci < total) {
+        const size_t o = (size_t)(n * a.L + lv[u]) * a.k + pos[u];
+        sc[u] = seg_scores[o];
+        bx[u] = seg_boxes[o];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int ci = base + u * kMergeThreads + threadIdx.x;
+      if (ci < total) gk[ci] = float_to_key(sc[u]);
+    }
+    __syncthreads();  // (total <= kPer * kMergeThreads in practice: one sweep; keys of this sweep visible)
+    if (base + kPer * kMergeThreads < total) continue;  // multi-sweep: ranks are computed in the second loop
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int ci = base + u * kMergeThreads + threadIdx.x;
+      if (ci >= total || total > kPer * kMergeThreads) continue;
+      const int l = lv[u];
+      const uint32_t key = gk[ci];
+      int rank = ci - s_off[l];
+      for (int l2 = 0; l2 < a.L; ++l2) {
+        if (l2 == l) continue;
+        const uint32_t* kl = gk + s_off[l2];
+        int lo = 0, hi = s_off[l2 + 1] - s_off[l2];
+        while (lo < hi) {  // first position whose element does NOT precede (key, ci)
+          const int mid = (lo + hi) >> 1;
+          const uint32_t ke = kl[mid];
+          const bool before = (l2 < l) ? (ke >= key) : (ke > key);
+          if (before) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+      }
+      if (rank < a.post) {
+        const size_t o = (size_t)n * a.post + rank;
+        out_boxes[o] = bx[u];
+        out_logits[o] = sc[u];
+        out_valid[o] = 1;
+      }
+    }
+  }
+  if (total > kPer * kMergeThreads) {
+    // rare: more survivors than one sweep holds (L * min(post, k) > 8192): straightforward second pass
+    __syncthreads();
+    for (int ci = threadIdx.x; ci < total; ci += kMergeThreads) {
+      int l = 0;
+      while (l + 1 < a.L && ci >= s_off[l + 1]) ++l;
+      const uint32_t key = gk[ci];
+      int rank = ci - s_off[l];
+      for (int l2 = 0; l2 < a.L; ++l2) {
+        if (l2 == l) continue;
+        const uint32_t* kl = gk + s_off[l2];
+        int lo = 0, hi = s_off[l2 + 1] - s_off[l2];
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          const uint32_t ke = kl[mid];
+          const bool before = (l2 < l) ? (ke >= key) : (ke > key);
+          if (before) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+      }
+      if (rank < a.post) {
+        const int row = n * a.L + l;
+        const int p2 = keep[(size_t)row * a.post + (ci - s_off[l])];
+        const size_t o = (size_t)n * a.post + rank;
+        out_boxes[o] = seg_boxes[(size_t)row * a.k + p2];
+        out_logits[o] = seg_scores[(size_t)row * a.k + p2];
+        out_valid[o] = 1;
+      }
     }
   }
   for (int j = kk + threadIdx.x; j < a.post; j += kMergeThreads) {  // zero padding :111-114
