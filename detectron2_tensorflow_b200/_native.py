@@ -56,7 +56,9 @@ class RpnProposalsParams(C.Structure):
                 ("num_images", _i32), ("image_shapes", _vp), ("nms_thresh", _f32), ("pre_nms_topk", _i32),
                 ("post_nms_topk", _i32), ("min_box_side_len", _f32), ("weights", _f32 * 4),
                 ("scale_clamp", _f32), ("out_boxes", _vp), ("out_logits", _vp), ("out_valid", _vp),
-                ("out_num_valid", _vp), ("out_nms_boxes_in", _vp)]
+                ("out_num_valid", _vp), ("out_nms_boxes_in", _vp),
+                ("cell_anchors", _vp * MAX_LEVELS), ("num_cell_anchors", _i32 * MAX_LEVELS),
+                ("grid_w", _i32 * MAX_LEVELS), ("stride", _i32 * MAX_LEVELS)]
 
 
 class FastRcnnParams(C.Structure):
@@ -73,7 +75,9 @@ class RetinanetParams(C.Structure):
                 ("topk_candidates", _i32), ("score_thresh", _f32), ("nms_thresh", _f32),
                 ("max_detections", _i32), ("weights", _f32 * 4), ("scale_clamp", _f32), ("out_boxes", _vp),
                 ("out_scores", _vp), ("out_classes", _vp), ("out_valid", _vp), ("out_num", _vp),
-                ("out_nms_boxes_in", _vp)]
+                ("out_nms_boxes_in", _vp),
+                ("cell_anchors", _vp * MAX_LEVELS), ("num_cell_anchors", _i32 * MAX_LEVELS),
+                ("grid_w", _i32 * MAX_LEVELS), ("stride", _i32 * MAX_LEVELS)]
 
 
 class MatrixNmsParams(C.Structure):

@@ -43,6 +43,22 @@ __device__ __forceinline__ int block_compact(bool flag, int& base_reg, int* s_wa
   return slot;
 }
 
+// Anchor of flat index idx: read from the materialised table, or synthesised as
+// DefaultAnchorGenerator.grid_anchors does (anchor_generator.py:92-109): cell anchor + integer grid shift.
+struct AnchorSrc {
+  const float4* table;  // [hwa, 4] or NULL
+  const float4* cell;   // [A, 4]
+  int A, gw, stride;
+  __device__ __forceinline__ float4 at(unsigned idx) const {
+    if (table) return __ldg(table + idx);
+    const unsigned a = idx % (unsigned)A, cellidx = idx / (unsigned)A;
+    const unsigned gx = cellidx % (unsigned)gw, gy = cellidx / (unsigned)gw;
+    const float sy = (float)(gy * (unsigned)stride), sx = (float)(gx * (unsigned)stride);
+    const float4 c = __ldg(cell + a);
+    return make_float4(sy + c.x, sx + c.y, sy + c.z, sx + c.w);
+  }
+};
+
 // =====================================================================================
 // RPN
 // =====================================================================================
@@ -50,7 +66,7 @@ struct RpnArgs {
   const float* logits[D2B_MAX_LEVELS];
   const float4* proposals[D2B_MAX_LEVELS];
   const float4* deltas[D2B_MAX_LEVELS];
-  const float4* anchors[D2B_MAX_LEVELS];
+  AnchorSrc anchors[D2B_MAX_LEVELS];
   long long hwa[D2B_MAX_LEVELS];
   int L, N;
   const int32_t* shapes;
@@ -82,7 +98,7 @@ __global__ void __launch_bounds__(kRpnThreads) rpn_decode_kernel(RpnArgs a, cons
       const unsigned idx = key_index(keys[(size_t)row * a.P + j]);
       score = __ldg(a.logits[l] + rbase + idx);
       if (a.proposals[l]) box = __ldg(a.proposals[l] + rbase + idx);
-      else box = d2b_decode(__ldg(a.deltas[l] + rbase + idx), __ldg(a.anchors[l] + idx), a.w[0], a.w[1], a.w[2], a.w[3], a.clampv);
+      else box = d2b_decode(__ldg(a.deltas[l] + rbase + idx), a.anchors[l].at(idx), a.w[0], a.w[1], a.w[2], a.w[3], a.clampv);
       box = d2b_clip(box, h, w);  // rpn_outputs.py:77-80
       ok = true;
       if (a.min_len > 0.0f) {     // prune_small_boxes, :83-87
@@ -244,7 +260,11 @@ int rpn_plan(const d2b_rpn_proposals_params* p, RpnPlan& pl) {
     a.logits[l] = in ? p->logits[l] : nullptr;
     a.proposals[l] = in ? reinterpret_cast<const float4*>(p->proposals[l]) : nullptr;
     a.deltas[l] = in ? reinterpret_cast<const float4*>(p->deltas[l]) : nullptr;
-    a.anchors[l] = in ? reinterpret_cast<const float4*>(p->anchors[l]) : nullptr;
+    a.anchors[l].table = in ? reinterpret_cast<const float4*>(p->anchors[l]) : nullptr;
+    a.anchors[l].cell = in ? reinterpret_cast<const float4*>(p->cell_anchors[l]) : nullptr;
+    a.anchors[l].A = in && p->num_cell_anchors[l] > 0 ? p->num_cell_anchors[l] : 1;
+    a.anchors[l].gw = in && p->grid_w[l] > 0 ? p->grid_w[l] : 1;
+    a.anchors[l].stride = in ? p->stride[l] : 0;
     a.hwa[l] = in ? p->hwa[l] : 0;
     td.scores[l] = a.logits[l];
     td.row_len[l] = a.hwa[l];
@@ -253,8 +273,12 @@ int rpn_plan(const d2b_rpn_proposals_params* p, RpnPlan& pl) {
       D2B_REQUIRE(p->hwa[l] >= 0, "hwa[%d] negative", l);
       if (p->num_images > 0 && p->hwa[l] > 0) {
         D2B_REQUIRE(p->logits[l] != nullptr, "logits[%d] is NULL", l);
-        D2B_REQUIRE(p->proposals[l] != nullptr || (p->deltas[l] != nullptr && p->anchors[l] != nullptr),
-                    "level %d: need proposals or deltas+anchors", l);
+        D2B_REQUIRE(p->proposals[l] != nullptr ||
+                        (p->deltas[l] != nullptr &&
+                         (p->anchors[l] != nullptr ||
+                          (p->cell_anchors[l] != nullptr && p->num_cell_anchors[l] > 0 && p->grid_w[l] > 0 &&
+                           p->hwa[l] % p->num_cell_anchors[l] == 0))),
+                    "level %d: need proposals, or deltas + anchors, or deltas + cell_anchors/grid_w/stride", l);
       }
       if (p->hwa[l] > maxlen) maxlen = p->hwa[l];
     }
@@ -452,7 +476,7 @@ __global__ void frcnn_prep_kernel(const float4* boxes, const float* scores, cons
 // ------------------------------------------------------------------ RetinaNet front
 struct RetinaArgs {
   const float4* deltas[D2B_MAX_LEVELS];
-  const float4* anchors[D2B_MAX_LEVELS];
+  AnchorSrc anchors[D2B_MAX_LEVELS];
   long long hwa[D2B_MAX_LEVELS];
   int L, N, K;
   float thresh;
@@ -491,7 +515,7 @@ __global__ void __launch_bounds__(kRetThreads) retina_decode_kernel(RetinaArgs a
       if (slot >= 0) {
         const unsigned anc = idx / (unsigned)a.K;       // :333
         const int cls = (int)(idx - anc * (unsigned)a.K);  // :334
-        const float4 box = d2b_decode(__ldg(a.deltas[l] + rbase + anc), __ldg(a.anchors[l] + anc), a.w[0], a.w[1],
+        const float4 box = d2b_decode(__ldg(a.deltas[l] + rbase + anc), a.anchors[l].at(anc), a.w[0], a.w[1],
                                       a.w[2], a.w[3], a.clampv);
         const size_t o = (size_t)n * a.stride + slot;
         cand_boxes[o] = box;
@@ -680,7 +704,11 @@ int retina_plan(const d2b_retinanet_params* p, RetinaPlan& pl) {
   for (int l = 0; l < D2B_MAX_LEVELS; ++l) {
     const bool in = l < p->num_levels;
     a.deltas[l] = in ? reinterpret_cast<const float4*>(p->box_delta[l]) : nullptr;
-    a.anchors[l] = in ? reinterpret_cast<const float4*>(p->anchors[l]) : nullptr;
+    a.anchors[l].table = in ? reinterpret_cast<const float4*>(p->anchors[l]) : nullptr;
+    a.anchors[l].cell = in ? reinterpret_cast<const float4*>(p->cell_anchors[l]) : nullptr;
+    a.anchors[l].A = in && p->num_cell_anchors[l] > 0 ? p->num_cell_anchors[l] : 1;
+    a.anchors[l].gw = in && p->grid_w[l] > 0 ? p->grid_w[l] : 1;
+    a.anchors[l].stride = in ? p->stride[l] : 0;
     a.hwa[l] = in ? p->hwa[l] : 0;
     td.scores[l] = in ? p->box_cls[l] : nullptr;
     td.row_len[l] = in ? p->hwa[l] * p->num_classes : 0;
@@ -688,7 +716,9 @@ int retina_plan(const d2b_retinanet_params* p, RetinaPlan& pl) {
     if (in) {
       D2B_REQUIRE(p->hwa[l] >= 0 && p->hwa[l] * p->num_classes < (1ll << 32) - 1, "hwa[%d] out of range", l);
       if (p->num_images > 0 && p->hwa[l] > 0)
-        D2B_REQUIRE(p->box_cls[l] && p->box_delta[l] && p->anchors[l], "level %d: NULL input", l);
+        D2B_REQUIRE(p->box_cls[l] && p->box_delta[l] &&
+                        (p->anchors[l] || (p->cell_anchors[l] && p->num_cell_anchors[l] > 0 && p->grid_w[l] > 0)),
+                    "level %d: NULL input", l);
       if (p->hwa[l] > maxhwa) maxhwa = p->hwa[l];
       if (td.k_limit[l] == 0 && p->hwa[l] == 0) td.row_len[l] = 0;
     }

@@ -19,7 +19,11 @@ def _rpn_call(logits, proposals, deltas, anchors, image_shapes, nms_thresh, pre_
     lg = [x.reshape(N, -1) for x in lg]
     pr = None if proposals is None else [nv.to_device(x, dev, torch.float32).reshape(N, -1, 4) for x in proposals]
     dl = None if deltas is None else [nv.to_device(x, dev, torch.float32).reshape(N, -1, 4) for x in deltas]
-    an = None if anchors is None else [nv.to_device(x, dev, torch.float32).reshape(-1, 4) for x in anchors]
+    from ..anchor_generator import GridAnchors
+    an = None
+    if anchors is not None:
+        an = [a if isinstance(a, GridAnchors) else nv.to_device(a, dev, torch.float32).reshape(-1, 4) for a in anchors]
+    keep_alive = []
     shapes = nv.to_device(image_shapes, dev, torch.int32).reshape(N, 2)
     post = int(post_nms_topk)
     out_boxes = torch.empty((N, post, 4), dtype=torch.float32, device=dev)
@@ -34,9 +38,19 @@ def _rpn_call(logits, proposals, deltas, anchors, image_shapes, nms_thresh, pre_
             assert pr[l].shape[1] == lg[l].shape[1]
             p.proposals[l] = pr[l].data_ptr()
         if dl is not None:
-            assert dl[l].shape[1] == lg[l].shape[1] and an[l].shape[0] == lg[l].shape[1]
+            assert dl[l].shape[1] == lg[l].shape[1]
             p.deltas[l] = dl[l].data_ptr()
-            p.anchors[l] = an[l].data_ptr()
+            if isinstance(an[l], GridAnchors):  # synthesised in-kernel (anchor_generator.py:92-109)
+                assert an[l].num_anchors == lg[l].shape[1]
+                cell = nv.to_device(an[l].cell_anchors, dev, torch.float32).reshape(-1, 4)
+                keep_alive.append(cell)
+                p.cell_anchors[l] = cell.data_ptr()
+                p.num_cell_anchors[l] = cell.shape[0]
+                p.grid_w[l] = an[l].grid_hw[1]
+                p.stride[l] = an[l].stride
+            else:
+                assert an[l].shape[0] == lg[l].shape[1]
+                p.anchors[l] = an[l].data_ptr()
     p.num_levels, p.num_images = L, N
     p.image_shapes = shapes.data_ptr()
     p.nms_thresh = float(nms_thresh)
@@ -96,6 +110,7 @@ class RPNOutputs(object):
         self.images = images
         self.pred_objectness_logits = pred_objectness_logits
         self.pred_anchor_deltas = pred_anchor_deltas
+        # BoxLists / tensors of materialised anchors, or GridAnchors descriptors (synthesised in-kernel)
         self.anchors = [a.boxes if hasattr(a, "boxes") else a for a in anchors]
         self.num_images = pred_objectness_logits[0].shape[0]
 
@@ -103,6 +118,8 @@ class RPNOutputs(object):
         """Decode ALL anchors (rpn_outputs.py:403-426) -> L tensors (N, Hi*Wi*A, 4)."""
         out = []
         for anchors_i, deltas_i in zip(self.anchors, self.pred_anchor_deltas):
+            if hasattr(anchors_i, "materialize"):
+                anchors_i = anchors_i.materialize().to(deltas_i.device)
             N = deltas_i.shape[0]
             d = deltas_i.reshape(-1, 4)
             a = anchors_i.unsqueeze(0).expand(N, -1, -1).reshape(-1, 4)

@@ -33,7 +33,10 @@ class RetinaNetInference(object):
         N = box_cls[0].shape[0]
         cls = [nv.to_device(x, dev, torch.float32).reshape(N, -1, K) for x in box_cls]   # reshape_to_N_HWA_K :371
         dl = [nv.to_device(x, dev, torch.float32).reshape(N, -1, 4) for x in box_delta]  # :372
-        an = [nv.to_device(a.boxes if hasattr(a, "boxes") else a, dev, torch.float32).reshape(-1, 4) for a in anchors]
+        from ..anchor_generator import GridAnchors
+        an = [a if isinstance(a, GridAnchors) else
+              nv.to_device(a.boxes if hasattr(a, "boxes") else a, dev, torch.float32).reshape(-1, 4) for a in anchors]
+        keep_alive = []
         L = len(cls)
         T = int(self.max_detections_per_image)
         ob = torch.empty((N, T, 4), dtype=torch.float32, device=dev)
@@ -42,8 +45,17 @@ class RetinaNetInference(object):
         ov = torch.empty((N, T), dtype=torch.bool, device=dev)
         p = nv.RetinanetParams()
         for l in range(L):
-            assert cls[l].shape[1] == dl[l].shape[1] == an[l].shape[0]
-            p.box_cls[l], p.box_delta[l], p.anchors[l] = cls[l].data_ptr(), dl[l].data_ptr(), an[l].data_ptr()
+            assert cls[l].shape[1] == dl[l].shape[1]
+            p.box_cls[l], p.box_delta[l] = cls[l].data_ptr(), dl[l].data_ptr()
+            if isinstance(an[l], GridAnchors):
+                assert an[l].num_anchors == cls[l].shape[1]
+                cell = nv.to_device(an[l].cell_anchors, dev, torch.float32).reshape(-1, 4)
+                keep_alive.append(cell)
+                p.cell_anchors[l], p.num_cell_anchors[l] = cell.data_ptr(), cell.shape[0]
+                p.grid_w[l], p.stride[l] = an[l].grid_hw[1], an[l].stride
+            else:
+                assert an[l].shape[0] == cls[l].shape[1]
+                p.anchors[l] = an[l].data_ptr()
             p.hwa[l] = cls[l].shape[1]
         p.num_levels, p.num_images, p.num_classes = L, N, K
         p.topk_candidates = int(self.topk_candidates)

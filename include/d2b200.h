@@ -195,6 +195,13 @@ typedef struct {
   uint8_t* out_valid;    /* [N, post] */
   int32_t* out_num_valid; /* optional [N] */
   int64_t* out_nms_boxes_in; /* optional [1]: total boxes that entered NMS (metric bookkeeping) */
+  /* In-kernel anchor synthesis == DefaultAnchorGenerator.grid_anchors (lib/modeling/anchor_generator.py:92-109),
+   * used for level l when anchors[l] == NULL:
+   *   anchor(y, x, a) = cell_anchors[l][a] + (y*stride, x*stride, y*stride, x*stride),  index = (y*grid_w + x)*A + a */
+  const float* cell_anchors[D2B_MAX_LEVELS]; /* [num_cell_anchors[l], 4] or NULL */
+  int32_t num_cell_anchors[D2B_MAX_LEVELS];
+  int32_t grid_w[D2B_MAX_LEVELS];
+  int32_t stride[D2B_MAX_LEVELS];
 } d2b_rpn_proposals_params;
 D2B_API size_t d2b_rpn_proposals_workspace_bytes(const d2b_rpn_proposals_params* p);
 D2B_API int d2b_rpn_proposals(const d2b_rpn_proposals_params* p, void* workspace,
@@ -235,7 +242,7 @@ D2B_API int d2b_fast_rcnn_postprocess(const d2b_fast_rcnn_params* p, void* works
 typedef struct {
   const float* box_cls[D2B_MAX_LEVELS];   /* [N, hwa[l], K] logits */
   const float* box_delta[D2B_MAX_LEVELS]; /* [N, hwa[l], 4] */
-  const float* anchors[D2B_MAX_LEVELS];   /* [hwa[l], 4] */
+  const float* anchors[D2B_MAX_LEVELS];   /* [hwa[l], 4] or NULL (then cell_anchors below) */
   int64_t hwa[D2B_MAX_LEVELS];
   int32_t num_levels, num_images, num_classes;
   int32_t topk_candidates;
@@ -249,6 +256,13 @@ typedef struct {
   uint8_t* out_valid;   /* [N, max_det] */
   int32_t* out_num;     /* optional [N] */
   int64_t* out_nms_boxes_in; /* optional [1] */
+  /* In-kernel anchor synthesis == DefaultAnchorGenerator.grid_anchors (lib/modeling/anchor_generator.py:92-109),
+   * used for level l when anchors[l] == NULL:
+   *   anchor(y, x, a) = cell_anchors[l][a] + (y*stride, x*stride, y*stride, x*stride),  index = (y*grid_w + x)*A + a */
+  const float* cell_anchors[D2B_MAX_LEVELS]; /* [num_cell_anchors[l], 4] or NULL */
+  int32_t num_cell_anchors[D2B_MAX_LEVELS];
+  int32_t grid_w[D2B_MAX_LEVELS];
+  int32_t stride[D2B_MAX_LEVELS];
 } d2b_retinanet_params;
 D2B_API size_t d2b_retinanet_postprocess_workspace_bytes(const d2b_retinanet_params* p);
 D2B_API int d2b_retinanet_postprocess(const d2b_retinanet_params* p, void* workspace,

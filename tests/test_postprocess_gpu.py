@@ -298,3 +298,39 @@ def test_sigmoid_topk_paths(cuda, oracle_lib, case):
     assert cnt[0, 0].item() == k
     assert np.array_equal(idx[0, 0].cpu().numpy(), wi), case
     assert np.array_equal(vals[0, 0].cpu().numpy(), wv)
+
+
+# ------------------------------------------------------------------ in-kernel anchors (SURVEY.md 8f "next" #2)
+def test_anchor_generator_and_in_kernel_anchors(cuda, oracle_lib):
+    from detectron2_tensorflow_b200.modeling import DefaultAnchorGenerator
+    padded = (160, 224)
+    strides = syn.RPN_STRIDES
+    gen = DefaultAnchorGenerator([[s] for s in syn.RPN_SIZES], [list(syn.ASPECT_RATIOS)], strides, device=cuda)
+    grids = [syn.level_hw(s, padded) for s in strides]
+    tables = gen.grid_anchors(grids)
+    want_tables = syn.rpn_anchors(padded_hw=padded)          # numpy restatement of anchor_generator.py:92-144
+    for t, w in zip(tables, want_tables):
+        assert np.array_equal(t.cpu().numpy(), w)
+    anchors, logits, deltas, shapes = _small_rpn(13, "gaussian")
+    props = [oracle_lib.rpn_predict_proposals(d, a) for d, a in zip(deltas, anchors)]
+    wb, wl, wv, _ = oracle_lib.find_top_rpn_proposals(props, logits, shapes, 0.7, 300, 200, 0.0)
+    outs = RPNOutputs(Box2BoxTransform((1., 1., 1., 1.)), ImageList(None, T(shapes, cuda)),
+                      [T(x, cuda) for x in logits], [T(d, cuda) for d in deltas], gen.grid_descriptors(grids))
+    r = outs.find_top_proposals(0.7, 300, 200, 0.0)
+    assert np.array_equal(r.boxes.cpu().numpy(), wb) and np.array_equal(r.get_field("is_valid").cpu().numpy(), wv)
+    assert np.array_equal(r.get_field("objectness_logits").cpu().numpy(), wl)
+    # RetinaNet with synthesised anchors
+    rng = np.random.default_rng(3)
+    K = 5
+    rstr = syn.RETINA_STRIDES
+    rgen = DefaultAnchorGenerator([[s * 4 * 2 ** (i / 3.0) for i in range(3)] for s in rstr], [list(syn.ASPECT_RATIOS)],
+                                  rstr, device=cuda)
+    rgrids = [syn.level_hw(s, (256, 320)) for s in rstr]
+    ran = [a.cpu().numpy() for a in rgen.grid_anchors(rgrids)]
+    cls = [(rng.standard_normal((2, a.shape[0], K)) * 1.5 - 2.5).astype(np.float32) for a in ran]
+    dl = [(rng.standard_normal((2, a.shape[0], 4)) * 0.3).astype(np.float32) for a in ran]
+    wb, ws, wc, wv, wn = oracle_lib.retinanet_inference(cls, dl, ran, K, 200, 0.05, 0.5, 50)
+    head = RetinaNetInference(num_classes=K, topk_candidates=200, max_detections_per_image=50)
+    res = head.inference([T(x, cuda) for x in cls], [T(x, cuda) for x in dl], rgen.grid_descriptors(rgrids))
+    assert np.array_equal(res.boxes.cpu().numpy(), wb) and np.array_equal(res.get_field('scores').cpu().numpy(), ws)
+    assert np.array_equal(res.get_field('pred_classes').cpu().numpy(), wc)
