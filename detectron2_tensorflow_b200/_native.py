@@ -90,6 +90,51 @@ class PasteMasksParams(C.Structure):
                 ("image_h", _i32), ("image_w", _i32), ("mask_threshold", _f32), ("out", _vp)]
 
 
+class CropAndResizeParams(C.Structure):
+    _fields_ = [("image", _vp), ("num_images", _i32), ("height", _i32), ("width", _i32), ("channels", _i32),
+                ("boxes", _vp), ("box_ind", _vp), ("num_boxes", _i64), ("crop_h", _i32), ("crop_w", _i32),
+                ("aligned", _i32), ("pad_border", _i32), ("out", _vp)]
+
+
+class DecodeClipFilterParams(C.Structure):
+    _fields_ = [("deltas", _vp), ("anchors", _vp), ("num_images", _i32), ("n", _i64), ("image_shapes", _vp),
+                ("weights", _f32 * 4), ("scale_clamp", _f32), ("min_box_side_len", _f32), ("out_boxes", _vp),
+                ("out_keep", _vp)]
+
+
+class GetDeltasParams(C.Structure):
+    _fields_ = [("src_boxes", _vp), ("target_boxes", _vp), ("n", _i64), ("weights", _f32 * 4), ("out", _vp)]
+
+
+class PairwiseIouParams(C.Structure):
+    _fields_ = [("boxes1", _vp), ("boxes2", _vp), ("n1", _i64), ("n2", _i64), ("out", _vp)]
+
+
+MATCH_MAX_THRESHOLDS = 4
+MATCH_MAX_GT = 1024
+
+
+class LabelBoxesParams(C.Structure):
+    _fields_ = [("pred_boxes", _vp), ("pred_shared", _i32), ("pred_counts", _vp), ("num_images", _i32),
+                ("num_preds", _i32), ("gt_boxes", _vp), ("gt_valid", _vp), ("gt_crowd", _vp), ("gt_difficult", _vp),
+                ("max_gt", _i32), ("thresholds", _f32 * MATCH_MAX_THRESHOLDS), ("num_thresholds", _i32),
+                ("labels", _i32 * (MATCH_MAX_THRESHOLDS + 1)), ("allow_low_quality_matches", _i32),
+                ("boundary_threshold", _f32), ("image_shapes", _vp), ("compute_deltas", _i32), ("weights", _f32 * 4),
+                ("out_matches", _vp), ("out_labels", _vp), ("out_deltas", _vp)]
+
+
+class MatcherParams(C.Structure):
+    _fields_ = [("match_quality_matrix", _vp), ("crowd_matrix", _vp), ("difficult_matrix", _vp), ("num_gt", _i32),
+                ("num_crowd", _i32), ("num_difficult", _i32), ("use_crowd", _i32), ("use_difficult", _i32),
+                ("num_preds", _i64), ("thresholds", _f32 * MATCH_MAX_THRESHOLDS), ("num_thresholds", _i32),
+                ("labels", _i32 * (MATCH_MAX_THRESHOLDS + 1)), ("allow_low_quality_matches", _i32),
+                ("out_matches", _vp), ("out_labels", _vp)]
+
+
+class RoiAlignBackwardParams(C.Structure):
+    _fields_ = [("fwd", RoiAlignParams), ("grad_out", _vp), ("grad_features", _vp * MAX_LEVELS)]
+
+
 # op name -> params struct; every op exports d2b_<op> and d2b_<op>_workspace_bytes
 OPS = {
     "roi_align_multilevel": RoiAlignParams,
@@ -101,6 +146,13 @@ OPS = {
     "retinanet_postprocess": RetinanetParams,
     "matrix_nms": MatrixNmsParams,
     "paste_masks": PasteMasksParams,
+    "crop_and_resize_aligned": CropAndResizeParams,
+    "decode_clip_filter": DecodeClipFilterParams,
+    "get_deltas": GetDeltasParams,
+    "pairwise_iou": PairwiseIouParams,
+    "label_boxes": LabelBoxesParams,
+    "matcher": MatcherParams,
+    "roi_align_backward": RoiAlignBackwardParams,
 }
 EXPORTS = ["d2b_version", "d2b_status_string", "d2b_last_error", "d2b_kernel_launch_count"] + \
           [f"d2b_{op}{sfx}" for op in OPS for sfx in ("", "_workspace_bytes")]

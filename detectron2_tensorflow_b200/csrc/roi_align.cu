@@ -315,6 +315,92 @@ __global__ void __launch_bounds__(kThreads) roi_align_kernel(const RoiAlignArgs 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward: gradient w.r.t. the feature maps (AvgPoolGrad -> CropAndResizeGradImage ->
+// MirrorPadGrad -> per-level scatter in the reference's TF graph).  Same CTA-per-ROI frame and
+// tap tables as the forward kernel; one warp per crop sample, lanes own 16-byte channel groups,
+// the four corner contributions go out as vector reductions (RED.E.ADD.F32x4: one L2 atomic
+// transaction per 16 B instead of four).  The SYMMETRIC pad fold is the same index clamp the
+// forward uses, so border rows accumulate straight onto the edge pixel.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+struct RoiAlignGradArgs {
+  RoiAlignArgs f;
+  const float* grad_out;
+  float* grad[D2B_MAX_LEVELS];
+};
+
+__global__ void __launch_bounds__(kThreads) roi_align_backward_kernel(const RoiAlignGradArgs ga) {
+  const RoiAlignArgs& a = ga.f;
+  __shared__ Tap ty[kMaxSamples];
+  __shared__ Tap tx[kMaxSamples];
+  __shared__ int s_level;
+  __shared__ int s_img;
+  const long long roi = blockIdx.x;
+  const int s1 = a.sr > 0 ? a.sr : 1;
+  const int ch = a.oh * s1, cw = a.ow * s1;
+  const int tid = threadIdx.x;
+  if (tid < ch + cw || tid == kThreads - 1) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(a.boxes) + roi);
+    int lvl = 0;
+    if (a.L > 1) lvl = level_of(b.x, b.y, b.z, b.w, a.min_level, a.max_level, a.canon_size, a.canon_level);
+    const Level L = a.lv[lvl];
+    const float padf = a.pad ? 1.0f : 0.0f;
+    if (tid < ch) {
+      const float lo = b.x * L.scale + padf, hi = b.z * L.scale + padf;
+      ty[tid] = make_tap(lo, hi, tid, ch, L.H + 2 * a.pad, a.pad, L.H, a.aligned, L.W * a.C);
+    } else if (tid < ch + cw) {
+      const float lo = b.y * L.scale + padf, hi = b.w * L.scale + padf;
+      tx[tid - ch] = make_tap(lo, hi, tid - ch, cw, L.W + 2 * a.pad, a.pad, L.W, a.aligned, a.C);
+    }
+    if (tid == kThreads - 1) {
+      long long img = a.bidx64 ? reinterpret_cast<const long long*>(a.bidx)[roi * a.bidx_stride]
+                               : (long long)reinterpret_cast<const int*>(a.bidx)[roi * a.bidx_stride];
+      s_level = lvl;
+      s_img = (img >= 0 && img < a.N) ? (int)img : -1;
+    }
+  }
+  __syncthreads();
+  const int img = s_img;
+  if (img < 0) return;  // TF skips boxes whose box_ind is out of range
+  const int lvl = s_level;
+  const Level L = a.lv[lvl];
+  const int C = a.C;
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kThreads / 32;
+  float* base = ga.grad[lvl] + (size_t)img * L.H * L.W * C;
+  const float* gbase = ga.grad_out + (size_t)roi * a.oh * a.ow * C;
+  const float cnt = (float)(s1 * s1);
+  const int groups_total = C / 4;
+  const int bin_begin = blockIdx.y * kBinsPerCta;
+  const int bin_end = min(bin_begin + kBinsPerCta, a.oh * a.ow);
+  const int samples = s1 * s1;
+  // work item = (bin, sub-sample); a warp walks items, lanes walk channel groups
+  for (int item = bin_begin * samples + warp; item < bin_end * samples; item += kWarps) {
+    const int bin = item / samples, sub = item - bin * samples;
+    const int oy = bin / a.ow, ox = bin - oy * a.ow;
+    const int dy = sub / s1, dx = sub - dy * s1;
+    const Tap y = ty[oy * s1 + dy];
+    const Tap x = tx[ox * s1 + dx];
+    if (!(y.valid && x.valid)) continue;
+    const float omy = 1.0f - y.w, omx = 1.0f - x.w;
+    const float* g = gbase + (size_t)bin * C;
+    for (int grp = lane; grp < groups_total; grp += 32) {
+      float4 gv = __ldcs(reinterpret_cast<const float4*>(g) + grp);
+      if (s1 > 1) { gv.x = gv.x / cnt; gv.y = gv.y / cnt; gv.z = gv.z / cnt; gv.w = gv.w / cnt; }
+      const int c = grp * 4;
+      const float4 dt = make_float4(omy * gv.x, omy * gv.y, omy * gv.z, omy * gv.w);
+      const float4 db = make_float4(y.w * gv.x, y.w * gv.y, y.w * gv.z, y.w * gv.w);
+      red_add_v4(base + y.i0 + x.i0 + c, omx * dt.x, omx * dt.y, omx * dt.z, omx * dt.w);
+      red_add_v4(base + y.i0 + x.i1 + c, x.w * dt.x, x.w * dt.y, x.w * dt.z, x.w * dt.w);
+      red_add_v4(base + y.i1 + x.i0 + c, omx * db.x, omx * db.y, omx * db.z, omx * db.w);
+      red_add_v4(base + y.i1 + x.i1 + c, x.w * db.x, x.w * db.y, x.w * db.z, x.w * db.w);
+    }
+  }
+}
+
 template <typename TIn, typename TOut>
 int launch(const RoiAlignArgs& a, cudaStream_t st) {
   constexpr int E = Vec<TIn>::kElems;
@@ -337,8 +423,8 @@ using namespace d2b;
 
 extern "C" size_t d2b_roi_align_multilevel_workspace_bytes(const d2b_roi_align_params*) { return 0; }
 
-extern "C" int d2b_roi_align_multilevel(const d2b_roi_align_params* p, void* /*workspace*/,
-                                        size_t /*workspace_bytes*/, d2b_stream_t stream) {
+// validates the forward description and fills the kernel argument block; `backward` relaxes the pointer checks
+static int fill_args(const d2b_roi_align_params* p, RoiAlignArgs& a, bool backward) {
   D2B_REQUIRE(p != nullptr, "params is NULL");
   // poolers.py:148-150 asserts len(x) == len(scales); unknown pooler types raise ValueError (:118)
   D2B_REQUIRE(p->num_levels >= 1 && p->num_levels <= D2B_MAX_LEVELS, "num_levels=%d out of [1,%d]",
@@ -350,18 +436,21 @@ extern "C" int d2b_roi_align_multilevel(const d2b_roi_align_params* p, void* /*w
   D2B_REQUIRE(p->output_h * s1 <= kMaxSamples && p->output_w * s1 <= kMaxSamples &&
                   (p->output_h + p->output_w) * s1 < kThreads,
               "output_size*sampling_ratio too large (max %d per axis)", kMaxSamples);
+  if (backward) {
+    D2B_REQUIRE(p->feature_dtype == D2B_DTYPE_F32 && p->out_dtype == D2B_DTYPE_F32, "backward is fp32 only");
+  }
   D2B_REQUIRE(p->feature_dtype == D2B_DTYPE_F32 || p->feature_dtype == D2B_DTYPE_BF16, "bad feature_dtype");
   D2B_REQUIRE(p->out_dtype == D2B_DTYPE_F32 || (p->out_dtype == D2B_DTYPE_BF16 && p->feature_dtype == D2B_DTYPE_BF16),
               "bad out_dtype");
   const int E = p->feature_dtype == D2B_DTYPE_F32 ? 4 : 8;
   D2B_REQUIRE(p->channels > 0 && p->channels % E == 0, "channels=%d must be a multiple of %d", p->channels, E);
   D2B_REQUIRE(p->num_images > 0, "num_images must be positive");
+  a.M = 0;
   if (p->num_rois == 0) return D2B_OK;
-  D2B_REQUIRE(p->boxes && p->batch_idx && p->out, "boxes/batch_idx/out must be non-NULL");
+  D2B_REQUIRE(p->boxes && p->batch_idx && (backward || p->out), "boxes/batch_idx/out must be non-NULL");
 
-  RoiAlignArgs a;
   for (int l = 0; l < p->num_levels; ++l) {
-    D2B_REQUIRE(p->features[l] != nullptr && p->height[l] > 0 && p->width[l] > 0, "level %d: bad feature map", l);
+    D2B_REQUIRE((backward || p->features[l] != nullptr) && p->height[l] > 0 && p->width[l] > 0, "level %d: bad feature map", l);
     D2B_REQUIRE((long long)p->height[l] * p->width[l] * p->channels < (1ll << 31), "level %d: H*W*C must fit in int32", l);
     a.lv[l].ptr = p->features[l];
     a.lv[l].H = p->height[l];
@@ -382,9 +471,60 @@ extern "C" int d2b_roi_align_multilevel(const d2b_roi_align_params* p, void* /*w
     D2B_REQUIRE(p->min_level > 0 && p->canonical_box_size > 0, "min_level and canonical_box_size must be positive");
   }
 
+  return D2B_OK;
+}
+
+extern "C" int d2b_roi_align_multilevel(const d2b_roi_align_params* p, void* /*workspace*/,
+                                        size_t /*workspace_bytes*/, d2b_stream_t stream) {
+  RoiAlignArgs a;
+  const int rc = fill_args(p, a, false);
+  if (rc != D2B_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->level_counts) D2B_CUDA(cudaMemsetAsync(p->level_counts, 0, sizeof(int32_t) * p->num_levels, st));
+  if (a.M == 0) return D2B_OK;
   if (p->feature_dtype == D2B_DTYPE_F32) return launch<float, float>(a, st);
   if (p->out_dtype == D2B_DTYPE_F32) return launch<__nv_bfloat16, float>(a, st);
   return launch<__nv_bfloat16, __nv_bfloat16>(a, st);
+}
+
+extern "C" size_t d2b_roi_align_backward_workspace_bytes(const d2b_roi_align_backward_params*) { return 0; }
+
+extern "C" int d2b_roi_align_backward(const d2b_roi_align_backward_params* p, void*, size_t, d2b_stream_t stream) {
+  D2B_REQUIRE(p != nullptr, "params is NULL");
+  RoiAlignGradArgs g;
+  const int rc = fill_args(&p->fwd, g.f, true);
+  if (rc != D2B_OK) return rc;
+  if (g.f.M == 0) return D2B_OK;
+  D2B_REQUIRE(p->grad_out != nullptr, "grad_out is NULL");
+  for (int l = 0; l < D2B_MAX_LEVELS; ++l) {
+    g.grad[l] = p->grad_features[l < p->fwd.num_levels ? l : 0];
+    D2B_REQUIRE(g.grad[l] != nullptr, "grad_features[%d] is NULL", l);
+  }
+  g.grad_out = p->grad_out;
+  g.f.level_counts = nullptr;
+  g.f.level_out = nullptr;
+  const dim3 grid((unsigned)g.f.M, (unsigned)((g.f.oh * g.f.ow + kBinsPerCta - 1) / kBinsPerCta));
+  roi_align_backward_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(g);
+  D2B_LAUNCH_CHECK();
+  return D2B_OK;
+}
+
+extern "C" size_t d2b_crop_and_resize_aligned_workspace_bytes(const d2b_crop_and_resize_params*) { return 0; }
+
+// functional.py:100-166 on one map: the multi-level kernel with one level of scale 1
+extern "C" int d2b_crop_and_resize_aligned(const d2b_crop_and_resize_params* p, void* ws, size_t ws_bytes,
+                                           d2b_stream_t stream) {
+  D2B_REQUIRE(p != nullptr, "params is NULL");
+  d2b_roi_align_params r = {};
+  r.features[0] = p->image;
+  r.height[0] = p->height; r.width[0] = p->width; r.scale[0] = 1.0f;
+  r.num_levels = 1; r.num_images = p->num_images; r.channels = p->channels;
+  r.feature_dtype = D2B_DTYPE_F32; r.out_dtype = D2B_DTYPE_F32;
+  r.boxes = p->boxes; r.batch_idx = p->box_ind; r.batch_idx_is_int64 = 0; r.batch_idx_stride = 1;
+  r.num_rois = p->num_boxes;
+  r.output_h = p->crop_h; r.output_w = p->crop_w;
+  r.sampling_ratio = 0; r.aligned = p->aligned; r.pad_border = p->pad_border;
+  r.min_level = 0; r.canonical_box_size = 224; r.canonical_level = 4;
+  r.out = p->out;
+  return d2b_roi_align_multilevel(&r, ws, ws_bytes, stream);
 }

@@ -86,4 +86,67 @@ def crop_and_resize(image, boxes, box_ind, crop_size, aligned=True, method='bili
     """
     if method != 'bilinear':
         raise ValueError("only method='bilinear' is on the hot path")
-    return _roi_align_call([image], [1.0], boxes, box_ind, 1, crop_size, 0, aligned, pad_border)
+    if not (isinstance(image, torch.Tensor) and image.dtype == torch.float32):
+        return _roi_align_call([image], [1.0], boxes, box_ind, 1, crop_size, 0, aligned, pad_border)
+    host = not image.is_cuda
+    dev = nv.device_of(image, boxes)
+    img = nv.to_device(image, dev, torch.float32)
+    if img.dim() != 4:
+        raise ValueError("image must be an NHWC rank-4 tensor")
+    b = nv.to_device(boxes, dev, torch.float32).reshape(-1, 4)
+    bi = nv.to_device(box_ind, dev, torch.int32)  # functional.py:165 casts box_ind to int32
+    out = torch.empty((b.shape[0], int(crop_size[0]), int(crop_size[1]), img.shape[3]), dtype=torch.float32, device=dev)
+    p = nv.CropAndResizeParams()
+    p.image = img.data_ptr()
+    p.num_images, p.height, p.width, p.channels = img.shape
+    p.boxes, p.box_ind, p.num_boxes = b.data_ptr(), bi.data_ptr(), b.shape[0]
+    p.crop_h, p.crop_w = int(crop_size[0]), int(crop_size[1])
+    p.aligned, p.pad_border = int(bool(aligned)), int(bool(pad_border))
+    p.out = out.data_ptr()
+    nv.call("crop_and_resize_aligned", p, dev)
+    return nv.to_host(out) if host else out
+
+
+def _roi_align_backward_call(grad_out, feature_shapes, scales, boxes, batch_idx, sampling_ratio, aligned,
+                             pad_border=True, min_level=0, canonical_box_size=224, canonical_level=4,
+                             grad_features=None):
+    """Launcher of d2b_roi_align_backward: gradient of `_roi_align_call` w.r.t. every level's NHWC map.
+
+    `feature_shapes`: list of (N, H, W, C).  `grad_features` (optional list of fp32 tensors) is accumulated
+    into; when None, zero-initialised tensors are created."""
+    dev = nv.device_of(grad_out, boxes)
+    host = not grad_out.is_cuda
+    g = nv.to_device(grad_out, dev, torch.float32)
+    M, oh, ow, Cc = g.shape
+    boxes = nv.to_device(boxes, dev, torch.float32).reshape(-1, 4)
+    assert boxes.shape[0] == M
+    if not isinstance(batch_idx, torch.Tensor):
+        batch_idx = torch.as_tensor(batch_idx)
+    if batch_idx.dtype not in (torch.int32, torch.int64):
+        batch_idx = batch_idx.to(torch.int32)
+    batch_idx = batch_idx.to(dev).contiguous()
+    if grad_features is None:
+        grad_features = [torch.zeros(tuple(s), dtype=torch.float32, device=dev) for s in feature_shapes]
+    p = nv.RoiAlignBackwardParams()
+    f = p.fwd
+    for l, gf in enumerate(grad_features):
+        assert gf.is_cuda and gf.is_contiguous() and gf.dtype == torch.float32 and gf.shape[3] == Cc
+        f.height[l], f.width[l] = gf.shape[1], gf.shape[2]
+        f.scale[l] = float(scales[l])
+        p.grad_features[l] = gf.data_ptr()
+    f.num_levels, f.num_images, f.channels = len(grad_features), grad_features[0].shape[0], Cc
+    f.feature_dtype = f.out_dtype = nv.DTYPE_F32
+    f.boxes, f.batch_idx = boxes.data_ptr(), batch_idx.data_ptr()
+    f.batch_idx_is_int64 = 1 if batch_idx.dtype == torch.int64 else 0
+    f.batch_idx_stride = 1
+    f.num_rois = M
+    f.output_h, f.output_w = oh, ow
+    f.sampling_ratio = int(sampling_ratio)
+    f.aligned, f.pad_border = int(bool(aligned)), int(bool(pad_border))
+    f.min_level = int(min_level)
+    f.canonical_box_size, f.canonical_level = int(canonical_box_size), int(canonical_level)
+    p.grad_out = g.data_ptr()
+    nv.call("roi_align_backward", p, dev)
+    if host:
+        return [nv.to_host(t) for t in grad_features]
+    return grad_features

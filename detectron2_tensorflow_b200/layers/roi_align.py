@@ -1,6 +1,6 @@
 """Drop-in for lib/layers/roi_align.py (`ROIAlign`, :9-75)."""
 from .base import Layer
-from .functional import _roi_align_call
+from .functional import _roi_align_call, _roi_align_backward_call
 
 
 class ROIAlign(Layer):
@@ -33,6 +33,13 @@ class ROIAlign(Layer):
         """
         return _roi_align_call([inputs], [self.spatial_scale], boxes, box_inds, 1, self.output_size,
                                self.sampling_ratio, self.aligned, True)
+
+    def backward(self, grad_output, input_shape, boxes, box_inds, grad_input=None):
+        """Gradient of `call` w.r.t. `inputs` (what TF autodiff runs in training; boxes get none,
+        functional.py:120).  grad_output [B, oh, ow, C] -> [N, H, W, C]; accumulates into `grad_input` if given."""
+        return _roi_align_backward_call(grad_output, [input_shape], [self.spatial_scale], boxes, box_inds,
+                                        self.sampling_ratio, self.aligned,
+                                        grad_features=None if grad_input is None else [grad_input])[0]
 
     def __repr__(self):
         tmpstr = self.__class__.__name__ + "("

@@ -4,3 +4,4 @@ from .proposal_generator.rpn_outputs import find_top_rpn_proposals, RPNOutputs
 from .roi_heads.fast_rcnn import fast_rcnn_inference, FastRCNNOutputs
 from .single_stage_heads.retinanet import RetinaNetInference
 from .anchor_generator import DefaultAnchorGenerator, GridAnchors
+from .matcher import Matcher, label_boxes

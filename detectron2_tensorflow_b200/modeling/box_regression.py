@@ -14,12 +14,27 @@ __all__ = ["Box2BoxTransform"]
 class Box2BoxTransform(object):
     """
     The box-to-box transform defined in R-CNN, parameterized by 4 deltas (dy, dx, dh, dw).
-    Only `apply_deltas` is on the inference hot path (`get_deltas` builds training targets).
+    `apply_deltas` is on the inference hot path; `get_deltas` builds training targets (:38-74).
     """
 
     def __init__(self, weights, scale_clamp=_DEFAULT_SCALE_CLAMP):
         self.weights = weights
         self.scale_clamp = scale_clamp
+
+    def get_deltas(self, src_boxes, target_boxes):
+        """Deltas (dy, dx, dh, dw) that transform `src_boxes` into `target_boxes` (both (N, 4))."""
+        host = not src_boxes.is_cuda
+        dev = nv.device_of(src_boxes, target_boxes)
+        s = nv.to_device(src_boxes, dev, torch.float32).reshape(-1, 4)
+        t = nv.to_device(target_boxes, dev, torch.float32).reshape(-1, 4)
+        assert s.shape == t.shape
+        out = torch.empty_like(s)
+        p = nv.GetDeltasParams()
+        p.src_boxes, p.target_boxes, p.n, p.out = s.data_ptr(), t.data_ptr(), s.shape[0], out.data_ptr()
+        for i in range(4):
+            p.weights[i] = float(self.weights[i])
+        nv.call("get_deltas", p, dev)
+        return nv.to_host(out) if host else out
 
     def apply_deltas(self, deltas, boxes):
         """

@@ -11,7 +11,7 @@ import torch
 
 from .. import _native as nv
 from ..layers import Layer, ROIAlign
-from ..layers.functional import _roi_align_call
+from ..layers.functional import _roi_align_call, _roi_align_backward_call
 
 __all__ = ["ROIPooler", "assign_boxes_to_levels"]
 
@@ -111,3 +111,12 @@ class ROIPooler(Layer):
             canonical_level=self.canonical_level, want_levels=True)
         self.last_level_counts = counts
         return out
+
+    def backward(self, grad_output, x_shapes, instances, grad_x=None):
+        """Gradient of `call` w.r.t. the feature maps `x` (list of (N,H,W,C) shapes) -> list of NHWC tensors.
+        One kernel: each ROI scatters into the level `assign_boxes_to_levels` gave it."""
+        assert len(x_shapes) == len(self.level_poolers)
+        return _roi_align_backward_call(grad_output, x_shapes, self.scales, instances.data.boxes,
+                                        instances.indices[:, 0].contiguous(), self.sampling_ratio, self.aligned,
+                                        min_level=self.min_level, canonical_box_size=self.canonical_box_size,
+                                        canonical_level=self.canonical_level, grad_features=grad_x)

@@ -311,6 +311,166 @@ D2B_API size_t d2b_paste_masks_workspace_bytes(const d2b_paste_masks_params* p);
 D2B_API int d2b_paste_masks(const d2b_paste_masks_params* p, void* workspace, size_t workspace_bytes,
                             d2b_stream_t stream);
 
+/* ========================================================================
+ * SURVEY.md section 8(b) single-stage entry points (thin: same kernels as above)
+ * ====================================================================== */
+
+/* ------------------------------------------------------------------------
+ * crop_and_resize (single map)                    lib/layers/functional.py:100-166
+ * image [N,H,W,C] fp32 NHWC, boxes [M,4] in image pixels, box_ind [M] int32
+ * -> out [M, crop_h, crop_w, C].  aligned / pad_border as in the reference.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* image;
+  int32_t num_images, height, width, channels;
+  const float* boxes;
+  const int32_t* box_ind;
+  int64_t num_boxes;
+  int32_t crop_h, crop_w;
+  int32_t aligned, pad_border;
+  float* out;
+} d2b_crop_and_resize_params;
+D2B_API size_t d2b_crop_and_resize_aligned_workspace_bytes(const d2b_crop_and_resize_params* p);
+D2B_API int d2b_crop_and_resize_aligned(const d2b_crop_and_resize_params* p, void* workspace,
+                                        size_t workspace_bytes, d2b_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * decode + clip + small-box filter of one RPN level, all images
+ *   RPNOutputs.predict_proposals            rpn_outputs.py:403-426
+ *   clip_to_window / prune_small_boxes      box_list_ops.py:112-147, 502-517 (rpn_outputs.py:77-86)
+ * deltas [N, n, 4], anchors [n, 4] (shared by the images), image_shapes [N,2]
+ * -> out_boxes [N, n, 4] (clipped), out_keep [N, n] uint8 (1 = survives the
+ *    min_box_side_len filter; all 1 when min_box_side_len <= 0).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* deltas;
+  const float* anchors;
+  int32_t num_images;
+  int64_t n;
+  const int32_t* image_shapes;
+  float weights[4];
+  float scale_clamp;
+  float min_box_side_len;
+  float* out_boxes;
+  uint8_t* out_keep;
+} d2b_decode_clip_filter_params;
+D2B_API size_t d2b_decode_clip_filter_workspace_bytes(const d2b_decode_clip_filter_params* p);
+D2B_API int d2b_decode_clip_filter(const d2b_decode_clip_filter_params* p, void* workspace,
+                                   size_t workspace_bytes, d2b_stream_t stream);
+
+/* ========================================================================
+ * SURVEY.md section 8(f) "next" row #3: training-side neighbours of the path
+ * ====================================================================== */
+
+/* ------------------------------------------------------------------------
+ * Box2BoxTransform.get_deltas                 lib/modeling/box_regression.py:38-74
+ * src_boxes [n,4], target_boxes [n,4] -> out [n,4] (dy,dx,dh,dw)
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* src_boxes;
+  const float* target_boxes;
+  int64_t n;
+  float weights[4];
+  float* out;
+} d2b_get_deltas_params;
+D2B_API size_t d2b_get_deltas_workspace_bytes(const d2b_get_deltas_params* p);
+D2B_API int d2b_get_deltas(const d2b_get_deltas_params* p, void* workspace, size_t workspace_bytes,
+                           d2b_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * pairwise_iou (iou_type='iou')             lib/structures/box_list_ops.py:295-334
+ * boxes1 [n1,4], boxes2 [n2,4] -> out [n1, n2]
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* boxes1;
+  const float* boxes2;
+  int64_t n1, n2;
+  float* out;
+} d2b_pairwise_iou_params;
+D2B_API size_t d2b_pairwise_iou_workspace_bytes(const d2b_pairwise_iou_params* p);
+D2B_API int d2b_pairwise_iou(const d2b_pairwise_iou_params* p, void* workspace, size_t workspace_bytes,
+                             d2b_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Label assignment == pairwise_iou + Matcher fused (the [G, P] matrices are never written)
+ *   Matcher.__call__ / get_low_quality_matches_    lib/modeling/matcher.py:57-174
+ *   RPNOutputs._get_ground_truth                   rpn_outputs.py:245-304
+ *   ROIHeads.label_and_sample_proposals            roi_heads.py:100-165 (up to subsample_labels,
+ *                                                  whose tf.random_shuffle has no defined parity)
+ * Per image: valid GT list = gt_valid & ~gt_crowd & ~gt_difficult (order kept, boolean_mask),
+ * crowd list = gt_crowd, difficult list = gt_difficult.  out_matches indexes the VALID list.
+ * Rows >= pred_counts[i]: matches 0, labels -1, deltas 0.
+ * ---------------------------------------------------------------------- */
+#define D2B_MATCH_MAX_THRESHOLDS 4
+#define D2B_MATCH_MAX_GT 1024
+typedef struct {
+  const float* pred_boxes;     /* [N, P, 4], or [P, 4] when pred_shared (anchors) */
+  int32_t pred_shared;
+  const int32_t* pred_counts;  /* optional [N]: valid prefix (proposals' is_valid) */
+  int32_t num_images;
+  int32_t num_preds;           /* P */
+  const float* gt_boxes;       /* [N, G, 4] */
+  const uint8_t* gt_valid;     /* [N, G] */
+  const uint8_t* gt_crowd;     /* optional [N, G] */
+  const uint8_t* gt_difficult; /* optional [N, G] */
+  int32_t max_gt;              /* G <= D2B_MATCH_MAX_GT */
+  float thresholds[D2B_MATCH_MAX_THRESHOLDS]; /* ascending, without the -inf/+inf ends */
+  int32_t num_thresholds;
+  int32_t labels[D2B_MATCH_MAX_THRESHOLDS + 1]; /* in {-1,0,1} */
+  int32_t allow_low_quality_matches;
+  float boundary_threshold;    /* < 0: off (rpn_outputs.py:268) */
+  const int32_t* image_shapes; /* [N,2], needed when boundary_threshold >= 0 */
+  int32_t compute_deltas;      /* 1: out_deltas = get_deltas(pred, matched gt) where label > 0, else 0 */
+  float weights[4];
+  int64_t* out_matches;        /* [N, P] */
+  int64_t* out_labels;         /* [N, P] */
+  float* out_deltas;           /* [N, P, 4] or NULL */
+} d2b_label_boxes_params;
+D2B_API size_t d2b_label_boxes_workspace_bytes(const d2b_label_boxes_params* p);
+D2B_API int d2b_label_boxes(const d2b_label_boxes_params* p, void* workspace, size_t workspace_bytes,
+                            d2b_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Matcher.__call__ on materialised matrices          lib/modeling/matcher.py:57-150
+ * match_quality_matrix [num_gt, num_preds]; optional crowd / difficult matrices
+ * (use_crowd / use_difficult = "the argument was not None"; zero rows allowed).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* match_quality_matrix;
+  const float* crowd_matrix;
+  const float* difficult_matrix;
+  int32_t num_gt, num_crowd, num_difficult;
+  int32_t use_crowd, use_difficult;
+  int64_t num_preds;
+  float thresholds[D2B_MATCH_MAX_THRESHOLDS];
+  int32_t num_thresholds;
+  int32_t labels[D2B_MATCH_MAX_THRESHOLDS + 1];
+  int32_t allow_low_quality_matches;
+  int64_t* out_matches; /* [num_preds] */
+  int64_t* out_labels;  /* [num_preds] */
+} d2b_matcher_params;
+D2B_API size_t d2b_matcher_workspace_bytes(const d2b_matcher_params* p);
+D2B_API int d2b_matcher(const d2b_matcher_params* p, void* workspace, size_t workspace_bytes, d2b_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * ROIPooler / ROIAlign backward: gradient w.r.t. the feature maps (what TF
+ * autodiff runs in training for poolers.py:134-180: AvgPoolGrad ->
+ * CropAndResizeGradImage -> MirrorPadGrad -> per-level scatter).  Boxes get no
+ * gradient (functional.py:120 stop_gradient).  One kernel: vector fp32
+ * reductions (red.global.add.v4.f32) into grad_features, which are ACCUMULATED
+ * into (zero them first unless summing with another consumer's gradient).
+ * Summation order differs from the CPU kernel's => fp32 tolerance, not bit parity.
+ * `fwd` describes the forward call; its features/out/level_* fields are ignored.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  d2b_roi_align_params fwd;
+  const float* grad_out;                 /* [num_rois, output_h, output_w, channels] fp32 */
+  float* grad_features[D2B_MAX_LEVELS];  /* level l: [num_images, height[l], width[l], channels] fp32 */
+} d2b_roi_align_backward_params;
+D2B_API size_t d2b_roi_align_backward_workspace_bytes(const d2b_roi_align_backward_params* p);
+D2B_API int d2b_roi_align_backward(const d2b_roi_align_backward_params* p, void* workspace,
+                                   size_t workspace_bytes, d2b_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

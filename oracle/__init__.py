@@ -289,3 +289,100 @@ def reframe_box_masks_to_image_masks(box_masks, boxes, image_shape, mask_thresho
     out = np.zeros((M, H, W), np.uint8)
     lib().orc_reframe_box_masks(_p(box_masks), _p(boxes), C.c_int64(M), mh, mw, H, W, C.c_float(mask_threshold), _p(out))
     return out
+
+
+def pairwise_iou(boxes1, boxes2):
+    """lib/structures/box_list_ops.py:295-334 (iou_type='iou') -> [n1, n2]."""
+    b1 = _f32(boxes1).reshape(-1, 4)
+    b2 = _f32(boxes2).reshape(-1, 4)
+    out = np.zeros((b1.shape[0], b2.shape[0]), np.float32)
+    lib().orc_pairwise_iou(_p(b1), C.c_int64(b1.shape[0]), _p(b2), C.c_int64(b2.shape[0]), _p(out))
+    return out
+
+
+def matcher(q, thresholds, labels, allow_low_quality_matches=False, crowd=None, difficult=None):
+    """lib/modeling/matcher.py:8-174 -> (matches int64 [N], match_labels int64 [N])."""
+    q = _f32(q)
+    M, N = q.shape
+    th = _f32(thresholds)
+    lab = np.ascontiguousarray(labels, np.int32)
+    cr = None if crowd is None else _f32(crowd)
+    df = None if difficult is None else _f32(difficult)
+    matches = np.zeros(N, np.int64)
+    ml = np.zeros(N, np.int64)
+    lib().orc_matcher(_p(q), C.c_int64(M), C.c_int64(N), None if cr is None else _p(cr),
+                      C.c_int64(0 if cr is None else cr.shape[0]), None if df is None else _p(df),
+                      C.c_int64(0 if df is None else df.shape[0]), _p(th), len(th), _p(lab),
+                      int(bool(allow_low_quality_matches)), _p(matches), _p(ml))
+    return matches, ml
+
+
+def get_deltas(src_boxes, target_boxes, weights):
+    """lib/modeling/box_regression.py:38-74."""
+    s = _f32(src_boxes).reshape(-1, 4)
+    t = _f32(target_boxes).reshape(-1, 4)
+    out = np.zeros_like(s)
+    lib().orc_get_deltas(_p(s), _p(t), C.c_int64(s.shape[0]), _p(_f32(weights)), _p(out))
+    return out
+
+
+def label_boxes(pred_boxes, gt_boxes, gt_valid, thresholds, labels, allow_low_quality_matches=False, gt_crowd=None,
+                gt_difficult=None, pred_counts=None, boundary_threshold=-1.0, image_shapes=None, weights=None):
+    """rpn_outputs.py:245-304 / roi_heads.py:100-165: pairwise_iou + Matcher (+ inside_window, get_deltas).
+
+    pred_boxes [P,4] (shared, anchors) or [N,P,4]; gt_boxes [N,G,4]; flags [N,G].
+    -> (matches [N,P] int64, labels [N,P] int64, deltas [N,P,4] or None)."""
+    pb = _f32(pred_boxes)
+    shared = pb.ndim == 2
+    gt = _f32(gt_boxes)
+    N, G = gt.shape[:2]
+    P = pb.shape[-2]
+    u8 = lambda a: None if a is None else np.ascontiguousarray(a, np.uint8)
+    v, c, d = u8(gt_valid), u8(gt_crowd), u8(gt_difficult)
+    pc = None if pred_counts is None else np.ascontiguousarray(pred_counts, np.int32)
+    sh = None if image_shapes is None else np.ascontiguousarray(image_shapes, np.int32)
+    th = _f32(thresholds)
+    lab = np.ascontiguousarray(labels, np.int32)
+    w = None if weights is None else _f32(weights)
+    matches = np.zeros((N, P), np.int64)
+    out_labels = np.zeros((N, P), np.int64)
+    deltas = None if w is None else np.zeros((N, P, 4), np.float32)
+    q = lambda a: None if a is None else _p(a)
+    lib().orc_label_boxes(_p(pb), int(shared), q(pc), N, P, _p(gt), _p(v), q(c), q(d), G, _p(th), len(th), _p(lab),
+                          int(bool(allow_low_quality_matches)), C.c_float(boundary_threshold), q(sh), q(w),
+                          _p(matches), _p(out_labels), q(deltas))
+    return matches, out_labels, deltas
+
+
+def roi_align_backward(grad_out, image_shape, boxes, box_ind, spatial_scale, sampling_ratio, aligned=True):
+    """Gradient of lib/layers/roi_align.py:45-66 w.r.t. the NHWC feature map `image_shape` = (N,H,W,C)."""
+    g = _f32(grad_out)
+    M, oh, ow, Cc = g.shape
+    N, H, W, C2 = image_shape
+    assert C2 == Cc
+    b = _f32(boxes).reshape(-1, 4)
+    bi = np.ascontiguousarray(box_ind, np.int32)
+    out = np.zeros(image_shape, np.float32)
+    rc = lib().orc_roi_align_backward(_p(g), N, H, W, Cc, _p(b), _p(bi), C.c_int64(M), oh, ow,
+                                      C.c_float(spatial_scale), int(sampling_ratio), int(aligned), _p(out))
+    assert rc == 0
+    return out
+
+
+def roi_pooler_backward(grad_out, feat_shapes, scales, boxes, batch_idx, sampling_ratio, aligned=True,
+                        canonical_box_size=224, canonical_level=4):
+    """Gradient of ROIPooler.call (lib/modeling/poolers.py:134-180) w.r.t. every level's feature map."""
+    g = _f32(grad_out)
+    M, oh, ow, Cc = g.shape
+    L = len(feat_shapes)
+    N = feat_shapes[0][0]
+    outs = [np.zeros(s, np.float32) for s in feat_shapes]
+    Hs = (C.c_int * L)(*[s[1] for s in feat_shapes])
+    Ws = (C.c_int * L)(*[s[2] for s in feat_shapes])
+    b = _f32(boxes).reshape(-1, 4)
+    bi = np.ascontiguousarray(batch_idx, np.int64)
+    rc = lib().orc_roi_pooler_backward(_p(g), _ptr_array(outs), Hs, Ws, L, N, Cc, _p(_f32(scales)), _p(b), _p(bi),
+                                       C.c_int64(M), oh, ow, int(sampling_ratio), int(aligned),
+                                       int(canonical_box_size), int(canonical_level))
+    assert rc == 0
+    return outs

@@ -812,3 +812,273 @@ ORC_API void orc_reframe_box_masks(const float* box_masks, const float* boxes, i
     free(tmp);
   }
 }
+
+/* ------------------------------------------------------------------ training-side neighbours (SURVEY.md 8f "next" #3) */
+/* lib/structures/box_list_ops.py:295-334 pairwise_iou (iou_type='iou'): boxes1 [n1,4] rows, boxes2 [n2,4] columns */
+static inline float orc_pair_iou(const float* a, const float* b) {
+  const float ih = fmaxf(0.0f, fminf(a[2], b[2]) - fmaxf(a[0], b[0]));
+  const float iw = fmaxf(0.0f, fminf(a[3], b[3]) - fmaxf(a[1], b[1]));
+  const float inter = ih * iw;
+  const float area1 = (a[2] - a[0]) * (a[3] - a[1]);
+  const float area2 = (b[2] - b[0]) * (b[3] - b[1]);
+  float u = area1 + area2;
+  u = u - inter;
+  return (u == 0.0f) ? 0.0f : inter / u;
+}
+ORC_API void orc_pairwise_iou(const float* b1, int64_t n1, const float* b2, int64_t n2, float* out) {
+#pragma omp parallel for num_threads(ORC_NT) schedule(static)
+  for (int64_t i = 0; i < n1; ++i)
+    for (int64_t j = 0; j < n2; ++j) out[i * n2 + j] = orc_pair_iou(b1 + 4 * i, b2 + 4 * j);
+}
+
+/* lib/modeling/matcher.py:8-174 Matcher.__call__ on a match-quality matrix q [M, N] (+ optional crowd matrix
+ * [Mc, N]).  thresholds has nt entries (without the -inf/+inf ends), labels nt+1 entries. */
+ORC_API void orc_matcher(const float* q, int64_t M, int64_t N, const float* crowd, int64_t Mc,
+                         const float* difficult, int64_t Md, const float* thresholds, int nt,
+                         const int32_t* labels, int allow_low_quality, int64_t* matches,
+                         int64_t* match_labels) {
+  if (M <= 0) {
+    for (int64_t j = 0; j < N; ++j) { matches[j] = 0; match_labels[j] = 0; }
+  } else {
+    for (int64_t j = 0; j < N; ++j) { /* argmax / reduce_max over axis 0 (first maximum wins) :93-94 */
+      int64_t bi = 0; float bv = q[j];
+      for (int64_t i = 1; i < M; ++i) { const float v = q[i * N + j]; if (v > bv) { bv = v; bi = i; } }
+      matches[j] = bi;
+      int64_t lab = 0;
+      for (int t = 0; t <= nt; ++t) { /* :97-107 */
+        const float low = (t == 0) ? -INFINITY : thresholds[t - 1];
+        const float high = (t == nt) ? INFINITY : thresholds[t];
+        if (bv >= low && bv < high) lab = labels[t];
+      }
+      match_labels[j] = lab;
+    }
+    if (allow_low_quality) { /* get_low_quality_matches_ :152-174: dynamic_stitch overrides with 1 */
+      for (int64_t i = 0; i < M; ++i) {
+        float mx = q[i * N];
+        for (int64_t j = 1; j < N; ++j) { const float v = q[i * N + j]; mx = (v > mx) ? v : mx; }
+        for (int64_t j = 0; j < N; ++j) if (q[i * N + j] == mx) match_labels[j] = 1;
+      }
+    }
+  }
+  if (crowd) { /* :124-134 */
+    for (int64_t j = 0; j < N; ++j) {
+      int cb = 0;
+      if (Mc > 0) {
+        float mx = crowd[j];
+        for (int64_t i = 1; i < Mc; ++i) { const float v = crowd[i * N + j]; mx = (v > mx) ? v : mx; }
+        cb = mx > 1e-3f;
+      }
+      if (match_labels[j] == 0 && cb) match_labels[j] = -1;
+    }
+  }
+  if (difficult) { /* :136-148: reduce_max(difficult_matrix) > self.thresholds[1] (first user threshold) */
+    for (int64_t j = 0; j < N; ++j) {
+      int db = 0;
+      if (Md > 0) {
+        float mx = difficult[j];
+        for (int64_t i = 1; i < Md; ++i) { const float v = difficult[i * N + j]; mx = (v > mx) ? v : mx; }
+        db = mx > thresholds[0];
+      }
+      if (match_labels[j] == 0 && db) match_labels[j] = -1;
+    }
+  }
+}
+
+/* lib/modeling/box_regression.py:38-74 Box2BoxTransform.get_deltas (src -> target), weights (wy,wx,wh,ww) */
+ORC_API void orc_get_deltas(const float* src, const float* tgt, int64_t n, const float* w, float* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    const float* s = src + 4 * i; const float* t = tgt + 4 * i;
+    const float sh = s[2] - s[0], sw = s[3] - s[1];
+    float scy = 0.5f * sh; scy = s[0] + scy;
+    float scx = 0.5f * sw; scx = s[1] + scx;
+    const float th = t[2] - t[0], tw = t[3] - t[1];
+    float tcy = 0.5f * th; tcy = t[0] + tcy;
+    float tcx = 0.5f * tw; tcx = t[1] + tcx;
+    float dy = tcy - scy; dy = w[0] * dy; dy = dy / sh;
+    float dx = tcx - scx; dx = w[1] * dx; dx = dx / sw;
+    float dh = th / sh; dh = orc_logf(dh); dh = w[2] * dh;
+    float dw = tw / sw; dw = orc_logf(dw); dw = w[3] * dw;
+    out[4 * i + 0] = dy; out[4 * i + 1] = dx; out[4 * i + 2] = dh; out[4 * i + 3] = dw;
+  }
+}
+
+/* Label assignment of one batch, composition of
+ *   RPNOutputs._get_ground_truth            lib/modeling/proposal_generator/rpn_outputs.py:245-304
+ *   ROIHeads.label_and_sample_proposals     lib/modeling/roi_heads/roi_heads.py:100-165 (up to the random sampling)
+ * per image: boolean_mask GT by (valid & ~crowd [& ~difficult]), crowd list by is_crowd, difficult list by
+ * gt_difficult; pairwise_iou x3; Matcher; optional inside_window (box_list_ops.py:150-161); get_deltas of the
+ * positives stitched over zeros.  pred [N,P,4] (or [P,4] when pred_shared), pred_counts: valid prefix.
+ * Rows beyond the prefix: matches 0, labels -1, deltas 0 (the reference drops them with boolean_mask). */
+ORC_API void orc_label_boxes(const float* pred, int pred_shared, const int32_t* pred_counts, int N, int P,
+                             const float* gt, const uint8_t* gt_valid, const uint8_t* gt_crowd,
+                             const uint8_t* gt_difficult, int G, const float* thresholds, int nt,
+                             const int32_t* labels, int allow_low_quality, float boundary_threshold,
+                             const int32_t* image_shapes, const float* weights, int64_t* matches,
+                             int64_t* out_labels, float* deltas) {
+#pragma omp parallel for num_threads(ORC_NT) schedule(dynamic, 1)
+  for (int n = 0; n < N; ++n) {
+    const float* pb = pred_shared ? pred : pred + (size_t)n * P * 4;
+    const int64_t cnt = pred_counts ? (pred_counts[n] < P ? pred_counts[n] : P) : P;
+    float* vg = (float*)malloc(sizeof(float) * 4 * (size_t)(G + 1));
+    float* cg = (float*)malloc(sizeof(float) * 4 * (size_t)(G + 1));
+    float* dg = (float*)malloc(sizeof(float) * 4 * (size_t)(G + 1));
+    int64_t nv = 0, nc = 0, nd = 0;
+    for (int g = 0; g < G; ++g) {
+      const int v = gt_valid[(size_t)n * G + g] != 0;
+      const int c = gt_crowd ? gt_crowd[(size_t)n * G + g] != 0 : 0;
+      const int d = gt_difficult ? gt_difficult[(size_t)n * G + g] != 0 : 0;
+      const float* b = gt + ((size_t)n * G + g) * 4;
+      if (v && !c && !d) memcpy(vg + 4 * nv++, b, 16);
+      if (c) memcpy(cg + 4 * nc++, b, 16);
+      if (d) memcpy(dg + 4 * nd++, b, 16);
+    }
+    const size_t cc = (size_t)(cnt > 0 ? cnt : 1);
+    float* q = (float*)malloc(sizeof(float) * (size_t)(nv + 1) * cc);
+    float* qc = gt_crowd ? (float*)malloc(sizeof(float) * (size_t)(nc + 1) * cc) : NULL;
+    float* qd = gt_difficult ? (float*)malloc(sizeof(float) * (size_t)(nd + 1) * cc) : NULL;
+    for (int64_t i = 0; i < nv; ++i)
+      for (int64_t j = 0; j < cnt; ++j) q[i * cnt + j] = orc_pair_iou(vg + 4 * i, pb + 4 * j);
+    for (int64_t i = 0; i < nc && qc; ++i)
+      for (int64_t j = 0; j < cnt; ++j) qc[i * cnt + j] = orc_pair_iou(cg + 4 * i, pb + 4 * j);
+    for (int64_t i = 0; i < nd && qd; ++i)
+      for (int64_t j = 0; j < cnt; ++j) qd[i * cnt + j] = orc_pair_iou(dg + 4 * i, pb + 4 * j);
+    int64_t* m = matches + (size_t)n * P;
+    int64_t* l = out_labels + (size_t)n * P;
+    orc_matcher(q, nv, cnt, qc, nc, qd, nd, thresholds, nt, labels, allow_low_quality, m, l);
+    if (boundary_threshold >= 0.0f) { /* rpn_outputs.py:268-278 */
+      const float wy1 = 0.0f - boundary_threshold, wx1 = 0.0f - boundary_threshold;
+      const float wy2 = (float)image_shapes[2 * n] + boundary_threshold;
+      const float wx2 = (float)image_shapes[2 * n + 1] + boundary_threshold;
+      for (int64_t j = 0; j < cnt; ++j) {
+        const float* b = pb + 4 * j;
+        const int viol = (b[0] < wy1) || (b[1] < wx1) || (b[2] > wy2) || (b[3] > wx2);
+        if (viol) l[j] = -1;
+      }
+    }
+    for (int64_t j = cnt; j < P; ++j) { m[j] = 0; l[j] = -1; }
+    if (deltas) { /* rpn_outputs.py:280-292 */
+      float* d = deltas + (size_t)n * P * 4;
+      memset(d, 0, sizeof(float) * 4 * (size_t)P);
+      for (int64_t j = 0; j < cnt; ++j)
+        if (l[j] > 0 && nv > 0) orc_get_deltas(pb + 4 * j, vg + 4 * m[j], 1, weights, d + 4 * j);
+    }
+    free(q); free(qc); free(qd); free(vg); free(cg); free(dg);
+  }
+}
+
+/* ------------------------------------------------------------------ ROIAlign backward (gradient w.r.t. the feature maps)
+ * What TF autodiff runs for lib/layers/roi_align.py:45-66 + functional.py:100-166 in training:
+ *   AvgPoolGrad (each sample gets g / sr^2)  ->  CropAndResizeGradImage (TF CPU kernel: per box, per crop pixel,
+ *   dtop = (1-ly)*g; TL += (1-lx)*dtop; TR += lx*dtop; dbottom = ly*g; BL += (1-lx)*dbottom; BR += lx*dbottom,
+ *   boxes in index order)  ->  MirrorPadGrad SYMMETRIC (border rows/cols folded onto the edge pixel).
+ * Boxes receive no gradient (functional.py:120 stop_gradient).  grad_image [N,H,W,C] is ACCUMULATED into. */
+ORC_API int orc_roi_align_backward(const float* grad_out, int N, int H, int W, int C, const float* boxes,
+                                   const int32_t* box_ind, int64_t M, int oh, int ow, float spatial_scale,
+                                   int sampling_ratio, int aligned, float* grad_image) {
+  const int sr = sampling_ratio > 0 ? sampling_ratio : 1;
+  const int ch = oh * sr, cw = ow * sr;
+  const int Hp = H + 2, Wp = W + 2;
+  float* gp = (float*)calloc((size_t)N * Hp * Wp * C, sizeof(float));
+  if (!gp) return -1;
+  const float cnt = (float)(sr * sr);
+  for (int64_t b = 0; b < M; ++b) {
+    const int32_t bi = box_ind[b];
+    if (bi < 0 || bi >= N) continue;
+    const float ymin = boxes[4 * b + 0] * spatial_scale + 1.0f, xmin = boxes[4 * b + 1] * spatial_scale + 1.0f;
+    const float ymax = boxes[4 * b + 2] * spatial_scale + 1.0f, xmax = boxes[4 * b + 3] * spatial_scale + 1.0f;
+    float y1, x1, y2, x2;
+    if (aligned) {
+      float sph = (ymax - ymin) / (float)ch;
+      float spw = (xmax - xmin) / (float)cw;
+      float imh = (float)(Hp - 1), imw = (float)(Wp - 1);
+      float ny = sph / 2.0f; ny = ymin + ny; ny = ny - 0.5f; ny = ny / imh;
+      float nx = spw / 2.0f; nx = xmin + nx; nx = nx - 0.5f; nx = nx / imw;
+      float nh = sph * (float)(ch - 1); nh = nh / imh;
+      float nw = spw * (float)(cw - 1); nw = nw / imw;
+      y1 = ny; x1 = nx; y2 = ny + nh; x2 = nx + nw;
+    } else {
+      y1 = ymin / (float)Hp; x1 = xmin / (float)Wp; y2 = ymax / (float)Hp; x2 = xmax / (float)Wp;
+    }
+    const float hs = (ch > 1) ? (y2 - y1) * (float)(Hp - 1) / (float)(ch - 1) : 0.0f;
+    const float ws = (cw > 1) ? (x2 - x1) * (float)(Wp - 1) / (float)(cw - 1) : 0.0f;
+    for (int y = 0; y < ch; ++y) {
+      const float in_y = (ch > 1) ? y1 * (float)(Hp - 1) + (float)y * hs : 0.5f * (y1 + y2) * (float)(Hp - 1);
+      if (!(in_y >= 0.0f && in_y <= (float)(Hp - 1))) continue;
+      const int top = (int)floorf(in_y), bot = (int)ceilf(in_y);
+      const float ly = in_y - (float)top;
+      for (int x = 0; x < cw; ++x) {
+        const float in_x = (cw > 1) ? x1 * (float)(Wp - 1) + (float)x * ws : 0.5f * (x1 + x2) * (float)(Wp - 1);
+        if (!(in_x >= 0.0f && in_x <= (float)(Wp - 1))) continue;
+        const int left = (int)floorf(in_x), right = (int)ceilf(in_x);
+        const float lx = in_x - (float)left;
+        const float* g = grad_out + (((size_t)b * oh + y / sr) * ow + x / sr) * C;
+        float* TL = gp + (((size_t)bi * Hp + top) * Wp + left) * C;
+        float* TR = gp + (((size_t)bi * Hp + top) * Wp + right) * C;
+        float* BL = gp + (((size_t)bi * Hp + bot) * Wp + left) * C;
+        float* BR = gp + (((size_t)bi * Hp + bot) * Wp + right) * C;
+        const float omy = 1.0f - ly, omx = 1.0f - lx;
+        for (int c = 0; c < C; ++c) {
+          const float gv = (sr > 1) ? g[c] / cnt : g[c];
+          const float dtop = omy * gv;
+          TL[c] = TL[c] + omx * dtop;
+          TR[c] = TR[c] + lx * dtop;
+          const float dbot = ly * gv;
+          BL[c] = BL[c] + omx * dbot;
+          BR[c] = BR[c] + lx * dbot;
+        }
+      }
+    }
+  }
+  /* MirrorPadGrad SYMMETRIC, 1 px: padded (py,px) folds onto un-padded clamp(p-1) */
+  for (int n = 0; n < N; ++n)
+    for (int py = 0; py < Hp; ++py) {
+      int sy = py - 1; if (sy < 0) sy = 0; if (sy > H - 1) sy = H - 1;
+      for (int px = 0; px < Wp; ++px) {
+        int sx = px - 1; if (sx < 0) sx = 0; if (sx > W - 1) sx = W - 1;
+        const float* s = gp + (((size_t)n * Hp + py) * Wp + px) * C;
+        float* d = grad_image + (((size_t)n * H + sy) * W + sx) * C;
+        for (int c = 0; c < C; ++c) d[c] = d[c] + s[c];
+      }
+    }
+  free(gp);
+  return 0;
+}
+
+/* ROIPooler backward: routes each ROI's gradient to the level assign_boxes_to_levels gave it
+ * (gradient of the where/gather/concat/un-permute chain of lib/modeling/poolers.py:160-178). */
+ORC_API int orc_roi_pooler_backward(const float* grad_out, float* const* grad_feats, const int* Hs, const int* Ws,
+                                    int L, int N, int C, const float* scales, const float* boxes,
+                                    const int64_t* batch_idx, int64_t M, int oh, int ow, int sampling_ratio,
+                                    int aligned, int canonical_box_size, int canonical_level) {
+  const size_t row = (size_t)oh * ow * C;
+  int64_t* lv = (int64_t*)calloc((size_t)(M > 0 ? M : 1), sizeof(int64_t));
+  if (L > 1) {
+    const int min_level = (int)lroundf(-log2f(scales[0]));
+    const int max_level = (int)lroundf(-log2f(scales[L - 1]));
+    orc_assign_boxes_to_levels(boxes, M, min_level, max_level, canonical_box_size, canonical_level, lv);
+  }
+  int rc = 0;
+#pragma omp parallel for num_threads(ORC_NT) schedule(dynamic, 1)
+  for (int l = 0; l < L; ++l) {
+    float* lb = (float*)malloc(sizeof(float) * 4 * (size_t)(M > 0 ? M : 1));
+    int32_t* bi = (int32_t*)malloc(sizeof(int32_t) * (size_t)(M > 0 ? M : 1));
+    float* g = (float*)malloc(sizeof(float) * row * (size_t)(M > 0 ? M : 1));
+    int64_t m = 0;
+    for (int64_t i = 0; i < M; ++i)
+      if (lv[i] == l) {
+        memcpy(lb + 4 * m, boxes + 4 * i, 16);
+        bi[m] = (int32_t)batch_idx[i];
+        memcpy(g + (size_t)m * row, grad_out + (size_t)i * row, sizeof(float) * row);
+        ++m;
+      }
+    int r = orc_roi_align_backward(g, N, Hs[l], Ws[l], C, lb, bi, m, oh, ow, scales[l], sampling_ratio, aligned,
+                                   grad_feats[l]);
+    if (r) {
+#pragma omp atomic write
+      rc = r;
+    }
+    free(lb); free(bi); free(g);
+  }
+  free(lv);
+  return rc;
+}

@@ -42,7 +42,11 @@ def test_struct_layout_matches_header(lib, tmp_path):
              "segmented_topk": "d2b_segmented_topk_params", "batched_nms": "d2b_batched_nms_params",
              "rpn_proposals": "d2b_rpn_proposals_params", "fast_rcnn_postprocess": "d2b_fast_rcnn_params",
              "retinanet_postprocess": "d2b_retinanet_params", "matrix_nms": "d2b_matrix_nms_params",
-             "paste_masks": "d2b_paste_masks_params"}
+             "paste_masks": "d2b_paste_masks_params", "crop_and_resize_aligned": "d2b_crop_and_resize_params",
+             "decode_clip_filter": "d2b_decode_clip_filter_params", "get_deltas": "d2b_get_deltas_params",
+             "pairwise_iou": "d2b_pairwise_iou_params", "label_boxes": "d2b_label_boxes_params",
+             "matcher": "d2b_matcher_params", "roi_align_backward": "d2b_roi_align_backward_params"}
+    assert set(names) == set(_native.OPS)
     prog = '#include <stdio.h>\n#include "d2b200.h"\nint main(){' + "".join(
         f'printf("{op} %zu\\n", sizeof({st}));' for op, st in names.items()) + "return 0;}"
     src = tmp_path / "sz.c"
@@ -75,6 +79,21 @@ def test_argument_validation_without_gpu(lib):
     r.num_levels, r.pre_nms_topk, r.post_nms_topk = 1, 0, 10
     nv._bind("rpn_proposals")
     assert lib.d2b_rpn_proposals(C.byref(r), None, 0, None) == -1
+    lb = nv.LabelBoxesParams()
+    lb.num_thresholds, lb.max_gt = 2, 8
+    lb.thresholds[0], lb.thresholds[1] = 0.7, 0.3  # matcher.py:49 assert low <= high
+    nv._bind("label_boxes")
+    assert lib.d2b_label_boxes(C.byref(lb), None, 0, None) == -1
+    assert b"ascending" in lib.d2b_last_error()
+    lb.thresholds[0], lb.thresholds[1] = 0.3, 0.7
+    lb.labels[0], lb.labels[1], lb.labels[2] = 0, 2, 1  # matcher.py:50 labels in {-1,0,1}
+    assert lib.d2b_label_boxes(C.byref(lb), None, 0, None) == -1
+    bw = nv.RoiAlignBackwardParams()
+    bw.fwd.num_levels, bw.fwd.num_images, bw.fwd.channels, bw.fwd.output_h, bw.fwd.output_w = 1, 1, 8, 7, 7
+    bw.fwd.feature_dtype = nv.DTYPE_BF16
+    nv._bind("roi_align_backward")
+    assert lib.d2b_roi_align_backward(C.byref(bw), None, 0, None) == -1
+    assert b"fp32 only" in lib.d2b_last_error()
     # workspace queries are pure host arithmetic
     t = nv.SegmentedTopkParams()
     t.num_groups, t.rows_per_group, t.k = 2, 4, 1000
