@@ -1,0 +1,146 @@
+"""CPU: the oracle against outputs of the REFERENCE'S OWN PYTHON, executed unmodified on a numpy
+TF shim in the build container (tests/golden/make_reference_golden.py + tf_numpy_shim.py ->
+tests/golden/reference_python.npz).  This pins the oracle's restatement of the reference's composition
+(op order, ties, padding, class offsets, level routing, label stitching) to the reference's code.
+
+Exact (np.array_equal) wherever the path contains only +,-,*,/,min,max,compare,floor; 1e-5 relative
+where numpy's exp/log stand in for Eigen's (apply_deltas/get_deltas/matrix_nms), per north_star.
+"""
+import os
+
+import numpy as np
+import pytest
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def z():
+    return np.load(os.path.join(G, "reference_python.npz"))
+
+
+def test_pairwise_iou(oracle_lib, z):
+    assert np.array_equal(oracle_lib.pairwise_iou(z["iou_b1"], z["iou_b2"]), z["iou_out"])
+
+
+def test_matcher(oracle_lib, z):
+    for c in range(int(z["m_num_cases"])):
+        lq, uc, ud = (int(v) for v in z[f"m{c}_cfg"])
+        m, l = oracle_lib.matcher(z["m_q"], z[f"m{c}_th"], z[f"m{c}_lab"], bool(lq), z["m_crowd"] if uc else None,
+                                  z["m_diff"] if ud else None)
+        assert np.array_equal(m, z[f"m{c}_matches"]), c
+        assert np.array_equal(l, z[f"m{c}_labels"]), c
+
+
+def test_box2box_transform(oracle_lib, z):
+    w = (10., 10., 5., 5.)
+    got = oracle_lib.get_deltas(z["bt_src"], z["bt_tgt"], w)
+    assert np.allclose(got, z["bt_get"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(got[:, :2], z["bt_get"][:, :2])  # dy, dx contain no transcendental: exact
+    got = oracle_lib.apply_deltas(z["bt_deltas"], z["bt_src"], w)
+    assert np.allclose(got, z["bt_apply"], rtol=1e-5, atol=1e-3)
+
+
+def test_level_assignment(oracle_lib, z):
+    assert np.array_equal(oracle_lib.assign_boxes_to_levels(z["rp_boxes"], 2, 5, 224, 4), z["rp_levels"])
+    lv = oracle_lib.assign_boxes_to_levels(z["rp_boxes"], 2, 5, 56, 4)
+    assert np.array_equal(lv, z["rp_levels56"]) and len(np.unique(lv)) == 4
+
+
+@pytest.mark.parametrize("ptype,sr,osz", [("ROIAlignV2", 0, 7), ("ROIAlignV2", 2, 7), ("ROIAlign", 0, 14)])
+def test_roi_pooler(oracle_lib, z, ptype, sr, osz):
+    feats = [z[f"rp_feat{l}"] for l in range(4)]
+    got, _ = oracle_lib.roi_pooler(feats, [1 / 4., 1 / 8., 1 / 16., 1 / 32.], z["rp_boxes"], z["rp_idx"][:, 0],
+                                   (osz, osz), sr, aligned=(ptype == "ROIAlignV2"), canonical_box_size=56)
+    assert np.array_equal(got, z[f"rp_out_{ptype}_{sr}_{osz}"])
+
+
+def test_roi_align_and_crop(oracle_lib, z):
+    bi = z["rp_idx"][:, 0].astype(np.int32)
+    assert np.array_equal(oracle_lib.roi_align(z["rp_feat1"], z["rp_boxes"], bi, (7, 7), 1 / 8., 0, True), z["ra_single"])
+    got = oracle_lib.crop_and_resize(z["rp_feat0"], z["rp_boxes"] * np.float32(0.25), bi, (5, 6), True, False)
+    assert np.array_equal(got, z["cr_nopad"])
+
+
+def test_find_top_rpn_proposals(oracle_lib, z):
+    props = [z[f"rpn_props{l}"] for l in range(3)]
+    logits = [z[f"rpn_logits{l}"] for l in range(3)]
+    padded = 0
+    for c in range(int(z["rpn_num_cases"])):
+        pre, post, msl = z[f"rpn{c}_cfg"]
+        b, l, v, n = oracle_lib.find_top_rpn_proposals(props, logits, z["rpn_shapes"], 0.7, int(pre), int(post), float(msl))
+        assert np.array_equal(v, z[f"rpn{c}_valid"])
+        assert np.array_equal(b, z[f"rpn{c}_boxes"])
+        assert np.array_equal(l, z[f"rpn{c}_logits"])
+        padded += int(v.sum() < v.size)
+    assert padded > 0  # at least one case exercises the zero padding / is_valid=False tail
+
+
+def test_fast_rcnn_inference(oracle_lib, z):
+    for c, (agn, boxes) in enumerate(((False, z["fr_pred"]), (True, z["fr_agnostic_boxes"]))):
+        b, s, cl, v, _, _ = oracle_lib.fast_rcnn_inference(boxes, z["fr_scores"], z["fr_idx"], tuple(z["fr_dense"]),
+                                                           z["fr_shapes"], 0.05, 0.5, 15, agn)
+        assert np.array_equal(v, z[f"fr{c}_valid"])
+        assert np.array_equal(cl, z[f"fr{c}_classes"])
+        assert np.array_equal(s, z[f"fr{c}_scores"])
+        assert np.array_equal(b, z[f"fr{c}_boxes"])
+
+
+def test_matrix_nms(oracle_lib, z):
+    shp = tuple(z["mn_shape"])
+    m = np.unpackbits(z["mn_masks"])[:int(np.prod(shp))].reshape(shp).astype(np.float32)
+    got = oracle_lib.matrix_nms(m, z["mn_classes"], z["mn_scores"], None, "gaussian", 2.0)
+    assert np.allclose(got, z["mn_gauss"], rtol=1e-5, atol=1e-7)
+    # linear kernel: identical same-class masks give compensate_iou == 1 => the decay column holds 0/0 = NaN
+    # next to finite values, and tf.reduce_min over a column containing NaN is order-dependent in TF
+    # (Eigen's pmin keeps or drops NaN by operand position).  numpy propagates NaN; the oracle (and the
+    # kernel) use IEEE fmin, which drops it.  Columns without NaN must agree; NaN columns are unspecified.
+    got = oracle_lib.matrix_nms(m, z["mn_classes"], z["mn_scores"], None, "linear", 2.0)
+    want = z["mn_linear"]
+    ok = ~np.isnan(want)
+    assert ok.sum() >= want.size // 2
+    assert np.allclose(got[ok], want[ok], rtol=1e-5, atol=1e-7)
+
+
+def test_paste_masks(oracle_lib, z):
+    got = oracle_lib.reframe_box_masks_to_image_masks(z["pm_masks"], z["pm_boxes"], (60, 80))
+    assert np.array_equal(got, z["pm_out"])
+    assert 0 < got.sum() < got.size
+
+
+def test_rpn_ground_truth(oracle_lib, z):
+    """RPNOutputs._get_ground_truth (rpn_outputs.py:245-304) == oracle.label_boxes."""
+    for c, bthr in enumerate((-1.0, 0.0)):
+        _, lab, dl = oracle_lib.label_boxes(z["gt_anchors"], z["gt_boxes"], z["gt_valid"], [0.3, 0.7], [0, -1, 1], True,
+                                            gt_crowd=z["gt_crowd"], boundary_threshold=bthr, image_shapes=z["gt_shapes"],
+                                            weights=(1., 1., 1., 1.))
+        assert np.array_equal(lab, z[f"gt{c}_labels"])
+        want = z[f"gt{c}_deltas"]
+        assert np.array_equal(dl[..., :2], want[..., :2])
+        assert np.allclose(dl, want, rtol=1e-5, atol=1e-6)
+        assert (lab == 1).sum() > 0 and (lab == -1).sum() > 0
+
+
+def test_anchor_generator_host_mirror(z):
+    """The product's host-side DefaultAnchorGenerator mirror (plain torch on CPU: host logic, no kernel) against
+    the reference's DefaultAnchorGenerator (anchor_generator.py:44-162)."""
+    from detectron2_tensorflow_b200.modeling import DefaultAnchorGenerator
+    gen = DefaultAnchorGenerator([[32], [64], [128]], [[0.5, 1.0, 2.0]], [int(s) for s in z["ag_strides"]])
+    got = gen.grid_anchors([tuple(g) for g in z["ag_grid"]])
+    for l in range(3):
+        assert np.array_equal(gen.cell_anchors[l].numpy(), z[f"ag_cell{l}"])
+        assert np.array_equal(got[l].numpy(), z[f"ag_anchors{l}"])
+
+
+def test_retinanet_inference(oracle_lib, z):
+    """RetinaNetHead.inference (retinanet.py:285-387).  Scores/boxes pass through sigmoid/exp (numpy's in the
+    fixture, Eigen-Cephes in the oracle): 1e-5 relative; classes / validity / ordering exact."""
+    cls = [z[f"rn_cls{l}"] for l in range(3)]
+    reg = [z[f"rn_reg{l}"] for l in range(3)]
+    anchors = [z[f"ag_anchors{l}"] for l in range(3)]
+    b, s, c, v, n = oracle_lib.retinanet_inference(cls, reg, anchors, 4, 40, 0.05, 0.5, 25)
+    assert np.array_equal(v, z["rn_valid"])
+    assert np.array_equal(c, z["rn_classes"])
+    assert np.allclose(s, z["rn_scores"], rtol=1e-5, atol=1e-7)
+    assert np.allclose(b, z["rn_boxes"], rtol=1e-5, atol=1e-3)
+    assert 0 < v.sum()

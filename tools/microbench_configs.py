@@ -2,6 +2,7 @@
   config 3  RetinaNet R50-FPN inference post-processing, batch 32
   config 4  SOLOv2 Matrix-NMS, 500 masks at 200x336, batch 16
   config 5  ROIAlign / NMS sweep, 256 .. 65536 ROIs / boxes
+  train     SURVEY.md 8(f) #3: fused RPN label assignment (16 x 268 K anchors), ROIPooler backward (16,000 ROIs)
 Prints one JSON line per case (CUDA events, median of `--iters`, 256 MB L2 flush between iterations)."""
 import argparse
 import json
@@ -13,8 +14,8 @@ import numpy as np
 import torch
 
 from detectron2_tensorflow_b200.layers import batch_nms, matrix_nms
-from detectron2_tensorflow_b200.modeling import ROIPooler, RetinaNetInference
-from detectron2_tensorflow_b200.structures import BoxList, SparseBoxList
+from detectron2_tensorflow_b200.modeling import Box2BoxTransform, Matcher, ROIPooler, RetinaNetInference, label_boxes
+from detectron2_tensorflow_b200.structures import BoxList, SparseBoxList, pairwise_iou
 from detectron2_tensorflow_b200.utils import synthetic as syn
 
 ap = argparse.ArgumentParser()
@@ -93,3 +94,43 @@ if "5" in which:
         ms = timeit(run, iters=5)
         print(json.dumps({"config": 5, "case": f"NMS sweep n={n} (one segment, thr 0.7, uncapped)", "ms": ms,
                           "boxes_per_s": n / ms * 1e3, "kept": int(out["n"][0])}))
+
+if "train" in which:
+    # ---- RPN ground truth: pairwise_iou + Matcher + get_deltas fused (rpn_outputs.py:245-304)
+    N = 16
+    anchors = torch.from_numpy(np.concatenate(syn.rpn_anchors(), 0)).to(dev)
+    P = anchors.shape[0]
+    rng = np.random.default_rng(11)
+    for G in (20, 100):
+        cy, cx = rng.uniform(0, 800, (N, G)), rng.uniform(0, 1333, (N, G))
+        h, w = rng.uniform(16, 500, (N, G)), rng.uniform(16, 500, (N, G))
+        gt = torch.from_numpy(np.stack([cy - h / 2, cx - w / 2, cy + h / 2, cx + w / 2], 2).astype(np.float32)).to(dev)
+        valid = torch.ones((N, G), dtype=torch.bool, device=dev)
+        crowd = torch.zeros((N, G), dtype=torch.bool, device=dev)
+        m = Matcher([0.3, 0.7], [0, -1, 1], allow_low_quality_matches=True)
+        bt = Box2BoxTransform((1., 1., 1., 1.))
+        ms = timeit(lambda: label_boxes(anchors, gt, valid, m, gt_crowd=crowd, box2box_transform=bt))
+        out_bytes = N * P * 32 + P * 16
+        print(json.dumps({"config": "train", "case": f"RPN label assignment N={N} anchors={P} G={G} (fused iou+matcher+deltas)",
+                          "ms": ms, "anchors_per_s": N * P / ms * 1e3, "pairs_per_s": 2 * N * P * G / ms * 1e3,
+                          "alg_GBps": out_bytes / ms / 1e6, "frac_hbm": out_bytes / ms / 1e6 / HBM,
+                          "unfused_matrix_bytes_GB": N * P * G * 4 * 2 / 1e9}))
+    q_ms = timeit(lambda: pairwise_iou(gt[0], anchors))
+    print(json.dumps({"config": "train", "case": f"pairwise_iou [{G}, {P}] materialised", "ms": q_ms,
+                      "GBps": G * P * 4 / q_ms / 1e6, "frac_hbm": G * P * 4 / q_ms / 1e6 / HBM}))
+    # ---- ROIPooler backward (box head, 16,000 ROIs 7x7x256)
+    C = 256
+    shapes = [(N,) + syn.level_hw(s) + (C,) for s in syn.FPN_STRIDES]
+    grads = [torch.zeros(sh, device=dev) for sh in shapes]
+    pooler = ROIPooler(7, [1 / 4., 1 / 8., 1 / 16., 1 / 32.], 0, "ROIAlignV2")
+    for M in (16000, 8192):
+        boxes, idx = syn.rois(N, M // N, seed=1)
+        inst = SparseBoxList(torch.from_numpy(idx).to(dev), BoxList(torch.from_numpy(boxes).to(dev)), (N, M // N))
+        go = torch.randn((M, 7, 7, C), device=dev, generator=g)
+        ms = timeit(lambda: pooler.backward(go, shapes, inst, grad_x=grads))
+        rd = M * 49 * C * 4
+        print(json.dumps({"config": "train", "case": f"ROIPooler backward M={M} 7x7x{C} (accumulate into resident grads)",
+                          "ms": ms, "rois_per_s": M / ms * 1e3, "grad_read_GBps": rd / ms / 1e6,
+                          "red_GBps": 4 * rd / ms / 1e6, "frac_hbm_on_grad_read": rd / ms / 1e6 / HBM}))
+    zero_ms = timeit(lambda: [t_.zero_() for t_ in grads])
+    print(json.dumps({"config": "train", "case": "zero the 1.46 GB of feature gradients (torch memset)", "ms": zero_ms}))
