@@ -131,6 +131,18 @@ class MatcherParams(C.Structure):
                 ("out_matches", _vp), ("out_labels", _vp)]
 
 
+class YoloParams(C.Structure):
+    _fields_ = [("boxes", _vp), ("probs", _vp), ("num_images", _i32), ("num_boxes", _i32), ("num_classes", _i32),
+                ("score_thresh", _f32), ("nms_thresh", _f32), ("post_nms_topk", _i32), ("out_boxes", _vp),
+                ("out_scores", _vp), ("out_classes", _vp), ("out_valid", _vp), ("out_num", _vp),
+                ("out_nms_boxes_in", _vp)]
+
+
+class PointNmsParams(C.Structure):
+    _fields_ = [("scores", _vp), ("num_images", _i32), ("height", _i32), ("width", _i32), ("channels", _i32),
+                ("out", _vp)]
+
+
 class RoiAlignBackwardParams(C.Structure):
     _fields_ = [("fwd", RoiAlignParams), ("grad_out", _vp), ("grad_features", _vp * MAX_LEVELS)]
 
@@ -153,6 +165,8 @@ OPS = {
     "label_boxes": LabelBoxesParams,
     "matcher": MatcherParams,
     "roi_align_backward": RoiAlignBackwardParams,
+    "yolo_postprocess": YoloParams,
+    "point_nms": PointNmsParams,
 }
 EXPORTS = ["d2b_version", "d2b_status_string", "d2b_last_error", "d2b_kernel_launch_count"] + \
           [f"d2b_{op}{sfx}" for op in OPS for sfx in ("", "_workspace_bytes")]

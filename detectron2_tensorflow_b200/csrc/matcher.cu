@@ -130,14 +130,67 @@ __device__ __forceinline__ GtLists load_gt(const LabelArgs& a, int img, float4* 
   return r;
 }
 
+// Spatial culling.  A GT box whose intersection with the bounding box of ALL prediction boxes of this
+// CTA is empty has IoU exactly 0 (inter == 0, finite union) with every one of them, so it can only
+// matter through "everything ties at 0" cases, which the callers handle in closed form.  RPN anchors are
+// laid out (y, x, a)-major, so 256 consecutive anchors cover a thin strip of the image and most GT boxes
+// drop out.  Lists keep GT order (argmax ties go to the lower index).  Boxes with NaN coordinates are
+// outside this argument (the reference's result for them is NaN-comparison noise).
+struct Cull {
+  int nv, nc, nd;  // lengths of the filtered valid / crowd / difficult lists
+};
+__device__ __forceinline__ Cull cull_gt(const GtLists L, int G, const float4* s_box, const float* s_area, float y1,
+                                        float x1, float y2, float x2, bool any_live, int* s_sel, unsigned* s_bb,
+                                        int* s_cnt) {
+  // s_bb: [0]=min y1, [1]=min x1 (as keys), [2]=max y2, [3]=max x2 over the CTA's live predictions
+  if (threadIdx.x == 0) { s_bb[0] = 0xffffffffu; s_bb[1] = 0xffffffffu; s_bb[2] = 0u; s_bb[3] = 0u; }
+  __syncthreads();
+  unsigned k0 = any_live ? float_to_key(y1) : 0xffffffffu, k1 = any_live ? float_to_key(x1) : 0xffffffffu;
+  unsigned k2 = any_live ? float_to_key(y2) : 0u, k3 = any_live ? float_to_key(x2) : 0u;
+  k0 = __reduce_min_sync(0xffffffffu, k0); k1 = __reduce_min_sync(0xffffffffu, k1);
+  k2 = __reduce_max_sync(0xffffffffu, k2); k3 = __reduce_max_sync(0xffffffffu, k3);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(s_bb + 0, k0); atomicMin(s_bb + 1, k1); atomicMax(s_bb + 2, k2); atomicMax(s_bb + 3, k3);
+  }
+  __syncthreads();
+  const float by1 = key_to_float(s_bb[0]), bx1 = key_to_float(s_bb[1]);
+  const float by2 = key_to_float(s_bb[2]), bx2 = key_to_float(s_bb[3]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < 3) {  // one warp per list, ordered compaction
+    const int n = warp == 0 ? L.nv : (warp == 1 ? L.nc : L.nd);
+    const int base = warp * G;
+    int cnt = 0;
+    for (int c = 0; c < n; c += 32) {
+      const int g = c + lane;
+      bool hit = false;
+      if (g < n) {
+        const float4 b = s_box[base + g];
+        const bool apart = (b.x >= by2) || (b.z <= by1) || (b.y >= bx2) || (b.w <= bx1);
+        const bool finite = fabsf(s_area[base + g]) < __int_as_float(0x7f800000);
+        hit = !(apart && finite);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) s_sel[base + cnt + __popc(m & ((1u << lane) - 1u))] = g;
+      cnt += __popc(m);
+    }
+    if (lane == 0) s_cnt[4 + warp] = cnt;
+  }
+  __syncthreads();
+  Cull r;
+  r.nv = s_cnt[4]; r.nc = s_cnt[5]; r.nd = s_cnt[6];
+  return r;
+}
+
 // Pass 1 (allow_low_quality_matches only): highest_quality_foreach_gt = reduce_max(q, axis=1), matcher.py:152.
 __global__ void __launch_bounds__(kThreads) label_gtmax_kernel(const LabelArgs a) {
   extern __shared__ float4 smem[];
   const int G = a.G;
-  float4* s_box = smem;                                     // [3G]
-  float* s_area = reinterpret_cast<float*>(smem + 3 * G);   // [3G]
+  float4* s_box = smem;                                           // [3G]
+  float* s_area = reinterpret_cast<float*>(smem + 3 * G);         // [3G]
   unsigned* s_max = reinterpret_cast<unsigned*>(s_area + 3 * G);  // [G]
-  int* s_cnt = reinterpret_cast<int*>(s_max + G);           // [4]
+  int* s_sel = reinterpret_cast<int*>(s_max + G);                 // [3G]
+  int* s_cnt = s_sel + 3 * G;                                     // [8]
+  unsigned* s_bb = reinterpret_cast<unsigned*>(s_cnt + 8);        // [4]
   const int img = blockIdx.y;
   for (int g = threadIdx.x; g < G; g += kThreads) s_max[g] = 0u;
   const GtLists L = load_gt(a, img, s_box, s_area, s_cnt);
@@ -149,6 +202,8 @@ __global__ void __launch_bounds__(kThreads) label_gtmax_kernel(const LabelArgs a
   float pa[kPredsPerThread];
   bool live[kPredsPerThread];
   bool any = false;
+  const float inf = __int_as_float(0x7f800000);
+  float y1 = inf, x1 = inf, y2 = -inf, x2 = -inf;
 #pragma unroll
   for (int r = 0; r < kPredsPerThread; ++r) {
     const int j = j0 + r * kThreads;
@@ -156,10 +211,13 @@ __global__ void __launch_bounds__(kThreads) label_gtmax_kernel(const LabelArgs a
     p[r] = live[r] ? __ldg(pb + j) : make_float4(0.f, 0.f, 0.f, 0.f);
     pa[r] = box_area(p[r]);
     any |= live[r];
+    if (live[r]) { y1 = fminf(y1, p[r].x); x1 = fminf(x1, p[r].y); y2 = fmaxf(y2, p[r].z); x2 = fmaxf(x2, p[r].w); }
   }
+  const Cull Cn = cull_gt(L, G, s_box, s_area, y1, x1, y2, x2, any, s_sel, s_bb, s_cnt);
   const bool warp_any = __any_sync(0xffffffffu, any);
   if (warp_any) {
-    for (int g = 0; g < L.nv; ++g) {
+    for (int q = 0; q < Cn.nv; ++q) {
+      const int g = s_sel[q];
       const float4 gb = s_box[g];
       const float ga = s_area[g];
       unsigned k = 0u;
@@ -171,9 +229,11 @@ __global__ void __launch_bounds__(kThreads) label_gtmax_kernel(const LabelArgs a
     }
   }
   __syncthreads();
-  for (int g = threadIdx.x; g < L.nv; g += kThreads) {
+  // culled GT contribute exactly 0 here; the label kernel floors every maximum at key(0) instead
+  for (int q = threadIdx.x; q < Cn.nv; q += kThreads) {
+    const int g = s_sel[q];
     const unsigned k = s_max[g];
-    if (k) atomicMax(a.gtmax + (size_t)img * G + g, k);
+    if (k > 0x80000000u) atomicMax(a.gtmax + (size_t)img * G + g, k);
   }
 }
 
@@ -185,33 +245,49 @@ __global__ void __launch_bounds__(kThreads) label_kernel(const LabelArgs a) {
   float4* s_box = smem;
   float* s_area = reinterpret_cast<float*>(smem + 3 * G);
   unsigned* s_max = reinterpret_cast<unsigned*>(s_area + 3 * G);
-  int* s_cnt = reinterpret_cast<int*>(s_max + G);
+  int* s_sel = reinterpret_cast<int*>(s_max + G);
+  int* s_cnt = s_sel + 3 * G;
+  unsigned* s_bb = reinterpret_cast<unsigned*>(s_cnt + 8);
   const int img = blockIdx.y;
   const GtLists L = load_gt(a, img, s_box, s_area, s_cnt);
+  const int cnt = a.pred_counts ? min(a.pred_counts[img], a.P) : a.P;
+  const unsigned key0 = 0x80000000u;  // float_to_key(0.0f)
   if (a.allow_lq) {
-    for (int g = threadIdx.x; g < L.nv; g += kThreads) s_max[g] = a.gtmax[(size_t)img * G + g];
+    // every per-GT maximum is >= 0 once there is one live prediction (IoU is never negative)
+    if (threadIdx.x == 0) s_cnt[7] = 0;
     __syncthreads();
+    bool zero = false;
+    for (int g = threadIdx.x; g < L.nv; g += kThreads) {
+      const unsigned k = max(a.gtmax[(size_t)img * G + g], cnt > 0 ? key0 : 0u);
+      s_max[g] = k;
+      zero |= (k == key0);
+    }
+    if (zero) s_cnt[7] = 1;  // some GT overlaps nothing: every prediction ties with its maximum 0
   }
   const int j = blockIdx.x * kThreads + threadIdx.x;
-  if (j >= a.P) return;
   const size_t o = (size_t)img * a.P + j;
-  const int cnt = a.pred_counts ? min(a.pred_counts[img], a.P) : a.P;
-  if (j >= cnt) {
+  const bool live = j < cnt;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) p = __ldg(a.pred + (a.pred_shared ? (size_t)j : o));
+  const Cull Cn = cull_gt(L, G, s_box, s_area, p.x, p.y, p.z, p.w, live, s_sel, s_bb, s_cnt);
+  if (j >= a.P) return;
+  if (!live) {
     a.out_matches[o] = 0;
     a.out_labels[o] = -1;
     if (a.out_deltas) a.out_deltas[o] = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
   }
-  const float4 p = __ldg(a.pred + (a.pred_shared ? (size_t)j : o));
   const float pa = box_area(p);
   long long match = 0;
   int label = 0;
   if (L.nv > 0) {
-    // tf.argmax / tf.reduce_max over axis 0: first maximum wins (matcher.py:93-94)
-    float best = pair_iou(s_box[0], s_area[0], p, pa);
+    // tf.argmax / tf.reduce_max over axis 0: first maximum wins (matcher.py:93-94).  Culled GT are exact zeros,
+    // so the scan starts from (0, index 0) and only a strictly larger candidate moves it.
+    float best = 0.0f;
     int bi = 0;
-    bool lowq = a.allow_lq && float_to_key(best) != 0u && float_to_key(best) == s_max[0];
-    for (int g = 1; g < L.nv; ++g) {
+    bool lowq = a.allow_lq && s_cnt[7] != 0;
+    for (int q = 0; q < Cn.nv; ++q) {
+      const int g = s_sel[q];
       const float v = pair_iou(s_box[g], s_area[g], p, pa);
       if (v > best) { best = v; bi = g; }
       if (a.allow_lq) {
@@ -228,22 +304,20 @@ __global__ void __launch_bounds__(kThreads) label_kernel(const LabelArgs a) {
     if (lowq) label = 1;  // dynamic_stitch: the low-quality indices come last and win (matcher.py:109-115)
   }
   if (a.crowd) {  // matcher.py:124-134
-    bool cb = false;
-    if (L.nc > 0) {
-      float mx = pair_iou(s_box[G], s_area[G], p, pa);
-      for (int g = 1; g < L.nc; ++g) mx = fmaxf(mx, pair_iou(s_box[G + g], s_area[G + g], p, pa));
-      cb = mx > 1e-3f;
+    float mx = 0.0f;
+    for (int q = 0; q < Cn.nc; ++q) {
+      const int g = G + s_sel[G + q];
+      mx = fmaxf(mx, pair_iou(s_box[g], s_area[g], p, pa));
     }
-    if (label == 0 && cb) label = -1;
+    if (label == 0 && L.nc > 0 && mx > 1e-3f) label = -1;
   }
   if (a.difficult) {  // matcher.py:136-148
-    bool db = false;
-    if (L.nd > 0) {
-      float mx = pair_iou(s_box[2 * G], s_area[2 * G], p, pa);
-      for (int g = 1; g < L.nd; ++g) mx = fmaxf(mx, pair_iou(s_box[2 * G + g], s_area[2 * G + g], p, pa));
-      db = mx > a.thr[0];
+    float mx = 0.0f;
+    for (int q = 0; q < Cn.nd; ++q) {
+      const int g = 2 * G + s_sel[2 * G + q];
+      mx = fmaxf(mx, pair_iou(s_box[g], s_area[g], p, pa));
     }
-    if (label == 0 && db) label = -1;
+    if (label == 0 && L.nd > 0 && mx > a.thr[0]) label = -1;
   }
   if (a.boundary >= 0.0f) {  // rpn_outputs.py:268-278, box_list_ops.py:150-161
     const float wy1 = 0.0f - a.boundary, wx1 = 0.0f - a.boundary;
@@ -336,7 +410,7 @@ __global__ void matcher_col_kernel(const float* q, int M, long long N, const flo
   labels[j] = label;
 }
 
-size_t label_smem_bytes(int G) { return (size_t)3 * G * 16 + (size_t)3 * G * 4 + (size_t)G * 4 + 16; }
+size_t label_smem_bytes(int G) { return (size_t)3 * G * 16 + (size_t)3 * G * 4 + (size_t)G * 4 + (size_t)3 * G * 4 + 48; }
 
 }  // namespace
 }  // namespace d2b

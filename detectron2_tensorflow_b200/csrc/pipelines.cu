@@ -387,6 +387,54 @@ __global__ void det_emit_kernel(F f, const u64* keys, int P, const int32_t* keep
   if (out_roi) out_roi[o] = roi;
 }
 
+// ------------------------------------------------------------------ YOLOv4 front (yolov4_outputs.py:352-360)
+struct YoloFetch {
+  const float4* boxes;      // [N, n]
+  const float* cand_score;  // [N, n] max over classes
+  const int32_t* cand_cls;  // [N, n] first argmax
+  int n;
+  __device__ __forceinline__ void get(int img, unsigned ci, float4& box, float& score, int& cls, int& roi) const {
+    const size_t o = (size_t)img * n + ci;
+    box = __ldg(boxes + o);
+    score = cand_score[o];
+    cls = cand_cls[o];
+    roi = (int)ci;
+  }
+};
+
+// One warp per box, lanes stride the K class probabilities (coalesced); the (value, ~class) composite makes the
+// warp maximum pick the FIRST maximal class like tf.argmax.  Boxes above the threshold append a (score, index)
+// key to their image's candidate list; the segment sort restores (score desc, index asc).
+__global__ void yolo_prep_kernel(const float* probs, int n, int K, float thresh, int P, u64* keys, int32_t* count,
+                                 float* cand_score, int32_t* cand_cls) {
+  const int img = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const float* pr = probs + ((size_t)img * n + i) * K;
+  u64 best = 0ull;
+  for (int k = lane; k < K; k += 32) {
+    const u64 c = ((u64)float_to_key(__ldg(pr + k)) << 32) | (u64)(0xffffffffu - (unsigned)k);
+    best = c > best ? c : best;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const u64 o = __shfl_xor_sync(0xffffffffu, best, d);
+    best = o > best ? o : best;
+  }
+  if (lane == 0) {
+    const int cls = (int)(0xffffffffu - (unsigned)best);
+    const float s = __ldg(pr + cls);
+    const size_t o = (size_t)img * n + i;
+    cand_score[o] = s;
+    cand_cls[o] = cls;
+    if (s > thresh) {
+      const int slot = atomicAdd(count + img, 1);
+      keys[(size_t)img * P + slot] = make_key(s, (unsigned)i);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ Fast R-CNN front
 // one thread per (prediction row, class): threshold -> candidate key; also the dense slot map
 // and max_coord over ALL clipped boxes of the image (fast_rcnn.py:109-116,141).
@@ -802,6 +850,88 @@ extern "C" int d2b_retinanet_postprocess(const d2b_retinanet_params* p, void* wo
   if (rc != D2B_OK) return rc;
   det_emit_kernel<RetinaFetch, int32_t><<<dim3((T + 127) / 128, N), 128, 0, st>>>(
       f, keys3, a.P3, keep, nkeep, T, reinterpret_cast<float4*>(p->out_boxes), p->out_scores, p->out_classes,
+      p->out_valid, nullptr, p->out_num);
+  D2B_LAUNCH_CHECK();
+  return D2B_OK;
+}
+
+// =====================================================================================
+namespace {
+struct YoloPlan {
+  int P;
+  size_t bytes, o_keys, o_count, o_score, o_cls, o_nmsb, o_keep, o_nkeep, o_nms;
+};
+int yolo_plan(const d2b_yolo_params* p, YoloPlan& pl) {
+  D2B_REQUIRE(p != nullptr, "params is NULL");
+  D2B_REQUIRE(p->num_images >= 0 && p->num_boxes >= 0, "yolo: negative sizes");
+  D2B_REQUIRE(p->num_images <= 65535, "yolo: too many images");
+  D2B_REQUIRE(p->num_classes >= 1, "yolo: num_classes must be >= 1");
+  D2B_REQUIRE(p->post_nms_topk >= 1, "yolo: post_nms_topk must be >= 1");
+  D2B_REQUIRE(p->num_boxes < (1 << 30), "yolo: num_boxes too large");
+  const size_t N = p->num_images, n = p->num_boxes > 0 ? p->num_boxes : 1;
+  pl.P = pad_pow2((long long)n);
+  size_t o = 0;
+  pl.o_keys = o; o += ws_slice(N * pl.P * sizeof(u64));
+  pl.o_count = o; o += ws_slice(N * sizeof(int32_t));
+  pl.o_score = o; o += ws_slice(N * n * sizeof(float));
+  pl.o_cls = o; o += ws_slice(N * n * sizeof(int32_t));
+  pl.o_nmsb = o; o += ws_slice(N * n * sizeof(float4));
+  pl.o_keep = o; o += ws_slice(N * p->post_nms_topk * sizeof(int32_t));
+  pl.o_nkeep = o; o += ws_slice(N * sizeof(int32_t));
+  pl.o_nms = o; o += nms_sorted_workspace_bytes(p->num_images, (int)n, p->post_nms_topk);
+  pl.bytes = o;
+  return D2B_OK;
+}
+}  // namespace
+
+extern "C" size_t d2b_yolo_postprocess_workspace_bytes(const d2b_yolo_params* p) {
+  YoloPlan pl;
+  if (yolo_plan(p, pl) != D2B_OK) return 0;
+  return pl.bytes;
+}
+
+extern "C" int d2b_yolo_postprocess(const d2b_yolo_params* p, void* workspace, size_t workspace_bytes,
+                                    d2b_stream_t stream) {
+  YoloPlan pl;
+  int rc = yolo_plan(p, pl);
+  if (rc != D2B_OK) return rc;
+  if (p->num_images == 0) return D2B_OK;
+  D2B_REQUIRE(p->out_boxes && p->out_scores && p->out_classes && p->out_valid, "yolo: NULL output");
+  D2B_REQUIRE(p->num_boxes == 0 || (p->boxes && p->probs), "yolo: NULL input");
+  if (workspace == nullptr || workspace_bytes < pl.bytes) {
+    set_last_error("yolo_postprocess needs %zu workspace bytes", pl.bytes);
+    return D2B_EWORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  const int N = p->num_images, T = p->post_nms_topk, n = p->num_boxes;
+  const int stride = n > 0 ? n : 1;
+  u64* keys = reinterpret_cast<u64*>(ws + pl.o_keys);
+  int32_t* count = reinterpret_cast<int32_t*>(ws + pl.o_count);
+  float* cscore = reinterpret_cast<float*>(ws + pl.o_score);
+  int32_t* ccls = reinterpret_cast<int32_t*>(ws + pl.o_cls);
+  float4* nms_boxes = reinterpret_cast<float4*>(ws + pl.o_nmsb);
+  int32_t* keep = reinterpret_cast<int32_t*>(ws + pl.o_keep);
+  int32_t* nkeep = reinterpret_cast<int32_t*>(ws + pl.o_nkeep);
+  u64* nms_in = reinterpret_cast<u64*>(p->out_nms_boxes_in);
+  if (nms_in) D2B_CUDA(cudaMemsetAsync(nms_in, 0, sizeof(u64), st));
+  D2B_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t) * N, st));
+  if (n > 0) {
+    yolo_prep_kernel<<<dim3((n + 7) / 8, N), 256, 0, st>>>(p->probs, n, p->num_classes, p->score_thresh, pl.P, keys,
+                                                           count, cscore, ccls);
+    D2B_LAUNCH_CHECK();
+  }
+  rc = sort_segments_desc(keys, N, pl.P, count, st);
+  if (rc != D2B_OK) return rc;
+  YoloFetch f{reinterpret_cast<const float4*>(p->boxes), cscore, ccls, stride};
+  det_gather_kernel<YoloFetch><<<dim3((stride + 255) / 256, N), 256, 0, st>>>(f, keys, count, nullptr, pl.P, stride,
+                                                                               1, nms_boxes, nms_in);
+  D2B_LAUNCH_CHECK();
+  rc = nms_sorted(reinterpret_cast<const float*>(nms_boxes), count, N, stride, T, p->nms_thresh, keep, nkeep,
+                  ws + pl.o_nms, st);  // yolov4_outputs.py:362-364 (class-agnostic)
+  if (rc != D2B_OK) return rc;
+  det_emit_kernel<YoloFetch, int64_t><<<dim3((T + 127) / 128, N), 128, 0, st>>>(
+      f, keys, pl.P, keep, nkeep, T, reinterpret_cast<float4*>(p->out_boxes), p->out_scores, p->out_classes,
       p->out_valid, nullptr, p->out_num);
   D2B_LAUNCH_CHECK();
   return D2B_OK;

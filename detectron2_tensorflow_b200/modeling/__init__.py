@@ -5,3 +5,5 @@ from .roi_heads.fast_rcnn import fast_rcnn_inference, FastRCNNOutputs
 from .single_stage_heads.retinanet import RetinaNetInference
 from .anchor_generator import DefaultAnchorGenerator, GridAnchors
 from .matcher import Matcher, label_boxes
+from .single_stage_heads.yolov4_outputs import YOLOv4Inference
+from .single_stage_heads.solo_v2 import point_nms

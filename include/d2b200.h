@@ -471,6 +471,48 @@ D2B_API size_t d2b_roi_align_backward_workspace_bytes(const d2b_roi_align_backwa
 D2B_API int d2b_roi_align_backward(const d2b_roi_align_backward_params* p, void* workspace,
                                    size_t workspace_bytes, d2b_stream_t stream);
 
+/* ========================================================================
+ * SURVEY.md section 8(f) "next" row #4: YOLOv4 post-processing and SOLOv2's point NMS
+ * ====================================================================== */
+
+/* ------------------------------------------------------------------------
+ * YOLOv4Outputs.inference    lib/modeling/single_stage_heads/yolov4_outputs.py:331-390
+ * boxes [N, n, 4], probs [N, n, K] -> per image: max/argmax over classes, score
+ * threshold, ONE class-agnostic NMS capped at post_nms_topk, zero-padded outputs.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* boxes;
+  const float* probs;
+  int32_t num_images;
+  int32_t num_boxes;   /* n */
+  int32_t num_classes; /* K */
+  float score_thresh, nms_thresh;
+  int32_t post_nms_topk;
+  float* out_boxes;     /* [N, post, 4] */
+  float* out_scores;    /* [N, post] */
+  int64_t* out_classes; /* [N, post] */
+  uint8_t* out_valid;   /* [N, post] */
+  int32_t* out_num;     /* optional [N] */
+  int64_t* out_nms_boxes_in; /* optional [1] */
+} d2b_yolo_params;
+D2B_API size_t d2b_yolo_postprocess_workspace_bytes(const d2b_yolo_params* p);
+D2B_API int d2b_yolo_postprocess(const d2b_yolo_params* p, void* workspace, size_t workspace_bytes,
+                                 d2b_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * point_nms (kernel_size 2)        lib/modeling/single_stage_heads/solo_v2.py:29-40
+ * scores [N, H, W, C] NHWC -> out (same shape): x survives iff it equals the max of its
+ * 2x2 window (itself, up, left, up-left; zeros outside the map), else 0.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* scores;
+  int32_t num_images, height, width, channels;
+  float* out;
+} d2b_point_nms_params;
+D2B_API size_t d2b_point_nms_workspace_bytes(const d2b_point_nms_params* p);
+D2B_API int d2b_point_nms(const d2b_point_nms_params* p, void* workspace, size_t workspace_bytes,
+                          d2b_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -386,3 +386,28 @@ def roi_pooler_backward(grad_out, feat_shapes, scales, boxes, batch_idx, samplin
                                        int(canonical_box_size), int(canonical_level))
     assert rc == 0
     return outs
+
+
+def yolo_inference(boxes, probs, score_thresh, nms_thresh, post_nms_topk):
+    """lib/modeling/single_stage_heads/yolov4_outputs.py:331-390 -> (boxes, scores, classes int64, valid, num)."""
+    boxes = _f32(boxes)
+    probs = _f32(probs)
+    N, n, K = probs.shape
+    T = int(post_nms_topk)
+    ob = np.zeros((N, T, 4), np.float32)
+    os_ = np.zeros((N, T), np.float32)
+    oc = np.zeros((N, T), np.int64)
+    ov = np.zeros((N, T), np.uint8)
+    on = np.zeros(N, np.int32)
+    lib().orc_yolo_inference(_p(boxes), _p(probs), N, C.c_int64(n), K, C.c_float(score_thresh), C.c_float(nms_thresh),
+                             T, _p(ob), _p(os_), _p(oc), _p(ov), _p(on))
+    return ob, os_, oc, ov.astype(bool), on
+
+
+def point_nms(x):
+    """lib/modeling/single_stage_heads/solo_v2.py:29-40 on NHWC scores."""
+    x = _f32(x)
+    N, H, W, Cc = x.shape
+    out = np.empty_like(x)
+    lib().orc_point_nms(_p(x), N, H, W, Cc, _p(out))
+    return out

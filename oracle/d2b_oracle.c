@@ -1082,3 +1082,62 @@ ORC_API int orc_roi_pooler_backward(const float* grad_out, float* const* grad_fe
   free(lv);
   return rc;
 }
+
+/* ------------------------------------------------------------------ YOLOv4 post-processing (SURVEY.md 8f "next" #4)
+ * lib/modeling/single_stage_heads/yolov4_outputs.py:331-390 YOLOv4Outputs.inference, per image:
+ *   score_max = reduce_max(probs, -1); keep = where(score_max > score_threshold)        (:352-355)
+ *   classes = argmax(probs[keep], -1) (first maximum), scores = reduce_max(probs[keep]) (:359-360)
+ *   ONE class-agnostic tf.image.non_max_suppression(boxes[keep], scores, post_nms_topk) (:362-364)
+ *   gather, zero-pad to post_nms_topk with is_valid                                     (:365-375)
+ * boxes [N, n, 4], probs [N, n, K]. */
+ORC_API void orc_yolo_inference(const float* boxes, const float* probs, int N, int64_t n, int K,
+                                float score_thresh, float nms_thresh, int post_nms_topk, float* out_boxes,
+                                float* out_scores, int64_t* out_classes, uint8_t* out_valid, int32_t* out_num) {
+#pragma omp parallel for num_threads(ORC_NT) schedule(dynamic, 1)
+  for (int im = 0; im < N; ++im) {
+    const size_t cap = (size_t)(n > 0 ? n : 1);
+    float* cb = (float*)malloc(sizeof(float) * 4 * cap);
+    float* cs = (float*)malloc(sizeof(float) * cap);
+    int64_t* cc = (int64_t*)malloc(sizeof(int64_t) * cap);
+    int64_t total = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      const float* pr = probs + ((size_t)im * n + i) * K;
+      float mx = pr[0]; int64_t am = 0;
+      for (int k = 1; k < K; ++k) if (pr[k] > mx) { mx = pr[k]; am = k; }
+      if (!(mx > score_thresh)) continue;
+      memcpy(cb + 4 * total, boxes + ((size_t)im * n + i) * 4, 16);
+      cs[total] = mx; cc[total] = am; ++total;
+    }
+    int32_t* keep = (int32_t*)malloc(sizeof(int32_t) * (size_t)(post_nms_topk > 0 ? post_nms_topk : 1));
+    const int32_t nk = orc_nms(cb, cs, total, post_nms_topk, nms_thresh, keep);
+    for (int j = 0; j < post_nms_topk; ++j) {
+      const size_t o = (size_t)im * post_nms_topk + j;
+      float* ob = out_boxes + o * 4;
+      if (j < nk) { memcpy(ob, cb + 4 * (size_t)keep[j], 16); out_scores[o] = cs[keep[j]];
+                    out_classes[o] = cc[keep[j]]; out_valid[o] = 1; }
+      else { ob[0] = ob[1] = ob[2] = ob[3] = 0.0f; out_scores[o] = 0.0f; out_classes[o] = 0; out_valid[o] = 0; }
+    }
+    if (out_num) out_num[im] = nk;
+    free(keep); free(cc); free(cs); free(cb);
+  }
+}
+
+/* lib/modeling/single_stage_heads/solo_v2.py:29-40 point_nms (kernel_size 2) on NHWC scores:
+ * zero-pad 1, max_pool 2x2 stride 1 VALID, keep = (x == pooled[:, :-1, :-1]) => x[y,x] survives iff it equals
+ * max(x[y-1..y, x-1..x], with zeros outside). */
+ORC_API void orc_point_nms(const float* x, int N, int H, int W, int C, float* out) {
+#pragma omp parallel for collapse(2) num_threads(ORC_NT) schedule(static)
+  for (int n = 0; n < N; ++n)
+    for (int y = 0; y < H; ++y)
+      for (int xx = 0; xx < W; ++xx)
+        for (int c = 0; c < C; ++c) {
+          const size_t o = (((size_t)n * H + y) * W + xx) * C + c;
+          const float v = x[o];
+          float m = v;
+          const float up = (y > 0) ? x[o - (size_t)W * C] : 0.0f;
+          const float lf = (xx > 0) ? x[o - C] : 0.0f;
+          const float ul = (y > 0 && xx > 0) ? x[o - (size_t)W * C - C] : 0.0f;
+          m = fmaxf(m, up); m = fmaxf(m, lf); m = fmaxf(m, ul);
+          out[o] = (v == m) ? v * 1.0f : v * 0.0f;
+        }
+}

@@ -51,7 +51,11 @@ def load_reference():
     L.ROIAlign = imp("reflib.layers.roi_align").ROIAlign
     nms = imp("reflib.layers.nms")
     L.batch_nms, L.matrix_nms = nms.batch_nms, nms.matrix_nms
-    L.smooth_l1_loss = L.Linear = L.Conv2D = L.sigmoid_focal_loss = None  # training-only names pulled in by imports
+    # training-only / conv-layer names pulled in by import lines, never called on this path
+    for nm in ("smooth_l1_loss", "Linear", "Conv2D", "sigmoid_focal_loss", "iou_loss", "dice_loss", "DeformConv2D",
+               "ModulatedDeformConv2D", "GroupNorm", "Upsample"):
+        setattr(L, nm, None)
+    L.resize_images = fn.resize_images
     L.Sequential = imp("reflib.layers.base").Sequential
     L.ShapeSpec = imp("reflib.layers.shape_spec").ShapeSpec
     S = sys.modules["reflib.structures"]
@@ -64,7 +68,9 @@ def load_reference():
                 rpn_outputs=imp("reflib.modeling.proposal_generator.rpn_outputs"),
                 fast_rcnn=imp("reflib.modeling.roi_heads.fast_rcnn"),
                 anchor_generator=imp("reflib.modeling.anchor_generator"),
-                retinanet=imp("reflib.modeling.single_stage_heads.retinanet"))
+                retinanet=imp("reflib.modeling.single_stage_heads.retinanet"),
+                yolo=imp("reflib.modeling.single_stage_heads.yolov4_outputs"),
+                solo=imp("reflib.modeling.single_stage_heads.solo_v2"))
     return types.SimpleNamespace(**mods)
 
 
@@ -237,6 +243,22 @@ def main():
         out[f"rn_cls{l}"], out[f"rn_reg{l}"] = cls[l].reshape(Nimg, -1, K), reg[l].reshape(Nimg, -1, 4)
     out["rn_boxes"], out["rn_scores"] = np.asarray(res.boxes), np.asarray(res.get_field("scores"))
     out["rn_classes"], out["rn_valid"] = np.asarray(res.get_field("pred_classes")), np.asarray(res.get_field("is_valid"))
+
+    # ---- 12. YOLOv4Outputs.inference (yolov4_outputs.py:331-390)
+    Nimg, nb, K = 2, 300, 6
+    yb = np.stack([rand_boxes(rng, nb, 240, 320, 8, 120) for _ in range(Nimg)])
+    yb[:, 100:200] = yb[:, :100] + rng.normal(0, 3, (Nimg, 100, 4)).astype(np.float32)  # near duplicates
+    yp = (rng.random((Nimg, nb, K)) ** 4).astype(np.float32)
+    yp[:, ::7] = np.round(yp[:, ::7] * 4) / 4  # ties across classes (first argmax) and across boxes
+    yself = types.SimpleNamespace(score_threshold=0.3, nms_threshold=0.5, post_nms_topk=40,
+                                  _get_predictions=lambda: (t(yb), None, t(yp)))
+    res = R.yolo.YOLOV4Outputs.inference(yself)
+    out.update(yo_boxes_in=yb, yo_probs=yp, yo_boxes=np.asarray(res.boxes), yo_scores=np.asarray(res.get_field("scores")),
+               yo_classes=np.asarray(res.get_field("pred_classes")), yo_valid=np.asarray(res.get_field("is_valid")))
+
+    # ---- 13. point_nms (solo_v2.py:29-40)
+    pn = np.round(rng.standard_normal((2, 9, 11, 8)) * 2).astype(np.float32) / 2  # plateaus and negatives
+    out["pn_in"], out["pn_out"] = pn, np.asarray(R.solo.point_nms(t(pn)))
 
     np.savez_compressed(os.path.join(HERE, "reference_python.npz"), **out)
     print("reference_python.npz:", len(out), "arrays,",

@@ -399,7 +399,17 @@ def build_tf():
         x = np.asarray(x, np.float32)
         e = np.exp(x - x.max(axis=axis, keepdims=True))
         return t(e / e.sum(axis=axis, keepdims=True))
-    tf.nn = types.SimpleNamespace(top_k=_top_k, sigmoid=un(lambda x: (np.float32(1) / (np.float32(1) + np.exp(-x)))),
+    def max_pool(value, ksize, strides, padding, data_format="NHWC", name=None):
+        x = np.asarray(value)
+        kh, kw = ksize[1], ksize[2]
+        assert list(strides) == [1, 1, 1, 1] and padding == "VALID"
+        oh, ow = x.shape[1] - kh + 1, x.shape[2] - kw + 1
+        out = np.full((x.shape[0], oh, ow, x.shape[3]), -np.inf, x.dtype)
+        for dy in range(kh):
+            for dx in range(kw):
+                out = np.maximum(out, x[:, dy:dy + oh, dx:dx + ow])
+        return t(out)
+    tf.nn = types.SimpleNamespace(max_pool=max_pool, top_k=_top_k, sigmoid=un(lambda x: (np.float32(1) / (np.float32(1) + np.exp(-x)))),
                                   softmax=softmax, relu=un(lambda x: np.maximum(x, 0)))
     tf.image = types.SimpleNamespace(crop_and_resize=_crop_and_resize, non_max_suppression=_non_max_suppression,
                                      resize_images=None, ResizeMethod=types.SimpleNamespace(BILINEAR=0, NEAREST_NEIGHBOR=1))

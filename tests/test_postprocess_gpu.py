@@ -334,3 +334,30 @@ def test_anchor_generator_and_in_kernel_anchors(cuda, oracle_lib):
     res = head.inference([T(x, cuda) for x in cls], [T(x, cuda) for x in dl], rgen.grid_descriptors(rgrids))
     assert np.array_equal(res.boxes.cpu().numpy(), wb) and np.array_equal(res.get_field('scores').cpu().numpy(), ws)
     assert np.array_equal(res.get_field('pred_classes').cpu().numpy(), wc)
+
+
+# ------------------------------------------------------------------ YOLOv4 post-processing / point_nms (8f #4)
+@pytest.mark.parametrize("n,K,topk", [(22743, 80, 100), (3000, 20, 300), (50, 3, 10), (0, 5, 10)])
+def test_yolo_postprocess(cuda, oracle_lib, n, K, topk):
+    from detectron2_tensorflow_b200.modeling import YOLOv4Inference
+    rng = np.random.default_rng(n + K)
+    N = 3
+    boxes = np.stack([clustered_boxes(rng, n, k=40) if n else np.zeros((0, 4), np.float32) for _ in range(N)])
+    probs = (rng.random((N, n, K)) ** 6).astype(np.float32)
+    if n:
+        probs[:, ::5] = np.round(probs[:, ::5] * 8) / 8  # class ties (first argmax) and score ties (index order)
+        probs[1] *= 0.01  # an image with no candidate at all
+    want = oracle_lib.yolo_inference(boxes, probs, 0.25, 0.45, topk)
+    res = YOLOv4Inference(0.25, 0.45, topk).inference(T(boxes, cuda), T(probs, cuda))
+    assert np.array_equal(res.get_field("is_valid").cpu().numpy(), want[3])
+    assert np.array_equal(res.get_field("pred_classes").cpu().numpy(), want[2])
+    assert np.array_equal(res.get_field("scores").cpu().numpy(), want[1])
+    assert np.array_equal(res.boxes.cpu().numpy(), want[0])
+
+
+@pytest.mark.parametrize("shape", [(2, 40, 40, 80), (1, 12, 12, 80), (2, 7, 5, 3), (1, 1, 1, 4)])
+def test_point_nms(cuda, oracle_lib, shape):
+    from detectron2_tensorflow_b200.modeling import point_nms
+    rng = np.random.default_rng(sum(shape))
+    x = (np.round(rng.standard_normal(shape) * 3) / 3).astype(np.float32)
+    assert np.array_equal(point_nms(T(x, cuda)).cpu().numpy(), oracle_lib.point_nms(x))

@@ -144,3 +144,19 @@ def test_retinanet_inference(oracle_lib, z):
     assert np.allclose(s, z["rn_scores"], rtol=1e-5, atol=1e-7)
     assert np.allclose(b, z["rn_boxes"], rtol=1e-5, atol=1e-3)
     assert 0 < v.sum()
+
+
+def test_yolo_inference(oracle_lib, z):
+    """YOLOV4Outputs.inference (yolov4_outputs.py:331-390): no transcendental on the path => exact."""
+    b, s, c, v, n = oracle_lib.yolo_inference(z["yo_boxes_in"], z["yo_probs"], 0.3, 0.5, 40)
+    assert np.array_equal(v, z["yo_valid"])
+    assert np.array_equal(c, z["yo_classes"])
+    assert np.array_equal(s, z["yo_scores"])
+    assert np.array_equal(b, z["yo_boxes"])
+    assert 0 < v.sum()
+
+
+def test_point_nms(oracle_lib, z):
+    got = oracle_lib.point_nms(z["pn_in"])
+    assert np.array_equal(got, z["pn_out"])
+    assert 0 < (got != 0).sum() < (z["pn_in"] != 0).sum()

@@ -129,3 +129,13 @@ def test_retinanet_inference_with_synthesised_anchors(cuda, z):
         assert np.array_equal(res.get_field("pred_classes").cpu().numpy(), z["rn_classes"])
         assert np.allclose(res.get_field("scores").cpu().numpy(), z["rn_scores"], rtol=1e-5, atol=1e-7)
         assert np.allclose(res.boxes.cpu().numpy(), z["rn_boxes"], rtol=1e-5, atol=1e-3)
+
+
+def test_yolo_and_point_nms(cuda, z):
+    from detectron2_tensorflow_b200.modeling import YOLOv4Inference, point_nms
+    res = YOLOv4Inference(0.3, 0.5, 40).inference(T(z["yo_boxes_in"], cuda), T(z["yo_probs"], cuda))
+    assert np.array_equal(res.get_field("is_valid").cpu().numpy(), z["yo_valid"])
+    assert np.array_equal(res.get_field("pred_classes").cpu().numpy(), z["yo_classes"])
+    assert np.array_equal(res.get_field("scores").cpu().numpy(), z["yo_scores"])
+    assert np.array_equal(res.boxes.cpu().numpy(), z["yo_boxes"])
+    assert np.array_equal(point_nms(T(z["pn_in"], cuda)).cpu().numpy(), z["pn_out"])
