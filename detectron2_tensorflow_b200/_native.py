@@ -82,7 +82,8 @@ class RetinanetParams(C.Structure):
 
 class MatrixNmsParams(C.Structure):
     _fields_ = [("masks", _vp), ("classes", _vp), ("scores", _vp), ("sum_masks", _vp), ("counts", _vp),
-                ("batch", _i32), ("n", _i32), ("hw", _i64), ("kernel", _i32), ("sigma", _f32), ("out", _vp)]
+                ("batch", _i32), ("n", _i32), ("hw", _i64), ("kernel", _i32), ("sigma", _f32), ("out", _vp),
+                ("packed_masks", _vp)]
 
 
 class PasteMasksParams(C.Structure):
@@ -143,6 +144,11 @@ class PointNmsParams(C.Structure):
                 ("out", _vp)]
 
 
+class SoloMaskEncodeParams(C.Structure):
+    _fields_ = [("mask_logits", _vp), ("counts", _vp), ("batch", _i32), ("n", _i32), ("hw", _i64),
+                ("mask_threshold", _f32), ("packed_masks", _vp), ("sum_masks", _vp), ("score_sums", _vp)]
+
+
 class RoiAlignBackwardParams(C.Structure):
     _fields_ = [("fwd", RoiAlignParams), ("grad_out", _vp), ("grad_features", _vp * MAX_LEVELS)]
 
@@ -167,6 +173,7 @@ OPS = {
     "roi_align_backward": RoiAlignBackwardParams,
     "yolo_postprocess": YoloParams,
     "point_nms": PointNmsParams,
+    "solo_mask_encode": SoloMaskEncodeParams,
 }
 EXPORTS = ["d2b_version", "d2b_status_string", "d2b_last_error", "d2b_kernel_launch_count"] + \
           [f"d2b_{op}{sfx}" for op in OPS for sfx in ("", "_workspace_bytes")]

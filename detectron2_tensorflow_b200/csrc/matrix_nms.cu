@@ -57,6 +57,19 @@ __global__ void __launch_bounds__(256) mnms_pack_kernel(MnmsArgs a) {
   }
 }
 
+// packed input (d2b_solo_mask_encode): only the exact mask sums are missing; one warp per mask row
+__global__ void __launch_bounds__(256) mnms_popc_kernel(MnmsArgs a) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= rows_of(a, b)) return;
+  const int lane = threadIdx.x & 31;
+  const u64* pi = a.packed + ((size_t)b * a.n + i) * a.Wd;
+  unsigned c = 0;
+  for (int w = lane; w < a.Wd; w += 32) c += __popcll(pi[w]);
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) a.isum[(size_t)b * a.n + i] = c;
+}
+
 // Vector path (hw % 4 == 0): the one streaming read of the fp32 masks.  A warp packs 2 words per step
 // (lane = one float4 = 4 pixels; 16 lanes = 64 pixels = one word) and keeps kPackSteps independent
 // 16-byte loads in flight per lane.  grid (ceil(Wd / 128), n, B), 256 threads = 128 words per CTA.
@@ -188,7 +201,7 @@ __global__ void __launch_bounds__(256) mnms_decay_kernel(MnmsArgs a) {
 size_t mnms_bytes(const d2b_matrix_nms_params* p, size_t* o_packed, size_t* o_isum, size_t* o_iou, size_t* o_cmax) {
   const size_t B = p->batch, n = p->n, Wd = (size_t)((p->hw + 63) / 64);
   size_t o = 0;
-  *o_packed = o; o += ws_slice(B * n * Wd * sizeof(u64));
+  *o_packed = o; o += p->packed_masks ? 0 : ws_slice(B * n * Wd * sizeof(u64));
   *o_isum = o; o += ws_slice(B * n * sizeof(unsigned));
   *o_iou = o; o += ws_slice(B * n * n * sizeof(float));
   *o_cmax = o; o += ws_slice(B * n * sizeof(float));
@@ -215,7 +228,7 @@ extern "C" int d2b_matrix_nms(const d2b_matrix_nms_params* p, void* workspace, s
   if (p->batch == 0 || p->n == 0) return D2B_OK;
   D2B_REQUIRE(p->n <= 65535, "matrix_nms: n=%d too large", p->n);
   D2B_REQUIRE(p->hw > 0 && p->hw < (1ll << 31) * 32, "matrix_nms: bad mask size");
-  D2B_REQUIRE(p->masks && p->classes && p->scores && p->out, "matrix_nms: NULL pointer");
+  D2B_REQUIRE((p->masks || p->packed_masks) && p->classes && p->scores && p->out, "matrix_nms: NULL pointer");
   size_t o_packed, o_isum, o_iou, o_cmax;
   const size_t need = mnms_bytes(p, &o_packed, &o_isum, &o_iou, &o_cmax);
   if (workspace == nullptr || workspace_bytes < need) {
@@ -229,17 +242,20 @@ extern "C" int d2b_matrix_nms(const d2b_matrix_nms_params* p, void* workspace, s
   a.sum_in = p->sum_masks; a.counts = p->counts; a.B = p->batch; a.n = p->n; a.hw = p->hw;
   a.Wd = (int)((p->hw + 63) / 64); a.kernel = p->kernel;
   a.nsigma = (float)(-1.0 * (double)p->sigma);
-  a.packed = reinterpret_cast<u64*>(ws + o_packed);
+  a.packed = p->packed_masks ? const_cast<u64*>(reinterpret_cast<const u64*>(p->packed_masks))
+                             : reinterpret_cast<u64*>(ws + o_packed);
   a.isum = reinterpret_cast<unsigned*>(ws + o_isum);
   a.iou = reinterpret_cast<float*>(ws + o_iou);
   a.cmax = reinterpret_cast<float*>(ws + o_cmax);
   a.out = p->out;
   D2B_CUDA(cudaMemsetAsync(a.isum, 0, sizeof(unsigned) * (size_t)a.B * a.n, st));
-  if (a.hw % 4 == 0 && (reinterpret_cast<uintptr_t>(a.masks) & 15) == 0)
+  if (p->packed_masks) {
+    if (!a.sum_in) mnms_popc_kernel<<<dim3((a.n + 7) / 8, a.B), 256, 0, st>>>(a);
+  } else if (a.hw % 4 == 0 && (reinterpret_cast<uintptr_t>(a.masks) & 15) == 0)
     mnms_pack4_kernel<<<dim3((a.Wd + 8 * kPackSteps * 2 - 1) / (8 * kPackSteps * 2), a.n, a.B), 256, 0, st>>>(a);
   else
     mnms_pack_kernel<<<dim3((a.Wd + 7) / 8, a.n, a.B), 256, 0, st>>>(a);
-  D2B_LAUNCH_CHECK();
+  if (!(p->packed_masks && a.sum_in)) D2B_LAUNCH_CHECK();
   mnms_iou_kernel<<<dim3(a.n, a.B), 256, 0, st>>>(a);
   D2B_LAUNCH_CHECK();
   mnms_cmax_kernel<<<dim3((a.n + 7) / 8, a.B), 256, 0, st>>>(a);

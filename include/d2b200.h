@@ -287,6 +287,9 @@ typedef struct {
   int32_t kernel;
   float sigma;
   float* out; /* [B, n] */
+  /* optional [B, n, ceil(hw/64)] bit-packed masks (bit p of word w = pixel 64*w + p), e.g. from
+   * d2b_solo_mask_encode: when non-NULL `masks` is ignored and the 4 B/pixel read disappears */
+  const uint64_t* packed_masks;
 } d2b_matrix_nms_params;
 D2B_API size_t d2b_matrix_nms_workspace_bytes(const d2b_matrix_nms_params* p);
 D2B_API int d2b_matrix_nms(const d2b_matrix_nms_params* p, void* workspace, size_t workspace_bytes,
@@ -512,6 +515,28 @@ typedef struct {
 D2B_API size_t d2b_point_nms_workspace_bytes(const d2b_point_nms_params* p);
 D2B_API int d2b_point_nms(const d2b_point_nms_params* p, void* workspace, size_t workspace_bytes,
                           d2b_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * SOLOv2 mask stage        lib/modeling/single_stage_heads/solo_v2.py:513-517, 530-533
+ *   pred_mask_scores = sigmoid(mask_logits); pred_masks = cast(scores > mask_threshold)
+ *   sum_masks = reduce_sum(pred_masks); score_sums = reduce_sum(scores * pred_masks)
+ * One streaming read of the logits [B, n, hw]; the masks leave as bit-packed words for
+ * d2b_matrix_nms(packed_masks=...), so the fp32 0/1 masks are never materialised.
+ * sum_masks is exact; score_sums is an fp32 sum in unspecified order (like tf.reduce_sum).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* mask_logits;
+  const int32_t* counts; /* optional [B]: valid prefix per image */
+  int32_t batch, n;
+  int64_t hw;
+  float mask_threshold;
+  uint64_t* packed_masks; /* [B, n, ceil(hw/64)] */
+  float* sum_masks;       /* [B, n] */
+  float* score_sums;      /* [B, n] */
+} d2b_solo_mask_encode_params;
+D2B_API size_t d2b_solo_mask_encode_workspace_bytes(const d2b_solo_mask_encode_params* p);
+D2B_API int d2b_solo_mask_encode(const d2b_solo_mask_encode_params* p, void* workspace, size_t workspace_bytes,
+                                 d2b_stream_t stream);
 
 #ifdef __cplusplus
 }

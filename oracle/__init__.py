@@ -411,3 +411,15 @@ def point_nms(x):
     out = np.empty_like(x)
     lib().orc_point_nms(_p(x), N, H, W, Cc, _p(out))
     return out
+
+
+def solo_mask_stage(logits, mask_threshold=0.5):
+    """solo_v2.py:513-517,530-533: logits [n,H,W] -> (masks fp32 0/1 [n,H,W], sum_masks [n], score_sums [n])."""
+    x = _f32(logits)
+    n = x.shape[0]
+    hw = int(np.prod(x.shape[1:]))
+    masks = np.empty_like(x)
+    sm = np.empty(n, np.float32)
+    ss = np.empty(n, np.float32)
+    lib().orc_solo_mask_stage(_p(x), C.c_int64(n), C.c_int64(hw), C.c_float(mask_threshold), _p(masks), _p(sm), _p(ss))
+    return masks, sm, ss

@@ -1141,3 +1141,26 @@ ORC_API void orc_point_nms(const float* x, int N, int H, int W, int C, float* ou
           out[o] = (v == m) ? v * 1.0f : v * 0.0f;
         }
 }
+
+/* lib/modeling/single_stage_heads/solo_v2.py:513-517, 530-533 (mask stage of SOLOv2Head.inference):
+ *   scores = sigmoid(logits); masks = cast(scores > thr, float32); sum_masks = reduce_sum(masks);
+ *   score_sums = reduce_sum(scores * masks)   (TF's summation order is unspecified: the fp32 products are
+ *                                              accumulated in double here and rounded once)
+ * logits [n, hw] -> masks [n, hw] fp32 0/1, sum_masks [n], score_sums [n]. */
+ORC_API void orc_solo_mask_stage(const float* logits, int64_t n, int64_t hw, float thr, float* masks,
+                                 float* sum_masks, float* score_sums) {
+#pragma omp parallel for num_threads(ORC_NT) schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    float sm = 0.0f;
+    double ss = 0.0;
+    for (int64_t p = 0; p < hw; ++p) {
+      const float s = orc_sigmoidf(logits[i * hw + p]);
+      const float m = (s > thr) ? 1.0f : 0.0f;
+      masks[i * hw + p] = m;
+      sm = sm + m;
+      const float prod = s * m;
+      if (m != 0.0f) ss += (double)prod;
+    }
+    sum_masks[i] = sm; score_sums[i] = (float)ss;
+  }
+}

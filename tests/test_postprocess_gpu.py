@@ -361,3 +361,41 @@ def test_point_nms(cuda, oracle_lib, shape):
     rng = np.random.default_rng(sum(shape))
     x = (np.round(rng.standard_normal(shape) * 3) / 3).astype(np.float32)
     assert np.array_equal(point_nms(T(x, cuda)).cpu().numpy(), oracle_lib.point_nms(x))
+
+
+@pytest.mark.parametrize("hw,thr", [((40, 64), 0.5), ((25, 37), 0.5), ((200, 336), 0.5), ((16, 20), 0.9995), ((16, 20), 0.0)])
+def test_solo_mask_encode_and_packed_matrix_nms(cuda, oracle_lib, hw, thr):
+    """Mask stage of SOLOv2Head.inference (solo_v2.py:513-533) + Matrix-NMS fed with the packed words."""
+    from detectron2_tensorflow_b200.modeling import solo_mask_encode
+    rng = np.random.default_rng(hw[0] * 7 + hw[1])
+    n = 60 if hw[0] < 100 else 24
+    H, W = hw
+    # smooth blobs so masks are object-like; values dense around logit(thr) to stress the guard band
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    logits = np.empty((n, H, W), np.float32)
+    for i in range(n):
+        cy, cx, r = rng.uniform(0, H), rng.uniform(0, W), rng.uniform(3, max(H, W) / 2)
+        logits[i] = (r - np.sqrt((yy - cy) ** 2 + (xx - cx) ** 2)) * rng.uniform(0.01, 2.0)
+    if 0.0 < thr < 1.0:
+        x0 = np.float32(np.log(thr / (1 - thr)))
+        near = x0 + np.arange(-40, 41, dtype=np.float32) * np.spacing(x0) * 0.5  # +-20 ulp around the crossing
+        logits[0].ravel()[:near.size] = near
+        logits[1] = x0
+    logits[2, 0, :4] = [np.nan, np.inf, -np.inf, 0.0]
+    logits[n // 2:] = logits[:n - n // 2] + rng.normal(0, 0.05, (n - n // 2, H, W)).astype(np.float32)  # duplicates
+    masks, sm, ss = oracle_lib.solo_mask_stage(logits, thr)
+    packed, gsm, gss = solo_mask_encode(T(logits, cuda), thr)
+    bits = np.unpackbits(packed.cpu().numpy().view(np.uint8), axis=-1, bitorder="little")[:, :H * W]
+    assert np.array_equal(bits.reshape(n, H, W), masks.astype(np.uint8))
+    assert np.array_equal(gsm.cpu().numpy(), sm)
+    assert np.allclose(gss.cpu().numpy(), ss, rtol=1e-5, atol=1e-6)  # fp32 sum order (tf.reduce_sum is unspecified too)
+    # Matrix-NMS on the packed words == Matrix-NMS on the fp32 masks (both CUDA) == oracle
+    classes = rng.integers(0, 3, n).astype(np.int64)
+    scores = np.sort(rng.uniform(0.1, 1, n).astype(np.float32))[::-1].copy()
+    want = oracle_lib.matrix_nms(masks, classes, scores, sm, "gaussian", 2.0)
+    got_packed = matrix_nms(None, T(classes, cuda), T(scores, cuda), sum_masks=gsm, packed_masks=packed, mask_hw=H * W)
+    got_dense = matrix_nms(T(masks, cuda), T(classes, cuda), T(scores, cuda), sum_masks=T(sm, cuda))
+    assert np.array_equal(got_packed.cpu().numpy(), want, equal_nan=True)
+    assert np.array_equal(got_dense.cpu().numpy(), want, equal_nan=True)
+    got_nosum = matrix_nms(None, T(classes, cuda), T(scores, cuda), packed_masks=packed, mask_hw=H * W)
+    assert np.array_equal(got_nosum.cpu().numpy(), want, equal_nan=True)

@@ -70,6 +70,17 @@ if "4" in which:
                       "masks_per_s": B * n / ms * 1e3, "mask_read_GB": by / 1e9, "GBps": by / ms / 1e6,
                       "frac_hbm": by / ms / 1e6 / HBM}))
 
+    # 8(f) #4: the mask stage feeding Matrix-NMS with bit-packed masks (logits -> words; no fp32 0/1 masks)
+    from detectron2_tensorflow_b200.modeling import solo_mask_encode
+    logits = (masks * 8.0 - 4.0) + torch.randn(masks.shape, device=dev, generator=g) * 0.5
+    ms_e = timeit(lambda: solo_mask_encode(logits, 0.5))
+    packed, sums, _ = solo_mask_encode(logits, 0.5)
+    ms_p = timeit(lambda: matrix_nms(None, classes, scores, sum_masks=sums, packed_masks=packed, mask_hw=H * W))
+    print(json.dumps({"config": 4, "case": "SOLOv2 mask stage: sigmoid+threshold+bit-pack+sums of the logits", "ms": ms_e,
+                      "GBps": by / ms_e / 1e6, "frac_hbm": by / ms_e / 1e6 / HBM}))
+    print(json.dumps({"config": 4, "case": "Matrix-NMS on packed masks (no fp32 mask read)", "ms": ms_p,
+                      "images_per_s": B / ms_p * 1e3, "packed_GB": packed.numel() * 8 / 1e9}))
+
 if "5" in which:
     N, C = 16, 256
     feats = [torch.randn((N,) + syn.level_hw(s) + (C,), device=dev, generator=g) for s in syn.FPN_STRIDES]
