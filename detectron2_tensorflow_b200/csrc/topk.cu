@@ -52,6 +52,7 @@ struct RowState {
   unsigned pre_done;   // CTAs of the logit pre-histogram that have finished
   unsigned cand_count; // SIGMOID rows with a cutoff: composites appended to the candidate list by pass 0
   unsigned compact;    // 1 => the candidate list holds every element that can matter: later passes read it
+  unsigned redo;       // 1 => the sampled cutoff left fewer than k_r elements: pass 0 is repeated without a cutoff
   unsigned done[kPasses];
 };
 
@@ -87,13 +88,12 @@ __device__ __forceinline__ u64 composite_of(uint32_t key, unsigned idx) {
 // Calls f(value, index, valid) for every element of [beg, end) -- and, with valid == false, for the padding
 // slots -- with warp-uniform control flow (f may use warp collectives).  16-byte loads when the chunk is
 // 16-byte aligned, kBatch/4 vectors (or kBatch scalars) in flight per thread.
-template <typename F>
+template <int kV = kBatch / 4, typename F>
 __device__ __forceinline__ void for_each_elem(const float* x, long long beg, long long end, F f) {
   const bool vec = ((reinterpret_cast<uintptr_t>(x + beg) & 15) == 0);
   if (vec) {
     const long long nvec = (end - beg) >> 2;
     const float4* xv = reinterpret_cast<const float4*>(x + beg);
-    constexpr int kV = kBatch / 4;
     for (long long v0 = 0; v0 < nvec; v0 += (long long)kV * kHistThreads) {  // block-uniform trip count
       float4 q[kV];
 #pragma unroll
@@ -146,14 +146,14 @@ __global__ void topk_init(TopkArgs a, int rows, int32_t* seg_len, int32_t* out_c
   if (kr == 0) { s.active = 0; s.threshold = ~0ull; }            // take nothing
   else if (kr == a.d.row_len[g]) { s.active = 0; s.threshold = 0ull; }  // take the whole row
   else { s.active = 1; s.threshold = 0ull; }
-  s.cut_key = 0u; s.pre_done = 0u; s.cand_count = 0u; s.compact = 0u;
+  s.cut_key = 0u; s.pre_done = 0u; s.cand_count = 0u; s.compact = 0u; s.redo = 0u;
   a.state[r] = s;
   seg_len[r] = (int32_t)kr;
   if (out_counts) out_counts[r] = (int32_t)kr;
 }
 
 constexpr int kCopies = 4;  // replicated pass-0 histograms (lane & 3) to spread same-bin atomics
-__global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass) {
+__global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass, int redo) {
   __shared__ unsigned sh[kCopies][kBins];
   __shared__ int s_last;
   int g, img, chunk;
@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass) 
   const int row = img * a.d.G + g;
   RowState* st = a.state + row;
   if (!st->active) return;  // uniform per CTA
+  if (redo && !st->redo) return;  // the repeat launch only serves rows whose sampled cutoff failed
   const u64 prefix = st->prefix;
   const int shift = c_shift[pass], bits = c_bits[pass];
   const unsigned mask = (1u << bits) - 1u;
@@ -188,16 +189,25 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass) 
     expect = 1u;
     const u64* cand = a.cand + (size_t)row * kCandCap;
     const unsigned n = st->cand_count;
-    for (unsigned j = threadIdx.x; j < n; j += kHistThreads) {
-      const u64 c = cand[j];
-      if ((c >> hi_shift) == prefix) atomicAdd(gh + ((unsigned)(c >> shift) & mask), 1u);
+    for (unsigned j0 = 0; j0 < n; j0 += kBatch * kHistThreads) {  // kBatch independent loads in flight per thread
+      u64 c[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const unsigned j = j0 + u * kHistThreads + threadIdx.x;
+        c[u] = j < n ? __ldcg(cand + j) : 0ull;  // 0 never matches a live prefix bucket below
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const unsigned j = j0 + u * kHistThreads + threadIdx.x;
+        if (j < n && (c[u] >> hi_shift) == prefix) atomicAdd(gh + ((unsigned)(c[u] >> shift) & mask), 1u);
+      }
     }
   } else {
     // Candidate list: pass 0 of a row with a logit cutoff remembers every element above the cutoff
     // (measured: doing the same after pass 1 for rows without a cutoff does not pay at RPN sizes).
     const bool cand0 = (pass == 0 && cut != 0u);
     u64* cand = (cand0 && a.cand) ? a.cand + (size_t)row * kCandCap : nullptr;
-    for_each_elem(x, beg, end, [&](float v, long long i, bool ok) {
+    auto body = [&](float v, long long i, bool ok) {
       bool in = ok && float_to_key(v) >= cut;
       unsigned digit = 0;
       if (in) {
@@ -210,7 +220,10 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass) 
         digit = (unsigned)(c >> shift) & mask;
       }
       if (in) atomicAdd(my + digit, 1u);
-    });
+    };
+    // rows with a cutoff do one compare per element: keep 4 x 16 B per thread in flight to stay HBM-bound
+    if (cand0) for_each_elem<4>(x, beg, end, body);
+    else for_each_elem(x, beg, end, body);
   }
   __syncthreads();
   if (use_smem) {
@@ -253,6 +266,16 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass) 
     __syncthreads();
   }
   const unsigned incl = scan[threadIdx.x], excl = incl - sum;
+  if (pass == 0 && cut != 0u && scan[kHistThreads - 1] < k_rem) {
+    // The cutoff came from a SAMPLE of the row (topk_prehist) and kept fewer than k_r elements: throw this
+    // pass away and let the repeat launch histogram the whole row without a cutoff.
+    for (int j = 0; j < kPer; ++j) gh[top - j] = 0u;
+    if (threadIdx.x == 0) {
+      st->cut_key = 0u; st->cand_count = 0u; st->compact = 0u; st->done[0] = 0u; st->redo = 1u;
+    }
+    return;
+  }
+  if (redo && threadIdx.x == 0) st->redo = 0u;
   if (excl < k_rem && k_rem <= incl) {
     unsigned above = excl;
     for (int j = 0; j < kPer; ++j) {
@@ -305,10 +328,18 @@ __global__ void __launch_bounds__(kHistThreads) topk_collect(TopkArgs a, u64* ou
     if (chunk != 0) return;
     const u64* cand = a.cand + (size_t)row * kCandCap;
     const unsigned n = st->cand_count;
-    for (unsigned j0 = 0; j0 < n; j0 += kHistThreads) {  // block-uniform trip count
-      const unsigned j = j0 + threadIdx.x;
-      const u64 c = j < n ? cand[j] : 0ull;
-      emit(c, j < n && c >= thr);
+    for (unsigned j0 = 0; j0 < n; j0 += kBatch * kHistThreads) {  // block-uniform trip count
+      u64 c[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const unsigned j = j0 + u * kHistThreads + threadIdx.x;
+        c[u] = j < n ? __ldcg(cand + j) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const unsigned j = j0 + u * kHistThreads + threadIdx.x;
+        emit(c[u], j < n && c[u] >= thr);
+      }
     }
     return;
   }
@@ -323,49 +354,76 @@ __global__ void __launch_bounds__(kHistThreads) topk_collect(TopkArgs a, u64* ou
   });
 }
 
-// SIGMOID rows: histogram of the raw logit keys (top 11 bits), then the cutoff (see the header comment).
-constexpr int kPreBits = 8;             // coarse logit bins: sign + 7 exponent bits (a factor 4 in magnitude)
+// SIGMOID rows: histogram of the raw logit keys (sign + exponent = one bin per binade), then the cutoff (see the
+// header comment).  Long rows are SAMPLED: the first kPreSample elements of every chunk (1/16 of the row), one
+// CTA per kPreGroup chunks.  The cutoff only has to be a lower bound of the k-th largest logit, and pass 0
+// verifies it by exact count (and repeats without a cutoff otherwise), so the second full read of the class
+// logits disappears.
+constexpr int kPreBits = 9;
 constexpr int kPreBins = 1 << kPreBits;
+constexpr int kPreCopies = 16;       // [bin][lane & 15]: at most 2 lanes of a warp share a word
+constexpr int kPreSample = 4096;     // sampled elements per chunk of a long row
+constexpr int kPreGroup = 4;         // chunks served by one CTA in sampled mode
+constexpr int kPreMinChunks = 8;     // rows shorter than this many chunks are histogrammed in full
 __global__ void __launch_bounds__(kHistThreads) topk_prehist(TopkArgs a) {
-  // [bin][lane]: every lane owns a bank, so the atomics of a warp never collide however concentrated
-  // the logits are (class logits pile up in 2-3 bins, which serialises a shared histogram 32-way).
-  __shared__ unsigned sh[kPreBins * 32];
+  __shared__ unsigned sh[kPreBins * kPreCopies];
   __shared__ int s_last;
   int g, img, chunk;
   if (!locate(a, blockIdx.x, g, img, chunk)) return;
   const int row = img * a.d.G + g;
   RowState* st = a.state + row;
   if (!st->active) return;
-  for (int i = threadIdx.x; i < kPreBins * 32; i += kHistThreads) sh[i] = 0;
+  const bool sampled = a.chunks[g] >= kPreMinChunks && a.chunk_elems[g] > kPreSample;
+  if (sampled && (chunk % kPreGroup) != 0) return;
+  for (int i = threadIdx.x; i < kPreBins * kPreCopies; i += kHistThreads) sh[i] = 0;
   __syncthreads();
   const long long len = a.d.row_len[g];
   const float* x = a.d.scores[g] + (size_t)img * len;
-  const long long beg = (long long)chunk * a.chunk_elems[g];
-  const long long end = beg + a.chunk_elems[g] < len ? beg + a.chunk_elems[g] : len;
-  const int lane = threadIdx.x & 31;
-  for_each_elem(x, beg, end, [&](float v, long long, bool ok) {
-    if (ok) atomicAdd(&sh[(float_to_key(v) >> (32 - kPreBits)) * 32 + lane], 1u);
-  });
+  const int lane = threadIdx.x & (kPreCopies - 1);
+  auto count = [&](float v, long long, bool ok) {
+    if (ok) atomicAdd(&sh[(float_to_key(v) >> (32 - kPreBits)) * kPreCopies + lane], 1u);
+  };
+  if (sampled) {
+    for (int c = chunk; c < chunk + kPreGroup && c < a.chunks[g]; ++c) {
+      const long long beg = (long long)c * a.chunk_elems[g];
+      const long long end = beg + kPreSample < len ? beg + kPreSample : len;
+      for_each_elem<4>(x, beg, end, count);
+    }
+  } else {
+    const long long beg = (long long)chunk * a.chunk_elems[g];
+    const long long end = beg + a.chunk_elems[g] < len ? beg + a.chunk_elems[g] : len;
+    for_each_elem(x, beg, end, count);
+  }
   __syncthreads();
   unsigned* gh = a.prehist + (size_t)row * kBins;
   for (int b = threadIdx.x; b < kPreBins; b += kHistThreads) {
     unsigned v = 0;
-#pragma unroll 8
-    for (int l = 0; l < 32; ++l) v += sh[b * 32 + ((l + b) & 31)];
+#pragma unroll
+    for (int l = 0; l < kPreCopies; ++l) v += sh[b * kPreCopies + ((l + b) & (kPreCopies - 1))];
     if (v) atomicAdd(gh + b, v);
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&st->pre_done, 1u) == (unsigned)a.chunks[g] - 1u);
+  const unsigned expect = sampled ? (unsigned)((a.chunks[g] + kPreGroup - 1) / kPreGroup) : (unsigned)a.chunks[g];
+  if (threadIdx.x == 0) s_last = (atomicAdd(&st->pre_done, 1u) == expect - 1u);
   __syncthreads();
-  if (!s_last || threadIdx.x != 0) return;
+  if (!s_last) return;
   __threadfence();
-  // thread 0 of the last CTA: walk down from the top bin until k_r elements are covered
+  // last CTA of the row: stage the merged histogram in shared memory (coalesced) so that the serial walk
+  // below does not pay one L2 round trip per bin
+  for (int b = threadIdx.x; b < kPreBins; b += kHistThreads) sh[b] = __ldcg(gh + b);
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  // thread 0 of the last CTA: walk down from the top bin until the target rank is covered.  Sampled rows aim 3x
+  // past the scaled rank so that the full row holds >= k_r elements above the cutoff with overwhelming
+  // probability (verified exactly by pass 0).
+  const unsigned target = sampled ? (unsigned)(((u64)st->k_r * 3ull * kPreSample + a.chunk_elems[g] - 1) / a.chunk_elems[g]) + 16u
+                                  : st->k_r;
   unsigned acc = 0;
   int bin = kPreBins - 1;
   for (; bin > 0; --bin) {
-    acc += __ldcg(gh + bin);
-    if (acc >= st->k_r) break;
+    acc += sh[bin];
+    if (acc >= target) break;
   }
   const float c = key_to_float((unsigned)bin << (32 - kPreBits));  // lower edge of that bucket: c <= k-th largest logit
   unsigned cut = 0u;
@@ -393,11 +451,11 @@ __global__ void topk_emit(TopkArgs a, const u64* keys, float* out_values, int32_
   if (out_indices) out_indices[(size_t)row * a.d.k + j] = idx;
 }
 
-int fill_args(const TopkDesc& d, TopkArgs& a) {
+int fill_args(const TopkDesc& d, TopkArgs& a, int coarsen = 1) {
   a.d = d;
   int cta = 0;
   for (int g = 0; g < d.G; ++g) {
-    a.chunk_elems[g] = d.row_len[g] > (1ll << 20) ? kChunkLong : kChunk;
+    a.chunk_elems[g] = (d.row_len[g] > (1ll << 20) ? kChunkLong : kChunk) * coarsen;
     a.chunks[g] = (int)((d.row_len[g] + a.chunk_elems[g] - 1) / a.chunk_elems[g]);
     if (a.chunks[g] < 1) a.chunks[g] = 1;
     a.cta_begin[g] = cta;
@@ -455,11 +513,24 @@ int topk_run(const TopkDesc& d, unsigned long long* out_keys, float* out_values,
     topk_prehist<<<ctas, kHistThreads, 0, st>>>(a);
     D2B_LAUNCH_CHECK();
   }
-  for (int p = 0; p < kPasses; ++p) {
-    topk_hist<<<ctas, kHistThreads, 0, st>>>(a, p);
-    D2B_LAUNCH_CHECK();
+  // SIGMOID rows are normally resolved from their candidate lists by one CTA per row after pass 0: the later
+  // launches use 16x coarser chunks so that the (mostly idle) grids cost ~1/16 of the CTA launches.
+  TopkArgs b = a;
+  int ctas_b = ctas;
+  if (d.transform == D2B_TOPK_SIGMOID) {
+    ctas_b = fill_args(d, b, 16);
+    b.state = a.state; b.hist = a.hist; b.prehist = a.prehist; b.cand = a.cand;
   }
-  topk_collect<<<ctas, kHistThreads, 0, st>>>(a, out_keys);
+  for (int p = 0; p < kPasses; ++p) {
+    if (p == 0) topk_hist<<<ctas, kHistThreads, 0, st>>>(a, p, 0);
+    else topk_hist<<<ctas_b, kHistThreads, 0, st>>>(b, p, 0);
+    D2B_LAUNCH_CHECK();
+    if (p == 0 && d.transform == D2B_TOPK_SIGMOID) {  // rows whose sampled cutoff failed the exact count
+      topk_hist<<<ctas_b, kHistThreads, 0, st>>>(b, 0, 1);  // rare: coarse chunks are fine
+      D2B_LAUNCH_CHECK();
+    }
+  }
+  topk_collect<<<ctas_b, kHistThreads, 0, st>>>(b, out_keys);
   D2B_LAUNCH_CHECK();
   int rc = sort_segments_desc(out_keys, rows, a.P, seg_len, st);
   if (rc != D2B_OK) return rc;

@@ -423,3 +423,11 @@ def solo_mask_stage(logits, mask_threshold=0.5):
     ss = np.empty(n, np.float32)
     lib().orc_solo_mask_stage(_p(x), C.c_int64(n), C.c_int64(hw), C.c_float(mask_threshold), _p(masks), _p(sm), _p(ss))
     return masks, sm, ss
+
+
+def sigmoid_array(x):
+    """Elementwise orc_sigmoidf over an array (same function as `sigmoidf`, without the Python loop)."""
+    x = _f32(x)
+    out = np.empty_like(x)
+    lib().orc_sigmoid_array(_p(x), C.c_int64(x.size), _p(out))
+    return out

@@ -1164,3 +1164,9 @@ ORC_API void orc_solo_mask_stage(const float* logits, int64_t n, int64_t hw, flo
     sum_masks[i] = sm; score_sums[i] = (float)ss;
   }
 }
+
+/* vectorised orc_sigmoidf (test convenience) */
+ORC_API void orc_sigmoid_array(const float* x, int64_t n, float* out) {
+#pragma omp parallel for num_threads(ORC_NT) schedule(static)
+  for (int64_t i = 0; i < n; ++i) out[i] = orc_sigmoidf(x[i]);
+}

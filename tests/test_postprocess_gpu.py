@@ -272,14 +272,25 @@ def test_matrix_nms(cuda, oracle_lib, kernel):
 
 
 # ------------------------------------------------------------------ sigmoid top-k: cutoff / candidate-list paths
-@pytest.mark.parametrize("case", ["typical", "plateau_overflow", "tied_boundary", "negative_tail", "saturated"])
+@pytest.mark.parametrize("case", ["typical", "plateau_overflow", "tied_boundary", "negative_tail", "saturated",
+                                  "sampled_long", "sample_misleads"])
 def test_sigmoid_topk_paths(cuda, oracle_lib, case):
     """The RetinaNet top-k has a logit pre-histogram cutoff and a candidate list; exercise: the fast path,
     a candidate list that overflows its capacity (falls back to re-scanning the row), index ties exactly at
-    the k-th value, cutoffs in the negative range, and the saturated regime where the shortcut is disabled."""
-    rng = np.random.default_rng({"typical": 1, "plateau_overflow": 2, "tied_boundary": 3, "negative_tail": 4, "saturated": 5}[case])
+    the k-th value, cutoffs in the negative range, and the saturated regime where the shortcut is disabled.
+    Long rows take their cutoff from a 1/16 SAMPLE of the row: `sampled_long` is that fast path, and
+    `sample_misleads` plants the large logits exactly where the sampler looks so the cutoff keeps fewer than k
+    elements and pass 0 must detect it by exact count and repeat without a cutoff."""
+    rng = np.random.default_rng({"typical": 1, "plateau_overflow": 2, "tied_boundary": 3, "negative_tail": 4, "saturated": 5,
+                                 "sampled_long": 6, "sample_misleads": 7}[case])
     n, k = 300000, 1000
-    if case == "typical":
+    if case in ("sampled_long", "sample_misleads"):
+        n = 1300000
+        x = (rng.standard_normal(n) * 1.5 - 4.6).astype(np.float32)
+        if case == "sample_misleads":
+            for c0 in range(0, n, 65536):
+                x[c0 + rng.integers(0, 4096, 12)] = 3.0 + rng.random(12).astype(np.float32)
+    elif case == "typical":
         x = (rng.standard_normal(n) * 1.5 - 4.6).astype(np.float32)
     elif case == "plateau_overflow":
         x = np.full(n, 1.0, np.float32)          # > 65536 elements above the cutoff, all tied
@@ -293,7 +304,7 @@ def test_sigmoid_topk_paths(cuda, oracle_lib, case):
     else:
         x = (rng.standard_normal(n) * 40.0).astype(np.float32)
     vals, idx, cnt = segmented_top_k([T(x[None], cuda)], k, sigmoid=True)
-    p = oracle_lib.sigmoidf(x)
+    p = oracle_lib.sigmoid_array(x)
     wv, wi = oracle_lib.top_k(p, k)
     assert cnt[0, 0].item() == k
     assert np.array_equal(idx[0, 0].cpu().numpy(), wi), case
