@@ -258,10 +258,25 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "ROIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    EMIT(json.dumps(line))
 
 
 # --------------------------------------------------------------------------- GPU arm
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank to the CPUs NVML reports as local to its GPU BEFORE any pinned host buffer is allocated,
+    so that the H2D / D2H staging memory of the end-to-end leg lives on the GPU's own NUMA node (8 ranks on a
+    two-socket host otherwise push half of their PCIe traffic through the inter-socket link)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(ClockSampler._physical_index(local_rank))
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return {"cpus_before": before, "cpus_after": len(os.sched_getaffinity(0))}
+    except Exception as e:  # restricted cpusets, missing NVML: run unbound
+        return {"error": type(e).__name__}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -274,6 +289,8 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # (N=1 stays unbound: the cpu_baseline leg of the same process must see every host core)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else {"skipped": "single rank"}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     nv.lib()
@@ -351,7 +368,7 @@ def run_gpu(args):
 
     if args.no_e2e:
         if rank == 0:
-            print(json.dumps(line))
+            EMIT(json.dumps(line))
         return
     # ---- end-to-end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
     hx = to_torch(host, dev=None, pin=True)
@@ -372,21 +389,40 @@ def run_gpu(args):
     d2h = nbytes(ho)
     line["e2e"] = {"value": rois_rank * world / (e2e_s / Ke), "unit": "ROIs/s", "ms_per_step": e2e_s / Ke * 1e3,
                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": Ke,
+                   "host_numa_binding": numa,
                    "note": "MaskRCNNPostBackbone.run_host: pinned host tensors in, pinned host tensors out (all "
                            "inputs uploaded and all four outputs downloaded every step), 2-image chunks pipelined "
-                           "over two CUDA streams"}
+                           "over three CUDA streams (upload / kernels / download)"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     if world == 1 and not args.no_cpu:
         cb, _, _ = cpu_baseline_dict(host, 2, 2, 1, "first 2 of the 16 images, 2 timed steps after 1 warm-up")
         line["cpu_baseline"] = cb
     if rank == 0:
-        print(json.dumps(line))
+        EMIT(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+def _protect_stdout():
+    """Libraries (NCCL's version banner, torchrun warnings) may write to fd 1; the contract is ONE JSON line on
+    stdout.  Point fd 1 at stderr for the duration of the run and hand back a writer for the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), "w", buffering=1)
+
+    def emit(line):
+        os.write(real, (line + "\n").encode())
+    return emit
+
+
+EMIT = print
+
+
 def main():
+    global EMIT
+    EMIT = _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
