@@ -162,8 +162,9 @@ __device__ __forceinline__ void store_out(__nv_bfloat16* p, const float (&v)[E])
 }
 
 // TIn: feature element type; TOut: output element type; GROUPS: 16-byte groups
-// each lane owns per bin (0 => runtime loop for any channel count).
-template <typename TIn, typename TOut, int GROUPS, bool ONE>
+// each lane owns per bin (0 => runtime loop for any channel count).  S1: 1 / 2 = unrolled fast path for that
+// many samples per bin axis, 0 = generic loop.
+template <typename TIn, typename TOut, int GROUPS, int S1>
 __global__ void __launch_bounds__(kThreads) roi_align_kernel(const RoiAlignArgs a) {
   constexpr int E = Vec<TIn>::kElems;
   __shared__ Tap ty[kMaxSamples];
@@ -216,50 +217,62 @@ __global__ void __launch_bounds__(kThreads) roi_align_kernel(const RoiAlignArgs 
   const int bin_begin = blockIdx.y * kBinsPerCta;
   const int bin_end = min(bin_begin + kBinsPerCta, a.oh * a.ow);
 
-  if (ONE && GROUPS > 0) {
-    // sampling_ratio 0/1 (the reference default): one bilinear sample per bin, fully unrolled channel
-    // groups, corner addresses formed once per bin from the precomputed element offsets.
+  if constexpr (S1 > 0 && GROUPS > 0) {
+    // sampling_ratio 0/1 (the reference default; S1 == 1) and 2 (the keypoint head, defaults.py:513; S1 == 2):
+    // fully unrolled channel groups and samples, corner addresses formed once per sample from the precomputed
+    // element offsets, 8 x 16-byte corner loads in flight per lane.  S1 == 2 accumulates the 4 samples in the
+    // reference's row-major order and divides by 4 (roi_align.py:59-65 avg_pool).
     for (int bin = bin_begin + warp; bin < bin_end; bin += kWarps) {
       const int oy = bin / a.ow, ox = bin - oy * a.ow;
       TOut* o = obase + (size_t)bin * C + lane * E;
-      const Tap y = ty[oy];
-      const Tap x = tx[ox];
-      if (y.valid && x.valid && img >= 0) {
-        const TIn* p00 = base + (y.i0 + x.i0) + lane * E;
-        const TIn* p01 = base + (y.i0 + x.i1) + lane * E;
-        const TIn* p10 = base + (y.i1 + x.i0) + lane * E;
-        const TIn* p11 = base + (y.i1 + x.i1) + lane * E;
-        constexpr int G = GROUPS > 0 ? GROUPS : 1;
-        Vec<TIn> tl[G], tr[G], bl[G], br[G];
+      constexpr int G = GROUPS > 0 ? GROUPS : 1;
+      float acc[G][E];
 #pragma unroll
-        for (int j = 0; j < GROUPS; ++j) {
-          tl[j] = Vec<TIn>::load(p00 + j * 32 * E);
-          tr[j] = Vec<TIn>::load(p01 + j * 32 * E);
-          bl[j] = Vec<TIn>::load(p10 + j * 32 * E);
-          br[j] = Vec<TIn>::load(p11 + j * 32 * E);
+      for (int j = 0; j < G; ++j)
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[j][e] = 0.0f;
+#pragma unroll
+      for (int dy = 0; dy < S1; ++dy) {
+        const Tap y = ty[oy * S1 + dy];
+#pragma unroll
+        for (int dx = 0; dx < S1; ++dx) {
+          const Tap x = tx[ox * S1 + dx];
+          if (y.valid && x.valid && img >= 0) {  // warp-uniform
+            const TIn* p00 = base + (y.i0 + x.i0) + lane * E;
+            const TIn* p01 = base + (y.i0 + x.i1) + lane * E;
+            const TIn* p10 = base + (y.i1 + x.i0) + lane * E;
+            const TIn* p11 = base + (y.i1 + x.i1) + lane * E;
+            Vec<TIn> tl[G], tr[G], bl[G], br[G];
+#pragma unroll
+            for (int j = 0; j < GROUPS; ++j) {
+              tl[j] = Vec<TIn>::load(p00 + j * 32 * E);
+              tr[j] = Vec<TIn>::load(p01 + j * 32 * E);
+              bl[j] = Vec<TIn>::load(p10 + j * 32 * E);
+              br[j] = Vec<TIn>::load(p11 + j * 32 * E);
+            }
+#pragma unroll
+            for (int j = 0; j < GROUPS; ++j) {
+#pragma unroll
+              for (int e = 0; e < E; ++e) {
+                float t = tr[j].v[e] - tl[j].v[e]; t = t * x.w; t = tl[j].v[e] + t;
+                float bb = br[j].v[e] - bl[j].v[e]; bb = bb * x.w; bb = bl[j].v[e] + bb;
+                float r = bb - t; r = r * y.w; r = t + r;
+                acc[j][e] = (S1 == 1) ? r : acc[j][e] + r;
+              }
+            }
+          }  // an extrapolated sample contributes 0 (acc + 0.0f == acc)
         }
+      }
 #pragma unroll
-        for (int j = 0; j < GROUPS; ++j) {
-          float val[E];
+      for (int j = 0; j < GROUPS; ++j) {
+        if (S1 > 1) {
 #pragma unroll
-          for (int e = 0; e < E; ++e) {
-            float t = tr[j].v[e] - tl[j].v[e]; t = t * x.w; t = tl[j].v[e] + t;
-            float bb = br[j].v[e] - bl[j].v[e]; bb = bb * x.w; bb = bl[j].v[e] + bb;
-            float r = bb - t; r = r * y.w; r = t + r;
-            val[e] = r;
-          }
-          store_out<E>(o + j * 32 * E, val);
+          for (int e = 0; e < E; ++e) acc[j][e] = acc[j][e] / cnt;
         }
-      } else {
-        float val[E];
-#pragma unroll
-        for (int e = 0; e < E; ++e) val[e] = 0.0f;
-#pragma unroll
-        for (int j = 0; j < GROUPS; ++j) store_out<E>(o + j * 32 * E, val);
+        store_out<E>(o + j * 32 * E, acc[j]);
       }
     }
-    return;
-  }
+  } else {
   for (int bin = bin_begin + warp; bin < bin_end; bin += kWarps) {
     const int oy = bin / a.ow, ox = bin - oy * a.ow;
     TOut* o = obase + (size_t)bin * C;
@@ -312,6 +325,7 @@ __global__ void __launch_bounds__(kThreads) roi_align_kernel(const RoiAlignArgs 
     } else {
       for (int g = lane; g < groups_total; g += 32) do_group(g);
     }
+  }
   }
 }
 
@@ -406,12 +420,14 @@ int launch(const RoiAlignArgs& a, cudaStream_t st) {
   constexpr int E = Vec<TIn>::kElems;
   const dim3 grid((unsigned)a.M, (unsigned)((a.oh * a.ow + kBinsPerCta - 1) / kBinsPerCta)), block(kThreads);
   const int g = a.C / E;
-  const bool one = a.sr <= 1;
-  if (g == 32 && one) roi_align_kernel<TIn, TOut, 1, true><<<grid, block, 0, st>>>(a);
-  else if (g == 64 && one) roi_align_kernel<TIn, TOut, 2, true><<<grid, block, 0, st>>>(a);
-  else if (g == 32) roi_align_kernel<TIn, TOut, 1, false><<<grid, block, 0, st>>>(a);
-  else if (g == 64) roi_align_kernel<TIn, TOut, 2, false><<<grid, block, 0, st>>>(a);
-  else roi_align_kernel<TIn, TOut, 0, false><<<grid, block, 0, st>>>(a);
+  const int s1 = a.sr > 0 ? a.sr : 1;
+  if (g == 32 && s1 == 1) roi_align_kernel<TIn, TOut, 1, 1><<<grid, block, 0, st>>>(a);
+  else if (g == 64 && s1 == 1) roi_align_kernel<TIn, TOut, 2, 1><<<grid, block, 0, st>>>(a);
+  else if (g == 32 && s1 == 2) roi_align_kernel<TIn, TOut, 1, 2><<<grid, block, 0, st>>>(a);
+  else if (g == 64 && s1 == 2) roi_align_kernel<TIn, TOut, 2, 2><<<grid, block, 0, st>>>(a);
+  else if (g == 32) roi_align_kernel<TIn, TOut, 1, 0><<<grid, block, 0, st>>>(a);
+  else if (g == 64) roi_align_kernel<TIn, TOut, 2, 0><<<grid, block, 0, st>>>(a);
+  else roi_align_kernel<TIn, TOut, 0, 0><<<grid, block, 0, st>>>(a);
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }

@@ -93,6 +93,15 @@ if "5" in which:
         alg = M * 49 * C * 4 + min(fbytes, M * 49 * 4 * C * 4) + M * 24
         print(json.dumps({"config": 5, "case": f"ROIAlign 7x7 sweep M={M}", "ms": ms, "rois_per_s": M / ms * 1e3,
                           "alg_GBps": alg / ms / 1e6, "frac_hbm": alg / ms / 1e6 / HBM}))
+    # sampling_ratio = 2 (the keypoint head's setting, defaults.py:513): 4 samples per bin, same algorithmic bytes
+    for (osz, M) in ((7, 16384), (14, 1600)):
+        pooler2 = ROIPooler(osz, [1 / 4., 1 / 8., 1 / 16., 1 / 32.], 2, "ROIAlignV2")
+        boxes, idx = syn.rois(N, M // N, seed=1)
+        inst = SparseBoxList(torch.from_numpy(idx).to(dev), BoxList(torch.from_numpy(boxes).to(dev)), (N, M // N))
+        ms = timeit(lambda: pooler2(feats, inst))
+        alg = M * osz * osz * C * 4 + min(fbytes, M * osz * osz * 16 * C * 4) + M * 24
+        print(json.dumps({"config": 5, "case": f"ROIAlign {osz}x{osz} sampling_ratio=2 M={M}", "ms": ms,
+                          "rois_per_s": M / ms * 1e3, "alg_GBps": alg / ms / 1e6, "frac_hbm": alg / ms / 1e6 / HBM}))
     rng = np.random.default_rng(5)
     for n in (256, 1024, 4096, 16384, 65536):
         cy, cx = rng.uniform(0, 800, n), rng.uniform(0, 1333, n)
