@@ -291,3 +291,155 @@ REGISTER_KERNEL_BUILDER(Name("D2MatrixNms").Device(tf::DEVICE_GPU), D2MatrixNmsO
 
 // D2FastRcnnPostprocess and D2RetinanetPostprocess follow the same pattern over
 // d2b_fast_rcnn_postprocess / d2b_retinanet_postprocess (params structs in d2b200.h).
+
+// ------------------------------------------------------------------ D2RoiAlignMultilevelGrad
+// Gradient of D2RoiAlignMultilevel w.r.t. the feature maps (boxes carry none: functional.py:120
+// stop_gradient).  Registered from Python with @tf.RegisterGradient.
+REGISTER_OP("D2RoiAlignMultilevelGrad")
+    .Input("grad_pooled: float")   // [M, output_h, output_w, C]
+    .Input("features: L * float")  // only their shapes are read
+    .Input("boxes: float")
+    .Input("batch_idx: int64")
+    .Attr("L: int >= 1")
+    .Attr("sampling_ratio: int = 0")
+    .Attr("aligned: bool = true")
+    .Attr("scales: list(float)")
+    .Attr("canonical_box_size: int = 224")
+    .Attr("canonical_level: int = 4")
+    .Output("grad_features: L * float")
+    .SetShapeFn([](InferenceContext* c) {
+      int L;
+      TF_RETURN_IF_ERROR(c->GetAttr("L", &L));
+      for (int l = 0; l < L; ++l) c->set_output(l, c->input(1 + l));
+      return tf::Status::OK();
+    });
+
+class D2RoiAlignMultilevelGradOp : public tf::OpKernel {
+ public:
+  explicit D2RoiAlignMultilevelGradOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("L", &L_));
+    OP_REQUIRES_OK(c, c->GetAttr("sampling_ratio", &sr_));
+    OP_REQUIRES_OK(c, c->GetAttr("aligned", &aligned_));
+    OP_REQUIRES_OK(c, c->GetAttr("scales", &scales_));
+    OP_REQUIRES_OK(c, c->GetAttr("canonical_box_size", &cbs_));
+    OP_REQUIRES_OK(c, c->GetAttr("canonical_level", &cl_));
+    OP_REQUIRES(c, static_cast<int>(scales_.size()) == L_ && L_ <= D2B_MAX_LEVELS,
+                tf::errors::InvalidArgument("len(scales) must equal L <= ", D2B_MAX_LEVELS));
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    const tf::Tensor& g = ctx->input(0);
+    const tf::Tensor& boxes = ctx->input(1 + L_);
+    const tf::Tensor& bidx = ctx->input(2 + L_);
+    OP_REQUIRES(ctx, g.dims() == 4, tf::errors::InvalidArgument("grad_pooled must be [M,oh,ow,C]"));
+    d2b_roi_align_backward_params p = {};
+    d2b_roi_align_params& f = p.fwd;
+    for (int l = 0; l < L_; ++l) {
+      const tf::Tensor& x = ctx->input(1 + l);
+      tf::Tensor* gx = nullptr;
+      OP_REQUIRES_OK(ctx, ctx->allocate_output(l, x.shape(), &gx));
+      // the kernel accumulates: start from zero
+      cudaMemsetAsync(gx->flat<float>().data(), 0, sizeof(float) * gx->NumElements(), StreamOf(ctx));
+      p.grad_features[l] = gx->flat<float>().data();
+      f.height[l] = x.dim_size(1);
+      f.width[l] = x.dim_size(2);
+      f.scale[l] = scales_[l];
+    }
+    f.num_levels = L_;
+    f.num_images = ctx->input(1).dim_size(0);
+    f.channels = g.dim_size(3);
+    f.feature_dtype = f.out_dtype = D2B_DTYPE_F32;
+    f.boxes = boxes.flat<float>().data();
+    f.batch_idx = bidx.flat<tf::int64>().data();
+    f.batch_idx_is_int64 = 1;
+    f.batch_idx_stride = 1;
+    f.num_rois = boxes.dim_size(0);
+    f.output_h = g.dim_size(1); f.output_w = g.dim_size(2);
+    f.sampling_ratio = sr_; f.aligned = aligned_; f.pad_border = 1;
+    f.min_level = static_cast<int>(std::lround(-std::log2(scales_[0])));
+    f.canonical_box_size = cbs_; f.canonical_level = cl_;
+    p.grad_out = g.flat<float>().data();
+    RunOp(ctx, p, d2b_roi_align_backward_workspace_bytes, d2b_roi_align_backward);
+  }
+
+ private:
+  int L_, sr_, cbs_, cl_;
+  bool aligned_;
+  std::vector<float> scales_;
+};
+REGISTER_KERNEL_BUILDER(Name("D2RoiAlignMultilevelGrad").Device(tf::DEVICE_GPU), D2RoiAlignMultilevelGradOp);
+
+// ------------------------------------------------------------------ D2LabelBoxes
+// Replaces pairwise_iou + Matcher (+ inside_window + get_deltas) of RPNOutputs._get_ground_truth
+// (lib/modeling/proposal_generator/rpn_outputs.py:245-304) for the whole batch.
+REGISTER_OP("D2LabelBoxes")
+    .Input("anchors: float")        // [P, 4] shared by the images
+    .Input("gt_boxes: float")       // [N, G, 4]
+    .Input("gt_valid: bool")        // [N, G]
+    .Input("gt_crowd: bool")        // [N, G]
+    .Input("image_shapes: int32")   // [N, 2]
+    .Attr("thresholds: list(float)")
+    .Attr("labels: list(int)")
+    .Attr("allow_low_quality_matches: bool = false")
+    .Attr("boundary_threshold: float = -1.0")
+    .Attr("weights: list(float) = [1.0, 1.0, 1.0, 1.0]")
+    .Output("matches: int64")       // [N, P]
+    .Output("match_labels: int64")  // [N, P]  == gt_objectness_logits
+    .Output("gt_deltas: float")     // [N, P, 4]
+    .SetShapeFn([](InferenceContext* c) {
+      auto n = c->Dim(c->input(1), 0), pdim = c->Dim(c->input(0), 0);
+      c->set_output(0, c->MakeShape({n, pdim}));
+      c->set_output(1, c->MakeShape({n, pdim}));
+      c->set_output(2, c->MakeShape({n, pdim, 4}));
+      return tf::Status::OK();
+    });
+
+class D2LabelBoxesOp : public tf::OpKernel {
+ public:
+  explicit D2LabelBoxesOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("thresholds", &thr_));
+    OP_REQUIRES_OK(c, c->GetAttr("labels", &labels_));
+    OP_REQUIRES_OK(c, c->GetAttr("allow_low_quality_matches", &lq_));
+    OP_REQUIRES_OK(c, c->GetAttr("boundary_threshold", &boundary_));
+    OP_REQUIRES_OK(c, c->GetAttr("weights", &w_));
+    OP_REQUIRES(c, thr_.size() >= 1 && thr_.size() <= D2B_MATCH_MAX_THRESHOLDS && labels_.size() == thr_.size() + 1 &&
+                       w_.size() == 4,
+                tf::errors::InvalidArgument("bad thresholds / labels / weights"));
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    const tf::Tensor& anchors = ctx->input(0);
+    const tf::Tensor& gt = ctx->input(1);
+    OP_REQUIRES(ctx, anchors.dims() == 2 && gt.dims() == 3, tf::errors::InvalidArgument("anchors [P,4], gt_boxes [N,G,4]"));
+    d2b_label_boxes_params p = {};
+    p.pred_boxes = anchors.flat<float>().data();
+    p.pred_shared = 1;
+    p.num_images = gt.dim_size(0);
+    p.num_preds = anchors.dim_size(0);
+    p.gt_boxes = gt.flat<float>().data();
+    p.gt_valid = reinterpret_cast<const uint8_t*>(ctx->input(2).flat<bool>().data());
+    p.gt_crowd = reinterpret_cast<const uint8_t*>(ctx->input(3).flat<bool>().data());
+    p.max_gt = gt.dim_size(1);
+    p.num_thresholds = static_cast<int>(thr_.size());
+    for (size_t i = 0; i < thr_.size(); ++i) p.thresholds[i] = thr_[i];
+    for (size_t i = 0; i < labels_.size(); ++i) p.labels[i] = labels_[i];
+    p.allow_low_quality_matches = lq_;
+    p.boundary_threshold = boundary_;
+    p.image_shapes = ctx->input(4).flat<tf::int32>().data();
+    p.compute_deltas = 1;
+    for (int i = 0; i < 4; ++i) p.weights[i] = w_[i];
+    tf::Tensor *m = nullptr, *l = nullptr, *d = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({p.num_images, p.num_preds}), &m));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({p.num_images, p.num_preds}), &l));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, tf::TensorShape({p.num_images, p.num_preds, 4}), &d));
+    p.out_matches = reinterpret_cast<int64_t*>(m->flat<tf::int64>().data());
+    p.out_labels = reinterpret_cast<int64_t*>(l->flat<tf::int64>().data());
+    p.out_deltas = d->flat<float>().data();
+    RunOp(ctx, p, d2b_label_boxes_workspace_bytes, d2b_label_boxes);
+  }
+
+ private:
+  std::vector<float> thr_, w_;
+  std::vector<int> labels_;
+  bool lq_;
+  float boundary_;
+};
+REGISTER_KERNEL_BUILDER(Name("D2LabelBoxes").Device(tf::DEVICE_GPU), D2LabelBoxesOp);
