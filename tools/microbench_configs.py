@@ -2,6 +2,8 @@
   config 3  RetinaNet R50-FPN inference post-processing, batch 32
   config 4  SOLOv2 Matrix-NMS, 500 masks at 200x336, batch 16
   config 5  ROIAlign / NMS sweep, 256 .. 65536 ROIs / boxes
+  2         SURVEY.md 8(d) stage numbers at config-2 sizes: NMS-only (80 segments x 2000 boxes) and the full proposal
+            stage, gaussian / clustered / ties inputs, cold (L2 flushed) and warm, CPU oracle with 1 and all threads
   train     SURVEY.md 8(f) #3: fused RPN label assignment (16 x 268 K anchors), ROIPooler backward (16,000 ROIs)
 Prints one JSON line per case (CUDA events, median of `--iters`, 256 MB L2 flush between iterations)."""
 import argparse
@@ -27,13 +29,14 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 HBM = 6525.2
 
 
-def timeit(fn, iters=args.iters, warm=3):
+def timeit(fn, iters=args.iters, warm=3, cold=True):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
-        flush.zero_()
+        if cold:
+            flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
@@ -45,6 +48,62 @@ def timeit(fn, iters=args.iters, warm=3):
 
 which = set(args.which.split(","))
 g = torch.Generator(device=dev).manual_seed(0)
+
+if "2" in which:
+    import time
+    import oracle
+    from detectron2_tensorflow_b200.modeling import find_top_rpn_proposals
+    from detectron2_tensorflow_b200.structures import ImageList
+    N = 16
+    anchors = syn.rpn_anchors()
+    shapes = syn.image_shapes(N)
+    for variant in ("gaussian", "clustered", "ties"):
+        logits, deltas = syn.rpn_inputs(N, seed={"gaussian": 2, "clustered": 3, "ties": 4}[variant], variant=variant,
+                                        anchors=anchors)
+        props = [oracle.rpn_predict_proposals(d, a) for d, a in zip(deltas, anchors)]
+        tp = [torch.from_numpy(x).to(dev) for x in props]
+        tl = [torch.from_numpy(x).to(dev) for x in logits]
+        images = ImageList(None, torch.from_numpy(shapes).to(dev))
+        run = lambda: find_top_rpn_proposals(tp, tl, images, 0.7, 2000, 1000, 0.0)
+        cold, warm = timeit(run, iters=20, warm=5), timeit(run, iters=20, warm=5, cold=False)
+        res = run()
+        nms_in = N * sum(min(2000, a.shape[0]) for a in anchors)
+        # NMS-only on exactly the boxes that enter NMS: per (image, level) top-2000, clipped (oracle prepares them)
+        segs_b, segs_s = [], []
+        for l in range(len(anchors)):
+            for n in range(N):
+                k = min(2000, logits[l].shape[1])
+                v, i = oracle.top_k(logits[l][n], k)
+                b = props[l][n][i].copy()
+                b[:, 0::2] = np.clip(b[:, 0::2], 0, 800.0)
+                b[:, 1::2] = np.clip(b[:, 1::2], 0, 1333.0)
+                pad = 2000 - k
+                segs_b.append(np.concatenate([b, np.zeros((pad, 4), np.float32)]))
+                segs_s.append(np.concatenate([v, np.full(pad, -np.inf, np.float32)]))
+        sb, ss = np.stack(segs_b), np.stack(segs_s)
+        tb, ts_ = torch.from_numpy(sb).to(dev), torch.from_numpy(ss).to(dev)
+        nrun = lambda: batch_nms(tb, ts_, 1000, axis=1, iou_threshold=0.7)
+        ncold, nwarm = timeit(nrun, iters=20, warm=5), timeit(nrun, iters=20, warm=5, cold=False)
+        kept = int(nrun()[1].sum())
+        cpu = {}
+        for thr in (1, oracle.max_threads()):
+            oracle.set_num_threads(thr)
+            t0 = time.perf_counter()
+            oracle.batch_nms(sb[:16], ss[:16], 1000, 0.7)  # 16 of the 80 segments (bounded sample)
+            t_nms = (time.perf_counter() - t0) * 5
+            t0 = time.perf_counter()
+            oracle.find_top_rpn_proposals([x[:2] for x in props], [x[:2] for x in logits], shapes[:2], 0.7, 2000, 1000, 0.0)
+            t_stage = (time.perf_counter() - t0) * 8  # 2 of the 16 images
+            cpu[f"threads_{thr}"] = {"nms_only_boxes_per_s": nms_in / t_nms, "proposal_stage_boxes_per_s": nms_in / t_stage}
+        oracle.set_num_threads(0)
+        print(json.dumps({"config": 2, "case": f"RPN proposal stage, {variant} inputs, N=16 (80 segments, {nms_in} boxes enter NMS)",
+                          "proposal_stage_ms_cold": cold, "proposal_stage_ms_warm": warm,
+                          "proposal_stage_boxes_per_s": nms_in / cold * 1e3,
+                          "nms_only_ms_cold": ncold, "nms_only_ms_warm": nwarm, "nms_only_boxes_per_s": nms_in / ncold * 1e3,
+                          "kept_by_nms": kept, "valid_proposals": int(res.get_field("is_valid").sum()),
+                          "cpu_oracle": cpu,
+                          "speedup_nms_only_vs_all_threads": (nms_in / ncold * 1e3) /
+                          cpu[f"threads_{oracle.max_threads()}"]["nms_only_boxes_per_s"]}))
 
 if "3" in which:
     N, K = 32, 80
