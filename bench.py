@@ -306,29 +306,44 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing
+    # ---- device-resident timing, (1) eager single stream with per-stage CUDA events: stage breakdown + roofline
     for _ in range(W):
         out = hp(x)
     barrier()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
-    sampler = ClockSampler(local)
-    sampler.start()
-    l0 = nv.kernel_launch_count()
+    Ks = max(3, min(K, 30))
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(Ks)]
     barrier()
-    t0 = time.perf_counter()
-    for s in range(K):
+    for s in range(Ks):
         out = hp(x, evs[s])
     barrier()
-    wall = time.perf_counter() - t0
-    launches = nv.kernel_launch_count() - l0
-    clocks = sampler.summary()
-    dev_ms = evs[0][0].elapsed_time(evs[-1][4])  # first event of step 0 -> last event of step K-1
+    eager_ms = evs[0][0].elapsed_time(evs[-1][4]) / Ks
     stage = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in evs])  # rpn, boxpool, frcnn, maskpool
     st = stage.mean(0)
+
+    # ---- (2) the timed region: the same step captured as ONE CUDA graph, 4 image blocks on concurrent streams
+    # (images are independent; latency-bound proposal / post-processing kernels overlap the HBM-bound ROIAlign)
+    gstep = hp.capture(x, chunks=args.chunks)
+    for _ in range(W):
+        gstep.replay()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for s in range(K):
+        gstep.replay()
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = gstep.kernels_per_replay * K
+    clocks = sampler.summary()
+    dev_ms = e0.elapsed_time(e1)
     if world > 1:
-        t = torch.tensor([dev_ms, wall * 1e3], device=dev, dtype=torch.float64)
+        t = torch.tensor([dev_ms, wall * 1e3, eager_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, wall_ms = float(t[0]), float(t[1])
+        dev_ms, wall_ms, eager_ms = float(t[0]), float(t[1]), float(t[2])
     else:
         wall_ms = wall * 1e3
     ms_per_step = dev_ms / K  # CUDA events on the launching stream, max over ranks
@@ -353,6 +368,11 @@ def run_gpu(args):
                    "cache": "inputs larger than L2 (1.46 GB features + 0.8 GB outputs per step vs 126 MB L2)",
                    "sharding": "images by batch index, no collective"},
         "wall_ms_per_step": wall_ms / K,
+        "execution": {"timed_region": f"one CUDA graph per step, {args.chunks} image blocks on concurrent streams",
+                      "kernels_per_step": gstep.kernels_per_replay,
+                      "eager_single_stream_ms_per_step": eager_ms,
+                      "note": "stages_ms and roofline come from the eager single-stream run (CUDA events between "
+                              "stages on the launching stream); value / ms_per_step from the graph replays"},
         "stages_ms": {"rpn_proposals": st[0], "box_roi_align_7x7": st[1], "fast_rcnn_post": st[2],
                       "mask_roi_align_14x14": st[3]},
         "roi_align": {"rois_per_s": rois_rank * world / ((st[1] + st[3]) * 1e-3), "unit": "ROIs/s"},
@@ -428,6 +448,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="d2b200", choices=["d2b200", "reference"])
+    ap.add_argument("--chunks", type=int, default=4, help="image blocks run concurrently inside the graphed step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()

@@ -58,3 +58,28 @@ def test_engine_matches_oracle_and_host_path(cuda, oracle_lib):
         for k, v in out.items():
             assert ho[k].is_pinned() and not ho[k].is_cuda
             assert torch.equal(ho[k], v.cpu()), (chunk, k)
+
+
+@pytest.mark.parametrize("chunks", [1, 2, 3, 5])
+def test_graphed_chunked_step_matches_eager(cuda, chunks):
+    """`capture()`: the step as one CUDA graph, image blocks on concurrent streams.  Replays must reproduce the
+    eager single-stream outputs bit for bit, also after the static inputs are refilled in place."""
+    N, R, D, K, C = 5, 48, 12, 6, 16
+    eng = MaskRCNNPostBackbone(rois_per_image=R, dets_per_image=D, pre_nms_topk=150)
+    x = _t(_inputs(N, R, K, C, seed=1), cuda)
+    g = eng.capture(x, chunks=chunks)
+    assert g.kernels_per_replay > 0 and len(g.outputs) == min(chunks, N)
+    for seed in (1, 2):
+        fresh = _t(_inputs(N, R, K, C, seed=seed), cuda)
+        for k, v in fresh.items():  # refill the static input tensors in place
+            if isinstance(v, list):
+                for dst, src in zip(x[k], v):
+                    dst.copy_(src)
+            else:
+                x[k].copy_(v)
+        g.replay()
+        got = g.gathered()
+        want = eng.flatten_outputs(eng(fresh))
+        torch.cuda.synchronize()
+        for k, v in want.items():
+            assert torch.equal(got[k], v), (chunks, seed, k)
