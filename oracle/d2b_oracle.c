@@ -777,17 +777,12 @@ ORC_API void orc_reframe_box_masks(const float* box_masks, const float* boxes, i
     nb[2] = (1.0f - ymin) / (ymax - ymin);
     nb[3] = (1.0f - xmin) / (xmax - xmin);
     float* tmp = (float*)malloc(sizeof(float) * (size_t)H * W);
-    memset(tmp, 0, sizeof(float) * (size_t)H * W);
-    const int32_t zero = 0;
-    /* one box against its own mask: image = mask b as a [1, mh, mw, 1] tensor */
-    const int saved = g_threads;
-    (void)saved;
-    {
+    memset(tmp, 0, sizeof(float) * (size_t)H * W); /* extrapolation_value = 0 */
+    { /* tf.image.crop_and_resize of box b against its own mask (a [1, mh, mw, 1] image), crop = (H, W) */
       const float* image = box_masks + (size_t)b * mh * mw;
       const float y1 = nb[0], x1 = nb[1], y2 = nb[2], x2 = nb[3];
       const float hs = (H > 1) ? (y2 - y1) * (float)(mh - 1) / (float)(H - 1) : 0.0f;
       const float ws = (W > 1) ? (x2 - x1) * (float)(mw - 1) / (float)(W - 1) : 0.0f;
-      (void)zero;
       for (int y = 0; y < H; ++y) {
         const float in_y = (H > 1) ? y1 * (float)(mh - 1) + (float)y * hs : 0.5f * (y1 + y2) * (float)(mh - 1);
         if (!(in_y >= 0.0f && in_y <= (float)(mh - 1))) continue;
