@@ -149,6 +149,14 @@ class SoloMaskEncodeParams(C.Structure):
                 ("mask_threshold", _f32), ("packed_masks", _vp), ("sum_masks", _vp), ("score_sums", _vp)]
 
 
+class SoloPostprocessParams(C.Structure):
+    _fields_ = [("mask_logits", _vp), ("scores", _vp), ("classes", _vp), ("strides", _vp), ("counts", _vp),
+                ("batch", _i32), ("n", _i32), ("hw", _i64), ("mask_threshold", _f32), ("pre_nms_topk", _i32),
+                ("kernel", _i32), ("sigma", _f32), ("update_score_threshold", _f32), ("max_detections", _i32),
+                ("out_masks", _vp), ("out_packed_masks", _vp), ("out_classes", _vp), ("out_scores", _vp),
+                ("out_valid", _vp), ("out_num", _vp)]
+
+
 class RoiAlignBackwardParams(C.Structure):
     _fields_ = [("fwd", RoiAlignParams), ("grad_out", _vp), ("grad_features", _vp * MAX_LEVELS)]
 
@@ -174,6 +182,7 @@ OPS = {
     "yolo_postprocess": YoloParams,
     "point_nms": PointNmsParams,
     "solo_mask_encode": SoloMaskEncodeParams,
+    "solo_postprocess": SoloPostprocessParams,
 }
 EXPORTS = ["d2b_version", "d2b_status_string", "d2b_last_error", "d2b_kernel_launch_count"] + \
           [f"d2b_{op}{sfx}" for op in OPS for sfx in ("", "_workspace_bytes")]

@@ -119,6 +119,169 @@ __global__ void point_nms_scalar_kernel(const float* x, int H, int W, int C, flo
 }  // namespace
 }  // namespace d2b
 
+namespace d2b {
+namespace {
+// ------------------------------------------------------------------ SOLOv2 inference tail (solo_v2.py:507-558)
+__device__ __forceinline__ u64 solo_key(float score, unsigned idx) {
+  return ((u64)float_to_key(score) << 32) | (u64)(0xffffffffu - idx);
+}
+// :520-533  keep = sum_masks > strides; pred_scores *= score_sums / sum_masks; candidates become sort keys
+__global__ void solo_score_kernel(const float* scores, const float* strides, const float* sum_masks,
+                                  const float* score_sums, const int32_t* counts, int n, int P, u64* keys,
+                                  float* rescored, int32_t* nvalid) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cnt = counts ? min(counts[b], n) : n;
+  bool ok = false;
+  if (i < P) {
+    u64 key = 0ull;
+    if (i < cnt) {
+      const size_t o = (size_t)b * n + i;
+      const float sm = sum_masks[o];
+      if (sm > strides[o]) {
+        float ms = score_sums[o] / sm;
+        const float s = scores[o] * ms;
+        rescored[o] = s;
+        key = solo_key(s, (unsigned)i);
+        ok = true;
+      }
+    }
+    keys[(size_t)b * P + i] = key;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(nvalid + b, __popc(m));
+}
+// :536-540  the top-k rows (already sorted) gathered into a dense [kcap] block per image
+__global__ void solo_gather_kernel(const u64* keys, int P, const int32_t* nvalid, int pre, int n, int kcap, int Wd,
+                                   const u64* packed, const float* sum_masks, const long long* classes,
+                                   const float* rescored, u64* packed2, float* sum2, long long* cls2, float* sc2,
+                                   int32_t* kcount) {
+  const int b = blockIdx.y, r = blockIdx.x;
+  const int kc = min(min(pre, nvalid[b]), kcap);
+  if (r == 0 && threadIdx.x == 0) kcount[b] = kc;
+  if (r >= kc) return;
+  const unsigned idx = 0xffffffffu - (unsigned)keys[(size_t)b * P + r];
+  const u64* src = packed + ((size_t)b * n + idx) * Wd;
+  u64* dst = packed2 + ((size_t)b * kcap + r) * Wd;
+  for (int w = threadIdx.x; w < Wd; w += blockDim.x) dst[w] = src[w];
+  if (threadIdx.x == 0) {
+    const size_t o = (size_t)b * n + idx, q = (size_t)b * kcap + r;
+    sum2[q] = sum_masks[o];
+    cls2[q] = classes[o];
+    sc2[q] = rescored[o];
+  }
+}
+// :549-556  keep = updated > update_score_threshold (order kept), pad / clip to max_det.  One CTA per image.
+__global__ void __launch_bounds__(256) solo_emit_kernel(const float* upd, const long long* cls2, const int32_t* kcount,
+                                                        int kcap, float thr, int D, long long* out_classes,
+                                                        float* out_scores, uint8_t* out_valid, int32_t* src_row,
+                                                        int32_t* out_num) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const int b = blockIdx.x;
+  const int kc = kcount[b];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int r0 = 0; r0 < kc; r0 += 256) {
+    const int r = r0 + threadIdx.x;
+    const bool keep = r < kc && upd[(size_t)b * kcap + r] > thr;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { before += (w < warp) ? s_warp[w] : 0; total += s_warp[w]; }
+    const int slot = s_base + before + __popc(m & ((1u << lane) - 1u));
+    if (keep && slot < D) {
+      const size_t o = (size_t)b * D + slot;
+      out_classes[o] = cls2[(size_t)b * kcap + r];
+      out_scores[o] = upd[(size_t)b * kcap + r];
+      out_valid[o] = 1;
+      src_row[o] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += total;
+    __syncthreads();
+  }
+  const int nv = min(s_base, D);
+  for (int q = nv + threadIdx.x; q < D; q += 256) {
+    const size_t o = (size_t)b * D + q;
+    out_classes[o] = 0; out_scores[o] = 0.0f; out_valid[o] = 0; src_row[o] = -1;
+  }
+  if (threadIdx.x == 0 && out_num) out_num[b] = nv;
+}
+// masks of the kept detections: packed copy and / or fp32 0/1 expansion (zeros past the valid count)
+__global__ void __launch_bounds__(256) solo_unpack_kernel(const u64* packed2, const int32_t* src_row, int kcap, int Wd,
+                                                          long long hw, int D, u64* out_packed, float* out_masks) {
+  const int b = blockIdx.z, q = blockIdx.y;
+  const int r = src_row[(size_t)b * D + q];
+  const u64* src = r >= 0 ? packed2 + ((size_t)b * kcap + r) * Wd : nullptr;
+  const int w = blockIdx.x * 256 + threadIdx.x;  // one word (64 pixels) per thread
+  if (w >= Wd) return;
+  const u64 bits = src ? src[w] : 0ull;
+  if (out_packed) out_packed[((size_t)b * D + q) * Wd + w] = bits;
+  if (out_masks) {
+    float* o = out_masks + ((size_t)b * D + q) * hw + (long long)w * 64;
+    const long long left = hw - (long long)w * 64;
+    if (left >= 64 && (hw & 3) == 0) {
+#pragma unroll
+      for (int v = 0; v < 16; ++v)
+        __stcs(reinterpret_cast<float4*>(o) + v,
+               make_float4((bits >> (4 * v)) & 1 ? 1.f : 0.f, (bits >> (4 * v + 1)) & 1 ? 1.f : 0.f,
+                           (bits >> (4 * v + 2)) & 1 ? 1.f : 0.f, (bits >> (4 * v + 3)) & 1 ? 1.f : 0.f));
+    } else {
+      for (int c = 0; c < 64 && c < left; ++c) o[c] = (bits >> c) & 1 ? 1.0f : 0.0f;
+    }
+  }
+}
+
+struct SoloPlan {
+  int P, kcap, Wd;
+  size_t bytes, o_packed, o_sum, o_ssum, o_resc, o_keys, o_nvalid, o_kcount, o_packed2, o_sum2, o_cls2, o_sc2, o_upd,
+      o_src, o_mnms;
+  d2b_matrix_nms_params mp;
+};
+int solo_plan(const d2b_solo_postprocess_params* p, SoloPlan& pl) {
+  D2B_REQUIRE(p != nullptr, "params is NULL");
+  D2B_REQUIRE(p->batch >= 0 && p->n >= 0 && p->hw >= 0, "solo_postprocess: negative sizes");
+  D2B_REQUIRE(p->batch <= 65535 && p->n <= 65535, "solo_postprocess: batch / n too large");
+  D2B_REQUIRE(p->hw < (1ll << 24), "solo_postprocess: hw >= 2^24");
+  D2B_REQUIRE(p->pre_nms_topk >= 1 && p->max_detections >= 1 && p->max_detections <= 65535,
+              "solo_postprocess: bad pre_nms_topk / max_detections");
+  D2B_REQUIRE(p->kernel == D2B_MNMS_GAUSSIAN || p->kernel == D2B_MNMS_LINEAR, "NMS kernel %d not implemented yet.", p->kernel);
+  const size_t B = p->batch, n = p->n > 0 ? p->n : 1;
+  pl.Wd = (int)((p->hw + 63) / 64);
+  if (pl.Wd < 1) pl.Wd = 1;
+  pl.P = 1;
+  while ((size_t)pl.P < n) pl.P <<= 1;
+  pl.kcap = (int)(p->pre_nms_topk < (int)n ? p->pre_nms_topk : n);
+  const size_t Wd = pl.Wd, kc = pl.kcap, D = p->max_detections;
+  size_t o = 0;
+  pl.o_packed = o; o += ws_slice(B * n * Wd * 8);
+  pl.o_sum = o; o += ws_slice(B * n * 4);
+  pl.o_ssum = o; o += ws_slice(B * n * 4);
+  pl.o_resc = o; o += ws_slice(B * n * 4);
+  pl.o_keys = o; o += ws_slice(B * pl.P * 8);
+  pl.o_nvalid = o; o += ws_slice(B * 4);
+  pl.o_kcount = o; o += ws_slice(B * 4);
+  pl.o_packed2 = o; o += ws_slice(B * kc * Wd * 8);
+  pl.o_sum2 = o; o += ws_slice(B * kc * 4);
+  pl.o_cls2 = o; o += ws_slice(B * kc * 8);
+  pl.o_sc2 = o; o += ws_slice(B * kc * 4);
+  pl.o_upd = o; o += ws_slice(B * kc * 4);
+  pl.o_src = o; o += ws_slice(B * D * 4);
+  pl.o_mnms = o;
+  pl.mp = d2b_matrix_nms_params();
+  pl.mp.batch = p->batch; pl.mp.n = pl.kcap; pl.mp.hw = p->hw; pl.mp.kernel = p->kernel; pl.mp.sigma = p->sigma;
+  pl.mp.packed_masks = reinterpret_cast<const uint64_t*>(8);  // non-NULL: size the packed-input workspace
+  o += d2b_matrix_nms_workspace_bytes(&pl.mp);
+  pl.bytes = o;
+  return D2B_OK;
+}
+}  // namespace
+}  // namespace d2b
+
 using namespace d2b;
 
 extern "C" size_t d2b_point_nms_workspace_bytes(const d2b_point_nms_params*) { return 0; }
@@ -181,5 +344,81 @@ extern "C" int d2b_solo_mask_encode(const d2b_solo_mask_encode_params* p, void*,
   else
     solo_encode_kernel<false><<<grid, 256, 0, st>>>(a);
   D2B_LAUNCH_CHECK();
+  return D2B_OK;
+}
+
+extern "C" size_t d2b_solo_postprocess_workspace_bytes(const d2b_solo_postprocess_params* p) {
+  SoloPlan pl;
+  if (solo_plan(p, pl) != D2B_OK) return 0;
+  return pl.bytes;
+}
+
+extern "C" int d2b_solo_postprocess(const d2b_solo_postprocess_params* p, void* workspace, size_t workspace_bytes,
+                                    d2b_stream_t stream) {
+  SoloPlan pl;
+  int rc = solo_plan(p, pl);
+  if (rc != D2B_OK) return rc;
+  if (p->batch == 0) return D2B_OK;
+  D2B_REQUIRE(p->out_classes && p->out_scores && p->out_valid, "solo_postprocess: NULL output");
+  D2B_REQUIRE(p->n == 0 || (p->mask_logits && p->scores && p->classes && p->strides), "solo_postprocess: NULL input");
+  if (workspace == nullptr || workspace_bytes < pl.bytes) {
+    set_last_error("solo_postprocess needs %zu workspace bytes", pl.bytes);
+    return D2B_EWORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  const int B = p->batch, n = p->n, D = p->max_detections, kcap = pl.kcap, Wd = pl.Wd, P = pl.P;
+  u64* packed = reinterpret_cast<u64*>(ws + pl.o_packed);
+  float* sum_masks = reinterpret_cast<float*>(ws + pl.o_sum);
+  float* score_sums = reinterpret_cast<float*>(ws + pl.o_ssum);
+  float* rescored = reinterpret_cast<float*>(ws + pl.o_resc);
+  u64* keys = reinterpret_cast<u64*>(ws + pl.o_keys);
+  int32_t* nvalid = reinterpret_cast<int32_t*>(ws + pl.o_nvalid);
+  int32_t* kcount = reinterpret_cast<int32_t*>(ws + pl.o_kcount);
+  u64* packed2 = reinterpret_cast<u64*>(ws + pl.o_packed2);
+  float* sum2 = reinterpret_cast<float*>(ws + pl.o_sum2);
+  long long* cls2 = reinterpret_cast<long long*>(ws + pl.o_cls2);
+  float* sc2 = reinterpret_cast<float*>(ws + pl.o_sc2);
+  float* upd = reinterpret_cast<float*>(ws + pl.o_upd);
+  int32_t* src_row = reinterpret_cast<int32_t*>(ws + pl.o_src);
+  D2B_CUDA(cudaMemsetAsync(nvalid, 0, sizeof(int32_t) * B, st));
+  D2B_CUDA(cudaMemsetAsync(kcount, 0, sizeof(int32_t) * B, st));
+  if (n > 0 && p->hw > 0) {
+    d2b_solo_mask_encode_params e = {};
+    e.mask_logits = p->mask_logits; e.counts = p->counts; e.batch = B; e.n = n; e.hw = p->hw;
+    e.mask_threshold = p->mask_threshold;
+    e.packed_masks = reinterpret_cast<uint64_t*>(packed); e.sum_masks = sum_masks; e.score_sums = score_sums;
+    rc = d2b_solo_mask_encode(&e, nullptr, 0, stream);
+    if (rc != D2B_OK) return rc;
+    solo_score_kernel<<<dim3((P + 255) / 256, B), 256, 0, st>>>(p->scores, p->strides, sum_masks, score_sums, p->counts,
+                                                               n, P, keys, rescored, nvalid);
+    D2B_LAUNCH_CHECK();
+    rc = sort_segments_desc(keys, B, P, nullptr, st);
+    if (rc != D2B_OK) return rc;
+    solo_gather_kernel<<<dim3(kcap, B), 128, 0, st>>>(keys, P, nvalid, p->pre_nms_topk, n, kcap, Wd, packed, sum_masks,
+                                                     reinterpret_cast<const long long*>(p->classes), rescored, packed2,
+                                                     sum2, cls2, sc2, kcount);
+    D2B_LAUNCH_CHECK();
+    d2b_matrix_nms_params m = pl.mp;
+    m.packed_masks = reinterpret_cast<const uint64_t*>(packed2);
+    m.masks = nullptr;
+    m.classes = reinterpret_cast<const int64_t*>(cls2);
+    m.scores = sc2;
+    m.sum_masks = sum2;
+    m.counts = kcount;
+    m.out = upd;
+    rc = d2b_matrix_nms(&m, ws + pl.o_mnms, pl.bytes - pl.o_mnms, stream);
+    if (rc != D2B_OK) return rc;
+  }
+  solo_emit_kernel<<<B, 256, 0, st>>>(upd, cls2, kcount, kcap, p->update_score_threshold, D,
+                                      reinterpret_cast<long long*>(p->out_classes), p->out_scores, p->out_valid, src_row,
+                                      p->out_num);
+  D2B_LAUNCH_CHECK();
+  if ((p->out_masks || p->out_packed_masks) && p->hw > 0) {
+    solo_unpack_kernel<<<dim3((Wd + 255) / 256, D, B), 256, 0, st>>>(packed2, src_row, kcap, Wd, p->hw, D,
+                                                                     reinterpret_cast<u64*>(p->out_packed_masks),
+                                                                     p->out_masks);
+    D2B_LAUNCH_CHECK();
+  }
   return D2B_OK;
 }

@@ -3,7 +3,7 @@ import torch
 
 from ... import _native as nv
 
-__all__ = ["point_nms", "solo_mask_encode"]
+__all__ = ["point_nms", "solo_mask_encode", "SOLOv2Inference"]
 
 
 def point_nms(inputs, kernel_size=2, scope=None):
@@ -53,3 +53,58 @@ def solo_mask_encode(mask_logits, mask_threshold=0.5, counts=None):
     if not batched:
         outs = tuple(o[0] for o in outs)
     return tuple(nv.to_host(o) for o in outs) if host else outs
+
+
+class SOLOv2Inference(object):
+    """The tail of `SOLOv2Head.inference` after the dynamic convolution (solo_v2.py:507-558), batched: mask stage,
+    `sum_masks > strides` filter, mask scoring, top-k, Matrix-NMS on bit-packed masks, score filter, pad / clip.
+    Attributes mirror the ones `SOLOv2Head.__init__` reads from cfg (:140-149)."""
+
+    def __init__(self, mask_threshold=0.5, pre_nms_topk=500, nms_kernel="gaussian", nms_sigma=2.0,
+                 update_score_threshold=0.05, max_detections_per_image=100):
+        if nms_kernel not in ("gaussian", "linear"):
+            raise NotImplementedError(f"NMS kernel {nms_kernel} not implemented yet.")
+        self.mask_threshold = mask_threshold
+        self.pre_nms_topk = pre_nms_topk
+        self.nms_kernel = nms_kernel
+        self.nms_sigma = nms_sigma
+        self.update_score_threshold = update_score_threshold
+        self.max_detections_per_image = max_detections_per_image
+
+    def postprocess(self, mask_logits, scores, classes, strides, counts=None, return_masks=True):
+        """mask_logits [B, n, H, W]: conv output of each image's candidates (those with score > score_threshold, in
+        `tf.where` order; rows >= counts[b] are padding); scores / classes / strides [B, n].
+        Returns dict(pred_masks fp32 0/1 [B, D, H, W] (or None), packed_masks int64 [B, D, ceil(HW/64)],
+        pred_classes int64 [B, D], scores [B, D], is_valid [B, D], num [B])."""
+        host = not mask_logits.is_cuda
+        dev = nv.device_of(mask_logits)
+        x = nv.to_device(mask_logits, dev, torch.float32)
+        assert x.dim() == 4
+        B, n, H, W = x.shape
+        hw = H * W
+        D = int(self.max_detections_per_image)
+        sc = nv.to_device(scores, dev, torch.float32).reshape(B, n)
+        cl = nv.to_device(classes, dev, torch.int64).reshape(B, n)
+        stv = nv.to_device(strides, dev, torch.float32).reshape(B, n)
+        cnt = None if counts is None else nv.to_device(counts, dev, torch.int32)
+        Wd = (hw + 63) // 64
+        masks = torch.empty((B, D, H, W), dtype=torch.float32, device=dev) if return_masks else None
+        packed = torch.empty((B, D, Wd), dtype=torch.int64, device=dev)
+        oc = torch.empty((B, D), dtype=torch.int64, device=dev)
+        os_ = torch.empty((B, D), dtype=torch.float32, device=dev)
+        ov = torch.empty((B, D), dtype=torch.bool, device=dev)
+        num = torch.empty(B, dtype=torch.int32, device=dev)
+        p = nv.SoloPostprocessParams()
+        p.mask_logits, p.scores, p.classes, p.strides = x.data_ptr(), sc.data_ptr(), cl.data_ptr(), stv.data_ptr()
+        p.counts = nv.ptr(cnt)
+        p.batch, p.n, p.hw = B, n, hw
+        p.mask_threshold, p.pre_nms_topk = float(self.mask_threshold), int(self.pre_nms_topk)
+        p.kernel = nv.MNMS_GAUSSIAN if self.nms_kernel == "gaussian" else nv.MNMS_LINEAR
+        p.sigma, p.update_score_threshold, p.max_detections = float(self.nms_sigma), float(self.update_score_threshold), D
+        p.out_masks, p.out_packed_masks = nv.ptr(masks), packed.data_ptr()
+        p.out_classes, p.out_scores, p.out_valid, p.out_num = oc.data_ptr(), os_.data_ptr(), ov.data_ptr(), num.data_ptr()
+        nv.call("solo_postprocess", p, dev)
+        out = dict(pred_masks=masks, packed_masks=packed, pred_classes=oc, scores=os_, is_valid=ov, num=num)
+        if host:
+            out = {k: (None if v is None else nv.to_host(v)) for k, v in out.items()}
+        return out

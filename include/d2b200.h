@@ -538,6 +538,41 @@ D2B_API size_t d2b_solo_mask_encode_workspace_bytes(const d2b_solo_mask_encode_p
 D2B_API int d2b_solo_mask_encode(const d2b_solo_mask_encode_params* p, void* workspace, size_t workspace_bytes,
                                  d2b_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * SOLOv2Head.inference tail after the dynamic conv          solo_v2.py:507-558
+ * Per image b (B images per call, the reference's tf.map_fn at :587): the first counts[b] of the n rows are
+ * the candidates that passed the score threshold, in tf.where order.
+ *   mask stage (d2b_solo_mask_encode) -> keep sum_masks > strides -> scores *= mask scoring ->
+ *   top_k(min(pre_nms_topk, #kept)) -> Matrix-NMS on the packed masks -> keep > update_score_threshold ->
+ *   pad / clip to max_detections.
+ * Outputs are zero padded.  out_masks (fp32 0/1, the reference's pred_masks before the resize) and
+ * out_packed_masks (bit-packed, 1/32 of the bytes) are both optional.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* mask_logits; /* [B, n, hw] */
+  const float* scores;      /* [B, n] */
+  const int64_t* classes;   /* [B, n] */
+  const float* strides;     /* [B, n] */
+  const int32_t* counts;    /* optional [B] */
+  int32_t batch, n;
+  int64_t hw;
+  float mask_threshold;
+  int32_t pre_nms_topk;
+  int32_t kernel; /* D2B_MNMS_* */
+  float sigma;
+  float update_score_threshold;
+  int32_t max_detections;
+  float* out_masks;           /* optional [B, max_det, hw] */
+  uint64_t* out_packed_masks; /* optional [B, max_det, ceil(hw/64)] */
+  int64_t* out_classes;       /* [B, max_det] */
+  float* out_scores;          /* [B, max_det] */
+  uint8_t* out_valid;         /* [B, max_det] */
+  int32_t* out_num;           /* optional [B] */
+} d2b_solo_postprocess_params;
+D2B_API size_t d2b_solo_postprocess_workspace_bytes(const d2b_solo_postprocess_params* p);
+D2B_API int d2b_solo_postprocess(const d2b_solo_postprocess_params* p, void* workspace, size_t workspace_bytes,
+                                 d2b_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

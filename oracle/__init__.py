@@ -431,3 +431,21 @@ def sigmoid_array(x):
     out = np.empty_like(x)
     lib().orc_sigmoid_array(_p(x), C.c_int64(x.size), _p(out))
     return out
+
+
+def solo_postprocess(mask_logits, scores, classes, strides, mask_threshold=0.5, pre_nms_topk=500, kernel="gaussian",
+                     sigma=2.0, update_score_threshold=0.05, max_detections=100):
+    """solo_v2.py:507-558 for one image -> (masks [D,H,W] fp32 0/1, classes int64 [D], scores [D], valid [D], n)."""
+    x = _f32(mask_logits)
+    n, H, W = x.shape
+    D = int(max_detections)
+    om = np.zeros((D, H, W), np.float32)
+    oc = np.zeros(D, np.int64)
+    os_ = np.zeros(D, np.float32)
+    ov = np.zeros(D, np.uint8)
+    f = lib().orc_solo_postprocess
+    f.restype = C.c_int
+    nv = f(_p(x), _p(_f32(scores)), _p(np.ascontiguousarray(classes, np.int64)), _p(_f32(strides)), n, C.c_int64(H * W),
+           C.c_float(mask_threshold), int(pre_nms_topk), {"gaussian": 0, "linear": 1}[kernel], C.c_float(sigma),
+           C.c_float(update_score_threshold), D, _p(om), _p(oc), _p(os_), _p(ov))
+    return om, oc, os_, ov.astype(bool), int(nv)

@@ -1165,3 +1165,61 @@ ORC_API void orc_sigmoid_array(const float* x, int64_t n, float* out) {
 #pragma omp parallel for num_threads(ORC_NT) schedule(static)
   for (int64_t i = 0; i < n; ++i) out[i] = orc_sigmoidf(x[i]);
 }
+
+/* lib/modeling/single_stage_heads/solo_v2.py:507-558: the tail of SOLOv2Head.inference_single_image after the
+ * dynamic convolution, for ONE image.  mask_logits [n, hw] (conv output of the candidates that passed the score
+ * threshold, in tf.where order), scores / classes / strides [n].
+ *   pred_mask_scores = sigmoid(logits); pred_masks = scores > mask_threshold; sum_masks        (:513-517)
+ *   keep = sum_masks > strides (boolean_mask keeps order)                                       (:520-526)
+ *   pred_scores *= reduce_sum(mask_scores * masks) / sum_masks                                  (:529-533)
+ *   top_k(min(pre_nms_topk, #kept), sorted)  + gathers                                          (:536-540)
+ *   matrix_nms(masks, classes, scores, sum_masks)                                               (:543-546)
+ *   keep = scores > update_score_threshold (order kept); pad_or_clip to max_det                 (:549-556)
+ * Outputs zero padded: out_masks [max_det, hw] fp32 0/1, out_classes int64, out_scores, out_valid. Returns #valid. */
+ORC_API int orc_solo_postprocess(const float* mask_logits, const float* scores, const int64_t* classes,
+                                 const float* strides, int n, int64_t hw, float mask_thr, int pre_nms_topk, int kernel,
+                                 float sigma, float update_thr, int max_det, float* out_masks, int64_t* out_classes,
+                                 float* out_scores, uint8_t* out_valid) {
+  memset(out_masks, 0, sizeof(float) * (size_t)max_det * hw);
+  for (int j = 0; j < max_det; ++j) { out_classes[j] = 0; out_scores[j] = 0.0f; out_valid[j] = 0; }
+  if (n <= 0) return 0;
+  float* masks = (float*)malloc(sizeof(float) * (size_t)n * hw);
+  float* sm = (float*)malloc(sizeof(float) * n);
+  float* ss = (float*)malloc(sizeof(float) * n);
+  orc_solo_mask_stage(mask_logits, n, hw, mask_thr, masks, sm, ss);
+  int* kept = (int*)malloc(sizeof(int) * n);
+  float* ks = (float*)malloc(sizeof(float) * n);
+  int m = 0;
+  for (int i = 0; i < n; ++i)
+    if (sm[i] > strides[i]) {
+      float sc = ss[i] / sm[i];
+      ks[m] = scores[i] * sc;
+      kept[m++] = i;
+    }
+  int k = pre_nms_topk < m ? pre_nms_topk : m;
+  int nv = 0;
+  if (k > 0) {
+    float* tv = (float*)malloc(sizeof(float) * k);
+    int32_t* ti = (int32_t*)malloc(sizeof(int32_t) * k);
+    orc_top_k(ks, m, k, tv, ti);
+    float* gm = (float*)malloc(sizeof(float) * (size_t)k * hw);
+    float* gs = (float*)malloc(sizeof(float) * k);
+    int64_t* gc = (int64_t*)malloc(sizeof(int64_t) * k);
+    for (int r = 0; r < k; ++r) {
+      const int src = kept[ti[r]];
+      memcpy(gm + (size_t)r * hw, masks + (size_t)src * hw, sizeof(float) * hw);
+      gs[r] = sm[src]; gc[r] = classes[src];
+    }
+    float* upd = (float*)malloc(sizeof(float) * k);
+    orc_matrix_nms(gm, gc, tv, gs, k, hw, kernel, sigma, upd);
+    for (int r = 0; r < k && nv < max_det; ++r)
+      if (upd[r] > update_thr) {
+        memcpy(out_masks + (size_t)nv * hw, gm + (size_t)r * hw, sizeof(float) * hw);
+        out_classes[nv] = gc[r]; out_scores[nv] = upd[r]; out_valid[nv] = 1;
+        ++nv;
+      }
+    free(upd); free(gc); free(gs); free(gm); free(ti); free(tv);
+  }
+  free(ks); free(kept); free(ss); free(sm); free(masks);
+  return nv;
+}

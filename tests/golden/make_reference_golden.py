@@ -260,6 +260,39 @@ def main():
     pn = np.round(rng.standard_normal((2, 9, 11, 8)) * 2).astype(np.float32) / 2  # plateaus and negatives
     out["pn_in"], out["pn_out"] = pn, np.asarray(R.solo.point_nms(t(pn)))
 
+    # ---- 14. MaskKernelBranch.inference (solo_v2.py:476-612) with image_shape == mask-feature size (resize = identity).
+    # The op under test starts after the dynamic conv, so the generator repeats the candidate selection (:481-497)
+    # and the 1x1 conv (:499-511) in numpy to record the op's inputs; everything after is the reference's code.
+    Nimg, K, E, Hm, Wm = 2, 3, 8, 24, 32
+    grids, sstr = [6, 4], [8, 16]
+    shead = types.SimpleNamespace(score_threshold=0.3, num_grids=grids, strides=sstr, mask_kernel_size=1,
+                                  mask_feature_out_dims=E, mask_threshold=0.5, pre_nms_topk=30, nms_kernel="gaussian",
+                                  nms_sigma=2.0, update_score_threshold=0.05, max_detections_per_image=12)
+    probs = [rng.random((Nimg, g_, g_, K)).astype(np.float32) ** 2 for g_ in grids]
+    kerns = [(rng.standard_normal((Nimg, g_, g_, E)) * 0.8).astype(np.float32) for g_ in grids]
+    yy_, xx_ = np.mgrid[0:Hm, 0:Wm].astype(np.float32)
+    mfeat = np.stack([np.stack([np.sin(yy_ * rng.uniform(0.1, 0.5) + xx_ * rng.uniform(0.1, 0.5) + rng.uniform(0, 6))
+                                for _ in range(E)], -1) for _ in range(Nimg)]).astype(np.float32)
+    res = R.solo.MaskKernelBranch.inference(shead, [t(p_) for p_ in probs], [t(k_) for k_ in kerns], t(mfeat), [Hm, Wm])
+    out.update(so_masks=np.asarray(res.get_field("pred_masks")), so_classes=np.asarray(res.get_field("pred_classes")),
+               so_scores=np.asarray(res.get_field("scores")), so_valid=np.asarray(res.get_field("is_valid")))
+    flat_p = np.concatenate([p_.reshape(Nimg, -1, K) for p_ in probs], 1)
+    flat_k = np.concatenate([k_.reshape(Nimg, -1, E) for k_ in kerns], 1)
+    cell_stride = np.concatenate([np.full(g_ * g_, s_, np.float32) for g_, s_ in zip(grids, sstr)])
+    ncap = int(max((flat_p[i] > 0.3).sum() for i in range(Nimg)))
+    so_logits = np.zeros((Nimg, ncap, Hm, Wm), np.float32)
+    so_sc, so_cl, so_st = np.zeros((Nimg, ncap), np.float32), np.zeros((Nimg, ncap), np.int64), np.ones((Nimg, ncap), np.float32)
+    so_cnt = np.zeros(Nimg, np.int32)
+    for i in range(Nimg):
+        keep = np.argwhere(flat_p[i] > 0.3)
+        c_ = keep.shape[0]
+        so_cnt[i] = c_
+        so_sc[i, :c_] = flat_p[i][keep[:, 0], keep[:, 1]]
+        so_cl[i, :c_] = keep[:, 1]
+        so_st[i, :c_] = cell_stride[keep[:, 0]]
+        so_logits[i, :c_] = np.einsum("nhwc,co->nhwo", mfeat[i:i + 1], flat_k[i][keep[:, 0]].T.copy())[0].transpose(2, 0, 1)
+    out.update(so_in_logits=so_logits, so_in_scores=so_sc, so_in_classes=so_cl, so_in_strides=so_st, so_in_counts=so_cnt)
+
     np.savez_compressed(os.path.join(HERE, "reference_python.npz"), **out)
     print("reference_python.npz:", len(out), "arrays,",
           os.path.getsize(os.path.join(HERE, "reference_python.npz")) // 1024, "KiB")

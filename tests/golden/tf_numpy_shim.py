@@ -409,7 +409,16 @@ def build_tf():
             for dx in range(kw):
                 out = np.maximum(out, x[:, dy:dy + oh, dx:dx + ow])
         return t(out)
-    tf.nn = types.SimpleNamespace(max_pool=max_pool, top_k=_top_k, sigmoid=un(lambda x: (np.float32(1) / (np.float32(1) + np.exp(-x)))),
+    def conv2d(x, filters, strides=None, padding="VALID", **kw):
+        x, f = np.asarray(x, np.float32), np.asarray(filters, np.float32)
+        assert f.shape[0] == 1 and f.shape[1] == 1 and padding == "VALID", "shim: 1x1 VALID convolutions only"
+        return t(np.einsum("nhwc,co->nhwo", x, f[0, 0]).astype(np.float32))
+
+    def resize_same(images, size, method=None, **kw):
+        x = np.asarray(images)
+        assert tuple(int(v) for v in size) == x.shape[1:3], "shim: resize only to the same size (identity)"
+        return t(x)
+    tf.nn = types.SimpleNamespace(conv2d=conv2d, max_pool=max_pool, top_k=_top_k, sigmoid=un(lambda x: (np.float32(1) / (np.float32(1) + np.exp(-x)))),
                                   softmax=softmax, relu=un(lambda x: np.maximum(x, 0)))
     tf.image = types.SimpleNamespace(crop_and_resize=_crop_and_resize, non_max_suppression=_non_max_suppression,
                                      resize_images=None, ResizeMethod=types.SimpleNamespace(BILINEAR=0, NEAREST_NEIGHBOR=1))
@@ -421,7 +430,7 @@ def build_tf():
     slim = types.SimpleNamespace(avg_pool2d=_avg_pool2d, max_pool2d=None, flatten=None, model_variable=None,
                                  add_arg_scope=lambda f: f)
     tf.contrib = types.SimpleNamespace(slim=slim, framework=types.SimpleNamespace(add_arg_scope=lambda f: f))
-    tf.compat = types.SimpleNamespace(v2=types.SimpleNamespace(image=types.SimpleNamespace(resize=None)),
+    tf.compat = types.SimpleNamespace(v2=types.SimpleNamespace(image=types.SimpleNamespace(resize=resize_same)),
                                       v1=tf)
     tf.random_normal_initializer = lambda *a, **k: None
     tf.constant_initializer = lambda *a, **k: None

@@ -410,3 +410,38 @@ def test_solo_mask_encode_and_packed_matrix_nms(cuda, oracle_lib, hw, thr):
     assert np.array_equal(got_dense.cpu().numpy(), want, equal_nan=True)
     got_nosum = matrix_nms(None, T(classes, cuda), T(scores, cuda), packed_masks=packed, mask_hw=H * W)
     assert np.array_equal(got_nosum.cpu().numpy(), want, equal_nan=True)
+
+
+@pytest.mark.parametrize("n,hw,pre,D,kern", [(300, (40, 64), 120, 40, "gaussian"), (77, (25, 37), 500, 100, "linear"),
+                                             (1, (8, 8), 5, 3, "gaussian"), (600, (50, 84), 500, 100, "gaussian")])
+def test_solo_postprocess(cuda, oracle_lib, n, hw, pre, D, kern):
+    """SOLOv2Head.inference tail after the dynamic conv (solo_v2.py:507-558), batched with ragged counts."""
+    from detectron2_tensorflow_b200.modeling import SOLOv2Inference
+    rng = np.random.default_rng(n + D)
+    B, (H, W) = 3, hw
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    logits = np.empty((B, n, H, W), np.float32)
+    for b in range(B):
+        for i in range(n):
+            cy, cx, r = rng.uniform(0, H), rng.uniform(0, W), rng.uniform(1, max(H, W) / 2)
+            logits[b, i] = (r - np.sqrt((yy - cy) ** 2 + (xx - cx) ** 2)) * rng.uniform(0.05, 2.0)
+        logits[b, n // 2:] = logits[b, :n - n // 2] + rng.normal(0, 0.02, (n - n // 2, H, W)).astype(np.float32)
+    scores = rng.uniform(0.1, 1.0, (B, n)).astype(np.float32)
+    classes = rng.integers(0, 3, (B, n)).astype(np.int64)
+    strides = rng.choice([8.0, 16.0, 32.0], (B, n)).astype(np.float32)
+    counts = np.array([n, max(n - 7, 0), 0], np.int32)
+    head = SOLOv2Inference(0.5, pre, kern, 2.0, 0.05, D)
+    got = head.postprocess(T(logits, cuda), T(scores, cuda), T(classes, cuda), T(strides, cuda), T(counts, cuda))
+    for b in range(B):
+        c = int(counts[b])
+        wm, wc, ws, wv, wn = oracle_lib.solo_postprocess(logits[b, :c], scores[b, :c], classes[b, :c], strides[b, :c], 0.5,
+                                                        pre, kern, 2.0, 0.05, D)
+        assert int(got["num"][b]) == wn
+        assert np.array_equal(got["is_valid"][b].cpu().numpy(), wv)
+        assert np.array_equal(got["pred_classes"][b].cpu().numpy(), wc)
+        # scores carry the fp32 mask-scoring sums (order of summation differs): 1e-5 relative
+        assert np.allclose(got["scores"][b].cpu().numpy(), ws, rtol=1e-5, atol=1e-7, equal_nan=True)
+        assert np.array_equal(got["pred_masks"][b].cpu().numpy(), wm)
+        bits = np.unpackbits(got["packed_masks"][b].cpu().numpy().view(np.uint8), axis=-1, bitorder="little")[:, :H * W]
+        assert np.array_equal(bits.reshape(D, H, W), wm.astype(np.uint8))
+    assert int(got["num"].sum()) > 0

@@ -160,3 +160,20 @@ def test_point_nms(oracle_lib, z):
     got = oracle_lib.point_nms(z["pn_in"])
     assert np.array_equal(got, z["pn_out"])
     assert 0 < (got != 0).sum() < (z["pn_in"] != 0).sum()
+
+
+def test_solo_inference_tail(oracle_lib, z):
+    """MaskKernelBranch.inference (solo_v2.py:476-612) with image_shape == mask-feature size, from the recorded
+    post-conv candidates: masks / classes / validity exact, scores 1e-5 (sigmoid + summation order)."""
+    lg, sc, cl, st, cnt = z["so_in_logits"], z["so_in_scores"], z["so_in_classes"], z["so_in_strides"], z["so_in_counts"]
+    total = 0
+    for b in range(lg.shape[0]):
+        c = int(cnt[b])
+        m, oc, os_, ov, nv = oracle_lib.solo_postprocess(lg[b, :c], sc[b, :c], cl[b, :c], st[b, :c], 0.5, 30, "gaussian", 2.0,
+                                                         0.05, 12)
+        assert np.array_equal(ov, z["so_valid"][b])
+        assert np.array_equal(oc, z["so_classes"][b])
+        assert np.array_equal(m, z["so_masks"][b])
+        assert np.allclose(os_, z["so_scores"][b], rtol=1e-5, atol=1e-7)
+        total += nv
+    assert total > 0

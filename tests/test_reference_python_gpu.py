@@ -139,3 +139,14 @@ def test_yolo_and_point_nms(cuda, z):
     assert np.array_equal(res.get_field("scores").cpu().numpy(), z["yo_scores"])
     assert np.array_equal(res.boxes.cpu().numpy(), z["yo_boxes"])
     assert np.array_equal(point_nms(T(z["pn_in"], cuda)).cpu().numpy(), z["pn_out"])
+
+
+def test_solo_inference_tail(cuda, z):
+    from detectron2_tensorflow_b200.modeling import SOLOv2Inference
+    head = SOLOv2Inference(0.5, 30, "gaussian", 2.0, 0.05, 12)
+    got = head.postprocess(T(z["so_in_logits"], cuda), T(z["so_in_scores"], cuda), T(z["so_in_classes"], cuda),
+                           T(z["so_in_strides"], cuda), T(z["so_in_counts"], cuda))
+    assert np.array_equal(got["is_valid"].cpu().numpy(), z["so_valid"])
+    assert np.array_equal(got["pred_classes"].cpu().numpy(), z["so_classes"])
+    assert np.array_equal(got["pred_masks"].cpu().numpy(), z["so_masks"])
+    assert np.allclose(got["scores"].cpu().numpy(), z["so_scores"], rtol=1e-5, atol=1e-7)

@@ -137,6 +137,14 @@ if "4" in which:
     ms_p = timeit(lambda: matrix_nms(None, classes, scores, sum_masks=sums, packed_masks=packed, mask_hw=H * W))
     print(json.dumps({"config": 4, "case": "SOLOv2 mask stage: sigmoid+threshold+bit-pack+sums of the logits", "ms": ms_e,
                       "GBps": by / ms_e / 1e6, "frac_hbm": by / ms_e / 1e6 / HBM}))
+    from detectron2_tensorflow_b200.modeling import SOLOv2Inference
+    head = SOLOv2Inference(0.5, 500, "gaussian", 2.0, 0.05, 100)
+    strides = torch.full((B, n), 8.0, device=dev)
+    ms_t = timeit(lambda: head.postprocess(logits, scores, classes, strides, return_masks=False))
+    ms_tm = timeit(lambda: head.postprocess(logits, scores, classes, strides, return_masks=True))
+    print(json.dumps({"config": 4, "case": "SOLOv2 inference tail after the conv (encode + filter + scoring + top-k + Matrix-NMS + emit), B=16 n=500",
+                      "ms_packed_masks_out": ms_t, "ms_fp32_masks_out": ms_tm, "images_per_s": B / ms_t * 1e3,
+                      "logit_GBps": by / ms_t / 1e6, "frac_hbm": by / ms_t / 1e6 / HBM}))
     print(json.dumps({"config": 4, "case": "Matrix-NMS on packed masks (no fp32 mask read)", "ms": ms_p,
                       "images_per_s": B / ms_p * 1e3, "packed_GB": packed.numel() * 8 / 1e9}))
 
