@@ -5,9 +5,10 @@ numpy-in / numpy-out ctypes bindings over ``oracle/liboracle.so`` (built from
 ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
 legs may import this package; the product package never does.
 
-Parity status: *unpinned at the TF boundary* (the reference ships no tests and
-TensorFlow cannot be installed here); pinned against the reference's own numpy
-NMS and torchvision/torch -- see ``tests/golden/make_golden.py``.
+Parity status: the COMPOSITION is pinned on the reference's own Python, executed unmodified on a numpy
+stand-in for the TF ops it calls (``tests/golden/make_reference_golden.py`` -> ``reference_python.npz``); the
+arithmetic inside the stock TF kernels stays *unpinned* (TensorFlow cannot be installed here) and is
+cross-checked against the reference's numpy NMS and torchvision/torch -- see ``tests/golden/make_golden.py``.
 """
 import ctypes as C
 import os

@@ -12,12 +12,19 @@
  * reference tree; their published semantics are restated here, see SURVEY.md
  * Appendix A).  Every function cites the reference file:line it follows.
  *
- * PARITY STATUS: "parity unpinned" at the TF boundary -- the reference has no
- * tests/golden vectors and TensorFlow is not installable here.  The oracle IS
- * pinned against (a) the reference's own TF-free numpy NMS
- * (lib/structures/np_box_list_ops.py:146-216) run in the build container,
- * (b) torchvision.ops.roi_align/nms and torch.topk as independent
- * implementations; vectors are committed under tests/golden/.
+ * PARITY STATUS: pinned on the reference's own Python for the COMPOSITION, "parity unpinned" for the
+ * arithmetic inside the stock TF kernels.  The reference has no tests/golden vectors and TensorFlow is not
+ * installable here, but its post-backbone modules are plain Python over ~90 TF ops: they are executed
+ * UNMODIFIED on a numpy stand-in for that API slice (tests/golden/tf_numpy_shim.py) and their outputs are
+ * committed as tests/golden/reference_python.npz (generator: tests/golden/make_reference_golden.py;
+ * checked by tests/test_reference_python_golden.py).  That pins operation order, tie rules, padding, class
+ * offsets, level routing and label stitching of ROIPooler / ROIAlign / crop_and_resize, find_top_rpn_proposals,
+ * fast_rcnn_inference, RetinaNet / YOLOv4 / SOLOv2 inference, pairwise_iou, Matcher, _get_ground_truth,
+ * mask paste-back, point_nms and the anchor generator.  The kernels of CropAndResize, NonMaxSuppression,
+ * TopKV2 and AvgPool are restated there a second time, in numpy, independently of this file -- not run
+ * from TensorFlow itself.  Further pins: (a) the reference's own TF-free numpy NMS
+ * (lib/structures/np_box_list_ops.py:146-216), (b) torchvision.ops.roi_align/nms (+ autograd for the
+ * backward) and torch.topk as independent implementations; vectors under tests/golden/.
  *
  * The oracle deliberately keeps the reference's DATA MOVEMENT (SYMMETRIC pad
  * copy, per-level gather, concat + inverse-permutation gather, decode of all
