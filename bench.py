@@ -215,6 +215,8 @@ def time_cpu(host, n_images, steps, warmup):
     """Returns (ROIs/s, seconds per step, threads, per-stage seconds per step, NMS boxes entering per step)."""
     import oracle
     oracle.build()
+    # all the host threads this process may use -- explicitly, because torchrun exports OMP_NUM_THREADS=1
+    oracle.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     ts = []
     stage = [0.0, 0.0, 0.0, 0.0]
     for i in range(warmup + steps):
