@@ -80,7 +80,7 @@ def rand_boxes(rng, n, H=800, W=1333, smin=8, smax=400):
     return np.stack([cy - h / 2, cx - w / 2, cy + h / 2, cx + w / 2], 1).astype(np.float32)
 
 
-def main():
+def main(out_path=None):
     R = load_reference()
     from detectron2_tensorflow_b200.utils import synthetic as syn
     rng = np.random.default_rng(500)
@@ -293,10 +293,10 @@ def main():
         so_logits[i, :c_] = np.einsum("nhwc,co->nhwo", mfeat[i:i + 1], flat_k[i][keep[:, 0]].T.copy())[0].transpose(2, 0, 1)
     out.update(so_in_logits=so_logits, so_in_scores=so_sc, so_in_classes=so_cl, so_in_strides=so_st, so_in_counts=so_cnt)
 
-    np.savez_compressed(os.path.join(HERE, "reference_python.npz"), **out)
-    print("reference_python.npz:", len(out), "arrays,",
-          os.path.getsize(os.path.join(HERE, "reference_python.npz")) // 1024, "KiB")
+    out_path = out_path or os.path.join(HERE, "reference_python.npz")
+    np.savez_compressed(out_path, **out)
+    print(os.path.basename(out_path) + ":", len(out), "arrays,", os.path.getsize(out_path) // 1024, "KiB")
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)
