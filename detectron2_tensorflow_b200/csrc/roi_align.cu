@@ -115,6 +115,38 @@ __device__ __forceinline__ Tap make_tap(float lo, float hi, int s, int cs, int P
   return t;
 }
 
+// CTA prologue shared by the forward and backward kernels: every participating thread derives the ROI frame
+// redundantly (level, image, and the sample taps of every crop row / column) into shared memory.
+__device__ __forceinline__ void build_roi_frame(const RoiAlignArgs& a, long long roi, int ch, int cw, Tap* ty, Tap* tx,
+                                                int* s_level, int* s_img, bool publish_level) {
+  const int tid = threadIdx.x;
+  if (tid < ch + cw || tid == kThreads - 1) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(a.boxes) + roi);
+    int lvl = 0;
+    if (a.L > 1) lvl = level_of(b.x, b.y, b.z, b.w, a.min_level, a.max_level, a.canon_size, a.canon_level);
+    const Level L = a.lv[lvl];
+    const float padf = a.pad ? 1.0f : 0.0f;
+    if (tid < ch) {
+      const float lo = b.x * L.scale + padf, hi = b.z * L.scale + padf;
+      ty[tid] = make_tap(lo, hi, tid, ch, L.H + 2 * a.pad, a.pad, L.H, a.aligned, L.W * a.C);
+    } else if (tid < ch + cw) {
+      const float lo = b.y * L.scale + padf, hi = b.w * L.scale + padf;
+      tx[tid - ch] = make_tap(lo, hi, tid - ch, cw, L.W + 2 * a.pad, a.pad, L.W, a.aligned, a.C);
+    }
+    if (tid == kThreads - 1) {
+      long long img = a.bidx64 ? reinterpret_cast<const long long*>(a.bidx)[roi * a.bidx_stride]
+                               : (long long)reinterpret_cast<const int*>(a.bidx)[roi * a.bidx_stride];
+      *s_level = lvl;
+      *s_img = (img >= 0 && img < a.N) ? (int)img : -1;
+      if (publish_level) {
+        if (a.level_counts) atomicAdd(a.level_counts + lvl, 1);
+        if (a.level_out) a.level_out[roi] = lvl;
+      }
+    }
+  }
+  __syncthreads();
+}
+
 template <typename T>
 struct Vec;  // 16-byte channel group
 template <>
@@ -177,32 +209,7 @@ __global__ void __launch_bounds__(kThreads) roi_align_kernel(const RoiAlignArgs 
   const int ch = a.oh * s1, cw = a.ow * s1;
   const int tid = threadIdx.x;
 
-  // ---- prologue: every participating thread derives the ROI frame redundantly
-  if (tid < ch + cw || tid == kThreads - 1) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(a.boxes) + roi);
-    int lvl = 0;
-    if (a.L > 1) lvl = level_of(b.x, b.y, b.z, b.w, a.min_level, a.max_level, a.canon_size, a.canon_level);
-    const Level L = a.lv[lvl];
-    const float padf = a.pad ? 1.0f : 0.0f;
-    if (tid < ch) {
-      const float lo = b.x * L.scale + padf, hi = b.z * L.scale + padf;
-      ty[tid] = make_tap(lo, hi, tid, ch, L.H + 2 * a.pad, a.pad, L.H, a.aligned, L.W * a.C);
-    } else if (tid < ch + cw) {
-      const float lo = b.y * L.scale + padf, hi = b.w * L.scale + padf;
-      tx[tid - ch] = make_tap(lo, hi, tid - ch, cw, L.W + 2 * a.pad, a.pad, L.W, a.aligned, a.C);
-    }
-    if (tid == kThreads - 1) {
-      long long img = a.bidx64 ? reinterpret_cast<const long long*>(a.bidx)[roi * a.bidx_stride]
-                               : (long long)reinterpret_cast<const int*>(a.bidx)[roi * a.bidx_stride];
-      s_level = lvl;
-      s_img = (img >= 0 && img < a.N) ? (int)img : -1;
-      if (blockIdx.y == 0) {
-        if (a.level_counts) atomicAdd(a.level_counts + lvl, 1);
-        if (a.level_out) a.level_out[roi] = lvl;
-      }
-    }
-  }
-  __syncthreads();
+  build_roi_frame(a, roi, ch, cw, ty, tx, &s_level, &s_img, blockIdx.y == 0);
 
   const int lvl = s_level;
   const int img = s_img;
@@ -356,27 +363,7 @@ __global__ void __launch_bounds__(kThreads) roi_align_backward_kernel(const RoiA
   const int s1 = a.sr > 0 ? a.sr : 1;
   const int ch = a.oh * s1, cw = a.ow * s1;
   const int tid = threadIdx.x;
-  if (tid < ch + cw || tid == kThreads - 1) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(a.boxes) + roi);
-    int lvl = 0;
-    if (a.L > 1) lvl = level_of(b.x, b.y, b.z, b.w, a.min_level, a.max_level, a.canon_size, a.canon_level);
-    const Level L = a.lv[lvl];
-    const float padf = a.pad ? 1.0f : 0.0f;
-    if (tid < ch) {
-      const float lo = b.x * L.scale + padf, hi = b.z * L.scale + padf;
-      ty[tid] = make_tap(lo, hi, tid, ch, L.H + 2 * a.pad, a.pad, L.H, a.aligned, L.W * a.C);
-    } else if (tid < ch + cw) {
-      const float lo = b.y * L.scale + padf, hi = b.w * L.scale + padf;
-      tx[tid - ch] = make_tap(lo, hi, tid - ch, cw, L.W + 2 * a.pad, a.pad, L.W, a.aligned, a.C);
-    }
-    if (tid == kThreads - 1) {
-      long long img = a.bidx64 ? reinterpret_cast<const long long*>(a.bidx)[roi * a.bidx_stride]
-                               : (long long)reinterpret_cast<const int*>(a.bidx)[roi * a.bidx_stride];
-      s_level = lvl;
-      s_img = (img >= 0 && img < a.N) ? (int)img : -1;
-    }
-  }
-  __syncthreads();
+  build_roi_frame(a, roi, ch, cw, ty, tx, &s_level, &s_img, false);
   const int img = s_img;
   if (img < 0) return;  // TF skips boxes whose box_ind is out of range
   const int lvl = s_level;
