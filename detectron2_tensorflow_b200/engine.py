@@ -41,6 +41,34 @@ class GraphedStep(object):
         return {k: torch.cat([o[k] for o in self.outputs]) for k in keys}
 
 
+class StepPipeline(object):
+    """`depth` captured steps (each with its own static outputs) replayed round-robin on their own streams, so that
+    consecutive, independent batches overlap: the single-CTA latency chains of one step run under the HBM-bound
+    pooling of the next.  `run(k)` enqueues k steps forked from / joined to the current stream."""
+
+    def __init__(self, steps, device):
+        self.steps = list(steps)
+        self.device = device
+        self.streams = [torch.cuda.Stream(device) for _ in self.steps]
+        self._next = 0
+
+    def run(self, k):
+        cur = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        for s in self.streams:
+            s.wait_event(ev)
+        last = None
+        for _ in range(k):
+            i = self._next
+            self._next = (i + 1) % len(self.steps)
+            with torch.cuda.stream(self.streams[i]):
+                last = self.steps[i].replay()
+        for s in self.streams:
+            cur.wait_stream(s)
+        return last
+
+
 class MaskRCNNPostBackbone(object):
     def __init__(self, rois_per_image=1000, dets_per_image=100, pre_nms_topk=2000, rpn_nms_thresh=0.7,
                  min_box_side_len=0.0, score_thresh=0.05, nms_thresh=0.5, nms_cls_agnostic=False,
@@ -143,6 +171,10 @@ class MaskRCNNPostBackbone(object):
         with torch.cuda.graph(graph):
             outs = step()
         return GraphedStep(graph, outs, bounds, nv.kernel_launch_count() - l0)
+
+    def pipeline(self, x, chunks=4, depth=2):
+        """`depth` independent captures of the step over the same static inputs `x` -> StepPipeline."""
+        return StepPipeline([self.capture(x, chunks) for _ in range(max(1, int(depth)))], x["shapes"].device)
 
     # ------------------------------------------------------------------ host-buffer step
     @staticmethod

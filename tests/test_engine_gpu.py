@@ -83,3 +83,18 @@ def test_graphed_chunked_step_matches_eager(cuda, chunks):
         torch.cuda.synchronize()
         for k, v in want.items():
             assert torch.equal(got[k], v), (chunks, seed, k)
+
+
+def test_step_pipeline_outputs(cuda):
+    """StepPipeline: two captured steps in flight produce, each, the eager outputs."""
+    N, R, D, K, C = 4, 48, 12, 6, 16
+    eng = MaskRCNNPostBackbone(rois_per_image=R, dets_per_image=D, pre_nms_topk=150)
+    x = _t(_inputs(N, R, K, C, seed=3), cuda)
+    pipe = eng.pipeline(x, chunks=2, depth=2)
+    pipe.run(5)
+    torch.cuda.synchronize()
+    want = eng.flatten_outputs(eng(x))
+    for st in pipe.steps:
+        got = st.gathered()
+        for k, v in want.items():
+            assert torch.equal(got[k], v), k

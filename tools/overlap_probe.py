@@ -79,7 +79,7 @@ def graphed(fn):
 try:
     g1 = graphed(lambda: eng(x))
     res["graph_single_stream_16"] = timeit(g1.replay)
-    for nch, ns, stg in ((2, 2, False), (4, 4, False), (4, 2, False), (8, 4, False), (8, 8, False)):
+    for nch, ns, stg in ((4, 4, False),):
         streams = [torch.cuda.Stream(dev) for _ in range(ns)]
         gg = graphed(lambda: run_chunks(nch, streams, stg))
         res[f"graph_chunks{nch}_streams{ns}_{'staggered' if stg else 'free'}"] = timeit(gg.replay)
@@ -90,4 +90,28 @@ ref = bench.MaskRCNNPostBackbone.flatten_outputs(eng(x)) if hasattr(bench, "Mask
 for nch, ns, stg in ((2, 2, False), (2, 2, True)):
     streams = [torch.cuda.Stream(dev) for _ in range(ns)]
     res[f"chunks{nch}_streams{ns}_{'staggered' if stg else 'free'}"] = timeit(lambda: run_chunks(nch, streams, stg))
+# two (or three) graph instances replayed on alternating streams: consecutive steps overlap
+for depth in (2, 3):
+    gs = [eng.capture(x, chunks=4) for _ in range(depth)]
+    ss = [torch.cuda.Stream(dev) for _ in range(depth)]
+
+    def run_k(K=60):
+        cur = torch.cuda.current_stream(dev)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        for s_ in ss:
+            s_.wait_event(ev)
+        for k in range(K):
+            with torch.cuda.stream(ss[k % depth]):
+                gs[k % depth].replay()
+        for s_ in ss:
+            cur.wait_stream(s_)
+    run_k(6)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_k(60)
+    e1.record()
+    torch.cuda.synchronize()
+    res[f"steps_in_flight_{depth}_ms_per_step"] = e0.elapsed_time(e1) / 60
 print(json.dumps(res))
