@@ -56,7 +56,8 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc, "-ccbin", host] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        extra = os.environ.get("D2B_EXTRA_NVCC", "").split()  # experiments only (e.g. -DD2B_RA_THREADS=128)
+        cmd = [nvcc, "-ccbin", host] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     failed = False
     for src, p in procs:

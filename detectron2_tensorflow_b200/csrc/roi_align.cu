@@ -24,8 +24,11 @@ namespace d2b {
 namespace {
 
 constexpr int kMaxSamples = 128;  // max crop rows / cols per ROI (output * sampling_ratio)
-constexpr int kThreads = 256;
-constexpr int kBinsPerCta = 56;  // 7 bins per warp; larger outputs are split over blockIdx.y
+#ifndef D2B_RA_THREADS
+#define D2B_RA_THREADS 256
+#endif
+constexpr int kThreads = D2B_RA_THREADS;
+constexpr int kBinsPerCta = 56;  // 7 bins per warp (8 warps); larger outputs are split over blockIdx.y
 
 struct Level {
   const void* ptr;
