@@ -11,7 +11,7 @@ slot of the zero-padded dense outputs is pooled, `is_valid` tells which rows are
 
 `run_host` is the host-buffer entry point (the analogue of `sess.run(fetches, feed_dict)`): inputs are host
 tensors, outputs are pinned host tensors.  Images are independent, so the batch is cut into chunks that are
-software-pipelined over two CUDA streams: the upload of chunk i+1, the kernels of chunk i and the download
+software-pipelined over three CUDA streams: the upload of chunk i+1, the kernels of chunk i and the download
 of chunk i-1 overlap (PCIe is full duplex).
 """
 import numpy as np
