@@ -37,55 +37,37 @@ def assign_boxes_to_levels(boxlist, min_level, max_level, canonical_box_size, ca
 
 
 class ROIPooler(Layer):
-    """
-    Region of interest feature map pooler that supports pooling from one or
-    more feature maps.
-    """
+    """Pools ROI features from one map or from an FPN pyramid (poolers.py:52-180): every box is routed to the
+    level `assign_boxes_to_levels` picks and sampled there with ROIAlign -- here in a single kernel launch."""
 
-    def __init__(
-        self,
-        output_size,
-        scales,
-        sampling_ratio,
-        pooler_type,
-        canonical_box_size=224,
-        canonical_level=4,
-    ):
+    _ALIGNED = {"ROIAlign": False, "ROIAlignV2": True}
+
+    def __init__(self, output_size, scales, sampling_ratio, pooler_type, canonical_box_size=224, canonical_level=4):
         super().__init__()
-
-        if isinstance(output_size, int):
-            output_size = (output_size, output_size)
-        assert len(output_size) == 2
-        assert isinstance(output_size[0], int) and isinstance(output_size[1], int)
-        self.output_size = output_size
-
-        if pooler_type == "ROIAlign":
-            self.aligned = False
-        elif pooler_type == "ROIAlignV2":
-            self.aligned = True
-        else:
-            raise ValueError("Unknown pooler type: {}".format(pooler_type))
+        size = (output_size, output_size) if isinstance(output_size, int) else tuple(output_size)
+        if len(size) != 2 or not all(isinstance(v, int) for v in size):
+            raise AssertionError("output_size must be an int or a pair of ints")
+        if pooler_type not in self._ALIGNED:
+            raise ValueError("Unknown pooler type: {}".format(pooler_type))  # same error as poolers.py:118-119
+        self.output_size = size
+        self.aligned = self._ALIGNED[pooler_type]
         self.scales = list(scales)
         self.sampling_ratio = sampling_ratio
-        # kept for API parity with the reference (per-level poolers are not used by call())
-        self.level_poolers = [
-            ROIAlign(output_size, spatial_scale=scale, sampling_ratio=sampling_ratio, aligned=self.aligned)
-            for scale in scales
-        ]
-
-        # Map scale (defined as 1 / stride) to its feature map level under the
-        # assumption that stride is a power of 2.
-        min_level = -math.log2(scales[0])
-        max_level = -math.log2(scales[-1])
-        assert math.isclose(min_level, int(min_level)) and math.isclose(max_level, int(max_level))
-        self.min_level = int(min_level)
-        self.max_level = int(max_level)
-        assert 0 < self.min_level and self.min_level <= self.max_level
-        assert self.min_level <= canonical_level and canonical_level <= self.max_level
+        # API parity only (callers inspect it); `call` never loops over per-level poolers
+        self.level_poolers = [ROIAlign(size, spatial_scale=s, sampling_ratio=sampling_ratio, aligned=self.aligned)
+                              for s in self.scales]
+        # scales are 1/stride with power-of-two strides: level = -log2(scale)  (poolers.py:121-129)
+        lo, hi = -math.log2(self.scales[0]), -math.log2(self.scales[-1])
+        if not (math.isclose(lo, round(lo)) and math.isclose(hi, round(hi))):
+            raise AssertionError("scales must be powers of two")
+        self.min_level, self.max_level = int(round(lo)), int(round(hi))
+        if not (0 < self.min_level <= self.max_level):
+            raise AssertionError("levels must be positive and ascending")
+        if not (self.min_level <= canonical_level <= self.max_level) or canonical_box_size <= 0:
+            raise AssertionError("canonical level / box size out of range")
         self.canonical_level = canonical_level
-        assert canonical_box_size > 0
         self.canonical_box_size = canonical_box_size
-        self.last_level_counts = None  # 'roi_align/num_roi_level_k' summaries (poolers.py:173)
+        self.last_level_counts = None  # per-level ROI counts of the last call ('roi_align/num_roi_level_k', :173)
 
     def call(self, x, instances):
         """

@@ -8,7 +8,25 @@ with an `is_valid` field) follow the reference.
 import torch
 
 
-class BoxList(object):
+class _Trackings(object):
+    """Per-batch side data ("trackings", e.g. image_shape) shared by both containers (box_list.py:30-44, 192-202)."""
+
+    trackings = None
+
+    def get_all_trackings(self):
+        return self.trackings.keys()
+
+    def set_tracking(self, name, value):
+        self.trackings[name] = value
+
+    def get_tracking(self, name):
+        return self.trackings[name]
+
+    def has_tracking(self, name):
+        return name in self.trackings
+
+
+class BoxList(_Trackings):
     """Box list collection."""
 
     def __init__(self, boxes):
@@ -28,18 +46,6 @@ class BoxList(object):
         if boxes.dtype != torch.float32:
             raise ValueError('Invalid tensor type: should be float32')
         self.data['boxes'] = boxes
-
-    def get_all_trackings(self):
-        return self.trackings.keys()
-
-    def set_tracking(self, name, value):
-        self.trackings[name] = value
-
-    def get_tracking(self, name):
-        return self.trackings[name]
-
-    def has_tracking(self, name):
-        return name in self.trackings
 
     def num_boxes(self):
         return self.data['boxes'].shape[0]
@@ -75,7 +81,7 @@ class BoxList(object):
         return boxlist
 
 
-class SparseBoxList(object):
+class SparseBoxList(_Trackings):
     """COO batch -> ragged view of a dense [N, R] BoxList (box_list.py:174-264)."""
 
     def __init__(self, indices, data, dense_shape):
@@ -85,18 +91,6 @@ class SparseBoxList(object):
         assert indices.shape[0] == data.boxes.shape[0]
         self.indices = indices
         self.trackings = {}
-
-    def get_all_trackings(self):
-        return self.trackings.keys()
-
-    def set_tracking(self, name, value):
-        self.trackings[name] = value
-
-    def get_tracking(self, name):
-        return self.trackings[name]
-
-    def has_tracking(self, name):
-        return name in self.trackings
 
     def to_dense(self):
         """box_list.py:204-246: scatter rows to [N, R, ...], zero padding, adds `is_valid`."""
