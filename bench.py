@@ -386,6 +386,7 @@ def run_gpu(args):
                       "steps_in_flight": args.in_flight,
                       "kernels_per_step": gstep.kernels_per_replay,
                       "single_step_latency_ms": step_latency_ms,
+                      "value_one_step_at_a_time": rois_rank * world / (step_latency_ms * 1e-3),
                       "eager_single_stream_ms_per_step": eager_ms,
                       "note": "ms_per_step = time of the K timed steps / K (throughput; consecutive steps are "
                               "independent batches and overlap); single_step_latency_ms = one graph replay at a time; "
