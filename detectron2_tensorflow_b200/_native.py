@@ -154,7 +154,13 @@ class SoloPostprocessParams(C.Structure):
                 ("batch", _i32), ("n", _i32), ("hw", _i64), ("mask_threshold", _f32), ("pre_nms_topk", _i32),
                 ("kernel", _i32), ("sigma", _f32), ("update_score_threshold", _f32), ("max_detections", _i32),
                 ("out_masks", _vp), ("out_packed_masks", _vp), ("out_classes", _vp), ("out_scores", _vp),
-                ("out_valid", _vp), ("out_num", _vp)]
+                ("out_valid", _vp), ("out_num", _vp), ("mask_features", _vp), ("mask_kernels", _vp), ("channels", _i32)]
+
+
+class SoloDynamicMasksParams(C.Structure):
+    _fields_ = [("mask_features", _vp), ("mask_kernels", _vp), ("counts", _vp), ("batch", _i32), ("n", _i32),
+                ("channels", _i32), ("hw", _i64), ("mask_threshold", _f32), ("packed_masks", _vp), ("sum_masks", _vp),
+                ("score_sums", _vp), ("mask_logits", _vp)]
 
 
 class RoiAlignBackwardParams(C.Structure):
@@ -183,6 +189,7 @@ OPS = {
     "point_nms": PointNmsParams,
     "solo_mask_encode": SoloMaskEncodeParams,
     "solo_postprocess": SoloPostprocessParams,
+    "solo_dynamic_masks": SoloDynamicMasksParams,
 }
 EXPORTS = ["d2b_version", "d2b_status_string", "d2b_last_error", "d2b_kernel_launch_count"] + \
           [f"d2b_{op}{sfx}" for op in OPS for sfx in ("", "_workspace_bytes")]

@@ -38,4 +38,7 @@ size_t nms_sorted_workspace_bytes(int S, int n, int max_out);
 int nms_sorted(const float* boxes, const int32_t* counts, int S, int n, int max_out, float thr, int32_t* keep,
                int32_t* num_keep, void* ws, cudaStream_t st);
 
+// ---------------------------------------------------------------- SOLOv2 dynamic conv (solo_dynconv.cu)
+size_t solo_dynamic_masks_ws(int batch, int n, int channels);
+
 }  // namespace d2b

@@ -239,7 +239,8 @@ __global__ void __launch_bounds__(256) solo_unpack_kernel(const u64* packed2, co
 struct SoloPlan {
   int P, kcap, Wd;
   size_t bytes, o_packed, o_sum, o_ssum, o_resc, o_keys, o_nvalid, o_kcount, o_packed2, o_sum2, o_cls2, o_sc2, o_upd,
-      o_src, o_mnms;
+      o_src, o_mnms, o_dyn, dyn_bytes;
+  bool dynamic;
   d2b_matrix_nms_params mp;
 };
 int solo_plan(const d2b_solo_postprocess_params* p, SoloPlan& pl) {
@@ -271,6 +272,16 @@ int solo_plan(const d2b_solo_postprocess_params* p, SoloPlan& pl) {
   pl.o_sc2 = o; o += ws_slice(B * kc * 4);
   pl.o_upd = o; o += ws_slice(B * kc * 4);
   pl.o_src = o; o += ws_slice(B * D * 4);
+  // masks from the dynamic conv (solo_v2.py:499-511) when no logits are given
+  pl.dynamic = p->mask_logits == nullptr && p->mask_features != nullptr;
+  pl.o_dyn = o;
+  pl.dyn_bytes = 0;
+  if (pl.dynamic) {
+    D2B_REQUIRE(p->channels >= 4 && p->channels % 4 == 0 && p->channels <= 4096,
+                "solo_postprocess: channels=%d must be a multiple of 4 in [4, 4096]", p->channels);
+    pl.dyn_bytes = solo_dynamic_masks_ws(p->batch, p->n, p->channels);
+    o += pl.dyn_bytes;
+  }
   pl.o_mnms = o;
   pl.mp = d2b_matrix_nms_params();
   pl.mp.batch = p->batch; pl.mp.n = pl.kcap; pl.mp.hw = p->hw; pl.mp.kernel = p->kernel; pl.mp.sigma = p->sigma;
@@ -360,7 +371,8 @@ extern "C" int d2b_solo_postprocess(const d2b_solo_postprocess_params* p, void* 
   if (rc != D2B_OK) return rc;
   if (p->batch == 0) return D2B_OK;
   D2B_REQUIRE(p->out_classes && p->out_scores && p->out_valid, "solo_postprocess: NULL output");
-  D2B_REQUIRE(p->n == 0 || (p->mask_logits && p->scores && p->classes && p->strides), "solo_postprocess: NULL input");
+  D2B_REQUIRE(p->n == 0 || ((p->mask_logits || (p->mask_features && p->mask_kernels)) && p->scores && p->classes && p->strides),
+              "solo_postprocess: NULL input");
   if (workspace == nullptr || workspace_bytes < pl.bytes) {
     set_last_error("solo_postprocess needs %zu workspace bytes", pl.bytes);
     return D2B_EWORKSPACE;
@@ -384,11 +396,20 @@ extern "C" int d2b_solo_postprocess(const d2b_solo_postprocess_params* p, void* 
   D2B_CUDA(cudaMemsetAsync(nvalid, 0, sizeof(int32_t) * B, st));
   D2B_CUDA(cudaMemsetAsync(kcount, 0, sizeof(int32_t) * B, st));
   if (n > 0 && p->hw > 0) {
-    d2b_solo_mask_encode_params e = {};
-    e.mask_logits = p->mask_logits; e.counts = p->counts; e.batch = B; e.n = n; e.hw = p->hw;
-    e.mask_threshold = p->mask_threshold;
-    e.packed_masks = reinterpret_cast<uint64_t*>(packed); e.sum_masks = sum_masks; e.score_sums = score_sums;
-    rc = d2b_solo_mask_encode(&e, nullptr, 0, stream);
+    if (pl.dynamic) {
+      d2b_solo_dynamic_masks_params e = {};
+      e.mask_features = p->mask_features; e.mask_kernels = p->mask_kernels; e.counts = p->counts;
+      e.batch = B; e.n = n; e.channels = p->channels; e.hw = p->hw;
+      e.mask_threshold = p->mask_threshold;
+      e.packed_masks = reinterpret_cast<uint64_t*>(packed); e.sum_masks = sum_masks; e.score_sums = score_sums;
+      rc = d2b_solo_dynamic_masks(&e, ws + pl.o_dyn, pl.dyn_bytes, stream);
+    } else {
+      d2b_solo_mask_encode_params e = {};
+      e.mask_logits = p->mask_logits; e.counts = p->counts; e.batch = B; e.n = n; e.hw = p->hw;
+      e.mask_threshold = p->mask_threshold;
+      e.packed_masks = reinterpret_cast<uint64_t*>(packed); e.sum_masks = sum_masks; e.score_sums = score_sums;
+      rc = d2b_solo_mask_encode(&e, nullptr, 0, stream);
+    }
     if (rc != D2B_OK) return rc;
     solo_score_kernel<<<dim3((P + 255) / 256, B), 256, 0, st>>>(p->scores, p->strides, sum_masks, score_sums, p->counts,
                                                                n, P, keys, rescored, nvalid);

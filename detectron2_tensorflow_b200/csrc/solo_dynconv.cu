@@ -1,0 +1,500 @@
+// solo_dynconv.cu -- SOLOv2 mask generation fused with the mask stage (SURVEY.md 8f "next" #4):
+//   solo_v2.py:499-517, 530-533   mask_logits = conv2d(mask_features, pred_kernels 1x1)  ->  sigmoid  ->  > thr
+//                                 -> sum_masks, sum(scores * masks)
+// The 1x1 "dynamic convolution" is a GEMM per image:  logits[n, HW] = kernels[n, E] . features[HW, E]^T.  It is the
+// one contraction on the path, so it runs on the 5th-generation tensor cores:
+//   * tcgen05.mma kind::tf32, M=128 (mask kernels) x N=256 (pixels) x K=8, accumulators in TMEM (2 x 256 columns,
+//     double buffered), operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) through an mbarrier ring;
+//   * fp32 accuracy from three tf32 products per k-step (3xTF32: a = a_hi + a_lo with both halves tf32-exact,
+//     D += a_lo.b_hi + a_hi.b_lo + a_hi.b_hi): the kernels are split once by a tiny prologue kernel, the feature tile
+//     is split in shared memory by four converter warps between the TMA and the MMA (elementwise, so the swizzled
+//     layout is preserved), published to the async proxy with fence.proxy.async;
+//   * epilogue warps read the accumulators with tcgen05.ld (thread = one mask row, 32 consecutive pixels per load),
+//     take the threshold decision with the bit-exact sigmoid rule of solo_encode_kernel and emit BIT-PACKED masks,
+//     exact mask sums and the score sums -- the 4 B/pixel logits (134 MB per image at 500 x 200 x 336) never exist.
+// Persistent: one CTA per SM walks a contiguous range of (image, row block, pixel tile) tiles.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM owner), 2-5 = converters, 6-9 = epilogue.
+#include <cuda.h>
+#include <math.h>
+
+#include "kernels.cuh"
+
+namespace d2b {
+namespace {
+typedef unsigned long long u64;
+
+constexpr int kBM = 128;   // mask kernels per tile (UMMA M, = TMEM lanes)
+constexpr int kBN = 256;   // pixels per tile (UMMA N, = TMEM columns of one accumulator)
+constexpr int kBK = 32;    // fp32 per 128-byte swizzle row
+constexpr int kUmmaK = 8;  // tf32 MMA depth
+constexpr int kStages = 2;
+constexpr uint32_t kABytes = kBM * kBK * 4;                   // 16 KB
+constexpr uint32_t kBBytes = kBN * kBK * 4;                   // 32 KB
+constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // A_hi, A_lo, B (raw -> hi in place), B_lo
+constexpr uint32_t kTxBytes = 2 * kABytes + kBBytes;          // what the TMA writes per stage
+constexpr int kThreads = 320;
+constexpr int kCvtThreads = 128, kEpiThreads = 128;
+constexpr uint32_t kTmemCols = 512;
+constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + 256;
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+
+struct DynArgs {
+  const int32_t* counts;
+  int B, n, E, RB, PT, KB;
+  long long hw;
+  int Wd;
+  float thr, lo, hi;
+  u64* packed;
+  float* sum_masks;
+  float* score_sums;
+  float* logits;  // optional
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (unsigned spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((spin & 1023u) == 1023u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();  // ~2 s
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// K-major operand tile, 128-byte swizzle: 8-row groups 1024 B apart (SBO), LBO unused (1), descriptor version 1
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
+  h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+  l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y); l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
+}
+
+// kernels [B*n*E] -> hi / lo halves (both exactly representable in tf32)
+__global__ void dyn_split_kernel(const float4* x, float4* hi, float4* lo, long long total4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  float4 h, l;
+  split4(__ldg(x + i), h, l);
+  hi[i] = h;
+  lo[i] = l;
+}
+
+struct TileIter {  // every role walks the same tile sequence
+  long long t, t_end;
+  int b, rb, pt;
+  const DynArgs& a;
+  __device__ TileIter(const DynArgs& a_) : a(a_) {
+    const long long total = (long long)a.B * a.RB * a.PT;
+    t = total * blockIdx.x / gridDim.x - 1;
+    t_end = total * (blockIdx.x + 1) / gridDim.x;
+  }
+  __device__ bool next() {
+    for (;;) {
+      if (++t >= t_end) return false;
+      pt = (int)(t % a.PT);
+      const long long r = t / a.PT;
+      rb = (int)(r % a.RB);
+      b = (int)(r / a.RB);
+      const int cnt = a.counts ? min(a.counts[b], a.n) : a.n;
+      if (rb * kBM < cnt) return true;  // row blocks past the valid prefix have no work (their words are pre-zeroed)
+    }
+  }
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
+                    const __grid_constant__ CUtensorMap tm_feat, const DynArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-byte alignment
+  const uint32_t bars = base + kStages * kStageBytes;
+  // barrier slots (8 B each): full_raw[s], full_cvt[s], empty[s], tmem_full[2], tmem_empty[2], then the TMEM address
+  auto full_raw = [&](int s) { return bars + 8u * s; };
+  auto full_cvt = [&](int s) { return bars + 8u * (kStages + s); };
+  auto empty = [&](int s) { return bars + 8u * (2 * kStages + s); };
+  auto tmem_full = [&](int s) { return bars + 8u * (3 * kStages + s); };
+  auto tmem_empty = [&](int s) { return bars + 8u * (3 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (3 * kStages + 4);
+  auto sA_hi = [&](int s) { return base + s * kStageBytes; };
+  auto sA_lo = [&](int s) { return base + s * kStageBytes + kABytes; };
+  auto sB_hi = [&](int s) { return base + s * kStageBytes + 2 * kABytes; };
+  auto sB_lo = [&](int s) { return base + s * kStageBytes + 2 * kABytes + kBBytes; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_raw(s), 1);
+      mbar_init(full_cvt(s), kCvtThreads);
+      mbar_init(empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tmem_full(s), 1);
+      mbar_init(tmem_empty(s), kEpiThreads);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: the whole 512 columns (one CTA per SM by shared-memory footprint)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      TileIter it(a);
+      int s = 0;
+      uint32_t ph = 0;
+      while (it.next()) {
+        for (int kb = 0; kb < a.KB; ++kb) {
+          mbar_wait(empty(s), ph ^ 1u);
+          mbar_expect_tx(full_raw(s), kTxBytes);
+          tma_load_3d(sA_hi(s), &tm_ahi, full_raw(s), kb * kBK, it.rb * kBM, it.b);
+          tma_load_3d(sA_lo(s), &tm_alo, full_raw(s), kb * kBK, it.rb * kBM, it.b);
+          tma_load_3d(sB_hi(s), &tm_feat, full_raw(s), kb * kBK, it.pt * kBN, it.b);
+          if (++s == kStages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      TileIter it(a);
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t n_tile = 0;
+      while (it.next()) {
+        const uint32_t as = n_tile & 1u, aph = (n_tile >> 1) & 1u;
+        ++n_tile;
+        mbar_wait(tmem_empty(as), aph ^ 1u);  // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem_base + as * kBN;
+        for (int kb = 0; kb < a.KB; ++kb) {
+          mbar_wait(full_raw(s), ph);
+          mbar_wait(full_cvt(s), ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint32_t ko = k * kUmmaK * 4;  // bytes along K inside the 128-byte swizzle row
+            const uint64_t ahi = umma_desc(sA_hi(s) + ko), alo = umma_desc(sA_lo(s) + ko);
+            const uint64_t bhi = umma_desc(sB_hi(s) + ko), blo = umma_desc(sB_lo(s) + ko);
+            umma_tf32(d, alo, bhi, (kb | k) != 0);  // small terms first
+            umma_tf32(d, ahi, blo, 1u);
+            umma_tf32(d, ahi, bhi, 1u);
+          }
+          umma_commit(empty(s));  // implies tcgen05.fence::before_thread_sync
+          if (++s == kStages) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(tmem_full(as));
+      }
+    }
+  } else if (warp < 6) {
+    // ===================================================== converters: feature tile -> tf32 hi (in place) + lo
+    const int tid = threadIdx.x - 64;
+    TileIter it(a);
+    int s = 0;
+    uint32_t ph = 0;
+    while (it.next()) {
+      for (int kb = 0; kb < a.KB; ++kb) {
+        mbar_wait(full_raw(s), ph);
+        const uint32_t src = sB_hi(s), dst = sB_lo(s);
+#pragma unroll 4
+        for (int i = tid; i < (int)(kBBytes / 16); i += kCvtThreads) {
+          float4 v, h, l;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + 16u * i));
+          split4(v, h, l);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src + 16u * i), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u * i), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(full_cvt(s));
+        if (++s == kStages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ===================================================== epilogue: TMEM -> threshold -> packed bits + sums
+    const int q = warp & 3;  // a warp may only touch TMEM lanes 32*(warp % 4) .. +31
+    const int row_in_tile = q * 32 + lane;
+    TileIter it(a);
+    uint32_t n_tile = 0;
+    int cur_b = -1, cur_rb = -1;
+    unsigned acc_cnt = 0;
+    float acc_score = 0.0f;
+    auto flush = [&]() {
+      if (cur_b >= 0) {
+        const int row = cur_rb * kBM + row_in_tile;
+        if (acc_cnt) atomicAdd(a.sum_masks + (size_t)cur_b * a.n + row, (float)acc_cnt);  // integer valued < 2^24: exact
+        if (acc_score != 0.0f) atomicAdd(a.score_sums + (size_t)cur_b * a.n + row, acc_score);
+      }
+      acc_cnt = 0;
+      acc_score = 0.0f;
+    };
+    while (it.next()) {
+      const uint32_t as = n_tile & 1u, aph = (n_tile >> 1) & 1u;
+      ++n_tile;
+      if (it.b != cur_b || it.rb != cur_rb) {
+        flush();
+        cur_b = it.b;
+        cur_rb = it.rb;
+      }
+      const int cnt = a.counts ? min(a.counts[it.b], a.n) : a.n;
+      const int row = it.rb * kBM + row_in_tile;
+      const bool live = row < cnt;
+      mbar_wait(tmem_full(as), aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * kBN;
+      const long long p0 = (long long)it.pt * kBN;
+      u64 words[kBN / 64];
+#pragma unroll
+      for (int c = 0; c < kBN / 32; ++c) {
+        uint32_t r[32];
+        __syncwarp();  // .sync.aligned: the whole warp issues the load together
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr + c * 32)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t bits = 0;
+        const long long pc = p0 + c * 32;
+        if (live) {
+          if (a.logits) {
+            float* lg = a.logits + ((size_t)it.b * a.n + row) * a.hw;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (pc + j < a.hw) lg[pc + j] = __uint_as_float(r[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(r[j]);
+            // sigmoid(x) > thr: decided on x outside the guard band around logit(thr), by the exact sigmoid inside
+            if (x >= a.lo && pc + j < a.hw) {
+              const float sg = d2b_sigmoidf(x);
+              const bool on = (x > a.hi) ? true : (sg > a.thr);
+              if (on) {
+                bits |= 1u << j;
+                acc_score = acc_score + sg;
+              }
+            }
+          }
+        }
+        acc_cnt += __popc(bits);
+        if (c & 1) words[c >> 1] |= (u64)bits << 32;
+        else words[c >> 1] = (u64)bits;
+      }
+      // the accumulator is in registers / consumed: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(tmem_empty(as));
+      if (live) {
+        u64* dstw = a.packed + ((size_t)it.b * a.n + row) * a.Wd;
+#pragma unroll
+        for (int w = 0; w < kBN / 64; ++w) {
+          const int word = it.pt * (kBN / 64) + w;
+          if (word < a.Wd) dstw[word] = words[w];
+        }
+      }
+    }
+    flush();
+  }
+
+  // ------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// [batch, rows, E] fp32, E contiguous -> 3-D map with a (32 x box_rows x 1) box, 128-byte swizzle, zero OOB fill
+int make_map(CUtensorMap* m, const void* ptr, int E, long long rows, int batch, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled is not available from the driver");
+    return D2B_ECUDA;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)E, (cuuint64_t)rows, (cuuint64_t)batch};
+  const cuuint64_t strides[2] = {(cuuint64_t)E * 4, (cuuint64_t)rows * E * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (E=%d rows=%lld batch=%d)", (int)r, E, rows, batch);
+    return D2B_ECUDA;
+  }
+  return D2B_OK;
+}
+
+int dyn_check(const d2b_solo_dynamic_masks_params* p) {
+  D2B_REQUIRE(p != nullptr, "params is NULL");
+  D2B_REQUIRE(p->batch >= 0 && p->n >= 0 && p->hw >= 0 && p->channels >= 0, "solo_dynamic_masks: negative sizes");
+  D2B_REQUIRE(p->n <= 65535 && p->batch <= 65535, "solo_dynamic_masks: n / batch too large");
+  D2B_REQUIRE(p->hw < (1ll << 24), "solo_dynamic_masks: hw=%lld >= 2^24 (mask sums must stay exact in fp32)", (long long)p->hw);
+  D2B_REQUIRE(p->channels % 4 == 0 && p->channels >= 4 && p->channels <= 4096,
+              "solo_dynamic_masks: channels=%d must be a multiple of 4 in [4, 4096] (16-byte TMA rows)", p->channels);
+  return D2B_OK;
+}
+}  // namespace
+
+size_t solo_dynamic_masks_ws(int batch, int n, int channels) {
+  return 2 * ws_slice((size_t)batch * (n > 0 ? n : 1) * channels * 4);
+}
+}  // namespace d2b
+
+using namespace d2b;
+
+extern "C" size_t d2b_solo_dynamic_masks_workspace_bytes(const d2b_solo_dynamic_masks_params* p) {
+  if (dyn_check(p) != D2B_OK) return 0;
+  return solo_dynamic_masks_ws(p->batch, p->n, p->channels);
+}
+
+extern "C" int d2b_solo_dynamic_masks(const d2b_solo_dynamic_masks_params* p, void* workspace, size_t workspace_bytes,
+                                      d2b_stream_t stream) {
+  int rc = dyn_check(p);
+  if (rc != D2B_OK) return rc;
+  if (p->batch == 0 || p->n == 0) return D2B_OK;
+  D2B_REQUIRE(p->packed_masks && p->sum_masks && p->score_sums, "solo_dynamic_masks: NULL output");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t rows = (size_t)p->batch * p->n;
+  D2B_CUDA(cudaMemsetAsync(p->sum_masks, 0, sizeof(float) * rows, st));
+  D2B_CUDA(cudaMemsetAsync(p->score_sums, 0, sizeof(float) * rows, st));
+  if (p->hw == 0) return D2B_OK;
+  D2B_REQUIRE(p->mask_features && p->mask_kernels, "solo_dynamic_masks: NULL input");
+  D2B_REQUIRE((reinterpret_cast<uintptr_t>(p->mask_features) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->mask_kernels) & 15) == 0,
+              "solo_dynamic_masks: inputs must be 16-byte aligned");
+  const size_t need = solo_dynamic_masks_ws(p->batch, p->n, p->channels);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_last_error("solo_dynamic_masks needs %zu workspace bytes", need);
+    return D2B_EWORKSPACE;
+  }
+  const int E = p->channels;
+  Workspace ws(workspace);
+  float* a_hi = ws.take<float>(rows * E);
+  float* a_lo = ws.take<float>(rows * E);
+
+  DynArgs a;
+  a.counts = p->counts; a.B = p->batch; a.n = p->n; a.E = E; a.hw = p->hw;
+  a.RB = (p->n + kBM - 1) / kBM;
+  a.PT = (int)((p->hw + kBN - 1) / kBN);
+  a.KB = (E + kBK - 1) / kBK;
+  a.Wd = (int)((p->hw + 63) / 64);
+  a.thr = p->mask_threshold;
+  const double t = (double)p->mask_threshold;  // same guard band as solo_encode_kernel
+  if (t > 1e-3 && t < 1.0 - 1e-3) {
+    const double x0 = log(t / (1.0 - t));
+    const double d = 1e-3 * (fabs(x0) > 1.0 ? fabs(x0) : 1.0);
+    a.lo = (float)(x0 - d);
+    a.hi = (float)(x0 + d);
+  } else {
+    a.lo = -INFINITY;
+    a.hi = INFINITY;
+  }
+  a.packed = reinterpret_cast<u64*>(p->packed_masks);
+  a.sum_masks = p->sum_masks;
+  a.score_sums = p->score_sums;
+  a.logits = p->mask_logits;
+
+  // rows past the valid prefix / row blocks without work keep defined (empty) masks
+  if (p->counts) D2B_CUDA(cudaMemsetAsync(p->packed_masks, 0, sizeof(u64) * rows * a.Wd, st));
+
+  CUtensorMap tm_ahi, tm_alo, tm_feat;
+  if ((rc = make_map(&tm_ahi, a_hi, E, p->n, p->batch, kBM)) != D2B_OK) return rc;
+  if ((rc = make_map(&tm_alo, a_lo, E, p->n, p->batch, kBM)) != D2B_OK) return rc;
+  if ((rc = make_map(&tm_feat, p->mask_features, E, p->hw, p->batch, kBN)) != D2B_OK) return rc;
+
+  const long long total4 = (long long)rows * E / 4;
+  dyn_split_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(p->mask_kernels),
+                                                                     reinterpret_cast<float4*>(a_hi),
+                                                                     reinterpret_cast<float4*>(a_lo), total4);
+  D2B_LAUNCH_CHECK();
+
+  static int sm_count[64] = {0};
+  int dev = 0;
+  D2B_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && sm_count[dev] == 0) {
+    int v = 0;
+    D2B_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    sm_count[dev] = v > 0 ? v : 148;
+  }
+  const int sms = (dev >= 0 && dev < 64) ? sm_count[dev] : 148;
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    D2B_CUDA(cudaFuncSetAttribute(solo_dynconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const long long tiles = (long long)a.B * a.RB * a.PT;
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  solo_dynconv_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm_ahi, tm_alo, tm_feat, a);
+  D2B_LAUNCH_CHECK();
+  return D2B_OK;
+}

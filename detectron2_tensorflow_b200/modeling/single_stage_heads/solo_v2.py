@@ -3,7 +3,7 @@ import torch
 
 from ... import _native as nv
 
-__all__ = ["point_nms", "solo_mask_encode", "SOLOv2Inference"]
+__all__ = ["point_nms", "solo_mask_encode", "solo_dynamic_masks", "SOLOv2Inference"]
 
 
 def point_nms(inputs, kernel_size=2, scope=None):
@@ -55,6 +55,40 @@ def solo_mask_encode(mask_logits, mask_threshold=0.5, counts=None):
     return tuple(nv.to_host(o) for o in outs) if host else outs
 
 
+def solo_dynamic_masks(mask_features, mask_kernels, mask_threshold=0.5, counts=None, return_logits=False):
+    """Dynamic mask generation + mask stage of SOLOv2Head.inference (solo_v2.py:499-517, 530-533) in ONE kernel.
+
+    mask_features [B, H, W, E] (NHWC, the mask branch output); mask_kernels [B, n, E] (the `pred_kernels` rows of the
+    candidates that passed the score threshold, :486).  The 1x1 conv is a per-image GEMM on the tcgen05 tensor cores
+    (3 x tf32 = fp32-accurate); its epilogue thresholds the sigmoid and emits bit-packed masks, so the [B, n, H, W]
+    logits are never written unless `return_logits` asks for them.
+    Returns (packed_masks int64 [B, n, ceil(HW/64)], sum_masks [B, n], score_sums [B, n][, logits [B, n, H, W]]).
+    """
+    host = not mask_features.is_cuda
+    dev = nv.device_of(mask_features)
+    f = nv.to_device(mask_features, dev, torch.float32)
+    k = nv.to_device(mask_kernels, dev, torch.float32)
+    assert f.dim() == 4 and k.dim() == 3 and k.shape[0] == f.shape[0] and k.shape[2] == f.shape[3]
+    B, H, W, E = f.shape
+    n = k.shape[1]
+    hw = H * W
+    Wd = (hw + 63) // 64
+    packed = torch.empty((B, n, Wd), dtype=torch.int64, device=dev)
+    sums = torch.empty((B, n), dtype=torch.float32, device=dev)
+    ssum = torch.empty((B, n), dtype=torch.float32, device=dev)
+    logits = torch.zeros((B, n, H, W), dtype=torch.float32, device=dev) if return_logits else None
+    cnt = None if counts is None else nv.to_device(counts, dev, torch.int32)
+    p = nv.SoloDynamicMasksParams()
+    p.mask_features, p.mask_kernels, p.counts = f.data_ptr(), k.data_ptr(), nv.ptr(cnt)
+    p.batch, p.n, p.channels, p.hw = B, n, E, hw
+    p.mask_threshold = float(mask_threshold)
+    p.packed_masks, p.sum_masks, p.score_sums = packed.data_ptr(), sums.data_ptr(), ssum.data_ptr()
+    p.mask_logits = nv.ptr(logits)
+    nv.call("solo_dynamic_masks", p, dev)
+    outs = (packed, sums, ssum) + ((logits,) if return_logits else ())
+    return tuple(nv.to_host(o) for o in outs) if host else outs
+
+
 class SOLOv2Inference(object):
     """The tail of `SOLOv2Head.inference` after the dynamic convolution (solo_v2.py:507-558), batched: mask stage,
     `sum_masks > strides` filter, mask scoring, top-k, Matrix-NMS on bit-packed masks, score filter, pad / clip.
@@ -71,16 +105,28 @@ class SOLOv2Inference(object):
         self.update_score_threshold = update_score_threshold
         self.max_detections_per_image = max_detections_per_image
 
-    def postprocess(self, mask_logits, scores, classes, strides, counts=None, return_masks=True):
+    def postprocess(self, mask_logits, scores, classes, strides, counts=None, return_masks=True, mask_features=None,
+                    mask_kernels=None):
         """mask_logits [B, n, H, W]: conv output of each image's candidates (those with score > score_threshold, in
         `tf.where` order; rows >= counts[b] are padding); scores / classes / strides [B, n].
+        With mask_logits=None the masks come from the fused dynamic conv instead (`solo_dynamic_masks`):
+        mask_features [B, H, W, E] and mask_kernels [B, n, E].
         Returns dict(pred_masks fp32 0/1 [B, D, H, W] (or None), packed_masks int64 [B, D, ceil(HW/64)],
         pred_classes int64 [B, D], scores [B, D], is_valid [B, D], num [B])."""
-        host = not mask_logits.is_cuda
-        dev = nv.device_of(mask_logits)
-        x = nv.to_device(mask_logits, dev, torch.float32)
-        assert x.dim() == 4
-        B, n, H, W = x.shape
+        src = mask_logits if mask_logits is not None else mask_features
+        host = not src.is_cuda
+        dev = nv.device_of(src)
+        feat = kern = x = None
+        if mask_logits is not None:
+            x = nv.to_device(mask_logits, dev, torch.float32)
+            assert x.dim() == 4
+            B, n, H, W = x.shape
+        else:
+            feat = nv.to_device(mask_features, dev, torch.float32)
+            kern = nv.to_device(mask_kernels, dev, torch.float32)
+            assert feat.dim() == 4 and kern.dim() == 3 and kern.shape[0] == feat.shape[0] and kern.shape[2] == feat.shape[3]
+            B, H, W, _ = feat.shape
+            n = kern.shape[1]
         hw = H * W
         D = int(self.max_detections_per_image)
         sc = nv.to_device(scores, dev, torch.float32).reshape(B, n)
@@ -95,7 +141,9 @@ class SOLOv2Inference(object):
         ov = torch.empty((B, D), dtype=torch.bool, device=dev)
         num = torch.empty(B, dtype=torch.int32, device=dev)
         p = nv.SoloPostprocessParams()
-        p.mask_logits, p.scores, p.classes, p.strides = x.data_ptr(), sc.data_ptr(), cl.data_ptr(), stv.data_ptr()
+        p.mask_logits, p.scores, p.classes, p.strides = nv.ptr(x), sc.data_ptr(), cl.data_ptr(), stv.data_ptr()
+        p.mask_features, p.mask_kernels = nv.ptr(feat), nv.ptr(kern)
+        p.channels = 0 if feat is None else int(feat.shape[3])
         p.counts = nv.ptr(cnt)
         p.batch, p.n, p.hw = B, n, hw
         p.mask_threshold, p.pre_nms_topk = float(self.mask_threshold), int(self.pre_nms_topk)

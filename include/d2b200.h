@@ -539,6 +539,32 @@ D2B_API int d2b_solo_mask_encode(const d2b_solo_mask_encode_params* p, void* wor
                                  d2b_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * SOLOv2 dynamic mask generation fused with the mask stage
+ *                          lib/modeling/single_stage_heads/solo_v2.py:499-517, 530-533
+ *   pred_mask_logits = conv2d(pred_mask_features [1,H,W,E], pred_kernels as [1,1,E,n])   (a GEMM per image)
+ *   then exactly d2b_solo_mask_encode: sigmoid -> > mask_threshold -> bit-pack, sum_masks, score_sums.
+ * tcgen05 (tf32 x 3 = fp32-accurate) tensor-core kernel whose epilogue emits the packed masks, so the
+ * [B, n, hw] fp32 logits are never written (pass mask_logits != NULL only to inspect them).
+ * Floating point: a logit differs from the sequential fp32 sum by <= 2e-6 * sum_k |kernel_k * feature_k|
+ * (tests/test_solo_dynconv_gpu.py); mask bits can differ only where the logit is that close to logit(threshold).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* mask_features; /* [B, hw, E] NHWC, 16-byte aligned */
+  const float* mask_kernels;  /* [B, n, E]: pred_kernels rows gathered by keep_inds (:486) */
+  const int32_t* counts;      /* optional [B]: valid prefix per image */
+  int32_t batch, n, channels; /* channels = E, a multiple of 4 */
+  int64_t hw;
+  float mask_threshold;
+  uint64_t* packed_masks; /* [B, n, ceil(hw/64)] */
+  float* sum_masks;       /* [B, n] */
+  float* score_sums;      /* [B, n] */
+  float* mask_logits;     /* optional [B, n, hw] */
+} d2b_solo_dynamic_masks_params;
+D2B_API size_t d2b_solo_dynamic_masks_workspace_bytes(const d2b_solo_dynamic_masks_params* p);
+D2B_API int d2b_solo_dynamic_masks(const d2b_solo_dynamic_masks_params* p, void* workspace, size_t workspace_bytes,
+                                   d2b_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * SOLOv2Head.inference tail after the dynamic conv          solo_v2.py:507-558
  * Per image b (B images per call, the reference's tf.map_fn at :587): the first counts[b] of the n rows are
  * the candidates that passed the score threshold, in tf.where order.
@@ -568,6 +594,10 @@ typedef struct {
   float* out_scores;          /* [B, max_det] */
   uint8_t* out_valid;         /* [B, max_det] */
   int32_t* out_num;           /* optional [B] */
+  /* When mask_logits is NULL the masks come from the dynamic conv (d2b_solo_dynamic_masks) instead: */
+  const float* mask_features; /* [B, hw, E] */
+  const float* mask_kernels;  /* [B, n, E] */
+  int32_t channels;
 } d2b_solo_postprocess_params;
 D2B_API size_t d2b_solo_postprocess_workspace_bytes(const d2b_solo_postprocess_params* p);
 D2B_API int d2b_solo_postprocess(const d2b_solo_postprocess_params* p, void* workspace, size_t workspace_bytes,

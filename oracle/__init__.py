@@ -426,6 +426,20 @@ def solo_mask_stage(logits, mask_threshold=0.5):
     return masks, sm, ss
 
 
+def solo_dynamic_conv(features, kernels):
+    """solo_v2.py:499-511 for one image: features [H,W,E] (or [hw,E]), kernels [n,E] -> (logits [n,hw],
+    absum [n,hw] = sum_k |kernel_k * feature_k|, the scale of the GPU tolerance)."""
+    f = _f32(features)
+    E = f.shape[-1]
+    f = f.reshape(-1, E)
+    k = _f32(kernels).reshape(-1, E)
+    n, hw = k.shape[0], f.shape[0]
+    out = np.empty((n, hw), np.float32)
+    ab = np.empty((n, hw), np.float32)
+    lib().orc_solo_dynamic_conv(_p(f), _p(k), C.c_int64(n), C.c_int64(hw), C.c_int64(E), _p(out), _p(ab))
+    return out, ab
+
+
 def sigmoid_array(x):
     """Elementwise orc_sigmoidf over an array (same function as `sigmoidf`, without the Python loop)."""
     x = _f32(x)

@@ -1167,6 +1167,29 @@ ORC_API void orc_solo_mask_stage(const float* logits, int64_t n, int64_t hw, flo
   }
 }
 
+/* lib/modeling/single_stage_heads/solo_v2.py:499-511 (dynamic mask generation): tf.nn.conv2d of the mask features
+ * [1, H, W, E] with the candidates' kernels reshaped to [1, 1, E, n], VALID, stride 1 -- per pixel a dot product over
+ * E.  fp32, one multiply and one add per term in channel order (TF's CPU conv is an Eigen contraction whose summation
+ * order is blocked and unspecified; GPU parity for this op is a tolerance, stated in the test).  Also returns
+ * sum_k |kernel_k * feature_k| per output, the scale the tolerance is relative to.
+ * features [hw, E], kernels [n, E] -> logits [n, hw], absum [n, hw] (optional). */
+ORC_API void orc_solo_dynamic_conv(const float* features, const float* kernels, int64_t n, int64_t hw, int64_t E,
+                                   float* logits, float* absum) {
+#pragma omp parallel for num_threads(ORC_NT) schedule(static)
+  for (int64_t i = 0; i < n; ++i)
+    for (int64_t p = 0; p < hw; ++p) {
+      float acc = 0.0f;
+      double ab = 0.0;
+      for (int64_t k = 0; k < E; ++k) {
+        const float prod = kernels[i * E + k] * features[p * E + k];
+        acc = acc + prod;
+        ab += fabs((double)prod);
+      }
+      logits[i * hw + p] = acc;
+      if (absum) absum[i * hw + p] = (float)ab;
+    }
+}
+
 /* vectorised orc_sigmoidf (test convenience) */
 ORC_API void orc_sigmoid_array(const float* x, int64_t n, float* out) {
 #pragma omp parallel for num_threads(ORC_NT) schedule(static)

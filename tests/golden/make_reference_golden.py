@@ -283,6 +283,7 @@ def main(out_path=None):
     so_logits = np.zeros((Nimg, ncap, Hm, Wm), np.float32)
     so_sc, so_cl, so_st = np.zeros((Nimg, ncap), np.float32), np.zeros((Nimg, ncap), np.int64), np.ones((Nimg, ncap), np.float32)
     so_cnt = np.zeros(Nimg, np.int32)
+    so_kern = np.zeros((Nimg, ncap, E), np.float32)  # the gathered pred_kernels (:486): input of the fused dynamic conv
     for i in range(Nimg):
         keep = np.argwhere(flat_p[i] > 0.3)
         c_ = keep.shape[0]
@@ -290,8 +291,10 @@ def main(out_path=None):
         so_sc[i, :c_] = flat_p[i][keep[:, 0], keep[:, 1]]
         so_cl[i, :c_] = keep[:, 1]
         so_st[i, :c_] = cell_stride[keep[:, 0]]
+        so_kern[i, :c_] = flat_k[i][keep[:, 0]]
         so_logits[i, :c_] = np.einsum("nhwc,co->nhwo", mfeat[i:i + 1], flat_k[i][keep[:, 0]].T.copy())[0].transpose(2, 0, 1)
-    out.update(so_in_logits=so_logits, so_in_scores=so_sc, so_in_classes=so_cl, so_in_strides=so_st, so_in_counts=so_cnt)
+    out.update(so_in_logits=so_logits, so_in_scores=so_sc, so_in_classes=so_cl, so_in_strides=so_st, so_in_counts=so_cnt,
+               so_in_mask_features=mfeat, so_in_kernels=so_kern)
 
     out_path = out_path or os.path.join(HERE, "reference_python.npz")
     np.savez_compressed(out_path, **out)

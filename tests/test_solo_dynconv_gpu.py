@@ -1,0 +1,145 @@
+"""GPU parity of the fused SOLOv2 dynamic conv + mask stage (`d2b_solo_dynamic_masks`, csrc/solo_dynconv.cu) --
+solo_v2.py:499-517, 530-533 -- against the CPU oracle.
+
+This is the one floating-point contraction on the path, so the bar is the tolerance BASELINE.json states for floating
+point, relative to the magnitude being summed:
+    |logit_gpu - logit_oracle| <= 1e-5 * sum_k |kernel_k * feature_k|          (TOL below)
+(the oracle is a sequential fp32 sum; TF's conv is a blocked Eigen contraction whose order is unspecified, and the
+kernel is 3 x tf32 with fp32 accumulation in TMEM).  Everything AFTER the logits is exact: the packed bits, the mask
+sums and every downstream decision must equal the oracle's mask stage applied to the GPU's own logits, and may differ
+from the oracle-on-oracle-logits result only at pixels whose logit is within TOL of logit(threshold).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from detectron2_tensorflow_b200.modeling import SOLOv2Inference, solo_dynamic_masks, solo_mask_encode
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def T(x, dev):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+def unpack(packed, hw):
+    return np.unpackbits(packed.cpu().numpy().view(np.uint8), axis=-1, bitorder="little")[..., :hw]
+
+
+def make_inputs(rng, B, n, H, W, E, blobs=True):
+    """Mask features that make object-like masks: smooth fields per channel + noise; kernels ~ N(0, 1/sqrt(E))."""
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    feat = np.empty((B, H, W, E), np.float32)
+    for b in range(B):
+        for e in range(E):
+            feat[b, :, :, e] = np.sin(yy * rng.uniform(0.02, 0.4) + xx * rng.uniform(0.02, 0.4) + rng.uniform(0, 6))
+    feat += rng.normal(0, 0.1, feat.shape).astype(np.float32)
+    kern = (rng.standard_normal((B, n, E)) / np.sqrt(E) * 3).astype(np.float32)
+    return feat, kern
+
+
+@pytest.mark.parametrize("B,n,hw,E,thr", [(2, 130, (24, 32), 32, 0.5), (1, 500, (50, 84), 256, 0.5), (3, 77, (25, 37), 8, 0.5),
+                                          (2, 300, (40, 64), 40, 0.3), (1, 128, (16, 16), 256, 0.5), (1, 1, (3, 5), 4, 0.5),
+                                          (2, 257, (31, 33), 64, 0.7)])
+def test_dynamic_masks_vs_oracle(cuda, oracle_lib, B, n, hw, E, thr):
+    H, W = hw
+    rng = np.random.default_rng(B * 1000 + n + E)
+    feat, kern = make_inputs(rng, B, n, H, W, E)
+    counts = np.array([n, max(n - 5, 0), 0][:B], np.int32)
+    packed, sm, ss, logits = solo_dynamic_masks(T(feat, cuda), T(kern, cuda), thr, T(counts, cuda), return_logits=True)
+    bits = unpack(packed, H * W)
+    glog = logits.cpu().numpy().reshape(B, n, H * W)
+    x0 = np.float32(np.log(thr / (1 - thr)))
+    worst = 0.0
+    for b in range(B):
+        c = int(counts[b])
+        want, absum = oracle_lib.solo_dynamic_conv(feat[b], kern[b, :c])
+        err = np.abs(glog[b, :c].astype(np.float64) - want)
+        assert (err <= TOL * absum + 1e-30).all(), float((err / np.maximum(absum, 1e-30)).max())
+        worst = max(worst, float((err / np.maximum(absum, 1e-30)).max()) if c else 0.0)
+        # exact from the logits on: oracle mask stage on the GPU's logits
+        m, wsm, wss = oracle_lib.solo_mask_stage(glog[b, :c].reshape(c, H, W), thr)
+        assert np.array_equal(bits[b, :c].reshape(c, H, W), m.astype(np.uint8))
+        assert np.array_equal(sm[b, :c].cpu().numpy(), wsm)
+        assert np.allclose(ss[b, :c].cpu().numpy(), wss, rtol=1e-5, atol=1e-6)
+        # against the oracle's own logits: bits may differ only inside the tolerance band around logit(thr)
+        m0, _, _ = oracle_lib.solo_mask_stage(want.reshape(c, H, W), thr)
+        diff = bits[b, :c] != m0.reshape(c, -1).astype(np.uint8)
+        assert (np.abs(want - x0)[diff] <= TOL * absum[diff]).all()
+        # rows past the valid prefix: empty masks, zero sums
+        assert not bits[b, c:].any() and not sm[b, c:].any() and not ss[b, c:].any()
+    print(f"max |logit error| / sum|terms| = {worst:.3e}")
+
+
+def test_dynamic_masks_without_counts_and_logits(cuda, oracle_lib):
+    rng = np.random.default_rng(5)
+    B, n, H, W, E = 2, 140, 20, 28, 32
+    feat, kern = make_inputs(rng, B, n, H, W, E)
+    packed, sm, ss = solo_dynamic_masks(T(feat, cuda), T(kern, cuda))
+    packed2, sm2, ss2, logits = solo_dynamic_masks(T(feat, cuda), T(kern, cuda), return_logits=True)
+    assert torch.equal(packed, packed2) and torch.equal(sm, sm2)
+    # the streaming encoder on the same logits gives the same words
+    p3, sm3, _ = solo_mask_encode(logits)
+    assert torch.equal(packed, p3) and torch.equal(sm, sm3)
+
+
+def test_postprocess_from_features_equals_postprocess_from_logits(cuda):
+    """The whole tail (solo_v2.py:499-558) with the fused conv == the tail fed with the conv's logits."""
+    rng = np.random.default_rng(11)
+    B, n, H, W, E = 3, 200, 32, 48, 64
+    feat, kern = make_inputs(rng, B, n, H, W, E)
+    scores = rng.uniform(0.1, 1.0, (B, n)).astype(np.float32)
+    classes = rng.integers(0, 3, (B, n)).astype(np.int64)
+    strides = rng.choice([8.0, 16.0, 32.0], (B, n)).astype(np.float32)
+    counts = np.array([n, n - 9, 0], np.int32)
+    logits = solo_dynamic_masks(T(feat, cuda), T(kern, cuda), 0.5, T(counts, cuda), return_logits=True)[3]
+    head = SOLOv2Inference(0.5, 100, "gaussian", 2.0, 0.05, 40)
+    a = head.postprocess(None, T(scores, cuda), T(classes, cuda), T(strides, cuda), T(counts, cuda),
+                         mask_features=T(feat, cuda), mask_kernels=T(kern, cuda))
+    b = head.postprocess(logits, T(scores, cuda), T(classes, cuda), T(strides, cuda), T(counts, cuda))
+    for k in ("num", "is_valid", "pred_classes", "pred_masks", "packed_masks"):
+        assert torch.equal(a[k], b[k]), k
+    assert torch.allclose(a["scores"], b["scores"], rtol=1e-5, atol=1e-7)
+    assert int(a["num"].sum()) > 0
+
+
+def test_reference_python_golden_through_fused_conv(cuda):
+    """MaskKernelBranch.inference of the reference (executed on the numpy TF shim, tests/golden/make_reference_golden.py)
+    from the mask features and the gathered kernels: the conv of the reference is included in the op under test."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_python.npz"))
+    head = SOLOv2Inference(0.5, 30, "gaussian", 2.0, 0.05, 12)
+    got = head.postprocess(None, T(z["so_in_scores"], cuda), T(z["so_in_classes"], cuda), T(z["so_in_strides"], cuda),
+                           T(z["so_in_counts"], cuda), mask_features=T(z["so_in_mask_features"], cuda),
+                           mask_kernels=T(z["so_in_kernels"], cuda))
+    assert np.array_equal(got["is_valid"].cpu().numpy(), z["so_valid"])
+    assert np.array_equal(got["pred_classes"].cpu().numpy(), z["so_classes"])
+    assert np.array_equal(got["pred_masks"].cpu().numpy(), z["so_masks"])
+    assert np.allclose(got["scores"].cpu().numpy(), z["so_scores"], rtol=1e-5, atol=1e-7)
+
+
+def test_full_size_config4(cuda):
+    """BASELINE config 4 shapes (500 candidates, 200x336 mask features, E=256), 2 images: against cuBLAS fp32
+    (TF32 off) within TOL, and the packed words equal the streaming encoder's on the kernel's own logits."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cpu").manual_seed(3)
+    B, n, H, W, E = 2, 500, 200, 336, 256
+    feat = torch.randn((B, H, W, E), generator=g).to(cuda)
+    kern = (torch.randn((B, n, E), generator=g) / 16).to(cuda)
+    counts = torch.tensor([500, 391], dtype=torch.int32, device=cuda)
+    packed, sm, ss, logits = solo_dynamic_masks(feat, kern, 0.5, counts, return_logits=True)
+    ref = torch.bmm(kern, feat.reshape(B, H * W, E).transpose(1, 2))
+    absum = torch.bmm(kern.abs(), feat.abs().reshape(B, H * W, E).transpose(1, 2))
+    err = (logits.reshape(B, n, -1) - ref).abs()
+    err[1, 391:] = 0
+    ratio = float((err / absum.clamp_min(1e-30)).max())
+    assert ratio <= TOL, ratio
+    p2, sm2, ss2 = solo_mask_encode(logits, 0.5, counts)
+    assert torch.equal(packed, p2) and torch.equal(sm, sm2)
+    assert torch.allclose(ss, ss2, rtol=1e-5, atol=1e-5)
+    # fused call without the logits output gives the same words
+    p3, sm3, _ = solo_dynamic_masks(feat, kern, 0.5, counts)
+    assert torch.equal(packed, p3) and torch.equal(sm, sm3)
+    print(f"full size: max |logit error| / sum|terms| = {ratio:.3e}")

@@ -1,0 +1,62 @@
+"""SOLOv2 dynamic conv + mask stage at BASELINE config 4 shapes (16 images x 500 candidates x 200x336, E=256):
+the fused tcgen05 kernel (d2b_solo_dynamic_masks) next to the library route it replaces
+(cuBLAS fp32 bmm -> 2.15 GB of logits -> d2b_solo_mask_encode).  One JSON line per variant."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from detectron2_tensorflow_b200.modeling import solo_dynamic_masks, solo_mask_encode  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=16)
+ap.add_argument("--n", type=int, default=500)
+ap.add_argument("--hw", type=int, nargs=2, default=[200, 336])
+ap.add_argument("--channels", type=int, default=256)
+ap.add_argument("--iters", type=int, default=10)
+args = ap.parse_args()
+dev = torch.device("cuda", 0)
+B, n, (H, W), E = args.batch, args.n, args.hw, args.channels
+g = torch.Generator().manual_seed(0)
+feat = torch.randn((B, H, W, E), generator=g).to(dev)
+kern = (torch.randn((B, n, E), generator=g) / 16).to(dev)
+flops = 2.0 * B * n * H * W * E
+
+
+def timed(fn):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(args.iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def library_route(tf32):
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    logits = torch.bmm(kern, feat.reshape(B, H * W, E).transpose(1, 2)).reshape(B, n, H, W)
+    return solo_mask_encode(logits)
+
+
+for name, fn in (("fused_tcgen05_3xtf32", lambda: solo_dynamic_masks(feat, kern)),
+                 ("cublas_fp32_bmm_plus_encode", lambda: library_route(False)),
+                 ("cublas_tf32_bmm_plus_encode", lambda: library_route(True))):
+    med, best = timed(fn)
+    print(json.dumps({"variant": name, "batch": B, "n": n, "hw": [H, W], "channels": E, "ms": med, "min_ms": best,
+                      "useful_tflops": flops / med / 1e9, "tensor_tflops_issued": (3 if "fused" in name else 1) * flops / med / 1e9,
+                      "logits_bytes_avoided": 4 * B * n * H * W if "fused" in name else 0}))
+a = solo_dynamic_masks(feat, kern)
+b = library_route(False)
+mism = int((a[0] != b[0]).sum())
+print(json.dumps({"check": "packed words differing from the cuBLAS-fp32 route", "words": mism, "of": a[0].numel(),
+                  "sum_masks_max_abs_diff": float((a[1] - b[1]).abs().max())}))
