@@ -108,6 +108,17 @@ __device__ __forceinline__ float tf32_rn(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+__device__ __forceinline__ float tf32_near(float x) {  // finite inputs
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+// sigmoid for the score sums of the fused path: 2 MUFU ops, ~2 ulp (the logits themselves carry ~1e-6 of rounding)
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.44269504088896341f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+__device__ __noinline__ bool exact_sigmoid_above(float x, float thr) { return d2b_sigmoidf(x) > thr; }
 __device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
   h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
   l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y); l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
@@ -250,7 +261,10 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
         for (int i = tid; i < (int)(kBBytes / 16); i += kCvtThreads) {
           float4 v, h, l;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + 16u * i));
-          split4(v, h, l);
+          // hi = x rounded to tf32 (nearest, ties away: two integer ops); lo = x - hi exactly (<= 13 significant bits);
+          // the tensor core ignores the low 13 mantissa bits of lo, an error of < 2^-21 |x| with random sign
+          h.x = tf32_near(v.x); h.y = tf32_near(v.y); h.z = tf32_near(v.z); h.w = tf32_near(v.w);
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src + 16u * i), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u * i), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
         }
@@ -292,60 +306,54 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * kBN;
       const long long p0 = (long long)it.pt * kBN;
-      u64 words[kBN / 64];
-#pragma unroll
-      for (int c = 0; c < kBN / 32; ++c) {
-        uint32_t r[32];
+      u64 word = 0;
+      u64* dstw = a.packed + ((size_t)it.b * a.n + (live ? row : 0)) * a.Wd;
+      float* lg = a.logits ? a.logits + ((size_t)it.b * a.n + (live ? row : 0)) * a.hw : nullptr;
+#pragma unroll 1  // a rolled loop: the unrolled form is 160 KB of straight-line code and lives in instruction-cache misses
+      for (int c = 0; c < kBN / 16; ++c) {
+        uint32_t r[16];
         __syncwarp();  // .sync.aligned: the whole warp issues the load together
         asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr + c * 32)
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr + c * 16)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         uint32_t bits = 0;
-        const long long pc = p0 + c * 32;
+        const long long pc = p0 + c * 16;
         if (live) {
-          if (a.logits) {
-            float* lg = a.logits + ((size_t)it.b * a.n + row) * a.hw;
+          if (lg) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < 16; ++j)
               if (pc + j < a.hw) lg[pc + j] = __uint_as_float(r[j]);
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < 16; ++j) {
             const float x = __uint_as_float(r[j]);
-            // sigmoid(x) > thr: decided on x outside the guard band around logit(thr), by the exact sigmoid inside
-            if (x >= a.lo && pc + j < a.hw) {
-              const float sg = d2b_sigmoidf(x);
-              const bool on = (x > a.hi) ? true : (sg > a.thr);
-              if (on) {
-                bits |= 1u << j;
-                acc_score = acc_score + sg;
-              }
+            // sigmoid(x) > thr: decided on x outside the guard band around logit(thr), by the exact sigmoid inside it
+            bool on = x > a.hi;
+            if (x >= a.lo && !on) on = exact_sigmoid_above(x, a.thr);  // rare
+            on = on && (pc + j < a.hw);
+            const float sg = fast_sigmoid(x);
+            if (on) {
+              bits |= 1u << j;
+              acc_score = acc_score + sg;
             }
           }
         }
         acc_cnt += __popc(bits);
-        if (c & 1) words[c >> 1] |= (u64)bits << 32;
-        else words[c >> 1] = (u64)bits;
-      }
-      // the accumulator is in registers / consumed: hand the TMEM buffer back to the MMA warp
-      tc_fence_before();
-      mbar_arrive(tmem_empty(as));
-      if (live) {
-        u64* dstw = a.packed + ((size_t)it.b * a.n + row) * a.Wd;
-#pragma unroll
-        for (int w = 0; w < kBN / 64; ++w) {
-          const int word = it.pt * (kBN / 64) + w;
-          if (word < a.Wd) dstw[word] = words[w];
+        word |= (u64)bits << (16 * (c & 3));
+        if ((c & 3) == 3) {
+          const int wi = it.pt * (kBN / 64) + (c >> 2);
+          if (live && wi < a.Wd) dstw[wi] = word;
+          word = 0;
         }
       }
+      // the accumulator has been consumed: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(tmem_empty(as));
     }
     flush();
   }

@@ -67,7 +67,7 @@ def test_dynamic_masks_vs_oracle(cuda, oracle_lib, B, n, hw, E, thr):
         assert np.allclose(ss[b, :c].cpu().numpy(), wss, rtol=1e-5, atol=1e-6)
         # against the oracle's own logits: bits may differ only inside the tolerance band around logit(thr)
         m0, _, _ = oracle_lib.solo_mask_stage(want.reshape(c, H, W), thr)
-        diff = bits[b, :c] != m0.reshape(c, -1).astype(np.uint8)
+        diff = bits[b, :c] != m0.reshape(c, H * W).astype(np.uint8)
         assert (np.abs(want - x0)[diff] <= TOL * absum[diff]).all()
         # rows past the valid prefix: empty masks, zero sums
         assert not bits[b, c:].any() and not sm[b, c:].any() and not ss[b, c:].any()
