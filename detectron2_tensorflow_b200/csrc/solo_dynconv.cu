@@ -12,10 +12,11 @@
 //   * epilogue warps read the accumulators with tcgen05.ld (thread = one mask row, 32 consecutive pixels per load),
 //     take the threshold decision with the bit-exact sigmoid rule of solo_encode_kernel and emit BIT-PACKED masks,
 //     exact mask sums and the score sums -- the 4 B/pixel logits (134 MB per image at 500 x 200 x 336) never exist.
-// Persistent: one CTA per SM walks a contiguous range of (image, row block, pixel tile) tiles.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM owner), 2-5 = converters, 6-9 = epilogue.
+// Persistent: one CTA per SM walks the (image, pixel tile, row block) tiles round-robin.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM owner), 2-5 = converters, 6-13 = epilogue.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 
@@ -25,17 +26,30 @@ typedef unsigned long long u64;
 
 constexpr int kBM = 128;   // mask kernels per tile (UMMA M, = TMEM lanes)
 constexpr int kBN = 256;   // pixels per tile (UMMA N, = TMEM columns of one accumulator)
-constexpr int kBK = 32;    // fp32 per 128-byte swizzle row
 constexpr int kUmmaK = 8;  // tf32 MMA depth
-constexpr int kStages = 2;
-constexpr uint32_t kABytes = kBM * kBK * 4;                   // 16 KB
-constexpr uint32_t kBBytes = kBN * kBK * 4;                   // 32 KB
-constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // A_hi, A_lo, B (raw -> hi in place), B_lo
-constexpr uint32_t kTxBytes = 2 * kABytes + kBBytes;          // what the TMA writes per stage
-constexpr int kThreads = 320;
-constexpr int kCvtThreads = 128, kEpiThreads = 128;
+constexpr int kThreads = 448;
+constexpr int kCvtThreads = 128, kEpiThreads = 256;  // 2 epilogue warps per TMEM lane quarter (half the columns each)
 constexpr uint32_t kTmemCols = 512;
-constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + 256;
+
+// One pipeline stage holds a K block of BK fp32 = one swizzle row: BK = 32 -> 128-byte swizzle, 96 KB per stage,
+// 2 stages; BK = 16 -> 64-byte swizzle, 48 KB per stage, 4 stages (same bytes in flight, twice the depth: the
+// TMA -> converter -> MMA round trip of a stage is latency, not bandwidth).
+template <int BK>
+struct Cfg {
+  static_assert(BK == 32 || BK == 16, "one swizzle row per K block");
+  static constexpr int kBK = BK;
+  static constexpr int kStages = BK == 32 ? 2 : 4;
+  static constexpr uint32_t kRowBytes = BK * 4;
+  static constexpr uint32_t kABytes = kBM * kRowBytes;
+  static constexpr uint32_t kBBytes = kBN * kRowBytes;
+  static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;  // A_hi, A_lo, B (raw -> hi in place), B_lo
+  static constexpr uint32_t kTxBytes = 2 * kABytes + kBBytes;        // what the TMA writes per stage
+  static constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + 256;
+  // UMMA shared-memory descriptor, K-major: 8-row groups (SBO) 8 * row bytes apart, LBO unused (1), version 1,
+  // layout type 2 = SWIZZLE_128B / 4 = SWIZZLE_64B
+  static constexpr uint64_t kDescHi = (1ull << 16) | ((uint64_t)(8 * kRowBytes >> 4) << 32) | (1ull << 46) |
+                                      ((uint64_t)(BK == 32 ? 2 : 4) << 61);
+};
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
@@ -87,9 +101,9 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// K-major operand tile, 128-byte swizzle: 8-row groups 1024 B apart (SBO), LBO unused (1), descriptor version 1
+template <int BK>
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | Cfg<BK>::kDescHi;
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
@@ -134,31 +148,39 @@ __global__ void dyn_split_kernel(const float4* x, float4* hi, float4* lo, long l
   lo[i] = l;
 }
 
-struct TileIter {  // every role walks the same tile sequence
-  long long t, t_end;
+// Every role walks the same tile sequence.  Tiles are numbered (image, pixel tile, row block) with the row block
+// fastest and dealt round-robin to the CTAs, so the RB row blocks of one pixel tile run at the same time on
+// neighbouring SMs: the feature tile comes from DRAM once and from L2 for the others (measured: DRAM reads
+// 4.45 GB -> see profiles/), and a CTA keeps its row block for long runs (row sums stay in registers).
+struct TileIter {
+  long long t, total;
   int b, rb, pt;
   const DynArgs& a;
   __device__ TileIter(const DynArgs& a_) : a(a_) {
-    const long long total = (long long)a.B * a.RB * a.PT;
-    t = total * blockIdx.x / gridDim.x - 1;
-    t_end = total * (blockIdx.x + 1) / gridDim.x;
+    total = (long long)a.B * a.RB * a.PT;
+    t = (long long)blockIdx.x - gridDim.x;
   }
   __device__ bool next() {
     for (;;) {
-      if (++t >= t_end) return false;
-      pt = (int)(t % a.PT);
-      const long long r = t / a.PT;
-      rb = (int)(r % a.RB);
-      b = (int)(r / a.RB);
+      t += gridDim.x;
+      if (t >= total) return false;
+      rb = (int)(t % a.RB);
+      const long long r = t / a.RB;
+      pt = (int)(r % a.PT);
+      b = (int)(r / a.PT);
       const int cnt = a.counts ? min(a.counts[b], a.n) : a.n;
       if (rb * kBM < cnt) return true;  // row blocks past the valid prefix have no work (their words are pre-zeroed)
     }
   }
 };
 
+template <int BK>
 __global__ void __launch_bounds__(kThreads, 1)
 solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
                     const __grid_constant__ CUtensorMap tm_feat, const DynArgs a) {
+  constexpr int kBK = BK, kStages = Cfg<BK>::kStages;
+  constexpr uint32_t kABytes = Cfg<BK>::kABytes, kBBytes = Cfg<BK>::kBBytes, kStageBytes = Cfg<BK>::kStageBytes,
+                     kTxBytes = Cfg<BK>::kTxBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-byte alignment
   const uint32_t bars = base + kStages * kStageBytes;
@@ -234,9 +256,9 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
-            const uint32_t ko = k * kUmmaK * 4;  // bytes along K inside the 128-byte swizzle row
-            const uint64_t ahi = umma_desc(sA_hi(s) + ko), alo = umma_desc(sA_lo(s) + ko);
-            const uint64_t bhi = umma_desc(sB_hi(s) + ko), blo = umma_desc(sB_lo(s) + ko);
+            const uint32_t ko = k * kUmmaK * 4;  // bytes along K inside the swizzle row
+            const uint64_t ahi = umma_desc<BK>(sA_hi(s) + ko), alo = umma_desc<BK>(sA_lo(s) + ko);
+            const uint64_t bhi = umma_desc<BK>(sB_hi(s) + ko), blo = umma_desc<BK>(sB_lo(s) + ko);
             umma_tf32(d, alo, bhi, (kb | k) != 0);  // small terms first
             umma_tf32(d, ahi, blo, 1u);
             umma_tf32(d, ahi, bhi, 1u);
@@ -276,6 +298,7 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
   } else {
     // ===================================================== epilogue: TMEM -> threshold -> packed bits + sums
     const int q = warp & 3;  // a warp may only touch TMEM lanes 32*(warp % 4) .. +31
+    const int half = (warp - 6) >> 2;  // which 128 of the tile's 256 columns
     const int row_in_tile = q * 32 + lane;
     TileIter it(a);
     uint32_t n_tile = 0;
@@ -310,7 +333,7 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
       u64* dstw = a.packed + ((size_t)it.b * a.n + (live ? row : 0)) * a.Wd;
       float* lg = a.logits ? a.logits + ((size_t)it.b * a.n + (live ? row : 0)) * a.hw : nullptr;
 #pragma unroll 1  // a rolled loop: the unrolled form is 160 KB of straight-line code and lives in instruction-cache misses
-      for (int c = 0; c < kBN / 16; ++c) {
+      for (int c = half * (kBN / 32); c < (half + 1) * (kBN / 32); ++c) {
         uint32_t r[16];
         __syncwarp();  // .sync.aligned: the whole warp issues the load together
         asm volatile(
@@ -321,7 +344,7 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
             : "r"(taddr + c * 16)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        uint32_t bits = 0;
+        uint32_t bits = 0, band = 0;
         const long long pc = p0 + c * 16;
         if (live) {
           if (lg) {
@@ -329,18 +352,32 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
             for (int j = 0; j < 16; ++j)
               if (pc + j < a.hw) lg[pc + j] = __uint_as_float(r[j]);
           }
+          // sigmoid(x) > thr is decided on x outside the guard band around logit(thr); branch-free so that the 16
+          // elements' MUFU chains overlap.  The (rare) elements inside the band take the exact sigmoid below.
+          float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float x = __uint_as_float(r[j]);
-            // sigmoid(x) > thr: decided on x outside the guard band around logit(thr), by the exact sigmoid inside it
-            bool on = x > a.hi;
-            if (x >= a.lo && !on) on = exact_sigmoid_above(x, a.thr);  // rare
-            on = on && (pc + j < a.hw);
+            const bool inr = pc + j < a.hw;
+            const bool on = inr && x > a.hi;
+            const bool mid = inr && x >= a.lo && !(x > a.hi);
             const float sg = fast_sigmoid(x);
-            if (on) {
-              bits |= 1u << j;
-              acc_score = acc_score + sg;
-            }
+            bits |= (on ? 1u : 0u) << j;
+            band |= (mid ? 1u : 0u) << j;
+            if (j & 1) s1 = s1 + (on ? sg : 0.0f);
+            else s0 = s0 + (on ? sg : 0.0f);
+          }
+          acc_score = acc_score + (s0 + s1);
+          if (band) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if ((band >> j) & 1u) {
+                const float x = __uint_as_float(r[j]);
+                if (exact_sigmoid_above(x, a.thr)) {
+                  bits |= 1u << j;
+                  acc_score = acc_score + fast_sigmoid(x);
+                }
+              }
           }
         }
         acc_cnt += __popc(bits);
@@ -382,8 +419,8 @@ EncodeTiledFn encode_tiled_fn() {
   }();
   return fn;
 }
-// [batch, rows, E] fp32, E contiguous -> 3-D map with a (32 x box_rows x 1) box, 128-byte swizzle, zero OOB fill
-int make_map(CUtensorMap* m, const void* ptr, int E, long long rows, int batch, int box_rows) {
+// [batch, rows, E] fp32, E contiguous -> 3-D map with a (bk x box_rows x 1) box, swizzle = row bytes, zero OOB fill
+int make_map(CUtensorMap* m, const void* ptr, int E, long long rows, int batch, int box_rows, int bk) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -391,16 +428,27 @@ int make_map(CUtensorMap* m, const void* ptr, int E, long long rows, int batch, 
   }
   const cuuint64_t dims[3] = {(cuuint64_t)E, (cuuint64_t)rows, (cuuint64_t)batch};
   const cuuint64_t strides[2] = {(cuuint64_t)E * 4, (cuuint64_t)rows * E * 4};
-  const cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)box_rows, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (E=%d rows=%lld batch=%d)", (int)r, E, rows, batch);
     return D2B_ECUDA;
   }
   return D2B_OK;
+}
+
+// K block per pipeline stage: 16 (64-byte swizzle, 4 stages) by default; D2B_DYNCONV_BK=32 selects the 128-byte
+// swizzle / 2-stage variant (kept for measurement).
+int dyn_block_k() {
+  static const int bk = []() {
+    const char* e = getenv("D2B_DYNCONV_BK");
+    return (e && atoi(e) == 32) ? 32 : 16;
+  }();
+  return bk;
 }
 
 int dyn_check(const d2b_solo_dynamic_masks_params* p) {
@@ -454,7 +502,8 @@ extern "C" int d2b_solo_dynamic_masks(const d2b_solo_dynamic_masks_params* p, vo
   a.counts = p->counts; a.B = p->batch; a.n = p->n; a.E = E; a.hw = p->hw;
   a.RB = (p->n + kBM - 1) / kBM;
   a.PT = (int)((p->hw + kBN - 1) / kBN);
-  a.KB = (E + kBK - 1) / kBK;
+  const int bk = dyn_block_k();
+  a.KB = (E + bk - 1) / bk;
   a.Wd = (int)((p->hw + 63) / 64);
   a.thr = p->mask_threshold;
   const double t = (double)p->mask_threshold;  // same guard band as solo_encode_kernel
@@ -476,9 +525,9 @@ extern "C" int d2b_solo_dynamic_masks(const d2b_solo_dynamic_masks_params* p, vo
   if (p->counts) D2B_CUDA(cudaMemsetAsync(p->packed_masks, 0, sizeof(u64) * rows * a.Wd, st));
 
   CUtensorMap tm_ahi, tm_alo, tm_feat;
-  if ((rc = make_map(&tm_ahi, a_hi, E, p->n, p->batch, kBM)) != D2B_OK) return rc;
-  if ((rc = make_map(&tm_alo, a_lo, E, p->n, p->batch, kBM)) != D2B_OK) return rc;
-  if ((rc = make_map(&tm_feat, p->mask_features, E, p->hw, p->batch, kBN)) != D2B_OK) return rc;
+  if ((rc = make_map(&tm_ahi, a_hi, E, p->n, p->batch, kBM, bk)) != D2B_OK) return rc;
+  if ((rc = make_map(&tm_alo, a_lo, E, p->n, p->batch, kBM, bk)) != D2B_OK) return rc;
+  if ((rc = make_map(&tm_feat, p->mask_features, E, p->hw, p->batch, kBN, bk)) != D2B_OK) return rc;
 
   const long long total4 = (long long)rows * E / 4;
   dyn_split_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(p->mask_kernels),
@@ -495,14 +544,21 @@ extern "C" int d2b_solo_dynamic_masks(const d2b_solo_dynamic_masks_params* p, vo
     sm_count[dev] = v > 0 ? v : 148;
   }
   const int sms = (dev >= 0 && dev < 64) ? sm_count[dev] : 148;
-  static bool attr_set[64] = {false};
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    D2B_CUDA(cudaFuncSetAttribute(solo_dynconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
-  }
   const long long tiles = (long long)a.B * a.RB * a.PT;
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  solo_dynconv_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm_ahi, tm_alo, tm_feat, a);
+  static bool attr_set[2][64] = {{false}};
+  const int vi = bk == 32 ? 0 : 1;
+  if (dev < 0 || dev >= 64 || !attr_set[vi][dev]) {
+    if (bk == 32)
+      D2B_CUDA(cudaFuncSetAttribute(solo_dynconv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<32>::kSmemBytes));
+    else
+      D2B_CUDA(cudaFuncSetAttribute(solo_dynconv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<16>::kSmemBytes));
+    if (dev >= 0 && dev < 64) attr_set[vi][dev] = true;
+  }
+  if (bk == 32)
+    solo_dynconv_kernel<32><<<grid, kThreads, Cfg<32>::kSmemBytes, st>>>(tm_ahi, tm_alo, tm_feat, a);
+  else
+    solo_dynconv_kernel<16><<<grid, kThreads, Cfg<16>::kSmemBytes, st>>>(tm_ahi, tm_alo, tm_feat, a);
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }
