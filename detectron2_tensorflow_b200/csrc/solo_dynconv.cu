@@ -122,9 +122,7 @@ __device__ __forceinline__ float tf32_rn(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-__device__ __forceinline__ float tf32_near(float x) {  // finite inputs
-  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
-}
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 // sigmoid for the score sums of the fused path: 2 MUFU ops, ~2 ulp (the logits themselves carry ~1e-6 of rounding)
 __device__ __forceinline__ float fast_sigmoid(float x) {
   float e, r;
@@ -259,9 +257,9 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
             const uint32_t ko = k * kUmmaK * 4;  // bytes along K inside the swizzle row
             const uint64_t ahi = umma_desc<BK>(sA_hi(s) + ko), alo = umma_desc<BK>(sA_lo(s) + ko);
             const uint64_t bhi = umma_desc<BK>(sB_hi(s) + ko), blo = umma_desc<BK>(sB_lo(s) + ko);
-            umma_tf32(d, alo, bhi, (kb | k) != 0);  // small terms first
-            umma_tf32(d, ahi, blo, 1u);
+            umma_tf32(d, alo, bhi, (kb | k) != 0);  // consecutive MMAs share one operand tile
             umma_tf32(d, ahi, bhi, 1u);
+            umma_tf32(d, ahi, blo, 1u);
           }
           umma_commit(empty(s));  // implies tcgen05.fence::before_thread_sync
           if (++s == kStages) { s = 0; ph ^= 1u; }
@@ -281,13 +279,14 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
         const uint32_t src = sB_hi(s), dst = sB_lo(s);
 #pragma unroll 4
         for (int i = tid; i < (int)(kBBytes / 16); i += kCvtThreads) {
-          float4 v, h, l;
+          float4 v, l;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + 16u * i));
-          // hi = x rounded to tf32 (nearest, ties away: two integer ops); lo = x - hi exactly (<= 13 significant bits);
-          // the tensor core ignores the low 13 mantissa bits of lo, an error of < 2^-21 |x| with random sign
-          h.x = tf32_near(v.x); h.y = tf32_near(v.y); h.z = tf32_near(v.z); h.w = tf32_near(v.w);
-          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src + 16u * i), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+          // The tensor core reads only the upper 19 bits of a tf32 operand, so the raw tile already IS the hi half
+          // (x truncated to tf32); the converter adds lo = x - trunc(x), exact in fp32 with <= 13 significant bits
+          // (the MMA keeps its upper 11: < 2^-20 |x| lost, in the direction of x, i.e. a scale of the dot product by
+          // 1 - O(2^-21), plus zero-mean noise far below the fp32 rounding of the sum).  No write-back of hi: one
+          // LDS + one STS per 16 bytes, which matters because this kernel is bound by shared-memory bandwidth.
+          l.x = v.x - tf32_trunc(v.x); l.y = v.y - tf32_trunc(v.y); l.z = v.z - tf32_trunc(v.z); l.w = v.w - tf32_trunc(v.w);
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u * i), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
@@ -355,17 +354,33 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
           // sigmoid(x) > thr is decided on x outside the guard band around logit(thr); branch-free so that the 16
           // elements' MUFU chains overlap.  The (rare) elements inside the band take the exact sigmoid below.
           float s0 = 0.0f, s1 = 0.0f;
+          const long long left = a.hw - pc;  // pixels of this chunk inside the map
+          if (left >= 16) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float x = __uint_as_float(r[j]);
-            const bool inr = pc + j < a.hw;
-            const bool on = inr && x > a.hi;
-            const bool mid = inr && x >= a.lo && !(x > a.hi);
-            const float sg = fast_sigmoid(x);
-            bits |= (on ? 1u : 0u) << j;
-            band |= (mid ? 1u : 0u) << j;
-            if (j & 1) s1 = s1 + (on ? sg : 0.0f);
-            else s0 = s0 + (on ? sg : 0.0f);
+            for (int j = 0; j < 16; ++j) {
+              const float x = __uint_as_float(r[j]);
+              const float sg = fast_sigmoid(x);
+              if (x > a.hi) {
+                bits |= 1u << j;
+                if (j & 1) s1 = s1 + sg;
+                else s0 = s0 + sg;
+              } else if (x >= a.lo) {
+                band |= 1u << j;
+              }
+            }
+          } else {  // the last tile of the map: TMA zero-filled the rows past hw, they must not set bits
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float x = __uint_as_float(r[j]);
+              if (j < left) {
+                if (x > a.hi) {
+                  bits |= 1u << j;
+                  s0 = s0 + fast_sigmoid(x);
+                } else if (x >= a.lo) {
+                  band |= 1u << j;
+                }
+              }
+            }
           }
           acc_score = acc_score + (s0 + s1);
           if (band) {
