@@ -443,3 +443,56 @@ class D2LabelBoxesOp : public tf::OpKernel {
   float boundary_;
 };
 REGISTER_KERNEL_BUILDER(Name("D2LabelBoxes").Device(tf::DEVICE_GPU), D2LabelBoxesOp);
+
+// ------------------------------------------------------------------ D2SoloDynamicMasks
+// Replaces the dynamic mask generation + mask stage of SOLOv2Head.inference_single_image
+// (lib/modeling/single_stage_heads/solo_v2.py:499-517, 530-533): tf.nn.conv2d(mask_features, pred_kernels) ->
+// sigmoid -> > mask_threshold -> reduce_sum, for one image.  Outputs the bit-packed masks (int64 words, bit p of
+// word w = pixel 64*w+p), sum_masks and the score sums; mask_scoring (:531-533) = score_sums / sum_masks and the
+// packed words feed D2MatrixNms' packed variant (d2b_matrix_nms_params.packed_masks).
+REGISTER_OP("D2SoloDynamicMasks")
+    .Input("mask_features: float")  // [H, W, E]   (pred_mask_features of one image)
+    .Input("mask_kernels: float")   // [n, E]      (pred_kernels gathered by keep_inds, :486)
+    .Attr("mask_threshold: float = 0.5")
+    .Output("packed_masks: int64")  // [n, ceil(H*W/64)]
+    .Output("sum_masks: float")     // [n]
+    .Output("score_sums: float")    // [n]
+    .SetShapeFn([](InferenceContext* c) {
+      c->set_output(0, c->Matrix(c->Dim(c->input(1), 0), InferenceContext::kUnknownDim));
+      c->set_output(1, c->Vector(c->Dim(c->input(1), 0)));
+      c->set_output(2, c->Vector(c->Dim(c->input(1), 0)));
+      return tf::Status::OK();
+    });
+
+class D2SoloDynamicMasksOp : public tf::OpKernel {
+ public:
+  explicit D2SoloDynamicMasksOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("mask_threshold", &thr_));
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    const tf::Tensor& f = ctx->input(0);
+    const tf::Tensor& k = ctx->input(1);
+    OP_REQUIRES(ctx, f.dims() == 3 && k.dims() == 2 && k.dim_size(1) == f.dim_size(2),
+                tf::errors::InvalidArgument("mask_features must be [H,W,E] and mask_kernels [n,E]"));
+    d2b_solo_dynamic_masks_params p = {};
+    p.mask_features = f.flat<float>().data();
+    p.mask_kernels = k.flat<float>().data();
+    p.batch = 1;
+    p.n = k.dim_size(0);
+    p.channels = k.dim_size(1);
+    p.hw = f.dim_size(0) * f.dim_size(1);
+    p.mask_threshold = thr_;
+    tf::Tensor *packed = nullptr, *sums = nullptr, *ssum = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({k.dim_size(0), (p.hw + 63) / 64}), &packed));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({k.dim_size(0)}), &sums));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, tf::TensorShape({k.dim_size(0)}), &ssum));
+    p.packed_masks = reinterpret_cast<uint64_t*>(packed->flat<tf::int64>().data());
+    p.sum_masks = sums->flat<float>().data();
+    p.score_sums = ssum->flat<float>().data();
+    RunOp(ctx, p, d2b_solo_dynamic_masks_workspace_bytes, d2b_solo_dynamic_masks);
+  }
+
+ private:
+  float thr_;
+};
+REGISTER_KERNEL_BUILDER(Name("D2SoloDynamicMasks").Device(tf::DEVICE_GPU), D2SoloDynamicMasksOp);

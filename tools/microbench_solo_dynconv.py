@@ -9,7 +9,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from detectron2_tensorflow_b200.modeling import solo_dynamic_masks, solo_mask_encode  # noqa: E402
+from detectron2_tensorflow_b200.modeling import SOLOv2Inference, solo_dynamic_masks, solo_mask_encode  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)
@@ -55,6 +55,25 @@ for name, fn in (("fused_tcgen05_3xtf32", lambda: solo_dynamic_masks(feat, kern)
     print(json.dumps({"variant": name, "batch": B, "n": n, "hw": [H, W], "channels": E, "ms": med, "min_ms": best,
                       "useful_tflops": flops / med / 1e9, "tensor_tflops_issued": (3 if "fused" in name else 1) * flops / med / 1e9,
                       "logits_bytes_avoided": 4 * B * n * H * W if "fused" in name else 0}))
+# the whole inference tail (solo_v2.py:499-558): conv -> mask stage -> filter -> scoring -> top-k -> Matrix-NMS -> pad
+head = SOLOv2Inference(0.5, 500, "gaussian", 2.0, 0.05, 100)
+sc = torch.rand((B, n), generator=g).to(dev) * 0.9 + 0.1
+cl = torch.randint(0, 80, (B, n), generator=g).to(dev)
+stv = torch.full((B, n), 8.0, device=dev)
+
+
+def tail_library():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    logits = torch.bmm(kern, feat.reshape(B, H * W, E).transpose(1, 2)).reshape(B, n, H, W)
+    return head.postprocess(logits, sc, cl, stv, return_masks=False)
+
+
+for name, fn in (("tail_from_features_fused", lambda: head.postprocess(None, sc, cl, stv, return_masks=False, mask_features=feat,
+                                                                        mask_kernels=kern)),
+                 ("tail_cublas_fp32_bmm_then_postprocess", tail_library)):
+    med, best = timed(fn)
+    print(json.dumps({"variant": name, "batch": B, "n": n, "hw": [H, W], "channels": E, "ms": med, "min_ms": best,
+                      "images_per_s": B / med * 1e3}))
 a = solo_dynamic_masks(feat, kern)
 b = library_route(False)
 mism = int((a[0] != b[0]).sum())
