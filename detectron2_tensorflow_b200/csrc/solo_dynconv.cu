@@ -5,6 +5,9 @@
 // one contraction on the path, so it runs on the 5th-generation tensor cores:
 //   * tcgen05.mma kind::tf32, M=128 (mask kernels) x N=256 (pixels) x K=8, accumulators in TMEM (2 x 256 columns,
 //     double buffered), operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) through an mbarrier ring;
+//     by default two CTAs of a cluster form a cta_group::2 pair (M=256): each CTA owns one 128-row block of D in its
+//     own TMEM and stages / converts only HALF of the feature tile, the leader CTA issues the MMAs for both and
+//     tcgen05.commit multicasts the completion to the barriers of both CTAs;
 //   * fp32 accuracy from three tf32 products per k-step (3xTF32: a = a_hi + a_lo with both halves tf32-exact,
 //     D += a_lo.b_hi + a_hi.b_lo + a_hi.b_hi): the kernels are split once by a tiny prologue kernel, the feature tile
 //     is split in shared memory by four converter warps between the TMA and the MMA (elementwise, so the swizzled
@@ -34,25 +37,27 @@ constexpr uint32_t kTmemCols = 512;
 // One pipeline stage holds a K block of BK fp32 = one swizzle row: BK = 32 -> 128-byte swizzle, 96 KB per stage,
 // 2 stages; BK = 16 -> 64-byte swizzle, 48 KB per stage, 4 stages (same bytes in flight, twice the depth: the
 // TMA -> converter -> MMA round trip of a stage is latency, not bandwidth).
-template <int BK>
+template <int BK, int CTAS>
 struct Cfg {
   static_assert(BK == 32 || BK == 16, "one swizzle row per K block");
-  static constexpr int kBK = BK;
-  static constexpr int kStages = BK == 32 ? 2 : 4;
+  static_assert(CTAS == 1 || CTAS == 2, "one CTA or a cta_group::2 pair");
   static constexpr uint32_t kRowBytes = BK * 4;
+  static constexpr int kBRows = kBN / CTAS;  // feature rows (pixels) staged and converted by one CTA
   static constexpr uint32_t kABytes = kBM * kRowBytes;
-  static constexpr uint32_t kBBytes = kBN * kRowBytes;
-  static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;  // A_hi, A_lo, B (raw -> hi in place), B_lo
+  static constexpr uint32_t kBBytes = kBRows * kRowBytes;
+  static constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;  // A_hi, A_lo, B (raw = hi), B_lo
   static constexpr uint32_t kTxBytes = 2 * kABytes + kBBytes;        // what the TMA writes per stage
+  static constexpr int kStages = (192 * 1024) / kStageBytes;          // 2 / 4 (one CTA), 3 / 6 (pair)
   static constexpr size_t kSmemBytes = 1024 + (size_t)kStages * kStageBytes + 256;
   // UMMA shared-memory descriptor, K-major: 8-row groups (SBO) 8 * row bytes apart, LBO unused (1), version 1,
   // layout type 2 = SWIZZLE_128B / 4 = SWIZZLE_64B
   static constexpr uint64_t kDescHi = (1ull << 16) | ((uint64_t)(8 * kRowBytes >> 4) << 32) | (1ull << 46) |
                                       ((uint64_t)(BK == 32 ? 2 : 4) << 61);
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
+  // (M = 256 for the pair: each CTA owns 128 rows of D and stages half of B)
+  static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) |
+                                     ((uint32_t)((kBM * CTAS) >> 4) << 24);
 };
-
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 
 struct DynArgs {
   const int32_t* counts;
@@ -78,15 +83,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
                : "memory");
 }
 // Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the device.
+template <bool CLUSTER = false>  // CLUSTER: the arrivals come from the peer CTA too (acquire at cluster scope)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
   long long t0 = 0;
   for (unsigned spin = 0;; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
+    if constexpr (CLUSTER)
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar), "r"(parity)
+          : "memory");
+    else
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar), "r"(parity)
+          : "memory");
     if (ok) return;
     if ((spin & 1023u) == 1023u) {
       const long long now = clock64();
@@ -103,17 +116,43 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 }
 template <int BK>
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | Cfg<BK>::kDescHi;
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | Cfg<BK, 1>::kDescHi;
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+template <int CTAS>
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CTAS == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// tcgen05.commit: the mbarrier (same offset in every CTA of the pair) is signalled when the MMAs issued so far are done
+template <int CTAS>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  if constexpr (CTAS == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+// arrive on the barrier at the same offset in the LEADER CTA (rank 0) of the pair
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -150,35 +189,42 @@ __global__ void dyn_split_kernel(const float4* x, float4* hi, float4* lo, long l
 // fastest and dealt round-robin to the CTAs, so the RB row blocks of one pixel tile run at the same time on
 // neighbouring SMs: the feature tile comes from DRAM once and from L2 for the others (measured: DRAM reads
 // 4.45 GB -> see profiles/), and a CTA keeps its row block for long runs (row sums stay in registers).
+template <int CTAS>
 struct TileIter {
   long long t, total;
-  int b, rb, pt;
+  int b, rb, pt, units, rank;
   const DynArgs& a;
-  __device__ TileIter(const DynArgs& a_) : a(a_) {
-    total = (long long)a.B * a.RB * a.PT;
-    t = (long long)blockIdx.x - gridDim.x;
+  __device__ TileIter(const DynArgs& a_, int rank_) : rank(rank_), a(a_) {
+    units = (a.RB + CTAS - 1) / CTAS;  // row-block groups: one row block per CTA of the pair
+    total = (long long)a.B * units * a.PT;
+    t = (long long)(blockIdx.x / CTAS) - (long long)(gridDim.x / CTAS);
   }
   __device__ bool next() {
     for (;;) {
-      t += gridDim.x;
+      t += gridDim.x / CTAS;
       if (t >= total) return false;
-      rb = (int)(t % a.RB);
-      const long long r = t / a.RB;
+      const int u = (int)(t % units);
+      const long long r = t / units;
       pt = (int)(r % a.PT);
       b = (int)(r / a.PT);
+      rb = u * CTAS + rank;
       const int cnt = a.counts ? min(a.counts[b], a.n) : a.n;
-      if (rb * kBM < cnt) return true;  // row blocks past the valid prefix have no work (their words are pre-zeroed)
+      // groups past the valid prefix have no work (their words are pre-zeroed); the test is on the group's FIRST row
+      // block so that both CTAs of a pair take the same decision
+      if (u * CTAS * kBM < cnt) return true;
     }
   }
 };
 
-template <int BK>
+template <int BK, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_constant__ CUtensorMap tm_alo,
                     const __grid_constant__ CUtensorMap tm_feat, const DynArgs a) {
-  constexpr int kBK = BK, kStages = Cfg<BK>::kStages;
-  constexpr uint32_t kABytes = Cfg<BK>::kABytes, kBBytes = Cfg<BK>::kBBytes, kStageBytes = Cfg<BK>::kStageBytes,
-                     kTxBytes = Cfg<BK>::kTxBytes;
+  using C = Cfg<BK, CTAS>;
+  constexpr int kBK = BK, kStages = C::kStages;
+  constexpr uint32_t kABytes = C::kABytes, kBBytes = C::kBBytes, kStageBytes = C::kStageBytes, kTxBytes = C::kTxBytes;
+  uint32_t rank = 0;  // CTA rank in the pair; rank 0 (the leader) issues the MMAs and owns the cross-CTA barriers
+  if constexpr (CTAS == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-byte alignment
   const uint32_t bars = base + kStages * kStageBytes;
@@ -198,22 +244,29 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_raw(s), 1);
-      mbar_init(full_cvt(s), kCvtThreads);
+      mbar_init(full_cvt(s), kCvtThreads * CTAS);
       mbar_init(empty(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full(s), 1);
-      mbar_init(tmem_empty(s), kEpiThreads);
+      mbar_init(tmem_empty(s), kEpiThreads * CTAS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: the whole 512 columns (one CTA per SM by shared-memory footprint)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTAS == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {  // the same warp of both CTAs, same destination offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
@@ -221,7 +274,7 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
-      TileIter it(a);
+      TileIter<CTAS> it(a, rank);
       int s = 0;
       uint32_t ph = 0;
       while (it.next()) {
@@ -230,47 +283,47 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
           mbar_expect_tx(full_raw(s), kTxBytes);
           tma_load_3d(sA_hi(s), &tm_ahi, full_raw(s), kb * kBK, it.rb * kBM, it.b);
           tma_load_3d(sA_lo(s), &tm_alo, full_raw(s), kb * kBK, it.rb * kBM, it.b);
-          tma_load_3d(sB_hi(s), &tm_feat, full_raw(s), kb * kBK, it.pt * kBN, it.b);
+          tma_load_3d(sB_hi(s), &tm_feat, full_raw(s), kb * kBK, it.pt * kBN + (int)rank * C::kBRows, it.b);
           if (++s == kStages) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (one thread)
-    if (lane == 0) {
-      TileIter it(a);
+    if (lane == 0 && rank == 0) {
+      TileIter<CTAS> it(a, rank);
       int s = 0;
       uint32_t ph = 0;
       uint32_t n_tile = 0;
       while (it.next()) {
         const uint32_t as = n_tile & 1u, aph = (n_tile >> 1) & 1u;
         ++n_tile;
-        mbar_wait(tmem_empty(as), aph ^ 1u);  // the epilogue has drained this accumulator
+        mbar_wait<CTAS == 2>(tmem_empty(as), aph ^ 1u);  // the epilogue (of both CTAs) has drained this accumulator
         tc_fence_after();
         const uint32_t d = tmem_base + as * kBN;
         for (int kb = 0; kb < a.KB; ++kb) {
           mbar_wait(full_raw(s), ph);
-          mbar_wait(full_cvt(s), ph);
+          mbar_wait<CTAS == 2>(full_cvt(s), ph);  // converters of both CTAs (each waited for its own TMA)
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             const uint32_t ko = k * kUmmaK * 4;  // bytes along K inside the swizzle row
             const uint64_t ahi = umma_desc<BK>(sA_hi(s) + ko), alo = umma_desc<BK>(sA_lo(s) + ko);
             const uint64_t bhi = umma_desc<BK>(sB_hi(s) + ko), blo = umma_desc<BK>(sB_lo(s) + ko);
-            umma_tf32(d, alo, bhi, (kb | k) != 0);  // consecutive MMAs share one operand tile
-            umma_tf32(d, ahi, bhi, 1u);
-            umma_tf32(d, ahi, blo, 1u);
+            umma_tf32<CTAS>(d, alo, bhi, C::kIdesc, (kb | k) != 0);  // consecutive MMAs share one operand tile
+            umma_tf32<CTAS>(d, ahi, bhi, C::kIdesc, 1u);
+            umma_tf32<CTAS>(d, ahi, blo, C::kIdesc, 1u);
           }
-          umma_commit(empty(s));  // implies tcgen05.fence::before_thread_sync
+          umma_commit<CTAS>(empty(s));  // implies tcgen05.fence::before_thread_sync
           if (++s == kStages) { s = 0; ph ^= 1u; }
         }
-        umma_commit(tmem_full(as));
+        umma_commit<CTAS>(tmem_full(as));
       }
     }
   } else if (warp < 6) {
     // ===================================================== converters: feature tile -> tf32 hi (in place) + lo
     const int tid = threadIdx.x - 64;
-    TileIter it(a);
+    TileIter<CTAS> it(a, rank);
     int s = 0;
     uint32_t ph = 0;
     while (it.next()) {
@@ -290,7 +343,8 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u * i), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
-        mbar_arrive(full_cvt(s));
+        if constexpr (CTAS == 1) mbar_arrive(full_cvt(s));
+        else mbar_arrive_leader(full_cvt(s));
         if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
@@ -299,7 +353,7 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
     const int q = warp & 3;  // a warp may only touch TMEM lanes 32*(warp % 4) .. +31
     const int half = (warp - 6) >> 2;  // which 128 of the tile's 256 columns
     const int row_in_tile = q * 32 + lane;
-    TileIter it(a);
+    TileIter<CTAS> it(a, rank);
     uint32_t n_tile = 0;
     int cur_b = -1, cur_rb = -1;
     unsigned acc_cnt = 0;
@@ -405,7 +459,8 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
       }
       // the accumulator has been consumed: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
-      mbar_arrive(tmem_empty(as));
+      if constexpr (CTAS == 1) mbar_arrive(tmem_empty(as));
+      else mbar_arrive_leader(tmem_empty(as));
     }
     flush();
   }
@@ -413,9 +468,13 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
   // ------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();  // no CTA of the pair leaves while the other can still signal it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if constexpr (CTAS == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -456,14 +515,57 @@ int make_map(CUtensorMap* m, const void* ptr, int E, long long rows, int batch, 
   return D2B_OK;
 }
 
-// K block per pipeline stage: 16 (64-byte swizzle, 4 stages) by default; D2B_DYNCONV_BK=32 selects the 128-byte
-// swizzle / 2-stage variant (kept for measurement).
-int dyn_block_k() {
-  static const int bk = []() {
+// Variants (all four are built and parity-tested; measured at 16 x 500 x 200x336, E=256):
+//   pair, BK=32 (128-byte swizzle, 3 stages of 64 KB)  1.19 ms   <- default when n > 128
+//   one CTA, BK=16 (64-byte swizzle, 4 stages of 48 KB) 1.23 ms   <- default when n <= 128 (a pair would idle one SM)
+//   one CTA, BK=32 (2 stages of 96 KB)                  1.29 ms
+//   pair, BK=16 (6 stages of 32 KB)                     1.74 ms
+// D2B_DYNCONV_CTAS=1 / D2B_DYNCONV_BK=16|32 override the choice (measurement only).
+int dyn_block_k(int ctas) {
+  static const int forced = []() {
     const char* e = getenv("D2B_DYNCONV_BK");
-    return (e && atoi(e) == 32) ? 32 : 16;
+    const int v = e ? atoi(e) : 0;
+    return (v == 16 || v == 32) ? v : 0;
   }();
-  return bk;
+  return forced ? forced : (ctas == 2 ? 32 : 16);
+}
+int dyn_ctas() {
+  static const int c = []() {
+    const char* e = getenv("D2B_DYNCONV_CTAS");
+    return (e && atoi(e) == 1) ? 1 : 2;
+  }();
+  return c;
+}
+
+template <int BK, int CTAS>
+int launch_dyn(const CUtensorMap& tm_ahi, const CUtensorMap& tm_alo, const CUtensorMap& tm_feat, const DynArgs& a, int sms,
+               int dev, cudaStream_t st) {
+  using C = Cfg<BK, CTAS>;
+  static bool attr_set[64] = {false};
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    D2B_CUDA(cudaFuncSetAttribute(solo_dynconv_kernel<BK, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)C::kSmemBytes));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const long long units = (a.RB + CTAS - 1) / CTAS;
+  const long long tiles = (long long)a.B * units * a.PT;
+  long long grid = tiles * CTAS < sms ? tiles * CTAS : sms;
+  grid -= grid % CTAS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CTAS == 2 ? 1 : 0;
+  D2B_CUDA(cudaLaunchKernelEx(&cfg, solo_dynconv_kernel<BK, CTAS>, tm_ahi, tm_alo, tm_feat, a));
+  D2B_LAUNCH_CHECK();
+  return D2B_OK;
 }
 
 int dyn_check(const d2b_solo_dynamic_masks_params* p) {
@@ -517,7 +619,9 @@ extern "C" int d2b_solo_dynamic_masks(const d2b_solo_dynamic_masks_params* p, vo
   a.counts = p->counts; a.B = p->batch; a.n = p->n; a.E = E; a.hw = p->hw;
   a.RB = (p->n + kBM - 1) / kBM;
   a.PT = (int)((p->hw + kBN - 1) / kBN);
-  const int bk = dyn_block_k();
+  // a cta_group::2 pair works on two row blocks at once; with a single row block (n <= 128) it would idle one SM
+  const int ctas = (dyn_ctas() == 2 && p->n > kBM) ? 2 : 1;
+  const int bk = dyn_block_k(ctas);
   a.KB = (E + bk - 1) / bk;
   a.Wd = (int)((p->hw + 63) / 64);
   a.thr = p->mask_threshold;
@@ -542,7 +646,7 @@ extern "C" int d2b_solo_dynamic_masks(const d2b_solo_dynamic_masks_params* p, vo
   CUtensorMap tm_ahi, tm_alo, tm_feat;
   if ((rc = make_map(&tm_ahi, a_hi, E, p->n, p->batch, kBM, bk)) != D2B_OK) return rc;
   if ((rc = make_map(&tm_alo, a_lo, E, p->n, p->batch, kBM, bk)) != D2B_OK) return rc;
-  if ((rc = make_map(&tm_feat, p->mask_features, E, p->hw, p->batch, kBN, bk)) != D2B_OK) return rc;
+  if ((rc = make_map(&tm_feat, p->mask_features, E, p->hw, p->batch, kBN / ctas, bk)) != D2B_OK) return rc;
 
   const long long total4 = (long long)rows * E / 4;
   dyn_split_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(p->mask_kernels),
@@ -559,21 +663,8 @@ extern "C" int d2b_solo_dynamic_masks(const d2b_solo_dynamic_masks_params* p, vo
     sm_count[dev] = v > 0 ? v : 148;
   }
   const int sms = (dev >= 0 && dev < 64) ? sm_count[dev] : 148;
-  const long long tiles = (long long)a.B * a.RB * a.PT;
-  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  static bool attr_set[2][64] = {{false}};
-  const int vi = bk == 32 ? 0 : 1;
-  if (dev < 0 || dev >= 64 || !attr_set[vi][dev]) {
-    if (bk == 32)
-      D2B_CUDA(cudaFuncSetAttribute(solo_dynconv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<32>::kSmemBytes));
-    else
-      D2B_CUDA(cudaFuncSetAttribute(solo_dynconv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<16>::kSmemBytes));
-    if (dev >= 0 && dev < 64) attr_set[vi][dev] = true;
-  }
-  if (bk == 32)
-    solo_dynconv_kernel<32><<<grid, kThreads, Cfg<32>::kSmemBytes, st>>>(tm_ahi, tm_alo, tm_feat, a);
-  else
-    solo_dynconv_kernel<16><<<grid, kThreads, Cfg<16>::kSmemBytes, st>>>(tm_ahi, tm_alo, tm_feat, a);
-  D2B_LAUNCH_CHECK();
-  return D2B_OK;
+  if (ctas == 2) return bk == 32 ? launch_dyn<32, 2>(tm_ahi, tm_alo, tm_feat, a, sms, dev, st)
+                                 : launch_dyn<16, 2>(tm_ahi, tm_alo, tm_feat, a, sms, dev, st);
+  return bk == 32 ? launch_dyn<32, 1>(tm_ahi, tm_alo, tm_feat, a, sms, dev, st)
+                  : launch_dyn<16, 1>(tm_ahi, tm_alo, tm_feat, a, sms, dev, st);
 }
