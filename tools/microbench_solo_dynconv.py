@@ -55,6 +55,25 @@ for name, fn in (("fused_tcgen05_3xtf32", lambda: solo_dynamic_masks(feat, kern)
     print(json.dumps({"variant": name, "batch": B, "n": n, "hw": [H, W], "channels": E, "ms": med, "min_ms": best,
                       "useful_tflops": flops / med / 1e9, "tensor_tflops_issued": (3 if "fused" in name else 1) * flops / med / 1e9,
                       "logits_bytes_avoided": 4 * B * n * H * W if "fused" in name else 0}))
+# sustained: 300 launches back to back with the SM clock sampled during the run (a 1 kW part under tensor load may sit
+# below its maximum clock: the tensor roofline in cycles is what the kernel is judged on)
+from bench import ClockSampler  # noqa: E402
+cs = ClockSampler(0)
+cs.start()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(300):
+    solo_dynamic_masks(feat, kern)
+e1.record()
+torch.cuda.synchronize()
+clk = cs.summary()
+ms = e0.elapsed_time(e1) / 300
+tiles_per_sm = B * ((n + 127) // 128) * ((H * W + 255) // 256) / 148.0
+mma_cycles = tiles_per_sm * (E // 8) * 3 * 128  # 3 tf32 MMAs of 128 x 256 x 8 per k-step, 128 cycles each at 4096 flop/clk/SM
+print(json.dumps({"variant": "fused_sustained_300_launches", "ms": ms, "issued_tflops": 3 * flops / ms / 1e9, "clocks": clk,
+                  "mma_cycles_per_sm": mma_cycles,
+                  "tensor_pipe_fraction_at_sampled_clock": mma_cycles / (ms * 1e-3 * clk["sm_mhz"] * 1e6) if clk["sm_mhz"] else None}))
+
 # the whole inference tail (solo_v2.py:499-558): conv -> mask stage -> filter -> scoring -> top-k -> Matrix-NMS -> pad
 head = SOLOv2Inference(0.5, 500, "gaussian", 2.0, 0.05, 100)
 sc = torch.rand((B, n), generator=g).to(dev) * 0.9 + 0.1
