@@ -163,6 +163,12 @@ class SoloDynamicMasksParams(C.Structure):
                 ("score_sums", _vp), ("mask_logits", _vp)]
 
 
+class SoloUpsampleParams(C.Structure):
+    _fields_ = [("packed_masks", _vp), ("batch", _i32), ("num_dets", _i32), ("mask_h", _i32), ("mask_w", _i32),
+                ("image_h", _i32), ("image_w", _i32), ("align_corners", _i32), ("mask_threshold", _f32),
+                ("out_masks", _vp), ("out_packed_masks", _vp), ("out_boxes", _vp)]
+
+
 class RoiAlignBackwardParams(C.Structure):
     _fields_ = [("fwd", RoiAlignParams), ("grad_out", _vp), ("grad_features", _vp * MAX_LEVELS)]
 
@@ -190,6 +196,7 @@ OPS = {
     "solo_mask_encode": SoloMaskEncodeParams,
     "solo_postprocess": SoloPostprocessParams,
     "solo_dynamic_masks": SoloDynamicMasksParams,
+    "solo_upsample": SoloUpsampleParams,
 }
 EXPORTS = ["d2b_version", "d2b_status_string", "d2b_last_error", "d2b_kernel_launch_count"] + \
           [f"d2b_{op}{sfx}" for op in OPS for sfx in ("", "_workspace_bytes")]

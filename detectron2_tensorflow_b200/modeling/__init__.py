@@ -6,4 +6,5 @@ from .single_stage_heads.retinanet import RetinaNetInference
 from .anchor_generator import DefaultAnchorGenerator, GridAnchors
 from .matcher import Matcher, label_boxes
 from .single_stage_heads.yolov4_outputs import YOLOv4Inference
-from .single_stage_heads.solo_v2 import point_nms, solo_mask_encode, solo_dynamic_masks, SOLOv2Inference
+from .single_stage_heads.solo_v2 import (point_nms, solo_mask_encode, solo_dynamic_masks, solo_upsample_masks,
+                                         SOLOv2Inference)

@@ -3,7 +3,7 @@ import torch
 
 from ... import _native as nv
 
-__all__ = ["point_nms", "solo_mask_encode", "solo_dynamic_masks", "SOLOv2Inference"]
+__all__ = ["point_nms", "solo_mask_encode", "solo_dynamic_masks", "solo_upsample_masks", "SOLOv2Inference"]
 
 
 def point_nms(inputs, kernel_size=2, scope=None):
@@ -87,6 +87,40 @@ def solo_dynamic_masks(mask_features, mask_kernels, mask_threshold=0.5, counts=N
     nv.call("solo_dynamic_masks", p, dev)
     outs = (packed, sums, ssum) + ((logits,) if return_logits else ())
     return tuple(nv.to_host(o) for o in outs) if host else outs
+
+
+def solo_upsample_masks(packed_masks, mask_hw, image_shape, mask_threshold=0.5, align_corners=False, return_masks=True,
+                        return_packed=False):
+    """The last stage of `MaskKernelBranch.inference` (solo_v2.py:599-627): bilinear `resize_images` of the kept masks
+    to `image_shape`, threshold, boxes from masks -- from the bit-packed masks of `SOLOv2Inference.postprocess`.
+
+    packed_masks int64 [B, D, ceil(h*w/64)], mask_hw = (h, w), image_shape = (H, W).
+    align_corners=False is what `resize_images` does when `tf.compat.v2.image.resize` exists (functional.py:21-24: the
+    align_corners kwarg is dropped, half-pixel centres); True is the TF 1.13 fall-back (:26-35).
+    Returns dict(pred_masks uint8 [B, D, H, W] or None, packed_masks int64 [B, D, ceil(H*W/64)] or None,
+    boxes fp32 [B, D, 4] as (ymin, xmin, ymax, xmax))."""
+    host = not packed_masks.is_cuda
+    dev = nv.device_of(packed_masks)
+    pk = nv.to_device(packed_masks, dev, torch.int64)
+    assert pk.dim() == 3
+    B, D, Wd = pk.shape
+    h, w = int(mask_hw[0]), int(mask_hw[1])
+    H, W = int(image_shape[0]), int(image_shape[1])
+    assert Wd == (h * w + 63) // 64
+    masks = torch.empty((B, D, H, W), dtype=torch.uint8, device=dev) if return_masks else None
+    packed = torch.empty((B, D, (H * W + 63) // 64), dtype=torch.int64, device=dev) if return_packed else None
+    boxes = torch.empty((B, D, 4), dtype=torch.float32, device=dev)
+    p = nv.SoloUpsampleParams()
+    p.packed_masks = pk.data_ptr()
+    p.batch, p.num_dets, p.mask_h, p.mask_w, p.image_h, p.image_w = B, D, h, w, H, W
+    p.align_corners = 1 if align_corners else 0
+    p.mask_threshold = float(mask_threshold)
+    p.out_masks, p.out_packed_masks, p.out_boxes = nv.ptr(masks), nv.ptr(packed), boxes.data_ptr()
+    nv.call("solo_upsample", p, dev)
+    out = dict(pred_masks=masks, packed_masks=packed, boxes=boxes)
+    if host:
+        out = {k: (None if v is None else nv.to_host(v)) for k, v in out.items()}
+    return out
 
 
 class SOLOv2Inference(object):

@@ -603,6 +603,32 @@ D2B_API size_t d2b_solo_postprocess_workspace_bytes(const d2b_solo_postprocess_p
 D2B_API int d2b_solo_postprocess(const d2b_solo_postprocess_params* p, void* workspace, size_t workspace_bytes,
                                  d2b_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * SOLOv2: image-size masks and boxes from the kept masks
+ *                          lib/modeling/single_stage_heads/solo_v2.py:599-627
+ *   pred_masks = resize_images(pred_masks [N, D, h, w], image_shape) (bilinear)   (:599-601)
+ *   pred_masks = cast(pred_masks > mask_threshold)                                (:602)
+ *   boxes from masks: mean / where / reduce_min / reduce_max                      (:606-625)
+ * resize_images (lib/layers/functional.py:9-36) resolves to tf.compat.v2.image.resize when TensorFlow has it
+ * (half-pixel centres; the align_corners kwarg is filtered out) and to tf.image.resize_images(align_corners=True)
+ * otherwise: `align_corners` selects the convention.  Input: the bit-packed masks d2b_solo_postprocess emits
+ * (rows past the valid count are zero and give empty masks and zero boxes, like the reference's padding).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const uint64_t* packed_masks; /* [B, D, ceil(mask_h*mask_w/64)] */
+  int32_t batch, num_dets;
+  int32_t mask_h, mask_w;
+  int32_t image_h, image_w;
+  int32_t align_corners; /* 0 = half-pixel centres (tf.compat.v2.image.resize), 1 = align_corners=True (TF 1.13) */
+  float mask_threshold;
+  uint8_t* out_masks;         /* optional [B, D, image_h, image_w] {0,1} */
+  uint64_t* out_packed_masks; /* optional [B, D, ceil(image_h*image_w/64)] */
+  float* out_boxes;           /* [B, D, 4] (ymin, xmin, ymax, xmax) */
+} d2b_solo_upsample_params;
+D2B_API size_t d2b_solo_upsample_workspace_bytes(const d2b_solo_upsample_params* p);
+D2B_API int d2b_solo_upsample(const d2b_solo_upsample_params* p, void* workspace, size_t workspace_bytes,
+                              d2b_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

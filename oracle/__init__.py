@@ -464,3 +464,16 @@ def solo_postprocess(mask_logits, scores, classes, strides, mask_threshold=0.5, 
            C.c_float(mask_threshold), int(pre_nms_topk), {"gaussian": 0, "linear": 1}[kernel], C.c_float(sigma),
            C.c_float(update_score_threshold), D, _p(om), _p(oc), _p(os_), _p(ov))
     return om, oc, os_, ov.astype(bool), int(nv)
+
+
+def solo_upsample_boxes(masks, image_hw, align_corners=False, mask_threshold=0.5):
+    """solo_v2.py:599-627 for one image: masks [D,h,w] fp32 0/1 -> (image masks uint8 [D,H,W], boxes [D,4] yxyx).
+    align_corners=False: tf.compat.v2.image.resize (half-pixel centres); True: tf.image.resize_images(align_corners=True)."""
+    m = _f32(masks)
+    D, h, w = m.shape
+    H, W = int(image_hw[0]), int(image_hw[1])
+    out = np.empty((D, H, W), np.uint8)
+    boxes = np.empty((D, 4), np.float32)
+    lib().orc_solo_upsample_boxes(_p(m), C.c_int64(D), h, w, H, W, int(bool(align_corners)), C.c_float(mask_threshold),
+                                  _p(out), _p(boxes))
+    return out, boxes

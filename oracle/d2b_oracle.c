@@ -1253,3 +1253,75 @@ ORC_API int orc_solo_postprocess(const float* mask_logits, const float* scores, 
   free(ks); free(kept); free(ss); free(sm); free(masks);
   return nv;
 }
+
+/* lib/modeling/single_stage_heads/solo_v2.py:599-627: what MaskKernelBranch.inference does with the kept masks after
+ * the per-image tail: resize_images(bilinear) to the image size -> > mask_threshold -> boxes from masks.
+ *   resize_images (lib/layers/functional.py:9-36) picks tf.compat.v2.image.resize when it exists (TF >= 1.14; the
+ *   align_corners kwarg is then filtered out, :23-24 -> half-pixel centres) and tf.image.resize_images(
+ *   align_corners=True) otherwise (:26-35): `align_corners` selects which of the two is restated.
+ *   TF ResizeBilinear CPU kernel (un-vendored tensorflow, core/kernels/resize_bilinear_op.cc +
+ *   image_resizer_state.h), fp32: scale = (align_corners && out > 1) ? (in-1)/(float)(out-1) : in/(float)out;
+ *   src = half_pixel ? (i + 0.5f)*scale - 0.5f : i*scale; lower = max((int)floorf(src), 0);
+ *   upper = min((int)ceilf(src), in-1); lerp = src - floorf(src);
+ *   top = tl + (tr - tl)*x_lerp; bottom = bl + (br - bl)*x_lerp; value = top + (bottom - top)*y_lerp.
+ *   boxes (:606-625): yy = mask*y, xx = mask*x; mean = sum/(count + 1e-5); yy = where(yy > 0, yy, mean);
+ *   [ymin, xmin, ymax, xmax] = min / max over ALL pixels (so the mean always takes part, and mask pixels in row /
+ *   column 0 count as "mean").  The sums are integer valued; TF's fp32 reduce_sum order is unspecified, here they
+ *   are exact (double) and rounded once.
+ * masks [D, h, w] fp32 0/1 -> out_masks [D, H, W] uint8 0/1, boxes [D, 4]. */
+static void orc_resize_taps(int in_size, int out_size, int align_corners, int* lo, int* hi, float* lerp) {
+  const float scale = (align_corners && out_size > 1) ? (float)(in_size - 1) / (float)(out_size - 1)
+                                                      : (float)in_size / (float)out_size;
+  for (int i = 0; i < out_size; ++i) {
+    float src;
+    if (align_corners) {
+      src = (float)i * scale;
+    } else {
+      src = (float)i + 0.5f;
+      src = src * scale;
+      src = src - 0.5f;
+    }
+    const float f = floorf(src);
+    int l = (int)f; if (l < 0) l = 0;
+    int u = (int)ceilf(src); if (u > in_size - 1) u = in_size - 1;
+    lo[i] = l; hi[i] = u; lerp[i] = src - f;
+  }
+}
+ORC_API void orc_solo_upsample_boxes(const float* masks, int64_t D, int h, int w, int H, int W, int align_corners,
+                                     float thr, uint8_t* out_masks, float* boxes) {
+  int* ylo = (int*)malloc(sizeof(int) * (size_t)(2 * H + 2 * W + 4));
+  int* yhi = ylo + H; int* xlo = yhi + H; int* xhi = xlo + W;
+  float* yl = (float*)malloc(sizeof(float) * (size_t)(H + W + 2));
+  float* xl = yl + H;
+  orc_resize_taps(h, H, align_corners, ylo, yhi, yl);
+  orc_resize_taps(w, W, align_corners, xlo, xhi, xl);
+#pragma omp parallel for num_threads(ORC_NT) schedule(static)
+  for (int64_t d = 0; d < D; ++d) {
+    const float* m = masks + (size_t)d * h * w;
+    uint8_t* o = out_masks + (size_t)d * H * W;
+    double cnt = 0.0, sy = 0.0, sx = 0.0;
+    float ymin = INFINITY, xmin = INFINITY, ymax = -INFINITY, xmax = -INFINITY;
+    for (int y = 0; y < H; ++y) {
+      const float* r0 = m + (size_t)ylo[y] * w;
+      const float* r1 = m + (size_t)yhi[y] * w;
+      for (int x = 0; x < W; ++x) {
+        const float tl = r0[xlo[x]], tr = r0[xhi[x]], bl = r1[xlo[x]], br = r1[xhi[x]];
+        float top = tr - tl; top = top * xl[x]; top = tl + top;
+        float bot = br - bl; bot = bot * xl[x]; bot = bl + bot;
+        float v = bot - top; v = v * yl[y]; v = top + v;
+        const int on = v > thr;
+        o[(size_t)y * W + x] = (uint8_t)on;
+        if (on) {
+          cnt += 1.0; sy += (double)y; sx += (double)x;
+          if (y > 0) { if ((float)y < ymin) ymin = (float)y; if ((float)y > ymax) ymax = (float)y; }
+          if (x > 0) { if ((float)x < xmin) xmin = (float)x; if ((float)x > xmax) xmax = (float)x; }
+        }
+      }
+    }
+    const float den = (float)cnt + 1e-5f;
+    const float ymean = (float)sy / den, xmean = (float)sx / den;
+    boxes[d * 4 + 0] = fminf(ymin, ymean); boxes[d * 4 + 1] = fminf(xmin, xmean);
+    boxes[d * 4 + 2] = fmaxf(ymax, ymean); boxes[d * 4 + 3] = fmaxf(xmax, xmean);
+  }
+  free(ylo); free(yl);
+}

@@ -296,6 +296,13 @@ def main(out_path=None):
     out.update(so_in_logits=so_logits, so_in_scores=so_sc, so_in_classes=so_cl, so_in_strides=so_st, so_in_counts=so_cnt,
                so_in_mask_features=mfeat, so_in_kernels=so_kern)
 
+    # ---- 15. the same inference with image_shape != mask-feature size: resize_images (functional.py:9-36 takes the
+    # tf.compat.v2.image.resize branch on the shim -> half-pixel centres) + threshold + boxes from masks (:599-627)
+    Hi, Wi = 95, 130
+    res2 = R.solo.MaskKernelBranch.inference(shead, [t(p_) for p_ in probs], [t(k_) for k_ in kerns], t(mfeat), [Hi, Wi])
+    out.update(so2_masks=np.asarray(res2.get_field("pred_masks")).astype(np.uint8), so2_boxes=np.asarray(res2.boxes),
+               so2_image_shape=np.array([Hi, Wi], np.int32))
+
     out_path = out_path or os.path.join(HERE, "reference_python.npz")
     np.savez_compressed(out_path, **out)
     print(os.path.basename(out_path) + ":", len(out), "arrays,", os.path.getsize(out_path) // 1024, "KiB")

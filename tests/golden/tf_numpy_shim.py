@@ -415,9 +415,30 @@ def build_tf():
         return t(np.einsum("nhwc,co->nhwo", x, f[0, 0]).astype(np.float32))
 
     def resize_same(images, size, method=None, **kw):
-        x = np.asarray(images)
-        assert tuple(int(v) for v in size) == x.shape[1:3], "shim: resize only to the same size (identity)"
-        return t(x)
+        """tf.compat.v2.image.resize(images NHWC, size, 'bilinear'): ResizeBilinear with half-pixel centres, fp32,
+        one rounding per written operation (numpy float32 arithmetic)."""
+        x = np.asarray(images, np.float32)
+        oh, ow = (int(v) for v in size)
+        if (oh, ow) == x.shape[1:3]:
+            return t(x)
+        assert method in (None, "bilinear"), "shim: bilinear resize only"
+        f32 = np.float32
+
+        def taps(n_in, n_out):
+            scale = f32(n_in) / f32(n_out)
+            src = (np.arange(n_out, dtype=np.float32) + f32(0.5)) * scale - f32(0.5)
+            fl = np.floor(src)
+            lo = np.maximum(fl.astype(np.int64), 0)
+            hi = np.minimum(np.ceil(src).astype(np.int64), n_in - 1)
+            return lo, hi, (src - fl).astype(np.float32)
+        ylo, yhi, yl = taps(x.shape[1], oh)
+        xlo, xhi, xl = taps(x.shape[2], ow)
+        xl_ = xl[None, None, :, None]
+        yl_ = yl[None, :, None, None]
+        r0, r1 = x[:, ylo], x[:, yhi]
+        top = r0[:, :, xlo] + (r0[:, :, xhi] - r0[:, :, xlo]) * xl_
+        bot = r1[:, :, xlo] + (r1[:, :, xhi] - r1[:, :, xlo]) * xl_
+        return t((top + (bot - top) * yl_).astype(np.float32))
     tf.nn = types.SimpleNamespace(conv2d=conv2d, max_pool=max_pool, top_k=_top_k, sigmoid=un(lambda x: (np.float32(1) / (np.float32(1) + np.exp(-x)))),
                                   softmax=softmax, relu=un(lambda x: np.maximum(x, 0)))
     tf.image = types.SimpleNamespace(crop_and_resize=_crop_and_resize, non_max_suppression=_non_max_suppression,

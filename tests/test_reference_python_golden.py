@@ -177,3 +177,14 @@ def test_solo_inference_tail(oracle_lib, z):
         assert np.allclose(os_, z["so_scores"][b], rtol=1e-5, atol=1e-7)
         total += nv
     assert total > 0
+
+
+def test_solo_image_masks_and_boxes(oracle_lib, z):
+    """The end of MaskKernelBranch.inference (solo_v2.py:599-627) with image_shape != mask-feature size: the reference's
+    resize_images (half-pixel branch on the shim) + threshold + boxes from masks, bit-exact."""
+    H, W = (int(v) for v in z["so2_image_shape"])
+    for b in range(z["so_masks"].shape[0]):
+        masks, boxes = oracle_lib.solo_upsample_boxes(z["so_masks"][b], (H, W), False, 0.5)
+        assert np.array_equal(masks, z["so2_masks"][b])
+        assert np.array_equal(boxes, z["so2_boxes"][b])
+    assert z["so2_masks"].any() and not z["so2_masks"].all()
