@@ -433,6 +433,12 @@ def run_gpu(args):
                            "inputs uploaded and all four outputs downloaded every step), 2-image chunks pipelined "
                            "over three CUDA streams (upload / kernels / download)"}
 
+    # ---- the other BASELINE.json configs (parity-test cases, not bench lines): device-resident timings, N=1 only
+    if world == 1 and not args.no_extras:
+        del hx, ho
+        torch.cuda.empty_cache()
+        line["other_configs"] = other_configs(dev)
+
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     if world == 1 and not args.no_cpu:
         cb, _, _ = cpu_baseline_dict(host, 2, 2, 1, "first 2 of the 16 images, 2 timed steps after 1 warm-up")
@@ -441,6 +447,75 @@ def run_gpu(args):
         EMIT(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs(dev, iters=10):
+    """configs[2] (RetinaNet post-processing, batch 32) and configs[3] (SOLOv2: Matrix-NMS over 500 candidates at 1/4
+    resolution, batch 16, plus the steps either side of it), inputs resident, CUDA events, median of `iters` after 3
+    warm-ups; inputs (2 GB each) are larger than L2.  Informational: a failure is recorded, it does not fail the bench."""
+    from detectron2_tensorflow_b200.layers import matrix_nms
+    from detectron2_tensorflow_b200.modeling import (RetinaNetInference, SOLOv2Inference, solo_dynamic_masks,
+                                                     solo_upsample_masks)
+    from detectron2_tensorflow_b200.utils import synthetic as syn
+    out = {}
+    g = torch.Generator(device=dev).manual_seed(0)
+
+    def med(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+    try:
+        N, K = 32, 80
+        anchors = [torch.from_numpy(a).to(dev) for a in syn.retinanet_anchors()]
+        cls = [torch.randn((N, a.shape[0], K), device=dev, generator=g) * 1.5 - 4.6 for a in anchors]
+        dl = [torch.randn((N, a.shape[0], 4), device=dev, generator=g) * 0.3 for a in anchors]
+        head = RetinaNetInference(num_classes=K)
+        ms = med(lambda: head.inference(cls, dl, anchors))
+        nsc = sum(c.numel() for c in cls)
+        out["configs[2] RetinaNet R50-FPN post-processing, batch 32"] = {
+            "ms": ms, "images_per_s": N / ms * 1e3, "logit_GB": nsc * 4 / 1e9, "single_read_GBps": nsc * 4 / ms / 1e6}
+        del cls, dl, anchors
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out["configs[2]"] = {"error": repr(e)[:200]}
+    try:
+        B, n, H, W, E = 16, 500, 200, 336, 256
+        m, c, s = syn.solo_masks(n, hw=(H, W), seed=7)
+        masks = torch.from_numpy(m).to(dev)[None].repeat(B, 1, 1, 1).contiguous()
+        classes = torch.from_numpy(c).to(dev)[None].repeat(B, 1).contiguous()
+        scores = torch.from_numpy(s).to(dev)[None].repeat(B, 1).contiguous()
+        ms = med(lambda: matrix_nms(masks, classes, scores))
+        by = masks.numel() * 4
+        r = {"matrix_nms_fp32_masks_ms": ms, "matrix_nms_images_per_s": B / ms * 1e3, "mask_read_GBps": by / ms / 1e6}
+        del masks
+        torch.cuda.empty_cache()
+        feat = torch.randn((B, H, W, E), device=dev, generator=g)
+        kern = torch.randn((B, n, E), device=dev, generator=g) / 16
+        ms = med(lambda: solo_dynamic_masks(feat, kern))
+        r.update(dynamic_conv_plus_mask_stage_ms=ms, tf32_mma_tflops_issued=3 * 2.0 * B * n * H * W * E / ms / 1e9)
+        head = SOLOv2Inference(0.5, 500, "gaussian", 2.0, 0.05, 100)
+        strides = torch.full((B, n), 8.0, device=dev)
+        ms = med(lambda: head.postprocess(None, scores, classes, strides, return_masks=False, mask_features=feat,
+                                          mask_kernels=kern))
+        r.update(inference_tail_from_features_ms=ms, inference_tail_images_per_s=B / ms * 1e3)
+        obj = np.stack([syn.solo_masks(100, hw=(H, W), seed=70 + i)[0] for i in range(B)]).reshape(B, 100, -1).astype(np.uint8)
+        obj = np.concatenate([obj, np.zeros((B, 100, (-obj.shape[-1]) % 64), np.uint8)], -1)
+        kept = torch.from_numpy(np.packbits(obj, axis=-1, bitorder="little").view(np.int64)).to(dev)
+        ms = med(lambda: solo_upsample_masks(kept, (H, W), (800, 1333), 0.5, False))
+        r.update(image_masks_and_boxes_ms=ms, image_mask_write_GBps=B * 100 * 800 * 1333 / ms / 1e6)
+        out["configs[3] SOLOv2 R50: 500 candidates at 200x336, batch 16"] = r
+    except Exception as e:  # noqa: BLE001
+        out["configs[3]"] = {"error": repr(e)[:200]}
+    return out
 
 
 def _protect_stdout():
@@ -471,6 +546,8 @@ def main():
     ap.add_argument("--in-flight", type=int, default=3, dest="in_flight",
                     help="graphed steps replayed concurrently on alternating streams (1 = strictly one after another)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", dest="no_extras",
+                    help="skip the device timings of the other BASELINE.json configs (other_configs key)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -71,7 +71,6 @@ __global__ void __launch_bounds__(kUpThreads) solo_upsample_kernel(const UpArgs 
   float* rows = reinterpret_cast<float*>(up_smem);                                 // [rows_cap][w]
   int2* span = reinterpret_cast<int2*>(rows + (((size_t)a.rows_cap * a.w + 1) & ~(size_t)1));  // [rows_cap] first / last set column
   Tap* xt = reinterpret_cast<Tap*>(span + a.rows_cap);                             // [W]
-  __shared__ int s_any;
 
   const int b = blockIdx.z, d = blockIdx.y;
   const long long hw_out = (long long)a.H * a.W;
@@ -86,8 +85,28 @@ __global__ void __launch_bounds__(kUpThreads) solo_upsample_kernel(const UpArgs 
   const int n_rows = r1 - r0 + 1;  // <= rows_cap by construction (host)
   const u64* src = a.packed + ((size_t)b * a.D + d) * a.Wd_in;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_any = 0;
-  __syncthreads();
+  uint8_t* om = a.out_masks ? a.out_masks + ((size_t)b * a.D + d) * hw_out : nullptr;
+  u64* op = a.out_packed ? a.out_packed + ((size_t)b * a.D + d) * a.Wd_out : nullptr;
+  const bool vec16 = om && ((reinterpret_cast<uintptr_t>(om) & 15) == 0);  // flat runs start at multiples of 16
+  {
+    // ---- cheap rejection first: OR of the words that hold source rows r0..r1 (edge words may carry neighbouring
+    // rows' bits: conservative).  Most chunks of an image see no mask at all and leave as zeros right here.
+    const long long w_first = ((long long)r0 * a.w) >> 6, w_last = (((long long)(r1 + 1) * a.w - 1) >> 6);
+    u64 acc = 0;
+    for (long long q = w_first + tid; q <= w_last; q += kUpThreads) acc |= __ldg(src + q);
+    if (!__syncthreads_or(acc != 0ull)) {
+      for (int it = 0; it < a.iters; ++it) {
+        const long long p = p_begin + ((long long)it * kUpThreads + tid) * kRun;
+        if (p >= p_end) break;
+        if (om) {
+          if (vec16 && p + kRun <= p_end) *reinterpret_cast<uint4*>(om + p) = make_uint4(0, 0, 0, 0);
+          else for (long long q = p; q < min(p + kRun, p_end); ++q) om[q] = 0;
+        }
+        if (op && (p & 63) == 0) op[p >> 6] = 0ull;  // one 64-bit word = 4 runs; the owner of the first run writes it
+      }
+      return;
+    }
+  }
 
   // ---- stage the source rows: bits -> fp32 0/1, and each row's span of set columns
   for (int r = warp; r < n_rows; r += kUpThreads / 32) {
@@ -104,31 +123,9 @@ __global__ void __launch_bounds__(kUpThreads) solo_upsample_kernel(const UpArgs 
       first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
       last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
     }
-    if (lane == 0) {
-      span[r] = make_int2(first, last);
-      if (last >= 0) s_any = 1;
-    }
+    if (lane == 0) span[r] = make_int2(first, last);
   }
   __syncthreads();
-  uint8_t* om = a.out_masks ? a.out_masks + ((size_t)b * a.D + d) * hw_out : nullptr;
-  u64* op = a.out_packed ? a.out_packed + ((size_t)b * a.D + d) * a.Wd_out : nullptr;
-  const bool vec16 = om && ((reinterpret_cast<uintptr_t>(om) & 15) == 0);  // flat runs start at multiples of 16
-
-  if (!s_any) {  // nothing set in the rows this chunk samples: zeros, no sampling
-    for (int it = 0; it < a.iters; ++it) {
-      const long long p = p_begin + ((long long)it * kUpThreads + tid) * kRun;
-      if (p >= p_end) break;
-      if (om) {
-        if (vec16 && p + kRun <= p_end) *reinterpret_cast<uint4*>(om + p) = make_uint4(0, 0, 0, 0);
-        else for (long long q = p; q < min(p + kRun, p_end); ++q) om[q] = 0;
-      }
-      if (op && (p & 63) == 0) {
-        // packed output: one 64-bit word = 4 runs; the thread owning the first run of a word writes it
-        if (p < hw_out) op[p >> 6] = 0ull;
-      }
-    }
-    return;
-  }
   for (int x = tid; x < a.W; x += kUpThreads) {
     int lo, hi;
     float l;
@@ -139,47 +136,90 @@ __global__ void __launch_bounds__(kUpThreads) solo_upsample_kernel(const UpArgs 
   }
   __syncthreads();
 
-  u64 cnt = 0, sum_y = 0, sum_x = 0;
+  // per-thread statistics fit 32 bits (<= iters * 16 pixels per thread, coordinates < 65536); widened at the reduction
+  unsigned cnt32 = 0, sum_y32 = 0, sum_x32 = 0;
   int min_y = 0x7fffffff, max_y = -1, min_x = 0x7fffffff, max_x = -1;
+  // A warp owns 512 consecutive flat pixels per step; in sub-step j lane l samples pixel base + 32 j + l, so the tap
+  // table and the source rows are read without bank conflicts (neighbouring pixels share or neighbour their taps) and
+  // the 32 decisions leave as one ballot = 32 packed mask bits.  Lane j keeps ballot j; a shuffle then hands every
+  // lane the 16 bits of ITS 16-pixel run for the 16-byte uint8 store.
+  const int chunk_len = (int)(p_end - p_begin);
   for (int it = 0; it < a.iters; ++it) {
-    const long long p = p_begin + ((long long)it * kUpThreads + tid) * kRun;
-    unsigned bits = 0;
-    if (p < p_end) {
-      int y = (int)(p / a.W), x = (int)(p - (long long)y * a.W);
-      const int n = (int)min((long long)kRun, p_end - p);
-      int k = 0;
-      while (k < n) {
-        // the part of the run inside output row y
-        const int seg = min(n - k, a.W - x);
-        int ylo, yhi;
-        float yl;
-        resize_tap(y, a.h, a.scale_y, a.align_corners, ylo, yhi, yl);
-        const int2 s0 = span[ylo - r0], s1 = span[yhi - r0];
-        const int xa = xt[x].lo, xb = xt[x + seg - 1].hi;
-        const bool empty = (s0.y < xa || s0.x > xb) && (s1.y < xa || s1.x > xb);
+    const int off = (it * (kUpThreads / 32) + warp) * (32 * kRun);  // offset of the warp's 512 pixels in the chunk
+    if (off >= chunk_len) break;  // warp-uniform
+    const long long base = p_begin + off;
+    int left = chunk_len - off - lane;  // > 0 while this lane's pixel is inside the chunk
+    int y = (int)((base + lane) / a.W), x = (int)((base + lane) - (long long)y * a.W);
+    int y_cached = -1;
+    float yl = 0.0f;
+    int2 s0 = make_int2(0, -1), s1 = make_int2(0, -1);
+    const float *q0 = rows, *q1 = rows;
+    unsigned mine = 0;
+    // warp-level rejection: the 512 pixels lie in at most ceil(512 / W) + 1 output rows; if the source rows of each of
+    // them are empty over the columns the warp can touch, all 16 ballots are zero
+    bool skip;
+    {
+      const int span_len = min(32 * kRun, chunk_len - off);
+      const int ya = (int)(base / a.W), xa = (int)(base - (long long)ya * a.W);
+      const int yb = (int)((base + span_len - 1) / a.W), xb = (int)((base + span_len - 1) - (long long)yb * a.W);
+      skip = true;
+      for (int yy = ya; yy <= yb && skip; ++yy) {
+        int lo_r, hi_r;
+        float l_r;
+        resize_tap(yy, a.h, a.scale_y, a.align_corners, lo_r, hi_r, l_r);
+        const int c0 = xt[yy == ya ? xa : 0].lo, c1 = xt[yy == yb ? xb : a.W - 1].hi;
+        const int2 t0 = span[lo_r - r0], t1 = span[hi_r - r0];
+        skip = (t0.y < c0 || t0.x > c1) && (t1.y < c0 || t1.x > c1);
+      }
+    }
+    if (!skip) {
+#pragma unroll 4
+    for (int j = 0; j < kRun; ++j) {
+      bool on = false;
+      if (left > 0) {
+        if (y != y_cached) {
+          int ylo, yhi;
+          resize_tap(y, a.h, a.scale_y, a.align_corners, ylo, yhi, yl);
+          s0 = span[ylo - r0];
+          s1 = span[yhi - r0];
+          q0 = rows + (ylo - r0) * a.w;
+          q1 = rows + (yhi - r0) * a.w;
+          y_cached = y;
+        }
+        const Tap t = xt[x];
+        const int lo = t.lo, hi = t.hi;
+        const bool empty = (s0.y < lo || s0.x > hi) && (s1.y < lo || s1.x > hi);
         if (!empty) {
-          const float* q0 = rows + (size_t)(ylo - r0) * a.w;
-          const float* q1 = rows + (size_t)(yhi - r0) * a.w;
-          for (int j = 0; j < seg; ++j) {
-            const Tap t = xt[x + j];
-            const float tl = q0[t.lo], tr = q0[t.hi], bl = q1[t.lo], br = q1[t.hi];
-            float top = tr - tl; top = top * t.lerp; top = tl + top;
-            float bot = br - bl; bot = bot * t.lerp; bot = bl + bot;
-            float v = bot - top; v = v * yl; v = top + v;
-            if (v > a.thr) {
-              bits |= 1u << (k + j);
-              const int xx = x + j;
-              cnt += 1; sum_y += (unsigned)y; sum_x += (unsigned)xx;
-              if (y > 0) { min_y = min(min_y, y); max_y = max(max_y, y); }
-              if (xx > 0) { min_x = min(min_x, xx); max_x = max(max_x, xx); }
-            }
+          const float tl = q0[lo], tr = q0[hi], bl = q1[lo], br = q1[hi];
+          float top = tr - tl; top = top * t.lerp; top = tl + top;
+          float bot = br - bl; bot = bot * t.lerp; bot = bl + bot;
+          float v = bot - top; v = v * yl; v = top + v;
+          on = v > a.thr;
+          if (on) {
+            cnt32 += 1; sum_y32 += (unsigned)y; sum_x32 += (unsigned)x;
+            if (y > 0) { min_y = min(min_y, y); max_y = max(max_y, y); }
+            if (x > 0) { min_x = min(min_x, x); max_x = max(max_x, x); }
           }
         }
-        k += seg;
-        x += seg;
-        if (x >= a.W) { x = 0; ++y; }
       }
-      if (om) {
+      const unsigned word = __ballot_sync(0xffffffffu, on);  // pixels base + 32 j .. + 31
+      if (lane == j) mine = word;
+      left -= 32;
+      x += 32;
+      while (x >= a.W) { x -= a.W; ++y; }
+    }
+    }
+    if (op) {  // lanes 0..15 hold the 16 ballots: two neighbours make one 64-bit word
+      const unsigned hi32 = __shfl_down_sync(0xffffffffu, mine, 1);
+      const long long pw = base + 64ll * (lane >> 1);
+      if (lane < kRun && (lane & 1) == 0 && pw < p_end) op[pw >> 6] = (u64)mine | ((u64)hi32 << 32);
+    }
+    if (om) {
+      const unsigned src_word = __shfl_sync(0xffffffffu, mine, lane >> 1);
+      const unsigned bits = (src_word >> (16 * (lane & 1))) & 0xffffu;
+      const long long pr = base + (long long)lane * kRun;  // this lane's 16-pixel run
+      if (pr < p_end) {
+        const int n = (int)min((long long)kRun, p_end - pr);
         if (vec16 && n == kRun) {
           uint4 v4;
           unsigned* wv = reinterpret_cast<unsigned*>(&v4);
@@ -188,21 +228,15 @@ __global__ void __launch_bounds__(kUpThreads) solo_upsample_kernel(const UpArgs 
             const unsigned nib = (bits >> (4 * q)) & 15u;
             wv[q] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
           }
-          *reinterpret_cast<uint4*>(om + p) = v4;
+          *reinterpret_cast<uint4*>(om + pr) = v4;
         } else {
-          for (int j = 0; j < n; ++j) om[p + j] = (uint8_t)((bits >> j) & 1u);
+          for (int q = 0; q < n; ++q) om[pr + q] = (uint8_t)((bits >> q) & 1u);
         }
       }
     }
-    if (op) {
-      // 4 consecutive lanes hold the 4 runs of one 64-bit word (runs start at multiples of 16, chunks at multiples of 64)
-      u64 word = (u64)bits << (16 * (lane & 3));
-      word |= __shfl_xor_sync(0xffffffffu, word, 1);
-      word |= __shfl_xor_sync(0xffffffffu, word, 2);
-      if ((lane & 3) == 0 && p < p_end) op[p >> 6] = word;
-    }
   }
   // ---- box statistics: warp reduce, then one set of atomics per warp
+  u64 cnt = cnt32, sum_y = sum_y32, sum_x = sum_x32;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);

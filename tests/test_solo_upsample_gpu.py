@@ -30,7 +30,7 @@ def blobs(rng, B, D, h, w):
     for b in range(B):
         for d in range(D):
             cy, cx = rng.uniform(0, h), rng.uniform(0, w)
-            ry, rx = rng.uniform(0.6, h / 2), rng.uniform(0.6, w / 2)
+            ry, rx = rng.uniform(0.6, max(0.7, h / 2)), rng.uniform(0.6, max(0.7, w / 2))
             m[b, d] = (((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1).astype(np.float32)
     return m
 

@@ -9,7 +9,8 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from detectron2_tensorflow_b200.modeling import SOLOv2Inference, solo_dynamic_masks, solo_mask_encode  # noqa: E402
+from detectron2_tensorflow_b200.modeling import (SOLOv2Inference, solo_dynamic_masks, solo_mask_encode,  # noqa: E402
+                                                 solo_upsample_masks)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)
@@ -93,6 +94,26 @@ for name, fn in (("tail_from_features_fused", lambda: head.postprocess(None, sc,
     med, best = timed(fn)
     print(json.dumps({"variant": name, "batch": B, "n": n, "hw": [H, W], "channels": E, "ms": med, "min_ms": best,
                       "images_per_s": B / med * 1e3}))
+# the last stage (solo_v2.py:599-627): kept masks -> 800x1333 image masks + boxes.  Two inputs: object-like masks
+# (ellipses, utils/synthetic.solo_masks: what a trained head emits) and the worst case (the noise masks the random
+# features above produce: every 16-pixel run has to be sampled)
+import numpy as np  # noqa: E402
+from detectron2_tensorflow_b200.utils import synthetic as syn  # noqa: E402
+IH, IW = 800, 1333
+obj = np.stack([syn.solo_masks(100, hw=(H, W), seed=70 + i)[0] for i in range(B)])  # [B, 100, H, W] fp32 0/1
+flat = obj.reshape(B, 100, -1).astype(np.uint8)
+flat = np.concatenate([flat, np.zeros((B, 100, (-flat.shape[-1]) % 64), np.uint8)], -1)
+kept_obj = torch.from_numpy(np.packbits(flat, axis=-1, bitorder="little").view(np.int64)).to(dev)
+kept_noise = head.postprocess(None, sc, cl, stv, return_masks=False, mask_features=feat, mask_kernels=kern)["packed_masks"]
+for inp, kept in (("object_masks", kept_obj), ("noise_masks_worst_case", kept_noise)):
+    for name, kw in (("upsample_uint8_masks_and_boxes", dict(return_masks=True, return_packed=False)),
+                     ("upsample_packed_masks_and_boxes", dict(return_masks=False, return_packed=True))):
+        med, best = timed(lambda: solo_upsample_masks(kept, (H, W), (IH, IW), 0.5, False, **kw))
+        out_bytes = B * 100 * IH * IW * (1 if kw["return_masks"] else 1 / 8)
+        print(json.dumps({"variant": name, "input": inp, "batch": B, "dets": 100, "from": [H, W], "to": [IH, IW], "ms": med,
+                          "min_ms": best, "out_GB": out_bytes / 1e9, "write_GBps": out_bytes / med / 1e6,
+                          "coverage": float(obj.mean()) if inp == "object_masks" else None,
+                          "reference_fp32_bytes_per_pass_GB": B * 100 * IH * IW * 4 / 1e9}))
 a = solo_dynamic_masks(feat, kern)
 b = library_route(False)
 mism = int((a[0] != b[0]).sum())
