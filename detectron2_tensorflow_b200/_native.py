@@ -163,6 +163,13 @@ class SoloDynamicMasksParams(C.Structure):
                 ("score_sums", _vp), ("mask_logits", _vp)]
 
 
+class SoloSelectParams(C.Structure):
+    _fields_ = [("scores", _vp), ("kernels", _vp), ("cell_strides", _vp), ("batch", _i32), ("num_cells", _i32),
+                ("num_classes", _i32), ("channels", _i32), ("score_threshold", _f32), ("max_candidates", _i32),
+                ("out_scores", _vp), ("out_classes", _vp), ("out_strides", _vp), ("out_kernels", _vp),
+                ("out_counts", _vp), ("out_total", _vp)]
+
+
 class SoloUpsampleParams(C.Structure):
     _fields_ = [("packed_masks", _vp), ("batch", _i32), ("num_dets", _i32), ("mask_h", _i32), ("mask_w", _i32),
                 ("image_h", _i32), ("image_w", _i32), ("align_corners", _i32), ("mask_threshold", _f32),
@@ -197,6 +204,7 @@ OPS = {
     "solo_postprocess": SoloPostprocessParams,
     "solo_dynamic_masks": SoloDynamicMasksParams,
     "solo_upsample": SoloUpsampleParams,
+    "solo_select": SoloSelectParams,
 }
 EXPORTS = ["d2b_version", "d2b_status_string", "d2b_last_error", "d2b_kernel_launch_count"] + \
           [f"d2b_{op}{sfx}" for op in OPS for sfx in ("", "_workspace_bytes")]

@@ -443,3 +443,113 @@ extern "C" int d2b_solo_postprocess(const d2b_solo_postprocess_params* p, void* 
   }
   return D2B_OK;
 }
+
+// ------------------------------------------------------------------ candidate selection (solo_v2.py:481-497)
+//   keep_inds = tf.where(pred_scores > score_threshold)      (row-major over [G cells, K classes])
+//   scores = gather_nd, classes = keep_inds[:, 1], kernels = gather(pred_kernels, keep_inds[:, 0]), strides likewise
+// One CTA per image walks the G*K scores in order: ballot + warp prefix + block prefix give every kept element its
+// rank, i.e. the compaction is ORDERED (tf.where order) without a sort.  Candidates past `cap` are dropped (the
+// reference has no cap; `out_total` reports how many passed so the caller can detect it).
+namespace d2b {
+namespace {
+__global__ void __launch_bounds__(1024) solo_select_kernel(const float* scores, const float* cell_strides, int G, int K,
+                                                           float thr, int cap, float* out_scores, long long* out_classes,
+                                                           float* out_strides, int32_t* out_cells, int32_t* out_counts,
+                                                           int32_t* out_total) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int b = blockIdx.x;
+  const long long total = (long long)G * K;
+  const float* sc = scores + (size_t)b * total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (long long i0 = 0; i0 < total; i0 += 1024) {
+    const long long i = i0 + threadIdx.x;
+    const float v = i < total ? __ldg(sc + i) : 0.0f;
+    const bool keep = i < total && v > thr;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) {
+      const int c = s_warp[w];
+      before += w < warp ? c : 0;
+      all += c;
+    }
+    const int slot = s_base + before + __popc(m & ((1u << lane) - 1u));
+    if (keep && slot < cap) {
+      const int cell = (int)(i / K);
+      const size_t o = (size_t)b * cap + slot;
+      out_scores[o] = v;
+      out_classes[o] = (long long)(i - (long long)cell * K);
+      out_strides[o] = cell_strides[cell];
+      out_cells[o] = cell;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += all;
+    __syncthreads();
+  }
+  const int n = min(s_base, cap);
+  for (int q = n + threadIdx.x; q < cap; q += 1024) {  // defined padding
+    const size_t o = (size_t)b * cap + q;
+    out_scores[o] = 0.0f; out_classes[o] = 0; out_strides[o] = 1.0f; out_cells[o] = 0;
+  }
+  if (threadIdx.x == 0) {
+    out_counts[b] = n;
+    if (out_total) out_total[b] = s_base;
+  }
+}
+// kernels [B, G, E] rows of the kept cells -> [B, cap, E] (zeros past the count); one warp per row, 16-byte copies
+__global__ void solo_gather_kernels_kernel(const float4* kernels, const int32_t* cells, const int32_t* counts, int G, int E4,
+                                           int cap, float4* out) {
+  const int b = blockIdx.y;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= cap) return;
+  const int lane = threadIdx.x & 31;
+  const bool live = row < counts[b];
+  const float4* src = kernels + ((size_t)b * G + (live ? cells[(size_t)b * cap + row] : 0)) * E4;
+  float4* dst = out + ((size_t)b * cap + row) * E4;
+  for (int c = lane; c < E4; c += 32) dst[c] = live ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+}  // namespace
+}  // namespace d2b
+
+extern "C" size_t d2b_solo_select_workspace_bytes(const d2b_solo_select_params* p) {
+  if (!p || p->batch < 0 || p->max_candidates < 1) return 0;
+  return ws_slice(sizeof(int32_t) * (size_t)p->batch * p->max_candidates);
+}
+extern "C" int d2b_solo_select(const d2b_solo_select_params* p, void* workspace, size_t workspace_bytes,
+                               d2b_stream_t stream) {
+  D2B_REQUIRE(p != nullptr, "params is NULL");
+  D2B_REQUIRE(p->batch >= 0 && p->num_cells >= 0 && p->num_classes >= 1 && p->channels >= 0, "solo_select: negative sizes");
+  D2B_REQUIRE(p->max_candidates >= 1 && p->max_candidates <= 65535, "solo_select: max_candidates must be in [1, 65535]");
+  D2B_REQUIRE(p->channels % 4 == 0, "solo_select: channels=%d must be a multiple of 4", p->channels);
+  if (p->batch == 0) return D2B_OK;
+  D2B_REQUIRE(p->scores && p->cell_strides && p->out_scores && p->out_classes && p->out_strides && p->out_counts,
+              "solo_select: NULL pointer");
+  D2B_REQUIRE(!p->out_kernels || p->kernels, "solo_select: out_kernels needs kernels");
+  const size_t need = ws_slice(sizeof(int32_t) * (size_t)p->batch * p->max_candidates);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_last_error("solo_select needs %zu workspace bytes", need);
+    return D2B_EWORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int32_t* cells = static_cast<int32_t*>(workspace);
+  solo_select_kernel<<<p->batch, 1024, 0, st>>>(p->scores, p->cell_strides, p->num_cells, p->num_classes, p->score_threshold,
+                                                p->max_candidates, p->out_scores,
+                                                reinterpret_cast<long long*>(p->out_classes), p->out_strides, cells,
+                                                p->out_counts, p->out_total);
+  D2B_LAUNCH_CHECK();
+  if (p->out_kernels && p->channels > 0) {
+    D2B_REQUIRE((reinterpret_cast<uintptr_t>(p->kernels) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->out_kernels) & 15) == 0,
+                "solo_select: kernels must be 16-byte aligned");
+    const dim3 grid((p->max_candidates + 7) / 8, p->batch);
+    solo_gather_kernels_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(p->kernels), cells, p->out_counts,
+                                                     p->num_cells, p->channels / 4, p->max_candidates,
+                                                     reinterpret_cast<float4*>(p->out_kernels));
+    D2B_LAUNCH_CHECK();
+  }
+  return D2B_OK;
+}

@@ -129,9 +129,15 @@ class SOLOv2Inference(object):
     Attributes mirror the ones `SOLOv2Head.__init__` reads from cfg (:140-149)."""
 
     def __init__(self, mask_threshold=0.5, pre_nms_topk=500, nms_kernel="gaussian", nms_sigma=2.0,
-                 update_score_threshold=0.05, max_detections_per_image=100):
+                 update_score_threshold=0.05, max_detections_per_image=100, score_threshold=0.1,
+                 num_grids=(40, 36, 24, 16, 12), strides=(8, 8, 16, 32, 32), max_candidates=2048, align_corners=False):
         if nms_kernel not in ("gaussian", "linear"):
             raise NotImplementedError(f"NMS kernel {nms_kernel} not implemented yet.")
+        self.score_threshold = score_threshold
+        self.num_grids = tuple(num_grids)
+        self.strides = tuple(strides)
+        self.max_candidates = int(max_candidates)  # static row count of the candidate list (the reference's is dynamic)
+        self.align_corners = align_corners         # which TF resize `resize_images` resolved to (functional.py:21-35)
         self.mask_threshold = mask_threshold
         self.pre_nms_topk = pre_nms_topk
         self.nms_kernel = nms_kernel
@@ -189,4 +195,55 @@ class SOLOv2Inference(object):
         out = dict(pred_masks=masks, packed_masks=packed, pred_classes=oc, scores=os_, is_valid=ov, num=num)
         if host:
             out = {k: (None if v is None else nv.to_host(v)) for k, v in out.items()}
+        return out
+
+    def select_candidates(self, pred_scores, pred_kernels):
+        """solo_v2.py:481-497 batched: pred_scores [B, G, K], pred_kernels [B, G, E] (levels concatenated) ->
+        dict(scores, classes, strides [B, n], kernels [B, n, E], counts [B], total [B]) with n = max_candidates, rows
+        in `tf.where` order; total > counts means the static cap dropped candidates."""
+        dev = nv.device_of(pred_scores)
+        sc = nv.to_device(pred_scores, dev, torch.float32)
+        kn = nv.to_device(pred_kernels, dev, torch.float32)
+        B, G, K = sc.shape
+        E = kn.shape[2]
+        assert kn.shape[:2] == (B, G) and G == sum(g * g for g in self.num_grids)
+        cell = torch.cat([torch.full((g * g,), float(s_), dtype=torch.float32) for g, s_ in zip(self.num_grids, self.strides)])
+        cell = cell.to(dev)
+        n = self.max_candidates
+        o_sc = torch.empty((B, n), dtype=torch.float32, device=dev)
+        o_cl = torch.empty((B, n), dtype=torch.int64, device=dev)
+        o_st = torch.empty((B, n), dtype=torch.float32, device=dev)
+        o_kn = torch.empty((B, n, E), dtype=torch.float32, device=dev)
+        cnt = torch.empty(B, dtype=torch.int32, device=dev)
+        tot = torch.empty(B, dtype=torch.int32, device=dev)
+        p = nv.SoloSelectParams()
+        p.scores, p.kernels, p.cell_strides = sc.data_ptr(), kn.data_ptr(), cell.data_ptr()
+        p.batch, p.num_cells, p.num_classes, p.channels = B, G, K, E
+        p.score_threshold, p.max_candidates = float(self.score_threshold), n
+        p.out_scores, p.out_classes, p.out_strides, p.out_kernels = o_sc.data_ptr(), o_cl.data_ptr(), o_st.data_ptr(), o_kn.data_ptr()
+        p.out_counts, p.out_total = cnt.data_ptr(), tot.data_ptr()
+        nv.call("solo_select", p, dev)
+        return dict(scores=o_sc, classes=o_cl, strides=o_st, kernels=o_kn, counts=cnt, total=tot)
+
+    def inference(self, pred_probs, pred_kernels, pred_mask_features, image_shape):
+        """Drop-in for `MaskKernelBranch.inference(pred_probs, pred_kernels, pred_mask_features, image_shape)`
+        (solo_v2.py:476-627): per-level lists of [B, g, g, K] probabilities and [B, g, g, E] kernels, mask features
+        [B, H, W, E], image_shape (H_img, W_img).  Candidate selection -> dynamic conv + mask stage (tensor cores) ->
+        filter / mask scoring / top-k / Matrix-NMS / score filter / pad -> image-size masks + boxes from masks.
+        Returns dict(pred_classes int64 [B, D], pred_masks uint8 [B, D, H_img, W_img], scores [B, D], is_valid [B, D],
+        boxes fp32 [B, D, 4], num [B], num_candidates [B])."""
+        host = not pred_mask_features.is_cuda
+        dev = nv.device_of(pred_mask_features)
+        feat = nv.to_device(pred_mask_features, dev, torch.float32)
+        B = feat.shape[0]
+        sc = torch.cat([nv.to_device(p_, dev, torch.float32).reshape(B, -1, p_.shape[-1]) for p_ in pred_probs], 1)
+        kn = torch.cat([nv.to_device(k_, dev, torch.float32).reshape(B, -1, k_.shape[-1]) for k_ in pred_kernels], 1)
+        cand = self.select_candidates(sc.contiguous(), kn.contiguous())
+        tail = self.postprocess(None, cand["scores"], cand["classes"], cand["strides"], cand["counts"], return_masks=False,
+                                mask_features=feat, mask_kernels=cand["kernels"])
+        up = solo_upsample_masks(tail["packed_masks"], feat.shape[1:3], image_shape, self.mask_threshold, self.align_corners)
+        out = dict(pred_classes=tail["pred_classes"], pred_masks=up["pred_masks"], scores=tail["scores"],
+                   is_valid=tail["is_valid"], boxes=up["boxes"], num=tail["num"], num_candidates=cand["total"])
+        if host:
+            out = {k: nv.to_host(v) for k, v in out.items()}
         return out

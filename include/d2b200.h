@@ -604,6 +604,33 @@ D2B_API int d2b_solo_postprocess(const d2b_solo_postprocess_params* p, void* wor
                                  d2b_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * SOLOv2 candidate selection          lib/modeling/single_stage_heads/solo_v2.py:481-497
+ *   keep_inds = tf.where(pred_scores > score_threshold)   (row-major over [cells, classes])
+ *   scores = gather_nd(pred_scores, keep_inds); classes = keep_inds[:, 1];
+ *   kernels = gather(pred_kernels, keep_inds[:, 0]); strides = gather(cell strides, keep_inds[:, 0])
+ * Ordered compaction per image into fixed [B, max_candidates] rows (zero padded) + counts -- the inputs of
+ * d2b_solo_postprocess.  The reference has no cap: out_total[b] is the number that passed the threshold, so
+ * out_total[b] > max_candidates tells the caller that candidates were dropped (in tf.where order, from the end).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* scores;       /* [B, G, K] pred_probs of all levels concatenated (:639-655) */
+  const float* kernels;      /* [B, G, E] pred_kernels of all levels concatenated; may be NULL if out_kernels is */
+  const float* cell_strides; /* [G] stride of the level each cell belongs to (:489-496) */
+  int32_t batch, num_cells, num_classes, channels;
+  float score_threshold;
+  int32_t max_candidates;
+  float* out_scores;    /* [B, max_candidates] */
+  int64_t* out_classes; /* [B, max_candidates] */
+  float* out_strides;   /* [B, max_candidates] */
+  float* out_kernels;   /* optional [B, max_candidates, E] */
+  int32_t* out_counts;  /* [B] = min(total, max_candidates) */
+  int32_t* out_total;   /* optional [B] */
+} d2b_solo_select_params;
+D2B_API size_t d2b_solo_select_workspace_bytes(const d2b_solo_select_params* p);
+D2B_API int d2b_solo_select(const d2b_solo_select_params* p, void* workspace, size_t workspace_bytes,
+                            d2b_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * SOLOv2: image-size masks and boxes from the kept masks
  *                          lib/modeling/single_stage_heads/solo_v2.py:599-627
  *   pred_masks = resize_images(pred_masks [N, D, h, w], image_shape) (bilinear)   (:599-601)

@@ -477,3 +477,12 @@ def solo_upsample_boxes(masks, image_hw, align_corners=False, mask_threshold=0.5
     lib().orc_solo_upsample_boxes(_p(m), C.c_int64(D), h, w, H, W, int(bool(align_corners)), C.c_float(mask_threshold),
                                   _p(out), _p(boxes))
     return out, boxes
+
+
+def solo_select(pred_scores, pred_kernels, num_grids, strides, score_threshold):
+    """solo_v2.py:481-497 for one image: pred_scores [G, K], pred_kernels [G, E] ->
+    (scores [n], classes int64 [n], kernels [n, E], strides [n]) in tf.where (row-major) order."""
+    sc = _f32(pred_scores)
+    keep = np.argwhere(sc > np.float32(score_threshold))
+    cell = np.concatenate([np.full(g * g, s_, np.float32) for g, s_ in zip(num_grids, strides)])
+    return sc[keep[:, 0], keep[:, 1]], keep[:, 1].astype(np.int64), _f32(pred_kernels)[keep[:, 0]], cell[keep[:, 0]]

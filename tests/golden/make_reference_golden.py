@@ -293,6 +293,8 @@ def main(out_path=None):
         so_st[i, :c_] = cell_stride[keep[:, 0]]
         so_kern[i, :c_] = flat_k[i][keep[:, 0]]
         so_logits[i, :c_] = np.einsum("nhwc,co->nhwo", mfeat[i:i + 1], flat_k[i][keep[:, 0]].T.copy())[0].transpose(2, 0, 1)
+    for li, (p_, k_) in enumerate(zip(probs, kerns)):  # the raw arguments of MaskKernelBranch.inference
+        out[f"so_raw_probs_{li}"], out[f"so_raw_kernels_{li}"] = p_, k_
     out.update(so_in_logits=so_logits, so_in_scores=so_sc, so_in_classes=so_cl, so_in_strides=so_st, so_in_counts=so_cnt,
                so_in_mask_features=mfeat, so_in_kernels=so_kern)
 
