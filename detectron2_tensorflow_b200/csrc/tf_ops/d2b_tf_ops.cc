@@ -496,3 +496,63 @@ class D2SoloDynamicMasksOp : public tf::OpKernel {
   float thr_;
 };
 REGISTER_KERNEL_BUILDER(Name("D2SoloDynamicMasks").Device(tf::DEVICE_GPU), D2SoloDynamicMasksOp);
+
+// ------------------------------------------------------------------ D2SoloUpsample
+// Replaces the end of MaskKernelBranch.inference (solo_v2.py:599-627): resize_images(pred_masks, image_shape) ->
+// > mask_threshold -> boxes from masks, from the packed masks of the tail.  image_shape is a host-memory input
+// because it sizes the output (the reference passes a Python list).
+REGISTER_OP("D2SoloUpsample")
+    .Input("packed_masks: int64")  // [N, D, ceil(h*w/64)]
+    .Input("image_shape: int32")   // [2] (H, W), host memory
+    .Attr("mask_h: int")
+    .Attr("mask_w: int")
+    .Attr("mask_threshold: float = 0.5")
+    .Attr("align_corners: bool = false")  // false: tf.compat.v2.image.resize exists (functional.py:21-24)
+    .Output("pred_masks: uint8")          // [N, D, H, W]
+    .Output("boxes: float")               // [N, D, 4]
+    .SetShapeFn([](InferenceContext* c) {
+      c->set_output(0, c->MakeShape({c->Dim(c->input(0), 0), c->Dim(c->input(0), 1), InferenceContext::kUnknownDim,
+                                     InferenceContext::kUnknownDim}));
+      c->set_output(1, c->MakeShape({c->Dim(c->input(0), 0), c->Dim(c->input(0), 1), 4}));
+      return tf::Status::OK();
+    });
+
+class D2SoloUpsampleOp : public tf::OpKernel {
+ public:
+  explicit D2SoloUpsampleOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("mask_h", &h_));
+    OP_REQUIRES_OK(c, c->GetAttr("mask_w", &w_));
+    OP_REQUIRES_OK(c, c->GetAttr("mask_threshold", &thr_));
+    OP_REQUIRES_OK(c, c->GetAttr("align_corners", &ac_));
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    const tf::Tensor& pk = ctx->input(0);
+    const tf::Tensor& shp = ctx->input(1);
+    OP_REQUIRES(ctx, pk.dims() == 3 && shp.NumElements() == 2, tf::errors::InvalidArgument("packed_masks [N,D,Wd], image_shape [2]"));
+    d2b_solo_upsample_params p = {};
+    p.packed_masks = reinterpret_cast<const uint64_t*>(pk.flat<tf::int64>().data());
+    p.batch = pk.dim_size(0);
+    p.num_dets = pk.dim_size(1);
+    p.mask_h = h_;
+    p.mask_w = w_;
+    p.image_h = shp.flat<tf::int32>()(0);
+    p.image_w = shp.flat<tf::int32>()(1);
+    p.align_corners = ac_ ? 1 : 0;
+    p.mask_threshold = thr_;
+    tf::Tensor *masks = nullptr, *boxes = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({pk.dim_size(0), pk.dim_size(1), p.image_h, p.image_w}), &masks));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({pk.dim_size(0), pk.dim_size(1), 4}), &boxes));
+    p.out_masks = masks->flat<tf::uint8>().data();
+    p.out_boxes = boxes->flat<float>().data();
+    RunOp(ctx, p, d2b_solo_upsample_workspace_bytes, d2b_solo_upsample);
+  }
+
+ private:
+  int h_, w_;
+  float thr_;
+  bool ac_;
+};
+REGISTER_KERNEL_BUILDER(Name("D2SoloUpsample").Device(tf::DEVICE_GPU).HostMemory("image_shape"), D2SoloUpsampleOp);
+
+// D2SoloSelect / D2SoloPostprocess follow the same pattern over d2b_solo_select / d2b_solo_postprocess (static
+// max_candidates / max_detections attrs give the fixed output shapes TF needs).
