@@ -188,3 +188,20 @@ def test_solo_image_masks_and_boxes(oracle_lib, z):
         assert np.array_equal(masks, z["so2_masks"][b])
         assert np.array_equal(boxes, z["so2_boxes"][b])
     assert z["so2_masks"].any() and not z["so2_masks"].all()
+
+
+def test_solo_candidate_selection(oracle_lib, z):
+    """solo_v2.py:481-497 from the raw arguments of MaskKernelBranch.inference: the oracle's selection equals the
+    candidates the golden generator recorded (scores, classes, strides, gathered kernels, counts)."""
+    B = z["so_raw_probs_0"].shape[0]
+    for b in range(B):
+        sc = np.concatenate([z[f"so_raw_probs_{l}"][b].reshape(-1, 3) for l in range(2)], 0)
+        kn = np.concatenate([z[f"so_raw_kernels_{l}"][b].reshape(-1, 8) for l in range(2)], 0)
+        s, c, k, st = oracle_lib.solo_select(sc, kn, (6, 4), (8, 16), 0.3)
+        n = int(z["so_in_counts"][b])
+        assert len(s) == n
+        assert np.array_equal(s, z["so_in_scores"][b, :n]) and np.array_equal(c, z["so_in_classes"][b, :n])
+        assert np.array_equal(k, z["so_in_kernels"][b, :n]) and np.array_equal(st, z["so_in_strides"][b, :n])
+        # and the dynamic conv of those candidates reproduces the recorded logits (numpy einsum in the generator)
+        lg, absum = oracle_lib.solo_dynamic_conv(z["so_in_mask_features"][b], k)
+        assert np.all(np.abs(lg - z["so_in_logits"][b, :n].reshape(n, -1)) <= 1e-5 * absum + 1e-30)
