@@ -95,14 +95,19 @@ __global__ void __launch_bounds__(kUpThreads) solo_upsample_kernel(const UpArgs 
     u64 acc = 0;
     for (long long q = w_first + tid; q <= w_last; q += kUpThreads) acc |= __ldg(src + q);
     if (!__syncthreads_or(acc != 0ull)) {
-      for (int it = 0; it < a.iters; ++it) {
-        const long long p = p_begin + ((long long)it * kUpThreads + tid) * kRun;
-        if (p >= p_end) break;
-        if (om) {
-          if (vec16 && p + kRun <= p_end) *reinterpret_cast<uint4*>(om + p) = make_uint4(0, 0, 0, 0);
-          else for (long long q = p; q < min(p + kRun, p_end); ++q) om[q] = 0;
+      const int len = (int)(p_end - p_begin);
+      if (om) {
+        if (vec16) {  // p_begin is a multiple of 16: whole 16-byte stores, then the (image-end) tail
+          uint4* dst = reinterpret_cast<uint4*>(om + p_begin);
+          for (int v = tid; v < (len >> 4); v += kUpThreads) dst[v] = make_uint4(0, 0, 0, 0);
+          for (int q = (len & ~15) + tid; q < len; q += kUpThreads) om[p_begin + q] = 0;
+        } else {
+          for (int q = tid; q < len; q += kUpThreads) om[p_begin + q] = 0;
         }
-        if (op && (p & 63) == 0) op[p >> 6] = 0ull;  // one 64-bit word = 4 runs; the owner of the first run writes it
+      }
+      if (op) {
+        u64* dst = op + (p_begin >> 6);  // p_begin is a multiple of 64
+        for (int v = tid; v < ((len + 63) >> 6); v += kUpThreads) dst[v] = 0ull;
       }
       return;
     }
@@ -148,66 +153,53 @@ __global__ void __launch_bounds__(kUpThreads) solo_upsample_kernel(const UpArgs 
     const int off = (it * (kUpThreads / 32) + warp) * (32 * kRun);  // offset of the warp's 512 pixels in the chunk
     if (off >= chunk_len) break;  // warp-uniform
     const long long base = p_begin + off;
-    int left = chunk_len - off - lane;  // > 0 while this lane's pixel is inside the chunk
-    int y = (int)((base + lane) / a.W), x = (int)((base + lane) - (long long)y * a.W);
-    int y_cached = -1;
-    float yl = 0.0f;
-    int2 s0 = make_int2(0, -1), s1 = make_int2(0, -1);
-    const float *q0 = rows, *q1 = rows;
+    const int span_len = min(32 * kRun, chunk_len - off);
+    const int ya = (int)(base / a.W), xa = (int)(base - (long long)ya * a.W);
+    const int yb = (int)((base + span_len - 1) / a.W);
     unsigned mine = 0;
-    // warp-level rejection: the 512 pixels lie in at most ceil(512 / W) + 1 output rows; if the source rows of each of
-    // them are empty over the columns the warp can touch, all 16 ballots are zero
-    bool skip;
-    {
-      const int span_len = min(32 * kRun, chunk_len - off);
-      const int ya = (int)(base / a.W), xa = (int)(base - (long long)ya * a.W);
-      const int yb = (int)((base + span_len - 1) / a.W), xb = (int)((base + span_len - 1) - (long long)yb * a.W);
-      skip = true;
-      for (int yy = ya; yy <= yb && skip; ++yy) {
-        int lo_r, hi_r;
-        float l_r;
-        resize_tap(yy, a.h, a.scale_y, a.align_corners, lo_r, hi_r, l_r);
-        const int c0 = xt[yy == ya ? xa : 0].lo, c1 = xt[yy == yb ? xb : a.W - 1].hi;
-        const int2 t0 = span[lo_r - r0], t1 = span[hi_r - r0];
-        skip = (t0.y < c0 || t0.x > c1) && (t1.y < c0 || t1.x > c1);
+    // The span is cut by output row (1-2 rows for W >= 512): everything that depends on the row -- its two source
+    // rows, their lerp weight and set-column spans -- is warp-uniform inside the sub-step loop.
+    for (int y = ya; y <= yb; ++y) {
+      const int f0 = y == ya ? 0 : (y - ya) * a.W - xa;                 // flat range of this row inside the span
+      const int f1 = min(span_len, (y - ya + 1) * a.W - xa);
+      int ylo, yhi;
+      float yl;
+      resize_tap(y, a.h, a.scale_y, a.align_corners, ylo, yhi, yl);
+      const int2 s0 = span[ylo - r0], s1 = span[yhi - r0];
+      const int xbase = xa - (y - ya) * a.W;                             // x = xbase + f
+      {  // row-level rejection over the columns this row's part can touch
+        const int c0 = xt[xbase + f0].lo, c1 = xt[xbase + f1 - 1].hi;
+        if ((s0.y < c0 || s0.x > c1) && (s1.y < c0 || s1.x > c1)) continue;
       }
-    }
-    if (!skip) {
-#pragma unroll 4
-    for (int j = 0; j < kRun; ++j) {
-      bool on = false;
-      if (left > 0) {
-        if (y != y_cached) {
-          int ylo, yhi;
-          resize_tap(y, a.h, a.scale_y, a.align_corners, ylo, yhi, yl);
-          s0 = span[ylo - r0];
-          s1 = span[yhi - r0];
-          q0 = rows + (ylo - r0) * a.w;
-          q1 = rows + (yhi - r0) * a.w;
-          y_cached = y;
-        }
-        const Tap t = xt[x];
-        const int lo = t.lo, hi = t.hi;
-        const bool empty = (s0.y < lo || s0.x > hi) && (s1.y < lo || s1.x > hi);
-        if (!empty) {
-          const float tl = q0[lo], tr = q0[hi], bl = q1[lo], br = q1[hi];
-          float top = tr - tl; top = top * t.lerp; top = tl + top;
-          float bot = br - bl; bot = bot * t.lerp; bot = bl + bot;
-          float v = bot - top; v = v * yl; v = top + v;
-          on = v > a.thr;
-          if (on) {
-            cnt32 += 1; sum_y32 += (unsigned)y; sum_x32 += (unsigned)x;
-            if (y > 0) { min_y = min(min_y, y); max_y = max(max_y, y); }
-            if (x > 0) { min_x = min(min_x, x); max_x = max(max_x, x); }
+      const float* q0 = rows + (ylo - r0) * a.w;
+      const float* q1 = rows + (yhi - r0) * a.w;
+      unsigned row_cnt = 0;
+      for (int j = f0 >> 5; j <= (f1 - 1) >> 5; ++j) {
+        const int f = lane + 32 * j;
+        bool on = false;
+        if (f >= f0 && f < f1) {
+          const int x = xbase + f;
+          const Tap t = xt[x];
+          const int lo = t.lo, hi = t.hi;
+          const bool empty = (s0.y < lo || s0.x > hi) && (s1.y < lo || s1.x > hi);
+          if (!empty) {
+            const float tl = q0[lo], tr = q0[hi], bl = q1[lo], br = q1[hi];
+            float top = tr - tl; top = top * t.lerp; top = tl + top;
+            float bot = br - bl; bot = bot * t.lerp; bot = bl + bot;
+            float v = bot - top; v = v * yl; v = top + v;
+            on = v > a.thr;
+            if (on) {
+              row_cnt += 1; sum_x32 += (unsigned)x;
+              if (x > 0) { min_x = min(min_x, x); max_x = max(max_x, x); }
+            }
           }
         }
+        const unsigned word = __ballot_sync(0xffffffffu, on);  // pixels base + 32 j .. + 31 (this row's part)
+        if (lane == j) mine |= word;
       }
-      const unsigned word = __ballot_sync(0xffffffffu, on);  // pixels base + 32 j .. + 31
-      if (lane == j) mine = word;
-      left -= 32;
-      x += 32;
-      while (x >= a.W) { x -= a.W; ++y; }
-    }
+      cnt32 += row_cnt;
+      sum_y32 += row_cnt * (unsigned)y;
+      if (row_cnt && y > 0) { min_y = min(min_y, y); max_y = max(max_y, y); }
     }
     if (op) {  // lanes 0..15 hold the 16 ballots: two neighbours make one 64-bit word
       const unsigned hi32 = __shfl_down_sync(0xffffffffu, mine, 1);
