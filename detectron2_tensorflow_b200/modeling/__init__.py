@@ -8,3 +8,4 @@ from .matcher import Matcher, label_boxes
 from .single_stage_heads.yolov4_outputs import YOLOv4Inference
 from .single_stage_heads.solo_v2 import (point_nms, solo_mask_encode, solo_dynamic_masks, solo_upsample_masks,
                                          SOLOv2Inference)
+from .postprocessing import detector_postprocess

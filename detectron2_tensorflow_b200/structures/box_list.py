@@ -62,6 +62,12 @@ class BoxList(_Trackings):
     def has_field(self, field):
         return field in self.data
 
+    def set_field(self, field, field_data):
+        """box_list.py:106-121: replace the value of an existing field."""
+        if not self.has_field(field):
+            raise ValueError('field %s does not exist' % field)
+        self.data[field] = field_data
+
     def get_field(self, field):
         if not self.has_field(field):
             raise ValueError('field ' + str(field) + ' does not exist')

@@ -70,7 +70,8 @@ def load_reference():
                 anchor_generator=imp("reflib.modeling.anchor_generator"),
                 retinanet=imp("reflib.modeling.single_stage_heads.retinanet"),
                 yolo=imp("reflib.modeling.single_stage_heads.yolov4_outputs"),
-                solo=imp("reflib.modeling.single_stage_heads.solo_v2"))
+                solo=imp("reflib.modeling.single_stage_heads.solo_v2"),
+                postprocessing=imp("reflib.modeling.postprocessing"))
     return types.SimpleNamespace(**mods)
 
 
@@ -304,6 +305,22 @@ def main(out_path=None):
     res2 = R.solo.MaskKernelBranch.inference(shead, [t(p_) for p_ in probs], [t(k_) for k_ in kerns], t(mfeat), [Hi, Wi])
     out.update(so2_masks=np.asarray(res2.get_field("pred_masks")).astype(np.uint8), so2_boxes=np.asarray(res2.boxes),
                so2_image_shape=np.array([Hi, Wi], np.int32))
+
+    # ---- 16. detector_postprocess (postprocessing.py:9-59): dense results -> from_dense -> (scaled) boxes -> paste
+    dp_boxes = np.stack([rand_boxes(rng, 5, 60, 80, 8, 40) for _ in range(2)])
+    dp_masks = rng.random((2, 5, 14, 14)).astype(np.float32)
+    dp_valid = np.array([[1, 1, 0, 1, 1], [1, 0, 0, 1, 0]], bool)
+    dp_shapes = np.array([[60, 80], [50, 70]], np.int32)
+    out.update(dp_boxes=dp_boxes, dp_masks=dp_masks, dp_valid=dp_valid, dp_shapes=dp_shapes)
+    for fmt, oshape in (("fixed", [90, 120]), ("conventional", [60, 80])):
+        bl = R.box_list.BoxList(t(dp_boxes))
+        bl.add_field("pred_masks", t(dp_masks))
+        bl.add_field("is_valid", t(dp_valid))
+        bl.set_tracking("image_shape", t(dp_shapes))
+        res = R.postprocessing.detector_postprocess(bl, oshape, fmt, image_shapes=t(dp_shapes))
+        out[f"dp_{fmt}_masks"] = np.asarray(res.get_field("pred_masks"))
+        out[f"dp_{fmt}_boxes"] = np.asarray(res.boxes)
+        out[f"dp_{fmt}_valid"] = np.asarray(res.get_field("is_valid"))
 
     out_path = out_path or os.path.join(HERE, "reference_python.npz")
     np.savez_compressed(out_path, **out)

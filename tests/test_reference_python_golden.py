@@ -205,3 +205,21 @@ def test_solo_candidate_selection(oracle_lib, z):
         # and the dynamic conv of those candidates reproduces the recorded logits (numpy einsum in the generator)
         lg, absum = oracle_lib.solo_dynamic_conv(z["so_in_mask_features"][b], k)
         assert np.all(np.abs(lg - z["so_in_logits"][b, :n].reshape(n, -1)) <= 1e-5 * absum + 1e-30)
+
+
+def test_detector_postprocess(oracle_lib, z):
+    """detector_postprocess (postprocessing.py:9-59), "fixed" and "conventional": from_dense (row-major valid rows),
+    boxes scaled by float32(float64(output_shape) / image_shape) for "fixed", paste, to_dense -- masks bit-exact."""
+    valid, shapes = z["dp_valid"], z["dp_shapes"]
+    idx = np.argwhere(valid)
+    for fmt, oshape in (("fixed", (90, 120)), ("conventional", (60, 80))):
+        boxes = z["dp_boxes"][valid]
+        if fmt == "fixed":
+            sc = (np.array(oshape, np.float64)[None] / shapes.astype(np.float64))[idx[:, 0]].astype(np.float32)
+            boxes = np.stack([sc[:, 0] * boxes[:, 0], sc[:, 1] * boxes[:, 1], sc[:, 0] * boxes[:, 2], sc[:, 1] * boxes[:, 3]], 1)
+        pasted = oracle_lib.reframe_box_masks_to_image_masks(z["dp_masks"][valid], boxes, oshape, 0.5)
+        dense = np.zeros(valid.shape + tuple(oshape), np.uint8)
+        dense[valid] = pasted
+        assert np.array_equal(dense, z[f"dp_{fmt}_masks"])
+        assert np.array_equal(z[f"dp_{fmt}_valid"], valid)
+        assert np.array_equal(z[f"dp_{fmt}_boxes"], z["dp_boxes"] * valid[..., None])  # boxes stay unscaled

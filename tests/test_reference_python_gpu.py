@@ -150,3 +150,20 @@ def test_solo_inference_tail(cuda, z):
     assert np.array_equal(got["pred_classes"].cpu().numpy(), z["so_classes"])
     assert np.array_equal(got["pred_masks"].cpu().numpy(), z["so_masks"])
     assert np.allclose(got["scores"].cpu().numpy(), z["so_scores"], rtol=1e-5, atol=1e-7)
+
+
+def test_detector_postprocess(cuda, z):
+    """The reference's detector_postprocess (postprocessing.py:9-59) on the dense results of an R-CNN, both mask
+    formats: the mirror (from_dense -> scaled boxes -> d2b_paste_masks -> to_dense) is bit-exact."""
+    from detectron2_tensorflow_b200.modeling import detector_postprocess
+    for fmt, oshape in (("fixed", (90, 120)), ("conventional", (60, 80))):
+        bl = BoxList(T(z["dp_boxes"], cuda))
+        bl.add_field("pred_masks", T(z["dp_masks"], cuda))
+        bl.add_field("is_valid", T(z["dp_valid"], cuda))
+        bl.set_tracking("image_shape", T(z["dp_shapes"], cuda))
+        res = detector_postprocess(bl, oshape, fmt, image_shapes=T(z["dp_shapes"], cuda))
+        assert np.array_equal(res.get_field("pred_masks").cpu().numpy(), z[f"dp_{fmt}_masks"])
+        assert np.array_equal(res.boxes.cpu().numpy(), z[f"dp_{fmt}_boxes"])
+        assert np.array_equal(res.get_field("is_valid").cpu().numpy(), z[f"dp_{fmt}_valid"])
+    with pytest.raises(ValueError):
+        detector_postprocess(bl, (60, 80), "bitmap")
