@@ -69,7 +69,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(f"nvcc failed on {src}\n")
     if failed:
         raise RuntimeError("libd2b200 build failed")
-    cmd = [nvcc, "-ccbin", host, "-shared", "-cudart", "static", "-o", LIB] + objs
+    cmd = [nvcc, "-ccbin", host, "-shared", "-cudart", "static", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs
     subprocess.check_call(cmd, env=env)
     return LIB
 
