@@ -98,6 +98,28 @@ def test_argument_validation_without_gpu(lib):
     nv._bind("roi_align_backward")
     assert lib.d2b_roi_align_backward(C.byref(bw), None, 0, None) == -1
     assert b"fp32 only" in lib.d2b_last_error()
+    # SOLOv2 ops
+    dm = nv.SoloDynamicMasksParams()
+    dm.batch, dm.n, dm.channels, dm.hw = 1, 4, 6, 64  # channels % 4 (16-byte TMA rows)
+    nv._bind("solo_dynamic_masks")
+    assert lib.d2b_solo_dynamic_masks(C.byref(dm), None, 0, None) == -1
+    assert b"multiple of 4" in lib.d2b_last_error()
+    dm.channels, dm.hw = 8, 1 << 24  # mask sums must stay exact in fp32
+    assert lib.d2b_solo_dynamic_masks(C.byref(dm), None, 0, None) == -1
+    dm.hw = 64
+    assert lib.d2b_solo_dynamic_masks_workspace_bytes(C.byref(dm)) >= 2 * 4 * 8 * 4
+    up = nv.SoloUpsampleParams()
+    up.batch, up.num_dets, up.mask_h, up.mask_w, up.image_h, up.image_w = 1, 1, 0, 8, 16, 16
+    nv._bind("solo_upsample")
+    assert lib.d2b_solo_upsample(C.byref(up), None, 0, None) == -1
+    up.mask_h, up.mask_w, up.image_h, up.image_w = 4000, 4000, 8, 8  # a 500x shrink does not fit a CTA's shared memory
+    assert lib.d2b_solo_upsample(C.byref(up), None, 0, None) == -1
+    assert b"shared memory" in lib.d2b_last_error()
+    se = nv.SoloSelectParams()
+    se.batch, se.num_cells, se.num_classes, se.channels, se.max_candidates = 1, 4, 2, 8, 0
+    nv._bind("solo_select")
+    assert lib.d2b_solo_select(C.byref(se), None, 0, None) == -1
+    assert b"max_candidates" in lib.d2b_last_error()
     # workspace queries are pure host arithmetic
     t = nv.SegmentedTopkParams()
     t.num_groups, t.rows_per_group, t.k = 2, 4, 1000
