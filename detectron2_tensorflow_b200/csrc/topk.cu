@@ -88,7 +88,8 @@ __device__ __forceinline__ u64 composite_of(uint32_t key, unsigned idx) {
 // Calls f(value, index, valid) for every element of [beg, end) -- and, with valid == false, for the padding
 // slots -- with warp-uniform control flow (f may use warp collectives).  16-byte loads when the chunk is
 // 16-byte aligned, kBatch/4 vectors (or kBatch scalars) in flight per thread.
-template <int kV = kBatch / 4, typename F>
+// kStream: the row is read exactly once (RetinaNet rows with a sampled cutoff) -> evict-first loads.
+template <int kV = kBatch / 4, bool kStream = false, typename F>
 __device__ __forceinline__ void for_each_elem(const float* x, long long beg, long long end, F f) {
   const bool vec = ((reinterpret_cast<uintptr_t>(x + beg) & 15) == 0);
   if (vec) {
@@ -99,7 +100,7 @@ __device__ __forceinline__ void for_each_elem(const float* x, long long beg, lon
 #pragma unroll
       for (int u = 0; u < kV; ++u) {
         const long long vi = v0 + (long long)u * kHistThreads + threadIdx.x;
-        q[u] = vi < nvec ? __ldg(xv + vi) : make_float4(0, 0, 0, 0);
+        q[u] = vi < nvec ? (kStream ? __ldcs(xv + vi) : __ldg(xv + vi)) : make_float4(0, 0, 0, 0);
       }
 #pragma unroll
       for (int u = 0; u < kV; ++u) {
@@ -166,8 +167,10 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass, 
   const int shift = c_shift[pass], bits = c_bits[pass];
   const unsigned mask = (1u << bits) - 1u;
   // pass 0 sees every element: shared-memory histogram.  Later passes only count the few elements
-  // inside the current prefix: they go straight to the row's global histogram.
-  const bool use_smem = (pass == 0);
+  // inside the current prefix: they go straight to the row's global histogram -- and so does pass 0 of a row with a
+  // sampled cutoff (only ~3k of its elements pass the compare; zeroing and merging a 32 KB shared histogram per
+  // 32 KB of input cost as much as the streaming read itself).
+  const bool use_smem = (pass == 0) && (st->cut_key == 0u);
   unsigned* gh = a.hist + ((size_t)row * kPasses + pass) * kBins;
   if (use_smem) {
     for (int i = threadIdx.x; i < kCopies * kBins; i += kHistThreads) (&sh[0][0])[i] = 0;
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass, 
       if (in) atomicAdd(my + digit, 1u);
     };
     // rows with a cutoff do one compare per element: keep 4 x 16 B per thread in flight to stay HBM-bound
-    if (cand0) for_each_elem<4>(x, beg, end, body);
+    if (cand0) for_each_elem<4, true>(x, beg, end, body);
     else for_each_elem(x, beg, end, body);
   }
   __syncthreads();
