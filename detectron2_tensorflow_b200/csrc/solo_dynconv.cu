@@ -8,14 +8,18 @@
 //     by default two CTAs of a cluster form a cta_group::2 pair (M=256): each CTA owns one 128-row block of D in its
 //     own TMEM and stages / converts only HALF of the feature tile, the leader CTA issues the MMAs for both and
 //     tcgen05.commit multicasts the completion to the barriers of both CTAs;
-//   * fp32 accuracy from three tf32 products per k-step (3xTF32: a = a_hi + a_lo with both halves tf32-exact,
-//     D += a_lo.b_hi + a_hi.b_lo + a_hi.b_hi): the kernels are split once by a tiny prologue kernel, the feature tile
-//     is split in shared memory by four converter warps between the TMA and the MMA (elementwise, so the swizzled
-//     layout is preserved), published to the async proxy with fence.proxy.async;
-//   * epilogue warps read the accumulators with tcgen05.ld (thread = one mask row, 32 consecutive pixels per load),
-//     take the threshold decision with the bit-exact sigmoid rule of solo_encode_kernel and emit BIT-PACKED masks,
-//     exact mask sums and the score sums -- the 4 B/pixel logits (134 MB per image at 500 x 200 x 336) never exist.
-// Persistent: one CTA per SM walks the (image, pixel tile, row block) tiles round-robin.
+//   * fp32 accuracy from three tf32 products per k-step (3xTF32: a = a_hi + a_lo, D += a_lo.b_hi + a_hi.b_hi +
+//     a_hi.b_lo; the dropped a_lo.b_lo is O(2^-22)): the kernels are split once by a tiny prologue kernel (both halves
+//     rounded to tf32); for the feature tile the raw fp32 tile IS the hi half (the tensor core ignores the low 13
+//     mantissa bits) and four converter warps write lo = x - trunc_tf32(x) beside it between the TMA and the MMA
+//     (elementwise, so the swizzled layout is preserved), published to the async proxy with fence.proxy.async;
+//   * epilogue warps read the accumulators with tcgen05.ld (thread = one mask row, 16 consecutive pixels per load),
+//     take the threshold decision on the logit (exact sigmoid only inside the guard band around logit(thr), the rule
+//     of solo_encode_kernel) and emit BIT-PACKED masks, exact mask sums and the score sums (2-MUFU sigmoid: the sums
+//     are tolerance-based like every fp32 reduction here) -- the 4 B/pixel logits (134 MB per image at
+//     500 x 200 x 336) never exist.
+// Persistent: one CTA (pair) per SM (pair) walks the (image, pixel tile, row block) tiles round-robin.
+// Non-finite features / kernels give unspecified bits (inf - inf in the lo half).
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM owner), 2-5 = converters, 6-13 = epilogue.
 #include <cuda.h>
 #include <math.h>
@@ -34,9 +38,9 @@ constexpr int kThreads = 448;
 constexpr int kCvtThreads = 128, kEpiThreads = 256;  // 2 epilogue warps per TMEM lane quarter (half the columns each)
 constexpr uint32_t kTmemCols = 512;
 
-// One pipeline stage holds a K block of BK fp32 = one swizzle row: BK = 32 -> 128-byte swizzle, 96 KB per stage,
-// 2 stages; BK = 16 -> 64-byte swizzle, 48 KB per stage, 4 stages (same bytes in flight, twice the depth: the
-// TMA -> converter -> MMA round trip of a stage is latency, not bandwidth).
+// One pipeline stage holds a K block of BK fp32 = one swizzle row (BK = 32: 128-byte swizzle, BK = 16: 64-byte
+// swizzle); the ring fills 192 KB: 2 x 96 KB / 4 x 48 KB for one CTA, 3 x 64 KB / 6 x 32 KB for a pair (which stages
+// only half of the feature tile per CTA).
 template <int BK, int CTAS>
 struct Cfg {
   static_assert(BK == 32 || BK == 16, "one swizzle row per K block");
@@ -104,7 +108,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if ((spin & 1023u) == 1023u) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ll) __trap();  // ~2 s
+      else if (now - t0 > 20000000000ll) __trap();  // ~10 s: a kernel that takes 1 ms is deadlocked by then
     }
   }
 }
