@@ -215,3 +215,63 @@ def test_fuzz_label_boxes_yolo_matrix_nms(cuda, oracle_lib, seed):
         want = oracle_lib.matrix_nms(m, cls, sc, None, kern, 2.0)
         got = matrix_nms(T(m, cuda), T(cls, cuda), T(sc, cuda), kernel=kern, sigma=2.0).cpu().numpy()
         assert np.array_equal(got, want, equal_nan=True), (seed, kern)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_fuzz_solo_upsample_and_select(cuda, oracle_lib, seed):
+    """SOLOv2 neighbours: image-size masks + boxes (both resize conventions, up- and down-scaling, odd sizes, empty /
+    full / single-pixel masks) and the ordered candidate selection (random thresholds, caps that overflow)."""
+    from detectron2_tensorflow_b200.modeling import SOLOv2Inference, solo_upsample_masks
+    rng = np.random.default_rng(7000 + seed)
+    B, D = int(rng.integers(1, 3)), int(rng.integers(1, 6))
+    h, w = int(rng.integers(1, 40)), int(rng.integers(1, 50))
+    H, W = int(rng.integers(1, 150)), int(rng.integers(1, 200))
+    if max(h / H, 1.0) * w * 4 * 40 > 150_000:  # keep a CTA's staged source rows inside shared memory
+        H = max(H, h // 4)
+    ac = bool(rng.integers(0, 2))
+    thr = float(rng.choice([0.5, 0.5, 0.3, 0.7]))
+    m = (rng.random((B, D, h, w)) < rng.choice([0.02, 0.3, 0.7])).astype(np.float32)
+    yy, xx = np.mgrid[0:h, 0:w]
+    for b in range(B):
+        for d in range(D):
+            kind = rng.integers(0, 6)
+            if kind == 0:
+                m[b, d] = 0
+            elif kind == 1:
+                m[b, d] = 1
+            elif kind == 2:
+                m[b, d] = 0
+                m[b, d, rng.integers(0, h), rng.integers(0, w)] = 1
+            elif kind == 3:
+                cy, cx, r = rng.uniform(0, h), rng.uniform(0, w), rng.uniform(0.5, max(h, w))
+                m[b, d] = ((yy - cy) ** 2 + (xx - cx) ** 2 <= r * r).astype(np.float32)
+    flat = m.reshape(B, D, -1).astype(np.uint8)
+    flat = np.concatenate([flat, np.zeros((B, D, (-flat.shape[-1]) % 64), np.uint8)], -1)
+    packed = np.packbits(flat, axis=-1, bitorder="little").view(np.int64)
+    got = solo_upsample_masks(T(packed, cuda), (h, w), (H, W), thr, ac, return_masks=True, return_packed=True)
+    for b in range(B):
+        wm, wb = oracle_lib.solo_upsample_boxes(m[b], (H, W), ac, thr)
+        assert np.array_equal(got["pred_masks"][b].cpu().numpy(), wm)
+        assert np.array_equal(got["boxes"][b].cpu().numpy(), wb)
+        bits = np.unpackbits(got["packed_masks"][b].cpu().numpy().view(np.uint8), axis=-1, bitorder="little")
+        assert np.array_equal(bits[:, :H * W].reshape(D, H, W), wm) and not bits[:, H * W:].any()
+    # candidate selection
+    grids = tuple(int(g) for g in rng.integers(1, 9, rng.integers(1, 4)))
+    strides = tuple(int(s_) for s_ in rng.choice([4, 8, 16, 32], len(grids)))
+    K, E = int(rng.integers(1, 9)), 4 * int(rng.integers(1, 5))
+    G = sum(g * g for g in grids)
+    sc = rng.random((B, G, K)).astype(np.float32)
+    sc[rng.random(sc.shape) < 0.2] = 0.5  # ties with the threshold (strict >)
+    kn = rng.standard_normal((B, G, E)).astype(np.float32)
+    sthr = float(rng.choice([0.5, 0.1, 0.9, 0.0, 1.0]))
+    cap = int(rng.choice([1, 7, 64, 2048]))
+    head = SOLOv2Inference(score_threshold=sthr, num_grids=grids, strides=strides, max_candidates=cap)
+    sel = head.select_candidates(T(sc, cuda), T(kn, cuda))
+    for b in range(B):
+        ws, wc, wk, wst = oracle_lib.solo_select(sc[b], kn[b], grids, strides, sthr)
+        n = int(sel["counts"][b])
+        assert int(sel["total"][b]) == len(ws) and n == min(len(ws), cap)
+        assert np.array_equal(sel["scores"][b, :n].cpu().numpy(), ws[:n])
+        assert np.array_equal(sel["classes"][b, :n].cpu().numpy(), wc[:n])
+        assert np.array_equal(sel["strides"][b, :n].cpu().numpy(), wst[:n])
+        assert np.array_equal(sel["kernels"][b, :n].cpu().numpy(), wk[:n])
