@@ -275,3 +275,33 @@ def test_fuzz_solo_upsample_and_select(cuda, oracle_lib, seed):
         assert np.array_equal(sel["classes"][b, :n].cpu().numpy(), wc[:n])
         assert np.array_equal(sel["strides"][b, :n].cpu().numpy(), wst[:n])
         assert np.array_equal(sel["kernels"][b, :n].cpu().numpy(), wk[:n])
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_solo_dynamic_masks(cuda, oracle_lib, seed):
+    """The tensor-core dynamic conv + mask stage on irregular shapes (row blocks 1..3, channels not a multiple of the K
+    block, maps that end inside a pixel tile, ragged counts): logits within 1e-5 of sum|terms| of the oracle's fp32 sum,
+    everything after the logits exact."""
+    from detectron2_tensorflow_b200.modeling import solo_dynamic_masks
+    rng = np.random.default_rng(9000 + seed)
+    B = int(rng.integers(1, 4))
+    n = int(rng.choice([1, 3, 127, 128, 129, 200, 256, 257, 300]))
+    H, W = int(rng.integers(1, 40)), int(rng.integers(1, 60))
+    E = 4 * int(rng.integers(1, 24))
+    thr = float(rng.choice([0.5, 0.5, 0.4, 0.6]))
+    feat = (rng.standard_normal((B, H, W, E)) * rng.choice([0.1, 1.0, 30.0])).astype(np.float32)
+    kern = (rng.standard_normal((B, n, E)) * rng.choice([0.05, 1.0])).astype(np.float32)
+    counts = rng.integers(0, n + 1, B).astype(np.int32)
+    counts[0] = n
+    packed, sm, ss, logits = solo_dynamic_masks(T(feat, cuda), T(kern, cuda), thr, T(counts, cuda), return_logits=True)
+    bits = np.unpackbits(packed.cpu().numpy().view(np.uint8), axis=-1, bitorder="little")[..., :H * W]
+    glog = logits.cpu().numpy().reshape(B, n, H * W)
+    for b in range(B):
+        c = int(counts[b])
+        want, absum = oracle_lib.solo_dynamic_conv(feat[b], kern[b, :c])
+        assert (np.abs(glog[b, :c].astype(np.float64) - want) <= 1e-5 * absum + 1e-30).all()
+        m, wsm, wss = oracle_lib.solo_mask_stage(glog[b, :c].reshape(c, H, W), thr)
+        assert np.array_equal(bits[b, :c].reshape(c, H, W), m.astype(np.uint8))
+        assert np.array_equal(sm[b, :c].cpu().numpy(), wsm)
+        assert np.allclose(ss[b, :c].cpu().numpy(), wss, rtol=1e-5, atol=1e-5)
+        assert not bits[b, c:].any() and not sm[b, c:].any() and not ss[b, c:].any()
