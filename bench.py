@@ -516,6 +516,31 @@ def other_configs(dev, iters=10):
         kept = torch.from_numpy(np.packbits(obj, axis=-1, bitorder="little").view(np.int64)).to(dev)
         ms = med(lambda: solo_upsample_masks(kept, (H, W), (800, 1333), 0.5, False))
         r.update(image_masks_and_boxes_ms=ms, image_mask_write_GBps=B * 100 * 800 * 1333 / ms / 1e6)
+        # the whole MaskKernelBranch.inference from the head outputs (about 500 cells x classes above the threshold)
+        grids = (40, 36, 24, 16, 12)
+        probs = [torch.where(torch.rand((B, g_, g_, 80), device=dev, generator=g) < 0.0016,
+                             torch.rand((B, g_, g_, 80), device=dev, generator=g) * 0.8 + 0.15, torch.zeros((), device=dev))
+                 for g_ in grids]
+        kerns = [torch.randn((B, g_, g_, E), device=dev, generator=g) / 16 for g_ in grids]
+        full = SOLOv2Inference(0.5, 500, "gaussian", 2.0, 0.05, 100, score_threshold=0.1, num_grids=grids,
+                               strides=(8, 8, 16, 32, 32), max_candidates=1024)
+        # object-like masks need smooth mask features: low-frequency waves per channel + a bias channel that the
+        # kernels weight negatively (a few % of the pixels end up inside a mask, in blobs)
+        yy = torch.arange(H, device=dev, dtype=torch.float32)[None, :, None, None]
+        xx = torch.arange(W, device=dev, dtype=torch.float32)[None, None, :, None]
+        fy = torch.rand((1, 1, 1, E), device=dev, generator=g) * 0.12
+        fx = torch.rand((1, 1, 1, E), device=dev, generator=g) * 0.12
+        ph = torch.rand((B, 1, 1, E), device=dev, generator=g) * 6.28
+        sfeat = torch.cos(yy * fy + xx * fx + ph).contiguous()
+        sfeat[..., 0] = 1.0
+        for k_ in kerns:
+            k_[..., 0] = -1.6 * (E / 2.0) ** 0.5 / 16  # about -1.6 sigma of the logit
+        ms = med(lambda: full.inference(probs, kerns, sfeat, (800, 1333)))
+        res = full.inference(probs, kerns, sfeat, (800, 1333))
+        r["full_inference_mask_coverage"] = float(res["pred_masks"].float().mean())
+        r.update(full_inference_from_head_outputs_ms=ms, full_inference_images_per_s=B / ms * 1e3,
+                 full_inference_candidates_per_image=float(res["num_candidates"].float().mean()),
+                 full_inference_detections_per_image=float(res["num"].float().mean()))
         out["configs[3] SOLOv2 R50: 500 candidates at 200x336, batch 16"] = r
     except Exception as e:  # noqa: BLE001
         out["configs[3]"] = {"error": repr(e)[:200]}

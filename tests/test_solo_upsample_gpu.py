@@ -65,7 +65,7 @@ def test_upsample_masks_and_boxes(cuda, oracle_lib, hw, HW, ac):
     check(cuda, oracle_lib, m, HW, ac)
 
 
-@pytest.mark.parametrize("thr", [0.3, 0.5, 0.75])
+@pytest.mark.parametrize("thr", [0.3, 0.5, 0.75, 0.0, 1.0, -0.1, 1.5])
 def test_thresholds(cuda, oracle_lib, thr):
     rng = np.random.default_rng(3)
     check(cuda, oracle_lib, blobs(rng, 1, 9, 30, 44), (121, 170), False, thr)
