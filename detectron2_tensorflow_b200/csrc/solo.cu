@@ -447,58 +447,114 @@ extern "C" int d2b_solo_postprocess(const d2b_solo_postprocess_params* p, void* 
 // ------------------------------------------------------------------ candidate selection (solo_v2.py:481-497)
 //   keep_inds = tf.where(pred_scores > score_threshold)      (row-major over [G cells, K classes])
 //   scores = gather_nd, classes = keep_inds[:, 1], kernels = gather(pred_kernels, keep_inds[:, 0]), strides likewise
-// One CTA per image walks the G*K scores in order: ballot + warp prefix + block prefix give every kept element its
-// rank, i.e. the compaction is ORDERED (tf.where order) without a sort.  Candidates past `cap` are dropped (the
+// Three small launches: kept scores per 4096-score chunk, an exclusive scan of the chunk counts per image, and a
+// scatter in which every kept element's rank = chunk base + rank inside the chunk, i.e. the compaction is ORDERED
+// (tf.where order) without a sort.  Candidates past `cap` are dropped (the
 // reference has no cap; `out_total` reports how many passed so the caller can detect it).
 namespace d2b {
 namespace {
-__global__ void __launch_bounds__(1024) solo_select_kernel(const float* scores, const float* cell_strides, int G, int K,
-                                                           float thr, int cap, float* out_scores, long long* out_classes,
-                                                           float* out_strides, int32_t* out_cells, int32_t* out_counts,
-                                                           int32_t* out_total) {
-  __shared__ int s_warp[32];
-  __shared__ int s_base;
-  const int b = blockIdx.x;
-  const long long total = (long long)G * K;
+constexpr int kSelThreads = 256, kSelPer = 16;          // one CTA covers 4096 consecutive scores of one image
+constexpr int kSelChunk = kSelThreads * kSelPer;
+// pass 1: kept scores per chunk
+__global__ void __launch_bounds__(kSelThreads) solo_select_count_kernel(const float* scores, long long total, float thr,
+                                                                       int n_chunks, int32_t* chunk_counts) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
   const float* sc = scores + (size_t)b * total;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_base = 0;
-  __syncthreads();
-  for (long long i0 = 0; i0 < total; i0 += 1024) {
-    const long long i = i0 + threadIdx.x;
-    const float v = i < total ? __ldg(sc + i) : 0.0f;
-    const bool keep = i < total && v > thr;
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) s_warp[warp] = __popc(m);
-    __syncthreads();
-    int before = 0, all = 0;
+  const long long i0 = (long long)chunk * kSelChunk + (long long)threadIdx.x * kSelPer;
+  int c = 0;
 #pragma unroll
-    for (int w = 0; w < 32; ++w) {
-      const int c = s_warp[w];
-      before += w < warp ? c : 0;
-      all += c;
-    }
-    const int slot = s_base + before + __popc(m & ((1u << lane) - 1u));
-    if (keep && slot < cap) {
-      const int cell = (int)(i / K);
-      const size_t o = (size_t)b * cap + slot;
-      out_scores[o] = v;
-      out_classes[o] = (long long)(i - (long long)cell * K);
-      out_strides[o] = cell_strides[cell];
-      out_cells[o] = cell;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_base += all;
-    __syncthreads();
+  for (int e = 0; e < kSelPer; ++e) {
+    const long long i = i0 + e;
+    c += (i < total && __ldg(sc + i) > thr) ? 1 : 0;
   }
-  const int n = min(s_base, cap);
-  for (int q = n + threadIdx.x; q < cap; q += 1024) {  // defined padding
-    const size_t o = (size_t)b * cap + q;
-    out_scores[o] = 0.0f; out_classes[o] = 0; out_strides[o] = 1.0f; out_cells[o] = 0;
-  }
+  __shared__ int s_w[kSelThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+  __syncthreads();
   if (threadIdx.x == 0) {
-    out_counts[b] = n;
-    if (out_total) out_total[b] = s_base;
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < kSelThreads / 32; ++w) t += s_w[w];
+    chunk_counts[(size_t)b * n_chunks + chunk] = t;
+  }
+}
+// pass 2: exclusive scan of the chunk counts of one image (one warp), counts / totals out
+__global__ void solo_select_scan_kernel(int32_t* chunk_counts, int n_chunks, int cap, int32_t* out_counts, int32_t* out_total) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  int32_t* cc = chunk_counts + (size_t)b * n_chunks;
+  int run = 0;
+  for (int c0 = 0; c0 < n_chunks; c0 += 32) {
+    const int c = c0 + lane;
+    const int v = c < n_chunks ? cc[c] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (c < n_chunks) cc[c] = run + inc - v;  // exclusive prefix
+    run += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (lane == 0) {
+    out_counts[b] = min(run, cap);
+    if (out_total) out_total[b] = run;
+  }
+}
+// pass 3: every chunk writes its kept elements at base + rank (thread = 16 consecutive scores, so ranks follow the
+// row-major tf.where order); the last chunk's CTA also pads the rows past the count
+__global__ void __launch_bounds__(kSelThreads) solo_select_scatter_kernel(const float* scores, const float* cell_strides,
+                                                                         long long total, int K, float thr, int cap,
+                                                                         int n_chunks, const int32_t* chunk_base,
+                                                                         const int32_t* counts, float* out_scores,
+                                                                         long long* out_classes, float* out_strides,
+                                                                         int32_t* out_cells) {
+  __shared__ int s_w[kSelThreads / 32];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* sc = scores + (size_t)b * total;
+  const long long i0 = (long long)chunk * kSelChunk + (long long)threadIdx.x * kSelPer;
+  float v[kSelPer];
+  unsigned keep = 0;
+#pragma unroll
+  for (int e = 0; e < kSelPer; ++e) {
+    const long long i = i0 + e;
+    v[e] = i < total ? __ldg(sc + i) : 0.0f;
+    keep |= (i < total && v[e] > thr) ? (1u << e) : 0u;
+  }
+  const int mine = __popc(keep);
+  int inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  int before = 0;
+#pragma unroll
+  for (int w = 0; w < kSelThreads / 32; ++w) before += w < warp ? s_w[w] : 0;
+  int slot = chunk_base[(size_t)b * n_chunks + chunk] + before + inc - mine;
+#pragma unroll
+  for (int e = 0; e < kSelPer; ++e) {
+    if ((keep >> e) & 1u) {
+      if (slot < cap) {
+        const long long i = i0 + e;
+        const int cell = (int)(i / K);
+        const size_t o = (size_t)b * cap + slot;
+        out_scores[o] = v[e];
+        out_classes[o] = (long long)(i - (long long)cell * K);
+        out_strides[o] = cell_strides[cell];
+        out_cells[o] = cell;
+      }
+      ++slot;
+    }
+  }
+  if (chunk == n_chunks - 1) {  // defined padding
+    for (int q = counts[b] + threadIdx.x; q < cap; q += kSelThreads) {
+      const size_t o = (size_t)b * cap + q;
+      out_scores[o] = 0.0f; out_classes[o] = 0; out_strides[o] = 1.0f; out_cells[o] = 0;
+    }
   }
 }
 // kernels [B, G, E] rows of the kept cells -> [B, cap, E] (zeros past the count); one warp per row, 16-byte copies
@@ -516,9 +572,15 @@ __global__ void solo_gather_kernels_kernel(const float4* kernels, const int32_t*
 }  // namespace
 }  // namespace d2b
 
+static size_t solo_select_chunks(const d2b_solo_select_params* p) {
+  const long long total = (long long)p->num_cells * p->num_classes;
+  const long long n = (total + kSelChunk - 1) / kSelChunk;
+  return (size_t)(n > 0 ? n : 1);
+}
 extern "C" size_t d2b_solo_select_workspace_bytes(const d2b_solo_select_params* p) {
-  if (!p || p->batch < 0 || p->max_candidates < 1) return 0;
-  return ws_slice(sizeof(int32_t) * (size_t)p->batch * p->max_candidates);
+  if (!p || p->batch < 0 || p->max_candidates < 1 || p->num_cells < 0 || p->num_classes < 1) return 0;
+  return ws_slice(sizeof(int32_t) * (size_t)p->batch * p->max_candidates) +
+         ws_slice(sizeof(int32_t) * (size_t)p->batch * solo_select_chunks(p));
 }
 extern "C" int d2b_solo_select(const d2b_solo_select_params* p, void* workspace, size_t workspace_bytes,
                                d2b_stream_t stream) {
@@ -526,21 +588,31 @@ extern "C" int d2b_solo_select(const d2b_solo_select_params* p, void* workspace,
   D2B_REQUIRE(p->batch >= 0 && p->num_cells >= 0 && p->num_classes >= 1 && p->channels >= 0, "solo_select: negative sizes");
   D2B_REQUIRE(p->max_candidates >= 1 && p->max_candidates <= 65535, "solo_select: max_candidates must be in [1, 65535]");
   D2B_REQUIRE(p->channels % 4 == 0, "solo_select: channels=%d must be a multiple of 4", p->channels);
+  D2B_REQUIRE(p->batch <= 65535, "solo_select: batch too large");
   if (p->batch == 0) return D2B_OK;
   D2B_REQUIRE(p->scores && p->cell_strides && p->out_scores && p->out_classes && p->out_strides && p->out_counts,
               "solo_select: NULL pointer");
   D2B_REQUIRE(!p->out_kernels || p->kernels, "solo_select: out_kernels needs kernels");
-  const size_t need = ws_slice(sizeof(int32_t) * (size_t)p->batch * p->max_candidates);
+  const size_t need = d2b_solo_select_workspace_bytes(p);
   if (workspace == nullptr || workspace_bytes < need) {
     set_last_error("solo_select needs %zu workspace bytes", need);
     return D2B_EWORKSPACE;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int32_t* cells = static_cast<int32_t*>(workspace);
-  solo_select_kernel<<<p->batch, 1024, 0, st>>>(p->scores, p->cell_strides, p->num_cells, p->num_classes, p->score_threshold,
-                                                p->max_candidates, p->out_scores,
-                                                reinterpret_cast<long long*>(p->out_classes), p->out_strides, cells,
-                                                p->out_counts, p->out_total);
+  int32_t* chunk_counts = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) +
+                                                     ws_slice(sizeof(int32_t) * (size_t)p->batch * p->max_candidates));
+  const long long total = (long long)p->num_cells * p->num_classes;
+  const int n_chunks = (int)solo_select_chunks(p);
+  const dim3 grid(n_chunks, p->batch);
+  solo_select_count_kernel<<<grid, kSelThreads, 0, st>>>(p->scores, total, p->score_threshold, n_chunks, chunk_counts);
+  D2B_LAUNCH_CHECK();
+  solo_select_scan_kernel<<<p->batch, 32, 0, st>>>(chunk_counts, n_chunks, p->max_candidates, p->out_counts, p->out_total);
+  D2B_LAUNCH_CHECK();
+  solo_select_scatter_kernel<<<grid, kSelThreads, 0, st>>>(p->scores, p->cell_strides, total, p->num_classes,
+                                                          p->score_threshold, p->max_candidates, n_chunks, chunk_counts,
+                                                          p->out_counts, p->out_scores,
+                                                          reinterpret_cast<long long*>(p->out_classes), p->out_strides, cells);
   D2B_LAUNCH_CHECK();
   if (p->out_kernels && p->channels > 0) {
     D2B_REQUIRE((reinterpret_cast<uintptr_t>(p->kernels) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->out_kernels) & 15) == 0,
