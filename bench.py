@@ -524,17 +524,20 @@ def other_configs(dev, iters=10):
         kerns = [torch.randn((B, g_, g_, E), device=dev, generator=g) / 16 for g_ in grids]
         full = SOLOv2Inference(0.5, 500, "gaussian", 2.0, 0.05, 100, score_threshold=0.1, num_grids=grids,
                                strides=(8, 8, 16, 32, 32), max_candidates=1024)
-        # object-like masks need smooth mask features: low-frequency waves per channel + a bias channel that the
-        # kernels weight negatively (a few % of the pixels end up inside a mask, in blobs)
+        # object-like masks (one blob per candidate, like a trained head): channel 0 is a bias, every other channel a
+        # Gaussian bump; a candidate's kernel picks one bump (+8) against the bias (-4) -> a disk of radius ~1.2 sigma
         yy = torch.arange(H, device=dev, dtype=torch.float32)[None, :, None, None]
         xx = torch.arange(W, device=dev, dtype=torch.float32)[None, None, :, None]
-        fy = torch.rand((1, 1, 1, E), device=dev, generator=g) * 0.12
-        fx = torch.rand((1, 1, 1, E), device=dev, generator=g) * 0.12
-        ph = torch.rand((B, 1, 1, E), device=dev, generator=g) * 6.28
-        sfeat = torch.cos(yy * fy + xx * fx + ph).contiguous()
+        cy = torch.rand((B, 1, 1, E), device=dev, generator=g) * H
+        cx = torch.rand((B, 1, 1, E), device=dev, generator=g) * W
+        sg = torch.rand((B, 1, 1, E), device=dev, generator=g) * 35 + 5
+        sfeat = torch.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * sg * sg)).contiguous()
         sfeat[..., 0] = 1.0
         for k_ in kerns:
-            k_[..., 0] = -1.6 * (E / 2.0) ** 0.5 / 16  # about -1.6 sigma of the logit
+            k_.mul_(0.01)
+            pick = torch.randint(1, E, k_.shape[:-1] + (1,), device=dev, generator=g)
+            k_.scatter_(-1, pick, 8.0)
+            k_[..., 0] = -4.0
         ms = med(lambda: full.inference(probs, kerns, sfeat, (800, 1333)))
         res = full.inference(probs, kerns, sfeat, (800, 1333))
         r["full_inference_mask_coverage"] = float(res["pred_masks"].float().mean())

@@ -13,13 +13,16 @@ probs = [torch.where(torch.rand((B, g_, g_, 80), device=dev, generator=g) < 0.00
 kerns = [torch.randn((B, g_, g_, E), device=dev, generator=g) / 16 for g_ in grids]
 yy = torch.arange(H, device=dev, dtype=torch.float32)[None, :, None, None]
 xx = torch.arange(W, device=dev, dtype=torch.float32)[None, None, :, None]
-fy = torch.rand((1, 1, 1, E), device=dev, generator=g) * 0.12
-fx = torch.rand((1, 1, 1, E), device=dev, generator=g) * 0.12
-ph = torch.rand((B, 1, 1, E), device=dev, generator=g) * 6.28
-feat = torch.cos(yy * fy + xx * fx + ph).contiguous()
+cy = torch.rand((B, 1, 1, E), device=dev, generator=g) * H
+cx = torch.rand((B, 1, 1, E), device=dev, generator=g) * W
+sg = torch.rand((B, 1, 1, E), device=dev, generator=g) * 35 + 5
+feat = torch.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * sg * sg)).contiguous()  # bumps: one blob per candidate
 feat[..., 0] = 1.0
 for k_ in kerns:
-    k_[..., 0] = -1.6 * (E / 2.0) ** 0.5 / 16
+    k_.mul_(0.01)
+    pick = torch.randint(1, E, k_.shape[:-1] + (1,), device=dev, generator=g)
+    k_.scatter_(-1, pick, 8.0)
+    k_[..., 0] = -4.0
 head = SOLOv2Inference(0.5, 500, "gaussian", 2.0, 0.05, 100, score_threshold=0.1, num_grids=grids, strides=(8, 8, 16, 32, 32),
                        max_candidates=int(sys.argv[1]) if len(sys.argv) > 1 else 1024)
 
@@ -48,4 +51,7 @@ tail = head.postprocess(None, cand["scores"], cand["classes"], cand["strides"], 
 out["upsample_ms"] = med(lambda: solo_upsample_masks(tail["packed_masks"], (H, W), (800, 1333), 0.5, False))
 out["inference_ms"] = med(lambda: head.inference(probs, kerns, feat, (800, 1333)))
 out["candidates"] = float(cand["counts"].float().mean())
+res = head.inference(probs, kerns, feat, (800, 1333))
+out["detections"] = float(res["num"].float().mean())
+out["coverage"] = float(res["pred_masks"].float().mean())
 print(json.dumps(out))
