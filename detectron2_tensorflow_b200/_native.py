@@ -15,6 +15,7 @@ MAX_LEVELS = 8
 DTYPE_F32, DTYPE_BF16 = 0, 1
 TOPK_IDENTITY, TOPK_SIGMOID = 0, 1
 MNMS_GAUSSIAN, MNMS_LINEAR = 0, 1
+IOU_TYPES = {"iou": 0, "giou": 1, "diou": 2, "ciou": 3}
 
 _vp = C.c_void_p
 _i32 = C.c_int32
@@ -108,7 +109,7 @@ class GetDeltasParams(C.Structure):
 
 
 class PairwiseIouParams(C.Structure):
-    _fields_ = [("boxes1", _vp), ("boxes2", _vp), ("n1", _i64), ("n2", _i64), ("out", _vp)]
+    _fields_ = [("boxes1", _vp), ("boxes2", _vp), ("n1", _i64), ("n2", _i64), ("out", _vp), ("iou_type", _i32)]
 
 
 MATCH_MAX_THRESHOLDS = 4

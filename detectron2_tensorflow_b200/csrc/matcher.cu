@@ -57,6 +57,42 @@ __global__ void get_deltas_kernel(const float4* src, const float4* tgt, long lon
   if (i < n) out[i] = encode_deltas(__ldg(src + i), __ldg(tgt + i), wy, wx, wh, ww);
 }
 
+// box_list_ops.py:335-371 (iou_type giou / diou / ciou), the reference's op order; boxes are (y1, x1, y2, x2)
+__device__ __forceinline__ float pair_iou_variant(const float4 a, const float4 b, int type) {
+  const float ih = fmaxf(0.0f, fminf(a.z, b.z) - fmaxf(a.x, b.x));
+  const float iw = fmaxf(0.0f, fminf(a.w, b.w) - fmaxf(a.y, b.y));
+  const float inter = ih * iw;
+  const float h1 = a.z - a.x, w1 = a.w - a.y, h2 = b.z - b.x, w2 = b.w - b.y;
+  float u = h1 * w1 + h2 * w2;
+  u = u - inter;
+  const float iou = (u == 0.0f) ? 0.0f : inter / u;
+  const float dy = fmaxf(a.z, b.z) - fminf(a.x, b.x);
+  const float dx = fmaxf(a.w, b.w) - fminf(a.y, b.y);
+  if (type == D2B_GIOU) {
+    const float convex = fmaxf(0.0f, dy) * iw;  // (sic) :344
+    float t = convex - u;
+    t = (convex == 0.0f) ? 0.0f : t / convex;
+    return iou - t;
+  }
+  const float diag2 = dy * dy + dx * dx;
+  const float cx = (a.y + a.w) / 2.0f - (b.y + b.w) / 2.0f;
+  const float cy = (a.x + a.z) / 2.0f - (b.x + b.z) / 2.0f;
+  const float cd2 = cx * cx + cy * cy;
+  const float diou = iou - ((diag2 == 0.0f) ? 0.0f : cd2 / diag2);
+  if (type == D2B_DIOU) return diou;
+  const float d = atanf(w1 / h1) - atanf(w2 / h2);
+  const float v = 0.40528473456935109f * (d * d);  // 4 / pi^2
+  float den = 1.0f - iou;
+  den = den + v;
+  return diou - (v / den) * v;
+}
+__global__ void pairwise_iou_variant_kernel(const float4* b1, const float4* b2, long long n2, int type, float* out) {
+  const long long i = blockIdx.y;
+  const float4 g = __ldg(b1 + i);
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += (long long)gridDim.x * blockDim.x)
+    __stcs(out + i * n2 + j, pair_iou_variant(g, __ldg(b2 + j), type));
+}
+
 __global__ void pairwise_iou_kernel(const float4* b1, long long n1, const float4* b2, long long n2, float* out) {
   // one row of boxes1 per blockIdx.y, columns strided over the block: coalesced 4 B/pair stores
   const long long i = blockIdx.y;
@@ -437,7 +473,12 @@ extern "C" int d2b_pairwise_iou(const d2b_pairwise_iou_params* p, void*, size_t,
   if (p->n1 == 0 || p->n2 == 0) return D2B_OK;
   D2B_REQUIRE(p->boxes1 && p->boxes2 && p->out, "pairwise_iou: NULL pointer");
   D2B_REQUIRE(p->n1 <= 65535, "pairwise_iou: n1=%lld > 65535 rows (put the larger set in boxes2)", (long long)p->n1);
+  D2B_REQUIRE(p->iou_type >= D2B_IOU && p->iou_type <= D2B_CIOU, "pairwise_iou: unknown iou_type %d", p->iou_type);
   const unsigned gx = (unsigned)((p->n2 + 4 * 256 - 1) / (4 * 256));
+  if (p->iou_type != D2B_IOU)
+    pairwise_iou_variant_kernel<<<dim3(gx, (unsigned)p->n1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(p->boxes1), reinterpret_cast<const float4*>(p->boxes2), p->n2, p->iou_type, p->out);
+  else
   pairwise_iou_kernel<<<dim3(gx, (unsigned)p->n1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(p->boxes1), p->n1, reinterpret_cast<const float4*>(p->boxes2), p->n2, p->out);
   D2B_LAUNCH_CHECK();

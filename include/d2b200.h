@@ -381,14 +381,21 @@ D2B_API int d2b_get_deltas(const d2b_get_deltas_params* p, void* workspace, size
                            d2b_stream_t stream);
 
 /* ------------------------------------------------------------------------
- * pairwise_iou (iou_type='iou')             lib/structures/box_list_ops.py:295-334
- * boxes1 [n1,4], boxes2 [n2,4] -> out [n1, n2]
+ * pairwise_iou                              lib/structures/box_list_ops.py:295-371
+ * boxes1 [n1,4], boxes2 [n2,4] -> out [n1, n2].  iou_type: D2B_IOU (:295-334, the matching path),
+ * D2B_GIOU / D2B_DIOU / D2B_CIOU (:335-371, the YOLOv4 losses; GIoU keeps the reference's
+ * convex_heights * intersect_widths product; CIoU goes through atan: 1e-5 relative, the others are exact).
  * ---------------------------------------------------------------------- */
+#define D2B_IOU 0
+#define D2B_GIOU 1
+#define D2B_DIOU 2
+#define D2B_CIOU 3
 typedef struct {
   const float* boxes1;
   const float* boxes2;
   int64_t n1, n2;
   float* out;
+  int32_t iou_type;
 } d2b_pairwise_iou_params;
 D2B_API size_t d2b_pairwise_iou_workspace_bytes(const d2b_pairwise_iou_params* p);
 D2B_API int d2b_pairwise_iou(const d2b_pairwise_iou_params* p, void* workspace, size_t workspace_bytes,

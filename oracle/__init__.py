@@ -292,12 +292,16 @@ def reframe_box_masks_to_image_masks(box_masks, boxes, image_shape, mask_thresho
     return out
 
 
-def pairwise_iou(boxes1, boxes2):
-    """lib/structures/box_list_ops.py:295-334 (iou_type='iou') -> [n1, n2]."""
+def pairwise_iou(boxes1, boxes2, iou_type="iou"):
+    """lib/structures/box_list_ops.py:295-371 -> [n1, n2]; iou_type in iou / giou / diou / ciou."""
     b1 = _f32(boxes1).reshape(-1, 4)
     b2 = _f32(boxes2).reshape(-1, 4)
     out = np.zeros((b1.shape[0], b2.shape[0]), np.float32)
-    lib().orc_pairwise_iou(_p(b1), C.c_int64(b1.shape[0]), _p(b2), C.c_int64(b2.shape[0]), _p(out))
+    if iou_type == "iou":
+        lib().orc_pairwise_iou(_p(b1), C.c_int64(b1.shape[0]), _p(b2), C.c_int64(b2.shape[0]), _p(out))
+    else:
+        lib().orc_pairwise_iou_variant(_p(b1), C.c_int64(b1.shape[0]), _p(b2), C.c_int64(b2.shape[0]),
+                                       {"giou": 1, "diou": 2, "ciou": 3}[iou_type], _p(out))
     return out
 
 

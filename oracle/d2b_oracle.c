@@ -833,6 +833,48 @@ ORC_API void orc_pairwise_iou(const float* b1, int64_t n1, const float* b2, int6
     for (int64_t j = 0; j < n2; ++j) out[i * n2 + j] = orc_pair_iou(b1 + 4 * i, b2 + 4 * j);
 }
 
+/* lib/structures/box_list_ops.py:335-371: the iou_type != "iou" branches of pairwise_iou (YOLOv4 losses).
+ *   giou (:343-349): convex = convex_heights * intersect_widths  (sic: the reference multiplies by the INTERSECTION
+ *        width); giou = iou - where(convex == 0, 0, (convex - unions) / convex)
+ *   diou (:351-364): iou - where(diag2 == 0, 0, centre_dist2 / diag2)
+ *   ciou (:365-370): v = 4/pi^2 * (atan(w1/h1) - atan(w2/h2))^2; alpha = v / (1 - iou + v); diou - alpha * v
+ * fp32, one rounding per written op; tf.atan on the CPU is libm's atanf.  type: 1 giou, 2 diou, 3 ciou. */
+static float orc_pair_iou_variant(const float* a, const float* b, int type) {
+  const float ih = fmaxf(0.0f, fminf(a[2], b[2]) - fmaxf(a[0], b[0]));
+  const float iw = fmaxf(0.0f, fminf(a[3], b[3]) - fmaxf(a[1], b[1]));
+  const float inter = ih * iw;
+  const float h1 = a[2] - a[0], w1 = a[3] - a[1], h2 = b[2] - b[0], w2 = b[3] - b[1];
+  float u = h1 * w1 + h2 * w2;
+  u = u - inter;
+  const float iou = (u == 0.0f) ? 0.0f : inter / u;
+  const float dy = fmaxf(a[2], b[2]) - fminf(a[0], b[0]);
+  const float dx = fmaxf(a[3], b[3]) - fminf(a[1], b[1]);
+  if (type == 1) {
+    const float convex = fmaxf(0.0f, dy) * iw;
+    float t = convex - u;
+    t = (convex == 0.0f) ? 0.0f : t / convex;
+    return iou - t;
+  }
+  const float diag2 = dy * dy + dx * dx;
+  float cx = (a[1] + a[3]) / 2.0f - (b[1] + b[3]) / 2.0f;
+  float cy = (a[0] + a[2]) / 2.0f - (b[0] + b[2]) / 2.0f;
+  const float cd2 = cx * cx + cy * cy;
+  const float diou = iou - ((diag2 == 0.0f) ? 0.0f : cd2 / diag2);
+  if (type == 2) return diou;
+  float d = atanf(w1 / h1) - atanf(w2 / h2);
+  const float v = 0.40528473456935109f * (d * d); /* 4 / pi^2 */
+  float den = 1.0f - iou;
+  den = den + v;
+  const float alpha = v / den;
+  return diou - alpha * v;
+}
+ORC_API void orc_pairwise_iou_variant(const float* b1, int64_t n1, const float* b2, int64_t n2, int type, float* out) {
+#pragma omp parallel for num_threads(ORC_NT) schedule(static)
+  for (int64_t i = 0; i < n1; ++i)
+    for (int64_t j = 0; j < n2; ++j)
+      out[i * n2 + j] = type == 0 ? orc_pair_iou(b1 + 4 * i, b2 + 4 * j) : orc_pair_iou_variant(b1 + 4 * i, b2 + 4 * j, type);
+}
+
 /* lib/modeling/matcher.py:8-174 Matcher.__call__ on a match-quality matrix q [M, N] (+ optional crowd matrix
  * [Mc, N]).  thresholds has nt entries (without the -inf/+inf ends), labels nt+1 entries. */
 ORC_API void orc_matcher(const float* q, int64_t M, int64_t N, const float* crowd, int64_t Mc,

@@ -322,6 +322,15 @@ def main(out_path=None):
         out[f"dp_{fmt}_boxes"] = np.asarray(res.boxes)
         out[f"dp_{fmt}_valid"] = np.asarray(res.get_field("is_valid"))
 
+    # ---- 17. pairwise_iou with iou_type giou / diou / ciou (box_list_ops.py:335-371)
+    ia, ib = rand_boxes(rng, 40, 200, 300, 4, 150), rand_boxes(rng, 25, 200, 300, 4, 150)
+    ib[:5] = ia[:5]                      # identical boxes
+    ib[5] = [10, 10, 10, 40]             # zero height
+    ia[6] = [300, 300, 320, 330]         # disjoint from everything
+    out["pi_a"], out["pi_b"] = ia, ib
+    for ty in ("iou", "giou", "diou", "ciou"):
+        out[f"pi_{ty}"] = np.asarray(R.box_list_ops.pairwise_iou(R.box_list.BoxList(t(ia)), R.box_list.BoxList(t(ib)), ty))
+
     out_path = out_path or os.path.join(HERE, "reference_python.npz")
     np.savez_compressed(out_path, **out)
     print(os.path.basename(out_path) + ":", len(out), "arrays,", os.path.getsize(out_path) // 1024, "KiB")

@@ -223,3 +223,13 @@ def test_detector_postprocess(oracle_lib, z):
         assert np.array_equal(dense, z[f"dp_{fmt}_masks"])
         assert np.array_equal(z[f"dp_{fmt}_valid"], valid)
         assert np.array_equal(z[f"dp_{fmt}_boxes"], z["dp_boxes"] * valid[..., None])  # boxes stay unscaled
+
+
+def test_pairwise_iou_variants(oracle_lib, z):
+    """pairwise_iou(iou_type=...) (box_list_ops.py:295-371): iou / giou (with the reference's convex_heights *
+    intersect_widths) / diou exact; ciou 1e-5 (atan), same NaN pattern (zero-height boxes)."""
+    for ty in ("iou", "giou", "diou"):
+        assert np.array_equal(oracle_lib.pairwise_iou(z["pi_a"], z["pi_b"], ty), z[f"pi_{ty}"])
+    got, want = oracle_lib.pairwise_iou(z["pi_a"], z["pi_b"], "ciou"), z["pi_ciou"]
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-6, equal_nan=True)

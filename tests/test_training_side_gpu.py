@@ -235,3 +235,30 @@ def test_roi_pooler_backward_adjoint(cuda, oracle_lib):
     lhs = float((out.double() * T(g, cuda).double()).sum())
     rhs = float(sum((T(f, cuda).double() * gf.double()).sum() for f, gf in zip(feats, got)))
     assert abs(lhs - rhs) <= 1e-5 * float(sum((np.abs(f).astype(np.float64) * c).sum() for f, c in zip(feats, bound)))
+
+
+@pytest.mark.parametrize("iou_type", ["iou", "giou", "diou", "ciou"])
+def test_pairwise_iou_variants(cuda, oracle_lib, iou_type):
+    """pairwise_iou(iou_type=...) (box_list_ops.py:295-371) vs the oracle (exact; CIoU 1e-5 through atan) and vs the
+    reference-python golden."""
+    import os
+    from detectron2_tensorflow_b200.structures import pairwise_iou
+    rng = np.random.default_rng(77)
+    a = np.stack([rng.uniform(0, 200, 300), rng.uniform(0, 300, 300), rng.uniform(0, 200, 300), rng.uniform(0, 300, 300)], 1)
+    a = np.concatenate([np.minimum(a[:, :2], a[:, 2:]), np.maximum(a[:, :2], a[:, 2:])], 1).astype(np.float32)
+    b = a[rng.permutation(300)[:130]] + rng.normal(0, 3, (130, 4)).astype(np.float32)
+    b[:10] = a[:10]
+    b[10] = [5, 5, 5, 50]
+    got = pairwise_iou(torch.from_numpy(a).to(cuda), torch.from_numpy(b).to(cuda), iou_type).cpu().numpy()
+    want = oracle_lib.pairwise_iou(a, b, iou_type)
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_python.npz"))
+    gz = pairwise_iou(torch.from_numpy(z["pi_a"]).to(cuda), torch.from_numpy(z["pi_b"]).to(cuda), iou_type).cpu().numpy()
+    if iou_type == "ciou":
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        assert np.allclose(got, want, rtol=1e-5, atol=1e-6, equal_nan=True)
+        assert np.allclose(gz, z["pi_ciou"], rtol=1e-5, atol=1e-6, equal_nan=True)
+    else:
+        assert np.array_equal(got, want)
+        assert np.array_equal(gz, z[f"pi_{iou_type}"])
+    with pytest.raises(ValueError):
+        pairwise_iou(torch.from_numpy(a).to(cuda), torch.from_numpy(b).to(cuda), "siou")
