@@ -164,6 +164,11 @@ class SoloDynamicMasksParams(C.Structure):
                 ("score_sums", _vp), ("mask_logits", _vp)]
 
 
+class MaskRcnnInferenceParams(C.Structure):
+    _fields_ = [("mask_logits", _vp), ("pred_classes", _vp), ("num_masks", _i64), ("mask_h", _i32), ("mask_w", _i32),
+                ("num_classes", _i32), ("out", _vp)]
+
+
 class SoloSelectParams(C.Structure):
     _fields_ = [("scores", _vp), ("kernels", _vp), ("cell_strides", _vp), ("batch", _i32), ("num_cells", _i32),
                 ("num_classes", _i32), ("channels", _i32), ("score_threshold", _f32), ("max_candidates", _i32),
@@ -206,6 +211,7 @@ OPS = {
     "solo_dynamic_masks": SoloDynamicMasksParams,
     "solo_upsample": SoloUpsampleParams,
     "solo_select": SoloSelectParams,
+    "mask_rcnn_inference": MaskRcnnInferenceParams,
 }
 EXPORTS = ["d2b_version", "d2b_status_string", "d2b_last_error", "d2b_kernel_launch_count"] + \
           [f"d2b_{op}{sfx}" for op in OPS for sfx in ("", "_workspace_bytes")]

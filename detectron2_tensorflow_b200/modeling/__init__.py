@@ -9,3 +9,4 @@ from .single_stage_heads.yolov4_outputs import YOLOv4Inference
 from .single_stage_heads.solo_v2 import (point_nms, solo_mask_encode, solo_dynamic_masks, solo_upsample_masks,
                                          SOLOv2Inference)
 from .postprocessing import detector_postprocess
+from .roi_heads.mask_head import mask_rcnn_inference

@@ -611,6 +611,24 @@ D2B_API int d2b_solo_postprocess(const d2b_solo_postprocess_params* p, void* wor
                                  d2b_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * mask_rcnn_inference                  lib/modeling/roi_heads/mask_head.py:71-103
+ *   pred_mask_logits [M, Hm, Wm, C] NHWC -> (transpose, gather_nd by pred_classes, sigmoid) -> [M, Hm, Wm]
+ * The soft masks `detector_postprocess` pastes (d2b_paste_masks).  C == 1 is the class-agnostic head (the reference
+ * indexes channel 1 of 1 there, :98, which TF's GPU gather_nd turns into zeros; channel 0 is used here).  A class
+ * outside [0, C) gives sigmoid(0) = 0.5 like TF's GPU gather_nd.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const float* mask_logits;
+  const int64_t* pred_classes; /* [M] */
+  int64_t num_masks;
+  int32_t mask_h, mask_w, num_classes;
+  float* out; /* [M, Hm, Wm] */
+} d2b_mask_rcnn_inference_params;
+D2B_API size_t d2b_mask_rcnn_inference_workspace_bytes(const d2b_mask_rcnn_inference_params* p);
+D2B_API int d2b_mask_rcnn_inference(const d2b_mask_rcnn_inference_params* p, void* workspace, size_t workspace_bytes,
+                                    d2b_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * SOLOv2 candidate selection          lib/modeling/single_stage_heads/solo_v2.py:481-497
  *   keep_inds = tf.where(pred_scores > score_threshold)   (row-major over [cells, classes])
  *   scores = gather_nd(pred_scores, keep_inds); classes = keep_inds[:, 1];

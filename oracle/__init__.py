@@ -490,3 +490,14 @@ def solo_select(pred_scores, pred_kernels, num_grids, strides, score_threshold):
     keep = np.argwhere(sc > np.float32(score_threshold))
     cell = np.concatenate([np.full(g * g, s_, np.float32) for g, s_ in zip(num_grids, strides)])
     return sc[keep[:, 0], keep[:, 1]], keep[:, 1].astype(np.int64), _f32(pred_kernels)[keep[:, 0]], cell[keep[:, 0]]
+
+
+def mask_rcnn_inference(pred_mask_logits, pred_classes):
+    """lib/modeling/roi_heads/mask_head.py:71-103: logits [M,Hm,Wm,C] NHWC, classes [M] -> sigmoid of the class channel
+    [M,Hm,Wm] (class-agnostic C == 1: channel 0)."""
+    x = _f32(pred_mask_logits)
+    M, Hm, Wm, Cc = x.shape
+    c = np.zeros(M, np.int64) if Cc == 1 else np.asarray(pred_classes, np.int64)
+    sel = x[np.arange(M), :, :, np.clip(c, 0, Cc - 1)]
+    sel = np.where(((c >= 0) & (c < Cc))[:, None, None], sel, np.float32(0))
+    return sigmoid_array(sel)

@@ -53,7 +53,7 @@ def load_reference():
     L.batch_nms, L.matrix_nms = nms.batch_nms, nms.matrix_nms
     # training-only / conv-layer names pulled in by import lines, never called on this path
     for nm in ("smooth_l1_loss", "Linear", "Conv2D", "sigmoid_focal_loss", "iou_loss", "dice_loss", "DeformConv2D",
-               "ModulatedDeformConv2D", "GroupNorm", "Upsample"):
+               "ModulatedDeformConv2D", "GroupNorm", "Upsample", "ConvTranspose2D", "get_norm"):
         setattr(L, nm, None)
     L.resize_images = fn.resize_images
     L.Sequential = imp("reflib.layers.base").Sequential
@@ -71,7 +71,8 @@ def load_reference():
                 retinanet=imp("reflib.modeling.single_stage_heads.retinanet"),
                 yolo=imp("reflib.modeling.single_stage_heads.yolov4_outputs"),
                 solo=imp("reflib.modeling.single_stage_heads.solo_v2"),
-                postprocessing=imp("reflib.modeling.postprocessing"))
+                postprocessing=imp("reflib.modeling.postprocessing"),
+                mask_head=imp("reflib.modeling.roi_heads.mask_head"))
     return types.SimpleNamespace(**mods)
 
 
@@ -330,6 +331,15 @@ def main(out_path=None):
     out["pi_a"], out["pi_b"] = ia, ib
     for ty in ("iou", "giou", "diou", "ciou"):
         out[f"pi_{ty}"] = np.asarray(R.box_list_ops.pairwise_iou(R.box_list.BoxList(t(ia)), R.box_list.BoxList(t(ib)), ty))
+
+    # ---- 18. mask_rcnn_inference (mask_head.py:71-103): NHWC logits -> class channel -> sigmoid
+    ml = (rng.standard_normal((7, 6, 6, 5)) * 3).astype(np.float32)
+    mc = rng.integers(0, 5, 7).astype(np.int64)
+    inst = R.box_list.SparseBoxList(t(np.stack([np.zeros(7, np.int64), np.arange(7)], 1)),
+                                    R.box_list.BoxList(t(rand_boxes(rng, 7, 60, 80, 8, 40))), [1, 7])
+    inst.data.add_field("pred_classes", t(mc))
+    R.mask_head.mask_rcnn_inference(t(ml), inst)
+    out.update(mi_logits=ml, mi_classes=mc, mi_out=np.asarray(inst.data.get_field("pred_masks")))
 
     out_path = out_path or os.path.join(HERE, "reference_python.npz")
     np.savez_compressed(out_path, **out)

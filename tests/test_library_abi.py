@@ -49,7 +49,8 @@ def test_struct_layout_matches_header(lib, tmp_path):
              "yolo_postprocess": "d2b_yolo_params", "point_nms": "d2b_point_nms_params",
              "solo_mask_encode": "d2b_solo_mask_encode_params", "solo_postprocess": "d2b_solo_postprocess_params",
              "solo_dynamic_masks": "d2b_solo_dynamic_masks_params",
-             "solo_upsample": "d2b_solo_upsample_params", "solo_select": "d2b_solo_select_params"}
+             "solo_upsample": "d2b_solo_upsample_params", "solo_select": "d2b_solo_select_params",
+             "mask_rcnn_inference": "d2b_mask_rcnn_inference_params"}
     assert set(names) == set(_native.OPS)
     prog = '#include <stdio.h>\n#include "d2b200.h"\nint main(){' + "".join(
         f'printf("{op} %zu\\n", sizeof({st}));' for op, st in names.items()) + "return 0;}"

@@ -47,3 +47,30 @@ def test_paste_masks_full_image(cuda, oracle_lib):
     got = reframe_box_masks_to_image_masks(torch.from_numpy(masks).to(cuda), torch.from_numpy(boxes).to(cuda), (800, 1333))
     assert np.array_equal(got.cpu().numpy(), want)
     assert want.sum() > 0
+
+
+def test_mask_rcnn_inference(cuda, oracle_lib):
+    """mask_rcnn_inference (mask_head.py:71-103): gather of the predicted class channel + sigmoid, bit-exact vs the oracle
+    (same Cephes sigmoid), 1e-6 vs the reference-python golden; class-agnostic head; out-of-range classes."""
+    import os
+    import torch
+    from detectron2_tensorflow_b200.modeling import mask_rcnn_inference
+    from detectron2_tensorflow_b200.structures import BoxList, SparseBoxList
+    rng = np.random.default_rng(31)
+
+    def run(logits, classes):
+        M = logits.shape[0]
+        idx = torch.stack([torch.zeros(M, dtype=torch.int64), torch.arange(M)], 1).to(cuda)
+        inst = SparseBoxList(idx, BoxList(torch.zeros((M, 4), device=cuda)), (1, M))
+        inst.data.add_field("pred_classes", torch.from_numpy(classes).to(cuda))
+        assert mask_rcnn_inference(torch.from_numpy(logits).to(cuda), inst) is None
+        return inst.data.get_field("pred_masks").cpu().numpy()
+
+    for M, hm, C in ((1600, 28, 80), (37, 14, 3), (5, 7, 1)):
+        lg = (rng.standard_normal((M, hm, hm, C)) * 4).astype(np.float32)
+        cl = rng.integers(0, C, M).astype(np.int64)
+        if C > 1:
+            cl[0], cl[-1] = -1, C  # out of range: sigmoid(0)
+        assert np.array_equal(run(lg, cl), oracle_lib.mask_rcnn_inference(lg, cl))
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_python.npz"))
+    assert np.allclose(run(z["mi_logits"], z["mi_classes"]), z["mi_out"], rtol=1e-6, atol=1e-7)

@@ -233,3 +233,10 @@ def test_pairwise_iou_variants(oracle_lib, z):
     got, want = oracle_lib.pairwise_iou(z["pi_a"], z["pi_b"], "ciou"), z["pi_ciou"]
     assert np.array_equal(np.isnan(got), np.isnan(want))
     assert np.allclose(got, want, rtol=1e-5, atol=1e-6, equal_nan=True)
+
+
+def test_mask_rcnn_inference(oracle_lib, z):
+    """mask_rcnn_inference (mask_head.py:71-103): class channel of the NHWC logits -> sigmoid (shim sigmoid is numpy's:
+    1e-6 relative)."""
+    got = oracle_lib.mask_rcnn_inference(z["mi_logits"], z["mi_classes"])
+    assert np.allclose(got, z["mi_out"], rtol=1e-6, atol=1e-7)
