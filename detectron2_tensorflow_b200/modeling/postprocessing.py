@@ -7,7 +7,7 @@ from ..structures.mask_ops import reframe_box_masks_to_image_masks
 
 
 def detector_postprocess(results, output_shape, mask_format, image_shapes=None, mask_threshold=0.5, scope=None):
-    """Resize the output instances (same arguments and return structure as the reference).
+    """Image-size masks for the detections of an R-CNN (arguments and return structure of the reference function).
 
     results: dense BoxList [N, R] with `pred_masks` [N, R, mh, mw], `is_valid` and the `image_shape` tracking.
     mask_format "conventional": masks are pasted at the boxes as they are; "fixed": at the boxes scaled by

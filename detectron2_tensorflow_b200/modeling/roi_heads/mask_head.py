@@ -5,9 +5,9 @@ from ... import _native as nv
 
 
 def mask_rcnn_inference(pred_mask_logits, pred_instances):
-    """Convert pred_mask_logits [M, Hmask, Wmask, C] (NHWC; C = 1 for a class-agnostic head) to foreground probability
-    masks of the predicted classes and attach them to `pred_instances` (SparseBoxList with `pred_classes`) as the
-    `pred_masks` field [M, Hmask, Wmask] -- like the reference, returns None.  One gather + sigmoid kernel instead of the
+    """Per detection, sigmoid of the mask-head logits of ITS predicted class: logits [M, Hmask, Wmask, C] (NHWC; C = 1
+    for a class-agnostic head) + `pred_instances.data['pred_classes']` -> new field `pred_masks` [M, Hmask, Wmask] on
+    `pred_instances` (a SparseBoxList); returns None, as the reference function does.  One gather + sigmoid kernel instead of the
     reference's full NHWC -> NCHW transpose."""
     dev = nv.device_of(pred_mask_logits)
     x = nv.to_device(pred_mask_logits, dev, torch.float32)
