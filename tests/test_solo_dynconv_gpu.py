@@ -143,3 +143,41 @@ def test_full_size_config4(cuda):
     p3, sm3, _ = solo_dynamic_masks(feat, kern, 0.5, counts)
     assert torch.equal(packed, p3) and torch.equal(sm, sm3)
     print(f"full size: max |logit error| / sum|terms| = {ratio:.3e}")
+
+
+def test_graph_capture_and_concurrent_streams(cuda):
+    """The cluster-launched tensor-core kernel inside a CUDA graph (replays bit-identical to the eager call, also after
+    the static inputs are refilled) and two calls in flight on different streams (each allocates all of TMEM on its SMs:
+    the second waits for shared memory, no deadlock)."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    B, n, H, W, E = 2, 300, 64, 96, 64
+    feat = torch.randn((B, H, W, E), generator=g).to(cuda)
+    kern = (torch.randn((B, n, E), generator=g) / 8).to(cuda)
+    want = solo_dynamic_masks(feat, kern)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(device=cuda)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        solo_dynamic_masks(feat, kern)  # warm-up on the capture stream (workspace, function attributes)
+        torch.cuda.current_stream().synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            got = solo_dynamic_masks(feat, kern)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    feat2 = torch.randn((B, H, W, E), generator=g).to(cuda)
+    want2 = solo_dynamic_masks(feat2, kern)
+    feat.copy_(feat2)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(got[0], want2[0]) and torch.equal(got[1], want2[1])
+    # two streams in flight
+    s1, s2 = torch.cuda.Stream(device=cuda), torch.cuda.Stream(device=cuda)
+    outs = []
+    for s in (s1, s2, s1, s2):
+        with torch.cuda.stream(s):
+            outs.append(solo_dynamic_masks(feat, kern))
+    torch.cuda.synchronize()
+    for o in outs:
+        assert torch.equal(o[0], want2[0]) and torch.equal(o[1], want2[1])
