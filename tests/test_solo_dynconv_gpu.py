@@ -43,7 +43,8 @@ def make_inputs(rng, B, n, H, W, E, blobs=True):
 
 @pytest.mark.parametrize("B,n,hw,E,thr", [(2, 130, (24, 32), 32, 0.5), (1, 500, (50, 84), 256, 0.5), (3, 77, (25, 37), 8, 0.5),
                                           (2, 300, (40, 64), 40, 0.3), (1, 128, (16, 16), 256, 0.5), (1, 1, (3, 5), 4, 0.5),
-                                          (2, 257, (31, 33), 64, 0.7), (1, 40, (9, 13), 16, 0.9995), (1, 140, (9, 13), 16, 0.0)])
+                                          (2, 257, (31, 33), 64, 0.7), (1, 40, (9, 13), 16, 0.9995), (1, 140, (9, 13), 16, 0.0),
+                                          (1, 1000, (50, 100), 512, 0.5), (2, 640, (23, 29), 1024, 0.5)])
 def test_dynamic_masks_vs_oracle(cuda, oracle_lib, B, n, hw, E, thr):
     H, W = hw
     rng = np.random.default_rng(B * 1000 + n + E)
