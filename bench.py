@@ -438,7 +438,7 @@ def run_gpu(args):
         del hx, ho
         torch.cuda.empty_cache()
         try:
-            line["other_configs"] = other_configs(dev)
+            line["other_configs"] = other_configs(dev, cpu=not args.no_cpu)
         except Exception as e:  # noqa: BLE001  (informational leg: never fails the bench line)
             line["other_configs"] = {"error": repr(e)[:200]}
 
@@ -452,7 +452,7 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def other_configs(dev, iters=10):
+def other_configs(dev, iters=10, cpu=True):
     """configs[2] (RetinaNet post-processing, batch 32) and configs[3] (SOLOv2: Matrix-NMS over 500 candidates at 1/4
     resolution, batch 16, plus the steps either side of it), inputs resident, CUDA events, median of `iters` after 3
     warm-ups; inputs (2 GB each) are larger than L2.  Informational: a failure is recorded, it does not fail the bench."""
@@ -485,8 +485,18 @@ def other_configs(dev, iters=10):
         head = RetinaNetInference(num_classes=K)
         ms = med(lambda: head.inference(cls, dl, anchors))
         nsc = sum(c.numel() for c in cls)
-        out["configs[2] RetinaNet R50-FPN post-processing, batch 32"] = {
-            "ms": ms, "images_per_s": N / ms * 1e3, "logit_GB": nsc * 4 / 1e9, "single_read_GBps": nsc * 4 / ms / 1e6}
+        r2 = {"ms": ms, "images_per_s": N / ms * 1e3, "logit_GB": nsc * 4 / 1e9, "single_read_GBps": nsc * 4 / ms / 1e6}
+        if cpu:  # the oracle (port of the reference's TF-CPU path) on 2 of the 32 images, all host threads
+            import oracle
+            hc = [c[:2].cpu().numpy() for c in cls]
+            hd = [d[:2].cpu().numpy() for d in dl]
+            ha = [a.cpu().numpy() for a in anchors]
+            t0 = time.perf_counter()
+            oracle.retinanet_inference(hc, hd, ha, K, 1000, 0.05, 0.5, 100)
+            dt = time.perf_counter() - t0
+            r2["cpu_oracle"] = {"images_per_s": 2 / dt, "cores": oracle.max_threads(), "sample": "2 of the 32 images, one pass",
+                                "gpu_over_cpu": (N / ms * 1e3) / (2 / dt)}
+        out["configs[2] RetinaNet R50-FPN post-processing, batch 32"] = r2
         del cls, dl, anchors
         torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001
@@ -500,6 +510,14 @@ def other_configs(dev, iters=10):
         ms = med(lambda: matrix_nms(masks, classes, scores))
         by = masks.numel() * 4
         r = {"matrix_nms_fp32_masks_ms": ms, "matrix_nms_images_per_s": B / ms * 1e3, "mask_read_GBps": by / ms / 1e6}
+        if cpu:  # the oracle's matrix_nms (lib/layers/nms.py:29-83 restated) on ONE image's 500 masks, all host threads
+            import oracle
+            t0 = time.perf_counter()
+            oracle.matrix_nms(m, c, s, None, "gaussian", 2.0)
+            dt = time.perf_counter() - t0
+            r["matrix_nms_cpu_oracle"] = {"images_per_s": 1 / dt, "cores": oracle.max_threads(),
+                                          "sample": "1 of the 16 images (500 masks), one pass",
+                                          "gpu_over_cpu": (B / ms * 1e3) * dt}
         del masks
         torch.cuda.empty_cache()
         feat = torch.randn((B, H, W, E), device=dev, generator=g)
