@@ -358,14 +358,14 @@ __global__ void __launch_bounds__(kHistThreads) topk_collect(TopkArgs a, u64* ou
 }
 
 // SIGMOID rows: histogram of the raw logit keys (sign + exponent = one bin per binade), then the cutoff (see the
-// header comment).  Long rows are SAMPLED: the first kPreSample elements of every chunk (1/16 of the row), one
+// header comment).  Long rows are SAMPLED: the first kPreSample elements of every chunk (1/32 of the row; 1/16 measured 30 us slower), one
 // CTA per kPreGroup chunks.  The cutoff only has to be a lower bound of the k-th largest logit, and pass 0
 // verifies it by exact count (and repeats without a cutoff otherwise), so the second full read of the class
 // logits disappears.
 constexpr int kPreBits = 9;
 constexpr int kPreBins = 1 << kPreBits;
 constexpr int kPreCopies = 16;       // [bin][lane & 15]: at most 2 lanes of a warp share a word
-constexpr int kPreSample = 4096;     // sampled elements per chunk of a long row
+constexpr int kPreSample = 2048;     // sampled elements per chunk of a long row (1/32 of a 64 K-element chunk)
 constexpr int kPreGroup = 4;         // chunks served by one CTA in sampled mode
 constexpr int kPreMinChunks = 8;     // rows shorter than this many chunks are histogrammed in full
 __global__ void __launch_bounds__(kHistThreads) topk_prehist(TopkArgs a) {
