@@ -37,6 +37,14 @@ WORKLOAD = ("configs[1]: Mask R-CNN R50-FPN, 16 synthetic 800x1333 images/GPU: R
             "box ROIAlign 7x7 on 16000 ROIs, Fast R-CNN per-class NMS, mask ROIAlign 14x14 on 1600 dets")
 
 
+def workload_config(world=1):
+    """The `config` object of BOTH arms (GPU and --impl reference): one workload, described once."""
+    n = IMAGES_PER_RANK
+    return {"workload": WORKLOAD, "images_per_gpu": n, "rois_per_step_per_gpu": n * (ROIS_PER_IMAGE + DETS_PER_IMAGE),
+            "cache": "inputs larger than L2 (1.46 GB features + 0.8 GB outputs per step vs 126 MB L2)",
+            "sharding": "images by batch index, no collective"}
+
+
 def measured_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
     (profiles/roofline_traffic.json; null when absent)."""
@@ -211,12 +219,14 @@ def cpu_step(host, n_images, stage_s=None):
     return dict(proposals=(pb, pl, pv), box_feats=box_feats, dets=(db, ds, dc, dv), mask_feats=mask_feats)
 
 
-def time_cpu(host, n_images, steps, warmup):
-    """Returns (ROIs/s, seconds per step, threads, per-stage seconds per step, NMS boxes entering per step)."""
+def time_cpu(host, n_images, steps, warmup, threads=None):
+    """Returns dict: ROIs/s (from the median step), seconds per step (median, mean), threads, per-stage seconds per
+    step, NMS boxes entering per step."""
     import oracle
     oracle.build()
     # all the host threads this process may use -- explicitly, because torchrun exports OMP_NUM_THREADS=1
-    oracle.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    oracle.set_num_threads(threads if threads else avail)
     ts = []
     stage = [0.0, 0.0, 0.0, 0.0]
     for i in range(warmup + steps):
@@ -229,33 +239,54 @@ def time_cpu(host, n_images, steps, warmup):
     # boxes entering NMS on this sample: min(pre, HWA) per (image, level) + Fast R-CNN candidates
     nms_in = n_images * sum(min(PRE_NMS, a.shape[0]) for a in host["anchors"]) + \
         int((host["scores"][:n_images * ROIS_PER_IMAGE, :-1] > SCORE_THR).sum())
-    return rois / float(np.mean(ts)), float(np.mean(ts)), oracle.max_threads(), [x / steps for x in stage], nms_in
+    med = float(np.median(ts))
+    r = {"rois_per_s": rois / med, "sec_median": med, "sec_mean": float(np.mean(ts)), "threads": oracle.max_threads(),
+         "stage_sec": [x / steps for x in stage], "nms_in": nms_in, "rois": rois}
+    oracle.set_num_threads(avail)
+    return r
 
 
-def cpu_baseline_dict(host, n_images, steps, warmup, sample):
-    v, sec, cores, st, nms_in = time_cpu(host, n_images, steps, warmup)
-    return {"value": v, "unit": "ROIs/s", "cores": cores, "kind": "port", "sample": sample, "ms_per_step": sec * 1e3,
-            "stages_ms": {"rpn_proposals": st[0] * 1e3, "box_roi_align_7x7": st[1] * 1e3, "fast_rcnn_post": st[2] * 1e3,
-                          "mask_roi_align_14x14": st[3] * 1e3},
-            "roi_align_rois_per_s": n_images * (ROIS_PER_IMAGE + DETS_PER_IMAGE) / (st[1] + st[3]),
-            "nms_boxes_per_s": nms_in / (st[0] + st[2]),
-            "note": "oracle/ = C restatement of the reference's TF-CPU path (TensorFlow is not installable here), "
-                    "OpenMP over all host threads"}, v, sec
+def cpu_baseline_dict(host, n_images, steps, warmup, sample, one_thread_images=2):
+    """The CPU oracle (port of the reference's TF-CPU path) on `n_images` of the workload with every host thread
+    (median of `steps` after `warmup`), plus a 1-thread leg on a smaller sample."""
+    r = time_cpu(host, n_images, steps, warmup)
+    st = r["stage_sec"]
+    cb = {"value": r["rois_per_s"], "unit": "ROIs/s", "cores": r["threads"], "kind": "port", "sample": sample,
+          "ms_per_step": r["sec_median"] * 1e3, "ms_per_step_mean": r["sec_mean"] * 1e3, "statistic": "median",
+          "stages_ms": {"rpn_proposals": st[0] * 1e3, "box_roi_align_7x7": st[1] * 1e3, "fast_rcnn_post": st[2] * 1e3,
+                        "mask_roi_align_14x14": st[3] * 1e3},
+          "roi_align_rois_per_s": r["rois"] / (st[1] + st[3]),
+          "nms_boxes_per_s": r["nms_in"] / (st[0] + st[2]),
+          "note": "oracle/ = C restatement of the reference's TF-CPU path (TensorFlow is not installable here), "
+                  "OpenMP over all host threads"}
+    if one_thread_images:
+        k = min(one_thread_images, n_images)
+        r1 = time_cpu(host, k, 3, 1, threads=1)
+        s1 = r1["stage_sec"]
+        cb["one_thread"] = {"value": r1["rois_per_s"], "unit": "ROIs/s", "cores": 1,
+                            "sample": f"first {k} of the {IMAGES_PER_RANK} images, median of 3 steps after 1 warm-up",
+                            "ms_per_image": r1["sec_median"] * 1e3 / k,
+                            "roi_align_rois_per_s": r1["rois"] / (s1[1] + s1[3]),
+                            "nms_boxes_per_s": r1["nms_in"] / (s1[0] + s1[2])}
+    return cb, r["rois_per_s"], r["sec_median"]
 
 
 def run_reference(args):
+    """The reference arm: the CPU oracle (port of the reference's TF-CPU path) on the SAME config as the GPU arm --
+    all 16 images per step, the same warm-up count, every host thread."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_img = 2
+    n_img = IMAGES_PER_RANK
     host = make_host_inputs(n_img)
-    steps, warmup = max(min(args.steps, 20), 1), max(min(args.warmup, 2), 1)  # bounded: each step ~0.3-1 s of CPU
-    cb, v, sec = cpu_baseline_dict(host, n_img, steps, warmup, f"{n_img} images/step x {steps} steps")
+    steps, warmup = max(min(args.steps, 150), 1), max(args.warmup, 3)  # ~0.7 s of CPU per step
+    cb, v, sec = cpu_baseline_dict(host, n_img, steps, warmup,
+                                   f"{n_img} of {n_img} images per step, median of {steps} steps after {warmup} warm-ups")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "ROIs/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{n_img} of the 16 images per step"},
+        "config": workload_config(),
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "ROIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -373,13 +404,23 @@ def run_gpu(args):
     hbm_peak, peak_src = peaks()
     alg = algorithmic_bytes_box_pool(n)
     ach = alg / (st[1] * 1e-3) / 1e9
+    traffic = measured_traffic()
+    roofline = {"kernel": "roi_align_kernel<float,float,2> (box pooler 7x7, 16000 ROIs)", "bound": "hbm",
+                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
+                "algorithmic_bytes_per_launch": alg, "peak_source": peak_src, "kernel_ms": float(st[1]),
+                "traffic_source": "profiles/roofline_traffic.json (ncu --set full capture of the same launch; "
+                                  "constant, not re-measured in this run)",
+                "note": "frac uses SURVEY 8(d)'s algorithmic bytes (whole pyramid read once), which over-count: 1,000 "
+                        "ROIs/image touch about 2/3 of the pyramid.  frac_on_traffic = DRAM bytes actually moved / "
+                        "kernel time / peak is the honest distance from the HBM roofline."}
+    if traffic:
+        roofline["achieved_on_traffic"] = traffic / (st[1] * 1e-3) / 1e9
+        roofline["frac_on_traffic"] = roofline["achieved_on_traffic"] / hbm_peak
     line = {
         "metric": METRIC, "value": value, "unit": "ROIs/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "images_per_gpu": n, "rois_per_step_per_gpu": rois_rank,
-                   "cache": "inputs larger than L2 (1.46 GB features + 0.8 GB outputs per step vs 126 MB L2)",
-                   "sharding": "images by batch index, no collective"},
+        "config": workload_config(world),
         "wall_ms_per_step": wall_ms / K,
         "execution": {"timed_region": f"one CUDA graph per step ({args.chunks} image blocks on concurrent streams), "
                                       f"{args.in_flight} steps in flight on alternating streams",
@@ -398,16 +439,31 @@ def run_gpu(args):
         "nms": {"boxes_per_s": (rpn_nms_in + cand) * world / ((st[0] + st[2]) * 1e-3), "unit": "boxes/s",
                 "boxes_in_per_step_per_gpu": rpn_nms_in + cand,
                 "note": "boxes entering NMS / time of the full proposal + Fast R-CNN post stages"},
-        "roofline": {"kernel": "roi_align_kernel<float,float,2> (box pooler 7x7, 16000 ROIs)", "bound": "hbm",
-                     "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": measured_traffic(),
-                     "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
+        "roofline": roofline,
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
 
+    # ---- strong scaling of the fixed 16-image batch (north_star / SURVEY 8e), gather to rank 0 timed
+    pipe.run(2 * args.in_flight)
+    barrier()
+    if world > 1:
+        try:
+            line["strong"] = strong_scaling(hp, x, dev, world, rank, K, W, args.chunks, args.in_flight, gstep,
+                                            step_latency_ms, ms_per_step)
+        except Exception as e:  # noqa: BLE001
+            line["strong"] = {"error": repr(e)[:300]}
+    else:
+        line["strong"] = {"global_batch": n, "images_per_rank": [n], "ms_per_step": step_latency_ms,
+                          "speedup_vs_1gpu": 1.0, "gather_ms": 0.0, "pipelined_ms_per_step": ms_per_step,
+                          "pipelined_speedup_vs_1gpu": 1.0,
+                          "note": "1 GPU: the whole batch on one rank, results already on rank 0 (no gather); "
+                                  "ms_per_step = one graphed step at a time"}
     if args.no_e2e:
         if rank == 0:
             EMIT(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
         return
     # ---- end-to-end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
     hx = to_torch(host, dev=None, pin=True)
@@ -434,22 +490,308 @@ def run_gpu(args):
                            "over three CUDA streams (upload / kernels / download)"}
 
     # ---- the other BASELINE.json configs (parity-test cases, not bench lines): device-resident timings, N=1 only
-    if world == 1 and not args.no_extras:
-        del hx, ho
+    if not args.no_extras:
+        del hx, ho, x, pipe, gstep, out
         torch.cuda.empty_cache()
+        oc = {}
+        if world == 1:
+            try:
+                oc["configs[0] Faster R-CNN R50-FPN post-backbone ops, 1 image"] = config0_single_image(dev, cpu=not args.no_cpu)
+            except Exception as e:  # noqa: BLE001  (informational leg: never fails the bench line)
+                oc["configs[0]"] = {"error": repr(e)[:200]}
+            try:
+                oc.update(other_configs(dev, cpu=not args.no_cpu))
+            except Exception as e:  # noqa: BLE001
+                oc["configs[2..3]"] = {"error": repr(e)[:200]}
         try:
-            line["other_configs"] = other_configs(dev, cpu=not args.no_cpu)
-        except Exception as e:  # noqa: BLE001  (informational leg: never fails the bench line)
-            line["other_configs"] = {"error": repr(e)[:200]}
+            oc["configs[4] ROIAlign / NMS sweep 256..65536"] = config4_sweep(dev, world, rank, cpu=not args.no_cpu)
+        except Exception as e:  # noqa: BLE001
+            oc["configs[4]"] = {"error": repr(e)[:200]}
+        line["other_configs"] = oc
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     if world == 1 and not args.no_cpu:
-        cb, _, _ = cpu_baseline_dict(host, 2, 2, 1, "first 2 of the 16 images, 2 timed steps after 1 warm-up")
+        cb, _, _ = cpu_baseline_dict(host, n, 10, 2, f"{n} of {n} images per step, median of 10 steps after 2 warm-ups")
         line["cpu_baseline"] = cb
     if rank == 0:
         EMIT(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def strong_scaling(hp, x, dev, world, rank, K, W, chunks, in_flight, full_step, full_latency_ms, full_pipe_ms):
+    """SURVEY.md 8(e) / north_star: the FIXED batch of 16 images partitioned by image index over the ranks, no
+    collective on the path, and the fixed-size padded results (proposals + detections) gathered to rank 0 with one
+    grouped send/recv over NVLink inside the timed region.  Every rank holds the same seeded global batch and cuts
+    its own block.  Returns the `strong` object of the bench line (rank 0's view; times are max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    from detectron2_tensorflow_b200 import sharding
+    from detectron2_tensorflow_b200.engine import GATHER_KEYS
+    n = IMAGES_PER_RANK
+    R = ROIS_PER_IMAGE
+    b, e = sharding.image_block(n, world, rank)
+    xl = {"anchors": x["anchors"], "shapes": x["shapes"][b:e].contiguous(), "scores": x["scores"][b * R:e * R].contiguous(),
+          "cls_deltas": x["cls_deltas"][b * R:e * R].contiguous()}
+    for k in ("logits", "deltas", "feats"):
+        xl[k] = [t[b:e].contiguous() for t in x[k]]
+    ch = max(1, min(chunks, (e - b) // 2))
+    pipe = hp.pipeline(xl, chunks=ch, depth=in_flight)
+    g0 = pipe.steps[0]
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather(step):
+        return sharding.gather_to_rank0(step.gathered(GATHER_KEYS), n)
+
+    for _ in range(W):
+        g0.replay()
+        full = gather(g0)
+    barrier()
+    # byte identity of the gathered results with the 1-GPU run of the whole batch (rank 0's own full-batch graph)
+    identical = None
+    if rank == 0:
+        want = full_step.gathered(GATHER_KEYS)
+        identical = all(torch.equal(full[k], want[k]) for k in GATHER_KEYS)
+    # (1) latency: one step at a time, gather inside
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    barrier()
+    ev[0].record()
+    for _ in range(K):
+        g0.replay()
+        gather(g0)
+    ev[1].record()
+    barrier()
+    lat_ms = ev[0].elapsed_time(ev[1]) / K
+    # (2) the gather alone (pack + one collective + unpack on rank 0)
+    barrier()
+    ev[2].record()
+    for _ in range(K):
+        gather(g0)
+    ev[3].record()
+    barrier()
+    gather_ms = ev[2].elapsed_time(ev[3]) / K
+    # (3) throughput: `in_flight` graphed steps on alternating streams, each followed by its gather
+    cur = torch.cuda.current_stream(dev)
+
+    def run_pipe(k):
+        start = torch.cuda.Event()
+        start.record(cur)
+        for s_ in pipe.streams:
+            s_.wait_event(start)
+        for i in range(k):
+            j = i % len(pipe.steps)
+            with torch.cuda.stream(pipe.streams[j]):
+                pipe.steps[j].replay()
+                gather(pipe.steps[j])
+        for s_ in pipe.streams:
+            cur.wait_stream(s_)
+    run_pipe(2 * in_flight)
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    run_pipe(K)
+    p1.record()
+    barrier()
+    pipe_ms = p0.elapsed_time(p1) / K
+    t = torch.tensor([lat_ms, gather_ms, pipe_ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    lat_ms, gather_ms, pipe_ms = (float(v) for v in t)
+    rois = n * (ROIS_PER_IMAGE + DETS_PER_IMAGE)
+    return {"global_batch": n, "images_per_rank": [sharding.image_block(n, world, r)[1] - sharding.image_block(n, world, r)[0]
+                                                   for r in range(world)],
+            "ms_per_step": lat_ms, "rois_per_s": rois / (lat_ms * 1e-3),
+            "one_gpu_ms_per_step": full_latency_ms, "speedup_vs_1gpu": full_latency_ms / lat_ms,
+            "gather_ms": gather_ms, "gather_bytes_per_rank": int(sum(nbytes(v) for v in g0.gathered(GATHER_KEYS).values())),
+            "pipelined_ms_per_step": pipe_ms, "one_gpu_pipelined_ms_per_step": full_pipe_ms,
+            "pipelined_speedup_vs_1gpu": full_pipe_ms / pipe_ms, "pipelined_rois_per_s": rois / (pipe_ms * 1e-3),
+            "gathered_identical_to_1gpu": identical, "kernels_per_step_per_rank": g0.kernels_per_replay,
+            "note": "the fixed 16-image batch split by image index; ms_per_step = graph replay of the rank's block + "
+                    "pack + ONE dist.gather of proposals and detections to rank 0 + unpack, one step at a time, max over "
+                    "ranks (CUDA events); one_gpu_* = the same measurement of the whole batch on one GPU in this run "
+                    "(no gather needed); pipelined_* = several steps in flight on alternating streams"}
+
+
+def config0_single_image(dev, iters=20, cpu=True):
+    """BASELINE.json configs[0]: Faster R-CNN R50-FPN inference post-backbone ops on ONE 800x1333 image (test-time
+    RPN settings 1000 pre / 1000 post, 1000 ROIs 7x7, Fast R-CNN per-class NMS; rcnn.py:92-144): the latency regime."""
+    import torch
+    from detectron2_tensorflow_b200.engine import MaskRCNNPostBackbone
+    pre = post = 1000
+    host = make_host_inputs(1)
+    x = to_torch(host, dev=dev)
+    hp = MaskRCNNPostBackbone(rois_per_image=post, dets_per_image=DETS_PER_IMAGE, pre_nms_topk=pre, rpn_nms_thresh=RPN_THR,
+                              score_thresh=SCORE_THR, nms_thresh=NMS_THR, mask_on=False)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def med(fn, cold):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            if cold:
+                flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+    g = hp.capture(x, chunks=1)
+    r = {"workload": "1 image: RPN top-k 1000/level + NMS 0.7 -> 1000 proposals, ROIAlign 7x7 on 1000 ROIs, Fast R-CNN "
+                     "per-class NMS -> 100 detections",
+         "eager_ms_cold_l2": med(lambda: hp(x), True), "eager_ms_warm": med(lambda: hp(x), False),
+         "graph_ms_cold_l2": med(g.replay, True), "graph_ms_warm": med(g.replay, False),
+         "kernels_per_step": g.kernels_per_replay}
+    r["rois_per_s"] = post / (r["graph_ms_cold_l2"] * 1e-3)
+    r["images_per_s"] = 1e3 / r["graph_ms_cold_l2"]
+    if cpu:
+        import oracle
+        avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+        def cpu_once():
+            props = [oracle.rpn_predict_proposals(d, a) for d, a in zip(host["deltas"], host["anchors"])]
+            pb, _, _, _ = oracle.find_top_rpn_proposals(props, host["logits"], host["shapes"], RPN_THR, pre, post, 0.0)
+            idx = np.stack([np.zeros(post, np.int64), np.arange(post)], 1)
+            boxes = pb.reshape(-1, 4)
+            oracle.roi_pooler(host["feats"], [1 / 4., 1 / 8., 1 / 16., 1 / 32.], boxes, idx[:, 0], (7, 7), 0)
+            pred = oracle.apply_deltas(host["cls_deltas"][:post], boxes, (10., 10., 5., 5.))
+            oracle.fast_rcnn_inference(pred, host["scores"][:post], idx, (1, post), host["shapes"], SCORE_THR, NMS_THR,
+                                       DETS_PER_IMAGE, False)
+        for thr in (avail, 1):
+            oracle.set_num_threads(thr)
+            cpu_once()
+            ts = []
+            for _ in range(5):
+                t0 = time.perf_counter()
+                cpu_once()
+                ts.append(time.perf_counter() - t0)
+            ms = float(np.median(ts)) * 1e3
+            r[f"cpu_oracle_{'all' if thr == avail else 'one'}_thread{'s' if thr == avail else ''}"] = {
+                "ms": ms, "cores": thr, "rois_per_s": post / (ms * 1e-3), "gpu_over_cpu": ms / r["graph_ms_cold_l2"],
+                "sample": "the whole config (1 image), median of 5 after 1 warm-up"}
+        oracle.set_num_threads(avail)
+    return r
+
+
+def config4_sweep(dev, world=1, rank=0, iters=10, cpu=True):
+    """BASELINE.json configs[4]: ROIAlign / NMS microbenchmark sweep, 256 .. 65536 ROIs / boxes, C=256, FPN P2-P5
+    maps of 16 images, L2 flushed between iterations, CPU oracle beside each point.  Under --gpus N the M ROIs /
+    the 16 NMS segments are partitioned by image / segment index over the ranks (time = max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    from detectron2_tensorflow_b200 import sharding
+    from detectron2_tensorflow_b200.layers import batch_nms
+    from detectron2_tensorflow_b200.modeling import ROIPooler
+    from detectron2_tensorflow_b200.structures import BoxList, SparseBoxList
+    from detectron2_tensorflow_b200.utils import synthetic as syn
+    hbm_peak, _ = peaks()
+    N, C = 16, CHANNELS
+    b0, e0 = sharding.image_block(N, world, rank)
+    nl = e0 - b0
+    g = torch.Generator(device=dev).manual_seed(0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    feats = [torch.randn((nl,) + syn.level_hw(s_) + (C,), device=dev, generator=g) for s_ in syn.FPN_STRIDES]
+    scales = [1 / 4., 1 / 8., 1 / 16., 1 / 32.]
+
+    def med(fn, it=iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(it):
+            flush.zero_()
+            if world > 1:
+                dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = float(np.median(ts))
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    do_cpu = cpu and world == 1
+    if do_cpu:
+        import oracle
+        oracle.set_num_threads(avail)
+        hfeats = [f.cpu().numpy() for f in feats]
+    pooler = ROIPooler(7, scales, 0, "ROIAlignV2")
+    fbytes_all = sum(N * h * w * C * 4 for h, w in (syn.level_hw(s_) for s_ in syn.FPN_STRIDES))
+    roi_pts, nms_pts = [], []
+    for M in (256, 1024, 4096, 16384, 65536):
+        boxes, idx = syn.rois(N, M // N, seed=1)
+        sel = (idx[:, 0] >= b0) & (idx[:, 0] < e0)
+        lb, li = boxes[sel], idx[sel].copy()
+        li[:, 0] -= b0
+        inst = SparseBoxList(torch.from_numpy(li).to(dev), BoxList(torch.from_numpy(lb).to(dev)), (nl, M // N))
+        ms = med(lambda: pooler(feats, inst))
+        alg = M * 49 * C * 4 + min(fbytes_all, M * 49 * 4 * C * 4) + M * 24
+        pt = {"rois": M, "ms": ms, "rois_per_s": M / ms * 1e3, "alg_GBps": alg / ms / 1e6,
+              "frac_hbm": alg / ms / 1e6 / hbm_peak / world}
+        if do_cpu:
+            Mc = min(M, 16384)  # bounded sample of the larger points
+            t0 = time.perf_counter()
+            oracle.roi_pooler(hfeats, scales, boxes[:Mc], idx[:Mc, 0], (7, 7), 0)
+            dt = time.perf_counter() - t0
+            pt["cpu_oracle"] = {"rois_per_s": Mc / dt, "cores": avail, "sample": f"first {Mc} ROIs, one pass",
+                                "gpu_over_cpu": (M / ms * 1e3) / (Mc / dt)}
+        roi_pts.append(pt)
+    del feats
+    rng = np.random.default_rng(5)
+    S = 16  # segments (one per image), partitioned like the images
+    for n in (256, 1024, 4096, 16384, 65536):
+        cy, cx = rng.uniform(0, 800, (S, n)), rng.uniform(0, 1333, (S, n))
+        h, w = rng.uniform(16, 300, (S, n)), rng.uniform(16, 300, (S, n))
+        hb = np.stack([cy - h / 2, cx - w / 2, cy + h / 2, cx + w / 2], 2).astype(np.float32)
+        hs = rng.standard_normal((S, n)).astype(np.float32)
+        pt = {"boxes_per_segment": n}
+        for label, segs, cap in (("one_segment_uncapped", 1, n), ("sixteen_segments_cap1000", S, min(n, 1000))):
+            if segs == 1 and rank != 0:
+                continue
+            sb, se = (0, 1) if segs == 1 else (b0, e0)
+            tb = torch.from_numpy(hb[sb:se]).to(dev)
+            tsc = torch.from_numpy(hs[sb:se]).to(dev)
+            if segs == 1 and world > 1:  # a single segment does not shard: rank 0 only, no barrier
+                for _ in range(3):
+                    batch_nms(tb, tsc, cap, axis=1, iou_threshold=0.7)
+                torch.cuda.synchronize()
+                ts = []
+                for _ in range(5):
+                    flush.zero_()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    batch_nms(tb, tsc, cap, axis=1, iou_threshold=0.7)
+                    b.record()
+                    torch.cuda.synchronize()
+                    ts.append(a.elapsed_time(b))
+                ms = float(np.median(ts))
+            elif segs == 1:
+                ms = med(lambda: batch_nms(tb, tsc, cap, axis=1, iou_threshold=0.7), 5)
+            else:
+                ms = med(lambda: batch_nms(tb, tsc, cap, axis=1, iou_threshold=0.7), 5)
+            pt[label] = {"ms": ms, "boxes_per_s": segs * n / ms * 1e3, "max_output_size": cap}
+            if do_cpu:
+                k = 1 if segs == 1 else (S if n <= 4096 else 2)  # bounded sample of the big multi-segment points
+                t0 = time.perf_counter()
+                oracle.batch_nms(hb[:k], hs[:k], cap, 0.7)
+                dt = time.perf_counter() - t0
+                pt[label]["cpu_oracle"] = {"boxes_per_s": k * n / dt, "cores": min(avail, k), "sample": f"{k} segment(s), one pass",
+                                           "gpu_over_cpu": (segs * n / ms * 1e3) / (k * n / dt)}
+        nms_pts.append(pt)
+    return {"roi_align_7x7_sweep": roi_pts, "nms_sweep_thr0.7": nms_pts, "n_gpus": world,
+            "note": "16 images' P2-P5 maps, C=256, fp32; L2 flushed (256 MB write) before every timed iteration; median; "
+                    "under --gpus N the ROIs (with their images) and the 16 NMS segments are split by index over the ranks "
+                    "and the time is the max over ranks; `one_segment` cannot shard and runs on rank 0"}
 
 
 def other_configs(dev, iters=10, cpu=True):

@@ -286,7 +286,15 @@ _ws_cache = {}
 
 
 def _workspace(nbytes, device):
-    """Grow-only per-(device, stream) scratch buffer owned by the host layer (the C library never allocates)."""
+    """Scratch buffer owned by the host layer (the C library never allocates).
+
+    Eager calls: a grow-only buffer per (device, CUDA stream) -- two torch Stream objects with the same handle ARE
+    the same CUDA stream, so sharing is ordered.  During CUDA-graph capture the buffer is a fresh allocation from
+    the capturing graph's private memory pool instead: the graph then owns every workspace its kernels were baked
+    with (the pool lives as long as the graph), a later, larger eager call can never free it, and two graphs
+    replayed concurrently never share scratch memory."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:

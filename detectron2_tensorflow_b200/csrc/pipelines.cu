@@ -903,11 +903,8 @@ extern "C" int d2b_retinanet_postprocess(const d2b_retinanet_params* p, void* wo
   D2B_LAUNCH_CHECK();
   const size_t merge_smem = (size_t)a.stride * sizeof(u64);
   if (merge_smem <= 96 * 1024) {  // the per-level runs are sorted already: merge by rank instead of sorting
-    static bool attr_set = false;
-    if (!attr_set) {
-      D2B_CUDA(cudaFuncSetAttribute(retina_merge_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attr_set = true;
-    }
+    if (merge_smem > 48 * 1024)  // per device / context: set on every call (cheap), as nms.cu and sort.cu do
+      D2B_CUDA(cudaFuncSetAttribute(retina_merge_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem));
     u64* keys3b = reinterpret_cast<u64*>(ws + pl.o_keys3b);
     retina_merge_rank_kernel<<<N, 1024, merge_smem, st>>>(keys3, lvl_off, a.L, a.P3, keys3b);
     D2B_LAUNCH_CHECK();

@@ -22,6 +22,9 @@ from .structures import BoxList, ImageList, SparseBoxList
 
 PER_IMAGE_KEYS = ("logits", "deltas", "feats", "shapes")   # tensors (or lists of) with a leading image dim
 PER_ROI_KEYS = ("scores", "cls_deltas")                      # [N * rois_per_image, ...], image-major
+# the fixed-size padded per-image results a caller may want on rank 0; ROI features stay local
+GATHER_KEYS = ("proposal_boxes", "proposal_logits", "proposal_valid", "det_boxes", "det_scores", "det_classes",
+               "det_valid")
 
 
 class GraphedStep(object):
@@ -73,7 +76,9 @@ class MaskRCNNPostBackbone(object):
     def __init__(self, rois_per_image=1000, dets_per_image=100, pre_nms_topk=2000, rpn_nms_thresh=0.7,
                  min_box_side_len=0.0, score_thresh=0.05, nms_thresh=0.5, nms_cls_agnostic=False,
                  scales=(1 / 4., 1 / 8., 1 / 16., 1 / 32.), box_resolution=7, mask_resolution=14, sampling_ratio=0,
-                 pooler_type="ROIAlignV2", rpn_weights=(1.0, 1.0, 1.0, 1.0), box_weights=(10.0, 10.0, 5.0, 5.0)):
+                 pooler_type="ROIAlignV2", rpn_weights=(1.0, 1.0, 1.0, 1.0), box_weights=(10.0, 10.0, 5.0, 5.0),
+                 mask_on=True):
+        self.mask_on = bool(mask_on)  # False: Faster R-CNN (no mask pooler; BASELINE.json configs[0])
         self.R, self.D = int(rois_per_image), int(dets_per_image)
         self.pre, self.rpn_thr, self.min_len = int(pre_nms_topk), float(rpn_nms_thresh), float(min_box_side_len)
         self.score_thr, self.nms_thr, self.agnostic = float(score_thresh), float(nms_thresh), bool(nms_cls_agnostic)
@@ -118,8 +123,10 @@ class MaskRCNNPostBackbone(object):
         boxes = self.box_tf.apply_deltas(x["cls_deltas"], inst.data.boxes)
         dets, _ = fast_rcnn_inference(boxes, x["scores"], inst, self.score_thr, self.nms_thr, self.D, self.agnostic)
         mark(3)
-        dinst = SparseBoxList(self._grid(n, self.D, dev), BoxList(dets.boxes.reshape(-1, 4)), (n, self.D))
-        mask_feats = self.mask_pooler(x["feats"], dinst)
+        mask_feats = None
+        if self.mask_on:
+            dinst = SparseBoxList(self._grid(n, self.D, dev), BoxList(dets.boxes.reshape(-1, 4)), (n, self.D))
+            mask_feats = self.mask_pooler(x["feats"], dinst)
         mark(4)
         return dict(proposals=props, box_feats=box_feats, dets=dets, mask_feats=mask_feats)
 
@@ -180,10 +187,13 @@ class MaskRCNNPostBackbone(object):
     @staticmethod
     def flatten_outputs(out):
         p, d = out["proposals"], out["dets"]
-        return {"proposal_boxes": p.boxes, "proposal_logits": p.get_field("objectness_logits"),
+        flat = {"proposal_boxes": p.boxes, "proposal_logits": p.get_field("objectness_logits"),
                 "proposal_valid": p.get_field("is_valid"), "box_feats": out["box_feats"],
                 "det_boxes": d.boxes, "det_scores": d.get_field("scores"), "det_classes": d.get_field("pred_classes"),
-                "det_valid": d.get_field("is_valid"), "mask_feats": out["mask_feats"]}
+                "det_valid": d.get_field("is_valid")}
+        if out["mask_feats"] is not None:
+            flat["mask_feats"] = out["mask_feats"]
+        return flat
 
     def run_host(self, x, device=None, chunk_images=2):
         """x: dict of HOST tensors (pinned for full PCIe rate).  Returns a dict of pinned host tensors

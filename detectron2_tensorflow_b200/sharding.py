@@ -33,22 +33,61 @@ def shard_instances(indices, boxes, num_images, world_size, rank):
     return idx, boxes[sel]
 
 
+def _field_layout(local):
+    """Per-image byte layout of the packed row: key -> (offset, nbytes, trailing shape, dtype); 16-byte aligned."""
+    layout, off = {}, 0
+    for k, t in local.items():
+        per = t.element_size()
+        for d in t.shape[1:]:
+            per *= int(d)
+        layout[k] = (off, per, tuple(t.shape[1:]), t.dtype)
+        off += (per + 15) // 16 * 16
+    return layout, off
+
+
+def pack_rows(local, rows):
+    """One [rows, bytes_per_image] uint8 buffer holding every tensor of `local` ([n_local, ...] each, n_local <=
+    rows; missing rows are zero): a single concatenation kernel."""
+    layout, width = _field_layout(local)
+    n = next(iter(local.values())).shape[0]
+    parts = []
+    for k, t in local.items():
+        off, per, _, _ = layout[k]
+        b = t.contiguous().reshape(n, -1).view(torch.uint8)
+        pad = (per + 15) // 16 * 16 - per
+        parts.append(b if not pad else torch.nn.functional.pad(b, (0, pad)))
+    buf = torch.cat(parts, dim=1)
+    if n < rows:
+        buf = torch.cat([buf, buf.new_zeros((rows - n, width))])
+    return buf, layout
+
+
+def unpack_rows(buf, layout):
+    """Inverse of pack_rows on a [rows, bytes_per_image] buffer."""
+    out = {}
+    for k, (off, per, shape, dtype) in layout.items():
+        out[k] = buf[:, off:off + per].contiguous().view(dtype).reshape((buf.shape[0],) + shape)
+    return out
+
+
 def gather_to_rank0(local, num_images, group=None):
-    """Gather fixed-size per-image outputs ([n_local, ...] tensors in a dict) to rank 0 in image order.
-    Returns the full-batch dict on rank 0 and None elsewhere.  Blocks may differ by one image, so shorter
-    blocks are padded to the longest before the (equal-size) gather and trimmed afterwards."""
+    """Gather fixed-size per-image outputs ([n_local, ...] tensors in a dict) to rank 0 in image order with ONE
+    collective: every rank packs its tensors into one [longest_block, bytes_per_image] byte buffer (one kernel),
+    `dist.gather` moves it (NCCL: one grouped ncclSend/ncclRecv over NVLink; gloo in the CPU tests), rank 0 drops
+    the padding rows of shorter blocks and unpacks.  Returns the full-batch dict on rank 0 and None elsewhere."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     sizes = [image_block(num_images, world, r) for r in range(world)]
     longest = max(e - b for b, e in sizes)
-    out = {}
-    for k, t in local.items():
-        pad = longest - t.shape[0]
-        if pad:
-            t = torch.cat([t, t.new_zeros((pad,) + tuple(t.shape[1:]))])
-        t = t.contiguous()
-        bufs = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-        dist.gather(t, bufs, dst=0, group=group)
-        if rank == 0:
-            out[k] = torch.cat([bufs[r][:sizes[r][1] - sizes[r][0]] for r in range(world)])
-    return out if rank == 0 else None
+    buf, layout = pack_rows(local, longest)
+    recv = None
+    if rank == 0:
+        recv = buf.new_empty((world,) + tuple(buf.shape))
+    dist.gather(buf, list(recv.unbind(0)) if rank == 0 else None, dst=0, group=group)
+    if rank != 0:
+        return None
+    if all(e - b == longest for b, e in sizes):
+        rows = recv.reshape(world * longest, -1)
+    else:
+        rows = torch.cat([recv[r, :sizes[r][1] - sizes[r][0]] for r in range(world)])
+    return unpack_rows(rows, layout)
