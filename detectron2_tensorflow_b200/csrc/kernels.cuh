@@ -35,8 +35,11 @@ int sort_segments_desc(unsigned long long* keys, int S, int P, const int32_t* se
 // boxes [S, n, 4]; counts [S] (device, live prefix per segment; NULL => n).
 // keep [S, max_out] positions into the segment (selection order, -1 padded), num_keep [S].
 size_t nms_sorted_workspace_bytes(int S, int n, int max_out);
+// sweep = false (bitmask formulation only, see nms_uses_bitmask): only the suppression mask is built in `ws`
+// ([S][64 W][W] u64, W = ceil(n / 64)); the caller sweeps it itself (rpn_fused.cu fuses the sweep with the merge).
 int nms_sorted(const float* boxes, const int32_t* counts, int S, int n, int max_out, float thr, int32_t* keep,
-               int32_t* num_keep, void* ws, cudaStream_t st);
+               int32_t* num_keep, void* ws, cudaStream_t st, bool sweep = true);
+bool nms_uses_bitmask(int n, int max_out);
 
 // ---------------------------------------------------------------- SOLOv2 dynamic conv (solo_dynconv.cu)
 size_t solo_dynamic_masks_ws(int batch, int n, int channels);

@@ -15,7 +15,7 @@
 //     diagonal tile with ballots, and exits once `cap` boxes are kept.  Only
 //     O(n * kept) IoUs are ever evaluated and no n^2 mask exists.
 // Both are latency/dependency-bound rather than HBM-bound.
-#include "kernels.cuh"
+#include "nms.cuh"
 
 namespace d2b {
 namespace {
@@ -55,85 +55,94 @@ __device__ __forceinline__ bool iou_gt(float inter, float area_a, float area_b, 
   return inter / u > thr;
 }
 
-// Centre-distance pair filter.  IoU > thr implies ih >= thr*max(h_i,h_j) (the intersection cannot be
-// taller than either box and inter >= thr*max(area)), and ih <= (h_i+h_j)/2 - |cy_i-cy_j|, hence
-//     |cy_i - cy_j| <= (1-thr)*(h_i+h_j)/2 ,   likewise in x.
-// Each box carries r = (1-0.999*thr)*extent/2 * 1.001 + 4e-7*(|lo|+|hi|): slack three orders of magnitude
-// above fp32 rounding of the centre, so the filter never rejects a pair the exact rule accepts.  It costs one
-// 16-byte shared load + 4 adds + 2 compares per pair and rejects all but a fraction of a percent of pairs,
-// so the exact (divergent) IoU evaluation is rare.  Degenerate boxes get r = -inf (never pass, IoU := 0).
-struct FBox { float cy, cx, ry, rx; };
+// Pair filter.  IoU > thr implies ih >= thr*max(h_i,h_j) (the intersection cannot be taller than either box and
+// inter >= thr*max(area)), and ih <= (h_i+h_j)/2 - |cy_i-cy_j|, hence
+//     |cy_i - cy_j| <= (1-thr)*(h_i+h_j)/2 ,   likewise in x,
+// i.e. the boxes SHRUNK about their centres to the fraction (1-thr) of their extent must overlap.  Each box carries
+// that shrunk interval [c - r, c + r] with r = (1-0.999*thr)*extent/2 * 1.001 + 1e-6*(|lo|+|hi|): slack three orders
+// of magnitude above the fp32 rounding of c, r and c +- r, so the filter never rejects a pair the exact rule
+// accepts.  The test is four compares on one 16-byte shared load (no arithmetic) and rejects all but a fraction
+// of a percent of pairs, so the exact (divergent) IoU evaluation is rare.  Degenerate boxes get an empty interval
+// (lo = +inf, hi = -inf: never pass, IoU := 0).
+struct FBox { float ylo, xlo, yhi, xhi; };
 __device__ __forceinline__ FBox filter_box(const CBox c, float kf) {
   FBox f;
   if (c.area > 0.0f) {
-    f.cy = 0.5f * (c.ymin + c.ymax);
-    f.cx = 0.5f * (c.xmin + c.xmax);
-    f.ry = 0.5f * (1.0f - kf) * (c.ymax - c.ymin) * 1.001f + 4e-7f * (fabsf(c.ymin) + fabsf(c.ymax));
-    f.rx = 0.5f * (1.0f - kf) * (c.xmax - c.xmin) * 1.001f + 4e-7f * (fabsf(c.xmin) + fabsf(c.xmax));
+    const float cy = 0.5f * (c.ymin + c.ymax);
+    const float cx = 0.5f * (c.xmin + c.xmax);
+    const float ry = 0.5f * (1.0f - kf) * (c.ymax - c.ymin) * 1.001f + 1e-6f * (fabsf(c.ymin) + fabsf(c.ymax));
+    const float rx = 0.5f * (1.0f - kf) * (c.xmax - c.xmin) * 1.001f + 1e-6f * (fabsf(c.xmin) + fabsf(c.xmax));
+    f.ylo = cy - ry; f.yhi = cy + ry;
+    f.xlo = cx - rx; f.xhi = cx + rx;
   } else {
-    f.cy = 0.0f; f.cx = 0.0f;
-    f.ry = __int_as_float(0xff800000); f.rx = __int_as_float(0xff800000);
+    const float inf = __int_as_float(0x7f800000);
+    f.ylo = inf; f.xlo = inf; f.yhi = -inf; f.xhi = -inf;
   }
   return f;
 }
 
-// grid (row_blocks, S).  mask[seg][i][w] bit c: box (w*64+c) is suppressed by box i (only j > i).
-// 8 independent warps per CTA: warp = (column group q, row half); it owns 32 rows of the 64-row block
-// and walks column blocks rb+q, rb+q+4, ...  The 64 column boxes of a block are staged in a warp-private
-// shared-memory slice (filter record, canonical box, area), so only __syncwarp is needed.
+// grid (ceil(W/2), S).  mask[seg][i][w] bit c: box (w*64+c) is suppressed by box i (only j > i).
+// A CTA handles the 64-row blocks x and nb-1-x of its segment, so every CTA walks nb+1 column blocks (the upper
+// triangle is balanced).  8 independent warps per CTA: warp = (column group q, row half); it owns 32 rows of the
+// 64-row block and walks column blocks rb+q, rb+q+4, ...  The 64 column boxes of a block are staged in a
+// warp-private shared-memory slice (filter record, canonical box, area), so only __syncwarp is needed.
 __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* boxes, const int32_t* counts, int n,
                                                                  int W, float thr, u64* mask) {
-  __shared__ float4 s_flt[kMaskThreads / 32][64];  // (cy, cx, ry, rx)
+  __shared__ float4 s_flt[kMaskThreads / 32][64];  // (ylo, xlo, yhi, xhi) of the shrunk box
   __shared__ float4 s_box[kMaskThreads / 32][64];
   __shared__ float s_area[kMaskThreads / 32][64];
-  const int seg = blockIdx.y, rb = blockIdx.x;
+  const int seg = blockIdx.y;
   const int cnt = counts ? min(counts[seg], n) : n;
-  if (rb * 64 >= cnt) return;
+  const int nb = (cnt + 63) >> 6;
+  if ((int)blockIdx.x * 2 >= nb) return;
   const float kf = thr * 0.999f;
   const float4* b = boxes + (size_t)seg * n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = warp >> 1, r = (warp & 1) * 32 + lane;
-  const int i = rb * 64 + r;
-  const bool live = i < cnt;
-  const CBox bi = canon(live ? b[i] : make_float4(0, 0, 0, 0), live);
-  const FBox fi = filter_box(bi, kf);
-  u64* mrow = mask + ((size_t)seg * W * 64 + i) * W;
-  const int nb = (cnt + 63) >> 6;
-  for (int cb = rb + q; cb < nb; cb += kMaskThreads / 64) {
-    const int j0 = cb * 64;
+  for (int side = 0; side < 2; ++side) {
+    const int rb = side == 0 ? (int)blockIdx.x : nb - 1 - (int)blockIdx.x;
+    if (side == 1 && rb <= (int)blockIdx.x) break;  // odd nb: the middle block is done once
+    const int i = rb * 64 + r;
+    const bool live = i < cnt;
+    const CBox bi = canon(live ? b[i] : make_float4(0, 0, 0, 0), live);
+    const FBox fi = filter_box(bi, kf);
+    u64* mrow = mask + ((size_t)seg * W * 64 + i) * W;
+    for (int cb = rb + q; cb < nb; cb += kMaskThreads / 64) {
+      const int j0 = cb * 64;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = j0 + h * 32 + lane;
-      const CBox c = canon(j < cnt ? __ldg(b + j) : make_float4(0, 0, 0, 0), j < cnt);
-      const FBox f = filter_box(c, kf);
-      s_flt[warp][h * 32 + lane] = make_float4(f.cy, f.cx, f.ry, f.rx);
-      s_box[warp][h * 32 + lane] = make_float4(c.ymin, c.xmin, c.ymax, c.xmax);
-      s_area[warp][h * 32 + lane] = c.area;
-    }
-    __syncwarp();
-    // (1) branch-free filter over the 64 columns -> candidate bits (fully unrolled: immediates only)
-    unsigned clo = 0, chi = 0;
+      for (int h = 0; h < 2; ++h) {
+        const int j = j0 + h * 32 + lane;
+        const CBox c = canon(j < cnt ? __ldg(b + j) : make_float4(0, 0, 0, 0), j < cnt);
+        const FBox f = filter_box(c, kf);
+        s_flt[warp][h * 32 + lane] = make_float4(f.ylo, f.xlo, f.yhi, f.xhi);
+        s_box[warp][h * 32 + lane] = make_float4(c.ymin, c.xmin, c.ymax, c.xmax);
+        s_area[warp][h * 32 + lane] = c.area;
+      }
+      __syncwarp();
+      // (1) branch-free filter over the 64 columns -> candidate bits (fully unrolled: immediates only)
+      unsigned clo = 0, chi = 0;
 #pragma unroll
-    for (int c = 0; c < 64; ++c) {
-      const float4 fj = s_flt[warp][c];
-      const bool pass = (fabsf(fi.cy - fj.x) <= fi.ry + fj.z) && (fabsf(fi.cx - fj.y) <= fi.rx + fj.w);
-      if (c < 32) clo |= pass ? (1u << c) : 0u; else chi |= pass ? (1u << (c - 32)) : 0u;
+      for (int c = 0; c < 64; ++c) {
+        const float4 fj = s_flt[warp][c];
+        const bool pass = (fj.x <= fi.yhi) && (fi.ylo <= fj.z) && (fj.y <= fi.xhi) && (fi.xlo <= fj.w);
+        if (c < 32) clo |= pass ? (1u << c) : 0u; else chi |= pass ? (1u << (c - 32)) : 0u;
+      }
+      u64 cand = ((u64)chi << 32) | clo;
+      if (cb == rb) cand &= (r == 63) ? 0ull : (~0ull << (r + 1));  // only j > i
+      // (2) exact rule on the rare candidates
+      u64 bits = 0;
+      while (cand) {
+        const int c = __ffsll((long long)cand) - 1;
+        cand &= cand - 1;
+        const float4 bj = s_box[warp][c];
+        const float ih = fmaxf(fminf(bi.ymax, bj.z) - fmaxf(bi.ymin, bj.x), 0.0f);
+        const float iw = fmaxf(fminf(bi.xmax, bj.w) - fmaxf(bi.xmin, bj.y), 0.0f);
+        const float inter = ih * iw;
+        if (iou_gt(inter, s_area[warp][c], bi.area, thr)) bits |= 1ull << c;
+      }
+      if (live) mrow[cb] = bits;
+      __syncwarp();
     }
-    u64 cand = ((u64)chi << 32) | clo;
-    if (cb == rb) cand &= (r == 63) ? 0ull : (~0ull << (r + 1));  // only j > i
-    // (2) exact rule on the rare candidates
-    u64 bits = 0;
-    while (cand) {
-      const int c = __ffsll((long long)cand) - 1;
-      cand &= cand - 1;
-      const float4 bj = s_box[warp][c];
-      const float ih = fmaxf(fminf(bi.ymax, bj.z) - fmaxf(bi.ymin, bj.x), 0.0f);
-      const float iw = fmaxf(fminf(bi.xmax, bj.w) - fmaxf(bi.xmin, bj.y), 0.0f);
-      const float inter = ih * iw;
-      if (iou_gt(inter, s_area[warp][c], bi.area, thr)) bits |= 1ull << c;
-    }
-    if (live) mrow[cb] = bits;
-    __syncwarp();
   }
 }
 
@@ -149,12 +158,6 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* bo
 // One CTA-wide barrier per block.  The sweep stops at the cap.
 constexpr int kSweepThreads = 256;
 constexpr int kOrThreads = kSweepThreads - 32;
-
-__device__ __forceinline__ u64 warp_or64(u64 v) {
-  const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
-  const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
-  return ((u64)hi << 32) | lo;
-}
 
 __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const int32_t* counts, int n, int W, int max_out,
                                                                    const u64* mask, int32_t* keep,
@@ -248,6 +251,16 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const int32_t*
   if (tid == 0) num_keep[seg] = kept;
 }
 
+// Column-owner sweep (nms.cuh) for W <= kColSweepMaxW; one CTA per segment.
+__global__ void __launch_bounds__(kColSweepThreads) nms_sweep_cols_kernel(const int32_t* counts, int n, int W,
+                                                                           int max_out, const u64* mask,
+                                                                           int32_t* keep, int32_t* num_keep) {
+  const int seg = blockIdx.x;
+  const int cnt = counts ? min(counts[seg], n) : n;
+  const int kept = nms_sweep_columns(cnt, W, max_out, mask + (size_t)seg * W * 64 * W, keep + (size_t)seg * max_out);
+  if (threadIdx.x == 0) num_keep[seg] = kept;
+}
+
 // ------------------------------------------------------------------ B: capped lazy sweep
 constexpr int kLazyThreads = 256;
 
@@ -326,8 +339,10 @@ size_t nms_sorted_workspace_bytes(int S, int n, int max_out) {
   return ws_slice((size_t)S * W * 64 * W * sizeof(u64));
 }
 
+bool nms_uses_bitmask(int n, int max_out) { return n > 0 && max_out > 0 && !use_lazy(n, max_out); }
+
 int nms_sorted(const float* boxes, const int32_t* counts, int S, int n, int max_out, float thr, int32_t* keep,
-               int32_t* num_keep, void* ws, cudaStream_t st) {
+               int32_t* num_keep, void* ws, cudaStream_t st, bool sweep) {
   if (S <= 0) return D2B_OK;
   D2B_REQUIRE(max_out >= 0 && n >= 0, "nms: negative sizes");
   D2B_REQUIRE(thr >= 0.0f && thr <= 1.0f, "iou_threshold must be in [0, 1]");  // as tf.image.non_max_suppression
@@ -353,9 +368,13 @@ int nms_sorted(const float* boxes, const int32_t* counts, int S, int n, int max_
               max_out, kBitmaskMaxN, kLazyMaxOut);
   const int W = (n + 63) / 64;
   u64* mask = static_cast<u64*>(ws);
-  nms_mask_kernel<<<dim3(W, S), kMaskThreads, 0, st>>>(b4, counts, n, W, thr, mask);
+  nms_mask_kernel<<<dim3((W + 1) / 2, S), kMaskThreads, 0, st>>>(b4, counts, n, W, thr, mask);
   D2B_LAUNCH_CHECK();
-  nms_sweep_kernel<<<S, kSweepThreads, (size_t)W * sizeof(u64), st>>>(counts, n, W, max_out, mask, keep, num_keep);
+  if (!sweep) return D2B_OK;  // the caller runs its own sweep over the mask (fused with the proposal merge)
+  if (W <= kColSweepMaxW)
+    nms_sweep_cols_kernel<<<S, kColSweepThreads, 0, st>>>(counts, n, W, max_out, mask, keep, num_keep);
+  else
+    nms_sweep_kernel<<<S, kSweepThreads, (size_t)W * sizeof(u64), st>>>(counts, n, W, max_out, mask, keep, num_keep);
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }

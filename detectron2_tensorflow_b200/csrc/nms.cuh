@@ -1,0 +1,109 @@
+// nms.cuh -- device pieces of the bitmask NMS shared by nms.cu and rpn_fused.cu.
+#pragma once
+#include "kernels.cuh"
+
+namespace d2b {
+
+__device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
+  const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+  const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+  return ((unsigned long long)hi << 32) | lo;
+}
+
+// Greedy sweep over the suppression bitmask of ONE segment by a CTA of kColSweepThreads threads (32 warps).
+// mask[i][w] bit c: box i suppresses box 64w+c (only c > i is set / read).  Warp q OWNS the column words
+// q, q+32, ...: for word b it ORs, block by block, the rows of the KEPT boxes of every earlier 64-row block into a
+// per-lane accumulator (lane = rows l and l+32 of the block; the loads do not depend on the kept bits, so they are
+// issued several blocks ahead of the flag they wait for), then resolves the diagonal 64x64 tile with a
+// warp-parallel fixpoint and publishes the kept bits of block b in shared memory.  The serial chain per block is
+// flag -> select -> REDUX -> fixpoint (a few hundred cycles, all shared memory / registers); every global load is
+// off that chain.  Same result as the serial greedy scan: a box is kept iff no earlier kept box suppresses it.
+// Blocks after the cap (max_out kept) publish an empty set at once.  Returns the number of kept boxes (uniform
+// over the CTA, after a __syncthreads()).
+constexpr int kColSweepThreads = 1024;
+constexpr int kColSweepMaxW = 64;  // n <= 4096
+
+__device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, const unsigned long long* __restrict__ m,
+                                                 int32_t* __restrict__ kp) {
+  typedef unsigned long long u64;
+  __shared__ volatile u64 s_keep[kColSweepMaxW];
+  __shared__ volatile int s_flag[kColSweepMaxW];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = (cnt + 63) >> 6;
+  if (tid < kColSweepMaxW) { s_keep[tid] = 0; s_flag[tid] = 0; }
+  __syncthreads();
+  const u64 bitA = 1ull << lane, bitB = 1ull << (lane + 32);
+  constexpr int kAhead = 4;  // blocks whose rows are loaded before their flag is awaited
+  for (int word = warp; word < nb; word += 32) {
+    u64 acc = 0;
+    int kept_before = 0;
+    bool capped = false;
+    u64 pa[kAhead], pb[kAhead];
+#pragma unroll
+    for (int u = 0; u < kAhead; ++u) {
+      pa[u] = 0; pb[u] = 0;
+      if (u < word) {
+        pa[u] = __ldcg(m + (size_t)(u * 64 + lane) * W + word);
+        pb[u] = __ldcg(m + (size_t)(u * 64 + 32 + lane) * W + word);
+      }
+    }
+    for (int b0 = 0; b0 < word && !capped; b0 += kAhead) {
+#pragma unroll
+      for (int u = 0; u < kAhead; ++u) {
+        const int b = b0 + u;
+        if (b < word && !capped) {  // warp-uniform
+          const u64 va = pa[u], vb = pb[u];
+          const int nx = b + kAhead;  // refill this slot for the block kAhead further on
+          if (nx < word) {
+            pa[u] = __ldcg(m + (size_t)(nx * 64 + lane) * W + word);
+            pb[u] = __ldcg(m + (size_t)(nx * 64 + 32 + lane) * W + word);
+          }
+          while (s_flag[b] == 0) { }
+          const u64 K = s_keep[b];
+          acc |= ((K & bitA) ? va : 0ull) | ((K & bitB) ? vb : 0ull);
+          kept_before += __popcll(K);
+          capped = kept_before >= max_out;
+        }
+      }
+    }
+    u64 K = 0;
+    if (!capped) {
+      const int rows = min(64, cnt - word * 64);
+      u64 rem = warp_or64(acc);
+      if (rows < 64) rem |= ~0ull << rows;
+      u64 dA = 0, dB = 0;
+      if (lane < rows) dA = __ldcg(m + (size_t)(word * 64 + lane) * W + word);
+      if (lane + 32 < rows) dB = __ldcg(m + (size_t)(word * 64 + 32 + lane) * W + word);
+      u64 U = ~rem;
+      while (U) {  // warp-uniform
+        const u64 blocked = warp_or64(((U & bitA) ? dA : 0ull) | ((U & bitB) ? dB : 0ull));
+        const u64 nk = U & ~blocked;  // never empty: the first undecided row cannot be blocked
+        K |= nk;
+        U &= ~nk;
+        U &= ~warp_or64(((nk & bitA) ? dA : 0ull) | ((nk & bitB) ? dB : 0ull));
+      }
+      int c = __popcll(K);
+      const int left = max_out - kept_before;
+      while (c > left) {  // cap reached inside this block: keep only the first `left`
+        K &= ~(1ull << (63 - __clzll((long long)K)));
+        --c;
+      }
+      if (K & bitA) kp[kept_before + __popcll(K & (bitA - 1ull))] = word * 64 + lane;
+      if (K & bitB) kp[kept_before + __popcll(K & (bitB - 1ull))] = word * 64 + 32 + lane;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      s_keep[word] = K;
+      __threadfence_block();
+      s_flag[word] = 1;
+    }
+  }
+  __syncthreads();
+  int kept = 0;
+  for (int b = 0; b < nb; ++b) kept += __popcll(s_keep[b]);
+  kept = min(kept, max_out);
+  for (int j = kept + tid; j < max_out; j += kColSweepThreads) kp[j] = -1;
+  return kept;
+}
+
+}  // namespace d2b

@@ -4,77 +4,12 @@
 //   d2b_fast_rcnn_postprocess  fast_rcnn.py:28-187
 //   d2b_retinanet_postprocess  retinanet.py:285-387
 // The reference runs them as tf.map_fn over images with a CPU NMS per segment.
-#include "kernels.cuh"
+#include <stdlib.h>
+
+#include "rpn.cuh"
 
 namespace d2b {
 namespace {
-
-typedef unsigned long long u64;
-
-__device__ __forceinline__ u64 make_key(float score, unsigned idx) {
-  return ((u64)float_to_key(score) << 32) | (u64)(0xffffffffu - idx);
-}
-__device__ __forceinline__ unsigned key_index(u64 k) { return 0xffffffffu - (unsigned)k; }
-
-int pad_pow2(long long n) {
-  int P = 1;
-  while (P < n) P <<= 1;
-  return P;
-}
-
-// Ordered block compaction helper: returns this thread's output slot (or -1) and adds the
-// block total to `base` (shared), preserving thread order.  All threads must call it.
-template <int THREADS>
-__device__ __forceinline__ int block_compact(bool flag, int& base_reg, int* s_warp) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned m = __ballot_sync(0xffffffffu, flag);
-  if (lane == 0) s_warp[warp] = __popc(m);
-  __syncthreads();
-  int before = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < THREADS / 32; ++w) {
-    const int c = s_warp[w];
-    if (w < warp) before += c;
-    total += c;
-  }
-  const int slot = flag ? base_reg + before + __popc(m & ((1u << lane) - 1u)) : -1;
-  base_reg += total;
-  __syncthreads();
-  return slot;
-}
-
-// Anchor of flat index idx: read from the materialised table, or synthesised as
-// DefaultAnchorGenerator.grid_anchors does (anchor_generator.py:92-109): cell anchor + integer grid shift.
-struct AnchorSrc {
-  const float4* table;  // [hwa, 4] or NULL
-  const float4* cell;   // [A, 4]
-  int A, gw, stride;
-  __device__ __forceinline__ float4 at(unsigned idx) const {
-    if (table) return __ldg(table + idx);
-    const unsigned a = idx % (unsigned)A, cellidx = idx / (unsigned)A;
-    const unsigned gx = cellidx % (unsigned)gw, gy = cellidx / (unsigned)gw;
-    const float sy = (float)(gy * (unsigned)stride), sx = (float)(gx * (unsigned)stride);
-    const float4 c = __ldg(cell + a);
-    return make_float4(sy + c.x, sx + c.y, sy + c.z, sx + c.w);
-  }
-};
-
-// =====================================================================================
-// RPN
-// =====================================================================================
-struct RpnArgs {
-  const float* logits[D2B_MAX_LEVELS];
-  const float4* proposals[D2B_MAX_LEVELS];
-  const float4* deltas[D2B_MAX_LEVELS];
-  AnchorSrc anchors[D2B_MAX_LEVELS];
-  long long hwa[D2B_MAX_LEVELS];
-  int L, N;
-  const int32_t* shapes;
-  float min_len;
-  float w[4];
-  float clampv;
-  int k, P, post, P2;
-};
 
 constexpr int kRpnThreads = 1024;
 
@@ -118,123 +53,13 @@ __global__ void __launch_bounds__(kRpnThreads) rpn_decode_kernel(RpnArgs a, cons
   }
 }
 
-// One CTA per image: the final per-image top-k (rpn_outputs.py:101-114) as a rank computation.
-// Each level's NMS survivors are already ordered (score desc, index asc), so the position of a
-// survivor in the sorted concatenation is its own position plus, per other level, the number of
-// survivors that precede it -- a binary search over that level's keys.  Ties across levels go to the
-// lower concat index, i.e. the earlier level (TF top_k rule).  No sort, no intermediate buffers.
-constexpr int kMergeThreads = 1024;
+constexpr int kMergeThreadsLocal = kMergeThreads;
 __global__ void __launch_bounds__(kMergeThreads) rpn_merge_rank_kernel(
     RpnArgs a, const float4* seg_boxes, const float* seg_scores, const int32_t* keep, const int32_t* num_keep,
     uint32_t* gkeys, int use_smem, float4* out_boxes, float* out_logits, uint8_t* out_valid, int32_t* out_num) {
   extern __shared__ uint32_t s_keys[];
-  const int n = blockIdx.x;
-  __shared__ int s_off[D2B_MAX_LEVELS + 1];
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int l = 0; l < a.L; ++l) { s_off[l] = acc; acc += num_keep[n * a.L + l]; }
-    s_off[a.L] = acc;
-  }
-  __syncthreads();
-  const int total = s_off[a.L];
-  const int kk = min(total, a.post);  // :105
-  uint32_t* gk = use_smem ? s_keys : gkeys + (size_t)n * a.P2;
-  constexpr int kPer = 8;  // survivors per thread per sweep: their dependent gathers are issued together
-  for (int base = 0; base < total; base += kPer * kMergeThreads) {
-    int lv[kPer], pos[kPer];
-    float sc[kPer];
-    float4 bx[kPer];
-#pragma unroll
-    for (int u = 0; u < kPer; ++u) {
-      const int ci = base + u * kMergeThreads + threadIdx.x;
-      lv[u] = 0; pos[u] = 0;
-      if (ci < total) {
-        int l = 0;
-        while (l + 1 < a.L && ci >= s_off[l + 1]) ++l;
-        lv[u] = l;
-        pos[u] = keep[(size_t)(n * a.L + l) * a.post + (ci - s_off[l])];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kPer; ++u) {
-      const int ci = base + u * kMergeThreads + threadIdx.x;
-      if (ci < total) {
-        const size_t o = (size_t)(n * a.L + lv[u]) * a.k + pos[u];
-        sc[u] = seg_scores[o];
-        bx[u] = seg_boxes[o];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kPer; ++u) {
-      const int ci = base + u * kMergeThreads + threadIdx.x;
-      if (ci < total) gk[ci] = float_to_key(sc[u]);
-    }
-    __syncthreads();  // (total <= kPer * kMergeThreads in practice: one sweep; keys of this sweep visible)
-    if (base + kPer * kMergeThreads < total) continue;  // multi-sweep: ranks are computed in the second loop
-#pragma unroll
-    for (int u = 0; u < kPer; ++u) {
-      const int ci = base + u * kMergeThreads + threadIdx.x;
-      if (ci >= total || total > kPer * kMergeThreads) continue;
-      const int l = lv[u];
-      const uint32_t key = gk[ci];
-      int rank = ci - s_off[l];
-      for (int l2 = 0; l2 < a.L; ++l2) {
-        if (l2 == l) continue;
-        const uint32_t* kl = gk + s_off[l2];
-        int lo = 0, hi = s_off[l2 + 1] - s_off[l2];
-        while (lo < hi) {  // first position whose element does NOT precede (key, ci)
-          const int mid = (lo + hi) >> 1;
-          const uint32_t ke = kl[mid];
-          const bool before = (l2 < l) ? (ke >= key) : (ke > key);
-          if (before) lo = mid + 1; else hi = mid;
-        }
-        rank += lo;
-      }
-      if (rank < a.post) {
-        const size_t o = (size_t)n * a.post + rank;
-        out_boxes[o] = bx[u];
-        out_logits[o] = sc[u];
-        out_valid[o] = 1;
-      }
-    }
-  }
-  if (total > kPer * kMergeThreads) {
-    // rare: more survivors than one sweep holds (L * min(post, k) > 8192): straightforward second pass
-    __syncthreads();
-    for (int ci = threadIdx.x; ci < total; ci += kMergeThreads) {
-      int l = 0;
-      while (l + 1 < a.L && ci >= s_off[l + 1]) ++l;
-      const uint32_t key = gk[ci];
-      int rank = ci - s_off[l];
-      for (int l2 = 0; l2 < a.L; ++l2) {
-        if (l2 == l) continue;
-        const uint32_t* kl = gk + s_off[l2];
-        int lo = 0, hi = s_off[l2 + 1] - s_off[l2];
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          const uint32_t ke = kl[mid];
-          const bool before = (l2 < l) ? (ke >= key) : (ke > key);
-          if (before) lo = mid + 1; else hi = mid;
-        }
-        rank += lo;
-      }
-      if (rank < a.post) {
-        const int row = n * a.L + l;
-        const int p2 = keep[(size_t)row * a.post + (ci - s_off[l])];
-        const size_t o = (size_t)n * a.post + rank;
-        out_boxes[o] = seg_boxes[(size_t)row * a.k + p2];
-        out_logits[o] = seg_scores[(size_t)row * a.k + p2];
-        out_valid[o] = 1;
-      }
-    }
-  }
-  for (int j = kk + threadIdx.x; j < a.post; j += kMergeThreads) {  // zero padding :111-114
-    const size_t o = (size_t)n * a.post + j;
-    out_boxes[o] = make_float4(0, 0, 0, 0);
-    out_logits[o] = 0.0f;
-    out_valid[o] = 0;
-  }
-  if (threadIdx.x == 0 && out_num) out_num[n] = kk;
+  rpn_merge_rank_body(a, blockIdx.x, seg_boxes, seg_scores, keep, num_keep, gkeys, s_keys, use_smem, out_boxes,
+                      out_logits, out_valid, out_num);
 }
 
 struct RpnPlan {
@@ -243,7 +68,9 @@ struct RpnPlan {
   int rows;
   size_t bytes;
   // offsets
-  size_t o_topk, o_keys, o_kr, o_boxes, o_scores, o_count, o_keep, o_nkeep, o_nms, o_keys2;
+  size_t o_topk, o_keys, o_kr, o_boxes, o_scores, o_count, o_keep, o_nkeep, o_nms, o_keys2, o_done;
+  bool fused_select;  // k small enough for the cluster-fused select / sort / decode kernel (rpn_fused.cu)
+  bool fused_sweep;   // ... and the NMS is the bitmask formulation: column sweep fused with the per-image merge
 };
 
 int rpn_plan(const d2b_rpn_proposals_params* p, RpnPlan& pl) {
@@ -305,7 +132,12 @@ int rpn_plan(const d2b_rpn_proposals_params* p, RpnPlan& pl) {
   pl.o_nkeep = o; o += ws_slice(rows * sizeof(int32_t));
   pl.o_nms = o; o += nms_sorted_workspace_bytes(pl.rows, a.k, a.post);
   pl.o_keys2 = o; o += ws_slice(N * a.P2 * sizeof(uint32_t));
+  pl.o_done = o; o += ws_slice(N * sizeof(int32_t));
   pl.bytes = o;
+  // D2B_RPN_GENERIC=1 forces the generic multi-launch chain (tests exercise both paths on the same inputs)
+  const char* force_generic = getenv("D2B_RPN_GENERIC");
+  pl.fused_select = a.k <= kRpnFusedMaxK && !(force_generic && force_generic[0] == '1');
+  pl.fused_sweep = pl.fused_select && nms_uses_bitmask(a.k, a.post);
   return D2B_OK;
 }
 
@@ -675,10 +507,27 @@ extern "C" int d2b_rpn_proposals(const d2b_rpn_proposals_params* p, void* worksp
   u64* nms_in = reinterpret_cast<u64*>(p->out_nms_boxes_in);
   if (nms_in) D2B_CUDA(cudaMemsetAsync(nms_in, 0, sizeof(u64), st));
 
-  rc = topk_run(pl.td, keys, nullptr, nullptr, kr, ws + pl.o_topk, st);  // rpn_outputs.py:70
-  if (rc != D2B_OK) return rc;
-  rpn_decode_kernel<<<pl.rows, kRpnThreads, 0, st>>>(a, keys, kr, seg_boxes, seg_scores, seg_count, nms_in);
-  D2B_LAUNCH_CHECK();
+  int32_t* img_done = reinterpret_cast<int32_t*>(ws + pl.o_done);
+  if (pl.fused_select) {
+    // ONE cluster launch: top-k select, sort, decode, clip, prune of every (image, level) row (:67-87)
+    rc = rpn_select_fused(a, seg_boxes, seg_scores, seg_count, img_done, nms_in, st);
+    if (rc != D2B_OK) return rc;
+  }
+  if (pl.fused_sweep) {
+    // suppression masks (:90-94), then ONE launch sweeps every segment and merges each image's levels (:101-114)
+    rc = nms_sorted(reinterpret_cast<const float*>(seg_boxes), seg_count, pl.rows, a.k, a.post, p->nms_thresh, keep,
+                    nkeep, ws + pl.o_nms, st, /*sweep=*/false);
+    if (rc != D2B_OK) return rc;
+    return rpn_sweep_merge_fused(a, seg_count, reinterpret_cast<const u64*>(ws + pl.o_nms), seg_boxes, seg_scores,
+                                 keep, nkeep, img_done, keys2, reinterpret_cast<float4*>(p->out_boxes), p->out_logits,
+                                 p->out_valid, p->out_num_valid, st);
+  }
+  if (!pl.fused_select) {
+    rc = topk_run(pl.td, keys, nullptr, nullptr, kr, ws + pl.o_topk, st);  // rpn_outputs.py:70
+    if (rc != D2B_OK) return rc;
+    rpn_decode_kernel<<<pl.rows, kRpnThreads, 0, st>>>(a, keys, kr, seg_boxes, seg_scores, seg_count, nms_in);
+    D2B_LAUNCH_CHECK();
+  }
   rc = nms_sorted(reinterpret_cast<const float*>(seg_boxes), seg_count, pl.rows, a.k, a.post, p->nms_thresh, keep,
                   nkeep, ws + pl.o_nms, st);  // :90-94
   if (rc != D2B_OK) return rc;

@@ -186,6 +186,36 @@ def test_rpn_proposals(cuda, oracle_lib, variant, pre, post, min_len):
         assert np.array_equal(a.cpu().numpy(), b)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant,pre,post,min_len", [("ties", 200, 150, 0.0), ("clustered", 2000, 1000, 4.0)])
+def test_rpn_proposals_generic_chain(cuda, oracle_lib, monkeypatch, variant, pre, post, min_len):
+    """The generic multi-launch chain (used when pre_nms_topk > 4096) on the same inputs as the cluster-fused path."""
+    monkeypatch.setenv("D2B_RPN_GENERIC", "1")
+    test_rpn_proposals(cuda, oracle_lib, variant, pre, post, min_len)
+
+
+@pytest.mark.gpu
+def test_rpn_proposals_large_k_uses_generic_chain(cuda, oracle_lib):
+    """pre_nms_topk above the fused kernel's 4096-key limit on a row that is longer than that."""
+    rng = np.random.default_rng(5)
+    N, hwa = 2, [9000, 700]
+    props = [np.stack([fuzz_like_boxes(rng, n) for _ in range(N)]) for n in hwa]
+    logits = [(np.round(rng.standard_normal((N, n)) * 16) / 16).astype(np.float32) for n in hwa]
+    shapes = np.array([[300, 400], [280, 390]], np.int32)
+    wb, wl, wv, _ = oracle_lib.find_top_rpn_proposals(props, logits, shapes, 0.7, 6000, 1000, 0.0)
+    res = find_top_rpn_proposals([T(p, cuda) for p in props], [T(x, cuda) for x in logits],
+                                 ImageList(None, T(shapes, cuda)), 0.7, 6000, 1000, 0.0)
+    assert np.array_equal(res.get_field("is_valid").cpu().numpy(), wv)
+    assert np.array_equal(res.boxes.cpu().numpy(), wb)
+    assert np.array_equal(res.get_field("objectness_logits").cpu().numpy(), wl)
+
+
+def fuzz_like_boxes(rng, n):
+    cy, cx = rng.uniform(0, 300, n), rng.uniform(0, 400, n)
+    h, w = rng.uniform(4, 120, n), rng.uniform(4, 120, n)
+    return np.stack([cy - h / 2, cx - w / 2, cy + h / 2, cx + w / 2], 1).astype(np.float32)
+
+
 def test_rpn_full_size_one_image(cuda, oracle_lib):
     """Config 1 shapes: one 800x1333 image, 268,569 anchors, 1000 pre / 1000 post (test-time FPN settings)."""
     anchors = syn.rpn_anchors()
