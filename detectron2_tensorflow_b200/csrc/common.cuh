@@ -42,6 +42,20 @@ void count_launch();  // every kernel launch of the library bumps d2b_kernel_lau
     }                                                                                    \
   } while (0)
 
+// -DD2B_PROFILE: phase timestamps (%globaltimer, ns) of selected CTAs in a device array read back by
+// d2b_debug_read_profile() (tools/phase_probe.py).  Compiled out of the product build.
+#ifdef D2B_PROFILE
+static __device__ unsigned long long g_d2b_prof[256];  // one copy per translation unit (no -rdc)
+__device__ __forceinline__ void d2b_prof_stamp(int slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  g_d2b_prof[slot] = t;
+}
+#define D2B_PROF(cond, slot) do { if (cond) ::d2b::d2b_prof_stamp(slot); } while (0)
+#else
+#define D2B_PROF(cond, slot) do { } while (0)
+#endif
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Bump allocator over the caller's workspace (256-byte aligned slices).

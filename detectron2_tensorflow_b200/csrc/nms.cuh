@@ -38,6 +38,11 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
     u64 acc = 0;
     int kept_before = 0;
     bool capped = false;
+    // the diagonal tile of this block (independent of everything before it): in flight during the wait below
+    const int rows = min(64, cnt - word * 64);
+    u64 dA = 0, dB = 0;
+    if (lane < rows) dA = __ldcg(m + (size_t)(word * 64 + lane) * W + word);
+    if (lane + 32 < rows) dB = __ldcg(m + (size_t)(word * 64 + 32 + lane) * W + word);
     u64 pa[kAhead], pb[kAhead];
 #pragma unroll
     for (int u = 0; u < kAhead; ++u) {
@@ -58,7 +63,12 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
             pa[u] = __ldcg(m + (size_t)(nx * 64 + lane) * W + word);
             pb[u] = __ldcg(m + (size_t)(nx * 64 + 32 + lane) * W + word);
           }
-          while (s_flag[b] == 0) { }
+          // only the owner of the next block polls back to back; warps further from their turn sleep in between, so
+          // that the polling does not take issue slots and shared-memory bandwidth from the warp on the critical path
+          while (s_flag[b] == 0) {
+            const int dist = word - b;
+            if (dist > 1) __nanosleep(dist > 8 ? 400 : 50 * dist);
+          }
           const u64 K = s_keep[b];
           acc |= ((K & bitA) ? va : 0ull) | ((K & bitB) ? vb : 0ull);
           kept_before += __popcll(K);
@@ -68,12 +78,8 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
     }
     u64 K = 0;
     if (!capped) {
-      const int rows = min(64, cnt - word * 64);
       u64 rem = warp_or64(acc);
       if (rows < 64) rem |= ~0ull << rows;
-      u64 dA = 0, dB = 0;
-      if (lane < rows) dA = __ldcg(m + (size_t)(word * 64 + lane) * W + word);
-      if (lane + 32 < rows) dB = __ldcg(m + (size_t)(word * 64 + 32 + lane) * W + word);
       u64 U = ~rem;
       while (U) {  // warp-uniform
         const u64 blocked = warp_or64(((U & bitA) ? dA : 0ull) | ((U & bitB) ? dB : 0ull));
@@ -96,6 +102,7 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
       s_keep[word] = K;
       __threadfence_block();
       s_flag[word] = 1;
+      D2B_PROF(blockIdx.x == 0 && word < 64, 32 + word);
     }
   }
   __syncthreads();

@@ -68,7 +68,7 @@ struct RpnPlan {
   int rows;
   size_t bytes;
   // offsets
-  size_t o_topk, o_keys, o_kr, o_boxes, o_scores, o_count, o_keep, o_nkeep, o_nms, o_keys2, o_done;
+  size_t o_topk, o_keys, o_kr, o_boxes, o_scores, o_count, o_keep, o_nkeep, o_nms, o_keys2;
   bool fused_select;  // k small enough for the cluster-fused select / sort / decode kernel (rpn_fused.cu)
   bool fused_sweep;   // ... and the NMS is the bitmask formulation: column sweep fused with the per-image merge
 };
@@ -132,12 +132,12 @@ int rpn_plan(const d2b_rpn_proposals_params* p, RpnPlan& pl) {
   pl.o_nkeep = o; o += ws_slice(rows * sizeof(int32_t));
   pl.o_nms = o; o += nms_sorted_workspace_bytes(pl.rows, a.k, a.post);
   pl.o_keys2 = o; o += ws_slice(N * a.P2 * sizeof(uint32_t));
-  pl.o_done = o; o += ws_slice(N * sizeof(int32_t));
   pl.bytes = o;
   // D2B_RPN_GENERIC=1 forces the generic multi-launch chain (tests exercise both paths on the same inputs)
   const char* force_generic = getenv("D2B_RPN_GENERIC");
   pl.fused_select = a.k <= kRpnFusedMaxK && !(force_generic && force_generic[0] == '1');
-  pl.fused_sweep = pl.fused_select && nms_uses_bitmask(a.k, a.post);
+  pl.fused_sweep = pl.fused_select && nms_uses_bitmask(a.k, a.post) &&
+                   (size_t)a.L * (a.post < a.k ? a.post : a.k) * sizeof(uint32_t) <= 200 * 1024;
   return D2B_OK;
 }
 
@@ -507,10 +507,9 @@ extern "C" int d2b_rpn_proposals(const d2b_rpn_proposals_params* p, void* worksp
   u64* nms_in = reinterpret_cast<u64*>(p->out_nms_boxes_in);
   if (nms_in) D2B_CUDA(cudaMemsetAsync(nms_in, 0, sizeof(u64), st));
 
-  int32_t* img_done = reinterpret_cast<int32_t*>(ws + pl.o_done);
   if (pl.fused_select) {
     // ONE cluster launch: top-k select, sort, decode, clip, prune of every (image, level) row (:67-87)
-    rc = rpn_select_fused(a, seg_boxes, seg_scores, seg_count, img_done, nms_in, st);
+    rc = rpn_select_fused(a, seg_boxes, seg_scores, seg_count, nms_in, st);
     if (rc != D2B_OK) return rc;
   }
   if (pl.fused_sweep) {
@@ -519,8 +518,8 @@ extern "C" int d2b_rpn_proposals(const d2b_rpn_proposals_params* p, void* worksp
                     nkeep, ws + pl.o_nms, st, /*sweep=*/false);
     if (rc != D2B_OK) return rc;
     return rpn_sweep_merge_fused(a, seg_count, reinterpret_cast<const u64*>(ws + pl.o_nms), seg_boxes, seg_scores,
-                                 keep, nkeep, img_done, keys2, reinterpret_cast<float4*>(p->out_boxes), p->out_logits,
-                                 p->out_valid, p->out_num_valid, st);
+                                 keep, reinterpret_cast<float4*>(p->out_boxes), p->out_logits, p->out_valid,
+                                 p->out_num_valid, st);
   }
   if (!pl.fused_select) {
     rc = topk_run(pl.td, keys, nullptr, nullptr, kr, ws + pl.o_topk, st);  // rpn_outputs.py:70

@@ -89,6 +89,7 @@ __device__ __forceinline__ void rpn_merge_rank_body(
     s_off[a.L] = acc;
   }
   __syncthreads();
+  D2B_PROF(threadIdx.x == 0, 20);
   const int total = s_off[a.L];
   const int kk = min(total, a.post);  // :105
   uint32_t* gk = use_smem ? s_keys : gkeys + (size_t)n * a.P2;
@@ -123,6 +124,7 @@ __device__ __forceinline__ void rpn_merge_rank_body(
       if (ci < total) gk[ci] = float_to_key(sc[u]);
     }
     __syncthreads();  // (total <= kPer * kMergeThreads in practice: one sweep; keys of this sweep visible)
+    D2B_PROF(threadIdx.x == 0, 21);
     if (base + kPer * kMergeThreads < total) continue;  // multi-sweep: ranks are computed in the second loop
 #pragma unroll
     for (int u = 0; u < kPer; ++u) {
@@ -151,6 +153,7 @@ __device__ __forceinline__ void rpn_merge_rank_body(
       }
     }
   }
+  D2B_PROF(threadIdx.x == 0, 22);
   if (total > kPer * kMergeThreads) {
     // rare: more survivors than one sweep holds (L * min(post, k) > 8192): straightforward second pass
     __syncthreads();
@@ -192,15 +195,15 @@ __device__ __forceinline__ void rpn_merge_rank_body(
 
 
 // ---------------------------------------------------------------- fused proposal stage (rpn_fused.cu)
-// k <= kRpnFusedMaxK: ONE cluster launch does top-k select + sort + decode + clip + prune for every (image, level)
-// row (seg_boxes / seg_scores [rows, a.k], seg_count [rows]) and zeroes img_done [N] for the sweep+merge kernel.
+// k <= kRpnFusedMaxK: ONE cluster launch (8 CTAs per row) does top-k select + sort + decode + clip + prune for every
+// (image, level) row: seg_boxes / seg_scores [rows, a.k], seg_count [rows] ...
 constexpr int kRpnFusedMaxK = 4096;
-int rpn_select_fused(const RpnArgs& a, float4* seg_boxes, float* seg_scores, int32_t* seg_count, int32_t* img_done,
+int rpn_select_fused(const RpnArgs& a, float4* seg_boxes, float* seg_scores, int32_t* seg_count,
                      unsigned long long* nms_in_total, cudaStream_t st);
-// ... and ONE launch sweeps every segment's suppression mask and merges each image's levels (top `post`, padded).
+// ... and ONE cluster launch (one cluster per image, one CTA per level) sweeps every segment's suppression mask and
+// merges each image's levels (top `post`, zero padded).  keep [rows, post] is scratch.
 int rpn_sweep_merge_fused(const RpnArgs& a, const int32_t* seg_count, const unsigned long long* mask,
-                          const float4* seg_boxes, const float* seg_scores, int32_t* keep, int32_t* num_keep,
-                          int32_t* img_done, uint32_t* gkeys, float4* out_boxes, float* out_logits, uint8_t* out_valid,
-                          int32_t* out_num, cudaStream_t st);
+                          const float4* seg_boxes, const float* seg_scores, int32_t* keep, float4* out_boxes,
+                          float* out_logits, uint8_t* out_valid, int32_t* out_num, cudaStream_t st);
 
 }  // namespace d2b

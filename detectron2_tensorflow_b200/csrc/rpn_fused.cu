@@ -31,21 +31,41 @@ namespace {
 constexpr int kSelThreads = 512;
 constexpr int kSelCluster = 8;
 constexpr int kSelWarps = kSelThreads / 32;
-constexpr int kHistCopies = 8;  // two warps share one copy of the 256 bins
+constexpr int kHistCopies = 8;   // two warps share one copy of the 256 bins
+constexpr int kHistStride = 260;  // 256 bins + [256] = "raw list overflowed" flag; two buffers (pass parity)
+constexpr int kCandCap = 256;     // boundary buckets up to this size are resolved by ranking their elements
 
 struct SelCtl {
-  unsigned digit, need, bucket;  // result of one pass (identical in every CTA of the cluster)
-  unsigned local_cnt;            // winners in this CTA's local list
-  unsigned tie_cnt;              // elements equal to the k-th value in this CTA's chunk
-  unsigned total;                // leader only: slots handed out in the final list
-  unsigned base;                 // this CTA's range in the leader's list
-  unsigned ties[kSelCluster];    // tie counts of every CTA (written remotely)
+  unsigned digit, need, bucket, overflow;  // result of one pass (identical in every CTA of the cluster)
+  unsigned raw_cnt;                // fast path: entries of the raw list (top byte >= boundary byte of pass 0)
+  unsigned local_cnt;              // entries of this CTA's final list
+  unsigned my_cand;                // fast path: candidates of this CTA written so far
+  unsigned tie_cnt;                // elements equal to the k-th value in this CTA's chunk
+  unsigned cand_cnt[kSelCluster];  // candidates (boundary-bucket elements) per CTA
+  unsigned cnt[kSelCluster];       // winners per CTA (written by the owners through DSMEM)
+  unsigned sel_cnt[kSelCluster];   // candidates selected per CTA (computed redundantly by every CTA)
+  unsigned ties[kSelCluster];      // tie counts of every CTA (written remotely)
 };
 
-// Dynamic shared memory: [hist 256][whist kHistCopies*256][scan 16][ctl][local P u64][final P u64]
+// Dynamic shared memory: [hist 2*260][whist kHistCopies*256][scan 32][ctl 256 B][cand 256 u64][raw P u64][tmp P u64]
+constexpr size_t kSelOffWhist = 2 * kHistStride * 4;
+constexpr size_t kSelOffScan = kSelOffWhist + kHistCopies * 256 * 4;
+constexpr size_t kSelOffCtl = kSelOffScan + 32 * 4;
+constexpr size_t kSelOffCand = kSelOffCtl + 256;
+constexpr size_t kSelOffRaw = kSelOffCand + kCandCap * 8;
+static_assert(kSelOffCtl % 8 == 0 && kSelOffCand % 8 == 0 && kSelOffRaw % 16 == 0, "shared-memory layout alignment");
+
 __device__ __forceinline__ unsigned key_of(float v) { return float_to_key(v); }
 
-// Calls f(value, index) for the elements of [beg, end) of row x; 16-byte loads when aligned, 4 vectors in flight.
+__device__ __forceinline__ float4 ldg_nc_v4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+// Calls f(value, index, valid) for the elements of [beg, end) of row x with warp-uniform control flow.  16-byte loads
+// when aligned; the kV loads of a trip are issued together (volatile loads + a compiler barrier: without it the
+// compiler sinks each load next to its conditional use and the trip pays kV dependent L2 round trips).
 template <typename F>
 __device__ __forceinline__ void scan_chunk(const float* __restrict__ x, long long beg, long long end, F f) {
   if (end <= beg) return;
@@ -59,8 +79,9 @@ __device__ __forceinline__ void scan_chunk(const float* __restrict__ x, long lon
 #pragma unroll
       for (int u = 0; u < kV; ++u) {
         const long long vi = v0 + (long long)u * kSelThreads + threadIdx.x;
-        q[u] = vi < nvec ? __ldg(xv + vi) : make_float4(0, 0, 0, 0);
+        q[u] = ldg_nc_v4(xv + (vi < nvec ? vi : 0));  // clamped: always a valid address
       }
+      asm volatile("" ::: "memory");
 #pragma unroll
       for (int u = 0; u < kV; ++u) {
         const long long vi = v0 + (long long)u * kSelThreads + threadIdx.x;
@@ -76,10 +97,20 @@ __device__ __forceinline__ void scan_chunk(const float* __restrict__ x, long lon
       f(ok ? __ldg(x + i) : 0.0f, i, ok);
     }
   } else {
-    for (long long i0 = beg; i0 < end; i0 += kSelThreads) {
-      const long long i = i0 + threadIdx.x;
-      const bool ok = i < end;
-      f(ok ? __ldg(x + i) : 0.0f, i, ok);
+    constexpr int kS = 8;
+    for (long long i0 = beg; i0 < end; i0 += (long long)kS * kSelThreads) {
+      float q[kS];
+#pragma unroll
+      for (int u = 0; u < kS; ++u) {
+        const long long i = i0 + (long long)u * kSelThreads + threadIdx.x;
+        q[u] = __ldg(x + (i < end ? i : beg));
+      }
+      asm volatile("" ::: "memory");
+#pragma unroll
+      for (int u = 0; u < kS; ++u) {
+        const long long i = i0 + (long long)u * kSelThreads + threadIdx.x;
+        f(q[u], i, i < end);
+      }
     }
   }
 }
@@ -108,15 +139,15 @@ __device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* s_w, u
 }
 
 __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, float4* seg_boxes, float* seg_scores,
-                                                                  int32_t* seg_count, int32_t* img_done,
-                                                                  u64* nms_in_total) {
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  unsigned* hist = reinterpret_cast<unsigned*>(s_raw);            // [256] merged histogram of this CTA (peers read it)
-  unsigned* whist = hist + 256;                                    // [kHistCopies][256]
-  unsigned* s_scan = whist + kHistCopies * 256;                    // [32]
-  SelCtl* ctl = reinterpret_cast<SelCtl*>(s_scan + 32);
-  u64* s_local = reinterpret_cast<u64*>(s_raw + 256 * 4 + kHistCopies * 256 * 4 + 32 * 4 + 128);  // [P]
-  u64* s_final = s_local + a.P;                                                                    // [P]
+                                                                  int32_t* seg_count, u64* nms_in_total) {
+  extern __shared__ __align__(16) unsigned char s_raw_bytes[];
+  unsigned* hist = reinterpret_cast<unsigned*>(s_raw_bytes);                         // [2][kHistStride], peers read it
+  unsigned* whist = reinterpret_cast<unsigned*>(s_raw_bytes + kSelOffWhist);         // [kHistCopies][256]
+  unsigned* s_scan = reinterpret_cast<unsigned*>(s_raw_bytes + kSelOffScan);         // [32]
+  SelCtl* ctl = reinterpret_cast<SelCtl*>(s_raw_bytes + kSelOffCtl);
+  u64* s_cand = reinterpret_cast<u64*>(s_raw_bytes + kSelOffCand);                   // [kCandCap] all CTAs' candidates
+  u64* s_raw = reinterpret_cast<u64*>(s_raw_bytes + kSelOffRaw);                     // [P] raw list, later all sorted runs
+  u64* s_tmp = s_raw + a.P;                                                          // [P] this CTA's final list / run
 
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
@@ -127,195 +158,336 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
   const long long len = a.hwa[l];
   const float* x = a.logits[l] + (size_t)n * len;
   const unsigned kr = (unsigned)(len < (long long)a.k ? len : (long long)a.k);
+  const unsigned P = (unsigned)a.P;
+  const bool prof = (blockIdx.x == 0 && tid == 0);
+  D2B_PROF(prof, 0);
 
-  if (tid == 0) {
-    ctl->local_cnt = 0; ctl->tie_cnt = 0; ctl->total = 0; ctl->base = 0;
-    if (rank == 0 && l == 0 && img_done) img_done[n] = 0;
-  }
-  cluster.sync();  // every CTA of the cluster runs and has initialised its control block
-  if (kr == 0) {
+  if (tid < (int)(sizeof(SelCtl) / 4)) reinterpret_cast<unsigned*>(ctl)[tid] = 0u;
+  if (kr == 0) {  // uniform over the cluster: nobody touches a peer
     if (rank == 0 && tid == 0) seg_count[row] = 0;
     return;
   }
+  __syncthreads();
   // contiguous chunk of the row, multiple of 4 elements so that 16-byte loads stay aligned
   long long per = (len + kSelCluster - 1) / kSelCluster;
   per = (per + 3) & ~3ll;
   const long long beg = per * rank < len ? per * rank : len;
   const long long end = beg + per < len ? beg + per : len;
 
-  // ------------------------------------------------------------------ select
-  unsigned prefix = 0;      // resolved high bits of the k-th largest key
-  unsigned k_rem = kr;      // winners still to be found inside the prefix bucket
-  bool all = (kr == (unsigned)len);
-  bool ties = false;        // k-th value tied: only `k_rem` of the elements equal to `prefix` are taken
-  unsigned cut = 0;         // take key > cut (plus the tie quota)
+  // One radix pass over the cluster: this CTA's warp-private counts -> hist[pass & 1] -> cluster barrier -> every
+  // CTA sums the 8 histograms through DSMEM (thread t owns bin 255 - t) and scans from the top bin down.
+  // hist is double-buffered by pass parity: a CTA overwrites buffer b two barriers after its peers read it.
+  unsigned prefix = 0;  // resolved high bits of the k-th largest key
+  unsigned k_rem = kr;  // winners still to be found inside the prefix bucket
+  unsigned bucket = 0, any_overflow = 0;
+  auto exchange = [&](int pass, unsigned my_overflow) {
+    unsigned* hb = hist + (pass & 1) * kHistStride;
+    if (tid < 256) {
+      unsigned v = 0;
+#pragma unroll
+      for (int c = 0; c < kHistCopies; ++c) v += whist[c * 256 + tid];
+      hb[tid] = v;
+    }
+    if (tid == 256) hb[256] = my_overflow;
+    cluster.sync();  // the 8 per-CTA histograms are visible cluster-wide
+    D2B_PROF(prof, 64 + pass * 8 + 3);
+    unsigned tot = 0, ovf = 0;
+    if (tid < 256) {
+#pragma unroll
+      for (unsigned r = 0; r < kSelCluster; ++r) tot += cluster.map_shared_rank(hb, r)[255 - tid];
+    } else if (tid < 256 + kSelCluster) {
+      ovf = cluster.map_shared_rank(hb, tid - 256)[256];
+    }
+    if (ovf) ctl->overflow = 1u;
+    unsigned total;
+    const unsigned excl = block_excl_scan(tot, s_scan, total);
+    if (tid < 256 && excl < k_rem && k_rem <= excl + tot) {
+      ctl->digit = 255u - (unsigned)tid;
+      ctl->need = k_rem - excl;
+      ctl->bucket = tot;
+    }
+    __syncthreads();
+    const unsigned digit = ctl->digit;
+    if (tid < kSelCluster) ctl->cand_cnt[tid] = cluster.map_shared_rank(hb, tid)[digit];  // per-CTA boundary counts
+    prefix = (prefix << 8) | digit;
+    k_rem = ctl->need;
+    bucket = ctl->bucket;
+    any_overflow = ctl->overflow;
+    __syncthreads();  // ctl fields are rewritten by the next pass
+    D2B_PROF(prof, 1 + pass);
+  };
+  auto zero_whist = [&]() {
+    for (int i = tid; i < kHistCopies * 256; i += kSelThreads) whist[i] = 0;
+    __syncthreads();
+  };
+  auto append_to = [&](u64* list, unsigned* counter, u64 c, bool take) -> bool {  // warp-uniform call; false = overflow
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    bool fits = true;
+    if (m) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(counter, (unsigned)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (take) {
+        const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
+        if (slot < P) list[slot] = c; else fits = false;
+      }
+    }
+    return fits;
+  };
+  unsigned* my = whist + (warp >> 1) * 256;
+
+  bool all = (kr == (unsigned)len);  // the whole row is taken (e.g. P6: 819 anchors < k)
+  if (all) cluster.sync();  // no radix pass follows: peers must be running (and initialised) before the first DSMEM store
+  bool have_lists = false;           // s_tmp / ctl->cnt[] hold the final per-CTA lists
+  bool ties = false;                 // k-th value tied: only `k_rem` of the elements equal to `prefix` are taken
+  bool resolved = all;
+  unsigned cut = 0;                  // generic collect: take key > cut (plus the tie quota)
+  int next_pass = 0;
+
   if (!all) {
-    bool resolved = false;
-    int pass = 0;
-    for (; pass < 4; ++pass) {
-      const int shift = 24 - 8 * pass;
-      for (int i = tid; i < kHistCopies * 256; i += kSelThreads) whist[i] = 0;
+    // ---------------------------------------------------------------- pass 0: top byte (the one HBM read of the row)
+    zero_whist();
+    scan_chunk(x, beg, end, [&](float v, long long, bool ok) {
+      if (ok) atomicAdd(my + (key_of(v) >> 24), 1u);
+    });
+    __syncthreads();
+    D2B_PROF(prof, 64 + 1);
+    exchange(0, 0u);
+    next_pass = 1;
+    if (bucket == k_rem) {  // boundary bucket taken whole: every key >= prefix << 24 wins
+      const unsigned thr = prefix << 24;
+      if (thr == 0u) all = true; else cut = thr - 1u;
+      resolved = true;
+    }
+  }
+  if (!resolved) {
+    // ---------------------------------------------------------------- pass 1 (L2 read): second byte of the boundary
+    // bucket, and every element whose top byte is >= the boundary byte goes to the raw list (composite keys).
+    const unsigned d0 = prefix;
+    zero_whist();
+    bool fits = true;
+    scan_chunk(x, beg, end, [&](float v, long long i, bool ok) {
+      const unsigned key = key_of(v);
+      const unsigned top = key >> 24;
+      fits &= append_to(s_raw, &ctl->raw_cnt, ((u64)key << 32) | (u64)(0xffffffffu - (unsigned)i), ok && top >= d0);
+      if (ok && top == d0) atomicAdd(my + ((key >> 16) & 255u), 1u);
+    });
+    const unsigned my_overflow = __syncthreads_or(fits ? 0 : 1) ? 1u : 0u;
+    D2B_PROF(prof, 64 + 8 + 1);
+    exchange(1, my_overflow);
+    next_pass = 2;
+    const bool whole = (bucket == k_rem);
+    if (!any_overflow && (whole || bucket <= (unsigned)kCandCap)) {
+      // ---- fast finish: winners = raw entries above the 16-bit boundary; the boundary bucket's elements
+      // (candidates) are sent to every CTA and ranked there (composites are unique: ties fall to the lower index)
+      unsigned cbase = 0;
+      for (unsigned r = 0; r < rank; ++r) cbase += ctl->cand_cnt[r];
+      const unsigned nraw = min(ctl->raw_cnt, P);
+      for (unsigned i0 = 0; i0 < nraw; i0 += kSelThreads) {  // block-uniform trip count
+        const unsigned i = i0 + tid;
+        const u64 c = i < nraw ? s_raw[i] : 0ull;
+        const unsigned t16 = (unsigned)(c >> 48);
+        const bool win = i < nraw && (t16 > prefix || (whole && t16 == prefix));
+        const bool cand = i < nraw && !whole && t16 == prefix;
+        append_to(s_tmp, &ctl->local_cnt, c, win);
+        if (cand) {
+          const unsigned j = cbase + atomicAdd(&ctl->my_cand, 1u);
+#pragma unroll
+          for (unsigned r = 0; r < kSelCluster; ++r) cluster.map_shared_rank(s_cand, r)[j] = c;
+        }
+      }
       __syncthreads();
-      unsigned* my = whist + (warp >> 1) * 256;
-      if (pass == 0) {
-        scan_chunk(x, beg, end, [&](float v, long long, bool ok) {
-          if (ok) atomicAdd(my + (key_of(v) >> 24), 1u);
-        });
-      } else {
+      if (tid < kSelCluster) cluster.map_shared_rank(ctl, tid)->cnt[rank] = ctl->local_cnt;
+      cluster.sync();  // every CTA holds all candidates and every CTA's winner count
+      if (!whole) {
+        const unsigned T = bucket;
+        if (tid < (int)T) {
+          const u64 mine = s_cand[tid];
+          unsigned r = 0;
+          for (unsigned j = 0; j < T; ++j) r += (s_cand[j] > mine) ? 1u : 0u;
+          if (r < k_rem) {  // selected: one of the k_rem largest candidates
+            unsigned q = 0, b = 0;
+            while (q + 1 < kSelCluster && tid >= (int)(b + ctl->cand_cnt[q])) { b += ctl->cand_cnt[q]; ++q; }
+            atomicAdd(&ctl->sel_cnt[q], 1u);
+            if (q == rank) s_tmp[atomicAdd(&ctl->local_cnt, 1u)] = mine;
+          }
+        }
+        __syncthreads();
+        if (tid < kSelCluster) ctl->cnt[tid] += ctl->sel_cnt[tid];
+        __syncthreads();
+      }
+      have_lists = true;
+    } else if (whole) {
+      const unsigned thr = prefix << 16;
+      cut = thr - 1u;  // prefix != 0 here: a zero top byte would have been "taken whole" only with thr == 0 in pass 0
+      if (thr == 0u) all = true;
+      resolved = true;
+    }
+  }
+  if (!have_lists) {
+    // ------------------------------------------------------------------ generic path (huge boundary buckets, i.e.
+    // massively tied values, or a raw list that overflowed): remaining radix passes over the row, then a collect
+    // scan; exact ties are split by index order through per-CTA quotas.
+    if (!resolved) {
+      for (int pass = next_pass; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
         const int hs = shift + 8;
+        zero_whist();
         scan_chunk(x, beg, end, [&](float v, long long, bool ok) {
           const unsigned key = key_of(v);
           if (ok && (key >> hs) == prefix) atomicAdd(my + ((key >> shift) & 255u), 1u);
         });
+        __syncthreads();
+        exchange(pass, 0u);
+        if (bucket == k_rem) {  // boundary bucket taken whole: every key >= prefix << shift wins
+          const unsigned thr = prefix << shift;
+          if (thr == 0u) all = true; else cut = thr - 1u;
+          resolved = true;
+          break;
+        }
       }
-      __syncthreads();
-      if (pass > 0) cluster.barrier_wait();  // every peer has finished reading `hist` of the previous pass
-      if (tid < 256) {
-        unsigned v = 0;
-#pragma unroll
-        for (int c = 0; c < kHistCopies; ++c) v += whist[c * 256 + tid];
-        hist[tid] = v;
-      }
-      cluster.sync();  // the 8 per-CTA histograms are visible cluster-wide
-      // every CTA sums the peers' histograms (thread t owns bin 255 - t) and scans from the top bin down
-      unsigned tot = 0;
-      if (tid < 256) {
-#pragma unroll
-        for (unsigned r = 0; r < kSelCluster; ++r) tot += cluster.map_shared_rank(hist, r)[255 - tid];
-      }
-      unsigned total;
-      const unsigned excl = block_excl_scan(tot, s_scan, total);
-      if (tid < 256 && excl < k_rem && k_rem <= excl + tot) {
-        ctl->digit = 255u - (unsigned)tid;
-        ctl->need = k_rem - excl;
-        ctl->bucket = tot;
-      }
-      __syncthreads();
-      cluster.barrier_arrive();  // done with the peers' `hist`
-      prefix = (prefix << 8) | ctl->digit;
-      k_rem = ctl->need;
-      const unsigned bucket = ctl->bucket;
-      __syncthreads();  // ctl fields are rewritten by the next pass
-      if (bucket == k_rem) {  // boundary bucket taken whole: every key >= prefix << shift wins
-        const unsigned thr = prefix << shift;
-        if (thr == 0u) all = true; else cut = thr - 1u;
-        resolved = true;
-        break;
+      if (!resolved) {  // all 32 value bits fixed and the bucket holds more than k_rem equal keys
+        ties = true;
+        cut = prefix;
       }
     }
-    cluster.barrier_wait();  // pairs with the last barrier_arrive
-    if (!resolved) {  // all 32 value bits fixed and the bucket holds more than k_rem equal keys
-      ties = true;
-      cut = prefix;
-    }
-  }
-
-  // ------------------------------------------------------------------ collect
-  auto append_local = [&](u64 c, bool take) {  // warp-uniform call
-    const unsigned m = __ballot_sync(0xffffffffu, take);
-    if (m) {
-      unsigned base = 0;
-      if (lane == 0) base = atomicAdd(&ctl->local_cnt, (unsigned)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (take) {
-        const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
-        if (slot < (unsigned)a.P) s_local[slot] = c;
-      }
-    }
-  };
-  auto flush_local = [&]() {  // reserve a range of the leader's list and copy the local winners there
-    __syncthreads();
-    if (tid == 0) {
-      const unsigned c = ctl->local_cnt;
-      ctl->base = c ? atomicAdd(&cluster.map_shared_rank(ctl, 0)->total, c) : 0u;
-    }
-    __syncthreads();
-    const unsigned c = ctl->local_cnt, base = ctl->base;
-    u64* dst = cluster.map_shared_rank(s_final, 0);
-    for (unsigned i = tid; i < c; i += kSelThreads)
-      if (base + i < (unsigned)a.P) dst[base + i] = s_local[i];
-    __syncthreads();
     if (tid == 0) ctl->local_cnt = 0;
     __syncthreads();
-  };
-  unsigned my_ties = 0;
-  scan_chunk(x, beg, end, [&](float v, long long i, bool ok) {
-    const unsigned key = key_of(v);
-    const bool take = ok && (all || key > cut);
-    if (ties) my_ties += (ok && key == cut) ? 1u : 0u;
-    append_local(((u64)key << 32) | (u64)(0xffffffffu - (unsigned)i), take);
-  });
-  flush_local();
-  if (ties) {  // block-uniform (identical in the whole cluster)
-    // per-CTA tie counts -> every CTA's table; chunks are contiguous index ranges in rank order
+    unsigned my_ties = 0;
+    scan_chunk(x, beg, end, [&](float v, long long i, bool ok) {
+      const unsigned key = key_of(v);
+      const bool take = ok && (all || key > cut);
+      if (ties) my_ties += (ok && key == cut) ? 1u : 0u;
+      append_to(s_tmp, &ctl->local_cnt, ((u64)key << 32) | (u64)(0xffffffffu - (unsigned)i), take);
+    });
+    if (ties) {  // block-uniform (identical in the whole cluster)
+      // per-CTA tie counts -> every CTA's table; chunks are contiguous index ranges in rank order
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) my_ties += __shfl_xor_sync(0xffffffffu, my_ties, o);
-    if (lane == 0 && my_ties) atomicAdd(&ctl->tie_cnt, my_ties);
-    __syncthreads();
-    if (tid < kSelCluster) cluster.map_shared_rank(ctl, tid)->ties[rank] = ctl->tie_cnt;
-    cluster.sync();
-    unsigned before = 0;
-    for (unsigned r = 0; r < rank; ++r) before += ctl->ties[r];
-    const unsigned mine = ctl->ties[rank];
-    const unsigned quota = before >= k_rem ? 0u : (k_rem - before < mine ? k_rem - before : mine);
-    if (quota == mine) {  // all of this chunk's ties (possibly none)
-      if (mine)
-        scan_chunk(x, beg, end, [&](float v, long long i, bool ok) {
-          const unsigned key = key_of(v);
-          append_local(((u64)key << 32) | (u64)(0xffffffffu - (unsigned)i), ok && key == cut);
-        });
-    } else if (quota > 0) {
-      // the one CTA with a partial quota: its `quota` lowest-index ties, found by walking the chunk in index order
-      // (thread t owns 4 consecutive elements per trip; an ordered block scan gives every tie its ordinal)
-      unsigned running = 0;
-      for (long long i0 = beg; i0 < end && running < quota; i0 += 4ll * kSelThreads) {
-        const long long i = i0 + 4ll * tid;
-        unsigned keyv[4];
-        unsigned cnt = 0;
+      for (int o = 16; o > 0; o >>= 1) my_ties += __shfl_xor_sync(0xffffffffu, my_ties, o);
+      if (lane == 0 && my_ties) atomicAdd(&ctl->tie_cnt, my_ties);
+      __syncthreads();
+      if (tid < kSelCluster) cluster.map_shared_rank(ctl, tid)->ties[rank] = ctl->tie_cnt;
+      cluster.sync();
+      unsigned before = 0;
+      for (unsigned r = 0; r < rank; ++r) before += ctl->ties[r];
+      const unsigned mine = ctl->ties[rank];
+      const unsigned quota = before >= k_rem ? 0u : (k_rem - before < mine ? k_rem - before : mine);
+      if (quota == mine) {  // all of this chunk's ties (possibly none)
+        if (mine)
+          scan_chunk(x, beg, end, [&](float v, long long i, bool ok) {
+            const unsigned key = key_of(v);
+            append_to(s_tmp, &ctl->local_cnt, ((u64)key << 32) | (u64)(0xffffffffu - (unsigned)i), ok && key == cut);
+          });
+      } else if (quota > 0) {
+        // the one CTA with a partial quota: its `quota` lowest-index ties, found by walking the chunk in index
+        // order (thread t owns 4 consecutive elements per trip; an ordered block scan gives every tie its ordinal)
+        unsigned running = 0;
+        for (long long i0 = beg; i0 < end && running < quota; i0 += 4ll * kSelThreads) {
+          const long long i = i0 + 4ll * tid;
+          unsigned keyv[4];
+          unsigned cnt = 0;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const bool ok = i + c < end;
-          keyv[c] = ok ? key_of(__ldg(x + i + c)) : 0u;
-          if (!ok || keyv[c] != cut) keyv[c] = cut + 1u;  // marks "not a tie" (cut + 1 != cut even on wrap-around)
-          else ++cnt;
-        }
-        unsigned total;
-        unsigned ord = running + block_excl_scan(cnt, s_scan, total);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (keyv[c] == cut) {
-            if (ord < quota) {
-              const unsigned slot = atomicAdd(&ctl->local_cnt, 1u);
-              if (slot < (unsigned)a.P) s_local[slot] = ((u64)cut << 32) | (u64)(0xffffffffu - (unsigned)(i + c));
-            }
-            ++ord;
+          for (int c = 0; c < 4; ++c) {
+            const bool ok = i + c < end;
+            keyv[c] = ok ? key_of(__ldg(x + i + c)) : 0u;
+            if (!ok || keyv[c] != cut) keyv[c] = cut + 1u;  // marks "not a tie" (cut + 1 != cut even on wrap-around)
+            else ++cnt;
           }
+          unsigned total;
+          unsigned ord = running + block_excl_scan(cnt, s_scan, total);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (keyv[c] == cut) {
+              if (ord < quota) {
+                const unsigned slot = atomicAdd(&ctl->local_cnt, 1u);
+                if (slot < P) s_tmp[slot] = ((u64)cut << 32) | (u64)(0xffffffffu - (unsigned)(i + c));
+              }
+              ++ord;
+            }
+          }
+          running += total;
         }
-        running += total;
       }
     }
-    flush_local();
+    __syncthreads();
+    if (tid < kSelCluster) cluster.map_shared_rank(ctl, tid)->cnt[rank] = ctl->local_cnt;
+    cluster.sync();  // every CTA knows every CTA's winner count
   }
-  cluster.sync();  // the leader's list is complete; no CTA touches a peer's shared memory after this point
-  if (rank != 0) return;
+  D2B_PROF(prof, 5);
 
-  // ------------------------------------------------------------------ leader: sort, decode, clip, prune
+  // ------------------------------------------------------------------ merge: every CTA sorts its own winners, the
+  // sorted runs are broadcast to all CTAs, and every CTA ranks, decodes and writes ITS winners (rank = position in
+  // its own run + per other run the number of larger keys: composites are unique).
+  const unsigned c_mine = min(ctl->cnt[rank], P);
+  unsigned base_mine = 0;
+  for (unsigned r = 0; r < rank; ++r) base_mine += ctl->cnt[r];
   int Pe = 1;
-  while (Pe < (int)kr) Pe <<= 1;
-  for (int i = (int)kr + tid; i < Pe; i += kSelThreads) s_final[i] = 0ull;
+  while (Pe < (int)c_mine) Pe <<= 1;
+  for (int i = (int)c_mine + tid; i < Pe; i += kSelThreads) s_tmp[i] = 0ull;
   __syncthreads();
   for (int k = 2; k <= Pe; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int p = tid; p < Pe / 2; p += kSelThreads) {
         const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
         const bool desc = ((i & k) == 0);
-        const u64 va = s_final[i], vb = s_final[i | j];
-        if (desc ? (va < vb) : (va > vb)) { s_final[i] = vb; s_final[i | j] = va; }
+        const u64 va = s_tmp[i], vb = s_tmp[i | j];
+        if (desc ? (va < vb) : (va > vb)) { s_tmp[i] = vb; s_tmp[i | j] = va; }
       }
       __syncthreads();
     }
+  D2B_PROF(prof, 6);
+  for (unsigned i = tid; i < c_mine; i += kSelThreads) {
+    const u64 c = s_tmp[i];
+    if (base_mine + i < P) {
+#pragma unroll
+      for (unsigned r = 0; r < kSelCluster; ++r) cluster.map_shared_rank(s_raw, r)[base_mine + i] = c;
+    }
+  }
+  cluster.sync();  // all runs are in every CTA's s_raw; nobody touches a peer's shared memory after this point
+  D2B_PROF(prof, 7);
   const float h = (float)a.shapes[2 * n], w = (float)a.shapes[2 * n + 1];
   const size_t rbase = (size_t)n * len;
+  for (unsigned i = tid; i < c_mine; i += kSelThreads) {
+    const u64 key = s_tmp[i];
+    unsigned pos = i;
+    unsigned b = 0;
+#pragma unroll
+    for (unsigned r = 0; r < kSelCluster; ++r) {
+      const unsigned c = ctl->cnt[r];
+      if (r != rank) {
+        unsigned lo = 0, hi = min(c, P - min(b, P));
+        const u64* run = s_raw + b;
+        while (lo < hi) {  // keys of run r greater than mine (runs are descending)
+          const unsigned mid = (lo + hi) >> 1;
+          if (run[mid] > key) lo = mid + 1; else hi = mid;
+        }
+        pos += lo;
+      }
+      b += c;
+    }
+    if (pos < kr) {
+      const unsigned idx = key_index(key);
+      const float score = __ldg(a.logits[l] + rbase + idx);
+      float4 box;
+      if (a.proposals[l]) box = __ldg(a.proposals[l] + rbase + idx);
+      else box = d2b_decode(__ldg(a.deltas[l] + rbase + idx), a.anchors[l].at(idx), a.w[0], a.w[1], a.w[2], a.w[3], a.clampv);
+      box = d2b_clip(box, h, w);  // rpn_outputs.py:77-80
+      seg_boxes[(size_t)row * a.k + pos] = box;
+      seg_scores[(size_t)row * a.k + pos] = score;
+    }
+  }
+  if (!(a.min_len > 0.0f)) {
+    if (rank == 0 && tid == 0) {
+      seg_count[row] = (int32_t)kr;
+      if (nms_in_total) atomicAdd(nms_in_total, (u64)kr);
+    }
+    D2B_PROF(prof, 8);
+    return;
+  }
+  // prune_small_boxes (rpn_outputs.py:83-87): ordered compaction of the row, in place, by the leader.  A trip reads
+  // positions [j0, j0 + 512) before anything is written, and writes land at or below the positions read so far.
+  cluster.sync();
+  if (rank != 0) return;
   int* s_warp = reinterpret_cast<int*>(s_scan);
   int base = 0;
   for (int j0 = 0; j0 < (int)kr; j0 += kSelThreads) {
@@ -324,16 +496,10 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
     float4 box = make_float4(0, 0, 0, 0);
     float score = 0.0f;
     if (j < (int)kr) {
-      const unsigned idx = key_index(s_final[j]);
-      score = __ldg(a.logits[l] + rbase + idx);
-      if (a.proposals[l]) box = __ldg(a.proposals[l] + rbase + idx);
-      else box = d2b_decode(__ldg(a.deltas[l] + rbase + idx), a.anchors[l].at(idx), a.w[0], a.w[1], a.w[2], a.w[3], a.clampv);
-      box = d2b_clip(box, h, w);  // rpn_outputs.py:77-80
-      ok = true;
-      if (a.min_len > 0.0f) {     // prune_small_boxes, :83-87
-        const float bh = box.z - box.x, bw = box.w - box.y;
-        ok = (bw >= a.min_len) && (bh >= a.min_len);
-      }
+      box = __ldcg(seg_boxes + (size_t)row * a.k + j);
+      score = __ldcg(seg_scores + (size_t)row * a.k + j);
+      const float bh = box.z - box.x, bw = box.w - box.y;
+      ok = (bw >= a.min_len) && (bh >= a.min_len);
     }
     const int slot = block_compact<kSelThreads>(ok, base, s_warp);
     if (slot >= 0) {
@@ -347,40 +513,92 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
   }
 }
 
-// One CTA per (image, level) segment sweeps its suppression mask (nms.cuh); the CTA that finishes an image's last
-// segment then merges the L survivor lists into the image's top `post` proposals (rpn_outputs.py:101-114,
-// rpn_merge_rank_body).  img_done [N] was zeroed by rpn_select_kernel.
+// One CTA per (image, level) segment, one CLUSTER per image (cluster size = number of levels <= 8): every CTA sweeps
+// its segment's suppression mask (nms.cuh), then the image's levels are merged into its top `post` proposals
+// (rpn_outputs.py:101-114) by all CTAs of the cluster: each publishes the score keys of its survivors (already in
+// (score desc, index asc) order) in shared memory, copies the other levels' lists through DSMEM, and ranks ITS OWN
+// survivors -- rank = position in its own list + per other level the number of survivors that precede it (binary
+// search; ties across levels go to the earlier level = lower concat index, TF top_k rule) -- and writes them
+// straight to their output slots.  No sort, no intermediate buffers, no last-block hand-off.
 __global__ void __launch_bounds__(kColSweepThreads) rpn_sweep_merge_kernel(
-    RpnArgs a, const int32_t* seg_count, int W, const u64* mask, const float4* seg_boxes, const float* seg_scores,
-    int32_t* keep, int32_t* num_keep, int32_t* img_done, uint32_t* gkeys, int use_smem, float4* out_boxes,
-    float* out_logits, uint8_t* out_valid, int32_t* out_num) {
-  extern __shared__ uint32_t s_merge_keys[];
-  __shared__ int s_last;
+    RpnArgs a, const int32_t* seg_count, int W, int cap, const u64* mask, const float4* seg_boxes,
+    const float* seg_scores, int32_t* keep, float4* out_boxes, float* out_logits, uint8_t* out_valid, int32_t* out_num) {
+  extern __shared__ uint32_t s_keys[];  // [L][cap]: score keys of every level's survivors (own slice written first)
+  __shared__ int s_cnt;
+  __shared__ int s_off[D2B_MAX_LEVELS + 1];
+  cg::cluster_group cluster = cg::this_cluster();
   const int seg = blockIdx.x;
-  const int n = seg / a.L;
+  const int n = seg / a.L, l = seg - n * a.L;
+  const int tid = threadIdx.x;
   const int cnt = min(seg_count[seg], a.k);
-  const int kept = nms_sweep_columns(cnt, W, a.post, mask + (size_t)seg * W * 64 * W, keep + (size_t)seg * a.post);
-  if (threadIdx.x == 0) {
-    num_keep[seg] = kept;
-    __threadfence();  // this segment's keep list and count are visible before the arrival is
-    s_last = (atomicAdd(img_done + n, 1) == a.L - 1);
+  int32_t* kp = keep + (size_t)seg * a.post;
+  D2B_PROF(blockIdx.x == 0 && tid == 0, 16);
+  const int kept = nms_sweep_columns(cnt, W, a.post, mask + (size_t)seg * W * 64 * W, kp);
+  D2B_PROF(blockIdx.x == 0 && tid == 0, 17);
+  // my survivors' keys (kp was written by this CTA: visible after the barrier inside nms_sweep_columns)
+  uint32_t* mine = s_keys + (size_t)l * cap;
+  const float* sc = seg_scores + (size_t)seg * a.k;
+  for (int j = tid; j < kept; j += kColSweepThreads) mine[j] = float_to_key(sc[kp[j]]);
+  if (tid == 0) s_cnt = kept;
+  cluster.sync();
+  if (tid < a.L) s_off[tid + 1] = *cluster.map_shared_rank(&s_cnt, tid);
+  if (tid == 0) s_off[0] = 0;
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < a.L; ++i) s_off[i + 1] += s_off[i];
   }
   __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  rpn_merge_rank_body(a, n, seg_boxes, seg_scores, keep, num_keep, gkeys, s_merge_keys, use_smem, out_boxes,
-                      out_logits, out_valid, out_num);
+  for (int l2 = 0; l2 < a.L; ++l2) {  // copy the other levels' key lists (DSMEM reads, coalesced)
+    if (l2 == l) continue;
+    const int c2 = s_off[l2 + 1] - s_off[l2];
+    const uint32_t* src = cluster.map_shared_rank(s_keys + (size_t)l2 * cap, l2);
+    uint32_t* dst = s_keys + (size_t)l2 * cap;
+    for (int j = tid; j < c2; j += kColSweepThreads) dst[j] = src[j];
+  }
+  cluster.sync();  // copies done: from here on every CTA works on its own shared memory only
+  D2B_PROF(blockIdx.x == 0 && tid == 0, 20);
+  const int total = s_off[a.L];
+  const int kk = min(total, a.post);  // :105
+  for (int j = tid; j < kept; j += kColSweepThreads) {
+    const uint32_t key = mine[j];
+    int rank = j;
+    for (int l2 = 0; l2 < a.L; ++l2) {
+      if (l2 == l) continue;
+      const uint32_t* kl = s_keys + (size_t)l2 * cap;
+      int lo = 0, hi = s_off[l2 + 1] - s_off[l2];
+      while (lo < hi) {  // first position whose element does NOT precede (key, level l)
+        const int mid = (lo + hi) >> 1;
+        const uint32_t ke = kl[mid];
+        const bool before = (l2 < l) ? (ke >= key) : (ke > key);
+        if (before) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < a.post) {
+      const int p = kp[j];
+      const size_t o = (size_t)n * a.post + rank;
+      out_boxes[o] = seg_boxes[(size_t)seg * a.k + p];
+      out_logits[o] = sc[p];
+      out_valid[o] = 1;
+    }
+  }
+  for (int j = kk + l * kColSweepThreads + tid; j < a.post; j += a.L * kColSweepThreads) {  // zero padding :111-114
+    const size_t o = (size_t)n * a.post + j;
+    out_boxes[o] = make_float4(0, 0, 0, 0);
+    out_logits[o] = 0.0f;
+    out_valid[o] = 0;
+  }
+  if (l == 0 && tid == 0 && out_num) out_num[n] = kk;
+  D2B_PROF(blockIdx.x == 0 && tid == 0, 18);
 }
 
-size_t select_smem_bytes(int P) {
-  return 256 * 4 + kHistCopies * 256 * 4 + 32 * 4 + 128 + 2 * (size_t)P * sizeof(u64);
-}
+size_t select_smem_bytes(int P) { return kSelOffRaw + 2 * (size_t)P * sizeof(u64); }
 
 }  // namespace
 
-int rpn_select_fused(const RpnArgs& a, float4* seg_boxes, float* seg_scores, int32_t* seg_count, int32_t* img_done,
+int rpn_select_fused(const RpnArgs& a, float4* seg_boxes, float* seg_scores, int32_t* seg_count,
                      unsigned long long* nms_in_total, cudaStream_t st) {
-  static_assert(sizeof(SelCtl) <= 128, "control block must fit its slot");
+  static_assert(sizeof(SelCtl) <= 256, "control block must fit its slot");
   D2B_REQUIRE(a.k <= kRpnFusedMaxK, "fused proposal stage: k=%d > %d", a.k, kRpnFusedMaxK);
   const int rows = a.L * a.N;
   if (rows == 0) return D2B_OK;
@@ -399,29 +617,47 @@ int rpn_select_fused(const RpnArgs& a, float4* seg_boxes, float* seg_scores, int
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  D2B_CUDA(cudaLaunchKernelEx(&cfg, rpn_select_kernel, a, seg_boxes, seg_scores, seg_count, img_done,
+  D2B_CUDA(cudaLaunchKernelEx(&cfg, rpn_select_kernel, a, seg_boxes, seg_scores, seg_count,
                               reinterpret_cast<u64*>(nms_in_total)));
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }
 
 int rpn_sweep_merge_fused(const RpnArgs& a, const int32_t* seg_count, const unsigned long long* mask,
-                          const float4* seg_boxes, const float* seg_scores, int32_t* keep, int32_t* num_keep,
-                          int32_t* img_done, uint32_t* gkeys, float4* out_boxes, float* out_logits, uint8_t* out_valid,
-                          int32_t* out_num, cudaStream_t st) {
+                          const float4* seg_boxes, const float* seg_scores, int32_t* keep, float4* out_boxes,
+                          float* out_logits, uint8_t* out_valid, int32_t* out_num, cudaStream_t st) {
   const int rows = a.L * a.N;
   if (rows == 0) return D2B_OK;
   const int W = (a.k + 63) / 64;
   D2B_REQUIRE(W <= kColSweepMaxW, "fused sweep: k=%d too large", a.k);
-  const size_t merge_smem = (size_t)a.P2 * sizeof(uint32_t);
-  const int in_smem = merge_smem <= 160 * 1024;
-  if (in_smem && merge_smem > 48 * 1024)
-    D2B_CUDA(cudaFuncSetAttribute(rpn_sweep_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem));
-  rpn_sweep_merge_kernel<<<rows, kColSweepThreads, in_smem ? merge_smem : 0, st>>>(
-      a, seg_count, W, mask, seg_boxes, seg_scores, keep, num_keep, img_done, gkeys, in_smem, out_boxes, out_logits,
-      out_valid, out_num);
+  const int cap = a.post < a.k ? a.post : a.k;  // survivors per segment
+  const size_t smem = (size_t)a.L * cap * sizeof(uint32_t);
+  D2B_REQUIRE(smem <= 200 * 1024, "fused sweep: %d levels x %d survivors do not fit shared memory", a.L, cap);
+  if (smem > 48 * 1024)
+    D2B_CUDA(cudaFuncSetAttribute(rpn_sweep_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)rows, 1, 1);
+  cfg.blockDim = dim3(kColSweepThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)a.L;  // one cluster per image (L <= D2B_MAX_LEVELS = 8: portable size)
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  D2B_CUDA(cudaLaunchKernelEx(&cfg, rpn_sweep_merge_kernel, a, seg_count, W, cap, reinterpret_cast<const u64*>(mask),
+                              seg_boxes, seg_scores, keep, out_boxes, out_logits, out_valid, out_num));
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }
 
 }  // namespace d2b
+
+#ifdef D2B_PROFILE
+// Debug builds only (-DD2B_PROFILE): copies the 256 phase timestamps of this translation unit to `out`.
+extern "C" __attribute__((visibility("default"))) int d2b_debug_read_profile(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, d2b::g_d2b_prof, sizeof(unsigned long long) * 256) == cudaSuccess ? 0 : -2;
+}
+#endif

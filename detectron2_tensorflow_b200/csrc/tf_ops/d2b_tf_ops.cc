@@ -1,8 +1,11 @@
 // d2b_tf_ops.cc -- TensorFlow custom-op shim over the C-ABI of libd2b200.so.
 //
-// NOT COMPILED IN THIS REPOSITORY'S BUILD: TensorFlow is not installable in the build image
-// (no wheel, no network).  It is the glue a maintainer of the reference compiles against their
-// own TensorFlow:
+// NOT LINKED IN THIS REPOSITORY'S BUILD: TensorFlow is not installable in the build image (no wheel, no network).
+// What IS checked here: `tests/test_tf_shim_syntax.py` type-checks this file with
+// `g++ -std=c++14 -fsyntax-only` against `tests/tf_stub/` -- minimal declarations of the TF C++ API it uses
+// (OpKernel, OpKernelContext, REGISTER_OP, InferenceContext, Tensor, errors::*) -- so names, argument types,
+// attr getters and the d2b200.h structs are verified; the runtime behaviour of TensorFlow itself is not.
+// It is the glue a maintainer of the reference compiles against their own TensorFlow:
 //   g++ -std=c++14 -shared -fPIC d2b_tf_ops.cc -o libd2b200_tf.so \
 //       $(python -c 'import tensorflow as tf; print(" ".join(tf.sysconfig.get_compile_flags()))') \
 //       -I<repo>/include -L<repo>/detectron2_tensorflow_b200/lib -ld2b200 \
@@ -16,6 +19,10 @@
 
 #define EIGEN_USE_GPU
 #include "tensorflow/core/util/gpu_kernel_helper.h"
+
+#include <cmath>
+#include <string>
+#include <vector>
 
 #include "d2b200.h"
 
@@ -235,10 +242,9 @@ class D2RpnProposalsOp : public tf::OpKernel {
   float thr_, min_len_;
   std::vector<float> w_;
 };
-REGISTER_KERNEL_BUILDER(Name("D2RpnProposals").Device(tf::DEVICE_GPU).HostMemory("image_shapes"), D2RpnProposalsOp);
-// NOTE: image_shapes is read by the kernels, so a production shim either drops HostMemory above or
-// copies the [N,2] array to the workspace first; kept explicit here because TF places small int32
-// tensors on the host by default.
+REGISTER_KERNEL_BUILDER(Name("D2RpnProposals").Device(tf::DEVICE_GPU), D2RpnProposalsOp);
+// image_shapes is read by the kernels, so it is a DEVICE input (no HostMemory): a custom GPU kernel receives
+// every input in device memory unless the registration says otherwise.
 
 // ------------------------------------------------------------------ D2MatrixNms
 // Replaces matrix_nms (lib/layers/nms.py:29-83).
@@ -289,8 +295,233 @@ class D2MatrixNmsOp : public tf::OpKernel {
 };
 REGISTER_KERNEL_BUILDER(Name("D2MatrixNms").Device(tf::DEVICE_GPU), D2MatrixNmsOp);
 
-// D2FastRcnnPostprocess and D2RetinanetPostprocess follow the same pattern over
-// d2b_fast_rcnn_postprocess / d2b_retinanet_postprocess (params structs in d2b200.h).
+// ------------------------------------------------------------------ D2FastRcnnPostprocess
+// Replaces fast_rcnn_inference (lib/modeling/roi_heads/fast_rcnn.py:28-187): clip -> score threshold -> fp32
+// class-offset NMS -> top-k, zero padded.  `indices` / `rmax` are SparseBoxList.indices and dense_shape[1].
+REGISTER_OP("D2FastRcnnPostprocess")
+    .Input("boxes: float")         // [M, Kb*4], Kb = num_classes or 1 (class-agnostic regression)
+    .Input("scores: float")        // [M, K+1], last column = background
+    .Input("indices: int64")       // [M, 2] (image, slot)
+    .Input("image_shapes: int32")  // [N, 2] (h, w)
+    .Attr("rmax: int")
+    .Attr("score_thresh: float = 0.05")
+    .Attr("nms_thresh: float = 0.5")
+    .Attr("topk_per_image: int = 100")
+    .Attr("nms_cls_agnostic: bool = false")
+    .Output("pred_boxes: float")     // [N, topk, 4]
+    .Output("scores_out: float")     // [N, topk]
+    .Output("pred_classes: int64")   // [N, topk]   (fast_rcnn.py:178)
+    .Output("is_valid: bool")        // [N, topk]
+    .Output("kept_roi_index: int32")  // [N, topk] slot of the source ROI, -1 padded (kept_indices, :150-166)
+    .SetShapeFn([](InferenceContext* c) {
+      int topk;
+      TF_RETURN_IF_ERROR(c->GetAttr("topk_per_image", &topk));
+      auto n = c->Dim(c->input(3), 0);
+      c->set_output(0, c->MakeShape({n, topk, 4}));
+      for (int i = 1; i < 5; ++i) c->set_output(i, c->MakeShape({n, topk}));
+      return tf::Status::OK();
+    });
+
+class D2FastRcnnPostprocessOp : public tf::OpKernel {
+ public:
+  explicit D2FastRcnnPostprocessOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("rmax", &rmax_));
+    OP_REQUIRES_OK(c, c->GetAttr("score_thresh", &score_thr_));
+    OP_REQUIRES_OK(c, c->GetAttr("nms_thresh", &nms_thr_));
+    OP_REQUIRES_OK(c, c->GetAttr("topk_per_image", &topk_));
+    OP_REQUIRES_OK(c, c->GetAttr("nms_cls_agnostic", &agnostic_));
+    OP_REQUIRES(c, rmax_ >= 0 && topk_ >= 1, tf::errors::InvalidArgument("rmax must be >= 0 and topk_per_image >= 1"));
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    const tf::Tensor& boxes = ctx->input(0);
+    const tf::Tensor& scores = ctx->input(1);
+    const tf::Tensor& indices = ctx->input(2);
+    const tf::Tensor& shapes = ctx->input(3);
+    OP_REQUIRES(ctx, boxes.dims() == 2 && scores.dims() == 2 && scores.dim_size(1) >= 2 &&
+                         boxes.dim_size(0) == scores.dim_size(0),
+                tf::errors::InvalidArgument("boxes must be [M,Kb*4] and scores [M,K+1]"));
+    OP_REQUIRES(ctx, indices.dims() == 2 && indices.dim_size(1) == 2 && indices.dim_size(0) == boxes.dim_size(0),
+                tf::errors::InvalidArgument("indices must be [M,2]"));
+    OP_REQUIRES(ctx, shapes.dims() == 2 && shapes.dim_size(1) == 2, tf::errors::InvalidArgument("image_shapes must be [N,2]"));
+    const int K = static_cast<int>(scores.dim_size(1)) - 1;
+    OP_REQUIRES(ctx, boxes.dim_size(1) == 4 || boxes.dim_size(1) == 4 * K,
+                tf::errors::InvalidArgument("boxes must have 4 or 4*num_classes columns"));
+    d2b_fast_rcnn_params p = {};
+    p.boxes = boxes.flat<float>().data();
+    p.scores = scores.flat<float>().data();
+    p.indices = reinterpret_cast<const int64_t*>(indices.flat<tf::int64>().data());
+    p.num_preds = boxes.dim_size(0);
+    p.num_images = static_cast<int>(shapes.dim_size(0));
+    p.rmax = rmax_;
+    p.num_bbox_reg_classes = static_cast<int>(boxes.dim_size(1) / 4);
+    p.num_classes = K;
+    p.image_shapes = shapes.flat<tf::int32>().data();
+    p.score_thresh = score_thr_;
+    p.nms_thresh = nms_thr_;
+    p.topk_per_image = topk_;
+    p.nms_cls_agnostic = agnostic_ ? 1 : 0;
+    tf::Tensor *ob = nullptr, *os = nullptr, *oc = nullptr, *ov = nullptr, *oi = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({p.num_images, topk_, 4}), &ob));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({p.num_images, topk_}), &os));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, tf::TensorShape({p.num_images, topk_}), &oc));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(3, tf::TensorShape({p.num_images, topk_}), &ov));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(4, tf::TensorShape({p.num_images, topk_}), &oi));
+    p.out_boxes = ob->flat<float>().data();
+    p.out_scores = os->flat<float>().data();
+    p.out_classes = reinterpret_cast<int64_t*>(oc->flat<tf::int64>().data());
+    p.out_valid = reinterpret_cast<uint8_t*>(ov->flat<bool>().data());
+    p.out_roi_index = oi->flat<tf::int32>().data();
+    RunOp(ctx, p, d2b_fast_rcnn_postprocess_workspace_bytes, d2b_fast_rcnn_postprocess);
+  }
+
+ private:
+  int rmax_, topk_;
+  float score_thr_, nms_thr_;
+  bool agnostic_;
+};
+REGISTER_KERNEL_BUILDER(Name("D2FastRcnnPostprocess").Device(tf::DEVICE_GPU), D2FastRcnnPostprocessOp);
+
+// ------------------------------------------------------------------ D2RetinanetPostprocess
+// Replaces RetinaNetHead.inference (lib/modeling/single_stage_heads/retinanet.py:285-387) for the whole batch:
+// sigmoid -> per-level top-k -> threshold -> decode -> class-offset NMS -> top max_detections, zero padded.
+REGISTER_OP("D2RetinanetPostprocess")
+    .Input("box_cls: L * float")    // L x [N, HWA_l, K] logits
+    .Input("box_delta: L * float")  // L x [N, HWA_l, 4]
+    .Input("anchors: L * float")    // L x [HWA_l, 4]
+    .Attr("L: int >= 1")
+    .Attr("topk_candidates: int = 1000")
+    .Attr("score_thresh: float = 0.05")
+    .Attr("nms_thresh: float = 0.5")
+    .Attr("max_detections: int = 100")
+    .Attr("weights: list(float) = [1.0, 1.0, 1.0, 1.0]")
+    .Output("pred_boxes: float")    // [N, max_detections, 4]
+    .Output("scores: float")        // [N, max_detections]
+    .Output("pred_classes: int32")  // [N, max_detections]   (retinanet.py:381)
+    .Output("is_valid: bool")       // [N, max_detections]
+    .SetShapeFn([](InferenceContext* c) {
+      int d;
+      TF_RETURN_IF_ERROR(c->GetAttr("max_detections", &d));
+      auto n = c->Dim(c->input(0), 0);
+      c->set_output(0, c->MakeShape({n, d, 4}));
+      for (int i = 1; i < 4; ++i) c->set_output(i, c->MakeShape({n, d}));
+      return tf::Status::OK();
+    });
+
+class D2RetinanetPostprocessOp : public tf::OpKernel {
+ public:
+  explicit D2RetinanetPostprocessOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("L", &L_));
+    OP_REQUIRES_OK(c, c->GetAttr("topk_candidates", &topk_));
+    OP_REQUIRES_OK(c, c->GetAttr("score_thresh", &score_thr_));
+    OP_REQUIRES_OK(c, c->GetAttr("nms_thresh", &nms_thr_));
+    OP_REQUIRES_OK(c, c->GetAttr("max_detections", &det_));
+    OP_REQUIRES_OK(c, c->GetAttr("weights", &w_));
+    OP_REQUIRES(c, L_ <= D2B_MAX_LEVELS && w_.size() == 4, tf::errors::InvalidArgument("bad L / weights"));
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    d2b_retinanet_params p = {};
+    const tf::Tensor& cls0 = ctx->input(0);
+    OP_REQUIRES(ctx, cls0.dims() == 3, tf::errors::InvalidArgument("box_cls must be [N,HWA,K]"));
+    for (int l = 0; l < L_; ++l) {
+      const tf::Tensor& cls = ctx->input(l);
+      const tf::Tensor& dl = ctx->input(L_ + l);
+      const tf::Tensor& an = ctx->input(2 * L_ + l);
+      OP_REQUIRES(ctx, cls.dims() == 3 && dl.dims() == 3 && an.dims() == 2 && an.dim_size(1) == 4 &&
+                           cls.dim_size(1) == an.dim_size(0) && dl.dim_size(1) == an.dim_size(0) &&
+                           dl.dim_size(2) == 4 && cls.dim_size(2) == cls0.dim_size(2),
+                  tf::errors::InvalidArgument("level ", l, ": box_cls [N,HWA,K], box_delta [N,HWA,4], anchors [HWA,4]"));
+      p.box_cls[l] = cls.flat<float>().data();
+      p.box_delta[l] = dl.flat<float>().data();
+      p.anchors[l] = an.flat<float>().data();
+      p.hwa[l] = an.dim_size(0);
+    }
+    p.num_levels = L_;
+    p.num_images = static_cast<int>(cls0.dim_size(0));
+    p.num_classes = static_cast<int>(cls0.dim_size(2));
+    p.topk_candidates = topk_;
+    p.score_thresh = score_thr_;
+    p.nms_thresh = nms_thr_;
+    p.max_detections = det_;
+    for (int i = 0; i < 4; ++i) p.weights[i] = w_[i];
+    p.scale_clamp = 4.135166556742356f;  // log(1000/16), box_regression.py:10
+    tf::Tensor *ob = nullptr, *os = nullptr, *oc = nullptr, *ov = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({p.num_images, det_, 4}), &ob));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({p.num_images, det_}), &os));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, tf::TensorShape({p.num_images, det_}), &oc));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(3, tf::TensorShape({p.num_images, det_}), &ov));
+    p.out_boxes = ob->flat<float>().data();
+    p.out_scores = os->flat<float>().data();
+    p.out_classes = oc->flat<tf::int32>().data();
+    p.out_valid = reinterpret_cast<uint8_t*>(ov->flat<bool>().data());
+    RunOp(ctx, p, d2b_retinanet_postprocess_workspace_bytes, d2b_retinanet_postprocess);
+  }
+
+ private:
+  int L_, topk_, det_;
+  float score_thr_, nms_thr_;
+  std::vector<float> w_;
+};
+REGISTER_KERNEL_BUILDER(Name("D2RetinanetPostprocess").Device(tf::DEVICE_GPU), D2RetinanetPostprocessOp);
+
+// ------------------------------------------------------------------ D2CropAndResizeAligned
+// Replaces crop_and_resize on ONE feature map (lib/layers/functional.py:100-166): SYMMETRIC 1-px pad, the
+// aligned half-pixel box transform and tf.image.crop_and_resize, without materialising the padded copy.
+REGISTER_OP("D2CropAndResizeAligned")
+    .Input("image: float")    // [N, H, W, C]
+    .Input("boxes: float")    // [M, 4] in image pixels (y1, x1, y2, x2)
+    .Input("box_ind: int32")  // [M]
+    .Attr("crop_h: int")
+    .Attr("crop_w: int")
+    .Attr("aligned: bool = true")
+    .Attr("pad_border: bool = true")
+    .Output("crops: float")   // [M, crop_h, crop_w, C]
+    .SetShapeFn([](InferenceContext* c) {
+      int ch, cw;
+      TF_RETURN_IF_ERROR(c->GetAttr("crop_h", &ch));
+      TF_RETURN_IF_ERROR(c->GetAttr("crop_w", &cw));
+      c->set_output(0, c->MakeShape({c->Dim(c->input(1), 0), ch, cw, c->Dim(c->input(0), 3)}));
+      return tf::Status::OK();
+    });
+
+class D2CropAndResizeAlignedOp : public tf::OpKernel {
+ public:
+  explicit D2CropAndResizeAlignedOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("crop_h", &ch_));
+    OP_REQUIRES_OK(c, c->GetAttr("crop_w", &cw_));
+    OP_REQUIRES_OK(c, c->GetAttr("aligned", &aligned_));
+    OP_REQUIRES_OK(c, c->GetAttr("pad_border", &pad_));
+    OP_REQUIRES(c, ch_ >= 1 && cw_ >= 1, tf::errors::InvalidArgument("crop size must be positive"));
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    const tf::Tensor& image = ctx->input(0);
+    const tf::Tensor& boxes = ctx->input(1);
+    const tf::Tensor& ind = ctx->input(2);
+    OP_REQUIRES(ctx, image.dims() == 4, tf::errors::InvalidArgument("image must be NHWC"));
+    OP_REQUIRES(ctx, boxes.dims() == 2 && boxes.dim_size(1) == 4 && ind.dims() == 1 && ind.dim_size(0) == boxes.dim_size(0),
+                tf::errors::InvalidArgument("boxes must be [M,4] and box_ind [M]"));
+    d2b_crop_and_resize_params p = {};
+    p.image = image.flat<float>().data();
+    p.num_images = static_cast<int>(image.dim_size(0));
+    p.height = static_cast<int>(image.dim_size(1));
+    p.width = static_cast<int>(image.dim_size(2));
+    p.channels = static_cast<int>(image.dim_size(3));
+    p.boxes = boxes.flat<float>().data();
+    p.box_ind = ind.flat<tf::int32>().data();
+    p.num_boxes = boxes.dim_size(0);
+    p.crop_h = ch_; p.crop_w = cw_;
+    p.aligned = aligned_ ? 1 : 0;
+    p.pad_border = pad_ ? 1 : 0;
+    tf::Tensor* out = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({p.num_boxes, ch_, cw_, p.channels}), &out));
+    p.out = out->flat<float>().data();
+    RunOp(ctx, p, d2b_crop_and_resize_aligned_workspace_bytes, d2b_crop_and_resize_aligned);
+  }
+
+ private:
+  int ch_, cw_;
+  bool aligned_, pad_;
+};
+REGISTER_KERNEL_BUILDER(Name("D2CropAndResizeAligned").Device(tf::DEVICE_GPU), D2CropAndResizeAlignedOp);
 
 // ------------------------------------------------------------------ D2RoiAlignMultilevelGrad
 // Gradient of D2RoiAlignMultilevel w.r.t. the feature maps (boxes carry none: functional.py:120
