@@ -81,7 +81,8 @@ __device__ __forceinline__ FBox filter_box(const CBox c, float kf) {
   return f;
 }
 
-// grid (ceil(W/2), S).  mask[seg][i][w] bit c: box (w*64+c) is suppressed by box i (only j > i).
+// grid (ceil(W/2), S, csplit).  mask[seg][i][w] bit c: box (w*64+c) is suppressed by box i (only j > i).
+// csplit > 1 (few segments: the latency regime) deals the column blocks of a row block to csplit CTAs.
 // A CTA handles the 64-row blocks x and nb-1-x of its segment, so every CTA walks nb+1 column blocks (the upper
 // triangle is balanced).  8 independent warps per CTA: warp = (column group q, row half); it owns 32 rows of the
 // 64-row block and walks column blocks rb+q, rb+q+4, ...  The 64 column boxes of a block are staged in a
@@ -107,12 +108,26 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* bo
     const CBox bi = canon(live ? b[i] : make_float4(0, 0, 0, 0), live);
     const FBox fi = filter_box(bi, kf);
     u64* mrow = mask + ((size_t)seg * W * 64 + i) * W;
-    for (int cb = rb + q; cb < nb; cb += kMaskThreads / 64) {
+    const int cstep = (kMaskThreads / 64) * (int)gridDim.z;
+    int cb = rb + q + (kMaskThreads / 64) * (int)blockIdx.z;
+    float4 nxt[2];  // the column boxes of the next visit are loaded one visit ahead
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = cb * 64 + h * 32 + lane;
+      nxt[h] = (cb < nb && j < cnt) ? __ldg(b + j) : make_float4(0, 0, 0, 0);
+    }
+    for (; cb < nb; cb += cstep) {
       const int j0 = cb * 64;
+      float4 cur[2] = {nxt[0], nxt[1]};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = (cb + cstep) * 64 + h * 32 + lane;
+        nxt[h] = (cb + cstep < nb && j < cnt) ? __ldg(b + j) : make_float4(0, 0, 0, 0);
+      }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int j = j0 + h * 32 + lane;
-        const CBox c = canon(j < cnt ? __ldg(b + j) : make_float4(0, 0, 0, 0), j < cnt);
+        const CBox c = canon(cur[h], j < cnt);
         const FBox f = filter_box(c, kf);
         s_flt[warp][h * 32 + lane] = make_float4(f.ylo, f.xlo, f.yhi, f.xhi);
         s_box[warp][h * 32 + lane] = make_float4(c.ymin, c.xmin, c.ymax, c.xmax);
@@ -368,7 +383,10 @@ int nms_sorted(const float* boxes, const int32_t* counts, int S, int n, int max_
               max_out, kBitmaskMaxN, kLazyMaxOut);
   const int W = (n + 63) / 64;
   u64* mask = static_cast<u64*>(ws);
-  nms_mask_kernel<<<dim3((W + 1) / 2, S), kMaskThreads, 0, st>>>(b4, counts, n, W, thr, mask);
+  // few segments: spread a row block's column blocks over up to 4 CTAs so that the grid still fills the SMs
+  int csplit = 1;
+  while (csplit < 4 && (long long)((W + 1) / 2) * S * csplit * 2 <= 2 * 148 && csplit * 8 < W) csplit *= 2;
+  nms_mask_kernel<<<dim3((W + 1) / 2, S, csplit), kMaskThreads, 0, st>>>(b4, counts, n, W, thr, mask);
   D2B_LAUNCH_CHECK();
   if (!sweep) return D2B_OK;  // the caller runs its own sweep over the mask (fused with the proposal merge)
   if (W <= kColSweepMaxW)

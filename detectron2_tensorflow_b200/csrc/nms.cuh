@@ -86,6 +86,7 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
         const u64 nk = U & ~blocked;  // never empty: the first undecided row cannot be blocked
         K |= nk;
         U &= ~nk;
+        if (!U) break;  // (the usual sparse tile: nothing undecided is blocked, one round)
         U &= ~warp_or64(((nk & bitA) ? dA : 0ull) | ((nk & bitB) ? dB : 0ull));
       }
       int c = __popcll(K);

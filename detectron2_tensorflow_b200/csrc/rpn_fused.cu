@@ -47,10 +47,17 @@ struct SelCtl {
   unsigned ties[kSelCluster];      // tie counts of every CTA (written remotely)
 };
 
-// Dynamic shared memory: [hist 2*260][whist kHistCopies*256][scan 32][ctl 256 B][cand 256 u64][raw P u64][tmp P u64]
-constexpr size_t kSelOffWhist = 2 * kHistStride * 4;
+// Radix digits: 11 + 8 + 8 + 5 bits of the 32-bit value key.  Pass 0 takes 11 bits (sign + exponent + 2 mantissa
+// bits = a quarter binade per bin: 8 bits would lump two binades into one bucket) with a two-level exchange: the
+// peers' 256 coarse sums are scanned first, then the 8 fine bins of the coarse boundary bin.
+__constant__ int c_sel_shift[4] = {21, 13, 5, 0};
+__constant__ int c_sel_bits[4] = {11, 8, 8, 5};
+constexpr int kFineBins = 2048;
+// Dynamic shared memory: [hist 2*260][fine 2048][whist kHistCopies*256][scan 32+64][ctl 256 B][cand 256 u64][raw P u64][tmp P u64]
+constexpr size_t kSelOffFine = 2 * kHistStride * 4;
+constexpr size_t kSelOffWhist = kSelOffFine + kFineBins * 4;
 constexpr size_t kSelOffScan = kSelOffWhist + kHistCopies * 256 * 4;
-constexpr size_t kSelOffCtl = kSelOffScan + 32 * 4;
+constexpr size_t kSelOffCtl = kSelOffScan + (32 + 64) * 4;
 constexpr size_t kSelOffCand = kSelOffCtl + 256;
 constexpr size_t kSelOffRaw = kSelOffCand + kCandCap * 8;
 static_assert(kSelOffCtl % 8 == 0 && kSelOffCand % 8 == 0 && kSelOffRaw % 16 == 0, "shared-memory layout alignment");
@@ -142,8 +149,10 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
                                                                   int32_t* seg_count, u64* nms_in_total) {
   extern __shared__ __align__(16) unsigned char s_raw_bytes[];
   unsigned* hist = reinterpret_cast<unsigned*>(s_raw_bytes);                         // [2][kHistStride], peers read it
-  unsigned* whist = reinterpret_cast<unsigned*>(s_raw_bytes + kSelOffWhist);         // [kHistCopies][256]
+  unsigned* fine = reinterpret_cast<unsigned*>(s_raw_bytes + kSelOffFine);           // [2048] pass 0 (peers read 8 bins)
+  unsigned* whist = reinterpret_cast<unsigned*>(s_raw_bytes + kSelOffWhist);         // [kHistCopies][256] / 2nd fine copy
   unsigned* s_scan = reinterpret_cast<unsigned*>(s_raw_bytes + kSelOffScan);         // [32]
+  unsigned* s_f = s_scan + 32;                                                       // [8 peers][8 fine bins]
   SelCtl* ctl = reinterpret_cast<SelCtl*>(s_raw_bytes + kSelOffCtl);
   u64* s_cand = reinterpret_cast<u64*>(s_raw_bytes + kSelOffCand);                   // [kCandCap] all CTAs' candidates
   u64* s_raw = reinterpret_cast<u64*>(s_raw_bytes + kSelOffRaw);                     // [P] raw list, later all sorted runs
@@ -182,7 +191,18 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
   unsigned bucket = 0, any_overflow = 0;
   auto exchange = [&](int pass, unsigned my_overflow) {
     unsigned* hb = hist + (pass & 1) * kHistStride;
-    if (tid < 256) {
+    const int nbits = c_sel_bits[pass];
+    if (pass == 0) {
+      // fine (2048 bins) = copy of the even warps + copy of the odd warps; coarse bin = 8 fine bins
+      for (int i = tid; i < kFineBins; i += kSelThreads) fine[i] += whist[i];
+      __syncthreads();
+      if (tid < 256) {
+        unsigned v = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v += fine[tid * 8 + j];
+        hb[tid] = v;
+      }
+    } else if (tid < 256) {
       unsigned v = 0;
 #pragma unroll
       for (int c = 0; c < kHistCopies; ++c) v += whist[c * 256 + tid];
@@ -207,9 +227,32 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
       ctl->bucket = tot;
     }
     __syncthreads();
-    const unsigned digit = ctl->digit;
-    if (tid < kSelCluster) ctl->cand_cnt[tid] = cluster.map_shared_rank(hb, tid)[digit];  // per-CTA boundary counts
-    prefix = (prefix << 8) | digit;
+    unsigned digit = ctl->digit;
+    if (pass == 0) {
+      // second level: the 8 fine bins of the coarse boundary bin, per peer
+      if (tid < 64) s_f[tid] = cluster.map_shared_rank(fine, tid >> 3)[digit * 8 + (tid & 7)];
+      __syncthreads();
+      if (tid == 0) {
+        unsigned need = ctl->need, above = 0;
+        for (int j = 7; j >= 0; --j) {
+          unsigned t = 0;
+          for (int r = 0; r < kSelCluster; ++r) t += s_f[r * 8 + j];
+          if (above + t >= need) {
+            ctl->digit = digit * 8 + (unsigned)j;
+            ctl->need = need - above;
+            ctl->bucket = t;
+            for (int r = 0; r < kSelCluster; ++r) ctl->cand_cnt[r] = s_f[r * 8 + j];
+            break;
+          }
+          above += t;
+        }
+      }
+      __syncthreads();
+      digit = ctl->digit;
+    } else if (tid < kSelCluster) {
+      ctl->cand_cnt[tid] = cluster.map_shared_rank(hb, tid)[digit];  // per-CTA boundary counts
+    }
+    prefix = (prefix << nbits) | digit;
     k_rem = ctl->need;
     bucket = ctl->bucket;
     any_overflow = ctl->overflow;
@@ -246,31 +289,33 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
 
   if (!all) {
     // ---------------------------------------------------------------- pass 0: top byte (the one HBM read of the row)
-    zero_whist();
+    for (int i = tid; i < kFineBins; i += kSelThreads) { fine[i] = 0; whist[i] = 0; }
+    __syncthreads();
+    unsigned* f0 = (warp & 1) ? whist : fine;
     scan_chunk(x, beg, end, [&](float v, long long, bool ok) {
-      if (ok) atomicAdd(my + (key_of(v) >> 24), 1u);
+      if (ok) atomicAdd(f0 + (key_of(v) >> 21), 1u);
     });
     __syncthreads();
     D2B_PROF(prof, 64 + 1);
     exchange(0, 0u);
     next_pass = 1;
-    if (bucket == k_rem) {  // boundary bucket taken whole: every key >= prefix << 24 wins
-      const unsigned thr = prefix << 24;
+    if (bucket == k_rem) {  // boundary bucket taken whole: every key >= prefix << 21 wins
+      const unsigned thr = prefix << 21;
       if (thr == 0u) all = true; else cut = thr - 1u;
       resolved = true;
     }
   }
   if (!resolved) {
-    // ---------------------------------------------------------------- pass 1 (L2 read): second byte of the boundary
-    // bucket, and every element whose top byte is >= the boundary byte goes to the raw list (composite keys).
+    // ---------------------------------------------------------------- pass 1 (L2 read): next 8 bits of the boundary
+    // bucket, and every element whose 11-bit digit is >= the boundary digit goes to the raw list (composite keys).
     const unsigned d0 = prefix;
     zero_whist();
     bool fits = true;
     scan_chunk(x, beg, end, [&](float v, long long i, bool ok) {
       const unsigned key = key_of(v);
-      const unsigned top = key >> 24;
+      const unsigned top = key >> 21;
       fits &= append_to(s_raw, &ctl->raw_cnt, ((u64)key << 32) | (u64)(0xffffffffu - (unsigned)i), ok && top >= d0);
-      if (ok && top == d0) atomicAdd(my + ((key >> 16) & 255u), 1u);
+      if (ok && top == d0) atomicAdd(my + ((key >> 13) & 255u), 1u);
     });
     const unsigned my_overflow = __syncthreads_or(fits ? 0 : 1) ? 1u : 0u;
     D2B_PROF(prof, 64 + 8 + 1);
@@ -278,7 +323,7 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
     next_pass = 2;
     const bool whole = (bucket == k_rem);
     if (!any_overflow && (whole || bucket <= (unsigned)kCandCap)) {
-      // ---- fast finish: winners = raw entries above the 16-bit boundary; the boundary bucket's elements
+      // ---- fast finish: winners = raw entries above the 19-bit boundary; the boundary bucket's elements
       // (candidates) are sent to every CTA and ranked there (composites are unique: ties fall to the lower index)
       unsigned cbase = 0;
       for (unsigned r = 0; r < rank; ++r) cbase += ctl->cand_cnt[r];
@@ -286,9 +331,9 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
       for (unsigned i0 = 0; i0 < nraw; i0 += kSelThreads) {  // block-uniform trip count
         const unsigned i = i0 + tid;
         const u64 c = i < nraw ? s_raw[i] : 0ull;
-        const unsigned t16 = (unsigned)(c >> 48);
-        const bool win = i < nraw && (t16 > prefix || (whole && t16 == prefix));
-        const bool cand = i < nraw && !whole && t16 == prefix;
+        const unsigned t19 = (unsigned)(c >> 45);
+        const bool win = i < nraw && (t19 > prefix || (whole && t19 == prefix));
+        const bool cand = i < nraw && !whole && t19 == prefix;
         append_to(s_tmp, &ctl->local_cnt, c, win);
         if (cand) {
           const unsigned j = cbase + atomicAdd(&ctl->my_cand, 1u);
@@ -318,8 +363,8 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
       }
       have_lists = true;
     } else if (whole) {
-      const unsigned thr = prefix << 16;
-      cut = thr - 1u;  // prefix != 0 here: a zero top byte would have been "taken whole" only with thr == 0 in pass 0
+      const unsigned thr = prefix << 13;
+      cut = thr - 1u;
       if (thr == 0u) all = true;
       resolved = true;
     }
@@ -330,12 +375,13 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
     // scan; exact ties are split by index order through per-CTA quotas.
     if (!resolved) {
       for (int pass = next_pass; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        const int hs = shift + 8;
+        const int shift = c_sel_shift[pass];
+        const int hs = shift + c_sel_bits[pass];
+        const unsigned dmask = (1u << c_sel_bits[pass]) - 1u;
         zero_whist();
         scan_chunk(x, beg, end, [&](float v, long long, bool ok) {
           const unsigned key = key_of(v);
-          if (ok && (key >> hs) == prefix) atomicAdd(my + ((key >> shift) & 255u), 1u);
+          if (ok && (key >> hs) == prefix) atomicAdd(my + ((key >> shift) & dmask), 1u);
         });
         __syncthreads();
         exchange(pass, 0u);
@@ -421,20 +467,47 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
   const unsigned c_mine = min(ctl->cnt[rank], P);
   unsigned base_mine = 0;
   for (unsigned r = 0; r < rank; ++r) base_mine += ctl->cnt[r];
-  int Pe = 1;
-  while (Pe < (int)c_mine) Pe <<= 1;
-  for (int i = (int)c_mine + tid; i < Pe; i += kSelThreads) s_tmp[i] = 0ull;
-  __syncthreads();
-  for (int k = 2; k <= Pe; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int p = tid; p < Pe / 2; p += kSelThreads) {
-        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-        const bool desc = ((i & k) == 0);
-        const u64 va = s_tmp[i], vb = s_tmp[i | j];
-        if (desc ? (va < vb) : (va > vb)) { s_tmp[i] = vb; s_tmp[i | j] = va; }
+  const float h = (float)a.shapes[2 * n], w = (float)a.shapes[2 * n + 1];
+  const size_t rbase = (size_t)n * len;
+  for (unsigned i = tid; i < c_mine; i += kSelThreads) {  // the gathers of the decode below: start them now
+    const unsigned idx = key_index(s_tmp[i]);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.logits[l] + rbase + idx));
+    if (a.proposals[l]) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.proposals[l] + rbase + idx));
+    else asm volatile("prefetch.global.L2 [%0];" ::"l"(a.deltas[l] + rbase + idx));
+  }
+  if (c_mine <= (unsigned)kSelThreads) {
+    // small list (the usual ~k/8 winners): rank by counting, one element per thread, then permute in place
+    // (every key is unique; two keys per broadcast 16-byte shared load)
+    u64 mine = 0;
+    unsigned r = 0;
+    if (tid < (int)c_mine) {
+      mine = s_tmp[tid];
+      const unsigned even = c_mine & ~1u;
+      for (unsigned j = 0; j < even; j += 2) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(s_tmp + j);
+        r += (v.x > mine ? 1u : 0u) + (v.y > mine ? 1u : 0u);
       }
-      __syncthreads();
+      if (even < c_mine) r += s_tmp[even] > mine ? 1u : 0u;
     }
+    __syncthreads();
+    if (tid < (int)c_mine) s_tmp[r] = mine;
+    __syncthreads();
+  } else {
+    int Pe = 1;
+    while (Pe < (int)c_mine) Pe <<= 1;
+    for (int i = (int)c_mine + tid; i < Pe; i += kSelThreads) s_tmp[i] = 0ull;
+    __syncthreads();
+    for (int k = 2; k <= Pe; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int p = tid; p < Pe / 2; p += kSelThreads) {
+          const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+          const bool desc = ((i & k) == 0);
+          const u64 va = s_tmp[i], vb = s_tmp[i | j];
+          if (desc ? (va < vb) : (va > vb)) { s_tmp[i] = vb; s_tmp[i | j] = va; }
+        }
+        __syncthreads();
+      }
+  }
   D2B_PROF(prof, 6);
   for (unsigned i = tid; i < c_mine; i += kSelThreads) {
     const u64 c = s_tmp[i];
@@ -445,8 +518,6 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
   }
   cluster.sync();  // all runs are in every CTA's s_raw; nobody touches a peer's shared memory after this point
   D2B_PROF(prof, 7);
-  const float h = (float)a.shapes[2 * n], w = (float)a.shapes[2 * n + 1];
-  const size_t rbase = (size_t)n * len;
   for (unsigned i = tid; i < c_mine; i += kSelThreads) {
     const u64 key = s_tmp[i];
     unsigned pos = i;
