@@ -23,8 +23,12 @@ __device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
 constexpr int kColSweepThreads = 1024;
 constexpr int kColSweepMaxW = 64;  // n <= 4096
 
+// SMEM_OUT: instead of the global keep list, the kept boxes' positions and the order-preserving keys of their scores
+// (sc = the segment's scores in candidate order) go to shared memory (s_pos / s_key, max_out entries each).
+template <bool SMEM_OUT = false>
 __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, const unsigned long long* __restrict__ m,
-                                                 int32_t* __restrict__ kp) {
+                                                 int32_t* __restrict__ kp, const float* __restrict__ sc = nullptr,
+                                                 uint32_t* s_key = nullptr, uint16_t* s_pos = nullptr) {
   typedef unsigned long long u64;
   __shared__ volatile u64 s_keep[kColSweepMaxW];
   __shared__ volatile int s_flag[kColSweepMaxW];
@@ -43,6 +47,11 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
     u64 dA = 0, dB = 0;
     if (lane < rows) dA = __ldcg(m + (size_t)(word * 64 + lane) * W + word);
     if (lane + 32 < rows) dB = __ldcg(m + (size_t)(word * 64 + 32 + lane) * W + word);
+    float scA = 0.0f, scB = 0.0f;
+    if (SMEM_OUT) {
+      if (lane < rows) scA = __ldg(sc + word * 64 + lane);
+      if (lane + 32 < rows) scB = __ldg(sc + word * 64 + 32 + lane);
+    }
     u64 pa[kAhead], pb[kAhead];
 #pragma unroll
     for (int u = 0; u < kAhead; ++u) {
@@ -95,8 +104,16 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
         K &= ~(1ull << (63 - __clzll((long long)K)));
         --c;
       }
-      if (K & bitA) kp[kept_before + __popcll(K & (bitA - 1ull))] = word * 64 + lane;
-      if (K & bitB) kp[kept_before + __popcll(K & (bitB - 1ull))] = word * 64 + 32 + lane;
+      if (K & bitA) {
+        const int slot = kept_before + __popcll(K & (bitA - 1ull));
+        if (SMEM_OUT) { s_key[slot] = float_to_key(scA); s_pos[slot] = (uint16_t)(word * 64 + lane); }
+        else kp[slot] = word * 64 + lane;
+      }
+      if (K & bitB) {
+        const int slot = kept_before + __popcll(K & (bitB - 1ull));
+        if (SMEM_OUT) { s_key[slot] = float_to_key(scB); s_pos[slot] = (uint16_t)(word * 64 + 32 + lane); }
+        else kp[slot] = word * 64 + 32 + lane;
+      }
     }
     __syncwarp();
     if (lane == 0) {
@@ -110,7 +127,8 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
   int kept = 0;
   for (int b = 0; b < nb; ++b) kept += __popcll(s_keep[b]);
   kept = min(kept, max_out);
-  for (int j = kept + tid; j < max_out; j += kColSweepThreads) kp[j] = -1;
+  if (!SMEM_OUT)
+    for (int j = kept + tid; j < max_out; j += kColSweepThreads) kp[j] = -1;
   return kept;
 }
 

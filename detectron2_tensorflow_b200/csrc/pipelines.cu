@@ -137,7 +137,7 @@ int rpn_plan(const d2b_rpn_proposals_params* p, RpnPlan& pl) {
   const char* force_generic = getenv("D2B_RPN_GENERIC");
   pl.fused_select = a.k <= kRpnFusedMaxK && !(force_generic && force_generic[0] == '1');
   pl.fused_sweep = pl.fused_select && nms_uses_bitmask(a.k, a.post) &&
-                   (size_t)a.L * (a.post < a.k ? a.post : a.k) * sizeof(uint32_t) <= 200 * 1024;
+                   ((size_t)a.L * 4 + 2) * (a.post < a.k ? a.post : a.k) + 16 <= 200 * 1024;
   return D2B_OK;
 }
 
@@ -518,7 +518,7 @@ extern "C" int d2b_rpn_proposals(const d2b_rpn_proposals_params* p, void* worksp
                     nkeep, ws + pl.o_nms, st, /*sweep=*/false);
     if (rc != D2B_OK) return rc;
     return rpn_sweep_merge_fused(a, seg_count, reinterpret_cast<const u64*>(ws + pl.o_nms), seg_boxes, seg_scores,
-                                 keep, reinterpret_cast<float4*>(p->out_boxes), p->out_logits, p->out_valid,
+                                 reinterpret_cast<float4*>(p->out_boxes), p->out_logits, p->out_valid,
                                  p->out_num_valid, st);
   }
   if (!pl.fused_select) {

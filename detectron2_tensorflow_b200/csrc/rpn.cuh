@@ -201,9 +201,9 @@ constexpr int kRpnFusedMaxK = 4096;
 int rpn_select_fused(const RpnArgs& a, float4* seg_boxes, float* seg_scores, int32_t* seg_count,
                      unsigned long long* nms_in_total, cudaStream_t st);
 // ... and ONE cluster launch (one cluster per image, one CTA per level) sweeps every segment's suppression mask and
-// merges each image's levels (top `post`, zero padded).  keep [rows, post] is scratch.
+// merges each image's levels (top `post`, zero padded).
 int rpn_sweep_merge_fused(const RpnArgs& a, const int32_t* seg_count, const unsigned long long* mask,
-                          const float4* seg_boxes, const float* seg_scores, int32_t* keep, float4* out_boxes,
-                          float* out_logits, uint8_t* out_valid, int32_t* out_num, cudaStream_t st);
+                          const float4* seg_boxes, const float* seg_scores, float4* out_boxes, float* out_logits,
+                          uint8_t* out_valid, int32_t* out_num, cudaStream_t st);
 
 }  // namespace d2b

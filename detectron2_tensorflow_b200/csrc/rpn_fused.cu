@@ -45,6 +45,7 @@ struct SelCtl {
   unsigned cnt[kSelCluster];       // winners per CTA (written by the owners through DSMEM)
   unsigned sel_cnt[kSelCluster];   // candidates selected per CTA (computed redundantly by every CTA)
   unsigned ties[kSelCluster];      // tie counts of every CTA (written remotely)
+  unsigned wcnt[kSelThreads / 32];  // fast path: entries of each warp's raw sublist
 };
 
 // Radix digits: 11 + 8 + 8 + 5 bits of the 32-bit value key.  Pass 0 takes 11 bits (sign + exponent + 2 mantissa
@@ -310,14 +311,25 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
     // bucket, and every element whose 11-bit digit is >= the boundary digit goes to the raw list (composite keys).
     const unsigned d0 = prefix;
     zero_whist();
-    bool fits = true;
+    // raw list = 16 per-warp sublists of P/16 entries, filled with a warp-uniform register count (a single shared
+    // counter serialises ~400 same-address shared-memory atomics per CTA: measured 11 us for this scan)
+    const unsigned cap_w = P / kSelWarps;
+    u64* wlist = s_raw + (size_t)warp * cap_w;
+    unsigned wcnt = 0;
     scan_chunk(x, beg, end, [&](float v, long long i, bool ok) {
       const unsigned key = key_of(v);
       const unsigned top = key >> 21;
-      fits &= append_to(s_raw, &ctl->raw_cnt, ((u64)key << 32) | (u64)(0xffffffffu - (unsigned)i), ok && top >= d0);
+      const bool take = ok && top >= d0;
+      const unsigned m = __ballot_sync(0xffffffffu, take);
+      if (m) {
+        const unsigned slot = wcnt + __popc(m & ((1u << lane) - 1u));
+        if (take && slot < cap_w) wlist[slot] = ((u64)key << 32) | (u64)(0xffffffffu - (unsigned)i);
+        wcnt += __popc(m);
+      }
       if (ok && top == d0) atomicAdd(my + ((key >> 13) & 255u), 1u);
     });
-    const unsigned my_overflow = __syncthreads_or(fits ? 0 : 1) ? 1u : 0u;
+    if (lane == 0) ctl->wcnt[warp] = wcnt;
+    const unsigned my_overflow = __syncthreads_or(wcnt > cap_w ? 1 : 0) ? 1u : 0u;
     D2B_PROF(prof, 64 + 8 + 1);
     exchange(1, my_overflow);
     next_pass = 2;
@@ -327,13 +339,17 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
       // (candidates) are sent to every CTA and ranked there (composites are unique: ties fall to the lower index)
       unsigned cbase = 0;
       for (unsigned r = 0; r < rank; ++r) cbase += ctl->cand_cnt[r];
-      const unsigned nraw = min(ctl->raw_cnt, P);
-      for (unsigned i0 = 0; i0 < nraw; i0 += kSelThreads) {  // block-uniform trip count
-        const unsigned i = i0 + tid;
-        const u64 c = i < nraw ? s_raw[i] : 0ull;
+      unsigned wmax = 0;
+#pragma unroll
+      for (int q = 0; q < kSelWarps; ++q) wmax = max(wmax, ctl->wcnt[q]);
+      const unsigned my_n = wcnt;
+      for (unsigned i0 = 0; i0 < wmax; i0 += 32) {  // block-uniform trip count; warp q walks its own sublist
+        const unsigned i = i0 + lane;
+        const bool live = i < my_n;
+        const u64 c = live ? wlist[i] : 0ull;
         const unsigned t19 = (unsigned)(c >> 45);
-        const bool win = i < nraw && (t19 > prefix || (whole && t19 == prefix));
-        const bool cand = i < nraw && !whole && t19 == prefix;
+        const bool win = live && (t19 > prefix || (whole && t19 == prefix));
+        const bool cand = live && !whole && t19 == prefix;
         append_to(s_tmp, &ctl->local_cnt, c, win);
         if (cand) {
           const unsigned j = cbase + atomicAdd(&ctl->my_cand, 1u);
@@ -593,8 +609,8 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
 // straight to their output slots.  No sort, no intermediate buffers, no last-block hand-off.
 __global__ void __launch_bounds__(kColSweepThreads) rpn_sweep_merge_kernel(
     RpnArgs a, const int32_t* seg_count, int W, int cap, const u64* mask, const float4* seg_boxes,
-    const float* seg_scores, int32_t* keep, float4* out_boxes, float* out_logits, uint8_t* out_valid, int32_t* out_num) {
-  extern __shared__ uint32_t s_keys[];  // [L][cap]: score keys of every level's survivors (own slice written first)
+    const float* seg_scores, float4* out_boxes, float* out_logits, uint8_t* out_valid, int32_t* out_num) {
+  extern __shared__ uint32_t s_keys[];  // [L][cap] score keys of every level's survivors, then [cap] u16 positions
   __shared__ int s_cnt;
   __shared__ int s_off[D2B_MAX_LEVELS + 1];
   cg::cluster_group cluster = cg::this_cluster();
@@ -602,14 +618,13 @@ __global__ void __launch_bounds__(kColSweepThreads) rpn_sweep_merge_kernel(
   const int n = seg / a.L, l = seg - n * a.L;
   const int tid = threadIdx.x;
   const int cnt = min(seg_count[seg], a.k);
-  int32_t* kp = keep + (size_t)seg * a.post;
-  D2B_PROF(blockIdx.x == 0 && tid == 0, 16);
-  const int kept = nms_sweep_columns(cnt, W, a.post, mask + (size_t)seg * W * 64 * W, kp);
-  D2B_PROF(blockIdx.x == 0 && tid == 0, 17);
-  // my survivors' keys (kp was written by this CTA: visible after the barrier inside nms_sweep_columns)
   uint32_t* mine = s_keys + (size_t)l * cap;
+  uint16_t* s_pos = reinterpret_cast<uint16_t*>(s_keys + (size_t)a.L * cap);
   const float* sc = seg_scores + (size_t)seg * a.k;
-  for (int j = tid; j < kept; j += kColSweepThreads) mine[j] = float_to_key(sc[kp[j]]);
+  D2B_PROF(blockIdx.x == 0 && tid == 0, 16);
+  // the sweep leaves the survivors' positions and score keys in shared memory (selection order = score order)
+  const int kept = nms_sweep_columns<true>(cnt, W, cap, mask + (size_t)seg * W * 64 * W, nullptr, sc, mine, s_pos);
+  D2B_PROF(blockIdx.x == 0 && tid == 0, 17);
   if (tid == 0) s_cnt = kept;
   cluster.sync();
   if (tid < a.L) s_off[tid + 1] = *cluster.map_shared_rank(&s_cnt, tid);
@@ -646,7 +661,7 @@ __global__ void __launch_bounds__(kColSweepThreads) rpn_sweep_merge_kernel(
       rank += lo;
     }
     if (rank < a.post) {
-      const int p = kp[j];
+      const int p = s_pos[j];
       const size_t o = (size_t)n * a.post + rank;
       out_boxes[o] = seg_boxes[(size_t)seg * a.k + p];
       out_logits[o] = sc[p];
@@ -695,14 +710,14 @@ int rpn_select_fused(const RpnArgs& a, float4* seg_boxes, float* seg_scores, int
 }
 
 int rpn_sweep_merge_fused(const RpnArgs& a, const int32_t* seg_count, const unsigned long long* mask,
-                          const float4* seg_boxes, const float* seg_scores, int32_t* keep, float4* out_boxes,
-                          float* out_logits, uint8_t* out_valid, int32_t* out_num, cudaStream_t st) {
+                          const float4* seg_boxes, const float* seg_scores, float4* out_boxes, float* out_logits,
+                          uint8_t* out_valid, int32_t* out_num, cudaStream_t st) {
   const int rows = a.L * a.N;
   if (rows == 0) return D2B_OK;
   const int W = (a.k + 63) / 64;
   D2B_REQUIRE(W <= kColSweepMaxW, "fused sweep: k=%d too large", a.k);
   const int cap = a.post < a.k ? a.post : a.k;  // survivors per segment
-  const size_t smem = (size_t)a.L * cap * sizeof(uint32_t);
+  const size_t smem = (size_t)a.L * cap * sizeof(uint32_t) + align_up((size_t)cap * sizeof(uint16_t), 16);
   D2B_REQUIRE(smem <= 200 * 1024, "fused sweep: %d levels x %d survivors do not fit shared memory", a.L, cap);
   if (smem > 48 * 1024)
     D2B_CUDA(cudaFuncSetAttribute(rpn_sweep_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -719,7 +734,7 @@ int rpn_sweep_merge_fused(const RpnArgs& a, const int32_t* seg_count, const unsi
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   D2B_CUDA(cudaLaunchKernelEx(&cfg, rpn_sweep_merge_kernel, a, seg_count, W, cap, reinterpret_cast<const u64*>(mask),
-                              seg_boxes, seg_scores, keep, out_boxes, out_logits, out_valid, out_num));
+                              seg_boxes, seg_scores, out_boxes, out_logits, out_valid, out_num));
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }

@@ -35,11 +35,8 @@ for it in range(3):
     print("   " + "  ".join(f"{n}={(sel[i] - sel[0]) / 1e3:.1f}" for i, n in enumerate(names) if sel[i] >= sel[0]))
     print(f"   sweep kernel (segment 0): sweep={(t[17] - t[16]) / 1e3:.1f} us, merge end={(t[18] - t[16]) / 1e3:.1f} us; "
           f"select start -> sweep start {(t[16] - t[0]) / 1e3:.1f} us")
-    for ps in range(4):
-        q = t[64 + ps * 8: 64 + ps * 8 + 5]
-        if q[0] >= sel[0]:
-            print(f"   pass {ps}: zeroed={(q[0] - sel[0]) / 1e3:.1f} scanned={(q[1] - sel[0]) / 1e3:.1f} barrier_wait={(q[2] - sel[0]) / 1e3:.1f} "
-                  f"cluster_sync={(q[3] - sel[0]) / 1e3:.1f} remote_sum={(q[4] - sel[0]) / 1e3:.1f}")
+    print("   pass 0: scanned={:.1f} cluster_sync={:.1f};  pass 1: scanned={:.1f} cluster_sync={:.1f}".format(
+        *[(t[i] - sel[0]) / 1e3 for i in (65, 67, 73, 75)]))
     print(f"   merge (since sweep start): lists exchanged={(t[20] - t[16]) / 1e3:.1f} written={(t[18] - t[16]) / 1e3:.1f}")
     blk = t[32:64]
     print("   block publish times (us since sweep start): " + " ".join(f"{(b - t[16]) / 1e3:.1f}" for b in blk))
