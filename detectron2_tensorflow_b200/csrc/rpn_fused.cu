@@ -316,18 +316,82 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
     const unsigned cap_w = P / kSelWarps;
     u64* wlist = s_raw + (size_t)warp * cap_w;
     unsigned wcnt = 0;
-    scan_chunk(x, beg, end, [&](float v, long long i, bool ok) {
+    // `top >= d0` is decided on the raw float (v >= smallest value of bin d0; extra NaNs taken when d0 <= 3 are dropped
+    // by the classification below), one compare per element; the order-preserving key is only computed for the ~2 % that are taken.
+    const float thr_f = key_to_float(d0 << 21);
+    const bool take_all = !(thr_f == thr_f);  // d0 <= 3: the bin of NaN (key 0) / -inf; its lower edge is no float
+    auto take_one = [&](float v, long long i, unsigned& slot) {
       const unsigned key = key_of(v);
-      const unsigned top = key >> 21;
-      const bool take = ok && top >= d0;
-      const unsigned m = __ballot_sync(0xffffffffu, take);
-      if (m) {
-        const unsigned slot = wcnt + __popc(m & ((1u << lane) - 1u));
-        if (take && slot < cap_w) wlist[slot] = ((u64)key << 32) | (u64)(0xffffffffu - (unsigned)i);
-        wcnt += __popc(m);
+      if (slot < cap_w) wlist[slot] = ((u64)key << 32) | (u64)(0xffffffffu - (unsigned)i);
+      ++slot;
+      if ((key >> 21) == d0) atomicAdd(my + ((key >> 13) & 255u), 1u);
+    };
+    if (end > beg && (reinterpret_cast<uintptr_t>(x + beg) & 15) == 0) {
+      const long long nvec = (end - beg) >> 2;
+      const float4* xv = reinterpret_cast<const float4*>(x + beg);
+      constexpr int kV = 4;
+      for (long long v0 = 0; v0 < nvec; v0 += (long long)kV * kSelThreads) {  // block-uniform trip count
+        float4 q[kV];
+#pragma unroll
+        for (int u = 0; u < kV; ++u) {
+          const long long vi = v0 + (long long)u * kSelThreads + tid;
+          q[u] = ldg_nc_v4(xv + (vi < nvec ? vi : 0));
+        }
+        asm volatile("" ::: "memory");
+        unsigned mask = 0;  // bit 4u+c: component c of vector u is taken
+#pragma unroll
+        for (int u = 0; u < kV; ++u) {
+          const long long vi = v0 + (long long)u * kSelThreads + tid;
+          if (vi < nvec) {
+            mask |= ((take_all || q[u].x >= thr_f) ? 1u : 0u) << (4 * u);
+            mask |= ((take_all || q[u].y >= thr_f) ? 2u : 0u) << (4 * u);
+            mask |= ((take_all || q[u].z >= thr_f) ? 4u : 0u) << (4 * u);
+            mask |= ((take_all || q[u].w >= thr_f) ? 8u : 0u) << (4 * u);
+          }
+        }
+        // slots: warp-exclusive scan of the per-thread counts, once per trip
+        const unsigned c = __popc(mask);
+        unsigned inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        unsigned slot = wcnt + inc - c;
+        wcnt += __shfl_sync(0xffffffffu, inc, 31);
+        if (mask) {
+#pragma unroll
+          for (int u = 0; u < kV; ++u) {
+            const long long i = beg + 4 * (v0 + (long long)u * kSelThreads + tid);
+            if (mask & (1u << (4 * u))) take_one(q[u].x, i, slot);
+            if (mask & (2u << (4 * u))) take_one(q[u].y, i + 1, slot);
+            if (mask & (4u << (4 * u))) take_one(q[u].z, i + 2, slot);
+            if (mask & (8u << (4 * u))) take_one(q[u].w, i + 3, slot);
+          }
+        }
       }
-      if (ok && top == d0) atomicAdd(my + ((key >> 13) & 255u), 1u);
-    });
+      const long long t0 = beg + 4 * nvec;  // < 4 leftover elements
+      {
+        const long long i = t0 + tid;
+        const bool ok = i < end;
+        const float v = ok ? __ldg(x + i) : 0.0f;
+        const bool take = ok && (take_all || v >= thr_f);
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        unsigned slot = wcnt + __popc(m & ((1u << lane) - 1u));
+        wcnt += __popc(m);
+        if (take) take_one(v, i, slot);
+      }
+    } else {
+      scan_chunk(x, beg, end, [&](float v, long long i, bool ok) {
+        const bool take = ok && (take_all || v >= thr_f);
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        if (m) {
+          unsigned slot = wcnt + __popc(m & ((1u << lane) - 1u));
+          wcnt += __popc(m);
+          if (take) take_one(v, i, slot);
+        }
+      });
+    }
     if (lane == 0) ctl->wcnt[warp] = wcnt;
     const unsigned my_overflow = __syncthreads_or(wcnt > cap_w ? 1 : 0) ? 1u : 0u;
     D2B_PROF(prof, 64 + 8 + 1);
@@ -489,7 +553,10 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
     const unsigned idx = key_index(s_tmp[i]);
     asm volatile("prefetch.global.L2 [%0];" ::"l"(a.logits[l] + rbase + idx));
     if (a.proposals[l]) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.proposals[l] + rbase + idx));
-    else asm volatile("prefetch.global.L2 [%0];" ::"l"(a.deltas[l] + rbase + idx));
+    else {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.deltas[l] + rbase + idx));
+      if (a.anchors[l].table) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.anchors[l].table + idx));
+    }
   }
   if (c_mine <= (unsigned)kSelThreads) {
     // small list (the usual ~k/8 winners): rank by counting, one element per thread, then permute in place
