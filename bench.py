@@ -535,16 +535,21 @@ def strong_scaling(hp, x, dev, world, rank, K, W, chunks, in_flight, full_step, 
           "cls_deltas": x["cls_deltas"][b * R:e * R].contiguous()}
     for k in ("logits", "deltas", "feats"):
         xl[k] = [t[b:e].contiguous() for t in x[k]]
-    ch = max(1, min(chunks, (e - b) // 2))
-    pipe = hp.pipeline(xl, chunks=ch, depth=in_flight)
+    chunks_of = lambda k: max(1, min(chunks, k // 2))
+    layout = sharding.block_layout(n, world, chunks_of)
+    pipe = hp.pipeline(xl, chunks=chunks_of(e - b), depth=in_flight)
     g0 = pipe.steps[0]
+    assert [(b + lb, b + le) for lb, le in g0.bounds] == layout[rank]
+    outs = {}  # rank 0: the full-batch result tensors of every graphed step, allocated once
 
     def barrier():
         dist.barrier()
         torch.cuda.synchronize()
 
     def gather(step):
-        return sharding.gather_to_rank0(step.gathered(GATHER_KEYS), n)
+        blocks = [{k: o[k] for k in GATHER_KEYS} for o in step.outputs]
+        outs[id(step)] = sharding.gather_blocks_to_rank0(blocks, layout, out=outs.get(id(step)))
+        return outs[id(step)]
 
     for _ in range(W):
         g0.replay()
@@ -565,7 +570,7 @@ def strong_scaling(hp, x, dev, world, rank, K, W, chunks, in_flight, full_step, 
     ev[1].record()
     barrier()
     lat_ms = ev[0].elapsed_time(ev[1]) / K
-    # (2) the gather alone (pack + one collective + unpack on rank 0)
+    # (2) the gather alone
     barrier()
     ev[2].record()
     for _ in range(K):
@@ -609,8 +614,8 @@ def strong_scaling(hp, x, dev, world, rank, K, W, chunks, in_flight, full_step, 
             "pipelined_speedup_vs_1gpu": full_pipe_ms / pipe_ms, "pipelined_rois_per_s": rois / (pipe_ms * 1e-3),
             "gathered_identical_to_1gpu": identical, "kernels_per_step_per_rank": g0.kernels_per_replay,
             "note": "the fixed 16-image batch split by image index; ms_per_step = graph replay of the rank's block + "
-                    "pack + ONE dist.gather of proposals and detections to rank 0 + unpack, one step at a time, max over "
-                    "ranks (CUDA events); one_gpu_* = the same measurement of the whole batch on one GPU in this run "
+                    "ONE grouped batch of NCCL send/recv (proposals + detections straight into rank 0's full-batch "
+                    "tensors, no packing), one step at a time, max over ranks (CUDA events); one_gpu_* = the same measurement of the whole batch on one GPU in this run "
                     "(no gather needed); pipelined_* = several steps in flight on alternating streams"}
 
 

@@ -91,3 +91,46 @@ def gather_to_rank0(local, num_images, group=None):
     else:
         rows = torch.cat([recv[r, :sizes[r][1] - sizes[r][0]] for r in range(world)])
     return unpack_rows(rows, layout)
+
+
+def block_layout(num_images, world_size, chunks_of=None):
+    """layout[r] = the (begin, end) global image ranges rank r holds: its image block, cut into `chunks_of(n_r)`
+    sub-blocks (the image blocks a graphed step runs on concurrent streams).  Identical on every rank."""
+    layout = []
+    for r in range(world_size):
+        b, e = image_block(num_images, world_size, r)
+        c = max(1, min(int(chunks_of(e - b)) if chunks_of else 1, max(e - b, 1)))
+        layout.append([(b + image_block(e - b, c, i)[0], b + image_block(e - b, c, i)[1]) for i in range(c)])
+    return layout
+
+
+def gather_blocks_to_rank0(blocks, layout, out=None, group=None):
+    """Gather the fixed-size per-image outputs of every rank to rank 0 with ONE grouped batch of point-to-point
+    transfers and no packing: `blocks[i]` is this rank's dict of [e - b, ...] tensors for `layout[rank][i]`; rank 0
+    receives every (rank, block, tensor) straight into its slot `out[key][b:e]` of the full-batch tensors (NCCL: the
+    whole batch is one ncclGroupStart/End, i.e. one fused send/recv kernel per peer over NVLink; gloo on CPU).
+    `out` (rank 0, optional) = preallocated {key: [N, ...]} tensors to reuse.  Returns `out` on rank 0, None elsewhere."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    ops = []
+    if rank == 0:
+        n_total = layout[-1][-1][1]
+        if out is None:
+            out = {k: t.new_empty((n_total,) + tuple(t.shape[1:])) for k, t in blocks[0].items()}
+        for (b, e), blk in zip(layout[0], blocks):
+            for k, t in blk.items():
+                out[k][b:e].copy_(t)
+        for r in range(1, world):
+            for (b, e) in layout[r]:
+                if e > b:
+                    for k in out:
+                        ops.append(dist.P2POp(dist.irecv, out[k][b:e], r, group))
+    else:
+        for (b, e), blk in zip(layout[rank], blocks):
+            if e > b:
+                for k, t in blk.items():
+                    ops.append(dist.P2POp(dist.isend, t.contiguous(), 0, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out if rank == 0 else None

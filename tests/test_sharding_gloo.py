@@ -37,6 +37,49 @@ def _worker(rank, world, port, n_images, result_path):
     dist.destroy_process_group()
 
 
+def _worker_p2p(rank, world, port, n_images, result_path):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from detectron2_tensorflow_b200 import sharding
+    g = torch.Generator().manual_seed(7)
+    full = {"boxes": torch.randn((n_images, 6, 4), generator=g), "valid": torch.rand((n_images, 6), generator=g) > 0.5,
+            "classes": torch.randint(0, 80, (n_images, 6), generator=g, dtype=torch.int64)}
+    layout = sharding.block_layout(n_images, world, chunks_of=lambda n: 2)
+    blocks = [{k: v[b:e].clone() for k, v in full.items()} for (b, e) in layout[rank]]
+    got = sharding.gather_blocks_to_rank0(blocks, layout)
+    if rank == 0:
+        assert all(torch.equal(got[k], full[k]) and got[k].dtype == full[k].dtype for k in full)
+        # reuse of the preallocated outputs
+        got2 = sharding.gather_blocks_to_rank0(blocks, layout, out=got)
+        assert got2 is got and all(torch.equal(got[k], full[k]) for k in full)
+        open(result_path, "w").write("ok")
+    else:
+        assert got is None
+        assert sharding.gather_blocks_to_rank0(blocks, layout) is None
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_images", [4, 5, 1])
+def test_two_rank_grouped_p2p_gather(tmp_path, n_images):
+    """The grouped send/recv gather (one batch of P2P ops, no packing): uneven blocks, sub-blocks, bool / int64."""
+    path = str(tmp_path / "ok.txt")
+    port = 31500 + os.getpid() % 2000 + n_images
+    mp.spawn(_worker_p2p, args=(2, port, n_images, path), nprocs=2, join=True)
+    assert open(path).read() == "ok"
+
+
+def test_block_layout_covers_batch():
+    from detectron2_tensorflow_b200.sharding import block_layout
+    for n in (1, 5, 16):
+        for w in (1, 2, 4, 8):
+            lay = block_layout(n, w, chunks_of=lambda k: 2)
+            flat = [be for r in lay for be in r if be[1] > be[0]]
+            assert flat[0][0] == 0 and flat[-1][1] == n
+            assert all(flat[i][1] == flat[i + 1][0] for i in range(len(flat) - 1))
+
+
 @pytest.mark.parametrize("n_images", [4, 5])
 def test_two_rank_gather_matches_single_rank(oracle_lib, tmp_path, n_images):
     from detectron2_tensorflow_b200.utils import synthetic as syn
