@@ -133,6 +133,12 @@ class MatcherParams(C.Structure):
                 ("out_matches", _vp), ("out_labels", _vp)]
 
 
+class SubsampleLabelsParams(C.Structure):
+    _fields_ = [("labels", _vp), ("num_images", _i32), ("num_labels", _i64), ("num_samples", _i32),
+                ("max_positives", _i32), ("bg_label", _i64), ("seed", C.c_uint64), ("out_pos_idx", _vp),
+                ("out_neg_idx", _vp), ("out_num_pos", _vp), ("out_num_neg", _vp), ("out_labels", _vp)]
+
+
 class YoloParams(C.Structure):
     _fields_ = [("boxes", _vp), ("probs", _vp), ("num_images", _i32), ("num_boxes", _i32), ("num_classes", _i32),
                 ("score_thresh", _f32), ("nms_thresh", _f32), ("post_nms_topk", _i32), ("out_boxes", _vp),
@@ -203,6 +209,7 @@ OPS = {
     "pairwise_iou": PairwiseIouParams,
     "label_boxes": LabelBoxesParams,
     "matcher": MatcherParams,
+    "subsample_labels": SubsampleLabelsParams,
     "roi_align_backward": RoiAlignBackwardParams,
     "yolo_postprocess": YoloParams,
     "point_nms": PointNmsParams,

@@ -42,6 +42,17 @@ void count_launch();  // every kernel launch of the library bumps d2b_kernel_lau
     }                                                                                    \
   } while (0)
 
+// -DD2B_DEBUG_BOUNDS (D2B_EXTRA_NVCC=-DD2B_DEBUG_BOUNDS python -m detectron2_tensorflow_b200.build --force): device-side
+// asserts on computed indices of the scan / select / NMS / dynamic-conv kernels.  A violated bound traps the kernel
+// (cudaErrorAssert) and every later call of the process fails; the parity suite is run once under this build and the
+// log is committed under profiles/.  Compiled out of the product build.
+#ifdef D2B_DEBUG_BOUNDS
+#include <assert.h>
+#define D2B_BOUND(i, n) assert((unsigned long long)(i) < (unsigned long long)(n))
+#else
+#define D2B_BOUND(i, n) ((void)0)
+#endif
+
 // -DD2B_PROFILE: phase timestamps (%globaltimer, ns) of selected CTAs in a device array read back by
 // d2b_debug_read_profile() (tools/phase_probe.py).  Compiled out of the product build.
 #ifdef D2B_PROFILE

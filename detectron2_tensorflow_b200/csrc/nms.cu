@@ -155,6 +155,8 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* bo
         const float inter = ih * iw;
         if (iou_gt(inter, s_area[warp][c], bi.area, thr)) bits |= 1ull << c;
       }
+      D2B_BOUND(cb, W);
+      D2B_BOUND(i, live ? (long long)W * 64 : (long long)i + 1);
       if (live) mrow[cb] = bits;
       __syncwarp();
     }
@@ -201,6 +203,7 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const int32_t*
       u64 pdA = 0, pdB = 0, pnA = 0, pnB = 0;
       if (b + 1 < nb) {
         const int i0 = (b + 1) * 64 + lane, i1 = i0 + 32;
+        D2B_BOUND(b + 1, W);
         if (i0 < cnt) { pdA = m[(size_t)i0 * W + (b + 1)]; if (b + 2 < W) pnA = m[(size_t)i0 * W + (b + 2)]; }
         if (i1 < cnt) { pdB = m[(size_t)i1 * W + (b + 1)]; if (b + 2 < W) pnB = m[(size_t)i1 * W + (b + 2)]; }
       }
@@ -222,6 +225,7 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const int32_t*
         K &= ~(1ull << (63 - __clzll((long long)K)));
         --c;
       }
+      D2B_BOUND(kept + c - 1, c > 0 ? max_out : kept + c);
       if (K & bitA) kp[kept + __popcll(K & (bitA - 1ull))] = b * 64 + lane;
       if (K & bitB) kp[kept + __popcll(K & (bitB - 1ull))] = b * 64 + 32 + lane;
       const u64 fold = warp_or64(((K & bitA) ? nA : 0ull) | ((K & bitB) ? nB : 0ull));
@@ -248,6 +252,7 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const int32_t*
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
                 const int x = x0 + u * groups;
+                D2B_BOUND(w, W);
                 v[u] = (x < 64 && ((pk >> x) & 1ull)) ? __ldg(m + ((size_t)(b - 1) * 64 + x) * W + w) : 0ull;
               }
 #pragma unroll
@@ -322,6 +327,7 @@ __global__ void __launch_bounds__(kLazyThreads) nms_lazy_kernel(const float4* bo
       int k = kept;
       for (int t = 0; t < rows && k < max_out; ++t) {
         if (!((rem >> t) & 1ull)) {
+          D2B_BOUND(k, max_out);
           s_kept[k] = s_blk[t];
           kp[k] = b0 + t;
           ++k;

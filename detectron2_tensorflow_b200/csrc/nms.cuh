@@ -69,6 +69,7 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
           const u64 va = pa[u], vb = pb[u];
           const int nx = b + kAhead;  // refill this slot for the block kAhead further on
           if (nx < word) {
+            D2B_BOUND(nx * 64 + 32 + lane, (long long)W * 64);
             pa[u] = __ldcg(m + (size_t)(nx * 64 + lane) * W + word);
             pb[u] = __ldcg(m + (size_t)(nx * 64 + 32 + lane) * W + word);
           }
@@ -104,13 +105,16 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
         K &= ~(1ull << (63 - __clzll((long long)K)));
         --c;
       }
+      D2B_BOUND(word, W);
       if (K & bitA) {
         const int slot = kept_before + __popcll(K & (bitA - 1ull));
+        D2B_BOUND(slot, max_out);
         if (SMEM_OUT) { s_key[slot] = float_to_key(scA); s_pos[slot] = (uint16_t)(word * 64 + lane); }
         else kp[slot] = word * 64 + lane;
       }
       if (K & bitB) {
         const int slot = kept_before + __popcll(K & (bitB - 1ull));
+        D2B_BOUND(slot, max_out);
         if (SMEM_OUT) { s_key[slot] = float_to_key(scB); s_pos[slot] = (uint16_t)(word * 64 + 32 + lane); }
         else kp[slot] = word * 64 + 32 + lane;
       }

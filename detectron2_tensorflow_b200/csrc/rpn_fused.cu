@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
     __syncthreads();
     unsigned* f0 = (warp & 1) ? whist : fine;
     scan_chunk(x, beg, end, [&](float v, long long, bool ok) {
+      D2B_BOUND(key_of(v) >> 21, kFineBins);
       if (ok) atomicAdd(f0 + (key_of(v) >> 21), 1u);
     });
     __syncthreads();
@@ -417,6 +418,7 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
         append_to(s_tmp, &ctl->local_cnt, c, win);
         if (cand) {
           const unsigned j = cbase + atomicAdd(&ctl->my_cand, 1u);
+          D2B_BOUND(j, kCandCap);
 #pragma unroll
           for (unsigned r = 0; r < kSelCluster; ++r) cluster.map_shared_rank(s_cand, r)[j] = c;
         }
@@ -434,6 +436,7 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
             unsigned q = 0, b = 0;
             while (q + 1 < kSelCluster && tid >= (int)(b + ctl->cand_cnt[q])) { b += ctl->cand_cnt[q]; ++q; }
             atomicAdd(&ctl->sel_cnt[q], 1u);
+            D2B_BOUND(ctl->local_cnt, P);
             if (q == rank) s_tmp[atomicAdd(&ctl->local_cnt, 1u)] = mine;
           }
         }
@@ -573,6 +576,7 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
       if (even < c_mine) r += s_tmp[even] > mine ? 1u : 0u;
     }
     __syncthreads();
+    D2B_BOUND(r, tid < (int)c_mine ? c_mine : r + 1);
     if (tid < (int)c_mine) s_tmp[r] = mine;
     __syncthreads();
   } else {
@@ -594,6 +598,7 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
   D2B_PROF(prof, 6);
   for (unsigned i = tid; i < c_mine; i += kSelThreads) {
     const u64 c = s_tmp[i];
+    D2B_BOUND(base_mine + i, kr);  // the per-CTA counts add up to exactly kr winners
     if (base_mine + i < P) {
 #pragma unroll
       for (unsigned r = 0; r < kSelCluster; ++r) cluster.map_shared_rank(s_raw, r)[base_mine + i] = c;
@@ -619,8 +624,10 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
       }
       b += c;
     }
+    D2B_BOUND(pos, kr);
     if (pos < kr) {
       const unsigned idx = key_index(key);
+      D2B_BOUND(idx, len);
       const float score = __ldg(a.logits[l] + rbase + idx);
       float4 box;
       if (a.proposals[l]) box = __ldg(a.proposals[l] + rbase + idx);
@@ -727,8 +734,10 @@ __global__ void __launch_bounds__(kColSweepThreads) rpn_sweep_merge_kernel(
       }
       rank += lo;
     }
+    D2B_BOUND(rank, total);
     if (rank < a.post) {
       const int p = s_pos[j];
+      D2B_BOUND(p, cnt);
       const size_t o = (size_t)n * a.post + rank;
       out_boxes[o] = seg_boxes[(size_t)seg * a.k + p];
       out_logits[o] = sc[p];

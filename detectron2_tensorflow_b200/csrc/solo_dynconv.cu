@@ -365,6 +365,8 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
     auto flush = [&]() {
       if (cur_b >= 0) {
         const int row = cur_rb * kBM + row_in_tile;
+        D2B_BOUND(acc_cnt || acc_score != 0.0f ? row : 0, a.n);  // only live rows accumulate
+        D2B_BOUND(cur_b, a.B);
         if (acc_cnt) atomicAdd(a.sum_masks + (size_t)cur_b * a.n + row, (float)acc_cnt);  // integer valued < 2^24: exact
         if (acc_score != 0.0f) atomicAdd(a.score_sums + (size_t)cur_b * a.n + row, acc_score);
       }
@@ -387,6 +389,8 @@ solo_dynconv_kernel(const __grid_constant__ CUtensorMap tm_ahi, const __grid_con
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * kBN;
       const long long p0 = (long long)it.pt * kBN;
       u64 word = 0;
+      D2B_BOUND(it.b, a.B);
+      D2B_BOUND(live ? row : 0, a.n);
       u64* dstw = a.packed + ((size_t)it.b * a.n + (live ? row : 0)) * a.Wd;
       float* lg = a.logits ? a.logits + ((size_t)it.b * a.n + (live ? row : 0)) * a.hw : nullptr;
 #pragma unroll 1  // a rolled loop: the unrolled form is 160 KB of straight-line code and lives in instruction-cache misses

@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass, 
         in = (pass == 0) || ((c >> hi_shift) == prefix);
         digit = (unsigned)(c >> shift) & mask;
       }
+      D2B_BOUND(digit, kBins);
       if (in) atomicAdd(my + digit, 1u);
     };
     // rows with a cutoff do one compare per element: keep 4 x 16 B per thread in flight to stay HBM-bound
@@ -284,6 +285,7 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass, 
     for (int j = 0; j < kPer; ++j) {
       if (above + loc[j] >= k_rem) {
         const unsigned digit = (unsigned)(top - j);
+        D2B_BOUND(digit, 1u << bits);
         const unsigned need = k_rem - above;
         const u64 np = (prefix << bits) | digit;
         st->prefix = np;
@@ -323,6 +325,7 @@ __global__ void __launch_bounds__(kHistThreads) topk_collect(TopkArgs a, u64* ou
       base = __shfl_sync(0xffffffffu, base, 0);
       if (take) {
         const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
+        D2B_BOUND(slot, P);  // exactly k_r <= P composites reach the threshold
         if (slot < (unsigned)P) out[slot] = c;
       }
     }
@@ -384,6 +387,7 @@ __global__ void __launch_bounds__(kHistThreads) topk_prehist(TopkArgs a) {
   const float* x = a.d.scores[g] + (size_t)img * len;
   const int lane = threadIdx.x & (kPreCopies - 1);
   auto count = [&](float v, long long, bool ok) {
+    D2B_BOUND((float_to_key(v) >> (32 - kPreBits)) * kPreCopies + lane, kPreBins * kPreCopies);
     if (ok) atomicAdd(&sh[(float_to_key(v) >> (32 - kPreBits)) * kPreCopies + lane], 1u);
   };
   if (sampled) {

@@ -10,3 +10,4 @@ from .single_stage_heads.solo_v2 import (point_nms, solo_mask_encode, solo_dynam
                                          SOLOv2Inference)
 from .postprocessing import detector_postprocess
 from .roi_heads.mask_head import mask_rcnn_inference
+from .sampling import subsample_labels, subsample_labels_batched

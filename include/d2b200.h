@@ -441,6 +441,34 @@ D2B_API int d2b_label_boxes(const d2b_label_boxes_params* p, void* workspace, si
                             d2b_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * subsample_labels                                   lib/modeling/sampling.py:6-45
+ * (callers: RPNOutputs.losses resample, rpn_outputs.py:315-332; ROIHeads.label_and_sample_proposals,
+ * roi_heads.py:181-187).  labels [N, P] int64 with -1 = ignore, bg_label = negative, anything else = positive.
+ * Per image: num_pos = min(#positives, max_positives), num_neg = min(#negatives,
+ * num_samples - num_pos); the sampled subsets are uniform random subsets in random order, as
+ * tf.random_shuffle(x)[:n] gives.  TF's shuffle has no defined bit pattern: the generator here is counter-based
+ * (splitmix64 of seed / image / element, see csrc/sampling.cu) and deterministic per seed.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const int64_t* labels;  /* [N, P] */
+  int32_t num_images;
+  int64_t num_labels;     /* P */
+  int32_t num_samples;
+  int32_t max_positives;  /* int(num_samples * positive_fraction), evaluated by the caller in Python's double
+                             arithmetic exactly as sampling.py:37 does (a float product could round across an integer) */
+  int64_t bg_label;
+  uint64_t seed;
+  int64_t* out_pos_idx;   /* optional [N, num_samples], -1 padded */
+  int64_t* out_neg_idx;   /* optional [N, num_samples], -1 padded */
+  int32_t* out_num_pos;   /* optional [N] */
+  int32_t* out_num_neg;   /* optional [N] */
+  int64_t* out_labels;    /* optional [N, P]: labels of the sampled elements, -1 elsewhere (the RPN "resample") */
+} d2b_subsample_labels_params;
+D2B_API size_t d2b_subsample_labels_workspace_bytes(const d2b_subsample_labels_params* p);
+D2B_API int d2b_subsample_labels(const d2b_subsample_labels_params* p, void* workspace, size_t workspace_bytes,
+                                 d2b_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Matcher.__call__ on materialised matrices          lib/modeling/matcher.py:57-150
  * match_quality_matrix [num_gt, num_preds]; optional crowd / difficult matrices
  * (use_crowd / use_difficult = "the argument was not None"; zero rows allowed).

@@ -501,3 +501,37 @@ def mask_rcnn_inference(pred_mask_logits, pred_classes):
     sel = x[np.arange(M), :, :, np.clip(c, 0, Cc - 1)]
     sel = np.where(((c >= 0) & (c < Cc))[:, None, None], sel, np.float32(0))
     return sigmoid_array(sel)
+
+
+def subsample_labels(labels, num_samples, positive_fraction, bg_label, seed=0, image=0):
+    """lib/modeling/sampling.py:6-45 with the documented counter-based generator of csrc/sampling.cu restated in numpy
+    (TF's random_shuffle has no defined bit pattern; see that file).  labels [P] -> (pos_idx, neg_idx) int64."""
+    labels = np.asarray(labels, np.int64)
+    P = labels.shape[0]
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+    def scores(stream):
+        with np.errstate(over="ignore"):
+            i = np.arange(P, dtype=np.uint64)
+            z = (np.uint64(seed & 0xFFFFFFFFFFFFFFFF) + np.uint64(image) * np.uint64(0x9E3779B97F4A7C15) +
+                 i * np.uint64(0xBF58476D1CE4E5B9) + np.uint64(stream) * np.uint64(0x94D049BB133111EB)) & M
+            z = (z + np.uint64(0x9E3779B97F4A7C15)) & M
+            z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & M
+            z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & M
+            z = z ^ (z >> np.uint64(31))
+        return ((z >> np.uint64(40)).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
+
+    is_pos = (labels != -1) & (labels != bg_label)
+    is_neg = labels == bg_label
+    num_pos = min(int(is_pos.sum()), int(num_samples * positive_fraction))
+    num_neg = min(int(is_neg.sum()), num_samples - num_pos)
+    k = min(int(num_samples), P)
+    out = []
+    for mask, stream, n in ((is_pos, 0, num_pos), (is_neg, 1, num_neg)):
+        if P == 0 or n == 0:
+            out.append(np.zeros(0, np.int64))
+            continue
+        sc = np.where(mask, scores(stream), np.float32(-np.inf)).astype(np.float32)
+        _, idx = top_k(sc, k)
+        out.append(np.asarray(idx[:n], np.int64))
+    return out[0], out[1]

@@ -45,7 +45,7 @@ def test_struct_layout_matches_header(lib, tmp_path):
              "paste_masks": "d2b_paste_masks_params", "crop_and_resize_aligned": "d2b_crop_and_resize_params",
              "decode_clip_filter": "d2b_decode_clip_filter_params", "get_deltas": "d2b_get_deltas_params",
              "pairwise_iou": "d2b_pairwise_iou_params", "label_boxes": "d2b_label_boxes_params",
-             "matcher": "d2b_matcher_params", "roi_align_backward": "d2b_roi_align_backward_params",
+             "matcher": "d2b_matcher_params", "subsample_labels": "d2b_subsample_labels_params", "roi_align_backward": "d2b_roi_align_backward_params",
              "yolo_postprocess": "d2b_yolo_params", "point_nms": "d2b_point_nms_params",
              "solo_mask_encode": "d2b_solo_mask_encode_params", "solo_postprocess": "d2b_solo_postprocess_params",
              "solo_dynamic_masks": "d2b_solo_dynamic_masks_params",

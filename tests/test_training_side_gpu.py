@@ -262,3 +262,63 @@ def test_pairwise_iou_variants(cuda, oracle_lib, iou_type):
         assert np.array_equal(gz, z[f"pi_{iou_type}"])
     with pytest.raises(ValueError):
         pairwise_iou(torch.from_numpy(a).to(cuda), torch.from_numpy(b).to(cuda), "siou")
+
+
+# ------------------------------------------------------------------ subsample_labels (sampling.py:6-45)
+@pytest.mark.parametrize("P,num_samples,frac,bg,npos,nneg", [
+    (268569, 256, 0.5, 0, 40, 200000),     # RPN: few positives, the sample is filled with negatives
+    (2000, 512, 0.25, 80, 300, 1500),      # ROI heads
+    (2000, 512, 0.25, 80, 20, 100),        # not enough of either class
+    (1000, 10, 0.7, 0, 500, 400),          # int(10 * 0.7) == 7 in double arithmetic
+    (50, 64, 0.5, 0, 0, 50), (7, 4, 0.5, 0, 7, 0), (0, 8, 0.5, 0, 0, 0)])
+def test_subsample_labels(cuda, oracle_lib, P, num_samples, frac, bg, npos, nneg):
+    from detectron2_tensorflow_b200.modeling import subsample_labels, subsample_labels_batched
+    rng = np.random.default_rng(P + num_samples)
+    N = 3
+    labels = np.full((N, P), -1, np.int64)
+    for n in range(N):
+        perm = rng.permutation(P)
+        labels[n, perm[:npos]] = rng.integers(1, 80, npos) if bg == 0 else rng.integers(0, 80, npos)
+        labels[n, perm[npos:npos + nneg]] = bg
+    pos, neg, cp, cn, lab = subsample_labels_batched(T(labels, cuda), num_samples, frac, bg, seed=1234, return_labels=True)
+    pos, neg, cp, cn, lab = (t.cpu().numpy() for t in (pos, neg, cp, cn, lab))
+    want_pos = min(npos, int(num_samples * frac))
+    want_neg = min(nneg, num_samples - want_pos)
+    for n in range(N):
+        # the reference's contract (properties): exact counts, only eligible indices, no duplicates, -1 padding
+        assert cp[n] == want_pos and cn[n] == want_neg
+        ip, ineg = pos[n, :cp[n]], neg[n, :cn[n]]
+        assert np.all(pos[n, cp[n]:] == -1) and np.all(neg[n, cn[n]:] == -1)
+        assert len(set(ip.tolist())) == len(ip) and len(set(ineg.tolist())) == len(ineg)
+        assert np.all((labels[n, ip] != -1) & (labels[n, ip] != bg)) and np.all(labels[n, ineg] == bg)
+        # resampled labels: sampled elements keep their label, everything else is ignore (rpn_outputs.py:315-329)
+        want_lab = np.full(P, -1, np.int64)
+        want_lab[ip] = labels[n, ip]
+        want_lab[ineg] = labels[n, ineg]
+        assert np.array_equal(lab[n], want_lab)
+        # the documented generator, restated in numpy: identical indices in identical order
+        op, on = oracle_lib.subsample_labels(labels[n], num_samples, frac, bg, seed=1234, image=n)
+        assert np.array_equal(ip, op) and np.array_equal(ineg, on)
+    if P:
+        # reference signature (1-D labels -> dynamic-length index tensors), determinism per seed, seeds differ
+        a1, b1 = subsample_labels(T(labels[0], cuda), num_samples, frac, bg, seed=5)
+        a2, b2 = subsample_labels(T(labels[0], cuda), num_samples, frac, bg, seed=5)
+        a3, b3 = subsample_labels(T(labels[0], cuda), num_samples, frac, bg, seed=6)
+        assert torch.equal(a1, a2) and torch.equal(b1, b2)
+        assert a1.shape[0] == want_pos and b1.shape[0] == want_neg
+        if nneg > 4 * num_samples:
+            assert not torch.equal(b1, b3)
+
+
+def test_subsample_labels_is_uniform(cuda):
+    """Every negative is equally likely: 2000 seeds x 8-of-64 sampling, chi-square well inside its 99.9 % bound."""
+    from detectron2_tensorflow_b200.modeling import subsample_labels_batched
+    labels = torch.zeros((1, 64), dtype=torch.int64, device=cuda)
+    hits = np.zeros(64, np.int64)
+    for seed in range(2000):
+        _, neg, _, cn = subsample_labels_batched(labels, 8, 0.5, 0, seed=seed)
+        assert int(cn[0]) == 8
+        hits[neg[0].cpu().numpy()] += 1
+    expected = 2000 * 8 / 64.0
+    chi2 = float(((hits - expected) ** 2 / expected).sum())
+    assert chi2 < 110.0  # 63 degrees of freedom: P(chi2 > 103.4) = 0.001
