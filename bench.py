@@ -537,19 +537,35 @@ def strong_scaling(hp, x, dev, world, rank, K, W, chunks, in_flight, full_step, 
         xl[k] = [t[b:e].contiguous() for t in x[k]]
     chunks_of = lambda k: max(1, min(chunks, k // 2))
     layout = sharding.block_layout(n, world, chunks_of)
-    pipe = hp.pipeline(xl, chunks=chunks_of(e - b), depth=in_flight)
+    # one GatherPlan per graphed step: its pack() is captured inside the step's graph, its unpack() is a graph of
+    # its own on rank 0, so a step costs two graph launches + one NCCL gather on the host
+    spec = hp.gather_spec()
+    plans = [sharding.GatherPlan(spec, layout, dev) for _ in range(in_flight)]
+    pipe = hp.pipeline(xl, chunks=chunks_of(e - b), depth=in_flight,
+                       epilogues=[(lambda outs, p=p: p.pack([{k: o[k] for k in GATHER_KEYS} for o in outs])) for p in plans])
     g0 = pipe.steps[0]
     assert [(b + lb, b + le) for lb, le in g0.bounds] == layout[rank]
-    outs = {}  # rank 0: the full-batch result tensors of every graphed step, allocated once
+    unpack_graphs = []
+    if rank == 0:
+        for p in plans:
+            p.unpack()
+            torch.cuda.synchronize()
+            ug = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ug):
+                p.unpack()
+            unpack_graphs.append(ug)
+    step_plan = {id(st): (plans[i], unpack_graphs[i] if rank == 0 else None) for i, st in enumerate(pipe.steps)}
 
     def barrier():
         dist.barrier()
         torch.cuda.synchronize()
 
     def gather(step):
-        blocks = [{k: o[k] for k in GATHER_KEYS} for o in step.outputs]
-        outs[id(step)] = sharding.gather_blocks_to_rank0(blocks, layout, out=outs.get(id(step)))
-        return outs[id(step)]
+        plan, ug = step_plan[id(step)]
+        plan.gather()
+        if ug is not None:
+            ug.replay()
+        return plan.out
 
     for _ in range(W):
         g0.replay()
@@ -614,8 +630,8 @@ def strong_scaling(hp, x, dev, world, rank, K, W, chunks, in_flight, full_step, 
             "pipelined_speedup_vs_1gpu": full_pipe_ms / pipe_ms, "pipelined_rois_per_s": rois / (pipe_ms * 1e-3),
             "gathered_identical_to_1gpu": identical, "kernels_per_step_per_rank": g0.kernels_per_replay,
             "note": "the fixed 16-image batch split by image index; ms_per_step = graph replay of the rank's block + "
-                    "ONE grouped batch of NCCL send/recv (proposals + detections straight into rank 0's full-batch "
-                    "tensors, no packing), one step at a time, max over ranks (CUDA events); one_gpu_* = the same measurement of the whole batch on one GPU in this run "
+                    "(with the pack of proposals + detections into one send buffer captured inside it) + ONE dist.gather "
+                    "over NCCL + rank 0's unpack graph, one step at a time, max over ranks (CUDA events); one_gpu_* = the same measurement of the whole batch on one GPU in this run "
                     "(no gather needed); pipelined_* = several steps in flight on alternating streams"}
 
 

@@ -131,12 +131,15 @@ class MaskRCNNPostBackbone(object):
         return dict(proposals=props, box_feats=box_feats, dets=dets, mask_feats=mask_feats)
 
     # ------------------------------------------------------------------ CUDA-graphed, chunk-concurrent step
-    def capture(self, x, chunks=4):
+    def capture(self, x, chunks=4, epilogue=None):
         """Capture the device-resident step as ONE CUDA graph in which the batch is cut into `chunks` image blocks
         that run on their own streams (forked from / joined to the capturing stream).  Images are independent, so
         the latency-bound proposal / post-processing kernels of one block overlap the HBM-bound ROIAlign of
         another, and replaying the graph removes the per-launch host cost of the ~47 x chunks kernel launches.
-        `x` holds the STATIC input tensors: refill them in place between replays.  Returns a `GraphedStep`."""
+        `x` holds the STATIC input tensors: refill them in place between replays.  `epilogue(outs)` (optional) is
+        captured at the end of the step, on the capturing stream after the image blocks have joined -- e.g.
+        `sharding.GatherPlan.pack`, so that packing the send buffer costs graph nodes instead of eager launches.
+        Returns a `GraphedStep`."""
         from . import _native as nv
         from .sharding import image_block
         dev = x["shapes"].device
@@ -164,6 +167,8 @@ class MaskRCNNPostBackbone(object):
                     outs.append(self.flatten_outputs(self(cut(b, e))))
             for s in streams:
                 cur.wait_stream(s)
+            if epilogue is not None:
+                epilogue(outs)
             return outs
 
         side = torch.cuda.Stream(dev)
@@ -179,9 +184,12 @@ class MaskRCNNPostBackbone(object):
             outs = step()
         return GraphedStep(graph, outs, bounds, nv.kernel_launch_count() - l0)
 
-    def pipeline(self, x, chunks=4, depth=2):
-        """`depth` independent captures of the step over the same static inputs `x` -> StepPipeline."""
-        return StepPipeline([self.capture(x, chunks) for _ in range(max(1, int(depth)))], x["shapes"].device)
+    def pipeline(self, x, chunks=4, depth=2, epilogues=None):
+        """`depth` independent captures of the step over the same static inputs `x` -> StepPipeline
+        (`epilogues[i]`: the capture epilogue of step i)."""
+        depth = max(1, int(depth))
+        return StepPipeline([self.capture(x, chunks, epilogues[i] if epilogues else None) for i in range(depth)],
+                            x["shapes"].device)
 
     # ------------------------------------------------------------------ host-buffer step
     @staticmethod
@@ -194,6 +202,13 @@ class MaskRCNNPostBackbone(object):
         if out["mask_feats"] is not None:
             flat["mask_feats"] = out["mask_feats"]
         return flat
+
+    def gather_spec(self):
+        """{key: (per-image shape, dtype)} of the GATHER_KEYS outputs (for sharding.GatherPlan)."""
+        R, D = self.R, self.D
+        return {"proposal_boxes": ((R, 4), torch.float32), "proposal_logits": ((R,), torch.float32),
+                "proposal_valid": ((R,), torch.bool), "det_boxes": ((D, 4), torch.float32),
+                "det_scores": ((D,), torch.float32), "det_classes": ((D,), torch.int64), "det_valid": ((D,), torch.bool)}
 
     def run_host(self, x, device=None, chunk_images=2):
         """x: dict of HOST tensors (pinned for full PCIe rate).  Returns a dict of pinned host tensors

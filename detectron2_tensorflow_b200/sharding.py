@@ -134,3 +134,65 @@ def gather_blocks_to_rank0(blocks, layout, out=None, group=None):
         for w in dist.batch_isend_irecv(ops):
             w.wait()
     return out if rank == 0 else None
+
+
+class GatherPlan(object):
+    """Steady-state gather of the fixed-size per-image outputs to rank 0, set up once per graphed step:
+
+      pack()    copies this rank's block tensors into ONE persistent send buffer (call it inside the CUDA-graph
+                capture of the step: the copies then cost graph nodes, not eager launches);
+      gather()  ONE `dist.gather` of that buffer (NCCL: one grouped send/recv over NVLink; gloo on CPU);
+      unpack()  rank 0: copies every rank's blocks from the receive buffer into the full-batch tensors `out[key]`
+                ([N, ...], image order; capture it once as a CUDA graph and replay it).
+
+    Buffer layout: one block per key sized for the LONGEST image block, so the key offsets are the same on every
+    rank and uneven blocks only leave a tail unused.  spec = {key: (trailing shape, dtype)}."""
+
+    def __init__(self, spec, layout, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.layout = layout
+        self.spec = dict(spec)
+        self.begin = [lay[0][0] for lay in layout]
+        self.count = [lay[-1][1] - lay[0][0] for lay in layout]
+        longest = max(self.count)
+        self.offsets, off = {}, 0
+        for k, (shape, dtype) in self.spec.items():
+            per = torch.empty(0, dtype=dtype).element_size()
+            for d in shape:
+                per *= int(d)
+            self.offsets[k] = (off, per)
+            off += (longest * per + 255) // 256 * 256
+        self.nbytes = max(off, 256)
+        self.sendbuf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        self.recv = torch.zeros((self.world, self.nbytes), dtype=torch.uint8, device=device) if self.rank == 0 else None
+        n_total = layout[-1][-1][1]
+        self.out = {k: torch.zeros((n_total,) + tuple(shape), dtype=dtype, device=device)
+                    for k, (shape, dtype) in self.spec.items()} if self.rank == 0 else None
+
+    def _view(self, buf, key, n):
+        off, per = self.offsets[key]
+        shape, dtype = self.spec[key]
+        return buf[off:off + n * per].view(dtype).reshape((n,) + tuple(shape))
+
+    def pack(self, blocks):
+        """blocks[i] = dict of [e - b, ...] tensors for layout[rank][i]."""
+        n = self.count[self.rank]
+        for (b, e), blk in zip(self.layout[self.rank], blocks):
+            lb = b - self.begin[self.rank]
+            for k in self.spec:
+                self._view(self.sendbuf, k, n)[lb:lb + (e - b)].copy_(blk[k])
+
+    def gather(self):
+        dist.gather(self.sendbuf, list(self.recv.unbind(0)) if self.rank == 0 else None, dst=0, group=self.group)
+
+    def unpack(self):
+        if self.rank != 0:
+            return None
+        for r in range(self.world):
+            n = self.count[r]
+            if n:
+                for k in self.spec:
+                    self.out[k][self.begin[r]:self.begin[r] + n].copy_(self._view(self.recv[r], k, n))
+        return self.out

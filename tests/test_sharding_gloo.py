@@ -70,6 +70,42 @@ def test_two_rank_grouped_p2p_gather(tmp_path, n_images):
     assert open(path).read() == "ok"
 
 
+def _worker_plan(rank, world, port, n_images, result_path):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from detectron2_tensorflow_b200 import sharding
+    g = torch.Generator().manual_seed(11)
+    full = {"boxes": torch.randn((n_images, 6, 4), generator=g), "valid": torch.rand((n_images, 6), generator=g) > 0.5,
+            "classes": torch.randint(0, 80, (n_images, 6), generator=g, dtype=torch.int64)}
+    spec = {k: (tuple(v.shape[1:]), v.dtype) for k, v in full.items()}
+    layout = sharding.block_layout(n_images, world, chunks_of=lambda n: 2)
+    plan = sharding.GatherPlan(spec, layout, torch.device("cpu"))
+    for rep in range(2):  # the plan is persistent: a second step reuses every buffer
+        blocks = [{k: v[b:e] + (rep if v.dtype == torch.float32 else 0) for k, v in full.items()} for (b, e) in layout[rank]]
+        plan.pack(blocks)
+        plan.gather()
+        out = plan.unpack()
+        if rank == 0:
+            for k, v in full.items():
+                assert torch.equal(out[k], v + (rep if v.dtype == torch.float32 else 0)), k
+        else:
+            assert out is None
+    if rank == 0:
+        open(result_path, "w").write("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_images", [4, 5])
+def test_two_rank_gather_plan(tmp_path, n_images):
+    """GatherPlan (persistent send / receive buffers, one dist.gather, unpack into full-batch tensors)."""
+    path = str(tmp_path / "ok.txt")
+    port = 33500 + os.getpid() % 2000 + n_images
+    mp.spawn(_worker_plan, args=(2, port, n_images, path), nprocs=2, join=True)
+    assert open(path).read() == "ok"
+
+
 def test_block_layout_covers_batch():
     from detectron2_tensorflow_b200.sharding import block_layout
     for n in (1, 5, 16):
