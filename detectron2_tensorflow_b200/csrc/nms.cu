@@ -281,6 +281,97 @@ __global__ void __launch_bounds__(kColSweepThreads) nms_sweep_cols_kernel(const 
   if (threadIdx.x == 0) num_keep[seg] = kept;
 }
 
+// ------------------------------------------------------------------ A': small segments, everything in one launch
+// n <= kSmallMaxN boxes per segment with UNSORTED scores (the stand-alone batch_nms entry): one CTA per segment
+// orders the candidates (score desc, index asc; composite keys, bitonic sort in shared memory), gathers the boxes,
+// builds the suppression mask in shared memory (same filter + exact rule as nms_mask_kernel), sweeps it with the
+// column-owner warps and maps the kept positions back to input indices.  Replaces 7 launches (memset, prep, sort,
+// gather, mask, sweep, unmap): at these sizes the chain is pure launch latency.
+constexpr int kSmallMaxN = 1024;
+__global__ void __launch_bounds__(kColSweepThreads) nms_small_kernel(const float4* boxes, const float* scores,
+                                                                      const int32_t* counts, int n, int P, int W,
+                                                                      int max_out, float thr, int32_t* keep,
+                                                                      int32_t* num_keep) {
+  extern __shared__ __align__(16) unsigned char s_small[];
+  u64* s_keys = reinterpret_cast<u64*>(s_small);                       // [P]
+  float4* s_box = reinterpret_cast<float4*>(s_keys + P);               // [n] canonical (ymin, xmin, ymax, xmax)
+  float4* s_flt = s_box + n;                                           // [n] shrunk interval
+  float* s_area = reinterpret_cast<float*>(s_flt + n);                 // [n]
+  u64* s_mask = reinterpret_cast<u64*>(s_area + ((n + 1) & ~1));       // [n][W]
+  __shared__ int s_live;
+  const int seg = blockIdx.x, tid = threadIdx.x;
+  const int cnt = counts ? min(counts[seg], n) : n;
+  if (tid == 0) s_live = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int i = tid; i < P; i += kColSweepThreads) {
+    u64 key = 0;
+    if (i < cnt) {
+      const float s = scores[(size_t)seg * n + i];
+      if (s > __int_as_float(0xff800000)) {  // candidates = { i : score > -inf }
+        key = ((u64)float_to_key(s) << 32) | (u64)(0xffffffffu - (unsigned)i);
+        ++mine;
+      }
+    }
+    s_keys[i] = key;
+  }
+  if (mine) atomicAdd(&s_live, mine);
+  __syncthreads();
+  const int live = s_live;
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int p = tid; p < P / 2; p += kColSweepThreads) {
+        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+        const bool desc = ((i & k) == 0);
+        const u64 a = s_keys[i], b = s_keys[i | j];
+        if (desc ? (a < b) : (a > b)) { s_keys[i] = b; s_keys[i | j] = a; }
+      }
+      __syncthreads();
+    }
+  const float kf = thr * 0.999f;
+  for (int j = tid; j < live; j += kColSweepThreads) {
+    const unsigned idx = 0xffffffffu - (unsigned)s_keys[j];
+    const CBox c = canon(boxes[(size_t)seg * n + idx], true);
+    const FBox f = filter_box(c, kf);
+    s_box[j] = make_float4(c.ymin, c.xmin, c.ymax, c.xmax);
+    s_flt[j] = make_float4(f.ylo, f.xlo, f.yhi, f.xhi);
+    s_area[j] = c.area;
+  }
+  __syncthreads();
+  // mask words (row i, word w >= i / 64): one item = 64 pair tests
+  const int nb = (live + 63) >> 6;
+  for (int item = tid; item < live * nb; item += kColSweepThreads) {
+    const int i = item / nb, w = item - i * nb;
+    if (w < (i >> 6)) continue;
+    const float4 fi = s_flt[i], bi = s_box[i];
+    const float ai = s_area[i];
+    u64 bits = 0;
+    const int c1 = min(64, live - w * 64);
+    for (int c = (w == (i >> 6)) ? (i & 63) + 1 : 0; c < c1; ++c) {
+      const int j = w * 64 + c;
+      const float4 fj = s_flt[j];
+      if ((fj.x <= fi.z) && (fi.x <= fj.z) && (fj.y <= fi.w) && (fi.y <= fj.w)) {
+        const float4 bj = s_box[j];
+        const float ih = fmaxf(fminf(bi.z, bj.z) - fmaxf(bi.x, bj.x), 0.0f);
+        const float iw = fmaxf(fminf(bi.w, bj.w) - fmaxf(bi.y, bj.y), 0.0f);
+        if (iou_gt(ih * iw, s_area[j], ai, thr)) bits |= 1ull << c;
+      }
+    }
+    s_mask[(size_t)i * W + w] = bits;
+  }
+  __syncthreads();
+  int32_t* kp = keep + (size_t)seg * max_out;
+  const int kept = nms_sweep_columns<false, true>(live, W, max_out, s_mask, kp);
+  __syncthreads();
+  for (int q = tid; q < kept; q += kColSweepThreads) kp[q] = (int32_t)(0xffffffffu - (unsigned)s_keys[kp[q]]);
+  if (tid == 0) num_keep[seg] = kept;
+}
+
+size_t nms_small_smem(int n, int P) {
+  const size_t W = (n + 63) / 64;
+  return (size_t)P * 8 + (size_t)n * 32 + (size_t)((n + 1) & ~1) * 4 + (size_t)n * W * 8;
+}
+
 // ------------------------------------------------------------------ B: capped lazy sweep
 constexpr int kLazyThreads = 256;
 
@@ -358,6 +449,23 @@ size_t nms_sorted_workspace_bytes(int S, int n, int max_out) {
   if (S <= 0 || n <= 0 || use_lazy(n, max_out)) return 0;
   const size_t W = (n + 63) / 64;
   return ws_slice((size_t)S * W * 64 * W * sizeof(u64));
+}
+
+bool nms_small_applies(int n) { return n >= 1 && n <= kSmallMaxN; }
+
+int nms_small(const float* boxes, const float* scores, const int32_t* counts, int S, int n, int max_out, float thr,
+              int32_t* keep, int32_t* num_keep, cudaStream_t st) {
+  D2B_REQUIRE(thr >= 0.0f && thr <= 1.0f, "iou_threshold must be in [0, 1]");  // as tf.image.non_max_suppression
+  int P = 2;  // >= 2 keeps the float4 arrays behind the keys 16-byte aligned
+  while (P < n) P <<= 1;
+  const int W = (n + 63) / 64;
+  const size_t smem = nms_small_smem(n, P);
+  if (smem > 48 * 1024)
+    D2B_CUDA(cudaFuncSetAttribute(nms_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nms_small_kernel<<<S, kColSweepThreads, smem, st>>>(reinterpret_cast<const float4*>(boxes), scores, counts, n, P, W,
+                                                      max_out, thr, keep, num_keep);
+  D2B_LAUNCH_CHECK();
+  return D2B_OK;
 }
 
 bool nms_uses_bitmask(int n, int max_out) { return n > 0 && max_out > 0 && !use_lazy(n, max_out); }

@@ -25,11 +25,13 @@ constexpr int kColSweepMaxW = 64;  // n <= 4096
 
 // SMEM_OUT: instead of the global keep list, the kept boxes' positions and the order-preserving keys of their scores
 // (sc = the segment's scores in candidate order) go to shared memory (s_pos / s_key, max_out entries each).
-template <bool SMEM_OUT = false>
+// MASK_SMEM: the mask lives in shared memory (plain loads instead of ld.global.cg).
+template <bool SMEM_OUT = false, bool MASK_SMEM = false>
 __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, const unsigned long long* __restrict__ m,
                                                  int32_t* __restrict__ kp, const float* __restrict__ sc = nullptr,
                                                  uint32_t* s_key = nullptr, uint16_t* s_pos = nullptr) {
   typedef unsigned long long u64;
+  auto ldm = [&](size_t idx) -> u64 { return MASK_SMEM ? m[idx] : __ldcg(m + idx); };
   __shared__ volatile u64 s_keep[kColSweepMaxW];
   __shared__ volatile int s_flag[kColSweepMaxW];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -45,8 +47,8 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
     // the diagonal tile of this block (independent of everything before it): in flight during the wait below
     const int rows = min(64, cnt - word * 64);
     u64 dA = 0, dB = 0;
-    if (lane < rows) dA = __ldcg(m + (size_t)(word * 64 + lane) * W + word);
-    if (lane + 32 < rows) dB = __ldcg(m + (size_t)(word * 64 + 32 + lane) * W + word);
+    if (lane < rows) dA = ldm((size_t)(word * 64 + lane) * W + word);
+    if (lane + 32 < rows) dB = ldm((size_t)(word * 64 + 32 + lane) * W + word);
     float scA = 0.0f, scB = 0.0f;
     if (SMEM_OUT) {
       if (lane < rows) scA = __ldg(sc + word * 64 + lane);
@@ -57,8 +59,8 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
     for (int u = 0; u < kAhead; ++u) {
       pa[u] = 0; pb[u] = 0;
       if (u < word) {
-        pa[u] = __ldcg(m + (size_t)(u * 64 + lane) * W + word);
-        pb[u] = __ldcg(m + (size_t)(u * 64 + 32 + lane) * W + word);
+        pa[u] = ldm((size_t)(u * 64 + lane) * W + word);
+        pb[u] = ldm((size_t)(u * 64 + 32 + lane) * W + word);
       }
     }
     for (int b0 = 0; b0 < word && !capped; b0 += kAhead) {
@@ -70,8 +72,8 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
           const int nx = b + kAhead;  // refill this slot for the block kAhead further on
           if (nx < word) {
             D2B_BOUND(nx * 64 + 32 + lane, (long long)W * 64);
-            pa[u] = __ldcg(m + (size_t)(nx * 64 + lane) * W + word);
-            pb[u] = __ldcg(m + (size_t)(nx * 64 + 32 + lane) * W + word);
+            pa[u] = ldm((size_t)(nx * 64 + lane) * W + word);
+            pb[u] = ldm((size_t)(nx * 64 + 32 + lane) * W + word);
           }
           // only the owner of the next block polls back to back; warps further from their turn sleep in between, so
           // that the polling does not take issue slots and shared-memory bandwidth from the warp on the critical path
