@@ -53,6 +53,8 @@ struct RowState {
   unsigned cand_count; // SIGMOID rows with a cutoff: composites appended to the candidate list by pass 0
   unsigned compact;    // 1 => the candidate list holds every element that can matter: later passes read it
   unsigned redo;       // 1 => the sampled cutoff left fewer than k_r elements: pass 0 is repeated without a cutoff
+  unsigned cut_hi;     // key of the cutoff c itself (cut_key = key of c - margin)
+  unsigned hi_count;   // elements with logit >= c counted by pass 0: the exactness argument needs >= k_r of them
   unsigned done[kPasses];
 };
 
@@ -147,7 +149,7 @@ __global__ void topk_init(TopkArgs a, int rows, int32_t* seg_len, int32_t* out_c
   if (kr == 0) { s.active = 0; s.threshold = ~0ull; }            // take nothing
   else if (kr == a.d.row_len[g]) { s.active = 0; s.threshold = 0ull; }  // take the whole row
   else { s.active = 1; s.threshold = 0ull; }
-  s.cut_key = 0u; s.pre_done = 0u; s.cand_count = 0u; s.compact = 0u; s.redo = 0u;
+  s.cut_key = 0u; s.pre_done = 0u; s.cand_count = 0u; s.compact = 0u; s.redo = 0u; s.cut_hi = 0u; s.hi_count = 0u;
   a.state[r] = s;
   seg_len[r] = (int32_t)kr;
   if (out_counts) out_counts[r] = (int32_t)kr;
@@ -210,8 +212,13 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass, 
     // (measured: doing the same after pass 1 for rows without a cutoff does not pay at RPN sizes).
     const bool cand0 = (pass == 0 && cut != 0u);
     u64* cand = (cand0 && a.cand) ? a.cand + (size_t)row * kCandCap : nullptr;
+    // key(v) >= cut  <=>  v >= cut_f for cut != 0 (keys are monotone in the float order and NaN has key 0): one
+    // compare per element instead of the ~8-instruction key -- pass 0 of the RetinaNet rows was issue-bound on it
+    const float cut_f = key_to_float(cut);
+    const bool use_f = (cut != 0u) && (cut_f == cut_f);
+    const unsigned cut_hi = st->cut_hi;
     auto body = [&](float v, long long i, bool ok) {
-      bool in = ok && float_to_key(v) >= cut;
+      bool in = ok && (use_f ? (v >= cut_f) : (float_to_key(v) >= cut));
       unsigned digit = 0;
       if (in) {
         const u64 c = composite_of(value_key(v, transform), (unsigned)i);
@@ -219,6 +226,7 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass, 
           const unsigned slot = atomicAdd(&st->cand_count, 1u);
           if (slot < (unsigned)kCandCap) cand[slot] = c;
         }
+        if (cand0 && float_to_key(v) >= cut_hi) atomicAdd(&st->hi_count, 1u);  // (rare path: ~3 k_r elements per row)
         in = (pass == 0) || ((c >> hi_shift) == prefix);
         digit = (unsigned)(c >> shift) & mask;
       }
@@ -270,12 +278,15 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass, 
     __syncthreads();
   }
   const unsigned incl = scan[threadIdx.x], excl = incl - sum;
-  if (pass == 0 && cut != 0u && scan[kHistThreads - 1] < k_rem) {
-    // The cutoff came from a SAMPLE of the row (topk_prehist) and kept fewer than k_r elements: throw this
+  if (pass == 0 && cut != 0u &&
+      (scan[kHistThreads - 1] < k_rem || *reinterpret_cast<volatile unsigned*>(&st->hi_count) < k_rem)) {
+    // The cutoff came from a SAMPLE of the row (topk_prehist) and kept fewer than k_r elements -- or fewer than k_r
+    // of them reach the cutoff c itself, in which case the k-th largest logit may sit inside the margin below c,
+    // where the computed-sigmoid order of an excluded neighbour is not guaranteed (header comment): throw this
     // pass away and let the repeat launch histogram the whole row without a cutoff.
     for (int j = 0; j < kPer; ++j) gh[top - j] = 0u;
     if (threadIdx.x == 0) {
-      st->cut_key = 0u; st->cand_count = 0u; st->compact = 0u; st->done[0] = 0u; st->redo = 1u;
+      st->cut_key = 0u; st->cand_count = 0u; st->compact = 0u; st->done[0] = 0u; st->redo = 1u; st->hi_count = 0u;
     }
     return;
   }
@@ -368,8 +379,8 @@ __global__ void __launch_bounds__(kHistThreads) topk_collect(TopkArgs a, u64* ou
 constexpr int kPreBits = 9;
 constexpr int kPreBins = 1 << kPreBits;
 constexpr int kPreCopies = 16;       // [bin][lane & 15]: at most 2 lanes of a warp share a word
-constexpr int kPreSample = 2048;     // sampled elements per chunk of a long row (1/32 of a 64 K-element chunk)
-constexpr int kPreGroup = 4;         // chunks served by one CTA in sampled mode
+constexpr int kPreSample = 1024;     // sampled elements per chunk of a long row (1/64 of a 64 K-element chunk)
+constexpr int kPreGroup = 8;         // chunks served by one CTA in sampled mode
 constexpr int kPreMinChunks = 8;     // rows shorter than this many chunks are histogrammed in full
 __global__ void __launch_bounds__(kHistThreads) topk_prehist(TopkArgs a) {
   __shared__ unsigned sh[kPreBins * kPreCopies];
@@ -437,6 +448,7 @@ __global__ void __launch_bounds__(kHistThreads) topk_prehist(TopkArgs a) {
   if (c == c && c > -80.0f && c < 8.0f) {
     const float cm = c - (0.01f * fmaxf(1.0f, fabsf(c)) + 0.01f);
     cut = float_to_key(cm);
+    st->cut_hi = float_to_key(c);
   }
   st->cut_key = cut;
 }
