@@ -28,7 +28,9 @@ int topk_padded_k(int k);
 // Sort each of S segments of P (power of two) u64 keys in DESCENDING order in place.
 // seg_len (optional, device [S]): only the first seg_len[s] entries are live; the rest are
 // overwritten with 0 before sorting (0 sorts last).
-int sort_segments_desc(unsigned long long* keys, int S, int P, const int32_t* seg_len, cudaStream_t st);
+// skip (optional, device [S]): segments with skip[s] != 0 are left untouched.
+int sort_segments_desc(unsigned long long* keys, int S, int P, const int32_t* seg_len, cudaStream_t st,
+                       const int32_t* skip = nullptr);
 
 // ---------------------------------------------------------------- NMS (nms.cu)
 // Boxes of every segment are already in candidate order (score desc, index asc).

@@ -29,9 +29,11 @@ __device__ __forceinline__ int eff_len(const int32_t* seg_len, int seg, int P) {
   return e;
 }
 
-__global__ void __launch_bounds__(kSortThreads) sort_local(u64* keys, int P, int tile, const int32_t* seg_len) {
+__global__ void __launch_bounds__(kSortThreads) sort_local(u64* keys, int P, int tile, const int32_t* seg_len,
+                                                           const int32_t* skip) {
   extern __shared__ u64 s[];
   const int seg = blockIdx.y;
+  if (skip && skip[seg]) return;  // already in order
   const int t0 = blockIdx.x * tile;
   const int Pe = eff_len(seg_len, seg, P);
   if (t0 >= Pe) return;
@@ -54,8 +56,10 @@ __global__ void __launch_bounds__(kSortThreads) sort_local(u64* keys, int P, int
 }
 
 // Segments longer than one tile: one CTA finishes stages k = 2*tile .. Pe in global memory.
-__global__ void __launch_bounds__(kSortThreads) sort_big(u64* keys, int P, int tile, const int32_t* seg_len) {
+__global__ void __launch_bounds__(kSortThreads) sort_big(u64* keys, int P, int tile, const int32_t* seg_len,
+                                                         const int32_t* skip) {
   const int seg = blockIdx.x;
+  if (skip && skip[seg]) return;
   const int Pe = eff_len(seg_len, seg, P);
   if (Pe <= tile) return;
   u64* g = keys + (size_t)seg * P;
@@ -73,17 +77,18 @@ __global__ void __launch_bounds__(kSortThreads) sort_big(u64* keys, int P, int t
 
 }  // namespace
 
-int sort_segments_desc(unsigned long long* keys, int S, int P, const int32_t* seg_len, cudaStream_t st) {
+int sort_segments_desc(unsigned long long* keys, int S, int P, const int32_t* seg_len, cudaStream_t st,
+                       const int32_t* skip) {
   if (S <= 0 || P <= 1) return D2B_OK;
   D2B_REQUIRE((P & (P - 1)) == 0, "sort: P=%d is not a power of two", P);
   const int tile = P < kTile ? P : kTile;
   const size_t smem = (size_t)tile * sizeof(u64);
   if (smem > 48 * 1024)
     D2B_CUDA(cudaFuncSetAttribute(sort_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sort_local<<<dim3(P / tile, S), kSortThreads, smem, st>>>(keys, P, tile, seg_len);
+  sort_local<<<dim3(P / tile, S), kSortThreads, smem, st>>>(keys, P, tile, seg_len, skip);
   D2B_LAUNCH_CHECK();
   if (P > tile) {
-    sort_big<<<S, kSortThreads, 0, st>>>(keys, P, tile, seg_len);
+    sort_big<<<S, kSortThreads, 0, st>>>(keys, P, tile, seg_len, skip);
     D2B_LAUNCH_CHECK();
   }
   return D2B_OK;
