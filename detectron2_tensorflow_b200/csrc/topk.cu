@@ -79,12 +79,6 @@ __device__ __forceinline__ bool locate(const TopkArgs& a, int cta, int& g, int& 
   return img < a.d.rows_per_group;
 }
 
-// Rows topk_pass0_cut_kernel takes: active, cutoff set, row base 16-byte aligned and row length a multiple of 4 elements.
-__device__ __forceinline__ bool tma_row_ok(const TopkArgs& a, int g, int img) {
-  const long long len = a.d.row_len[g];
-  return (len & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.d.scores[g] + (size_t)img * len) & 15) == 0);
-}
-
 __device__ __forceinline__ uint32_t value_key(float x, int transform) {
   if (transform == D2B_TOPK_SIGMOID) x = d2b_sigmoidf(x);
   return float_to_key(x);
@@ -162,7 +156,7 @@ __global__ void topk_init(TopkArgs a, int rows, int32_t* seg_len, int32_t* out_c
 }
 
 constexpr int kCopies = 4;  // replicated pass-0 histograms (lane & 3) to spread same-bin atomics
-__global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass, int redo, int tma_pass0) {
+__global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass, int redo) {
   __shared__ unsigned sh[kCopies][kBins];
   __shared__ int s_last;
   int g, img, chunk;
@@ -171,10 +165,6 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass, 
   RowState* st = a.state + row;
   if (!st->active) return;  // uniform per CTA
   if (redo && !st->redo) return;  // the repeat launch only serves rows whose sampled cutoff failed
-  if (pass == 0 && !redo && tma_pass0 && st->cut_key != 0u && tma_row_ok(a, g, img)) {
-    const float cf = key_to_float(st->cut_key);
-    if (cf == cf) return;  // streamed by topk_pass0_cut_kernel
-  }
   const u64 prefix = st->prefix;
   const int shift = c_shift[pass], bits = c_bits[pass];
   const unsigned mask = (1u << bits) - 1u;
@@ -313,164 +303,6 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass, 
         st->k_rem = need;
         if (loc[j] == need || pass == kPasses - 1) {  // bucket taken whole: row resolved
           st->threshold = np << shift;
-          st->active = 0;
-        }
-        break;
-      }
-      above += loc[j];
-    }
-  }
-}
-
-// ---------------------------------------------------------------- pass 0 of rows with a sampled cutoff, TMA-staged
-// The one full read of the RetinaNet class logits (2 GB at N = 32) is a pure streaming scan: one compare per element,
-// a handful of elements above the cutoff.  With register-staged loads the kernel sat at 56 % of DRAM peak (ncu:
-// long-scoreboard stalls, 5 CTAs/SM by registers and the 32 KB histogram, ~40 KB in flight per SM).  Here the chunk
-// streams through a 4-stage ring of 16 KB shared-memory tiles filled by bulk async copies (cp.async.bulk, one
-// elected thread, mbarrier complete_tx): 64 KB in flight per CTA at no register cost, 3 CTAs per SM.
-constexpr int kTmaStageBytes = 16384;
-constexpr int kTmaStages = 4;
-constexpr int kTmaStageElems = kTmaStageBytes / 4;
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  unsigned spins = 0;
-  while (!done) {
-    if (++spins > (1u << 28)) __trap();  // a protocol bug fails the launch instead of hanging the device
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
-__global__ void __launch_bounds__(kHistThreads) topk_pass0_cut_kernel(TopkArgs a) {
-  extern __shared__ __align__(128) unsigned char s_ring[];  // [kTmaStages][kTmaStageBytes]
-  __shared__ __align__(8) unsigned long long s_bar[kTmaStages];
-  __shared__ int s_last;
-  int g, img, chunk;
-  if (!locate(a, blockIdx.x, g, img, chunk)) return;
-  const int row = img * a.d.G + g;
-  RowState* st = a.state + row;
-  const unsigned cut = st->cut_key;
-  if (!st->active || cut == 0u || !tma_row_ok(a, g, img)) return;  // left to topk_hist(pass 0)
-  const float cut_f = key_to_float(cut);
-  if (!(cut_f == cut_f)) return;
-  const unsigned cut_hi = st->cut_hi;
-  const int transform = a.d.transform;
-  const long long len = a.d.row_len[g];
-  const float* x = a.d.scores[g] + (size_t)img * len;
-  const long long beg = (long long)chunk * a.chunk_elems[g];
-  const long long end = beg + a.chunk_elems[g] < len ? beg + a.chunk_elems[g] : len;
-  const int nstage = (int)((end - beg + kTmaStageElems - 1) / kTmaStageElems);
-  unsigned* gh = a.hist + ((size_t)row * kPasses + 0) * kBins;
-  u64* cand = a.cand ? a.cand + (size_t)row * kCandCap : nullptr;
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    for (int s = 0; s < kTmaStages; ++s) mbar_init(smem_addr(&s_bar[s]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  auto issue = [&](int t) {  // thread 0: tile t of the chunk -> ring slot t % kTmaStages
-    const long long e0 = beg + (long long)t * kTmaStageElems;
-    const uint32_t bytes = (uint32_t)(((end - e0) < kTmaStageElems ? (end - e0) : kTmaStageElems) * 4);
-    const uint32_t bar = smem_addr(&s_bar[t % kTmaStages]);
-    mbar_expect_tx(bar, bytes);
-    bulk_load(smem_addr(s_ring + (size_t)(t % kTmaStages) * kTmaStageBytes), x + e0, bytes, bar);
-  };
-  if (tid == 0)
-    for (int t = 0; t < kTmaStages && t < nstage; ++t) issue(t);
-  for (int t = 0; t < nstage; ++t) {
-    const int slot = t % kTmaStages;
-    mbar_wait(smem_addr(&s_bar[slot]), (uint32_t)((t / kTmaStages) & 1));
-    const long long e0 = beg + (long long)t * kTmaStageElems;
-    const int n = (int)((end - e0) < kTmaStageElems ? (end - e0) : kTmaStageElems);  // multiple of 4
-    const float4* tile = reinterpret_cast<const float4*>(s_ring + (size_t)slot * kTmaStageBytes);
-#pragma unroll
-    for (int u = 0; u < kTmaStageElems / 4 / kHistThreads; ++u) {
-      const int vi = u * kHistThreads + tid;
-      if (vi * 4 < n) {
-        const float4 q = tile[vi];
-        const float vv[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (vv[c] >= cut_f) {  // rare: ~3 k_r elements of the row
-            const long long i = e0 + vi * 4 + c;
-            const u64 cmp = composite_of(value_key(vv[c], transform), (unsigned)i);
-            if (cand) {
-              const unsigned s2 = atomicAdd(&st->cand_count, 1u);
-              if (s2 < (unsigned)kCandCap) cand[s2] = cmp;
-            }
-            if (float_to_key(vv[c]) >= cut_hi) atomicAdd(&st->hi_count, 1u);
-            atomicAdd(gh + ((unsigned)(cmp >> c_shift[0]) & ((1u << c_bits[0]) - 1u)), 1u);
-          }
-        }
-      }
-    }
-    __syncthreads();  // every thread has read slot `slot`: it may be refilled
-    if (tid == 0 && t + kTmaStages < nstage) issue(t + kTmaStages);
-  }
-  // ---- row bookkeeping: identical to the tail of topk_hist(pass 0) for a cutoff row
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(&st->done[0], 1u) == (unsigned)a.chunks[g] - 1u);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (tid == 0 && a.cand)
-    st->compact = (*reinterpret_cast<volatile unsigned*>(&st->cand_count) <= (unsigned)kCandCap) ? 1u : 0u;
-  const unsigned k_rem = st->k_rem;
-  constexpr int kPer = kBins / kHistThreads;
-  unsigned loc[kPer];
-  unsigned sum = 0;
-  const int top = kBins - 1 - tid * kPer;
-#pragma unroll
-  for (int j = 0; j < kPer; ++j) {
-    loc[j] = __ldcg(gh + (top - j));
-    sum += loc[j];
-  }
-  __shared__ unsigned scan[kHistThreads];
-  scan[tid] = sum;
-  __syncthreads();
-  for (int off = 1; off < kHistThreads; off <<= 1) {
-    unsigned v = tid >= off ? scan[tid - off] : 0;
-    __syncthreads();
-    scan[tid] += v;
-    __syncthreads();
-  }
-  const unsigned incl = scan[tid], excl = incl - sum;
-  if (scan[kHistThreads - 1] < k_rem || *reinterpret_cast<volatile unsigned*>(&st->hi_count) < k_rem) {
-    for (int j = 0; j < kPer; ++j) gh[top - j] = 0u;  // sampled cutoff failed: the repeat launch scans without one
-    if (tid == 0) {
-      st->cut_key = 0u; st->cand_count = 0u; st->compact = 0u; st->done[0] = 0u; st->redo = 1u; st->hi_count = 0u;
-    }
-    return;
-  }
-  if (excl < k_rem && k_rem <= incl) {
-    unsigned above = excl;
-    for (int j = 0; j < kPer; ++j) {
-      if (above + loc[j] >= k_rem) {
-        const unsigned digit = (unsigned)(top - j);
-        const unsigned need = k_rem - above;
-        const u64 np = (u64)digit;
-        st->prefix = np;
-        st->k_rem = need;
-        if (loc[j] == need) {  // bucket taken whole: row resolved
-          st->threshold = np << c_shift[0];
           st->active = 0;
         }
         break;
@@ -709,21 +541,11 @@ int topk_run(const TopkDesc& d, unsigned long long* out_keys, float* out_values,
     b.state = a.state; b.hist = a.hist; b.prehist = a.prehist; b.cand = a.cand;
   }
   for (int p = 0; p < kPasses; ++p) {
-    if (p == 0) {
-      const int tma = d.transform == D2B_TOPK_SIGMOID ? 1 : 0;
-      if (tma) {  // rows with a sampled cutoff: the TMA-staged streaming scan
-        D2B_CUDA(cudaFuncSetAttribute(topk_pass0_cut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kTmaStages * kTmaStageBytes));
-        topk_pass0_cut_kernel<<<ctas, kHistThreads, kTmaStages * kTmaStageBytes, st>>>(a);
-        D2B_LAUNCH_CHECK();
-      }
-      topk_hist<<<ctas, kHistThreads, 0, st>>>(a, p, 0, tma);
-    } else {
-      topk_hist<<<ctas_b, kHistThreads, 0, st>>>(b, p, 0, 0);
-    }
+    if (p == 0) topk_hist<<<ctas, kHistThreads, 0, st>>>(a, p, 0);
+    else topk_hist<<<ctas_b, kHistThreads, 0, st>>>(b, p, 0);
     D2B_LAUNCH_CHECK();
     if (p == 0 && d.transform == D2B_TOPK_SIGMOID) {  // rows whose sampled cutoff failed the exact count
-      topk_hist<<<ctas_b, kHistThreads, 0, st>>>(b, 0, 1, 0);  // rare: coarse chunks are fine
+      topk_hist<<<ctas_b, kHistThreads, 0, st>>>(b, 0, 1);  // rare: coarse chunks are fine
       D2B_LAUNCH_CHECK();
     }
   }
