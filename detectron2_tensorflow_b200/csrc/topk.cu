@@ -97,19 +97,39 @@ __device__ __forceinline__ void for_each_elem(const float* x, long long beg, lon
   if (vec) {
     const long long nvec = (end - beg) >> 2;
     const float4* xv = reinterpret_cast<const float4*>(x + beg);
-    for (long long v0 = 0; v0 < nvec; v0 += (long long)kV * kHistThreads) {  // block-uniform trip count
-      float4 q[kV];
+    const long long step = (long long)kV * kHistThreads;
+    auto load = [&](float4* q, long long v0) {
 #pragma unroll
       for (int u = 0; u < kV; ++u) {
         const long long vi = v0 + (long long)u * kHistThreads + threadIdx.x;
         q[u] = vi < nvec ? (kStream ? __ldcs(xv + vi) : __ldg(xv + vi)) : make_float4(0, 0, 0, 0);
       }
+    };
+    auto process = [&](const float4* q, long long v0) {
 #pragma unroll
       for (int u = 0; u < kV; ++u) {
         const long long vi = v0 + (long long)u * kHistThreads + threadIdx.x;
         const bool ok = vi < nvec;
         const long long i = beg + 4 * vi;
         f(q[u].x, i, ok); f(q[u].y, i + 1, ok); f(q[u].z, i + 2, ok); f(q[u].w, i + 3, ok);
+      }
+    };
+    if (kStream) {
+      // streaming scan (the row is read once, one compare per element): the loads of trip t+1 are in flight while
+      // trip t is processed -- 2 kV vectors per thread outstanding instead of kV, and never a load-free phase
+      float4 cur[kV], nxt[kV];
+      if (nvec > 0) load(cur, 0);
+      for (long long v0 = 0; v0 < nvec; v0 += step) {  // block-uniform trip count
+        if (v0 + step < nvec) load(nxt, v0 + step);
+        process(cur, v0);
+#pragma unroll
+        for (int u = 0; u < kV; ++u) cur[u] = nxt[u];
+      }
+    } else {
+      for (long long v0 = 0; v0 < nvec; v0 += step) {  // block-uniform trip count
+        float4 q[kV];
+        load(q, v0);
+        process(q, v0);
       }
     }
     const long long t0 = beg + 4 * nvec;  // < 4 leftover elements
