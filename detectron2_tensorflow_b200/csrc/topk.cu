@@ -356,8 +356,12 @@ __global__ void __launch_bounds__(kHistThreads, 8) topk_scan_cut_kernel(TopkArgs
   u64* cand = a.cand ? a.cand + (size_t)row * kCandCap : nullptr;
   const int sh0 = c_shift[0];
   const unsigned mk0 = (1u << c_bits[0]) - 1u;
-  for_each_elem<4, true>(x, beg, end, [&](float v, long long i, bool ok) {
-    if (ok && v >= cut_f) {
+  // the rare path (~3 k_r elements per row), ONE copy of it: the element is re-read by index (an L1/L2 hit) so that
+  // the hot loop needs no per-element code -- with the slow path inlined per element the loop was 25 KB of SASS
+  // and the scan stalled on instruction fetch
+  auto slow = [&](long long i) {
+    const float v = __ldg(x + i);
+    if (v >= cut_f) {
       const u64 c = composite_of(value_key(v, transform), (unsigned)i);
       if (cand) {
         const unsigned slot = atomicAdd(&st->cand_count, 1u);
@@ -366,7 +370,37 @@ __global__ void __launch_bounds__(kHistThreads, 8) topk_scan_cut_kernel(TopkArgs
       if (float_to_key(v) >= cut_hi) atomicAdd(&st->hi_count, 1u);
       atomicAdd(gh + ((unsigned)(c >> sh0) & mk0), 1u);
     }
-  });
+  };
+  if ((reinterpret_cast<uintptr_t>(x + beg) & 15) == 0) {
+    const long long nvec = (end - beg) >> 2;
+    const float4* xv = reinterpret_cast<const float4*>(x + beg);
+    constexpr int kV = 4;
+    const long long step = (long long)kV * kHistThreads;
+    for (long long v0 = 0; v0 < nvec; v0 += step) {
+      float4 q[kV];
+#pragma unroll
+      for (int u = 0; u < kV; ++u) {
+        const long long vi = v0 + (long long)u * kHistThreads + threadIdx.x;
+        q[u] = vi < nvec ? __ldcs(xv + vi) : make_float4(0, 0, 0, 0);
+      }
+      unsigned hit = 0;  // bit u: some element of vector u reaches the cutoff (max ignores NaN, which never does)
+#pragma unroll
+      for (int u = 0; u < kV; ++u) {
+        const long long vi = v0 + (long long)u * kHistThreads + threadIdx.x;
+        const float m = fmaxf(fmaxf(q[u].x, q[u].y), fmaxf(q[u].z, q[u].w));
+        hit |= (vi < nvec && m >= cut_f) ? (1u << u) : 0u;
+      }
+      while (hit) {  // rare
+        const int u = __ffs(hit) - 1;
+        hit &= hit - 1;
+        const long long i = beg + 4 * (v0 + (long long)u * kHistThreads + threadIdx.x);
+        for (int c = 0; c < 4; ++c) slow(i + c);
+      }
+    }
+    for (long long i = beg + 4 * nvec + threadIdx.x; i < end; i += kHistThreads) slow(i);  // < 4 leftover elements
+  } else {
+    for (long long i = beg + threadIdx.x; i < end; i += kHistThreads) slow(i);  // unaligned rows: plain scalar scan
+  }
   __syncthreads();
   pass_tail(a, st, gh, 0, (unsigned)a.chunks[g], false, cut, 0ull, c_shift[0], c_bits[0], 0);
 }
