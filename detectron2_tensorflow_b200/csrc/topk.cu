@@ -546,6 +546,132 @@ __global__ void __launch_bounds__(kHistThreads) topk_prehist(TopkArgs a) {
   st->cut_key = cut;
 }
 
+// SIGMOID rows after pass 0: ONE CTA per row runs the remaining radix passes, the collect and (k <= kFinSortMax) the
+// sort of the winners.  A row's pass 0 normally leaves a complete candidate list (every element that can matter:
+// a few thousand composites), and each later pass over such a list was one CTA's work anyway -- five launches of
+// mostly idle grids plus collect plus sort (82 us of launch latency at N = 32).  Rows WITHOUT a complete list (no
+// usable cutoff: k-th logit outside (-80, 8); or more than kCandCap elements above the cutoff) are finished by the
+// same CTA re-reading the row: correct, but serial -- such rows do not occur with detector outputs.
+constexpr int kFinThreads = 1024;
+constexpr int kFinSortMax = 2048;
+__global__ void __launch_bounds__(kFinThreads) topk_finish_kernel(TopkArgs a, u64* out_keys, int32_t* sorted_flag) {
+  __shared__ unsigned sh[kBins];
+  __shared__ unsigned s_warp[kFinThreads / 32];
+  __shared__ unsigned s_sel[3];  // digit, need, bucket
+  __shared__ unsigned s_cnt;
+  __shared__ u64 s_out[kFinSortMax];
+  const int row = blockIdx.x;
+  const int g = row % a.d.G, img = row / a.d.G;
+  RowState* st = a.state + row;
+  const unsigned kr = st->k_r;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  u64* out = out_keys + (size_t)row * a.P;
+  const bool sort_here = a.P <= kFinSortMax;
+  if (tid == 0 && sorted_flag) sorted_flag[row] = sort_here ? 1 : 0;
+  if (kr == 0) {
+    for (int i = tid; i < a.P; i += kFinThreads) out[i] = 0ull;
+    return;
+  }
+  const bool compact = st->compact != 0;
+  const unsigned n_list = st->cand_count;
+  const u64* cand = a.cand + (size_t)row * kCandCap;
+  const long long len = a.d.row_len[g];
+  const float* x = a.d.scores[g] + (size_t)img * len;
+  const unsigned cut = st->cut_key;
+  const int transform = a.d.transform;
+  // f(composite) for every element of the row that can still matter
+  auto for_each_comp = [&](auto f) {
+    if (compact) {
+      for (unsigned j0 = 0; j0 < n_list; j0 += 4 * kFinThreads) {
+        u64 c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const unsigned j = j0 + u * kFinThreads + tid;
+          c[u] = j < n_list ? __ldcg(cand + j) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j0 + u * kFinThreads + tid < n_list) f(c[u]);
+      }
+    } else {
+      for (long long i = tid; i < len; i += kFinThreads) {
+        const float v = __ldg(x + i);
+        if (float_to_key(v) >= cut) f(composite_of(value_key(v, transform), (unsigned)i));
+      }
+    }
+  };
+  u64 prefix = st->prefix, thr = st->threshold;
+  unsigned k_rem = st->k_rem;
+  bool active = st->active != 0;
+  for (int pass = 1; pass < kPasses && active; ++pass) {
+    const int shift = c_shift[pass], bits = c_bits[pass];
+    const unsigned mask = (1u << bits) - 1u;
+    const int hi_shift = shift + bits;
+    for (int i = tid; i < kBins; i += kFinThreads) sh[i] = 0;
+    __syncthreads();
+    for_each_comp([&](u64 c) {
+      if ((c >> hi_shift) == prefix) atomicAdd(&sh[(unsigned)(c >> shift) & mask], 1u);
+    });
+    __syncthreads();
+    // thread t owns bins 2047 - 2t and 2046 - 2t: inclusive scan from the top bin down
+    const unsigned b0 = sh[kBins - 1 - 2 * tid], b1 = sh[kBins - 2 - 2 * tid];
+    unsigned inc = b0 + b1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    unsigned before = 0;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    const unsigned incl = before + inc, excl = incl - (b0 + b1);
+    if (excl < k_rem && k_rem <= incl) {
+      if (excl + b0 >= k_rem) { s_sel[0] = kBins - 1 - 2 * tid; s_sel[1] = k_rem - excl; s_sel[2] = b0; }
+      else { s_sel[0] = kBins - 2 - 2 * tid; s_sel[1] = k_rem - excl - b0; s_sel[2] = b1; }
+    }
+    __syncthreads();
+    prefix = (prefix << bits) | s_sel[0];
+    k_rem = s_sel[1];
+    if (s_sel[2] == k_rem || pass == kPasses - 1) {  // bucket taken whole: row resolved
+      thr = prefix << shift;
+      active = false;
+    }
+    __syncthreads();
+  }
+  // collect the k_r composites >= thr
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  u64* dst = sort_here ? s_out : out;
+  for_each_comp([&](u64 c) {
+    if (c >= thr) {
+      const unsigned slot = atomicAdd(&s_cnt, 1u);
+      D2B_BOUND(slot, kr);
+      if (slot < (unsigned)a.P) dst[slot] = c;
+    }
+  });
+  __syncthreads();
+  if (!sort_here) {  // the segment sort runs as a separate launch
+    for (int i = (int)kr + tid; i < a.P; i += kFinThreads) out[i] = 0ull;
+    return;
+  }
+  int Pe = 1;
+  while (Pe < (int)kr) Pe <<= 1;
+  for (int i = (int)kr + tid; i < Pe; i += kFinThreads) s_out[i] = 0ull;
+  __syncthreads();
+  for (int k = 2; k <= Pe; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int p = tid; p < Pe / 2; p += kFinThreads) {
+        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+        const bool desc = ((i & k) == 0);
+        const u64 va = s_out[i], vb = s_out[i | j];
+        if (desc ? (va < vb) : (va > vb)) { s_out[i] = vb; s_out[i | j] = va; }
+      }
+      __syncthreads();
+    }
+  for (int i = tid; i < a.P; i += kFinThreads) out[i] = i < (int)kr ? s_out[i] : 0ull;
+}
+
 __global__ void topk_emit(TopkArgs a, const u64* keys, float* out_values, int32_t* out_indices,
                           int32_t* out_counts, int rows) {
   const int row = blockIdx.y;
@@ -633,27 +759,33 @@ int topk_run(const TopkDesc& d, unsigned long long* out_keys, float* out_values,
     ctas_b = fill_args(d, b, 16);
     b.state = a.state; b.hist = a.hist; b.prehist = a.prehist; b.cand = a.cand;
   }
-  for (int p = 0; p < kPasses; ++p) {
-    if (p == 0 && d.transform == D2B_TOPK_SIGMOID) {
-      // rows with a cutoff (normally all of them): the lean streaming scan; the rest: generic pass 0 on the coarse grid
-      topk_scan_cut_kernel<<<ctas, kHistThreads, 0, st>>>(a);
-      D2B_LAUNCH_CHECK();
-      topk_hist<<<ctas_b, kHistThreads, 0, st>>>(b, 0, 0, 1);
-    } else if (p == 0) {
-      topk_hist<<<ctas, kHistThreads, 0, st>>>(a, p, 0, 0);
-    } else {
-      topk_hist<<<ctas_b, kHistThreads, 0, st>>>(b, p, 0, 0);
-    }
+  int rc;
+  if (d.transform == D2B_TOPK_SIGMOID) {
+    // pass 0: rows with a cutoff (normally all of them) by the lean streaming scan, the rest -- and the rows whose
+    // sampled cutoff failed the exact count -- by the generic kernel on the coarse grid; then ONE CTA per row finishes
+    topk_scan_cut_kernel<<<ctas, kHistThreads, 0, st>>>(a);
     D2B_LAUNCH_CHECK();
-    if (p == 0 && d.transform == D2B_TOPK_SIGMOID) {  // rows whose sampled cutoff failed the exact count
-      topk_hist<<<ctas_b, kHistThreads, 0, st>>>(b, 0, 1, 0);  // rare: coarse chunks are fine
+    topk_hist<<<ctas_b, kHistThreads, 0, st>>>(b, 0, 0, 1);
+    D2B_LAUNCH_CHECK();
+    topk_hist<<<ctas_b, kHistThreads, 0, st>>>(b, 0, 1, 0);
+    D2B_LAUNCH_CHECK();
+    topk_finish_kernel<<<rows, kFinThreads, 0, st>>>(b, out_keys, nullptr);
+    D2B_LAUNCH_CHECK();
+    if (a.P > kFinSortMax) {
+      rc = sort_segments_desc(out_keys, rows, a.P, seg_len, st);
+      if (rc != D2B_OK) return rc;
+    }
+  } else {
+    for (int p = 0; p < kPasses; ++p) {
+      if (p == 0) topk_hist<<<ctas, kHistThreads, 0, st>>>(a, p, 0, 0);
+      else topk_hist<<<ctas_b, kHistThreads, 0, st>>>(b, p, 0, 0);
       D2B_LAUNCH_CHECK();
     }
+    topk_collect<<<ctas_b, kHistThreads, 0, st>>>(b, out_keys);
+    D2B_LAUNCH_CHECK();
+    rc = sort_segments_desc(out_keys, rows, a.P, seg_len, st);
+    if (rc != D2B_OK) return rc;
   }
-  topk_collect<<<ctas_b, kHistThreads, 0, st>>>(b, out_keys);
-  D2B_LAUNCH_CHECK();
-  int rc = sort_segments_desc(out_keys, rows, a.P, seg_len, st);
-  if (rc != D2B_OK) return rc;
   if (out_values || out_indices) {
     const dim3 grid((d.k + 255) / 256, rows);
     topk_emit<<<grid, 256, 0, st>>>(a, out_keys, out_values, out_indices, out_counts, rows);
