@@ -451,6 +451,8 @@ size_t nms_sorted_workspace_bytes(int S, int n, int max_out) {
   return ws_slice((size_t)S * W * 64 * W * sizeof(u64));
 }
 
+bool nms_lazy_applies(int n, int max_out) { return n > 0 && max_out > 0 && use_lazy(n, max_out); }
+
 bool nms_small_applies(int n) { return n >= 1 && n <= kSmallMaxN; }
 
 int nms_small(const float* boxes, const float* scores, const int32_t* counts, int S, int n, int max_out, float thr,

@@ -219,6 +219,133 @@ __global__ void det_emit_kernel(F f, const u64* keys, int P, const int32_t* keep
   if (out_roi) out_roi[o] = roi;
 }
 
+// Gather + capped lazy NMS + emit in ONE launch (one CTA per image): the tail of Fast R-CNN / RetinaNet / YOLOv4
+// post-processing when the cap is much smaller than the candidate list (top-100 of thousands).  Candidates are
+// visited 64 at a time in (score desc, index asc) order; only the visited blocks are fetched (box gather through
+// the head's Fetch functor + fp32 class offset), tested against the kept list and among themselves (exact TF IoU
+// rule), and resolved by one warp with the same fixpoint as the bitmask sweep; the loop stops at the cap.  Replaces
+// det_gather (all candidates) + nms_lazy + det_emit.
+constexpr int kTailThreads = 256;
+template <typename F, typename TCls>
+__global__ void __launch_bounds__(kTailThreads) det_tail_kernel(F f, const u64* keys, const int32_t* count,
+                                                                const float* max_coord, const unsigned* maxkey, int P,
+                                                                int stride, int agnostic, int max_out, float thr,
+                                                                float4* out_boxes, float* out_scores, TCls* out_classes,
+                                                                uint8_t* out_valid, int32_t* out_roi, int32_t* out_num,
+                                                                u64* nms_in_total) {
+  extern __shared__ __align__(16) unsigned char s_tail[];
+  float4* s_kept = reinterpret_cast<float4*>(s_tail);          // [max_out] offset boxes of the kept candidates
+  int32_t* s_keptj = reinterpret_cast<int32_t*>(s_kept + max_out);  // [max_out] their positions in the sorted list
+  __shared__ float4 s_blk[64];
+  __shared__ u64 s_diag[64];
+  __shared__ unsigned s_dead[2];
+  __shared__ int s_kept_n;
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int cnt = min(count[n], stride);
+  if (tid == 0) {
+    s_kept_n = 0;
+    if (nms_in_total) atomicAdd(nms_in_total, (u64)cnt);
+  }
+  float off1 = 0.0f;  // fast_rcnn.py:141-143 / retinanet.py:349-351: fp32 class offset on every coordinate
+  if (!agnostic) off1 = (max_coord ? max_coord[n] : key_to_float(maxkey[n])) + 1.0f;
+  __syncthreads();
+  const int r = tid & 63, q = tid >> 6;  // candidate r of the block, quarter q of the kept list / columns
+  for (int b0 = 0; b0 < cnt; b0 += 64) {
+    const int kept = s_kept_n;
+    if (kept >= max_out) break;
+    const int rows = min(64, cnt - b0);
+    if (tid < 64) {
+      float4 box = make_float4(0, 0, 0, 0);
+      if (tid < rows) {
+        float score; int cls, roi;
+        f.get(n, key_index(keys[(size_t)n * P + b0 + tid]), box, score, cls, roi);
+        if (!agnostic) {
+          const float off = (float)cls * off1;
+          box.x = box.x + off; box.y = box.y + off; box.z = box.z + off; box.w = box.w + off;
+        }
+      }
+      s_blk[tid] = box;
+      s_diag[tid] = 0;
+    }
+    if (tid < 2) s_dead[tid] = 0;
+    __syncthreads();
+    const float4 bi = s_blk[r];
+    bool dead = false;
+    if (r < rows)
+      for (int j = q; j < kept; j += kTailThreads / 64)
+        if (d2b_iou(bi, s_kept[j]) > thr) { dead = true; break; }
+    if (dead) atomicOr(&s_dead[r >> 5], 1u << (r & 31));
+    u64 bits = 0;  // bit c of row r: box r suppresses box c (c > r); quarter q covers 16 columns
+    if (r < rows)
+      for (int c = max(q * 16, r + 1); c < min(q * 16 + 16, rows); ++c)
+        if (d2b_iou(bi, s_blk[c]) > thr) bits |= 1ull << c;
+    if (bits) atomicOr(&s_diag[r], bits);
+    __syncthreads();
+    if (tid < 32) {  // warp 0: greedy resolve of the 64 candidates as a fixpoint (same result as the serial scan)
+      const u64 dA = s_diag[lane], dB = s_diag[lane + 32];
+      u64 rem = ((u64)s_dead[1] << 32) | (u64)s_dead[0];
+      if (rows < 64) rem |= ~0ull << rows;
+      const u64 bitA = 1ull << lane, bitB = 1ull << (lane + 32);
+      u64 U = ~rem, K = 0;
+      while (U) {  // warp-uniform
+        const u64 sel = ((U & bitA) ? dA : 0ull) | ((U & bitB) ? dB : 0ull);
+        const u64 blocked = ((u64)__reduce_or_sync(0xffffffffu, (unsigned)(sel >> 32)) << 32) |
+                            __reduce_or_sync(0xffffffffu, (unsigned)sel);
+        const u64 nk = U & ~blocked;  // never empty: the first undecided candidate cannot be blocked
+        K |= nk;
+        U &= ~nk;
+        if (!U) break;
+        const u64 s2 = ((nk & bitA) ? dA : 0ull) | ((nk & bitB) ? dB : 0ull);
+        U &= ~(((u64)__reduce_or_sync(0xffffffffu, (unsigned)(s2 >> 32)) << 32) |
+               __reduce_or_sync(0xffffffffu, (unsigned)s2));
+      }
+      int c = __popcll(K);
+      const int left = max_out - kept;
+      while (c > left) {  // cap reached inside this block: keep only the first `left`
+        K &= ~(1ull << (63 - __clzll((long long)K)));
+        --c;
+      }
+      if (K & bitA) { const int s = kept + __popcll(K & (bitA - 1ull)); s_kept[s] = s_blk[lane]; s_keptj[s] = b0 + lane; }
+      if (K & bitB) { const int s = kept + __popcll(K & (bitB - 1ull)); s_kept[s] = s_blk[lane + 32]; s_keptj[s] = b0 + lane + 32; }
+      if (lane == 0) s_kept_n = kept + c;
+    }
+    __syncthreads();
+  }
+  const int nk = s_kept_n;
+  if (tid == 0 && out_num) out_num[n] = nk;
+  for (int qo = tid; qo < max_out; qo += kTailThreads) {
+    float4 box = make_float4(0, 0, 0, 0);
+    float score = 0.0f;
+    int cls = 0, roi = -1;
+    uint8_t valid = 0;
+    if (qo < nk) {
+      f.get(n, key_index(keys[(size_t)n * P + s_keptj[qo]]), box, score, cls, roi);
+      valid = 1;
+    }
+    const size_t o = (size_t)n * max_out + qo;
+    out_boxes[o] = box;
+    out_scores[o] = score;
+    out_classes[o] = (TCls)cls;
+    out_valid[o] = valid;
+    if (out_roi) out_roi[o] = roi;
+  }
+}
+
+template <typename F, typename TCls>
+int det_tail(F f, const u64* keys, const int32_t* count, const float* max_coord, const unsigned* maxkey, int P, int stride,
+             int agnostic, int N, int max_out, float thr, float4* out_boxes, float* out_scores, TCls* out_classes,
+             uint8_t* out_valid, int32_t* out_roi, int32_t* out_num, u64* nms_in_total, cudaStream_t st) {
+  D2B_REQUIRE(thr >= 0.0f && thr <= 1.0f, "iou_threshold must be in [0, 1]");  // as tf.image.non_max_suppression
+  const size_t smem = (size_t)max_out * (sizeof(float4) + sizeof(int32_t));
+  if (smem > 40 * 1024)
+    D2B_CUDA(cudaFuncSetAttribute(det_tail_kernel<F, TCls>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  det_tail_kernel<F, TCls><<<N, kTailThreads, smem, st>>>(f, keys, count, max_coord, maxkey, P, stride, agnostic, max_out,
+                                                          thr, out_boxes, out_scores, out_classes, out_valid, out_roi,
+                                                          out_num, nms_in_total);
+  D2B_LAUNCH_CHECK();
+  return D2B_OK;
+}
+
 // ------------------------------------------------------------------ YOLOv4 front (yolov4_outputs.py:352-360)
 struct YoloFetch {
   const float4* boxes;      // [N, n]
@@ -618,6 +745,10 @@ extern "C" int d2b_fast_rcnn_postprocess(const d2b_fast_rcnn_params* p, void* wo
   if (rc != D2B_OK) return rc;
   FrcnnFetch f{reinterpret_cast<const float4*>(p->boxes), p->scores, slot_map, p->image_shapes, p->rmax,
                p->num_bbox_reg_classes, p->num_classes};
+  if (nms_lazy_applies(pl.stride, T))  // cap << candidates: gather + NMS + emit in one launch
+    return det_tail<FrcnnFetch, int64_t>(f, keys, count, max_coord, nullptr, pl.P, pl.stride, p->nms_cls_agnostic ? 1 : 0, N,
+                                         T, p->nms_thresh, reinterpret_cast<float4*>(p->out_boxes), p->out_scores,
+                                         p->out_classes, p->out_valid, p->out_roi_index, p->out_num, nms_in, st);
   det_gather_kernel<FrcnnFetch><<<dim3((pl.stride + 255) / 256, N), 256, 0, st>>>(
       f, keys, count, max_coord, pl.P, pl.stride, p->nms_cls_agnostic ? 1 : 0, nms_boxes, nms_in);
   D2B_LAUNCH_CHECK();
@@ -747,8 +878,6 @@ extern "C" int d2b_retinanet_postprocess(const d2b_retinanet_params* p, void* wo
   retina_decode_par_kernel<<<dim3((a.k + kRetThreads - 1) / kRetThreads, a.L, N), kRetThreads, 0, st>>>(
       a, keys, lvl_off, cb, cs, cc, keys3, maxkey);
   D2B_LAUNCH_CHECK();
-  retina_maxcoord_kernel<<<(N + 255) / 256, 256, 0, st>>>(maxkey, N, max_coord);
-  D2B_LAUNCH_CHECK();
   const size_t merge_smem = (size_t)a.stride * sizeof(u64);
   if (merge_smem <= 96 * 1024) {  // the per-level runs are sorted already: merge by rank instead of sorting
     if (merge_smem > 48 * 1024)  // per device / context: set on every call (cheap), as nms.cu and sort.cu do
@@ -762,6 +891,12 @@ extern "C" int d2b_retinanet_postprocess(const d2b_retinanet_params* p, void* wo
     if (rc != D2B_OK) return rc;
   }
   RetinaFetch f{cb, cs, cc, a.stride};
+  if (nms_lazy_applies(a.stride, T))
+    return det_tail<RetinaFetch, int32_t>(f, keys3, count, nullptr, maxkey, a.P3, a.stride, 0, N, T, p->nms_thresh,
+                                          reinterpret_cast<float4*>(p->out_boxes), p->out_scores, p->out_classes,
+                                          p->out_valid, nullptr, p->out_num, nms_in, st);
+  retina_maxcoord_kernel<<<(N + 255) / 256, 256, 0, st>>>(maxkey, N, max_coord);
+  D2B_LAUNCH_CHECK();
   det_gather_kernel<RetinaFetch><<<dim3((a.stride + 255) / 256, N), 256, 0, st>>>(f, keys3, count, max_coord, a.P3,
                                                                                     a.stride, 0, nms_boxes, nms_in);
   D2B_LAUNCH_CHECK();
@@ -844,6 +979,10 @@ extern "C" int d2b_yolo_postprocess(const d2b_yolo_params* p, void* workspace, s
   rc = sort_segments_desc(keys, N, pl.P, count, st);
   if (rc != D2B_OK) return rc;
   YoloFetch f{reinterpret_cast<const float4*>(p->boxes), cscore, ccls, stride};
+  if (nms_lazy_applies(stride, T))
+    return det_tail<YoloFetch, int64_t>(f, keys, count, nullptr, nullptr, pl.P, stride, 1, N, T, p->nms_thresh,
+                                        reinterpret_cast<float4*>(p->out_boxes), p->out_scores, p->out_classes,
+                                        p->out_valid, nullptr, p->out_num, nms_in, st);
   det_gather_kernel<YoloFetch><<<dim3((stride + 255) / 256, N), 256, 0, st>>>(f, keys, count, nullptr, pl.P, stride,
                                                                                1, nms_boxes, nms_in);
   D2B_LAUNCH_CHECK();
