@@ -338,26 +338,32 @@ __global__ void __launch_bounds__(kColSweepThreads) nms_small_kernel(const float
     s_area[j] = c.area;
   }
   __syncthreads();
-  // mask words (row i, word w >= i / 64): one item = 64 pair tests
+  // mask words (row i, word w >= i / 64).  A warp works on 32 consecutive rows against the SAME column word, so the
+  // column records are broadcast shared-memory loads (rows across lanes against different words would hit one bank)
   const int nb = (live + 63) >> 6;
-  for (int item = tid; item < live * nb; item += kColSweepThreads) {
-    const int i = item / nb, w = item - i * nb;
-    if (w < (i >> 6)) continue;
-    const float4 fi = s_flt[i], bi = s_box[i];
-    const float ai = s_area[i];
-    u64 bits = 0;
+  for (int w = 0; w < nb; ++w) {
     const int c1 = min(64, live - w * 64);
-    for (int c = (w == (i >> 6)) ? (i & 63) + 1 : 0; c < c1; ++c) {
-      const int j = w * 64 + c;
-      const float4 fj = s_flt[j];
-      if ((fj.x <= fi.z) && (fi.x <= fj.z) && (fj.y <= fi.w) && (fi.y <= fj.w)) {
-        const float4 bj = s_box[j];
-        const float ih = fmaxf(fminf(bi.z, bj.z) - fmaxf(bi.x, bj.x), 0.0f);
-        const float iw = fmaxf(fminf(bi.w, bj.w) - fmaxf(bi.y, bj.y), 0.0f);
-        if (iou_gt(ih * iw, s_area[j], ai, thr)) bits |= 1ull << c;
+    const int row_end = min(live, (w + 1) * 64);  // rows of later blocks have no bits in word w
+    for (int i = tid; i < row_end; i += kColSweepThreads) {
+      const float4 fi = s_flt[i], bi = s_box[i];
+      const float ai = s_area[i];
+      u64 bits = 0;
+      const int cbeg = (w == (i >> 6)) ? (i & 63) + 1 : 0;
+#pragma unroll 8
+      for (int c = 0; c < 64; ++c) {
+        if (c >= cbeg && c < c1) {
+          const int j = w * 64 + c;
+          const float4 fj = s_flt[j];
+          if ((fj.x <= fi.z) && (fi.x <= fj.z) && (fj.y <= fi.w) && (fi.y <= fj.w)) {
+            const float4 bj = s_box[j];
+            const float ih = fmaxf(fminf(bi.z, bj.z) - fmaxf(bi.x, bj.x), 0.0f);
+            const float iw = fmaxf(fminf(bi.w, bj.w) - fmaxf(bi.y, bj.y), 0.0f);
+            if (iou_gt(ih * iw, s_area[j], ai, thr)) bits |= 1ull << c;
+          }
+        }
       }
+      s_mask[(size_t)i * W + w] = bits;
     }
-    s_mask[(size_t)i * W + w] = bits;
   }
   __syncthreads();
   int32_t* kp = keep + (size_t)seg * max_out;
