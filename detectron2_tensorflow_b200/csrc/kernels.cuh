@@ -43,7 +43,7 @@ int nms_sorted(const float* boxes, const int32_t* counts, int S, int n, int max_
                int32_t* num_keep, void* ws, cudaStream_t st, bool sweep = true);
 bool nms_uses_bitmask(int n, int max_out);
 bool nms_lazy_applies(int n, int max_out);  // the capped lazy sweep would be chosen (cap << n)
-// Small segments with UNSORTED scores (n <= 1024): order, mask, sweep and index un-mapping in ONE launch, one CTA per
+// Small segments with UNSORTED scores (n <= 512): order, mask, sweep and index un-mapping in ONE launch, one CTA per
 // segment; keep holds input indices (selection order, -1 padded).  No workspace.
 bool nms_small_applies(int n);
 int nms_small(const float* boxes, const float* scores, const int32_t* counts, int S, int n, int max_out, float thr,

@@ -282,12 +282,12 @@ __global__ void __launch_bounds__(kColSweepThreads) nms_sweep_cols_kernel(const 
 }
 
 // ------------------------------------------------------------------ A': small segments, everything in one launch
-// n <= kSmallMaxN boxes per segment with UNSORTED scores (the stand-alone batch_nms entry): one CTA per segment
+// n <= kSmallMaxN (512) boxes per segment with UNSORTED scores (the stand-alone batch_nms entry): one CTA per segment
 // orders the candidates (score desc, index asc; composite keys, bitonic sort in shared memory), gathers the boxes,
 // builds the suppression mask in shared memory (same filter + exact rule as nms_mask_kernel), sweeps it with the
 // column-owner warps and maps the kept positions back to input indices.  Replaces 7 launches (memset, prep, sort,
 // gather, mask, sweep, unmap): at these sizes the chain is pure launch latency.
-constexpr int kSmallMaxN = 1024;
+constexpr int kSmallMaxN = 512;  // beyond this the n^2 / 2 pair tests on ONE SM cost more than the launches saved
 __global__ void __launch_bounds__(kColSweepThreads) nms_small_kernel(const float4* boxes, const float* scores,
                                                                       const int32_t* counts, int n, int P, int W,
                                                                       int max_out, float thr, int32_t* keep,
