@@ -226,14 +226,14 @@ __global__ void __launch_bounds__(256) mnms_fused_kernel(MnmsArgs a, FusedCounte
   if (threadIdx.x == 0) s_ticket = atomicAdd(ticket_ctr, 1u);
   __syncthreads();
   const unsigned ticket = s_ticket;
-  const int nP = a.n, nI = a.n;  // one pack CTA per mask row (it walks the row's nP_x blocks: the per-CTA ticket /
-  const int T = nP + nI + 2 * nC;  // fence / signal overhead is then small against ~45 us of streaming)
+  const int nP = nP_x * a.n, nI = a.n;
+  const int T = nP + nI + 2 * nC;
   const int slot = (int)(ticket / (unsigned)T);
   int r = (int)(ticket - (unsigned)slot * (unsigned)T);
   if (r < nP) {  // pack image `slot`
     const int b = slot;
     if (b >= a.B) return;
-    for (int xb = 0; xb < nP_x; ++xb) pack4_body(a, b, r, xb);
+    pack4_body(a, b, r / nP_x, r % nP_x);
     signal_counter(&ctr[b].pack_done);
     return;
   }
@@ -315,7 +315,7 @@ extern "C" int d2b_matrix_nms(const d2b_matrix_nms_params* p, void* workspace, s
   a.out = p->out;
   D2B_CUDA(cudaMemsetAsync(a.isum, 0, sizeof(unsigned) * (size_t)a.B * a.n, st));
   const int nP_x = (a.Wd + 8 * kPackSteps * 2 - 1) / (8 * kPackSteps * 2), nC = (a.n + 7) / 8;
-  const long long fused_ctas = ((long long)a.n + a.n + 2 * nC) * (a.B + 3);
+  const long long fused_ctas = ((long long)nP_x * a.n + a.n + 2 * nC) * (a.B + 3);
   if (!p->packed_masks && a.hw % 4 == 0 && (reinterpret_cast<uintptr_t>(a.masks) & 15) == 0 && fused_ctas < (1ll << 31) - 1) {
     FusedCounters* ctr = reinterpret_cast<FusedCounters*>(ws + o_cmax + ws_slice((size_t)a.B * a.n * sizeof(float)));
     D2B_CUDA(cudaMemsetAsync(ctr, 0, sizeof(FusedCounters) * (size_t)(a.B + 1), st));
