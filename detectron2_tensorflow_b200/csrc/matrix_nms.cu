@@ -74,12 +74,13 @@ __global__ void __launch_bounds__(256) mnms_popc_kernel(MnmsArgs a) {
 // (lane = one float4 = 4 pixels; 16 lanes = 64 pixels = one word) and keeps kPackSteps independent
 // 16-byte loads in flight per lane.  grid (ceil(Wd / 128), n, B), 256 threads = 128 words per CTA.
 constexpr int kPackSteps = 8;
-__device__ __forceinline__ void pack4_body(const MnmsArgs& a, int b, int i, int xblk) {
+__global__ void __launch_bounds__(256) mnms_pack4_kernel(MnmsArgs a) {
+  const int b = blockIdx.z, i = blockIdx.y;
   if (i >= rows_of(a, b)) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float4* m = reinterpret_cast<const float4*>(a.masks + ((size_t)b * a.n + i) * a.hw);
   const long long nvec = a.hw >> 2;
-  const int w_first = xblk * (8 * kPackSteps * 2) + warp * (kPackSteps * 2);
+  const int w_first = blockIdx.x * (8 * kPackSteps * 2) + warp * (kPackSteps * 2);
   float4 v[kPackSteps];
 #pragma unroll
   for (int s = 0; s < kPackSteps; ++s) {
@@ -103,17 +104,16 @@ __device__ __forceinline__ void pack4_body(const MnmsArgs& a, int b, int i, int 
   total += __shfl_xor_sync(0xffffffffu, total, 16);
   if (lane == 0 && total) atomicAdd(a.isum + (size_t)b * a.n + i, total);
 }
-__global__ void __launch_bounds__(256) mnms_pack4_kernel(MnmsArgs a) { pack4_body(a, blockIdx.z, blockIdx.y, blockIdx.x); }
 
 __device__ __forceinline__ float sum_of(const MnmsArgs& a, int b, int i) {
-  return a.sum_in ? a.sum_in[(size_t)b * a.n + i] : (float)__ldcg(a.isum + (size_t)b * a.n + i);
+  return a.sum_in ? a.sum_in[(size_t)b * a.n + i] : (float)a.isum[(size_t)b * a.n + i];
 }
 
 // One CTA per row i: the row of the decayed-IoU matrix is first filled with its "no overlap" value
 // (coalesced), then each warp takes the few columns j > i of the same class and does the AND+POPC
 // reduction over the packed words.  grid (n, B), 256 threads.
-template <bool FUSED>  // FUSED: inputs were written by other CTAs of the same launch (L2 loads)
-__device__ __forceinline__ void iou_body(const MnmsArgs& a, int b, int i) {
+__global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a) {
+  const int b = blockIdx.y, i = blockIdx.x;
   const int nb = rows_of(a, b);
   if (i >= nb) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -132,7 +132,7 @@ __device__ __forceinline__ void iou_body(const MnmsArgs& a, int b, int i) {
     if (a.classes[(size_t)b * a.n + j] != ci) continue;  // warp-uniform
     const u64* pj = a.packed + ((size_t)b * a.n + j) * a.Wd;
     unsigned c = 0;
-    for (int w = lane; w < a.Wd; w += 32) c += FUSED ? __popcll(__ldcg(pi + w) & __ldcg(pj + w)) : __popcll(pi[w] & pj[w]);
+    for (int w = lane; w < a.Wd; w += 32) c += __popcll(pi[w] & pj[w]);
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (lane == 0) {
       const float inter = (float)c;
@@ -142,20 +142,20 @@ __device__ __forceinline__ void iou_body(const MnmsArgs& a, int b, int i) {
     }
   }
 }
-__global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a) { iou_body<false>(a, blockIdx.y, blockIdx.x); }
 
 // compensate_iou = reduce_max(iou, axis=0) (:67): one warp per column, `(v > m) ? v : m` semantics
 // (NaNs are skipped unless the first row is NaN).
-__device__ __forceinline__ void cmax_body(const MnmsArgs& a, int b, int jblk) {
-  const int j = jblk * 8 + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(256) mnms_cmax_kernel(MnmsArgs a) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int nb = rows_of(a, b);
   if (j >= nb) return;
   const float* io = a.iou + (size_t)b * a.n * a.n;
-  const float first = __ldcg(io + j);
+  const float first = io[j];
   float m = __int_as_float(0xff800000);
   for (int i = lane; i < nb; i += 32) {
-    const float v = __ldcg(io + (size_t)i * a.n + j);
+    const float v = io[(size_t)i * a.n + j];
     m = (v > m) ? v : m;
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -165,11 +165,11 @@ __device__ __forceinline__ void cmax_body(const MnmsArgs& a, int b, int jblk) {
   if (first != first) m = first;
   if (lane == 0) a.cmax[(size_t)b * a.n + j] = m;
 }
-__global__ void __launch_bounds__(256) mnms_cmax_kernel(MnmsArgs a) { cmax_body(a, blockIdx.y, blockIdx.x); }
 
 // decay + reduce_min(axis=0) + score update (:72-82): one warp per column, `(d < m) ? d : m` semantics.
-__device__ __forceinline__ void decay_body(const MnmsArgs& a, int b, int jblk) {
-  const int j = jblk * 8 + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(256) mnms_decay_kernel(MnmsArgs a) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (j >= a.n) return;
   const int nb = rows_of(a, b);
@@ -181,8 +181,8 @@ __device__ __forceinline__ void decay_body(const MnmsArgs& a, int b, int jblk) {
   const float* cm = a.cmax + (size_t)b * a.n;
   float m = __int_as_float(0x7f800000);
   for (int i = lane; i < nb; i += 32) {
-    const float v = __ldcg(io + (size_t)i * a.n + j);
-    const float ci = __ldcg(cm + i);
+    const float v = io[(size_t)i * a.n + j];
+    const float ci = cm[i];
     float d;
     if (a.kernel == D2B_MNMS_GAUSSIAN) {
       float x = v * v; float y = ci * ci; x = x - y; x = a.nsigma * x; d = d2b_expf(x);
@@ -197,70 +197,6 @@ __device__ __forceinline__ void decay_body(const MnmsArgs& a, int b, int jblk) {
   }
   if (lane == 0) a.out[(size_t)b * a.n + j] = a.scores[(size_t)b * a.n + j] * m;
 }
-__global__ void __launch_bounds__(256) mnms_decay_kernel(MnmsArgs a) { decay_body(a, blockIdx.y, blockIdx.x); }
-
-// ---------------------------------------------------------------- one launch for the whole batch (fp32 masks in)
-// The pack phase is the HBM-bound read (134 MB per image); the IoU / column-max / decay phases are L2- and ALU-work
-// on 4 MB of packed words.  Run as four launches they serialise: 0.35 ms of streaming, then 0.15 ms during which
-// HBM idles.  Here ONE grid holds every phase of every image, ordered so that image b's IoU CTAs follow image
-// b+1's pack CTAs (slot s = [pack s][iou s-1][cmax s-2][decay s-3]): while image b+1 streams, the earlier images'
-// dependent phases run beside it.  A dependent CTA waits for its image's producers on a global counter; every
-// producer has a LOWER block index, and CTAs are dispatched in block-index order, so whatever a CTA waits for is
-// already running or done (the decoupled look-back argument) -- and the waits are short by construction.
-struct FusedCounters { unsigned pack_done, iou_done, cmax_done, pad; };
-__device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned target) {
-  if (threadIdx.x == 0) {
-    while (*reinterpret_cast<const volatile unsigned*>(ctr) < target) __nanosleep(200);
-    __threadfence();
-  }
-  __syncthreads();
-}
-__device__ __forceinline__ void signal_counter(unsigned* ctr) {
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(ctr, 1u);
-}
-__global__ void __launch_bounds__(256) mnms_fused_kernel(MnmsArgs a, FusedCounters* ctr, unsigned* ticket_ctr, int nP_x,
-                                                         int nC) {
-  __shared__ unsigned s_ticket;
-  if (threadIdx.x == 0) s_ticket = atomicAdd(ticket_ctr, 1u);
-  __syncthreads();
-  const unsigned ticket = s_ticket;
-  const int nP = nP_x * a.n, nI = a.n;
-  const int T = nP + nI + 2 * nC;
-  const int slot = (int)(ticket / (unsigned)T);
-  int r = (int)(ticket - (unsigned)slot * (unsigned)T);
-  if (r < nP) {  // pack image `slot`
-    const int b = slot;
-    if (b >= a.B) return;
-    pack4_body(a, b, r / nP_x, r % nP_x);
-    signal_counter(&ctr[b].pack_done);
-    return;
-  }
-  r -= nP;
-  if (r < nI) {  // IoU rows of image slot - 1
-    const int b = slot - 1;
-    if (b < 0 || b >= a.B) return;
-    wait_counter(&ctr[b].pack_done, (unsigned)nP);
-    iou_body<true>(a, b, r);
-    signal_counter(&ctr[b].iou_done);
-    return;
-  }
-  r -= nI;
-  if (r < nC) {  // column maxima of image slot - 2
-    const int b = slot - 2;
-    if (b < 0 || b >= a.B) return;
-    wait_counter(&ctr[b].iou_done, (unsigned)nI);
-    cmax_body(a, b, r);
-    signal_counter(&ctr[b].cmax_done);
-    return;
-  }
-  r -= nC;
-  const int b = slot - 3;  // decay + min + score update of image slot - 3
-  if (b < 0 || b >= a.B) return;
-  wait_counter(&ctr[b].cmax_done, (unsigned)nC);
-  decay_body(a, b, r);
-}
 
 size_t mnms_bytes(const d2b_matrix_nms_params* p, size_t* o_packed, size_t* o_isum, size_t* o_iou, size_t* o_cmax) {
   const size_t B = p->batch, n = p->n, Wd = (size_t)((p->hw + 63) / 64);
@@ -269,7 +205,6 @@ size_t mnms_bytes(const d2b_matrix_nms_params* p, size_t* o_packed, size_t* o_is
   *o_isum = o; o += ws_slice(B * n * sizeof(unsigned));
   *o_iou = o; o += ws_slice(B * n * n * sizeof(float));
   *o_cmax = o; o += ws_slice(B * n * sizeof(float));
-  o += ws_slice((B + 1) * sizeof(FusedCounters));  // directly after cmax (fused launch): per-image counters + ticket
   return o;
 }
 
@@ -314,15 +249,6 @@ extern "C" int d2b_matrix_nms(const d2b_matrix_nms_params* p, void* workspace, s
   a.cmax = reinterpret_cast<float*>(ws + o_cmax);
   a.out = p->out;
   D2B_CUDA(cudaMemsetAsync(a.isum, 0, sizeof(unsigned) * (size_t)a.B * a.n, st));
-  const int nP_x = (a.Wd + 8 * kPackSteps * 2 - 1) / (8 * kPackSteps * 2), nC = (a.n + 7) / 8;
-  const long long fused_ctas = ((long long)nP_x * a.n + a.n + 2 * nC) * (a.B + 3);
-  if (!p->packed_masks && a.hw % 4 == 0 && (reinterpret_cast<uintptr_t>(a.masks) & 15) == 0 && fused_ctas < (1ll << 31) - 1) {
-    FusedCounters* ctr = reinterpret_cast<FusedCounters*>(ws + o_cmax + ws_slice((size_t)a.B * a.n * sizeof(float)));
-    D2B_CUDA(cudaMemsetAsync(ctr, 0, sizeof(FusedCounters) * (size_t)(a.B + 1), st));
-    mnms_fused_kernel<<<(unsigned)fused_ctas, 256, 0, st>>>(a, ctr, &ctr[a.B].pack_done, nP_x, nC);
-    D2B_LAUNCH_CHECK();
-    return D2B_OK;
-  }
   if (p->packed_masks) {
     if (!a.sum_in) mnms_popc_kernel<<<dim3((a.n + 7) / 8, a.B), 256, 0, st>>>(a);
   } else if (a.hw % 4 == 0 && (reinterpret_cast<uintptr_t>(a.masks) & 15) == 0)
