@@ -113,10 +113,13 @@ __device__ __forceinline__ float sum_of(const MnmsArgs& a, int b, int i) {
 // (coalesced), then each warp takes the few columns j > i of the same class and does the AND+POPC
 // reduction over the packed words.  grid (n, B), 256 threads.
 __global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a) {
+  __shared__ int s_match[256];  // columns j > i of row i's class, compacted (the serial class scan was the latency:
+  __shared__ int s_nmatch;      // ~60 dependent global loads per warp for ~3 matching columns)
   const int b = blockIdx.y, i = blockIdx.x;
   const int nb = rows_of(a, b);
   if (i >= nb) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_nmatch = 0;
   const float si = sum_of(a, b, i);
   const long long ci = a.classes[(size_t)b * a.n + i];
   float* row = a.iou + ((size_t)b * a.n + i) * a.n;
@@ -128,8 +131,33 @@ __global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a) {
     row[j] = (u == 0.0f) ? __int_as_float(0x7fc00000) : 0.0f;
   }
   __syncthreads();
-  for (int j = i + 1 + warp; j < nb; j += 8) {
-    if (a.classes[(size_t)b * a.n + j] != ci) continue;  // warp-uniform
+  for (int j0 = i + 1; j0 < nb; j0 += 256) {  // all same-class columns in rounds of up to 256 matches
+    const int j = j0 + threadIdx.x;
+    if (j < nb && a.classes[(size_t)b * a.n + j] == ci) {
+      const int s = atomicAdd(&s_nmatch, 1);
+      if (s < 256) s_match[s] = j;
+    }
+  }
+  __syncthreads();
+  const int nmatch = s_nmatch;
+  if (nmatch > 256) {  // (more than 256 same-class columns: the plain scan)
+    for (int j = i + 1 + warp; j < nb; j += 8) {
+      if (a.classes[(size_t)b * a.n + j] != ci) continue;  // warp-uniform
+      const u64* pj = a.packed + ((size_t)b * a.n + j) * a.Wd;
+      unsigned c = 0;
+      for (int w = lane; w < a.Wd; w += 32) c += __popcll(pi[w] & pj[w]);
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (lane == 0) {
+        const float inter = (float)c;
+        float u = sum_of(a, b, j) + si;  // nms.py:51-52
+        u = u - inter;
+        row[j] = inter / u;  // :54
+      }
+    }
+    return;
+  }
+  for (int m = warp; m < nmatch; m += 8) {
+    const int j = s_match[m];
     const u64* pj = a.packed + ((size_t)b * a.n + j) * a.Wd;
     unsigned c = 0;
     for (int w = lane; w < a.Wd; w += 32) c += __popcll(pi[w] & pj[w]);
