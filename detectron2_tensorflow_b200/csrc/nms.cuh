@@ -21,7 +21,7 @@ __device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
 // Blocks after the cap (max_out kept) publish an empty set at once.  Returns the number of kept boxes (uniform
 // over the CTA, after a __syncthreads()).
 constexpr int kColSweepThreads = 1024;
-constexpr int kColSweepMaxW = 64;  // n <= 4096
+constexpr int kColSweepMaxW = 256;  // n <= 16384 (a warp owns words q, q + 32, ...: up to 8 of them)
 
 // SMEM_OUT: instead of the global keep list, the kept boxes' positions and the order-preserving keys of their scores
 // (sc = the segment's scores in candidate order) go to shared memory (s_pos / s_key, max_out entries each).
@@ -126,7 +126,7 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
       s_keep[word] = K;
       __threadfence_block();
       s_flag[word] = 1;
-      D2B_PROF(blockIdx.x == 0 && word < 64, 32 + word);
+      D2B_PROF(blockIdx.x == 0 && word < 32, 32 + word);
     }
   }
   __syncthreads();
