@@ -955,7 +955,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="d2b200", choices=["d2b200", "reference"])
-    ap.add_argument("--chunks", type=int, default=2, help="image blocks run concurrently inside the graphed step")
+    ap.add_argument("--chunks", type=int, default=4, help="image blocks run concurrently inside the graphed step")
     ap.add_argument("--in-flight", type=int, default=3, dest="in_flight",
                     help="graphed steps replayed concurrently on alternating streams (1 = strictly one after another)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -115,6 +115,7 @@ __device__ __forceinline__ float sum_of(const MnmsArgs& a, int b, int i) {
 __global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a) {
   __shared__ int s_match[256];  // columns j > i of row i's class, compacted (the serial class scan was the latency:
   __shared__ int s_nmatch;      // ~60 dependent global loads per warp for ~3 matching columns)
+  extern __shared__ u64 s_pi[];  // row i's packed mask: read from L2 once per row instead of once per pair
   const int b = blockIdx.y, i = blockIdx.x;
   const int nb = rows_of(a, b);
   if (i >= nb) return;
@@ -140,6 +141,10 @@ __global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a) {
   }
   __syncthreads();
   const int nmatch = s_nmatch;
+  if (nmatch > 0 && nmatch <= 256) {
+    for (int w = threadIdx.x; w < a.Wd; w += 256) s_pi[w] = pi[w];
+    __syncthreads();  // (block-uniform condition)
+  }
   if (nmatch > 256) {  // (more than 256 same-class columns: the plain scan)
     for (int j = i + 1 + warp; j < nb; j += 8) {
       if (a.classes[(size_t)b * a.n + j] != ci) continue;  // warp-uniform
@@ -160,7 +165,19 @@ __global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a) {
     const int j = s_match[m];
     const u64* pj = a.packed + ((size_t)b * a.n + j) * a.Wd;
     unsigned c = 0;
-    for (int w = lane; w < a.Wd; w += 32) c += __popcll(pi[w] & pj[w]);
+    for (int w0 = 0; w0 < a.Wd; w0 += 32 * 8) {  // 8 independent loads in flight per lane
+      u64 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int w = w0 + u * 32 + lane;
+        v[u] = w < a.Wd ? __ldg(pj + w) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int w = w0 + u * 32 + lane;
+        if (w < a.Wd) c += __popcll(s_pi[w] & v[u]);
+      }
+    }
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (lane == 0) {
       const float inter = (float)c;
@@ -284,7 +301,11 @@ extern "C" int d2b_matrix_nms(const d2b_matrix_nms_params* p, void* workspace, s
   else
     mnms_pack_kernel<<<dim3((a.Wd + 7) / 8, a.n, a.B), 256, 0, st>>>(a);
   if (!(p->packed_masks && a.sum_in)) D2B_LAUNCH_CHECK();
-  mnms_iou_kernel<<<dim3(a.n, a.B), 256, 0, st>>>(a);
+  const size_t iou_smem = (size_t)a.Wd * sizeof(u64);
+  D2B_REQUIRE(iou_smem <= 200 * 1024, "matrix_nms: masks of %lld pixels are too large", (long long)a.hw);
+  if (iou_smem > 48 * 1024)
+    D2B_CUDA(cudaFuncSetAttribute(mnms_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iou_smem));
+  mnms_iou_kernel<<<dim3(a.n, a.B), 256, iou_smem, st>>>(a);
   D2B_LAUNCH_CHECK();
   mnms_cmax_kernel<<<dim3((a.n + 7) / 8, a.B), 256, 0, st>>>(a);
   D2B_LAUNCH_CHECK();
