@@ -112,7 +112,7 @@ __device__ __forceinline__ float sum_of(const MnmsArgs& a, int b, int i) {
 // One CTA per row i: the row of the decayed-IoU matrix is first filled with its "no overlap" value
 // (coalesced), then each warp takes the few columns j > i of the same class and does the AND+POPC
 // reduction over the packed words.  grid (n, B), 256 threads.
-__global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a) {
+__global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a, int stage) {
   __shared__ int s_match[256];  // columns j > i of row i's class, compacted (the serial class scan was the latency:
   __shared__ int s_nmatch;      // ~60 dependent global loads per warp for ~3 matching columns)
   extern __shared__ u64 s_pi[];  // row i's packed mask: read from L2 once per row instead of once per pair
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a) {
   }
   __syncthreads();
   const int nmatch = s_nmatch;
-  if (nmatch > 0 && nmatch <= 256) {
+  if (stage && nmatch > 0 && nmatch <= 256) {
     for (int w = threadIdx.x; w < a.Wd; w += 256) s_pi[w] = pi[w];
     __syncthreads();  // (block-uniform condition)
   }
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int w = w0 + u * 32 + lane;
-        if (w < a.Wd) c += __popcll(s_pi[w] & v[u]);
+        if (w < a.Wd) c += __popcll((stage ? s_pi[w] : pi[w]) & v[u]);
       }
     }
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -301,11 +301,12 @@ extern "C" int d2b_matrix_nms(const d2b_matrix_nms_params* p, void* workspace, s
   else
     mnms_pack_kernel<<<dim3((a.Wd + 7) / 8, a.n, a.B), 256, 0, st>>>(a);
   if (!(p->packed_masks && a.sum_in)) D2B_LAUNCH_CHECK();
-  const size_t iou_smem = (size_t)a.Wd * sizeof(u64);
-  D2B_REQUIRE(iou_smem <= 200 * 1024, "matrix_nms: masks of %lld pixels are too large", (long long)a.hw);
+  size_t iou_smem = (size_t)a.Wd * sizeof(u64);
+  const int stage = iou_smem <= 160 * 1024;  // (larger masks: the row is re-read from L2 per pair)
+  if (!stage) iou_smem = 0;
   if (iou_smem > 48 * 1024)
     D2B_CUDA(cudaFuncSetAttribute(mnms_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iou_smem));
-  mnms_iou_kernel<<<dim3(a.n, a.B), 256, iou_smem, st>>>(a);
+  mnms_iou_kernel<<<dim3(a.n, a.B), 256, iou_smem, st>>>(a, stage);
   D2B_LAUNCH_CHECK();
   mnms_cmax_kernel<<<dim3((a.n + 7) / 8, a.B), 256, 0, st>>>(a);
   D2B_LAUNCH_CHECK();
