@@ -139,8 +139,21 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* bo
 #pragma unroll
       for (int c = 0; c < 64; ++c) {
         const float4 fj = s_flt[warp][c];
-        const bool pass = (fj.x <= fi.yhi) && (fi.ylo <= fj.z) && (fj.y <= fi.xhi) && (fi.xlo <= fj.w);
-        if (c < 32) clo |= pass ? (1u << c) : 0u; else chi |= pass ? (1u << (c - 32)) : 0u;
+        // four predicate-accumulating compares and ONE predicated OR-immediate per column, spelled in PTX: from the C++
+        // forms ptxas emits short-circuit predication or select chains (8-9 instructions per pair instead of 6)
+        if (c < 32) {
+          asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\tsetp.le.and.f32 p, %3, %4, p;\n\t"
+              "setp.le.and.f32 p, %5, %6, p;\n\tsetp.le.and.f32 p, %7, %8, p;\n\t@p or.b32 %0, %0, %9;\n\t}"
+              : "+r"(clo)
+              : "f"(fj.x), "f"(fi.yhi), "f"(fi.ylo), "f"(fj.z), "f"(fj.y), "f"(fi.xhi), "f"(fi.xlo), "f"(fj.w),
+                "r"(1u << (c & 31)));
+        } else {
+          asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\tsetp.le.and.f32 p, %3, %4, p;\n\t"
+              "setp.le.and.f32 p, %5, %6, p;\n\tsetp.le.and.f32 p, %7, %8, p;\n\t@p or.b32 %0, %0, %9;\n\t}"
+              : "+r"(chi)
+              : "f"(fj.x), "f"(fi.yhi), "f"(fi.ylo), "f"(fj.z), "f"(fj.y), "f"(fi.xhi), "f"(fi.xlo), "f"(fj.w),
+                "r"(1u << (c & 31)));
+        }
       }
       u64 cand = ((u64)chi << 32) | clo;
       if (cb == rb) cand &= (r == 63) ? 0ull : (~0ull << (r + 1));  // only j > i
