@@ -243,55 +243,6 @@ __global__ void __launch_bounds__(256) mnms_decay_kernel(MnmsArgs a) {
   if (lane == 0) a.out[(size_t)b * a.n + j] = a.scores[(size_t)b * a.n + j] * m;
 }
 
-// Column max + decay + min + score update of one image in ONE CTA (n <= kTailMaxN): the column maxima stay in
-// shared memory, so the two dependent launches (13 + 19 us of mostly latency) become one.
-constexpr int kTailMaxN = 4096;
-__global__ void __launch_bounds__(1024) mnms_tail_kernel(MnmsArgs a) {
-  __shared__ float s_cmax[kTailMaxN];
-  const int b = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nb = rows_of(a, b);
-  const float* io = a.iou + (size_t)b * a.n * a.n;
-  for (int j = warp; j < nb; j += 32) {  // compensate_iou = reduce_max(iou, axis=0) (:67), `(v > m) ? v : m`
-    const float first = io[j];
-    float m = __int_as_float(0xff800000);
-    for (int i = lane; i < nb; i += 32) {
-      const float v = io[(size_t)i * a.n + j];
-      m = (v > m) ? v : m;
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      const float v = __shfl_xor_sync(0xffffffffu, m, o);
-      m = (v > m) ? v : m;
-    }
-    if (first != first) m = first;
-    if (lane == 0) s_cmax[j] = m;
-  }
-  __syncthreads();
-  for (int j = warp; j < a.n; j += 32) {  // decay + reduce_min(axis=0) + score update (:72-82), `(d < m) ? d : m`
-    if (j >= nb) {
-      if (lane == 0) a.out[(size_t)b * a.n + j] = 0.0f;
-      continue;
-    }
-    float m = __int_as_float(0x7f800000);
-    for (int i = lane; i < nb; i += 32) {
-      const float v = io[(size_t)i * a.n + j];
-      const float ci = s_cmax[i];
-      float d;
-      if (a.kernel == D2B_MNMS_GAUSSIAN) {
-        float x = v * v; float y = ci * ci; x = x - y; x = a.nsigma * x; d = d2b_expf(x);
-      } else {
-        float x = 1.0f - v; float y = 1.0f - ci; d = x / y;
-      }
-      m = (d < m) ? d : m;
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      const float v = __shfl_xor_sync(0xffffffffu, m, o);
-      m = (v < m) ? v : m;
-    }
-    if (lane == 0) a.out[(size_t)b * a.n + j] = a.scores[(size_t)b * a.n + j] * m;
-  }
-}
-
 size_t mnms_bytes(const d2b_matrix_nms_params* p, size_t* o_packed, size_t* o_isum, size_t* o_iou, size_t* o_cmax) {
   const size_t B = p->batch, n = p->n, Wd = (size_t)((p->hw + 63) / 64);
   size_t o = 0;
@@ -357,11 +308,6 @@ extern "C" int d2b_matrix_nms(const d2b_matrix_nms_params* p, void* workspace, s
     D2B_CUDA(cudaFuncSetAttribute(mnms_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iou_smem));
   mnms_iou_kernel<<<dim3(a.n, a.B), 256, iou_smem, st>>>(a, stage);
   D2B_LAUNCH_CHECK();
-  if (a.n <= kTailMaxN && a.B >= 4) {  // (few images: the two wide launches use more SMs)
-    mnms_tail_kernel<<<a.B, 1024, 0, st>>>(a);
-    D2B_LAUNCH_CHECK();
-    return D2B_OK;
-  }
   mnms_cmax_kernel<<<dim3((a.n + 7) / 8, a.B), 256, 0, st>>>(a);
   D2B_LAUNCH_CHECK();
   mnms_decay_kernel<<<dim3((a.n + 7) / 8, a.B), 256, 0, st>>>(a);
