@@ -310,6 +310,45 @@ def bind_to_gpu_numa_node(local_rank):
         return {"error": type(e).__name__}
 
 
+def host_path_probe(dev, world, h2d_bytes, d2h_bytes, e2e_step_s):
+    """What the host<->device path of this box can carry with all `world` ranks copying at once (256 MiB pinned
+    buffers, both directions concurrently, max over ranks), and how close the e2e step comes to it."""
+    import torch
+    import torch.distributed as dist
+    n = 256 << 20
+    h_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    d_in = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def both():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+    both()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        both()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 4
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t[0])
+    duplex = n / dt / 1e9  # GB/s per rank in EACH direction with every rank copying both ways
+    floor_s = max(h2d_bytes, d2h_bytes) / (duplex * 1e9)
+    frac = floor_s / e2e_step_s
+    return {"duplex_GBps_per_rank_each_direction": duplex, "aggregate_GBps_each_direction": duplex * world,
+            "copy_floor_ms_per_step": floor_s * 1e3, "e2e_over_copy_floor": e2e_step_s / floor_s,
+            "limiter": ("host<->device copies of this box: the e2e step runs at %.0f %% of what %d rank(s) copying in "
+                        "both directions at once can move (measured in this run)" % (100.0 * frac, world))}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -482,7 +521,10 @@ def run_gpu(args):
         e2e_s = float(t[0])
     h2d = sum(nbytes(hx[k]) for k in ("feats", "logits", "deltas", "anchors", "scores", "cls_deltas", "shapes"))
     d2h = nbytes(ho)
+    del ho
+    host_path = host_path_probe(dev, world, h2d, d2h, e2e_s / Ke)
     line["e2e"] = {"value": rois_rank * world / (e2e_s / Ke), "unit": "ROIs/s", "ms_per_step": e2e_s / Ke * 1e3,
+                   "host_path": host_path, "limiter": host_path["limiter"],
                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": Ke,
                    "host_numa_binding": numa,
                    "note": "MaskRCNNPostBackbone.run_host: pinned host tensors in, pinned host tensors out (all "
@@ -491,7 +533,7 @@ def run_gpu(args):
 
     # ---- the other BASELINE.json configs (parity-test cases, not bench lines): device-resident timings, N=1 only
     if not args.no_extras:
-        del hx, ho, x, pipe, gstep, out
+        del hx, x, pipe, gstep, out
         torch.cuda.empty_cache()
         oc = {}
         if world == 1:

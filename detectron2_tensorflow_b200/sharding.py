@@ -148,10 +148,16 @@ class GatherPlan(object):
     Buffer layout: one block per key sized for the LONGEST image block, so the key offsets are the same on every
     rank and uneven blocks only leave a tail unused.  spec = {key: (trailing shape, dtype)}."""
 
-    def __init__(self, spec, layout, device, group=None):
+    def __init__(self, spec, layout, device, group=None, collective="auto"):
+        """collective: "gather" (dist.gather: grouped send/recv to rank 0), "all_gather" (one
+        all_gather_into_tensor: every rank receives the 48 KB blocks -- NCCL has no native gather and this is its
+        cheapest fixed-size collective), or "auto" (all_gather on NCCL, gather elsewhere)."""
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        if collective == "auto":
+            collective = "all_gather" if dist.get_backend(group) == "nccl" else "gather"
+        self.collective = collective
         self.layout = layout
         self.spec = dict(spec)
         self.begin = [lay[0][0] for lay in layout]
@@ -166,7 +172,8 @@ class GatherPlan(object):
             off += (longest * per + 255) // 256 * 256
         self.nbytes = max(off, 256)
         self.sendbuf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
-        self.recv = torch.zeros((self.world, self.nbytes), dtype=torch.uint8, device=device) if self.rank == 0 else None
+        need_recv = self.rank == 0 or self.collective == "all_gather"
+        self.recv = torch.zeros((self.world, self.nbytes), dtype=torch.uint8, device=device) if need_recv else None
         n_total = layout[-1][-1][1]
         self.out = {k: torch.zeros((n_total,) + tuple(shape), dtype=dtype, device=device)
                     for k, (shape, dtype) in self.spec.items()} if self.rank == 0 else None
@@ -185,7 +192,10 @@ class GatherPlan(object):
                 self._view(self.sendbuf, k, n)[lb:lb + (e - b)].copy_(blk[k])
 
     def gather(self):
-        dist.gather(self.sendbuf, list(self.recv.unbind(0)) if self.rank == 0 else None, dst=0, group=self.group)
+        if self.collective == "all_gather":
+            dist.all_gather_into_tensor(self.recv.view(-1), self.sendbuf, group=self.group)
+        else:
+            dist.gather(self.sendbuf, list(self.recv.unbind(0)) if self.rank == 0 else None, dst=0, group=self.group)
 
     def unpack(self):
         if self.rank != 0:
