@@ -341,7 +341,8 @@ def host_path_probe(dev, world, h2d_bytes, d2h_bytes, e2e_step_s):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t[0])
     duplex = n / dt / 1e9  # GB/s per rank in EACH direction with every rank copying both ways
-    floor_s = max(h2d_bytes, d2h_bytes) / (duplex * 1e9)
+    # the ranks share the host-memory / PCIe path: what counts is the total bytes moved per step, both directions
+    floor_s = (h2d_bytes + d2h_bytes) / (2.0 * duplex * 1e9)
     frac = floor_s / e2e_step_s
     return {"duplex_GBps_per_rank_each_direction": duplex, "aggregate_GBps_each_direction": duplex * world,
             "copy_floor_ms_per_step": floor_s * 1e3, "e2e_over_copy_floor": e2e_step_s / floor_s,
