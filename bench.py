@@ -489,7 +489,7 @@ def run_gpu(args):
     barrier()
     if world > 1:
         try:
-            line["strong"] = strong_scaling(hp, x, dev, world, rank, K, W, args.chunks, args.in_flight, gstep,
+            line["strong"] = strong_scaling(hp, x, dev, world, rank, K, W, args.chunks, args.strong_in_flight, gstep,
                                             step_latency_ms, ms_per_step)
         except Exception as e:  # noqa: BLE001
             line["strong"] = {"error": repr(e)[:300]}
@@ -1001,6 +1001,8 @@ def main():
     ap.add_argument("--chunks", type=int, default=4, help="image blocks run concurrently inside the graphed step")
     ap.add_argument("--in-flight", type=int, default=3, dest="in_flight",
                     help="graphed steps replayed concurrently on alternating streams (1 = strictly one after another)")
+    ap.add_argument("--strong-in-flight", type=int, default=6, dest="strong_in_flight",
+                    help="graphed steps in flight in the strong-scaling leg (small per-rank blocks: more steps overlap)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", dest="no_extras",
                     help="skip the device timings of the other BASELINE.json configs (other_configs key)")
