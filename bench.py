@@ -490,9 +490,18 @@ def run_gpu(args):
     if world > 1:
         try:
             line["strong"] = strong_scaling(hp, x, dev, world, rank, K, W, args.chunks, args.strong_in_flight, gstep,
-                                            step_latency_ms, ms_per_step)
+                                            step_latency_ms, ms_per_step, transport="peer")
         except Exception as e:  # noqa: BLE001
             line["strong"] = {"error": repr(e)[:300]}
+        barrier()
+        try:  # the library-collective route beside it (what the peer-memory kernels replace)
+            nccl = strong_scaling(hp, x, dev, world, rank, K, W, args.chunks, args.strong_in_flight, gstep,
+                                  step_latency_ms, ms_per_step, transport="nccl")
+            line["strong_nccl"] = {k: nccl[k] for k in ("transport", "ms_per_step", "speedup_vs_1gpu", "gather_ms",
+                                                        "pipelined_ms_per_step", "pipelined_speedup_vs_1gpu",
+                                                        "gathered_identical_to_1gpu")}
+        except Exception as e:  # noqa: BLE001
+            line["strong_nccl"] = {"error": repr(e)[:300]}
     else:
         line["strong"] = {"global_batch": n, "images_per_rank": [n], "ms_per_step": step_latency_ms,
                           "speedup_vs_1gpu": 1.0, "gather_ms": 0.0, "pipelined_ms_per_step": ms_per_step,
@@ -562,7 +571,8 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def strong_scaling(hp, x, dev, world, rank, K, W, chunks, in_flight, full_step, full_latency_ms, full_pipe_ms):
+def strong_scaling(hp, x, dev, world, rank, K, W, chunks, in_flight, full_step, full_latency_ms, full_pipe_ms,
+                   transport="peer"):
     """SURVEY.md 8(e) / north_star: the FIXED batch of 16 images partitioned by image index over the ranks, no
     collective on the path, and the fixed-size padded results (proposals + detections) gathered to rank 0 with one
     grouped send/recv over NVLink inside the timed region.  Every rank holds the same seeded global batch and cuts
@@ -583,20 +593,33 @@ def strong_scaling(hp, x, dev, world, rank, K, W, chunks, in_flight, full_step, 
     # one GatherPlan per graphed step: its pack() is captured inside the step's graph, its unpack() is a graph of
     # its own on rank 0, so a step costs two graph launches + one NCCL gather on the host
     spec = hp.gather_spec()
-    plans = [sharding.GatherPlan(spec, layout, dev) for _ in range(in_flight)]
+    peer = transport == "peer"
+    if peer:
+        # NVLink peer memory: the pack kernel captured in the step graph stores the block straight into rank 0's
+        # receive slot and raises a flag; rank 0's unpack kernel waits for the flags (sharding.PeerGatherPlan)
+        plans = [sharding.PeerGatherPlan(spec, layout, dev) for _ in range(in_flight)]
+    else:
+        plans = [sharding.GatherPlan(spec, layout, dev) for _ in range(in_flight)]
     pipe = hp.pipeline(xl, chunks=chunks_of(e - b), depth=in_flight,
-                       epilogues=[(lambda outs, p=p: p.pack([{k: o[k] for k in GATHER_KEYS} for o in outs])) for p in plans])
+                       epilogues=[(lambda outs, p=p: p.pack([{k: o[k] for k in GATHER_KEYS} for o in outs])) for p in plans],
+                       epilogue_warmup=not peer)
     g0 = pipe.steps[0]
     assert [(b + lb, b + le) for lb, le in g0.bounds] == layout[rank]
     unpack_graphs = []
     if rank == 0:
         for p in plans:
-            p.unpack()
-            torch.cuda.synchronize()
+            if not peer:
+                p.unpack()
+                torch.cuda.synchronize()
             ug = torch.cuda.CUDAGraph()
             with torch.cuda.graph(ug):
                 p.unpack()
             unpack_graphs.append(ug)
+    pack_only = None
+    if peer:  # the gather alone = this rank's pack kernel (+ rank 0's unpack): its own small graph over g0's outputs
+        pack_only = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(pack_only):
+            plans[0].pack([{k: o[k] for k in GATHER_KEYS} for o in g0.outputs])
     step_plan = {id(st): (plans[i], unpack_graphs[i] if rank == 0 else None) for i, st in enumerate(pipe.steps)}
 
     def barrier():
@@ -633,6 +656,8 @@ def strong_scaling(hp, x, dev, world, rank, K, W, chunks, in_flight, full_step, 
     barrier()
     ev[2].record()
     for _ in range(K):
+        if pack_only is not None:
+            pack_only.replay()
         gather(g0)
     ev[3].record()
     barrier()
@@ -664,7 +689,22 @@ def strong_scaling(hp, x, dev, world, rank, K, W, chunks, in_flight, full_step, 
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     lat_ms, gather_ms, pipe_ms = (float(v) for v in t)
     rois = n * (ROIS_PER_IMAGE + DETS_PER_IMAGE)
-    return {"global_batch": n, "images_per_rank": [sharding.image_block(n, world, r)[1] - sharding.image_block(n, world, r)[0]
+    if peer:
+        for p in plans:
+            p.check()  # a timed-out flag wait is an error, not a slow step
+    # the gathered results after the pipelined run too
+    if rank == 0:
+        last = step_plan[id(pipe.steps[(K - 1) % len(pipe.steps)])][0].out
+        identical = bool(identical and all(torch.equal(last[k], want[k]) for k in GATHER_KEYS))
+    kernels_gather = (1 + (1 if rank == 0 else 0)) if peer else None
+    del unpack_graphs, pack_only, pipe
+    if peer:
+        for p in plans:
+            p.close()
+    return {"transport": ("NVLink peer memory: 1 pack kernel per rank (remote stores + flag) + 1 unpack kernel on rank 0 "
+                          "(csrc/peer.cu)") if peer else "NCCL (one collective per step + packed copies)",
+            "gather_kernels_rank0": kernels_gather,
+            "global_batch": n, "images_per_rank": [sharding.image_block(n, world, r)[1] - sharding.image_block(n, world, r)[0]
                                                    for r in range(world)],
             "ms_per_step": lat_ms, "rois_per_s": rois / (lat_ms * 1e-3),
             "one_gpu_ms_per_step": full_latency_ms, "speedup_vs_1gpu": full_latency_ms / lat_ms,
@@ -672,10 +712,11 @@ def strong_scaling(hp, x, dev, world, rank, K, W, chunks, in_flight, full_step, 
             "pipelined_ms_per_step": pipe_ms, "one_gpu_pipelined_ms_per_step": full_pipe_ms,
             "pipelined_speedup_vs_1gpu": full_pipe_ms / pipe_ms, "pipelined_rois_per_s": rois / (pipe_ms * 1e-3),
             "gathered_identical_to_1gpu": identical, "kernels_per_step_per_rank": g0.kernels_per_replay,
-            "note": "the fixed 16-image batch split by image index; ms_per_step = graph replay of the rank's block + "
-                    "(with the pack of proposals + detections into one send buffer captured inside it) + ONE dist.gather "
-                    "over NCCL + rank 0's unpack graph, one step at a time, max over ranks (CUDA events); one_gpu_* = the same measurement of the whole batch on one GPU in this run "
-                    "(no gather needed); pipelined_* = several steps in flight on alternating streams"}
+            "note": "the fixed 16-image batch split by image index; ms_per_step = graph replay of the rank's block "
+                    "(with the pack of proposals + detections captured inside it) + the transport + rank 0's unpack "
+                    "graph, one step at a time, max over ranks (CUDA events); one_gpu_* = the same measurement of the "
+                    "whole batch on one GPU in this run (no gather needed); pipelined_* = several steps in flight on "
+                    "alternating streams"}
 
 
 def config0_single_image(dev, iters=20, cpu=True):

@@ -193,6 +193,19 @@ class RoiAlignBackwardParams(C.Structure):
 
 
 # op name -> params struct; every op exports d2b_<op> and d2b_<op>_workspace_bytes
+PEER_HANDLE_BYTES, PEER_MAX_SEGMENTS, PEER_MAX_FLAGS = 64, 112, 16
+
+
+class CopySegment(C.Structure):
+    _fields_ = [("src", _vp), ("dst", _vp), ("bytes", C.c_uint64)]
+
+
+class PeerCopyParams(C.Structure):
+    _fields_ = [("segments", C.POINTER(CopySegment)), ("num_segments", _i32), ("wait_flags", C.POINTER(_vp)),
+                ("num_wait", _i32), ("wait_lag", _i32), ("signal_flags", C.POINTER(_vp)), ("num_signal", _i32),
+                ("epoch_counter", _vp), ("ticket", _vp), ("error_flag", _vp), ("timeout_ms", C.c_uint32)]
+
+
 OPS = {
     "roi_align_multilevel": RoiAlignParams,
     "apply_deltas": ApplyDeltasParams,
@@ -219,9 +232,11 @@ OPS = {
     "solo_upsample": SoloUpsampleParams,
     "solo_select": SoloSelectParams,
     "mask_rcnn_inference": MaskRcnnInferenceParams,
+    "peer_copy": PeerCopyParams,
 }
 EXPORTS = ["d2b_version", "d2b_status_string", "d2b_last_error", "d2b_kernel_launch_count"] + \
-          [f"d2b_{op}{sfx}" for op in OPS for sfx in ("", "_workspace_bytes")]
+          [f"d2b_{op}{sfx}" for op in OPS for sfx in ("", "_workspace_bytes")] + \
+          ["d2b_peer_alloc", "d2b_peer_free", "d2b_peer_export", "d2b_peer_open", "d2b_peer_close"]
 
 
 class D2BError(RuntimeError):
@@ -350,3 +365,70 @@ def device_of(*tensors):
         if isinstance(t, torch.Tensor) and t.is_cuda:
             return t.device
     return default_device()
+
+
+# ---------------------------------------------------------------- peer-memory arenas (CUDA IPC; sharding.PeerGatherPlan)
+def _peer_check(rc, what):
+    if rc != 0:
+        L = lib()
+        raise D2BError(f"{what}: {L.d2b_status_string(rc).decode()}: {L.d2b_last_error().decode()}")
+
+
+def peer_alloc(nbytes, device):
+    """A zero-filled cudaMalloc arena on `device` that other processes of the node can map; returns its address."""
+    L = lib()
+    L.d2b_peer_alloc.argtypes = [C.c_size_t, C.POINTER(_vp)]
+    out = _vp()
+    with torch.cuda.device(device):
+        _peer_check(L.d2b_peer_alloc(int(nbytes), C.byref(out)), "d2b_peer_alloc")
+    return int(out.value)
+
+
+def peer_free(address, device):
+    L = lib()
+    L.d2b_peer_free.argtypes = [_vp]
+    with torch.cuda.device(device):
+        _peer_check(L.d2b_peer_free(_vp(address)), "d2b_peer_free")
+
+
+def peer_export(address, device):
+    """The CUDA IPC handle (bytes) of an arena of this process."""
+    L = lib()
+    L.d2b_peer_export.argtypes = [_vp, C.c_char_p]
+    buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+    with torch.cuda.device(device):
+        _peer_check(L.d2b_peer_export(_vp(address), buf), "d2b_peer_export")
+    return bytes(buf.raw)
+
+
+def peer_open(handle, device):
+    """Map another process's arena into this one (peer access over NVLink); returns the local address."""
+    L = lib()
+    L.d2b_peer_open.argtypes = [C.c_char_p, C.POINTER(_vp)]
+    out = _vp()
+    with torch.cuda.device(device):
+        _peer_check(L.d2b_peer_open(bytes(handle), C.byref(out)), "d2b_peer_open")
+    return int(out.value)
+
+
+def peer_close(address, device):
+    L = lib()
+    L.d2b_peer_close.argtypes = [_vp]
+    with torch.cuda.device(device):
+        _peer_check(L.d2b_peer_close(_vp(address)), "d2b_peer_close")
+
+
+def peer_copy(segments, device, epoch_counter, ticket, error_flag, wait_flags=(), wait_lag=0, signal_flags=(),
+              timeout_ms=2000):
+    """d2b_peer_copy on torch's current stream: [wait on flags] -> copy `segments` [(src, dst, nbytes) addresses]
+    -> [raise flags].  All addresses are plain ints (this GPU's memory or mapped peer memory)."""
+    segs = (CopySegment * max(len(segments), 1))()
+    for i, (src, dst, n) in enumerate(segments):
+        segs[i].src, segs[i].dst, segs[i].bytes = int(src), int(dst), int(n)
+    wf = (_vp * max(len(wait_flags), 1))(*[int(a) for a in wait_flags])
+    sf = (_vp * max(len(signal_flags), 1))(*[int(a) for a in signal_flags])
+    p = PeerCopyParams(segments=segs, num_segments=len(segments), wait_flags=wf, num_wait=len(wait_flags),
+                       wait_lag=int(wait_lag), signal_flags=sf, num_signal=len(signal_flags),
+                       epoch_counter=int(epoch_counter), ticket=int(ticket), error_flag=int(error_flag),
+                       timeout_ms=int(timeout_ms))
+    call("peer_copy", p, device)

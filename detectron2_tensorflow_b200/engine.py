@@ -131,7 +131,7 @@ class MaskRCNNPostBackbone(object):
         return dict(proposals=props, box_feats=box_feats, dets=dets, mask_feats=mask_feats)
 
     # ------------------------------------------------------------------ CUDA-graphed, chunk-concurrent step
-    def capture(self, x, chunks=4, epilogue=None):
+    def capture(self, x, chunks=4, epilogue=None, epilogue_warmup=True):
         """Capture the device-resident step as ONE CUDA graph in which the batch is cut into `chunks` image blocks
         that run on their own streams (forked from / joined to the capturing stream).  Images are independent, so
         the latency-bound proposal / post-processing kernels of one block overlap the HBM-bound ROIAlign of
@@ -156,7 +156,7 @@ class MaskRCNNPostBackbone(object):
                 d[k] = [t[b:e] for t in x[k]]
             return d
 
-        def step():
+        def step(with_epilogue=True):
             cur = torch.cuda.current_stream(dev)
             start = torch.cuda.Event()
             start.record(cur)
@@ -167,7 +167,7 @@ class MaskRCNNPostBackbone(object):
                     outs.append(self.flatten_outputs(self(cut(b, e))))
             for s in streams:
                 cur.wait_stream(s)
-            if epilogue is not None:
+            if epilogue is not None and with_epilogue:
                 epilogue(outs)
             return outs
 
@@ -175,7 +175,7 @@ class MaskRCNNPostBackbone(object):
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):  # warm-up outside the capture: workspaces, grids, smem attributes
             for _ in range(2):
-                step()
+                step(epilogue_warmup)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
@@ -184,11 +184,12 @@ class MaskRCNNPostBackbone(object):
             outs = step()
         return GraphedStep(graph, outs, bounds, nv.kernel_launch_count() - l0)
 
-    def pipeline(self, x, chunks=4, depth=2, epilogues=None):
+    def pipeline(self, x, chunks=4, depth=2, epilogues=None, epilogue_warmup=True):
         """`depth` independent captures of the step over the same static inputs `x` -> StepPipeline
         (`epilogues[i]`: the capture epilogue of step i)."""
         depth = max(1, int(depth))
-        return StepPipeline([self.capture(x, chunks, epilogues[i] if epilogues else None) for i in range(depth)],
+        return StepPipeline([self.capture(x, chunks, epilogues[i] if epilogues else None, epilogue_warmup)
+                             for i in range(depth)],
                             x["shapes"].device)
 
     # ------------------------------------------------------------------ host-buffer step

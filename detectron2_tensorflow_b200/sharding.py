@@ -206,3 +206,157 @@ class GatherPlan(object):
                 for k in self.spec:
                     self.out[k][self.begin[r]:self.begin[r] + n].copy_(self._view(self.recv[r], k, n))
         return self.out
+
+
+def gather_offsets(spec, layout):
+    """Byte layout of one rank's receive slot: {key: (offset, bytes per image)}, slot size.  One region per key sized
+    for the LONGEST image block (256-byte aligned), so the offsets are the same for every rank."""
+    longest = max(lay[-1][1] - lay[0][0] for lay in layout)
+    offsets, off = {}, 0
+    for k, (shape, dtype) in spec.items():
+        per = torch.empty(0, dtype=dtype).element_size()
+        for d in shape:
+            per *= int(d)
+        offsets[k] = (off, per)
+        off += (longest * per + 255) // 256 * 256
+    return offsets, max(off, 256)
+
+
+def pack_segments(block_addrs, layout, rank, offsets, slot_addr):
+    """Copy table of a sender: block_addrs[i][key] = address of this rank's [e - b, ...] tensor of image block
+    layout[rank][i]; every tensor goes to its rows of the receive slot at `slot_addr` (rank 0's memory).
+    Returns [(src, dst, nbytes)]."""
+    begin = layout[rank][0][0]
+    segs = []
+    for (b, e), blk in zip(layout[rank], block_addrs):
+        if e > b:
+            for k, (off, per) in offsets.items():
+                segs.append((blk[k], slot_addr + off + (b - begin) * per, (e - b) * per))
+    return segs
+
+
+def unpack_segments(slot_addrs, layout, offsets, out_addrs, ranks=None):
+    """Copy table of rank 0: the rows of every rank's receive slot go to that rank's image rows of the full-batch
+    tensors (out_addrs[key] = address of the [N, ...] tensor).  Returns [(src, dst, nbytes)]."""
+    segs = []
+    for r in (range(len(layout)) if ranks is None else ranks):
+        begin, n = layout[r][0][0], layout[r][-1][1] - layout[r][0][0]
+        if n > 0:
+            for k, (off, per) in offsets.items():
+                segs.append((slot_addrs[r] + off, out_addrs[k] + begin * per, n * per))
+    return segs
+
+
+class PeerGatherPlan(object):
+    """The same steady-state gather as GatherPlan, over NVLink PEER MEMORY instead of a collective (CUDA only):
+
+      pack()    ONE kernel on every sender: waits for rank 0's acknowledgement of the previous step, stores this
+                rank's block tensors straight into its receive slot in rank 0's memory, raises its flag there.  On
+                rank 0 the same kernel copies the local blocks into the full-batch tensors.  Capture it inside the
+                step's CUDA graph.
+      gather()  nothing to do (the transfer is the pack kernel's stores).
+      unpack()  rank 0, ONE kernel: waits for every sender's flag of this step, scatters the slots into `out[key]`
+                ([N, ...], image order), acknowledges into the senders' arenas.  Capturable too.
+
+    Every rank must run pack() / unpack() the same number of times (the epoch lives in device memory and is advanced
+    by the kernels).  A peer that never shows up makes the waiting kernel give up after `timeout_ms` and set the
+    error flag, which `check()` turns into an exception: the GPU never hangs.  Arena layout (one cudaMalloc per
+    rank, mapped by CUDA IPC): flags[world] | ack | counters | receive slots[world]; 128 bytes per flag."""
+
+    FLAG = 128
+
+    def __init__(self, spec, layout, device, group=None, timeout_ms=2000):
+        from . import _native as nv
+        self._nv = nv
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = device
+        self.layout = layout
+        self.spec = dict(spec)
+        self.timeout_ms = int(timeout_ms)
+        self.offsets, self.nbytes = gather_offsets(self.spec, layout)
+        F = self.FLAG
+        self._flags_off, self._ack_off, self._ctr_off = 0, self.world * F, (self.world + 1) * F
+        self._slot_off = (self.world + 1) * F + 8 * F
+        arena_bytes = self._slot_off + (self.world * self.nbytes if self.rank == 0 else 0)
+        self.arena = nv.peer_alloc(arena_bytes, device)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, nv.peer_export(self.arena, device), group=group)
+        self._mapped = {}
+        if self.rank == 0:
+            for r in range(1, self.world):
+                self._mapped[r] = nv.peer_open(handles[r], device)
+        else:
+            self._mapped[0] = nv.peer_open(handles[0], device)
+        n_total = layout[-1][-1][1]
+        self.out = {k: torch.zeros((n_total,) + tuple(shape), dtype=dtype, device=device)
+                    for k, (shape, dtype) in self.spec.items()} if self.rank == 0 else None
+        self._keep = []
+        nv.peer_copy([], device, self._ctr(5), self._ctr(6), self._ctr(7))  # loads the kernel outside any capture
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)
+
+    # counters of this rank's arena: 0 = pack epoch, 1 = pack ticket, 2 = unpack epoch, 3 = unpack ticket, 4 = error
+    def _ctr(self, i):
+        return self.arena + self._ctr_off + i * self.FLAG
+
+    def pack(self, blocks):
+        """blocks[i] = dict of [e - b, ...] contiguous tensors for layout[rank][i]."""
+        nv = self._nv
+        addrs = []
+        for blk in blocks:
+            for k in self.spec:
+                assert blk[k].is_contiguous() and blk[k].dtype == self.spec[k][1]
+            addrs.append({k: blk[k].data_ptr() for k in self.spec})
+            self._keep.append([blk[k] for k in self.spec])
+        if self.rank == 0:
+            segs = []  # the local blocks go straight to their rows of the full-batch tensors
+            for (b, e), blk in zip(self.layout[0], addrs):
+                for k, (off, per) in self.offsets.items():
+                    segs.append((blk[k], self.out[k].data_ptr() + b * per, (e - b) * per))
+            nv.peer_copy(segs, self.device, self._ctr(0), self._ctr(1), self._ctr(4), timeout_ms=self.timeout_ms)
+        else:
+            base0 = self._mapped[0]
+            slot = base0 + self._slot_off + self.rank * self.nbytes
+            segs = pack_segments(addrs, self.layout, self.rank, self.offsets, slot)
+            nv.peer_copy(segs, self.device, self._ctr(0), self._ctr(1), self._ctr(4),
+                         wait_flags=[self.arena + self._ack_off], wait_lag=1,
+                         signal_flags=[base0 + self._flags_off + self.rank * self.FLAG], timeout_ms=self.timeout_ms)
+
+    def gather(self):
+        return None
+
+    def unpack(self):
+        if self.rank != 0:
+            return None
+        nv = self._nv
+        slots = [self.arena + self._slot_off + r * self.nbytes for r in range(self.world)]
+        segs = unpack_segments(slots, self.layout, self.offsets, {k: t.data_ptr() for k, t in self.out.items()},
+                               ranks=range(1, self.world))
+        nv.peer_copy(segs, self.device, self._ctr(2), self._ctr(3), self._ctr(4),
+                     wait_flags=[self.arena + self._flags_off + r * self.FLAG for r in range(1, self.world)], wait_lag=0,
+                     signal_flags=[self._mapped[r] + self._ack_off for r in range(1, self.world)],
+                     timeout_ms=self.timeout_ms)
+        return self.out
+
+    def check(self):
+        """Raise if a wait of this rank ever timed out (host sync)."""
+        import ctypes as C
+        err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._nv.peer_copy([(self._ctr(4), err.data_ptr(), 4)], self.device, self._ctr(5), self._ctr(6), self._ctr(7))
+        if int(err.item()) != 0:
+            raise self._nv.D2BError("PeerGatherPlan: a wait on a peer's flag timed out (ranks out of step or a peer died)")
+
+    def close(self):
+        """Unmap the peers' arenas and free this rank's (collective: every rank calls it)."""
+        if self.arena is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        for a in self._mapped.values():
+            self._nv.peer_close(a, self.device)
+        self._mapped = {}
+        dist.barrier(group=self.group)
+        self._nv.peer_free(self.arena, self.device)
+        self.arena = None

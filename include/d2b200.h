@@ -709,6 +709,59 @@ D2B_API size_t d2b_solo_upsample_workspace_bytes(const d2b_solo_upsample_params*
 D2B_API int d2b_solo_upsample(const d2b_solo_upsample_params* p, void* workspace, size_t workspace_bytes,
                               d2b_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Final gather of the fixed-size padded per-image outputs to rank 0 (the reference's
+ * tf.map_fn stages keep every image independent: rpn_outputs.py:123, fast_rcnn.py:171), done over NVLink
+ * PEER MEMORY instead of a library collective: every rank maps one cudaMalloc'd arena of every other rank
+ * (CUDA IPC), the sender's pack kernel stores its block straight into rank 0's receive slot and then raises
+ * a flag there; rank 0's unpack kernel waits for the flags, scatters the slots into the full-batch tensors
+ * and acknowledges into the senders' arenas (so that a sender never overwrites a slot that is still being
+ * read).  One launch per rank per step, no host round trip; both launches can be captured in CUDA graphs
+ * (the epoch lives in device memory and is advanced by the kernel).
+ *
+ *   d2b_peer_alloc/free      an arena that can be exported (plain cudaMalloc, zero-filled)
+ *   d2b_peer_export/open/close   CUDA IPC handle (D2B_PEER_HANDLE_BYTES opaque bytes) of an arena / its
+ *                            mapping in another process of the same node (peer access is enabled lazily)
+ *   d2b_peer_copy            the kernel: [wait] -> copy segments -> [signal]
+ *
+ * d2b_peer_copy: epoch = *epoch_counter + 1.  If num_wait > 0, waits until every wait_flags[i] >=
+ * epoch - wait_lag (flags live in THIS GPU's memory; a wait that exceeds timeout_ms sets *error_flag = 1
+ * and the kernel goes on, so a lost peer can never hang the GPU).  Then copies every segment (src / dst are
+ * device pointers of this GPU or mapped peer memory; any alignment), makes the copies visible system-wide,
+ * stores `epoch` into every signal_flags[i] (peer or local memory) and writes *epoch_counter = epoch.
+ * `segments`, `wait_flags` pointer values and `signal_flags` are read on the HOST at call time (they travel
+ * as kernel parameters); at most D2B_PEER_MAX_SEGMENTS segments and D2B_PEER_MAX_FLAGS flags per call.
+ * ---------------------------------------------------------------------- */
+#define D2B_PEER_HANDLE_BYTES 64
+#define D2B_PEER_MAX_SEGMENTS 112
+#define D2B_PEER_MAX_FLAGS 16
+typedef struct {
+  const void* src;
+  void* dst;
+  uint64_t bytes;
+} d2b_copy_segment;
+typedef struct {
+  const d2b_copy_segment* segments; /* HOST array */
+  int32_t num_segments;
+  const uint64_t* const* wait_flags; /* HOST array of device pointers (this GPU's memory) */
+  int32_t num_wait;
+  int32_t wait_lag;                  /* 0: wait for this epoch (receiver); 1: for the previous one (sender's ack) */
+  uint64_t* const* signal_flags;     /* HOST array of device pointers (local or peer memory) */
+  int32_t num_signal;
+  uint64_t* epoch_counter;           /* device, this GPU; starts at 0 */
+  uint32_t* ticket;                  /* device, this GPU; zero; scratch of the kernel */
+  int32_t* error_flag;               /* device, this GPU; set to 1 when a wait timed out */
+  uint32_t timeout_ms;               /* 0 = 2000 */
+} d2b_peer_copy_params;
+D2B_API int d2b_peer_alloc(size_t bytes, void** ptr);
+D2B_API int d2b_peer_free(void* ptr);
+D2B_API int d2b_peer_export(void* ptr, unsigned char handle[D2B_PEER_HANDLE_BYTES]);
+D2B_API int d2b_peer_open(const unsigned char handle[D2B_PEER_HANDLE_BYTES], void** ptr);
+D2B_API int d2b_peer_close(void* ptr);
+D2B_API size_t d2b_peer_copy_workspace_bytes(const d2b_peer_copy_params* p);
+D2B_API int d2b_peer_copy(const d2b_peer_copy_params* p, void* workspace, size_t workspace_bytes,
+                          d2b_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

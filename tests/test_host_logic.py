@@ -52,3 +52,40 @@ def test_synthetic_shapes_match_survey_appendix_b():
     b, idx = syn.rois(2, 10)
     assert b.shape == (20, 4) and idx[:, 0].tolist() == [0] * 10 + [1] * 10
     assert np.all(b[:, 2] >= b[:, 0]) and np.all(b[:, 3] >= b[:, 1])
+
+
+def test_peer_gather_segment_tables():
+    """sharding.pack_segments / unpack_segments (the copy tables of PeerGatherPlan's two kernels), executed here
+    with memmove on host arrays: every rank's blocks -> its receive slot -> the full-batch tensors == concatenation
+    in image order, for even and uneven partitions and 1..3 image blocks per rank."""
+    import ctypes
+    import numpy as np
+    import torch
+    from detectron2_tensorflow_b200 import sharding
+    spec = {"boxes": ((5, 4), torch.float32), "valid": ((5,), torch.bool), "classes": ((3,), torch.int64),
+            "odd": ((7,), torch.uint8)}
+    np_dtype = {torch.float32: np.float32, torch.bool: np.bool_, torch.int64: np.int64, torch.uint8: np.uint8}
+    rng = np.random.default_rng(0)
+    for n_images, world, chunks in ((16, 8, 1), (16, 4, 2), (7, 3, 2), (5, 4, 3), (3, 4, 1)):
+        layout = sharding.block_layout(n_images, world, lambda k: chunks)
+        offsets, nbytes = sharding.gather_offsets(spec, layout)
+        full = {k: rng.integers(0, 255, size=(n_images,) + shape).astype(np_dtype[dt]) for k, (shape, dt) in spec.items()}
+        slots = [np.zeros(nbytes, np.uint8) for _ in range(world)]
+        out = {k: np.zeros_like(v) for k, v in full.items()}
+        keep = []
+        for r in range(world):
+            blocks = [{k: np.ascontiguousarray(v[b:e]) for k, v in full.items()} for (b, e) in layout[r]]
+            keep.append(blocks)
+            segs = sharding.pack_segments([{k: a.ctypes.data for k, a in blk.items()} for blk in blocks], layout, r,
+                                          offsets, slots[r].ctypes.data)
+            lo, hi = slots[r].ctypes.data, slots[r].ctypes.data + nbytes
+            for src, dst, nb in segs:
+                assert lo <= dst and dst + nb <= hi
+                ctypes.memmove(dst, src, nb)
+        segs = sharding.unpack_segments([s.ctypes.data for s in slots], layout, offsets,
+                                        {k: a.ctypes.data for k, a in out.items()})
+        assert len(segs) <= 112
+        for src, dst, nb in segs:
+            ctypes.memmove(dst, src, nb)
+        for k in full:
+            assert np.array_equal(out[k], full[k]), (n_images, world, chunks, k)

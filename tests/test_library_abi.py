@@ -26,7 +26,7 @@ def _declared_symbols():
 def test_header_symbols_exported(lib):
     from detectron2_tensorflow_b200 import _native
     syms = _declared_symbols()
-    assert len(syms) == 4 + 2 * len(_native.OPS)
+    assert len(syms) == 4 + 2 * len(_native.OPS) + 5  # + the five d2b_peer_* arena calls
     assert sorted(_native.EXPORTS) == syms
     for s in syms:
         assert hasattr(lib, s), s
@@ -50,7 +50,7 @@ def test_struct_layout_matches_header(lib, tmp_path):
              "solo_mask_encode": "d2b_solo_mask_encode_params", "solo_postprocess": "d2b_solo_postprocess_params",
              "solo_dynamic_masks": "d2b_solo_dynamic_masks_params",
              "solo_upsample": "d2b_solo_upsample_params", "solo_select": "d2b_solo_select_params",
-             "mask_rcnn_inference": "d2b_mask_rcnn_inference_params"}
+             "mask_rcnn_inference": "d2b_mask_rcnn_inference_params", "peer_copy": "d2b_peer_copy_params"}
     assert set(names) == set(_native.OPS)
     prog = '#include <stdio.h>\n#include "d2b200.h"\nint main(){' + "".join(
         f'printf("{op} %zu\\n", sizeof({st}));' for op, st in names.items()) + "return 0;}"

@@ -50,14 +50,35 @@ full = sharding.gather_to_rank0(small, N)
 e1.record()
 torch.cuda.synchronize()
 gather_ms = e0.elapsed_time(e1)
+# the same gather over NVLink peer memory (sharding.PeerGatherPlan: pack kernel with remote stores + flags, unpack kernel
+# on rank 0), several steps so that the acknowledgement hand-shake is exercised
+from detectron2_tensorflow_b200.engine import GATHER_KEYS
+layout = sharding.block_layout(N, world)
+plan = sharding.PeerGatherPlan(eng.gather_spec(), layout, dev)
+blk = {k: out[k].contiguous() for k in GATHER_KEYS}
+peer_ms = []
+for step in range(5):
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    plan.pack([blk])
+    plan.unpack()
+    e1.record()
+    torch.cuda.synchronize()
+    peer_ms.append(e0.elapsed_time(e1))
+plan.check()
+peer_full = {k: v.clone() for k, v in plan.out.items()} if rank == 0 else None
+plan.close()
 res = None
 if rank == 0:
     ref = MaskRCNNPostBackbone.flatten_outputs(eng(to_dev(0, N)))
     same = {k: bool(torch.equal(full[k], ref[k].to(torch.uint8) if ref[k].dtype == torch.bool else ref[k])) for k in full}
+    same_peer = {k: bool(torch.equal(peer_full[k], ref[k])) for k in GATHER_KEYS}
     nbytes = sum(v.numel() * v.element_size() for v in full.values())
     res = {"check": "sharded run + NCCL gather == single-GPU run (byte-identical)", "world": world, "images": N,
            "blocks": [sharding.image_block(N, world, r) for r in range(world)], "identical": same,
-           "all_identical": all(same.values()), "gathered_bytes": nbytes, "gather_ms": gather_ms}
+           "all_identical": all(same.values()) and all(same_peer.values()), "gathered_bytes": nbytes,
+           "gather_ms": gather_ms, "peer_memory_gather_identical": same_peer, "peer_memory_gather_ms_per_step": peer_ms}
     print(json.dumps(res))
 dist.barrier()
 dist.destroy_process_group()
