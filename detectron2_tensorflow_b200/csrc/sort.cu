@@ -9,6 +9,8 @@
 // bitonic network in global memory.  The EFFECTIVE length of a segment (next power of two of its
 // live count, read on the device) bounds the work: tiles and stages beyond it are skipped, so a
 // padded capacity (e.g. Rmax*K candidates of Fast R-CNN) costs nothing when few entries are live.
+// Inside a tile a thread keeps 1-8 consecutive keys in registers: strides inside the thread and inside the warp
+// (shuffles) need no barrier; only strides of 32 threads or more go through shared memory.
 #include "kernels.cuh"
 
 namespace d2b {
@@ -29,6 +31,96 @@ __device__ __forceinline__ int eff_len(const int32_t* seg_len, int seg, int P) {
   return e;
 }
 
+// One compare-exchange of the bitonic network on register values.
+__device__ __forceinline__ void cmpx(u64& lo, u64& hi, bool desc) {
+  const u64 a = lo, b = hi;
+  if (desc ? (a < b) : (a > b)) { lo = b; hi = a; }
+}
+
+// Steps j = jstart .. 1 of merge phase k on the E consecutive keys r[] a thread holds (index base + e): strides
+// >= E through warp shuffles (jstart <= 16 E), strides < E inside the thread.  No barrier, no shared memory.
+template <int E>
+__device__ __forceinline__ void low_steps(u64 (&r)[E], int base, int t0, int k, int jstart) {
+  for (int j = jstart; j >= E; j >>= 1) {
+    const int lane_mask = j / E;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const u64 mine = r[e];
+      const u64 other = __shfl_xor_sync(0xffffffffu, mine, lane_mask);
+      const int i = base + e;
+      const bool keep_max = ((((t0 + i) & k) == 0) == ((i & j) == 0));  // descending pair: the lower index keeps the max
+      const u64 mx = mine > other ? mine : other, mn = mine > other ? other : mine;
+      r[e] = keep_max ? mx : mn;
+    }
+  }
+#pragma unroll
+  for (int j = E / 2; j > 0; j >>= 1) {
+    if (j <= jstart) {
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        if ((e & j) == 0) cmpx(r[e], r[e | j], ((t0 + base + e) & k) == 0);
+    }
+  }
+}
+
+// Full bitonic sort of the tl keys in s[] (tl = a power of two, tl / E <= blockDim threads hold E keys each).
+// Merge phases up to k = 32 E run entirely in registers; later phases do their long strides (>= 32 E) in shared
+// memory two levels per barrier and the rest in registers: ~20 barriers for 4,096 keys instead of 78.
+template <int E>
+__device__ __forceinline__ void sort_tile(u64* s, const int tl, const int t0) {
+  const int t = threadIdx.x;
+  const int nact = tl / E;
+  const bool warp_on = (t & ~31) < nact;
+  const int base = t * E;
+  u64 r[E];
+  if (warp_on) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) r[e] = (base + e < tl) ? s[base + e] : 0ull;
+    const int kA = tl < 32 * E ? tl : 32 * E;
+    for (int k = 2; k <= kA; k <<= 1) low_steps<E>(r, base, t0, k, k >> 1);
+    if (base < tl) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) s[base + e] = r[e];
+    }
+  }
+  __syncthreads();
+  for (int k = 64 * E; k <= tl; k <<= 1) {
+    int j = k >> 1;
+    for (; j >= 64 * E; j >>= 2) {  // strides j and j/2 on quads
+      const int j2 = j >> 1;
+      for (int q = t; q < tl / 4; q += blockDim.x) {
+        const int i = ((q & ~(j2 - 1)) << 2) | (q & (j2 - 1));
+        const bool desc = (((t0 + i) & k) == 0);
+        u64 a0 = s[i], a1 = s[i | j2], a2 = s[i | j], a3 = s[i | j | j2];
+        cmpx(a0, a2, desc); cmpx(a1, a3, desc);
+        cmpx(a0, a1, desc); cmpx(a2, a3, desc);
+        s[i] = a0; s[i | j2] = a1; s[i | j] = a2; s[i | j | j2] = a3;
+      }
+      __syncthreads();
+    }
+    if (j >= 32 * E) {  // one long stride left
+      for (int p = t; p < tl / 2; p += blockDim.x) {
+        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+        u64 a = s[i], b = s[i | j];
+        cmpx(a, b, ((t0 + i) & k) == 0);
+        s[i] = a; s[i | j] = b;
+      }
+      __syncthreads();
+      j >>= 1;
+    }
+    if (warp_on) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) r[e] = (base + e < tl) ? s[base + e] : 0ull;
+      low_steps<E>(r, base, t0, k, j);
+      if (base < tl) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) s[base + e] = r[e];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(kSortThreads) sort_local(u64* keys, int P, int tile, const int32_t* seg_len,
                                                            const int32_t* skip) {
   extern __shared__ u64 s[];
@@ -42,16 +134,10 @@ __global__ void __launch_bounds__(kSortThreads) sort_local(u64* keys, int P, int
   const int live = seg_len ? seg_len[seg] : P;
   for (int i = threadIdx.x; i < tl; i += kSortThreads) s[i] = (t0 + i < live) ? g[i] : 0ull;
   __syncthreads();
-  for (int k = 2; k <= tl; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int p = threadIdx.x; p < tl / 2; p += kSortThreads) {
-        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-        const bool desc = (((t0 + i) & k) == 0);
-        const u64 a = s[i], b = s[i | j];
-        if (desc ? (a < b) : (a > b)) { s[i] = b; s[i | j] = a; }
-      }
-      __syncthreads();
-    }
+  if (tl >= 8 * kSortThreads) sort_tile<8>(s, tl, t0);
+  else if (tl >= 4 * kSortThreads) sort_tile<4>(s, tl, t0);
+  else if (tl >= 2 * kSortThreads) sort_tile<2>(s, tl, t0);
+  else sort_tile<1>(s, tl, t0);
   for (int i = threadIdx.x; i < tl; i += kSortThreads) g[i] = s[i];
 }
 

@@ -86,6 +86,8 @@ class MaskRCNNPostBackbone(object):
         self.box_tf = Box2BoxTransform(box_weights)
         self.box_pooler = ROIPooler(box_resolution, list(scales), sampling_ratio, pooler_type)
         self.mask_pooler = ROIPooler(mask_resolution, list(scales), sampling_ratio, pooler_type)
+        # the per-level ROI counts are a training-time tf.summary (poolers.py:173); inference does not record them
+        self.box_pooler.record_level_counts = self.mask_pooler.record_level_counts = False
         self._grids = {}
         self._streams = {}
         self._host_out = {}

@@ -37,7 +37,7 @@ def _roi_align_call(features, scales, boxes, batch_idx, bidx_stride, output_size
     odt = fdt if out_dtype is None else out_dtype
     out = torch.empty((M, oh, ow, Cc), dtype=odt, device=dev)
     L = len(feats)
-    counts = torch.zeros(L, dtype=torch.int32, device=dev) if want_levels else None
+    counts = torch.empty(L, dtype=torch.int32, device=dev) if want_levels else None  # zeroed by the C entry
     levels = torch.empty(M, dtype=torch.int64, device=dev) if want_levels else None
     p = nv.RoiAlignParams()
     for l, f in enumerate(feats):

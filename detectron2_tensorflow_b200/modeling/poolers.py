@@ -68,6 +68,7 @@ class ROIPooler(Layer):
         self.canonical_level = canonical_level
         self.canonical_box_size = canonical_box_size
         self.last_level_counts = None  # per-level ROI counts of the last call ('roi_align/num_roi_level_k', :173)
+        self.record_level_counts = True  # False: skip that summary statistic (one memset + an atomic per ROI)
 
     def call(self, x, instances):
         """
@@ -87,6 +88,11 @@ class ROIPooler(Layer):
         if num_level_assignments == 1:
             return _roi_align_call(x, self.scales, instances.data.boxes, batch_idx, 1, self.output_size,
                                    self.sampling_ratio, self.aligned, True)
+        if not self.record_level_counts:
+            return _roi_align_call(
+                x, self.scales, instances.data.boxes, batch_idx, 1, self.output_size, self.sampling_ratio,
+                self.aligned, True, min_level=self.min_level, canonical_box_size=self.canonical_box_size,
+                canonical_level=self.canonical_level)
         out, counts, _ = _roi_align_call(
             x, self.scales, instances.data.boxes, batch_idx, 1, self.output_size, self.sampling_ratio,
             self.aligned, True, min_level=self.min_level, canonical_box_size=self.canonical_box_size,
