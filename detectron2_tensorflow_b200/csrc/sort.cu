@@ -63,24 +63,34 @@ __device__ __forceinline__ void low_steps(u64 (&r)[E], int base, int t0, int k, 
   }
 }
 
-// Full bitonic sort of the tl keys in s[] (tl = a power of two, tl / E <= blockDim threads hold E keys each).
-// Merge phases up to k = 32 E run entirely in registers; later phases do their long strides (>= 32 E) in shared
-// memory two levels per barrier and the rest in registers: ~20 barriers for 4,096 keys instead of 78.
+// Shared-memory slot of key i: a thread's E consecutive keys are E * 8 bytes apart from its neighbour's, which would be
+// an E-way bank conflict on every register load / store; one pad slot per E keys makes consecutive threads hit
+// consecutive bank pairs (stride E + 1, odd).
 template <int E>
-__device__ __forceinline__ void sort_tile(u64* s, const int tl, const int t0) {
+__device__ __forceinline__ int sort_phys(int i) { return E > 1 ? i + i / E : i; }
+
+// Full bitonic sort of the tl keys g_in[0..tl) (entries at or beyond `live` count as 0) into g_out, staged in s[]
+// (tl = a power of two, tl / E <= blockDim threads hold E keys each).  Merge phases up to k = 32 E run entirely in
+// registers; later phases do their long strides (>= 32 E) in shared memory two levels per barrier and the rest in
+// registers: ~20 barriers for 4,096 keys instead of 78.
+template <int E>
+__device__ __forceinline__ void sort_tile(u64* s, const u64* g_in, u64* g_out, const int live, const int tl, const int t0) {
   const int t = threadIdx.x;
+  auto ph = [](int i) { return sort_phys<E>(i); };
+  for (int i = t; i < tl; i += blockDim.x) s[ph(i)] = (t0 + i < live) ? g_in[i] : 0ull;
+  __syncthreads();
   const int nact = tl / E;
   const bool warp_on = (t & ~31) < nact;
   const int base = t * E;
   u64 r[E];
   if (warp_on) {
 #pragma unroll
-    for (int e = 0; e < E; ++e) r[e] = (base + e < tl) ? s[base + e] : 0ull;
+    for (int e = 0; e < E; ++e) r[e] = (base + e < tl) ? s[ph(base + e)] : 0ull;
     const int kA = tl < 32 * E ? tl : 32 * E;
     for (int k = 2; k <= kA; k <<= 1) low_steps<E>(r, base, t0, k, k >> 1);
     if (base < tl) {
 #pragma unroll
-      for (int e = 0; e < E; ++e) s[base + e] = r[e];
+      for (int e = 0; e < E; ++e) s[ph(base + e)] = r[e];
     }
   }
   __syncthreads();
@@ -91,34 +101,35 @@ __device__ __forceinline__ void sort_tile(u64* s, const int tl, const int t0) {
       for (int q = t; q < tl / 4; q += blockDim.x) {
         const int i = ((q & ~(j2 - 1)) << 2) | (q & (j2 - 1));
         const bool desc = (((t0 + i) & k) == 0);
-        u64 a0 = s[i], a1 = s[i | j2], a2 = s[i | j], a3 = s[i | j | j2];
+        u64 a0 = s[ph(i)], a1 = s[ph(i | j2)], a2 = s[ph(i | j)], a3 = s[ph(i | j | j2)];
         cmpx(a0, a2, desc); cmpx(a1, a3, desc);
         cmpx(a0, a1, desc); cmpx(a2, a3, desc);
-        s[i] = a0; s[i | j2] = a1; s[i | j] = a2; s[i | j | j2] = a3;
+        s[ph(i)] = a0; s[ph(i | j2)] = a1; s[ph(i | j)] = a2; s[ph(i | j | j2)] = a3;
       }
       __syncthreads();
     }
     if (j >= 32 * E) {  // one long stride left
       for (int p = t; p < tl / 2; p += blockDim.x) {
         const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-        u64 a = s[i], b = s[i | j];
+        u64 a = s[ph(i)], b = s[ph(i | j)];
         cmpx(a, b, ((t0 + i) & k) == 0);
-        s[i] = a; s[i | j] = b;
+        s[ph(i)] = a; s[ph(i | j)] = b;
       }
       __syncthreads();
       j >>= 1;
     }
     if (warp_on) {
 #pragma unroll
-      for (int e = 0; e < E; ++e) r[e] = (base + e < tl) ? s[base + e] : 0ull;
+      for (int e = 0; e < E; ++e) r[e] = (base + e < tl) ? s[ph(base + e)] : 0ull;
       low_steps<E>(r, base, t0, k, j);
       if (base < tl) {
 #pragma unroll
-        for (int e = 0; e < E; ++e) s[base + e] = r[e];
+        for (int e = 0; e < E; ++e) s[ph(base + e)] = r[e];
       }
     }
     __syncthreads();
   }
+  for (int i = t; i < tl; i += blockDim.x) g_out[i] = s[ph(i)];
 }
 
 __global__ void __launch_bounds__(kSortThreads) sort_local(u64* keys, int P, int tile, const int32_t* seg_len,
@@ -132,13 +143,10 @@ __global__ void __launch_bounds__(kSortThreads) sort_local(u64* keys, int P, int
   const int tl = tile < Pe ? tile : Pe;  // live part of this tile (a power of two)
   u64* g = keys + (size_t)seg * P + t0;
   const int live = seg_len ? seg_len[seg] : P;
-  for (int i = threadIdx.x; i < tl; i += kSortThreads) s[i] = (t0 + i < live) ? g[i] : 0ull;
-  __syncthreads();
-  if (tl >= 8 * kSortThreads) sort_tile<8>(s, tl, t0);
-  else if (tl >= 4 * kSortThreads) sort_tile<4>(s, tl, t0);
-  else if (tl >= 2 * kSortThreads) sort_tile<2>(s, tl, t0);
-  else sort_tile<1>(s, tl, t0);
-  for (int i = threadIdx.x; i < tl; i += kSortThreads) g[i] = s[i];
+  if (tl >= 8 * kSortThreads) sort_tile<8>(s, g, g, live, tl, t0);
+  else if (tl >= 4 * kSortThreads) sort_tile<4>(s, g, g, live, tl, t0);
+  else if (tl >= 2 * kSortThreads) sort_tile<2>(s, g, g, live, tl, t0);
+  else sort_tile<1>(s, g, g, live, tl, t0);
 }
 
 // Segments longer than one tile: one CTA finishes stages k = 2*tile .. Pe in global memory.
@@ -168,7 +176,7 @@ int sort_segments_desc(unsigned long long* keys, int S, int P, const int32_t* se
   if (S <= 0 || P <= 1) return D2B_OK;
   D2B_REQUIRE((P & (P - 1)) == 0, "sort: P=%d is not a power of two", P);
   const int tile = P < kTile ? P : kTile;
-  const size_t smem = (size_t)tile * sizeof(u64);
+  const size_t smem = (size_t)(tile + tile / 2) * sizeof(u64);  // + the pad slots of sort_phys (at most 1 per 2 keys)
   if (smem > 48 * 1024)
     D2B_CUDA(cudaFuncSetAttribute(sort_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sort_local<<<dim3(P / tile, S), kSortThreads, smem, st>>>(keys, P, tile, seg_len, skip);
