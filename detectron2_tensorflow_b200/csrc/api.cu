@@ -1,5 +1,6 @@
 // api.cu -- version, status strings and the thread-local error detail.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -10,6 +11,13 @@ void set_last_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("D2B_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }

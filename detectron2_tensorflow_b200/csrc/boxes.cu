@@ -9,6 +9,7 @@ typedef unsigned long long u64;
 // box_regression.py:95-123; one thread per (box, class-slot)
 __global__ void apply_deltas_kernel(const float4* deltas, const float4* boxes, long long n, int k, float wy,
                                     float wx, float wh, float ww, float clampv, float4* out) {
+  grid_dep_sync();
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * k) return;
   const long long i = t / k;
@@ -72,10 +73,10 @@ extern "C" int d2b_apply_deltas(const d2b_apply_deltas_params* p, void*, size_t,
   D2B_REQUIRE(p->deltas && p->boxes && p->out, "apply_deltas: NULL pointer");
   const long long total = p->n * p->k;
   D2B_REQUIRE(total < (1ll << 31) * 256, "apply_deltas: too many boxes");
-  apply_deltas_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  D2B_CUDA(launch_pdl(apply_deltas_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 0,
       reinterpret_cast<const float4*>(p->deltas), reinterpret_cast<const float4*>(p->boxes), p->n, p->k,
       p->weights[0], p->weights[1], p->weights[2], p->weights[3], p->scale_clamp,
-      reinterpret_cast<float4*>(p->out));
+      reinterpret_cast<float4*>(p->out)));
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }

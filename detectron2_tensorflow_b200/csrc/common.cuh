@@ -67,6 +67,51 @@ __device__ __forceinline__ void d2b_prof_stamp(int slot) {
 #define D2B_PROF(cond, slot) do { } while (0)
 #endif
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// The latency chains (proposal stage -> pooler -> detection tail) are sequences of short kernels; with the
+// programmatic-stream-serialization attribute the NEXT kernel's CTAs are scheduled while the current one drains,
+// and `grid_dep_sync()` at the top of every such kernel blocks until the predecessor has completed and its writes
+// are visible.  Rules: (1) a kernel launched through launch_pdl() calls grid_dep_sync() before it touches global
+// memory -- every thread, unconditionally; (2) kernels launched the ordinary way are unaffected.  D2B_PDL=0 in the
+// environment turns the attribute off (A/B timing).
+bool pdl_enabled();
+__device__ __forceinline__ void grid_dep_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+struct LaunchCfg {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[2];
+  LaunchCfg(dim3 grid, dim3 block, size_t smem, cudaStream_t st, unsigned cluster_x = 0) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 0;
+    if (cluster_x) {
+      attr[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
+      attr[cfg.numAttrs].val.clusterDim.x = cluster_x;
+      attr[cfg.numAttrs].val.clusterDim.y = 1;
+      attr[cfg.numAttrs].val.clusterDim.z = 1;
+      ++cfg.numAttrs;
+    }
+    if (pdl_enabled()) {
+      attr[cfg.numAttrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
+      ++cfg.numAttrs;
+    }
+  }
+};
+// launch_pdl(kernel, grid, block, smem, stream, cluster_x, args...): the kernel MUST call grid_dep_sync() first.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     unsigned cluster_x, Args&&... args) {
+  LaunchCfg L(grid, block, smem, st, cluster_x);
+  return cudaLaunchKernelEx(&L.cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Bump allocator over the caller's workspace (256-byte aligned slices).

@@ -89,6 +89,7 @@ __device__ __forceinline__ FBox filter_box(const CBox c, float kf) {
 // warp-private shared-memory slice (filter record, canonical box, area), so only __syncwarp is needed.
 __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* boxes, const int32_t* counts, int n,
                                                                  int W, float thr, u64* mask) {
+  grid_dep_sync();
   __shared__ float4 s_flt[kMaskThreads / 32][64];  // (ylo, xlo, yhi, xhi) of the shrunk box
   __shared__ float4 s_box[kMaskThreads / 32][64];
   __shared__ float s_area[kMaskThreads / 32][64];
@@ -521,7 +522,8 @@ int nms_sorted(const float* boxes, const int32_t* counts, int S, int n, int max_
   // few segments: spread a row block's column blocks over up to 4 CTAs so that the grid still fills the SMs
   int csplit = 1;
   while (csplit < 4 && (long long)((W + 1) / 2) * S * csplit * 2 <= 2 * 148 && csplit * 8 < W) csplit *= 2;
-  nms_mask_kernel<<<dim3((W + 1) / 2, S, csplit), kMaskThreads, 0, st>>>(b4, counts, n, W, thr, mask);
+  D2B_CUDA(launch_pdl(nms_mask_kernel, dim3((W + 1) / 2, S, csplit), dim3(kMaskThreads), 0, st, 0, b4, counts, n, W, thr,
+                      mask));
   D2B_LAUNCH_CHECK();
   if (!sweep) return D2B_OK;  // the caller runs its own sweep over the mask (fused with the proposal merge)
   if (W <= kColSweepMaxW)

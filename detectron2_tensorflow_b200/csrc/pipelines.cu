@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(kTailThreads) det_tail_kernel(F f, const u64* 
                                                                 float4* out_boxes, float* out_scores, TCls* out_classes,
                                                                 uint8_t* out_valid, int32_t* out_roi, int32_t* out_num,
                                                                 u64* nms_in_total) {
+  grid_dep_sync();
   extern __shared__ __align__(16) unsigned char s_tail[];
   float4* s_kept = reinterpret_cast<float4*>(s_tail);          // [max_out] offset boxes of the kept candidates
   int32_t* s_keptj = reinterpret_cast<int32_t*>(s_kept + max_out);  // [max_out] their positions in the sorted list
@@ -339,9 +340,9 @@ int det_tail(F f, const u64* keys, const int32_t* count, const float* max_coord,
   const size_t smem = (size_t)max_out * (sizeof(float4) + sizeof(int32_t));
   if (smem > 40 * 1024)
     D2B_CUDA(cudaFuncSetAttribute(det_tail_kernel<F, TCls>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  det_tail_kernel<F, TCls><<<N, kTailThreads, smem, st>>>(f, keys, count, max_coord, maxkey, P, stride, agnostic, max_out,
-                                                          thr, out_boxes, out_scores, out_classes, out_valid, out_roi,
-                                                          out_num, nms_in_total);
+  D2B_CUDA(launch_pdl(det_tail_kernel<F, TCls>, dim3(N), dim3(kTailThreads), smem, st, 0, f, keys, count, max_coord, maxkey,
+                      P, stride, agnostic, max_out, thr, out_boxes, out_scores, out_classes, out_valid, out_roi, out_num,
+                      nms_in_total));
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }
@@ -400,6 +401,7 @@ __global__ void yolo_prep_kernel(const float* probs, int n, int K, float thresh,
 __global__ void frcnn_prep_kernel(const float4* boxes, const float* scores, const long long* indices, long long M,
                                   int N, int Rmax, int Kb, int K, const int32_t* shapes, float thresh, int P,
                                   u64* keys, int32_t* count, int32_t* slot_map, int* max_coord_bits) {
+  grid_dep_sync();
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   long long n = -1, r = 0, i = 0;
@@ -735,10 +737,10 @@ extern "C" int d2b_fast_rcnn_postprocess(const d2b_fast_rcnn_params* p, void* wo
   D2B_CUDA(cudaMemsetAsync(max_coord, 0, sizeof(float) * N, st));  // clipped coords are >= 0; padding rows are 0
   const long long MK = p->num_preds * p->num_classes;
   if (MK > 0) {
-    frcnn_prep_kernel<<<(unsigned)((MK + 255) / 256), 256, 0, st>>>(
+    D2B_CUDA(launch_pdl(frcnn_prep_kernel, dim3((unsigned)((MK + 255) / 256)), dim3(256), 0, st, 0,
         reinterpret_cast<const float4*>(p->boxes), p->scores, reinterpret_cast<const long long*>(p->indices),
         p->num_preds, N, p->rmax, p->num_bbox_reg_classes, p->num_classes, p->image_shapes, p->score_thresh, pl.P,
-        keys, count, slot_map, reinterpret_cast<int*>(max_coord));
+        keys, count, slot_map, reinterpret_cast<int*>(max_coord)));
     D2B_LAUNCH_CHECK();
   }
   rc = sort_segments_desc(keys, N, pl.P, count, st);

@@ -201,6 +201,7 @@ __device__ __forceinline__ void store_out(__nv_bfloat16* p, const float (&v)[E])
 // many samples per bin axis, 0 = generic loop.
 template <typename TIn, typename TOut, int GROUPS, int S1>
 __global__ void __launch_bounds__(kThreads) roi_align_kernel(const RoiAlignArgs a) {
+  grid_dep_sync();
   constexpr int E = Vec<TIn>::kElems;
   __shared__ Tap ty[kMaxSamples];
   __shared__ Tap tx[kMaxSamples];
@@ -411,13 +412,15 @@ int launch(const RoiAlignArgs& a, cudaStream_t st) {
   const dim3 grid((unsigned)a.M, (unsigned)((a.oh * a.ow + kBinsPerCta - 1) / kBinsPerCta)), block(kThreads);
   const int g = a.C / E;
   const int s1 = a.sr > 0 ? a.sr : 1;
-  if (g == 32 && s1 == 1) roi_align_kernel<TIn, TOut, 1, 1><<<grid, block, 0, st>>>(a);
-  else if (g == 64 && s1 == 1) roi_align_kernel<TIn, TOut, 2, 1><<<grid, block, 0, st>>>(a);
-  else if (g == 32 && s1 == 2) roi_align_kernel<TIn, TOut, 1, 2><<<grid, block, 0, st>>>(a);
-  else if (g == 64 && s1 == 2) roi_align_kernel<TIn, TOut, 2, 2><<<grid, block, 0, st>>>(a);
-  else if (g == 32) roi_align_kernel<TIn, TOut, 1, 0><<<grid, block, 0, st>>>(a);
-  else if (g == 64) roi_align_kernel<TIn, TOut, 2, 0><<<grid, block, 0, st>>>(a);
-  else roi_align_kernel<TIn, TOut, 0, 0><<<grid, block, 0, st>>>(a);
+  cudaError_t rc;
+  if (g == 32 && s1 == 1) rc = launch_pdl(roi_align_kernel<TIn, TOut, 1, 1>, grid, block, 0, st, 0, a);
+  else if (g == 64 && s1 == 1) rc = launch_pdl(roi_align_kernel<TIn, TOut, 2, 1>, grid, block, 0, st, 0, a);
+  else if (g == 32 && s1 == 2) rc = launch_pdl(roi_align_kernel<TIn, TOut, 1, 2>, grid, block, 0, st, 0, a);
+  else if (g == 64 && s1 == 2) rc = launch_pdl(roi_align_kernel<TIn, TOut, 2, 2>, grid, block, 0, st, 0, a);
+  else if (g == 32) rc = launch_pdl(roi_align_kernel<TIn, TOut, 1, 0>, grid, block, 0, st, 0, a);
+  else if (g == 64) rc = launch_pdl(roi_align_kernel<TIn, TOut, 2, 0>, grid, block, 0, st, 0, a);
+  else rc = launch_pdl(roi_align_kernel<TIn, TOut, 0, 0>, grid, block, 0, st, 0, a);
+  D2B_CUDA(rc);
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }

@@ -148,6 +148,7 @@ __device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* s_w, u
 
 __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, float4* seg_boxes, float* seg_scores,
                                                                   int32_t* seg_count, u64* nms_in_total) {
+  grid_dep_sync();
   extern __shared__ __align__(16) unsigned char s_raw_bytes[];
   unsigned* hist = reinterpret_cast<unsigned*>(s_raw_bytes);                         // [2][kHistStride], peers read it
   unsigned* fine = reinterpret_cast<unsigned*>(s_raw_bytes + kSelOffFine);           // [2048] pass 0 (peers read 8 bins)
@@ -684,6 +685,7 @@ __global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, floa
 __global__ void __launch_bounds__(kColSweepThreads) rpn_sweep_merge_kernel(
     RpnArgs a, const int32_t* seg_count, int W, int cap, const u64* mask, const float4* seg_boxes,
     const float* seg_scores, float4* out_boxes, float* out_logits, uint8_t* out_valid, int32_t* out_num) {
+  grid_dep_sync();
   extern __shared__ uint32_t s_keys[];  // [L][cap] score keys of every level's survivors, then [cap] u16 positions
   __shared__ int s_cnt;
   __shared__ int s_off[D2B_MAX_LEVELS + 1];
@@ -767,20 +769,8 @@ int rpn_select_fused(const RpnArgs& a, float4* seg_boxes, float* seg_scores, int
   const size_t smem = select_smem_bytes(a.P);
   if (smem > 48 * 1024)
     D2B_CUDA(cudaFuncSetAttribute(rpn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)rows * kSelCluster, 1, 1);
-  cfg.blockDim = dim3(kSelThreads, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kSelCluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  D2B_CUDA(cudaLaunchKernelEx(&cfg, rpn_select_kernel, a, seg_boxes, seg_scores, seg_count,
-                              reinterpret_cast<u64*>(nms_in_total)));
+  D2B_CUDA(launch_pdl(rpn_select_kernel, dim3((unsigned)rows * kSelCluster, 1, 1), dim3(kSelThreads, 1, 1), smem, st,
+                      kSelCluster, a, seg_boxes, seg_scores, seg_count, reinterpret_cast<u64*>(nms_in_total)));
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }
@@ -797,20 +787,10 @@ int rpn_sweep_merge_fused(const RpnArgs& a, const int32_t* seg_count, const unsi
   D2B_REQUIRE(smem <= 200 * 1024, "fused sweep: %d levels x %d survivors do not fit shared memory", a.L, cap);
   if (smem > 48 * 1024)
     D2B_CUDA(cudaFuncSetAttribute(rpn_sweep_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)rows, 1, 1);
-  cfg.blockDim = dim3(kColSweepThreads, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)a.L;  // one cluster per image (L <= D2B_MAX_LEVELS = 8: portable size)
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  D2B_CUDA(cudaLaunchKernelEx(&cfg, rpn_sweep_merge_kernel, a, seg_count, W, cap, reinterpret_cast<const u64*>(mask),
-                              seg_boxes, seg_scores, out_boxes, out_logits, out_valid, out_num));
+  // one cluster per image (L <= D2B_MAX_LEVELS = 8: portable size)
+  D2B_CUDA(launch_pdl(rpn_sweep_merge_kernel, dim3((unsigned)rows, 1, 1), dim3(kColSweepThreads, 1, 1), smem, st,
+                      (unsigned)a.L, a, seg_count, W, cap, reinterpret_cast<const u64*>(mask), seg_boxes, seg_scores,
+                      out_boxes, out_logits, out_valid, out_num));
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }

@@ -134,6 +134,7 @@ __device__ __forceinline__ void sort_tile(u64* s, const u64* g_in, u64* g_out, c
 
 __global__ void __launch_bounds__(kSortThreads) sort_local(u64* keys, int P, int tile, const int32_t* seg_len,
                                                            const int32_t* skip) {
+  grid_dep_sync();
   extern __shared__ u64 s[];
   const int seg = blockIdx.y;
   if (skip && skip[seg]) return;  // already in order
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_local(u64* keys, int P, int
 // Segments longer than one tile: one CTA finishes stages k = 2*tile .. Pe in global memory.
 __global__ void __launch_bounds__(kSortThreads) sort_big(u64* keys, int P, int tile, const int32_t* seg_len,
                                                          const int32_t* skip) {
+  grid_dep_sync();
   const int seg = blockIdx.x;
   if (skip && skip[seg]) return;
   const int Pe = eff_len(seg_len, seg, P);
@@ -179,10 +181,10 @@ int sort_segments_desc(unsigned long long* keys, int S, int P, const int32_t* se
   const size_t smem = (size_t)(tile + tile / 2) * sizeof(u64);  // + the pad slots of sort_phys (at most 1 per 2 keys)
   if (smem > 48 * 1024)
     D2B_CUDA(cudaFuncSetAttribute(sort_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sort_local<<<dim3(P / tile, S), kSortThreads, smem, st>>>(keys, P, tile, seg_len, skip);
+  D2B_CUDA(launch_pdl(sort_local, dim3(P / tile, S), dim3(kSortThreads), smem, st, 0, keys, P, tile, seg_len, skip));
   D2B_LAUNCH_CHECK();
   if (P > tile) {
-    sort_big<<<S, kSortThreads, 0, st>>>(keys, P, tile, seg_len, skip);
+    D2B_CUDA(launch_pdl(sort_big, dim3(S), dim3(kSortThreads), 0, st, 0, keys, P, tile, seg_len, skip));
     D2B_LAUNCH_CHECK();
   }
   return D2B_OK;
