@@ -72,8 +72,10 @@ __device__ __forceinline__ void d2b_prof_stamp(int slot) {
 // programmatic-stream-serialization attribute the NEXT kernel's CTAs are scheduled while the current one drains,
 // and `grid_dep_sync()` at the top of every such kernel blocks until the predecessor has completed and its writes
 // are visible.  Rules: (1) a kernel launched through launch_pdl() calls grid_dep_sync() before it touches global
-// memory -- every thread, unconditionally; (2) kernels launched the ordinary way are unaffected.  D2B_PDL=0 in the
-// environment turns the attribute off (A/B timing).
+// memory -- every thread, unconditionally; (2) kernels launched the ordinary way are unaffected.  MEASURED (B200,
+// profiles/r02aj_step_probe_*.jsonl): eager chains gain (Fast R-CNN post 87 -> 68 us at 2 images), but the step the
+// bench replays is a captured multi-stream graph and there the programmatic edges cost time (2 image blocks: 0.209 ->
+// 0.257 ms; 4 blocks of 16 images: 0.648 -> 0.701 ms), so the attribute is OFF unless D2B_PDL=1 is set.
 bool pdl_enabled();
 __device__ __forceinline__ void grid_dep_sync() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

@@ -280,15 +280,32 @@ class PeerGatherPlan(object):
         self._flags_off, self._ack_off, self._ctr_off = 0, self.world * F, (self.world + 1) * F
         self._slot_off = (self.world + 1) * F + 8 * F
         arena_bytes = self._slot_off + (self.world * self.nbytes if self.rank == 0 else 0)
-        self.arena = nv.peer_alloc(arena_bytes, device)
+        # set-up is collective: every step is followed by an agreement on its outcome, so that a rank whose CUDA IPC
+        # call fails (container without IPC, peer access unavailable) makes EVERY rank raise instead of leaving the
+        # others in a barrier
+        self.arena, self._mapped, err = None, {}, None
+        try:
+            self.arena = nv.peer_alloc(arena_bytes, device)
+            handle = nv.peer_export(self.arena, device)
+        except Exception as e:  # noqa: BLE001
+            handle, err = None, repr(e)
         handles = [None] * self.world
-        dist.all_gather_object(handles, nv.peer_export(self.arena, device), group=group)
-        self._mapped = {}
-        if self.rank == 0:
-            for r in range(1, self.world):
-                self._mapped[r] = nv.peer_open(handles[r], device)
-        else:
-            self._mapped[0] = nv.peer_open(handles[0], device)
+        dist.all_gather_object(handles, (handle, err), group=group)
+        if all(h is not None for h, _ in handles):
+            try:
+                if self.rank == 0:
+                    for r in range(1, self.world):
+                        self._mapped[r] = nv.peer_open(handles[r][0], device)
+                else:
+                    self._mapped[0] = nv.peer_open(handles[0][0], device)
+            except Exception as e:  # noqa: BLE001
+                err = repr(e)
+        status = [None] * self.world
+        dist.all_gather_object(status, err, group=group)
+        failed = [f"rank {r}: {handles[r][1] or status[r]}" for r in range(self.world) if handles[r][1] or status[r]]
+        if failed:
+            self._release()
+            raise nv.D2BError("PeerGatherPlan: peer-memory set-up failed (" + "; ".join(failed)[:400] + ")")
         n_total = layout[-1][-1][1]
         self.out = {k: torch.zeros((n_total,) + tuple(shape), dtype=dtype, device=device)
                     for k, (shape, dtype) in self.spec.items()} if self.rank == 0 else None
@@ -347,6 +364,20 @@ class PeerGatherPlan(object):
         self._nv.peer_copy([(self._ctr(4), err.data_ptr(), 4)], self.device, self._ctr(5), self._ctr(6), self._ctr(7))
         if int(err.item()) != 0:
             raise self._nv.D2BError("PeerGatherPlan: a wait on a peer's flag timed out (ranks out of step or a peer died)")
+
+    def _release(self):
+        for a in self._mapped.values():
+            try:
+                self._nv.peer_close(a, self.device)
+            except Exception:  # noqa: BLE001
+                pass
+        self._mapped = {}
+        if self.arena is not None:
+            try:
+                self._nv.peer_free(self.arena, self.device)
+            except Exception:  # noqa: BLE001
+                pass
+        self.arena = None
 
     def close(self):
         """Unmap the peers' arenas and free this rank's (collective: every rank calls it)."""
