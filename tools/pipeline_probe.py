@@ -12,7 +12,7 @@ dev = torch.device("cuda", 0)
 x = bench.to_torch(bench.make_host_inputs(16), dev=dev)
 eng = bench.make_engine()
 res = {}
-for chunks, depth in ((1, 1), (1, 2), (1, 3), (1, 4), (2, 2), (2, 3), (4, 1), (4, 2), (4, 3), (8, 2)):
+for chunks, depth in ((1, 1), (1, 3), (1, 4), (1, 6), (2, 3), (2, 4), (2, 6), (4, 1), (4, 2), (4, 3), (4, 4), (4, 6), (8, 2), (8, 3)):
     pipe = eng.pipeline(x, chunks=chunks, depth=depth)
     pipe.run(2 * depth)
     torch.cuda.synchronize()
