@@ -30,6 +30,9 @@ struct MnmsArgs {
   float nsigma;
   u64* packed;      // [B, n, Wd]
   unsigned* isum;   // [B, n] exact popcount
+  unsigned* wlo;    // [B, n] ~first / last non-zero word of a packed mask (0 / 0 when the mask is empty; the first
+  unsigned* whi;    //        word is kept inverted so that one memset(0) initialises everything and both ends grow by
+                    //        atomicMax): a pair's AND + POPC only runs over the intersection of the two ranges
   float* iou;       // [B, n, n]
   float* cmax;      // [B, n]
   float* out;
@@ -53,7 +56,11 @@ __global__ void __launch_bounds__(256) mnms_pack_kernel(MnmsArgs a) {
   if (lane == 0) {
     a.packed[((size_t)b * a.n + i) * a.Wd + word] = ((u64)hi << 32) | lo;
     const unsigned c = __popc(lo) + __popc(hi);
-    if (c) atomicAdd(a.isum + (size_t)b * a.n + i, c);
+    if (c) {
+      atomicAdd(a.isum + (size_t)b * a.n + i, c);
+      atomicMax(a.wlo + (size_t)b * a.n + i, ~(unsigned)word);
+      atomicMax(a.whi + (size_t)b * a.n + i, (unsigned)word);
+    }
   }
 }
 
@@ -64,10 +71,22 @@ __global__ void __launch_bounds__(256) mnms_popc_kernel(MnmsArgs a) {
   if (i >= rows_of(a, b)) return;
   const int lane = threadIdx.x & 31;
   const u64* pi = a.packed + ((size_t)b * a.n + i) * a.Wd;
-  unsigned c = 0;
-  for (int w = lane; w < a.Wd; w += 32) c += __popcll(pi[w]);
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if (lane == 0) a.isum[(size_t)b * a.n + i] = c;
+  unsigned c = 0, lo = 0xffffffffu, hi = 0u;
+  for (int w = lane; w < a.Wd; w += 32) {
+    const u64 v = pi[w];
+    c += __popcll(v);
+    if (v) { lo = min(lo, (unsigned)w); hi = max(hi, (unsigned)w); }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) {
+    a.isum[(size_t)b * a.n + i] = c;
+    a.wlo[(size_t)b * a.n + i] = ~lo;
+    a.whi[(size_t)b * a.n + i] = hi;
+  }
 }
 
 // Vector path (hw % 4 == 0): the one streaming read of the fp32 masks.  A warp packs 2 words per step
@@ -102,16 +121,21 @@ __global__ void __launch_bounds__(256) mnms_pack4_kernel(MnmsArgs a) {
     }
   }
   total += __shfl_xor_sync(0xffffffffu, total, 16);
-  if (lane == 0 && total) atomicAdd(a.isum + (size_t)b * a.n + i, total);
+  if (lane == 0 && total) {  // the word range at the granularity of a warp's 16 words (a superset is enough)
+    atomicAdd(a.isum + (size_t)b * a.n + i, total);
+    atomicMax(a.wlo + (size_t)b * a.n + i, ~(unsigned)w_first);
+    atomicMax(a.whi + (size_t)b * a.n + i, (unsigned)min(w_first + 2 * kPackSteps - 1, a.Wd - 1));
+  }
 }
 
 __device__ __forceinline__ float sum_of(const MnmsArgs& a, int b, int i) {
   return a.sum_in ? a.sum_in[(size_t)b * a.n + i] : (float)a.isum[(size_t)b * a.n + i];
 }
 
-// One CTA per row i: the row of the decayed-IoU matrix is first filled with its "no overlap" value
-// (coalesced), then each warp takes the few columns j > i of the same class and does the AND+POPC
-// reduction over the packed words.  grid (n, B), 256 threads.
+// One CTA per row i: each warp takes one of the few columns j > i of the same class and does the AND+POPC
+// reduction over the packed words.  Only those entries of the decayed-IoU matrix are ever written: every other
+// entry is a known constant (0, or NaN when both masks are empty) that mnms_decay_kernel synthesises instead of
+// reading 1 MB per image of zeros.  grid (n, B), 256 threads.
 __global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a, int stage) {
   __shared__ int s_match[256];  // columns j > i of row i's class, compacted (the serial class scan was the latency:
   __shared__ int s_nmatch;      // ~60 dependent global loads per warp for ~3 matching columns)
@@ -125,12 +149,6 @@ __global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a, int stage) {
   const long long ci = a.classes[(size_t)b * a.n + i];
   float* row = a.iou + ((size_t)b * a.n + i) * a.n;
   const u64* pi = a.packed + ((size_t)b * a.n + i) * a.Wd;
-  // lower triangle / other class: (x - x) resp. (x * 0) of the reference -- zero unless the union is
-  // empty (0/0), which propagates NaN exactly like the TF graph would.
-  for (int j = threadIdx.x; j < nb; j += 256) {
-    const float u = sum_of(a, b, j) + si;
-    row[j] = (u == 0.0f) ? __int_as_float(0x7fc00000) : 0.0f;
-  }
   __syncthreads();
   for (int j0 = i + 1; j0 < nb; j0 += 256) {  // all same-class columns in rounds of up to 256 matches
     const int j = j0 + threadIdx.x;
@@ -141,8 +159,10 @@ __global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a, int stage) {
   }
   __syncthreads();
   const int nmatch = s_nmatch;
+  if (nmatch == 0) return;
+  const unsigned lo_i = ~a.wlo[(size_t)b * a.n + i], hi_i = a.whi[(size_t)b * a.n + i];  // non-zero words of row i
   if (stage && nmatch > 0 && nmatch <= 256) {
-    for (int w = threadIdx.x; w < a.Wd; w += 256) s_pi[w] = pi[w];
+    for (int w = (int)lo_i + threadIdx.x; w <= (int)hi_i && lo_i != 0xffffffffu; w += 256) s_pi[w] = pi[w];
     __syncthreads();  // (block-uniform condition)
   }
   if (nmatch > 256) {  // (more than 256 same-class columns: the plain scan)
@@ -150,13 +170,17 @@ __global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a, int stage) {
       if (a.classes[(size_t)b * a.n + j] != ci) continue;  // warp-uniform
       const u64* pj = a.packed + ((size_t)b * a.n + j) * a.Wd;
       unsigned c = 0;
-      for (int w = lane; w < a.Wd; w += 32) c += __popcll(pi[w] & pj[w]);
+      const unsigned lo = max(lo_i, ~a.wlo[(size_t)b * a.n + j]), hi = min(hi_i, a.whi[(size_t)b * a.n + j]);
+      if (lo != 0xffffffffu)
+        for (int w = (int)lo + lane; w <= (int)hi; w += 32) c += __popcll(pi[w] & pj[w]);
       for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
       if (lane == 0) {
         const float inter = (float)c;
         float u = sum_of(a, b, j) + si;  // nms.py:51-52
         u = u - inter;
-        row[j] = inter / u;  // :54
+        const float v = inter / u;  // :54
+        row[j] = v;
+        if (v == v) atomicMax(reinterpret_cast<int*>(a.cmax) + (size_t)b * a.n + j, __float_as_int(v));
       }
     }
     return;
@@ -165,17 +189,20 @@ __global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a, int stage) {
     const int j = s_match[m];
     const u64* pj = a.packed + ((size_t)b * a.n + j) * a.Wd;
     unsigned c = 0;
-    for (int w0 = 0; w0 < a.Wd; w0 += 32 * 8) {  // 8 independent loads in flight per lane
+    // only the words where BOTH masks can be non-zero (an object covers a band of rows: ~10 % of the words)
+    const unsigned lo = max(lo_i, ~a.wlo[(size_t)b * a.n + j]), hi = min(hi_i, a.whi[(size_t)b * a.n + j]);
+    const int w_end = lo == 0xffffffffu ? 0 : (int)hi + 1;
+    for (int w0 = lo == 0xffffffffu ? 0 : (int)lo; w0 < w_end; w0 += 32 * 8) {  // 8 independent loads in flight per lane
       u64 v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int w = w0 + u * 32 + lane;
-        v[u] = w < a.Wd ? __ldg(pj + w) : 0ull;
+        v[u] = w < w_end ? __ldg(pj + w) : 0ull;
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int w = w0 + u * 32 + lane;
-        if (w < a.Wd) c += __popcll((stage ? s_pi[w] : pi[w]) & v[u]);
+        if (w < w_end) c += __popcll((stage ? s_pi[w] : pi[w]) & v[u]);
       }
     }
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -183,73 +210,90 @@ __global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a, int stage) {
       const float inter = (float)c;
       float u = sum_of(a, b, j) + si;  // nms.py:51-52
       u = u - inter;
-      row[j] = inter / u;  // :54
+      const float v = inter / u;  // :54
+      row[j] = v;
+      // column maximum (compensate_iou, :67) on the fly: IoUs are >= +0, so the int order of the bits is the float
+      // order; every entry this kernel does not compute is 0 (or NaN, see cmax_of)
+      if (v == v) atomicMax(reinterpret_cast<int*>(a.cmax) + (size_t)b * a.n + j, __float_as_int(v));
     }
   }
 }
 
-// compensate_iou = reduce_max(iou, axis=0) (:67): one warp per column, `(v > m) ? v : m` semantics
-// (NaNs are skipped unless the first row is NaN).
-__global__ void __launch_bounds__(256) mnms_cmax_kernel(MnmsArgs a) {
-  const int b = blockIdx.y;
-  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  const int nb = rows_of(a, b);
-  if (j >= nb) return;
-  const float* io = a.iou + (size_t)b * a.n * a.n;
-  const float first = io[j];
-  float m = __int_as_float(0xff800000);
-  for (int i = lane; i < nb; i += 32) {
-    const float v = io[(size_t)i * a.n + j];
-    m = (v > m) ? v : m;
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    const float v = __shfl_xor_sync(0xffffffffu, m, o);
-    m = (v > m) ? v : m;
-  }
-  if (first != first) m = first;
-  if (lane == 0) a.cmax[(size_t)b * a.n + j] = m;
+// compensate_iou = reduce_max(iou, axis=0) (:67) without a pass over the matrix.  With `(v > m) ? v : m` semantics
+// (NaNs skipped unless row 0's entry is NaN) column i of the decayed-IoU matrix has: NaN entries exactly where both
+// masks are empty (0 / 0), zeros elsewhere outside the same-class upper triangle, and the pair IoUs inside it.  Hence
+// max = NaN when mask i and mask 0 are both empty, else max(0, pair IoUs) = what mnms_iou_kernel accumulated.
+__device__ __forceinline__ float cmax_of(const MnmsArgs& a, int b, int i) {
+  const float u = sum_of(a, b, i) + sum_of(a, b, 0);
+  return (u == 0.0f) ? __int_as_float(0x7fc00000) : a.cmax[(size_t)b * a.n + i];
 }
 
-// decay + reduce_min(axis=0) + score update (:72-82): one warp per column, `(d < m) ? d : m` semantics.
-__global__ void __launch_bounds__(256) mnms_decay_kernel(MnmsArgs a) {
+// decay + reduce_min(axis=0) + score update (:72-82), `(d < m) ? d : m` semantics (NaN never enters the minimum, so
+// the order of the reduction is free).  CTA = 32 columns: lane = column (coalesced 128-byte rows of the matrix),
+// the 32 warps split the rows (4 loads in flight each), partial minima meet in shared memory.
+constexpr int kDecayWarps = 32;
+__global__ void __launch_bounds__(kDecayWarps * 32) mnms_decay_kernel(MnmsArgs a) {
+  __shared__ float s_min[kDecayWarps][32];
   const int b = blockIdx.y;
-  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (j >= a.n) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
   const int nb = rows_of(a, b);
-  if (j >= nb) {
-    if (lane == 0) a.out[(size_t)b * a.n + j] = 0.0f;
-    return;
-  }
   const float* io = a.iou + (size_t)b * a.n * a.n;
-  const float* cm = a.cmax + (size_t)b * a.n;
   float m = __int_as_float(0x7f800000);
-  for (int i = lane; i < nb; i += 32) {
-    const float v = io[(size_t)i * a.n + j];
-    const float ci = cm[i];
-    float d;
-    if (a.kernel == D2B_MNMS_GAUSSIAN) {
-      float x = v * v; float y = ci * ci; x = x - y; x = a.nsigma * x; d = d2b_expf(x);
-    } else {
-      float x = 1.0f - v; float y = 1.0f - ci; d = x / y;
+  if (j < nb) {
+    const long long cj = a.classes[(size_t)b * a.n + j];
+    const float sj = sum_of(a, b, j);
+    for (int i0 = warp; i0 < nb; i0 += 4 * kDecayWarps) {  // 4 independent rows in flight per warp
+      float v[4], ci[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kDecayWarps;
+        v[u] = 0.0f;
+        ci[u] = 0.0f;
+        if (i < nb) {  // (warp-uniform: the per-row values are broadcast loads)
+          ci[u] = cmax_of(a, b, i);
+          // same-class upper triangle: the pair IoU mnms_iou_kernel stored.  Elsewhere (x - x) resp. (x * 0) of
+          // the reference: zero unless the union is empty (0 / 0), which propagates NaN exactly like the TF graph.
+          if (i < j && a.classes[(size_t)b * a.n + i] == cj) v[u] = io[(size_t)i * a.n + j];
+          else v[u] = (sum_of(a, b, i) + sj == 0.0f) ? __int_as_float(0x7fc00000) : 0.0f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (i0 + u * kDecayWarps >= nb) break;
+        float d;
+        if (a.kernel == D2B_MNMS_GAUSSIAN) {
+          float x = v[u] * v[u]; float y = ci[u] * ci[u]; x = x - y; x = a.nsigma * x; d = d2b_expf(x);
+        } else {
+          float x = 1.0f - v[u]; float y = 1.0f - ci[u]; d = x / y;
+        }
+        m = (d < m) ? d : m;
+      }
     }
-    m = (d < m) ? d : m;
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    const float v = __shfl_xor_sync(0xffffffffu, m, o);
-    m = (v < m) ? v : m;
+  s_min[warp][lane] = m;
+  __syncthreads();
+  if (warp == 0 && j < a.n) {
+    if (j >= nb) {
+      a.out[(size_t)b * a.n + j] = 0.0f;
+      return;
+    }
+#pragma unroll
+    for (int w = 1; w < kDecayWarps; ++w) {
+      const float v = s_min[w][lane];
+      m = (v < m) ? v : m;
+    }
+    a.out[(size_t)b * a.n + j] = a.scores[(size_t)b * a.n + j] * m;
   }
-  if (lane == 0) a.out[(size_t)b * a.n + j] = a.scores[(size_t)b * a.n + j] * m;
 }
 
 size_t mnms_bytes(const d2b_matrix_nms_params* p, size_t* o_packed, size_t* o_isum, size_t* o_iou, size_t* o_cmax) {
   const size_t B = p->batch, n = p->n, Wd = (size_t)((p->hw + 63) / 64);
   size_t o = 0;
   *o_packed = o; o += p->packed_masks ? 0 : ws_slice(B * n * Wd * sizeof(u64));
-  *o_isum = o; o += ws_slice(B * n * sizeof(unsigned));
+  *o_isum = o; o += 3 * ws_slice(B * n * sizeof(unsigned));  // isum, wlo, whi
+  *o_cmax = o; o += ws_slice(B * n * sizeof(float));          // (adjacent: one memset zeroes all four)
   *o_iou = o; o += ws_slice(B * n * n * sizeof(float));
-  *o_cmax = o; o += ws_slice(B * n * sizeof(float));
   return o;
 }
 
@@ -290,17 +334,22 @@ extern "C" int d2b_matrix_nms(const d2b_matrix_nms_params* p, void* workspace, s
   a.packed = p->packed_masks ? const_cast<u64*>(reinterpret_cast<const u64*>(p->packed_masks))
                              : reinterpret_cast<u64*>(ws + o_packed);
   a.isum = reinterpret_cast<unsigned*>(ws + o_isum);
+  a.wlo = reinterpret_cast<unsigned*>(ws + o_isum + ws_slice(sizeof(unsigned) * (size_t)a.B * a.n));
+  a.whi = reinterpret_cast<unsigned*>(ws + o_isum + 2 * ws_slice(sizeof(unsigned) * (size_t)a.B * a.n));
   a.iou = reinterpret_cast<float*>(ws + o_iou);
   a.cmax = reinterpret_cast<float*>(ws + o_cmax);
   a.out = p->out;
-  D2B_CUDA(cudaMemsetAsync(a.isum, 0, sizeof(unsigned) * (size_t)a.B * a.n, st));
-  if (p->packed_masks) {
-    if (!a.sum_in) mnms_popc_kernel<<<dim3((a.n + 7) / 8, a.B), 256, 0, st>>>(a);
+  // column maxima start at +0; the pack kernels accumulate sums / word ranges with atomics (mnms_popc_kernel writes
+  // them whole)
+  if (p->packed_masks) D2B_CUDA(cudaMemsetAsync(a.cmax, 0, sizeof(float) * (size_t)a.B * a.n, st));
+  else D2B_CUDA(cudaMemsetAsync(a.isum, 0, (o_cmax - o_isum) + sizeof(float) * (size_t)a.B * a.n, st));
+  if (p->packed_masks) {  // (also with sum_masks given: the word ranges are needed)
+    mnms_popc_kernel<<<dim3((a.n + 7) / 8, a.B), 256, 0, st>>>(a);
   } else if (a.hw % 4 == 0 && (reinterpret_cast<uintptr_t>(a.masks) & 15) == 0)
     mnms_pack4_kernel<<<dim3((a.Wd + 8 * kPackSteps * 2 - 1) / (8 * kPackSteps * 2), a.n, a.B), 256, 0, st>>>(a);
   else
     mnms_pack_kernel<<<dim3((a.Wd + 7) / 8, a.n, a.B), 256, 0, st>>>(a);
-  if (!(p->packed_masks && a.sum_in)) D2B_LAUNCH_CHECK();
+  D2B_LAUNCH_CHECK();
   size_t iou_smem = (size_t)a.Wd * sizeof(u64);
   const int stage = iou_smem <= 160 * 1024;  // (larger masks: the row is re-read from L2 per pair)
   if (!stage) iou_smem = 0;
@@ -308,9 +357,7 @@ extern "C" int d2b_matrix_nms(const d2b_matrix_nms_params* p, void* workspace, s
     D2B_CUDA(cudaFuncSetAttribute(mnms_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iou_smem));
   mnms_iou_kernel<<<dim3(a.n, a.B), 256, iou_smem, st>>>(a, stage);
   D2B_LAUNCH_CHECK();
-  mnms_cmax_kernel<<<dim3((a.n + 7) / 8, a.B), 256, 0, st>>>(a);
-  D2B_LAUNCH_CHECK();
-  mnms_decay_kernel<<<dim3((a.n + 7) / 8, a.B), 256, 0, st>>>(a);
+  mnms_decay_kernel<<<dim3((a.n + 31) / 32, a.B), kDecayWarps * 32, 0, st>>>(a);
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }

@@ -28,4 +28,6 @@ def med(fn, k=20):
 out = {"fp32_masks_ms": med(lambda: matrix_nms(masks, classes, scores))}
 packed, sums, _ = solo_mask_encode(masks * 8 - 4, 0.5)
 out["packed_masks_ms"] = med(lambda: matrix_nms(None, classes, scores, sum_masks=sums, packed_masks=packed, mask_hw=H * W))
+out["fp32_masks_ms_again"] = med(lambda: matrix_nms(masks, classes, scores))
+out["mask_read_frac_of_6525GBps"] = B * n * H * W * 4 / (out["fp32_masks_ms_again"] * 1e-3) / 6525.2e9
 print(json.dumps(out))
