@@ -232,42 +232,78 @@ __device__ __forceinline__ float cmax_of(const MnmsArgs& a, int b, int i) {
 // the order of the reduction is free).  CTA = 32 columns: lane = column (coalesced 128-byte rows of the matrix),
 // the 32 warps split the rows (4 loads in flight each), partial minima meet in shared memory.
 constexpr int kDecayWarps = 32;
+constexpr int kDecayStageMax = 4096;  // rows whose per-row values fit the shared-memory table (20 bytes each)
+
+__device__ __forceinline__ float decay_of(const MnmsArgs& a, float v, float ci) {
+  if (a.kernel == D2B_MNMS_GAUSSIAN) {
+    float x = v * v; float y = ci * ci; x = x - y; x = a.nsigma * x;
+    return d2b_expf(x);
+  }
+  float x = 1.0f - v; float y = 1.0f - ci;
+  return x / y;
+}
+
+// STAGED: the per-row values (class, mask sum, column maximum and d0 = decay(0, cmax): what EVERY non-pair entry of the
+// row contributes, whatever the column) are computed once per CTA into shared memory, so the loop over the rows is a
+// shared-memory read and a compare per entry and only the few stored pair entries run the exp / division again.
+template <bool STAGED>
 __global__ void __launch_bounds__(kDecayWarps * 32) mnms_decay_kernel(MnmsArgs a) {
   __shared__ float s_min[kDecayWarps][32];
+  extern __shared__ __align__(16) unsigned char s_rows[];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + lane;
   const int nb = rows_of(a, b);
   const float* io = a.iou + (size_t)b * a.n * a.n;
+  long long* s_cls = reinterpret_cast<long long*>(s_rows);
+  float* s_sum = reinterpret_cast<float*>(s_cls + (STAGED ? a.n : 0));
+  float* s_ci = s_sum + (STAGED ? a.n : 0);
+  float* s_d0 = s_ci + (STAGED ? a.n : 0);
+  if (STAGED) {
+    for (int i = threadIdx.x; i < nb; i += kDecayWarps * 32) {
+      const float ci = cmax_of(a, b, i);
+      s_cls[i] = a.classes[(size_t)b * a.n + i];
+      s_sum[i] = sum_of(a, b, i);
+      s_ci[i] = ci;
+      s_d0[i] = decay_of(a, 0.0f, ci);
+    }
+    __syncthreads();
+  }
   float m = __int_as_float(0x7f800000);
   if (j < nb) {
     const long long cj = a.classes[(size_t)b * a.n + j];
     const float sj = sum_of(a, b, j);
-    for (int i0 = warp; i0 < nb; i0 += 4 * kDecayWarps) {  // 4 independent rows in flight per warp
-      float v[4], ci[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * kDecayWarps;
-        v[u] = 0.0f;
-        ci[u] = 0.0f;
-        if (i < nb) {  // (warp-uniform: the per-row values are broadcast loads)
-          ci[u] = cmax_of(a, b, i);
-          // same-class upper triangle: the pair IoU mnms_iou_kernel stored.  Elsewhere (x - x) resp. (x * 0) of
-          // the reference: zero unless the union is empty (0 / 0), which propagates NaN exactly like the TF graph.
-          if (i < j && a.classes[(size_t)b * a.n + i] == cj) v[u] = io[(size_t)i * a.n + j];
-          else v[u] = (sum_of(a, b, i) + sj == 0.0f) ? __int_as_float(0x7fc00000) : 0.0f;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (i0 + u * kDecayWarps >= nb) break;
+    if (STAGED) {
+      for (int i = warp; i < nb; i += kDecayWarps) {
         float d;
-        if (a.kernel == D2B_MNMS_GAUSSIAN) {
-          float x = v[u] * v[u]; float y = ci[u] * ci[u]; x = x - y; x = a.nsigma * x; d = d2b_expf(x);
-        } else {
-          float x = 1.0f - v[u]; float y = 1.0f - ci[u]; d = x / y;
-        }
+        // same-class upper triangle: the pair IoU mnms_iou_kernel stored.  Elsewhere (x - x) resp. (x * 0) of the
+        // reference: zero unless the union is empty (0 / 0), which propagates NaN exactly like the TF graph (and a
+        // NaN never enters the minimum).
+        if (i < j && s_cls[i] == cj) d = decay_of(a, io[(size_t)i * a.n + j], s_ci[i]);
+        else if (s_sum[i] + sj == 0.0f) continue;
+        else d = s_d0[i];
         m = (d < m) ? d : m;
+      }
+    } else {
+      for (int i0 = warp; i0 < nb; i0 += 4 * kDecayWarps) {  // 4 independent rows in flight per warp
+        float v[4], ci[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * kDecayWarps;
+          v[u] = 0.0f;
+          ci[u] = 0.0f;
+          if (i < nb) {  // (warp-uniform: the per-row values are broadcast loads)
+            ci[u] = cmax_of(a, b, i);
+            if (i < j && a.classes[(size_t)b * a.n + i] == cj) v[u] = io[(size_t)i * a.n + j];
+            else v[u] = (sum_of(a, b, i) + sj == 0.0f) ? __int_as_float(0x7fc00000) : 0.0f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (i0 + u * kDecayWarps >= nb) break;
+          const float d = decay_of(a, v[u], ci[u]);
+          m = (d < m) ? d : m;
+        }
       }
     }
   }
@@ -357,7 +393,14 @@ extern "C" int d2b_matrix_nms(const d2b_matrix_nms_params* p, void* workspace, s
     D2B_CUDA(cudaFuncSetAttribute(mnms_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iou_smem));
   mnms_iou_kernel<<<dim3(a.n, a.B), 256, iou_smem, st>>>(a, stage);
   D2B_LAUNCH_CHECK();
-  mnms_decay_kernel<<<dim3((a.n + 31) / 32, a.B), kDecayWarps * 32, 0, st>>>(a);
+  if (a.n <= kDecayStageMax) {
+    const size_t dsm = (size_t)a.n * (sizeof(long long) + 3 * sizeof(float));
+    if (dsm > 32 * 1024)
+      D2B_CUDA(cudaFuncSetAttribute(mnms_decay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+    mnms_decay_kernel<true><<<dim3((a.n + 31) / 32, a.B), kDecayWarps * 32, dsm, st>>>(a);
+  } else {
+    mnms_decay_kernel<false><<<dim3((a.n + 31) / 32, a.B), kDecayWarps * 32, 0, st>>>(a);
+  }
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }

@@ -318,6 +318,19 @@ def test_matrix_nms_empty_masks_and_big_class(cuda, oracle_lib, kernel):
         assert np.array_equal(got[ok], want[ok])
 
 
+def test_matrix_nms_many_masks(cuda, oracle_lib):
+    """n > 4096: the decay kernel's per-row table no longer fits shared memory (its global-load variant runs)."""
+    rng = np.random.default_rng(5)
+    n, H, W = 4200, 6, 10
+    masks = (rng.random((n, H, W)) < 0.3).astype(np.float32)
+    masks[rng.integers(0, n, 40)] = 0.0
+    classes = rng.integers(0, 30, n).astype(np.int64)
+    scores = np.sort(rng.uniform(0.1, 1.0, n).astype(np.float32))[::-1].copy()
+    want = oracle_lib.matrix_nms(masks, classes, scores, None, "gaussian", 2.0)
+    got = matrix_nms(T(masks, cuda), T(classes, cuda), T(scores, cuda), kernel="gaussian", sigma=2.0).cpu().numpy()
+    assert np.array_equal(got, want, equal_nan=True)
+
+
 # ------------------------------------------------------------------ sigmoid top-k: cutoff / candidate-list paths
 @pytest.mark.parametrize("case", ["typical", "plateau_overflow", "tied_boundary", "negative_tail", "saturated",
                                   "sampled_long", "sample_misleads"])
