@@ -24,6 +24,7 @@
 // disabled in the saturated / underflowing tails (c outside (-80, 8)) where plateaus make index ties matter.
 // HBM-bound scan (4 B per candidate score per pass); no tensor cores.
 #include "kernels.cuh"
+#include "sort_tile.cuh"
 
 namespace d2b {
 namespace {
@@ -475,19 +476,23 @@ constexpr int kPreCopies = 16;       // [bin][lane & 15]: at most 2 lanes of a w
 constexpr int kPreSample = 1024;     // sampled elements per chunk of a long row (1/64 of a 64 K-element chunk)
 constexpr int kPreGroup = 8;         // chunks served by one CTA in sampled mode
 constexpr int kPreMinChunks = 8;     // rows shorter than this many chunks are histogrammed in full
+// Launched on the kPreGroup-times coarser grid (`a` = fill_args(d, ., kPreGroup)): CTA `chunk` of a row serves the
+// fine chunks [chunk * kPreGroup, (chunk + 1) * kPreGroup), so every CTA of the launch has work.
 __global__ void __launch_bounds__(kHistThreads) topk_prehist(TopkArgs a) {
   __shared__ unsigned sh[kPreBins * kPreCopies];
+  __shared__ unsigned s_scan[kHistThreads];
   __shared__ int s_last;
   int g, img, chunk;
   if (!locate(a, blockIdx.x, g, img, chunk)) return;
   const int row = img * a.d.G + g;
   RowState* st = a.state + row;
   if (!st->active) return;
-  const bool sampled = a.chunks[g] >= kPreMinChunks && a.chunk_elems[g] > kPreSample;
-  if (sampled && (chunk % kPreGroup) != 0) return;
+  const long long len = a.d.row_len[g];
+  const long long fine = a.chunk_elems[g] / kPreGroup;  // elements of a fine chunk (what pass 0 gives one CTA)
+  const int fine_chunks = (int)((len + fine - 1) / fine);
+  const bool sampled = fine_chunks >= kPreMinChunks && fine > kPreSample;
   for (int i = threadIdx.x; i < kPreBins * kPreCopies; i += kHistThreads) sh[i] = 0;
   __syncthreads();
-  const long long len = a.d.row_len[g];
   const float* x = a.d.scores[g] + (size_t)img * len;
   const int lane = threadIdx.x & (kPreCopies - 1);
   auto count = [&](float v, long long, bool ok) {
@@ -495,10 +500,29 @@ __global__ void __launch_bounds__(kHistThreads) topk_prehist(TopkArgs a) {
     if (ok) atomicAdd(&sh[(float_to_key(v) >> (32 - kPreBits)) * kPreCopies + lane], 1u);
   };
   if (sampled) {
-    for (int c = chunk; c < chunk + kPreGroup && c < a.chunks[g]; ++c) {
-      const long long beg = (long long)c * a.chunk_elems[g];
-      const long long end = beg + kPreSample < len ? beg + kPreSample : len;
-      for_each_elem<4>(x, beg, end, count);
+    static_assert(kPreSample == 4 * kHistThreads, "one 16-byte vector per thread and fine chunk");
+    const int c0 = chunk * kPreGroup;
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (fine % 4 == 0);
+    if (vec) {  // the kPreGroup samples are independent loads: all in flight at once (one round trip, not eight)
+      float4 q[kPreGroup];
+#pragma unroll
+      for (int u = 0; u < kPreGroup; ++u) {
+        const long long i = (long long)(c0 + u) * fine + 4 * threadIdx.x;
+        q[u] = (c0 + u < fine_chunks && i + 3 < len) ? __ldg(reinterpret_cast<const float4*>(x + i))
+                                                     : make_float4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < kPreGroup; ++u) {
+        const long long i = (long long)(c0 + u) * fine + 4 * threadIdx.x;
+        const bool ok = c0 + u < fine_chunks && i + 3 < len;
+        count(q[u].x, i, ok); count(q[u].y, i + 1, ok); count(q[u].z, i + 2, ok); count(q[u].w, i + 3, ok);
+      }
+    } else {
+      for (int c = c0; c < c0 + kPreGroup && c < fine_chunks; ++c) {
+        const long long beg = (long long)c * fine;
+        const long long end = beg + kPreSample < len ? beg + kPreSample : len;
+        for_each_elem<4>(x, beg, end, count);
+      }
     }
   } else {
     const long long beg = (long long)chunk * a.chunk_elems[g];
@@ -515,27 +539,32 @@ __global__ void __launch_bounds__(kHistThreads) topk_prehist(TopkArgs a) {
   }
   __threadfence();
   __syncthreads();
-  const unsigned expect = sampled ? (unsigned)((a.chunks[g] + kPreGroup - 1) / kPreGroup) : (unsigned)a.chunks[g];
+  const unsigned expect = (unsigned)a.chunks[g];
   if (threadIdx.x == 0) s_last = (atomicAdd(&st->pre_done, 1u) == expect - 1u);
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // last CTA of the row: stage the merged histogram in shared memory (coalesced) so that the serial walk
-  // below does not pay one L2 round trip per bin
-  for (int b = threadIdx.x; b < kPreBins; b += kHistThreads) sh[b] = __ldcg(gh + b);
+  // last CTA of the row: the first bin from the top at which the running count covers the target rank.  Sampled
+  // rows aim 3x past the scaled rank so that the full row holds >= k_r elements above the cutoff with overwhelming
+  // probability (verified exactly by pass 0).  Thread t owns the bins kPreBins-1-2t and kPreBins-2-2t; a block scan
+  // of the pair sums replaces the serial walk (512 dependent shared-memory loads, ~6 us).
+  static_assert(kPreBins == 2 * kHistThreads, "two bins per thread");
+  const unsigned target = sampled ? (unsigned)(((u64)st->k_r * 3ull * kPreSample + fine - 1) / fine) + 16u : st->k_r;
+  const int top = kPreBins - 1 - 2 * threadIdx.x;
+  const unsigned h0 = __ldcg(gh + top), h1 = __ldcg(gh + top - 1);
+  s_scan[threadIdx.x] = h0 + h1;
   __syncthreads();
-  if (threadIdx.x != 0) return;
-  // thread 0 of the last CTA: walk down from the top bin until the target rank is covered.  Sampled rows aim 3x
-  // past the scaled rank so that the full row holds >= k_r elements above the cutoff with overwhelming
-  // probability (verified exactly by pass 0).
-  const unsigned target = sampled ? (unsigned)(((u64)st->k_r * 3ull * kPreSample + a.chunk_elems[g] - 1) / a.chunk_elems[g]) + 16u
-                                  : st->k_r;
-  unsigned acc = 0;
-  int bin = kPreBins - 1;
-  for (; bin > 0; --bin) {
-    acc += sh[bin];
-    if (acc >= target) break;
+  for (int off = 1; off < kHistThreads; off <<= 1) {  // inclusive scan from the top bins down
+    const unsigned v = threadIdx.x >= off ? s_scan[threadIdx.x - off] : 0;
+    __syncthreads();
+    s_scan[threadIdx.x] += v;
+    __syncthreads();
   }
+  const unsigned incl = s_scan[threadIdx.x], excl = incl - (h0 + h1);
+  int bin = -1;
+  if (excl < target && target <= incl) bin = (excl + h0 >= target) ? top : top - 1;
+  if (threadIdx.x == kHistThreads - 1 && incl < target) bin = 0;  // fewer elements than the target: the lowest bin
+  if (bin < 0) return;
   const float c = key_to_float((unsigned)bin << (32 - kPreBits));  // lower edge of that bucket: c <= k-th largest logit
   unsigned cut = 0u;
   if (c == c && c > -80.0f && c < 8.0f) {
@@ -659,16 +688,7 @@ __global__ void __launch_bounds__(kFinThreads) topk_finish_kernel(TopkArgs a, u6
   while (Pe < (int)kr) Pe <<= 1;
   for (int i = (int)kr + tid; i < Pe; i += kFinThreads) s_out[i] = 0ull;
   __syncthreads();
-  for (int k = 2; k <= Pe; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int p = tid; p < Pe / 2; p += kFinThreads) {
-        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-        const bool desc = ((i & k) == 0);
-        const u64 va = s_out[i], vb = s_out[i | j];
-        if (desc ? (va < vb) : (va > vb)) { s_out[i] = vb; s_out[i | j] = va; }
-      }
-      __syncthreads();
-    }
+  sort_smem_desc(s_out, Pe);  // registers + shuffles (sort_tile.cuh): ~15 barriers for 1,024 keys instead of 55
   for (int i = tid; i < a.P; i += kFinThreads) out[i] = i < (int)kr ? s_out[i] : 0ull;
 }
 
@@ -748,7 +768,10 @@ int topk_run(const TopkDesc& d, unsigned long long* out_keys, float* out_values,
   topk_init<<<(rows + 127) / 128, 128, 0, st>>>(a, rows, seg_len, out_counts);
   D2B_LAUNCH_CHECK();
   if (d.transform == D2B_TOPK_SIGMOID) {
-    topk_prehist<<<ctas, kHistThreads, 0, st>>>(a);
+    TopkArgs c = a;
+    const int ctas_c = fill_args(d, c, kPreGroup);
+    c.state = a.state; c.hist = a.hist; c.prehist = a.prehist; c.cand = a.cand;
+    topk_prehist<<<ctas_c, kHistThreads, 0, st>>>(c);
     D2B_LAUNCH_CHECK();
   }
   // SIGMOID rows are normally resolved from their candidate lists by one CTA per row after pass 0: the later
