@@ -12,12 +12,18 @@ void set_last_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-bool pdl_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("D2B_PDL");  // off by default: inside the captured multi-stream step it measured slower
-    return e && e[0] == '1';
+bool pdl_enabled(cudaStream_t st) {
+  static const int mode = [] {  // 0 = never, 1 = always, 2 = eager launches only (default)
+    const char* e = getenv("D2B_PDL");
+    return !e ? 2 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2));
   }();
-  return on;
+  if (mode != 2) return mode == 1;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return cs == cudaStreamCaptureStatusNone;
 }
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }

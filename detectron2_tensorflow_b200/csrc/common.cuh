@@ -75,8 +75,11 @@ __device__ __forceinline__ void d2b_prof_stamp(int slot) {
 // memory -- every thread, unconditionally; (2) kernels launched the ordinary way are unaffected.  MEASURED (B200,
 // profiles/r02aj_step_probe_*.jsonl): eager chains gain (Fast R-CNN post 87 -> 68 us at 2 images), but the step the
 // bench replays is a captured multi-stream graph and there the programmatic edges cost time (2 image blocks: 0.209 ->
-// 0.257 ms; 4 blocks of 16 images: 0.648 -> 0.701 ms), so the attribute is OFF unless D2B_PDL=1 is set.
-bool pdl_enabled();
+// 0.257 ms; 4 blocks of 16 images: 0.648 -> 0.701 ms).  Hence: the attribute is set on EAGER launches only -- never
+// while the stream is being captured -- unless D2B_PDL=0 (never) or D2B_PDL=1 (always) says otherwise.  The RetinaNet
+// top-k chain does not use it at all: there it measured slower even eagerly (0.572 -> 0.645 ms at N = 32: the early
+// CTAs of the dependents take slots from the HBM-bound scan); Matrix-NMS gains a little (0.418 -> 0.4135 ms).
+bool pdl_enabled(cudaStream_t st);
 __device__ __forceinline__ void grid_dep_sync() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -99,7 +102,7 @@ struct LaunchCfg {
       attr[cfg.numAttrs].val.clusterDim.z = 1;
       ++cfg.numAttrs;
     }
-    if (pdl_enabled()) {
+    if (pdl_enabled(st)) {
       attr[cfg.numAttrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
       ++cfg.numAttrs;

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) mnms_pack_kernel(MnmsArgs a) {
 
 // packed input (d2b_solo_mask_encode): only the exact mask sums are missing; one warp per mask row
 __global__ void __launch_bounds__(256) mnms_popc_kernel(MnmsArgs a) {
+  grid_dep_sync();
   const int b = blockIdx.y;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i >= rows_of(a, b)) return;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(256) mnms_popc_kernel(MnmsArgs a) {
 // 16-byte loads in flight per lane.  grid (ceil(Wd / 128), n, B), 256 threads = 128 words per CTA.
 constexpr int kPackSteps = 8;
 __global__ void __launch_bounds__(256) mnms_pack4_kernel(MnmsArgs a) {
+  grid_dep_sync();
   const int b = blockIdx.z, i = blockIdx.y;
   if (i >= rows_of(a, b)) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -137,6 +139,7 @@ __device__ __forceinline__ float sum_of(const MnmsArgs& a, int b, int i) {
 // entry is a known constant (0, or NaN when both masks are empty) that mnms_decay_kernel synthesises instead of
 // reading 1 MB per image of zeros.  grid (n, B), 256 threads.
 __global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a, int stage) {
+  grid_dep_sync();
   __shared__ int s_match[256];  // columns j > i of row i's class, compacted (the serial class scan was the latency:
   __shared__ int s_nmatch;      // ~60 dependent global loads per warp for ~3 matching columns)
   extern __shared__ u64 s_pi[];  // row i's packed mask: read from L2 once per row instead of once per pair
@@ -248,6 +251,7 @@ __device__ __forceinline__ float decay_of(const MnmsArgs& a, float v, float ci) 
 // shared-memory read and a compare per entry and only the few stored pair entries run the exp / division again.
 template <bool STAGED>
 __global__ void __launch_bounds__(kDecayWarps * 32) mnms_decay_kernel(MnmsArgs a) {
+  grid_dep_sync();
   __shared__ float s_min[kDecayWarps][32];
   extern __shared__ __align__(16) unsigned char s_rows[];
   const int b = blockIdx.y;
@@ -380,9 +384,9 @@ extern "C" int d2b_matrix_nms(const d2b_matrix_nms_params* p, void* workspace, s
   if (p->packed_masks) D2B_CUDA(cudaMemsetAsync(a.cmax, 0, sizeof(float) * (size_t)a.B * a.n, st));
   else D2B_CUDA(cudaMemsetAsync(a.isum, 0, (o_cmax - o_isum) + sizeof(float) * (size_t)a.B * a.n, st));
   if (p->packed_masks) {  // (also with sum_masks given: the word ranges are needed)
-    mnms_popc_kernel<<<dim3((a.n + 7) / 8, a.B), 256, 0, st>>>(a);
+    D2B_CUDA(launch_pdl(mnms_popc_kernel, dim3((a.n + 7) / 8, a.B), dim3(256), 0, st, 0, a));
   } else if (a.hw % 4 == 0 && (reinterpret_cast<uintptr_t>(a.masks) & 15) == 0)
-    mnms_pack4_kernel<<<dim3((a.Wd + 8 * kPackSteps * 2 - 1) / (8 * kPackSteps * 2), a.n, a.B), 256, 0, st>>>(a);
+    D2B_CUDA(launch_pdl(mnms_pack4_kernel, dim3((a.Wd + 8 * kPackSteps * 2 - 1) / (8 * kPackSteps * 2), a.n, a.B), dim3(256), 0, st, 0, a));
   else
     mnms_pack_kernel<<<dim3((a.Wd + 7) / 8, a.n, a.B), 256, 0, st>>>(a);
   D2B_LAUNCH_CHECK();
@@ -391,15 +395,15 @@ extern "C" int d2b_matrix_nms(const d2b_matrix_nms_params* p, void* workspace, s
   if (!stage) iou_smem = 0;
   if (iou_smem > 48 * 1024)
     D2B_CUDA(cudaFuncSetAttribute(mnms_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iou_smem));
-  mnms_iou_kernel<<<dim3(a.n, a.B), 256, iou_smem, st>>>(a, stage);
+  D2B_CUDA(launch_pdl(mnms_iou_kernel, dim3(a.n, a.B), dim3(256), iou_smem, st, 0, a, stage));
   D2B_LAUNCH_CHECK();
   if (a.n <= kDecayStageMax) {
     const size_t dsm = (size_t)a.n * (sizeof(long long) + 3 * sizeof(float));
     if (dsm > 32 * 1024)
       D2B_CUDA(cudaFuncSetAttribute(mnms_decay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-    mnms_decay_kernel<true><<<dim3((a.n + 31) / 32, a.B), kDecayWarps * 32, dsm, st>>>(a);
+    D2B_CUDA(launch_pdl(mnms_decay_kernel<true>, dim3((a.n + 31) / 32, a.B), dim3(kDecayWarps * 32), dsm, st, 0, a));
   } else {
-    mnms_decay_kernel<false><<<dim3((a.n + 31) / 32, a.B), kDecayWarps * 32, 0, st>>>(a);
+    D2B_CUDA(launch_pdl(mnms_decay_kernel<false>, dim3((a.n + 31) / 32, a.B), dim3(kDecayWarps * 32), 0, st, 0, a));
   }
   D2B_LAUNCH_CHECK();
   return D2B_OK;

@@ -475,7 +475,7 @@ constexpr int kPreBins = 1 << kPreBits;
 constexpr int kPreCopies = 16;       // [bin][lane & 15]: at most 2 lanes of a warp share a word
 constexpr int kPreSample = 1024;     // sampled elements per chunk of a long row (1/64 of a 64 K-element chunk)
 constexpr int kPreGroup = 8;         // chunks served by one CTA in sampled mode
-constexpr int kPreMinChunks = 8;     // rows shorter than this many chunks are histogrammed in full
+constexpr int kPreMinChunks = 2;     // rows shorter than this many chunks are histogrammed in full (one CTA reading a 7-chunk row serially was the long pole of the launch)
 // Launched on the kPreGroup-times coarser grid (`a` = fill_args(d, ., kPreGroup)): CTA `chunk` of a row serves the
 // fine chunks [chunk * kPreGroup, (chunk + 1) * kPreGroup), so every CTA of the launch has work.
 __global__ void __launch_bounds__(kHistThreads) topk_prehist(TopkArgs a) {
