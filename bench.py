@@ -341,10 +341,25 @@ def host_path_probe(dev, world, h2d_bytes, d2h_bytes, e2e_step_s):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t[0])
     duplex = n / dt / 1e9  # GB/s per rank in EACH direction with every rank copying both ways
-    # the ranks share the host-memory / PCIe path: what counts is the total bytes moved per step, both directions
-    floor_s = (h2d_bytes + d2h_bytes) / (2.0 * duplex * 1e9)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+    torch.cuda.synchronize()
+    du = (time.perf_counter() - t0) / 4
+    if world > 1:
+        t = torch.tensor([du], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        du = float(t[0])
+    uni = n / du / 1e9  # GB/s per rank, uploads only
+    # two lower bounds of the copy time of a step: the ranks share the host-memory / PCIe path (total bytes at the
+    # both-directions rate), and the longer direction cannot go faster than a one-directional stream
+    floor_s = max((h2d_bytes + d2h_bytes) / (2.0 * duplex * 1e9), max(h2d_bytes, d2h_bytes) / (uni * 1e9))
     frac = floor_s / e2e_step_s
     return {"duplex_GBps_per_rank_each_direction": duplex, "aggregate_GBps_each_direction": duplex * world,
+            "h2d_only_GBps_per_rank": uni,
             "copy_floor_ms_per_step": floor_s * 1e3, "e2e_over_copy_floor": e2e_step_s / floor_s,
             "limiter": ("host<->device copies of this box: the e2e step runs at %.0f %% of what %d rank(s) copying in "
                         "both directions at once can move (measured in this run)" % (100.0 * frac, world))}
