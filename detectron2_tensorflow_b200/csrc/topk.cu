@@ -36,7 +36,10 @@ constexpr int kPasses = 6;
 constexpr int kHistThreads = 256;
 constexpr int kChunk = 8192;        // elements per CTA per pass (rows up to 1 M elements)
 constexpr int kCandCap = 65536;     // candidate-list capacity per SIGMOID row (beyond it the row is re-scanned)
-constexpr int kChunkLong = 65536;   // ... for longer rows (RetinaNet class scores): amortises the per-CTA setup
+#ifndef D2B_CHUNK_LONG
+#define D2B_CHUNK_LONG 65536
+#endif
+constexpr int kChunkLong = D2B_CHUNK_LONG;   // ... for longer rows (RetinaNet class scores): amortises the per-CTA setup
 constexpr int kBatch = 8;       // independent loads in flight per thread
 
 __constant__ int c_shift[kPasses] = {53, 42, 32, 21, 10, 0};
@@ -339,7 +342,11 @@ __global__ void __launch_bounds__(kHistThreads) topk_hist(TopkArgs a, int pass, 
 // for cut != 0 (keys are monotone in the float order, NaN has key 0) -- and everything else (key, candidate append,
 // counters, global histogram) behind the rarely taken branch.  No shared histogram and few registers, so the
 // scan runs at full occupancy; rows without a cutoff stay with topk_hist(pass 0).
-__global__ void __launch_bounds__(kHistThreads, 8) topk_scan_cut_kernel(TopkArgs a) {
+#ifndef D2B_SCAN_KV
+#define D2B_SCAN_KV 4    // 16-byte loads in flight per thread
+#define D2B_SCAN_MINB 8  // CTAs per SM the register budget must allow
+#endif
+__global__ void __launch_bounds__(kHistThreads, D2B_SCAN_MINB) topk_scan_cut_kernel(TopkArgs a) {
   int g, img, chunk;
   if (!locate(a, blockIdx.x, g, img, chunk)) return;
   const int row = img * a.d.G + g;
@@ -375,7 +382,7 @@ __global__ void __launch_bounds__(kHistThreads, 8) topk_scan_cut_kernel(TopkArgs
   if ((reinterpret_cast<uintptr_t>(x + beg) & 15) == 0) {
     const long long nvec = (end - beg) >> 2;
     const float4* xv = reinterpret_cast<const float4*>(x + beg);
-    constexpr int kV = 4;
+    constexpr int kV = D2B_SCAN_KV;
     const long long step = (long long)kV * kHistThreads;
     for (long long v0 = 0; v0 < nvec; v0 += step) {
       float4 q[kV];
