@@ -165,7 +165,10 @@ __global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a, int stage) {
   if (nmatch == 0) return;
   const unsigned lo_i = ~a.wlo[(size_t)b * a.n + i], hi_i = a.whi[(size_t)b * a.n + i];  // non-zero words of row i
   if (stage && nmatch > 0 && nmatch <= 256) {
-    for (int w = (int)lo_i + threadIdx.x; w <= (int)hi_i && lo_i != 0xffffffffu; w += 256) s_pi[w] = pi[w];
+    for (int w = (int)lo_i + threadIdx.x; w <= (int)hi_i && lo_i != 0xffffffffu; w += 256) {
+      D2B_BOUND(w, a.Wd);
+      s_pi[w] = pi[w];
+    }
     __syncthreads();  // (block-uniform condition)
   }
   if (nmatch > 256) {  // (more than 256 same-class columns: the plain scan)
@@ -205,6 +208,7 @@ __global__ void __launch_bounds__(256) mnms_iou_kernel(MnmsArgs a, int stage) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int w = w0 + u * 32 + lane;
+        D2B_BOUND(w < w_end ? w : 0, a.Wd);
         if (w < w_end) c += __popcll((stage ? s_pi[w] : pi[w]) & v[u]);
       }
     }
