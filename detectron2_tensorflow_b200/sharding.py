@@ -322,6 +322,7 @@ class PeerGatherPlan(object):
         """blocks[i] = dict of [e - b, ...] contiguous tensors for layout[rank][i]."""
         nv = self._nv
         addrs = []
+        self._keep = []  # the tensors whose addresses the (possibly captured) kernel was given
         for blk in blocks:
             for k in self.spec:
                 assert blk[k].is_contiguous() and blk[k].dtype == self.spec[k][1]
