@@ -112,28 +112,42 @@ class MaskRCNNPostBackbone(object):
         def mark(i):
             if events is not None:
                 events[i].record()
-        n = x["shapes"].shape[0]
-        dev = x["shapes"].device
         mark(0)
+        st = self.stage_proposals(x)
+        mark(1)
+        self.stage_box_pool(x, st)
+        mark(2)
+        self.stage_detections(x, st)
+        mark(3)
+        self.stage_mask_pool(x, st)
+        mark(4)
+        return dict(proposals=st["props"], box_feats=st["box_feats"], dets=st["dets"], mask_feats=st["mask_feats"])
+
+    # the four stages of the step (each runs on torch's current stream; `st` carries the intermediate results)
+    def stage_proposals(self, x):
+        n, dev = x["shapes"].shape[0], x["shapes"].device
         outs = RPNOutputs(self.rpn_tf, ImageList(None, x["shapes"]), x["logits"], x["deltas"], x["anchors"])
         props = outs.find_top_proposals(self.rpn_thr, self.pre, self.R, self.min_len)
-        mark(1)
         inst = SparseBoxList(self._grid(n, self.R, dev), BoxList(props.boxes.reshape(-1, 4)), (n, self.R))
         inst.set_tracking("image_shape", x["shapes"])
-        box_feats = self.box_pooler(x["feats"], inst)
-        mark(2)
+        return {"props": props, "inst": inst, "box_feats": None, "dets": None, "mask_feats": None}
+
+    def stage_box_pool(self, x, st):
+        st["box_feats"] = self.box_pooler(x["feats"], st["inst"])
+
+    def stage_detections(self, x, st):
+        inst = st["inst"]
         boxes = self.box_tf.apply_deltas(x["cls_deltas"], inst.data.boxes)
-        dets, _ = fast_rcnn_inference(boxes, x["scores"], inst, self.score_thr, self.nms_thr, self.D, self.agnostic)
-        mark(3)
-        mask_feats = None
+        st["dets"], _ = fast_rcnn_inference(boxes, x["scores"], inst, self.score_thr, self.nms_thr, self.D, self.agnostic)
+
+    def stage_mask_pool(self, x, st):
         if self.mask_on:
-            dinst = SparseBoxList(self._grid(n, self.D, dev), BoxList(dets.boxes.reshape(-1, 4)), (n, self.D))
-            mask_feats = self.mask_pooler(x["feats"], dinst)
-        mark(4)
-        return dict(proposals=props, box_feats=box_feats, dets=dets, mask_feats=mask_feats)
+            n, dev = x["shapes"].shape[0], x["shapes"].device
+            dinst = SparseBoxList(self._grid(n, self.D, dev), BoxList(st["dets"].boxes.reshape(-1, 4)), (n, self.D))
+            st["mask_feats"] = self.mask_pooler(x["feats"], dinst)
 
     # ------------------------------------------------------------------ CUDA-graphed, chunk-concurrent step
-    def capture(self, x, chunks=4, epilogue=None, epilogue_warmup=True):
+    def capture(self, x, chunks=4, epilogue=None, epilogue_warmup=True, hbm_lane=False):
         """Capture the device-resident step as ONE CUDA graph in which the batch is cut into `chunks` image blocks
         that run on their own streams (forked from / joined to the capturing stream).  Images are independent, so
         the latency-bound proposal / post-processing kernels of one block overlap the HBM-bound ROIAlign of
@@ -163,10 +177,38 @@ class MaskRCNNPostBackbone(object):
             start = torch.cuda.Event()
             start.record(cur)
             outs = []
-            for s, (b, e) in zip(streams, bounds):
-                s.wait_event(start)
-                with torch.cuda.stream(s):
-                    outs.append(self.flatten_outputs(self(cut(b, e))))
+            if not hbm_lane or chunks == 1:
+                for s, (b, e) in zip(streams, bounds):
+                    s.wait_event(start)
+                    with torch.cuda.stream(s):
+                        outs.append(self.flatten_outputs(self(cut(b, e))))
+            else:
+                xs = [cut(b, e) for b, e in bounds]
+                sts = [None] * chunks
+                lane = [None]  # the event of the last pooler in the lane
+
+                def in_lane(c, fn):
+                    with torch.cuda.stream(streams[c]):
+                        if lane[0] is not None:
+                            streams[c].wait_event(lane[0])
+                        fn(xs[c], sts[c])
+                        ev = torch.cuda.Event()
+                        ev.record(streams[c])
+                        lane[0] = ev
+                lag = 2  # a detection stage lasts about two box poolers of a block
+                for i in range(chunks + lag):
+                    if i < chunks:
+                        streams[i].wait_event(start)
+                        with torch.cuda.stream(streams[i]):
+                            sts[i] = self.stage_proposals(xs[i])
+                        in_lane(i, self.stage_box_pool)
+                        with torch.cuda.stream(streams[i]):
+                            self.stage_detections(xs[i], sts[i])
+                    if i >= lag:
+                        in_lane(i - lag, self.stage_mask_pool)
+                for st in sts:
+                    outs.append(self.flatten_outputs(dict(proposals=st["props"], box_feats=st["box_feats"],
+                                                          dets=st["dets"], mask_feats=st["mask_feats"])))
             for s in streams:
                 cur.wait_stream(s)
             if epilogue is not None and with_epilogue:
@@ -186,11 +228,11 @@ class MaskRCNNPostBackbone(object):
             outs = step()
         return GraphedStep(graph, outs, bounds, nv.kernel_launch_count() - l0)
 
-    def pipeline(self, x, chunks=4, depth=2, epilogues=None, epilogue_warmup=True):
+    def pipeline(self, x, chunks=4, depth=2, epilogues=None, epilogue_warmup=True, hbm_lane=False):
         """`depth` independent captures of the step over the same static inputs `x` -> StepPipeline
         (`epilogues[i]`: the capture epilogue of step i)."""
         depth = max(1, int(depth))
-        return StepPipeline([self.capture(x, chunks, epilogues[i] if epilogues else None, epilogue_warmup)
+        return StepPipeline([self.capture(x, chunks, epilogues[i] if epilogues else None, epilogue_warmup, hbm_lane)
                              for i in range(depth)],
                             x["shapes"].device)
 

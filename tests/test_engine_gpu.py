@@ -60,14 +60,14 @@ def test_engine_matches_oracle_and_host_path(cuda, oracle_lib):
             assert torch.equal(ho[k], v.cpu()), (chunk, k)
 
 
-@pytest.mark.parametrize("chunks", [1, 2, 3, 5])
-def test_graphed_chunked_step_matches_eager(cuda, chunks):
+@pytest.mark.parametrize("chunks,hbm_lane", [(1, False), (2, False), (3, False), (5, False), (2, True), (3, True), (5, True)])
+def test_graphed_chunked_step_matches_eager(cuda, chunks, hbm_lane):
     """`capture()`: the step as one CUDA graph, image blocks on concurrent streams.  Replays must reproduce the
     eager single-stream outputs bit for bit, also after the static inputs are refilled in place."""
     N, R, D, K, C = 5, 48, 12, 6, 16
     eng = MaskRCNNPostBackbone(rois_per_image=R, dets_per_image=D, pre_nms_topk=150)
     x = _t(_inputs(N, R, K, C, seed=1), cuda)
-    g = eng.capture(x, chunks=chunks)
+    g = eng.capture(x, chunks=chunks, hbm_lane=hbm_lane)  # hbm_lane: the poolers of all blocks chained into one lane
     assert g.kernels_per_replay > 0 and len(g.outputs) == min(chunks, N)
     for seed in (1, 2):
         fresh = _t(_inputs(N, R, K, C, seed=seed), cuda)

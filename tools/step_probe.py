@@ -40,10 +40,10 @@ for n in [int(v) for v in args.images.split(",")]:
     stages = [float(np.median([ev[i][s].elapsed_time(ev[i][s + 1]) for i in range(args.iters)])) for s in range(4)]
     out = {"images": n, "stages_ms": dict(zip(("rpn_proposals", "box_roi_align", "fast_rcnn_post", "mask_roi_align"), stages)),
            "eager_ms": float(sum(stages))}
-    for chunks in (1, 2, 4):
+    for chunks, lane in ((1, False), (2, False), (4, False), (2, True), (4, True), (8, True), (16, True)):
         if chunks > n:
             continue
-        g = hp.capture(x, chunks=chunks)
+        g = hp.capture(x, chunks=chunks, hbm_lane=lane)
         for _ in range(3):
             g.replay()
         torch.cuda.synchronize()
@@ -52,7 +52,7 @@ for n in [int(v) for v in args.images.split(",")]:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); g.replay(); b.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
-        out[f"graph_ms_{chunks}_blocks"] = float(np.median(ts))
+        out[f"graph_ms_{chunks}_blocks" + ("_hbm_lane" if lane else "")] = float(np.median(ts))
         out["kernels"] = g.kernels_per_replay // chunks
         del g
     print(json.dumps(out), flush=True)
