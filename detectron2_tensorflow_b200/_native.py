@@ -67,7 +67,8 @@ class FastRcnnParams(C.Structure):
                 ("rmax", _i32), ("num_bbox_reg_classes", _i32), ("num_classes", _i32), ("image_shapes", _vp),
                 ("score_thresh", _f32), ("nms_thresh", _f32), ("topk_per_image", _i32),
                 ("nms_cls_agnostic", _i32), ("out_boxes", _vp), ("out_scores", _vp), ("out_classes", _vp),
-                ("out_valid", _vp), ("out_roi_index", _vp), ("out_num", _vp), ("out_nms_boxes_in", _vp)]
+                ("out_valid", _vp), ("out_roi_index", _vp), ("out_num", _vp), ("out_nms_boxes_in", _vp),
+                ("deltas", _vp), ("proposal_boxes", _vp), ("weights", _f32 * 4), ("scale_clamp", _f32)]
 
 
 class RetinanetParams(C.Structure):

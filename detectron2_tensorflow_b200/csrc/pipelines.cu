@@ -145,8 +145,22 @@ int rpn_plan(const d2b_rpn_proposals_params* p, RpnPlan& pl) {
 // detection tail shared by Fast R-CNN and RetinaNet:
 //   sorted candidate keys -> class-offset boxes -> NMS -> padded outputs
 // =====================================================================================
+// The predicted box (pred row i, regression class k) of the Fast R-CNN head: read from `boxes`, or -- fused decode --
+// Box2BoxTransform.apply_deltas of (deltas[i, k], proposals[i]) evaluated on the spot (same d2b_decode as
+// d2b_apply_deltas: identical bits).
+struct FrcnnBoxes {
+  const float4* boxes;   // [M, Kb] or NULL
+  const float4* deltas;  // [M, Kb]
+  const float4* props;   // [M]
+  float wy, wx, wh, ww, clampv;
+  __device__ __forceinline__ float4 get(long long i, int k, int Kb) const {
+    if (boxes) return __ldg(boxes + i * Kb + k);
+    return d2b_decode(__ldg(deltas + i * Kb + k), __ldg(props + i), wy, wx, wh, ww, clampv);
+  }
+};
+
 struct FrcnnFetch {
-  const float4* boxes;    // [M, Kb]
+  FrcnnBoxes boxes;       // [M, Kb]
   const float* scores;    // [M, K+1]
   const int32_t* slot_map;  // [N, Rmax] -> pred row
   const int32_t* shapes;
@@ -156,7 +170,7 @@ struct FrcnnFetch {
     roi = (int)(ci - (unsigned)cls * (unsigned)Rmax);
     const int i = slot_map[(size_t)n * Rmax + roi];
     const float h = (float)shapes[2 * n], w = (float)shapes[2 * n + 1];
-    box = d2b_clip(__ldg(boxes + (size_t)i * Kb + (Kb == 1 ? 0 : cls)), h, w);
+    box = d2b_clip(boxes.get(i, Kb == 1 ? 0 : cls, Kb), h, w);
     score = __ldg(scores + (size_t)i * (K + 1) + cls);
   }
 };
@@ -398,7 +412,7 @@ __global__ void yolo_prep_kernel(const float* probs, int n, int K, float thresh,
 // ------------------------------------------------------------------ Fast R-CNN front
 // one thread per (prediction row, class): threshold -> candidate key; also the dense slot map
 // and max_coord over ALL clipped boxes of the image (fast_rcnn.py:109-116,141).
-__global__ void frcnn_prep_kernel(const float4* boxes, const float* scores, const long long* indices, long long M,
+__global__ void frcnn_prep_kernel(const FrcnnBoxes boxes, const float* scores, const long long* indices, long long M,
                                   int N, int Rmax, int Kb, int K, const int32_t* shapes, float thresh, int P,
                                   u64* keys, int32_t* count, int32_t* slot_map, int* max_coord_bits) {
   grid_dep_sync();
@@ -420,7 +434,7 @@ __global__ void frcnn_prep_kernel(const float4* boxes, const float* scores, cons
     if (k == 0) slot_map[n * Rmax + r] = (int32_t)i;
     if (k < Kb) {
       const float h = (float)shapes[2 * n], w = (float)shapes[2 * n + 1];
-      const float4 b = d2b_clip(__ldg(boxes + i * Kb + k), h, w);
+      const float4 b = d2b_clip(boxes.get(i, k, Kb), h, w);
       mbits = __float_as_int(fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
     }
     s = __ldg(scores + i * (K + 1) + k);
@@ -716,7 +730,12 @@ extern "C" int d2b_fast_rcnn_postprocess(const d2b_fast_rcnn_params* p, void* wo
   if (p->num_images == 0) return D2B_OK;
   D2B_REQUIRE(p->image_shapes && p->out_boxes && p->out_scores && p->out_classes && p->out_valid,
               "fast_rcnn: NULL pointer");
-  D2B_REQUIRE(p->num_preds == 0 || (p->boxes && p->scores && p->indices), "fast_rcnn: NULL input");
+  D2B_REQUIRE(p->num_preds == 0 || (p->scores && p->indices), "fast_rcnn: NULL input");
+  D2B_REQUIRE(p->num_preds == 0 || p->boxes || (p->deltas && p->proposal_boxes),
+              "fast_rcnn: either boxes or (deltas, proposal_boxes) must be given");
+  const FrcnnBoxes fb{reinterpret_cast<const float4*>(p->boxes), reinterpret_cast<const float4*>(p->deltas),
+                      reinterpret_cast<const float4*>(p->proposal_boxes), p->weights[0], p->weights[1], p->weights[2],
+                      p->weights[3], p->scale_clamp};
   if (workspace == nullptr || workspace_bytes < pl.bytes) {
     set_last_error("fast_rcnn_postprocess needs %zu workspace bytes", pl.bytes);
     return D2B_EWORKSPACE;
@@ -738,14 +757,14 @@ extern "C" int d2b_fast_rcnn_postprocess(const d2b_fast_rcnn_params* p, void* wo
   const long long MK = p->num_preds * p->num_classes;
   if (MK > 0) {
     D2B_CUDA(launch_pdl(frcnn_prep_kernel, dim3((unsigned)((MK + 255) / 256)), dim3(256), 0, st, 0,
-        reinterpret_cast<const float4*>(p->boxes), p->scores, reinterpret_cast<const long long*>(p->indices),
+        fb, p->scores, reinterpret_cast<const long long*>(p->indices),
         p->num_preds, N, p->rmax, p->num_bbox_reg_classes, p->num_classes, p->image_shapes, p->score_thresh, pl.P,
         keys, count, slot_map, reinterpret_cast<int*>(max_coord)));
     D2B_LAUNCH_CHECK();
   }
   rc = sort_segments_desc(keys, N, pl.P, count, st);
   if (rc != D2B_OK) return rc;
-  FrcnnFetch f{reinterpret_cast<const float4*>(p->boxes), p->scores, slot_map, p->image_shapes, p->rmax,
+  FrcnnFetch f{fb, p->scores, slot_map, p->image_shapes, p->rmax,
                p->num_bbox_reg_classes, p->num_classes};
   if (nms_lazy_applies(pl.stride, T))  // cap << candidates: gather + NMS + emit in one launch
     return det_tail<FrcnnFetch, int64_t>(f, keys, count, max_coord, nullptr, pl.P, pl.stride, p->nms_cls_agnostic ? 1 : 0, N,

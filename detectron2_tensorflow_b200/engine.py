@@ -136,9 +136,10 @@ class MaskRCNNPostBackbone(object):
         st["box_feats"] = self.box_pooler(x["feats"], st["inst"])
 
     def stage_detections(self, x, st):
-        inst = st["inst"]
-        boxes = self.box_tf.apply_deltas(x["cls_deltas"], inst.data.boxes)
-        st["dets"], _ = fast_rcnn_inference(boxes, x["scores"], inst, self.score_thr, self.nms_thr, self.D, self.agnostic)
+        # FastRCNNOutputs.inference (fast_rcnn.py:381-395): predict_boxes' decode is fused into the post-processing
+        st["dets"], _ = fast_rcnn_inference(None, x["scores"], st["inst"], self.score_thr, self.nms_thr, self.D,
+                                            self.agnostic, pred_proposal_deltas=x["cls_deltas"],
+                                            box2box_transform=self.box_tf)
 
     def stage_mask_pool(self, x, st):
         if self.mask_on:

@@ -6,25 +6,33 @@ from ... import _native as nv
 from ...structures import BoxList
 
 
-def fast_rcnn_inference(boxes, scores, proposals, score_thresh, nms_thresh, topk_per_image, nms_cls_agnostic):
+def fast_rcnn_inference(boxes, scores, proposals, score_thresh, nms_thresh, topk_per_image, nms_cls_agnostic,
+                        pred_proposal_deltas=None, box2box_transform=None):
     """
     Postprocess predicted boxes: clip, score threshold, class-offset NMS, keep top-k, zero-pad.
 
     Args:
-        boxes (Tensor): (M, K*4) class-specific or (M, 4) class-agnostic predicted boxes.
+        boxes (Tensor): (M, K*4) class-specific or (M, 4) class-agnostic predicted boxes -- or None with
+            `pred_proposal_deltas` (M, K*4 | 4) and `box2box_transform` given: the boxes are then
+            `box2box_transform.apply_deltas(pred_proposal_deltas, proposals.data.boxes)` decoded inside the kernels
+            (what `FastRCNNOutputs.inference` computes, fast_rcnn.py:381-395; identical values, no [M, K*4] tensor).
         scores (Tensor): (M, K+1) class probabilities (last column = background).
         proposals (SparseBoxList): `.indices` [M,2] int64, `.dense_shape` (N, Rmax), tracking 'image_shape'.
     Returns:
         (BoxList, kept_indices): dense BoxList boxes [N,topk,4], scores [N,topk], pred_classes int64 [N,topk],
         is_valid [N,topk]; kept_indices int32 [N,topk] = ROI slot of each detection (-1 padding).
     """
-    host = not boxes.is_cuda
-    dev = nv.device_of(boxes, scores)
+    fused = boxes is None
+    if fused and (pred_proposal_deltas is None or box2box_transform is None):
+        raise ValueError("fast_rcnn_inference: boxes=None needs pred_proposal_deltas and box2box_transform")
+    host = not scores.is_cuda
+    dev = nv.device_of(scores) if fused else nv.device_of(boxes, scores)
     s = nv.to_device(scores, dev, torch.float32)
     M, K1 = s.shape
     K = K1 - 1
-    b = nv.to_device(boxes, dev, torch.float32).reshape(M, -1)
+    b = nv.to_device(pred_proposal_deltas if fused else boxes, dev, torch.float32).reshape(M, -1)
     Kb = b.shape[1] // 4
+    pb = nv.to_device(proposals.data.boxes, dev, torch.float32).reshape(M, 4) if fused else None
     idx = nv.to_device(proposals.indices, dev, torch.int64).reshape(M, 2)
     N, Rmax = int(proposals.dense_shape[0]), int(proposals.dense_shape[1])
     image_shapes = proposals.get_tracking('image_shape')
@@ -36,7 +44,12 @@ def fast_rcnn_inference(boxes, scores, proposals, score_thresh, nms_thresh, topk
     ov = torch.empty((N, T), dtype=torch.bool, device=dev)
     oroi = torch.empty((N, T), dtype=torch.int32, device=dev)
     p = nv.FastRcnnParams()
-    p.boxes, p.scores, p.indices = b.data_ptr(), s.data_ptr(), idx.data_ptr()
+    p.boxes, p.scores, p.indices = (None if fused else b.data_ptr()), s.data_ptr(), idx.data_ptr()
+    if fused:
+        p.deltas, p.proposal_boxes = b.data_ptr(), pb.data_ptr()
+        for i in range(4):
+            p.weights[i] = float(box2box_transform.weights[i])
+        p.scale_clamp = float(box2box_transform.scale_clamp)
     p.num_preds, p.num_images, p.rmax = M, N, Rmax
     p.num_bbox_reg_classes, p.num_classes = Kb, K
     p.image_shapes = shapes.data_ptr()
@@ -74,5 +87,7 @@ class FastRCNNOutputs(object):
         return torch.softmax(self.pred_class_logits, dim=-1)
 
     def inference(self, score_thresh, nms_thresh, topk_per_image, nms_cls_agnostic):
-        return fast_rcnn_inference(self.predict_boxes(), self.predict_probs(), self.proposals, score_thresh,
-                                   nms_thresh, topk_per_image, nms_cls_agnostic)
+        """fast_rcnn.py:381-395; the box decode of `predict_boxes` runs inside the post-processing kernels."""
+        return fast_rcnn_inference(None, self.predict_probs(), self.proposals, score_thresh, nms_thresh,
+                                   topk_per_image, nms_cls_agnostic, pred_proposal_deltas=self.pred_proposal_deltas,
+                                   box2box_transform=self.box2box_transform)

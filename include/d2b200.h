@@ -211,6 +211,9 @@ D2B_API int d2b_rpn_proposals(const d2b_rpn_proposals_params* p, void* workspace
  * fast_rcnn_inference                      lib/modeling/roi_heads/fast_rcnn.py:28-187
  * boxes [M, Kb*4] (Kb = K or 1), scores [M, K+1] (last column = background),
  * indices [M, 2] int64 (image, slot) with dense shape [N, Rmax].
+ * Fused decode (FastRCNNOutputs.inference, fast_rcnn.py:359-369, 381-395): with boxes == NULL the predicted boxes are
+ * Box2BoxTransform.apply_deltas(deltas [M, Kb*4], proposal_boxes [M, 4]) (box_regression.py:76-123) evaluated where a
+ * box is needed -- value-identical to d2b_apply_deltas followed by this call, without the [M, Kb*4] round trip.
  * ---------------------------------------------------------------------- */
 typedef struct {
   const float* boxes;
@@ -231,6 +234,10 @@ typedef struct {
   int32_t* out_roi_index; /* optional [N, topk]: slot of the source ROI, -1 pad (kept_indices) */
   int32_t* out_num;       /* optional [N] */
   int64_t* out_nms_boxes_in; /* optional [1] */
+  const float* deltas;         /* used when boxes == NULL: [M, Kb*4] (dy, dx, dh, dw) */
+  const float* proposal_boxes; /* [M, 4] */
+  float weights[4];            /* (wy, wx, wh, ww) */
+  float scale_clamp;
 } d2b_fast_rcnn_params;
 D2B_API size_t d2b_fast_rcnn_postprocess_workspace_bytes(const d2b_fast_rcnn_params* p);
 D2B_API int d2b_fast_rcnn_postprocess(const d2b_fast_rcnn_params* p, void* workspace,

@@ -261,6 +261,15 @@ def test_fast_rcnn_inference(cuda, oracle_lib, agnostic_reg, agnostic_nms, R, K,
     assert np.array_equal(res.get_field('scores').cpu().numpy(), ws)
     assert np.array_equal(res.boxes.cpu().numpy(), wb)
     assert np.array_equal(kept.cpu().numpy(), wr)
+    # fused decode (FastRCNNOutputs.inference): deltas + proposals in, the boxes decoded inside the kernels
+    res2, kept2 = fast_rcnn_inference(None, T(scores, cuda), inst, 0.05, 0.5, topk, agnostic_nms,
+                                      pred_proposal_deltas=T(deltas, cuda),
+                                      box2box_transform=Box2BoxTransform((10., 10., 5., 5.)))
+    for f in ('is_valid', 'pred_classes', 'scores'):
+        assert torch.equal(res2.get_field(f), res.get_field(f)), f
+    assert torch.equal(res2.boxes, res.boxes) and torch.equal(kept2, kept)
+    with pytest.raises(ValueError):
+        fast_rcnn_inference(None, T(scores, cuda), inst, 0.05, 0.5, topk, agnostic_nms)
 
 
 # ------------------------------------------------------------------ RetinaNet
