@@ -81,7 +81,8 @@ __device__ __forceinline__ FBox filter_box(const CBox c, float kf) {
   return f;
 }
 
-// grid (ceil(W/2), S, csplit).  mask[seg][i][w] bit c: box (w*64+c) is suppressed by box i (only j > i).
+// grid (ceil(W/2), S, csplit).  mask word (i, w) of a segment (column-word major, nms_mask_index), bit c: box (w*64+c)
+// is suppressed by box i (only j > i).
 // csplit > 1 (few segments: the latency regime) deals the column blocks of a row block to csplit CTAs.
 // A CTA handles the 64-row blocks x and nb-1-x of its segment, so every CTA walks nb+1 column blocks (the upper
 // triangle is balanced).  8 independent warps per CTA: warp = (column group q, row half); it owns 32 rows of the
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* bo
     const bool live = i < cnt;
     const CBox bi = canon(live ? b[i] : make_float4(0, 0, 0, 0), live);
     const FBox fi = filter_box(bi, kf);
-    u64* mrow = mask + ((size_t)seg * W * 64 + i) * W;
+    u64* mseg = mask + (size_t)seg * W * 64 * W;  // word (i, cb) at nms_mask_index: lanes = consecutive rows, coalesced
     const int cstep = (kMaskThreads / 64) * (int)gridDim.z;
     int cb = rb + q + (kMaskThreads / 64) * (int)blockIdx.z;
     float4 nxt[2];  // the column boxes of the next visit are loaded one visit ahead
@@ -171,118 +172,10 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* bo
       }
       D2B_BOUND(cb, W);
       D2B_BOUND(i, live ? (long long)W * 64 : (long long)i + 1);
-      if (live) mrow[cb] = bits;
+      if (live) mseg[nms_mask_index(i, cb, W)] = bits;
       __syncwarp();
     }
   }
-}
-
-// One CTA (8 warps) per segment; the removed-set lives in shared memory (W words).  Per 64-row block b:
-//   warp 0      resolves the diagonal 64x64 tile with a warp-parallel fixpoint instead of a 64-step serial
-//               chain: lane l holds the diagonal words of rows l and l+32 in registers; each round ORs
-//               (REDUX) the words of the still-undecided rows, keeps every undecided row no earlier
-//               undecided row can suppress, and removes the rows those suppress.  The result equals the
-//               greedy scan (a row is kept iff no earlier kept row suppresses it); sparse tiles converge
-//               in 2-3 rounds.  The same warp prefetches, a block ahead, the diagonal word and the NEXT
-//               word of its rows, so folding block b into removed[b+1] is a register select + REDUX.
-//   warps 1-7   OR the kept rows of block b-1 into the remaining words (>= b+1) meanwhile.
-// One CTA-wide barrier per block.  The sweep stops at the cap.
-constexpr int kSweepThreads = 256;
-constexpr int kOrThreads = kSweepThreads - 32;
-
-__global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const int32_t* counts, int n, int W, int max_out,
-                                                                   const u64* mask, int32_t* keep,
-                                                                   int32_t* num_keep) {
-  extern __shared__ u64 s_removed[];  // [W]
-  __shared__ u64 s_keepm[2];
-  const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-  const int cnt = counts ? min(counts[seg], n) : n;
-  const u64* m = mask + (size_t)seg * W * 64 * W;
-  int32_t* kp = keep + (size_t)seg * max_out;
-  for (int w = tid; w < W; w += kSweepThreads) s_removed[w] = 0;
-  const int nb = (cnt + 63) >> 6;
-  // warp 0, lane l: rows (b*64 + l) and (b*64 + 32 + l): diagonal word b and next word b+1
-  u64 dA = 0, dB = 0, nA = 0, nB = 0;
-  if (tid < 32 && nb > 0) {
-    const int i0 = lane, i1 = 32 + lane;
-    if (i0 < cnt) { dA = m[(size_t)i0 * W]; if (1 < W) nA = m[(size_t)i0 * W + 1]; }
-    if (i1 < cnt) { dB = m[(size_t)i1 * W]; if (1 < W) nB = m[(size_t)i1 * W + 1]; }
-  }
-  __syncthreads();
-  int kept = 0;
-  for (int b = 0; b < nb; ++b) {
-    const int par = b & 1;
-    if (tid < 32) {
-      // prefetch block b+1 (independent of the resolve)
-      u64 pdA = 0, pdB = 0, pnA = 0, pnB = 0;
-      if (b + 1 < nb) {
-        const int i0 = (b + 1) * 64 + lane, i1 = i0 + 32;
-        D2B_BOUND(b + 1, W);
-        if (i0 < cnt) { pdA = m[(size_t)i0 * W + (b + 1)]; if (b + 2 < W) pnA = m[(size_t)i0 * W + (b + 2)]; }
-        if (i1 < cnt) { pdB = m[(size_t)i1 * W + (b + 1)]; if (b + 2 < W) pnB = m[(size_t)i1 * W + (b + 2)]; }
-      }
-      const int rows = min(64, cnt - b * 64);
-      u64 rem = s_removed[b];
-      if (rows < 64) rem |= ~0ull << rows;
-      u64 U = ~rem, K = 0;
-      const u64 bitA = 1ull << lane, bitB = 1ull << (lane + 32);
-      while (U) {  // warp-uniform
-        const u64 blocked = warp_or64(((U & bitA) ? dA : 0ull) | ((U & bitB) ? dB : 0ull));
-        const u64 nk = U & ~blocked;  // never empty: the first undecided row cannot be blocked
-        K |= nk;
-        U &= ~nk;
-        U &= ~warp_or64(((nk & bitA) ? dA : 0ull) | ((nk & bitB) ? dB : 0ull));
-      }
-      int c = __popcll(K);
-      const int left = max_out - kept;
-      while (c > left) {  // cap reached inside this block: keep only the first `left`
-        K &= ~(1ull << (63 - __clzll((long long)K)));
-        --c;
-      }
-      D2B_BOUND(kept + c - 1, c > 0 ? max_out : kept + c);
-      if (K & bitA) kp[kept + __popcll(K & (bitA - 1ull))] = b * 64 + lane;
-      if (K & bitB) kp[kept + __popcll(K & (bitB - 1ull))] = b * 64 + 32 + lane;
-      const u64 fold = warp_or64(((K & bitA) ? nA : 0ull) | ((K & bitB) ? nB : 0ull));
-      if (lane == 0) {
-        s_keepm[par] = K;
-        if (fold && b + 1 < W) atomicOr(&s_removed[b + 1], fold);
-      }
-      dA = pdA; dB = pdB; nA = pnA; nB = pnB;
-    } else if (b > 0) {
-      // OR the kept rows of block b-1 into words >= b+1 (word b was folded in right after its resolve).
-      // Threads are laid out words-across x row-groups-down; each scans its share of the 64 rows.
-      const int t = tid - 32;
-      const u64 pk = s_keepm[par ^ 1];
-      const int wrem = W - (b + 1);
-      if (wrem > 0 && pk) {
-        const int Wp = wrem < kOrThreads ? wrem : kOrThreads;
-        const int groups = kOrThreads / Wp;
-        const int wl = t % Wp, rg = t / Wp;
-        if (rg < groups) {
-          for (int w = b + 1 + wl; w < W; w += Wp) {
-            u64 acc = 0;
-            for (int x0 = rg; x0 < 64; x0 += groups * 8) {
-              u64 v[8];  // independent (predicated) loads: all in flight before the first use
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const int x = x0 + u * groups;
-                D2B_BOUND(w, W);
-                v[u] = (x < 64 && ((pk >> x) & 1ull)) ? __ldg(m + ((size_t)(b - 1) * 64 + x) * W + w) : 0ull;
-              }
-#pragma unroll
-              for (int u = 0; u < 8; ++u) acc |= v[u];
-            }
-            if (acc) atomicOr(&s_removed[w], acc);
-          }
-        }
-      }
-    }
-    __syncthreads();  // block b resolved and folded into removed[b+1]; OR-rest of block b-1 complete
-    kept += __popcll(s_keepm[par]);
-    if (kept >= max_out) break;
-  }
-  for (int j = kept + tid; j < max_out; j += kSweepThreads) kp[j] = -1;
-  if (tid == 0) num_keep[seg] = kept;
 }
 
 // Column-owner sweep (nms.cuh) for W <= kColSweepMaxW; one CTA per segment.
@@ -526,10 +419,8 @@ int nms_sorted(const float* boxes, const int32_t* counts, int S, int n, int max_
                       mask));
   D2B_LAUNCH_CHECK();
   if (!sweep) return D2B_OK;  // the caller runs its own sweep over the mask (fused with the proposal merge)
-  if (W <= kColSweepMaxW)
-    nms_sweep_cols_kernel<<<S, kColSweepThreads, 0, st>>>(counts, n, W, max_out, mask, keep, num_keep);
-  else
-    nms_sweep_kernel<<<S, kSweepThreads, (size_t)W * sizeof(u64), st>>>(counts, n, W, max_out, mask, keep, num_keep);
+  D2B_REQUIRE(W <= kColSweepMaxW, "nms: n=%d too large for the bitmask sweep", n);
+  nms_sweep_cols_kernel<<<S, kColSweepThreads, 0, st>>>(counts, n, W, max_out, mask, keep, num_keep);
   D2B_LAUNCH_CHECK();
   return D2B_OK;
 }

@@ -11,7 +11,10 @@ __device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
 }
 
 // Greedy sweep over the suppression bitmask of ONE segment by a CTA of kColSweepThreads threads (32 warps).
-// mask[i][w] bit c: box i suppresses box 64w+c (only c > i is set / read).  Warp q OWNS the column words
+// mask word (row i, column word w), bit c: box i suppresses box 64w+c (only c > i is set / read).  In global memory
+// the mask is stored COLUMN-WORD MAJOR -- word (i, w) at w * (64 W) + i -- so that the 64 rows of a block's column
+// word are 512 contiguous bytes: the sweep's loads (lane = row) and nms_mask_kernel's stores (lane = row) are
+// coalesced; row-major they were 32 separate sectors per warp access.  Warp q OWNS the column words
 // q, q+32, ...: for word b it ORs, block by block, the rows of the KEPT boxes of every earlier 64-row block into a
 // per-lane accumulator (lane = rows l and l+32 of the block; the loads do not depend on the kept bits, so they are
 // issued several blocks ahead of the flag they wait for), then resolves the diagonal 64x64 tile with a
@@ -21,17 +24,23 @@ __device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
 // Blocks after the cap (max_out kept) publish an empty set at once.  Returns the number of kept boxes (uniform
 // over the CTA, after a __syncthreads()).
 constexpr int kColSweepThreads = 1024;
-constexpr int kColSweepMaxW = 256;  // n <= 16384 (a warp owns words q, q + 32, ...: up to 8 of them)
+// position of mask word (row, column word) of a segment whose mask has W column words (64 W rows)
+__host__ __device__ __forceinline__ size_t nms_mask_index(int row, int word, int W) {
+  return (size_t)word * ((size_t)W * 64) + (size_t)row;
+}
+constexpr int kColSweepMaxW = 1024;  // n <= 65536 (a warp owns words q, q + 32, ...: up to 32 of them)
 
 // SMEM_OUT: instead of the global keep list, the kept boxes' positions and the order-preserving keys of their scores
 // (sc = the segment's scores in candidate order) go to shared memory (s_pos / s_key, max_out entries each).
-// MASK_SMEM: the mask lives in shared memory (plain loads instead of ld.global.cg).
+// MASK_SMEM: the mask lives in shared memory, row-major [row][W] (plain loads instead of ld.global.cg).
 template <bool SMEM_OUT = false, bool MASK_SMEM = false>
 __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, const unsigned long long* __restrict__ m,
                                                  int32_t* __restrict__ kp, const float* __restrict__ sc = nullptr,
                                                  uint32_t* s_key = nullptr, uint16_t* s_pos = nullptr) {
   typedef unsigned long long u64;
-  auto ldm = [&](size_t idx) -> u64 { return MASK_SMEM ? m[idx] : __ldcg(m + idx); };
+  auto ldm = [&](int row, int word) -> u64 {
+    return MASK_SMEM ? m[(size_t)row * W + word] : __ldcg(m + nms_mask_index(row, word, W));
+  };
   __shared__ volatile u64 s_keep[kColSweepMaxW];
   __shared__ volatile int s_flag[kColSweepMaxW];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -47,8 +56,8 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
     // the diagonal tile of this block (independent of everything before it): in flight during the wait below
     const int rows = min(64, cnt - word * 64);
     u64 dA = 0, dB = 0;
-    if (lane < rows) dA = ldm((size_t)(word * 64 + lane) * W + word);
-    if (lane + 32 < rows) dB = ldm((size_t)(word * 64 + 32 + lane) * W + word);
+    if (lane < rows) dA = ldm(word * 64 + lane, word);
+    if (lane + 32 < rows) dB = ldm(word * 64 + 32 + lane, word);
     float scA = 0.0f, scB = 0.0f;
     if (SMEM_OUT) {
       if (lane < rows) scA = __ldg(sc + word * 64 + lane);
@@ -59,8 +68,8 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
     for (int u = 0; u < kAhead; ++u) {
       pa[u] = 0; pb[u] = 0;
       if (u < word) {
-        pa[u] = ldm((size_t)(u * 64 + lane) * W + word);
-        pb[u] = ldm((size_t)(u * 64 + 32 + lane) * W + word);
+        pa[u] = ldm(u * 64 + lane, word);
+        pb[u] = ldm(u * 64 + 32 + lane, word);
       }
     }
     for (int b0 = 0; b0 < word && !capped; b0 += kAhead) {
@@ -72,8 +81,8 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
           const int nx = b + kAhead;  // refill this slot for the block kAhead further on
           if (nx < word) {
             D2B_BOUND(nx * 64 + 32 + lane, (long long)W * 64);
-            pa[u] = ldm((size_t)(nx * 64 + lane) * W + word);
-            pb[u] = ldm((size_t)(nx * 64 + 32 + lane) * W + word);
+            pa[u] = ldm(nx * 64 + lane, word);
+            pb[u] = ldm(nx * 64 + 32 + lane, word);
           }
           // only the owner of the next block polls back to back; warps further from their turn sleep in between, so
           // that the polling does not take issue slots and shared-memory bandwidth from the warp on the critical path
