@@ -9,7 +9,7 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libd2b200.so")
+LIB_PATH = os.environ.get("D2B_LIB") or os.path.join(_PKG, "lib", "libd2b200.so")  # D2B_LIB: A/B builds (tools/)
 
 MAX_LEVELS = 8
 DTYPE_F32, DTYPE_BF16 = 0, 1
