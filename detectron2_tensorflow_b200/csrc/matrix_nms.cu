@@ -94,7 +94,10 @@ __global__ void __launch_bounds__(256) mnms_popc_kernel(MnmsArgs a) {
 // (lane = one float4 = 4 pixels; 16 lanes = 64 pixels = one word) and keeps kPackSteps independent
 // 16-byte loads in flight per lane.  grid (ceil(Wd / 128), n, B), 256 threads = 128 words per CTA.
 constexpr int kPackSteps = 8;
-__global__ void __launch_bounds__(256) mnms_pack4_kernel(MnmsArgs a) {
+#ifndef D2B_PACK_MINB
+#define D2B_PACK_MINB 1
+#endif
+__global__ void __launch_bounds__(256, D2B_PACK_MINB) mnms_pack4_kernel(MnmsArgs a) {
   grid_dep_sync();
   const int b = blockIdx.z, i = blockIdx.y;
   if (i >= rows_of(a, b)) return;
