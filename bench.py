@@ -463,7 +463,7 @@ def run_gpu(args):
     roofline = {"kernel": "roi_align_kernel<float,float,2> (box pooler 7x7, 16000 ROIs)", "bound": "hbm",
                 "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg, "peak_source": peak_src, "kernel_ms": float(st[1]),
-                "traffic_source": "profiles/roofline_traffic.json (ncu --set full capture of the same launch; "
+                "traffic_source": "profiles/roofline_traffic.json (ncu capture of the same launch of the same binary; "
                                   "constant, not re-measured in this run)",
                 "note": "frac uses SURVEY 8(d)'s algorithmic bytes (whole pyramid read once), which over-count: 1,000 "
                         "ROIs/image touch about 2/3 of the pyramid.  frac_on_traffic = DRAM bytes actually moved / "
