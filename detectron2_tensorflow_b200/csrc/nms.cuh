@@ -1,5 +1,7 @@
 // nms.cuh -- device pieces of the bitmask NMS shared by nms.cu and rpn_fused.cu.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "kernels.cuh"
 
 namespace d2b {
@@ -33,7 +35,12 @@ constexpr int kColSweepMaxW = 1024;  // n <= 65536 (a warp owns words q, q + 32,
 // SMEM_OUT: instead of the global keep list, the kept boxes' positions and the order-preserving keys of their scores
 // (sc = the segment's scores in candidate order) go to shared memory (s_pos / s_key, max_out entries each).
 // MASK_SMEM: the mask lives in shared memory, row-major [row][W] (plain loads instead of ld.global.cg).
-template <bool SMEM_OUT = false, bool MASK_SMEM = false>
+// CL > 1: the segment is swept by a CLUSTER of CL CTAs (launch with cluster dimension CL; every CTA calls this with the
+// same arguments): warp (rank * 32 + warp) owns the column words congruent to it modulo 32 CL, so the mask streams
+// into CL SMs instead of one (a 65,536-box segment is 268 MB of upper triangle), and the owner of a block publishes
+// its kept bits into the shared memory of EVERY CTA of the cluster (st.shared::cluster + a cluster-scope fence before
+// the flag); the polling stays local.  The return value is valid in every CTA; rank 0 writes the -1 padding.
+template <bool SMEM_OUT = false, bool MASK_SMEM = false, int CL = 1>
 __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, const unsigned long long* __restrict__ m,
                                                  int32_t* __restrict__ kp, const float* __restrict__ sc = nullptr,
                                                  uint32_t* s_key = nullptr, uint16_t* s_pos = nullptr) {
@@ -46,10 +53,17 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = (cnt + 63) >> 6;
   if (tid < kColSweepMaxW) { s_keep[tid] = 0; s_flag[tid] = 0; }
-  __syncthreads();
+  namespace cg = cooperative_groups;
+  int crank = 0;
+  if constexpr (CL > 1) {
+    crank = (int)cg::this_cluster().block_rank();
+    cg::this_cluster().sync();  // nobody publishes into a peer that has not cleared its flags yet
+  } else {
+    __syncthreads();
+  }
   const u64 bitA = 1ull << lane, bitB = 1ull << (lane + 32);
   constexpr int kAhead = 4;  // blocks whose rows are loaded before their flag is awaited
-  for (int word = warp; word < nb; word += 32) {
+  for (int word = crank * 32 + warp; word < nb; word += 32 * CL) {
     u64 acc = 0;
     int kept_before = 0;
     bool capped = false;
@@ -90,6 +104,7 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
             const int dist = word - b;
             if (dist > 1) __nanosleep(dist > 8 ? 400 : 50 * dist);
           }
+          if constexpr (CL > 1) asm volatile("fence.acq_rel.cluster;" ::: "memory");  // the flag came from a peer CTA
           const u64 K = s_keep[b];
           acc |= ((K & bitA) ? va : 0ull) | ((K & bitB) ? vb : 0ull);
           kept_before += __popcll(K);
@@ -131,18 +146,27 @@ __device__ __forceinline__ int nms_sweep_columns(int cnt, int W, int max_out, co
       }
     }
     __syncwarp();
-    if (lane == 0) {
+    if constexpr (CL > 1) {
+      if (lane < CL) {  // lane p publishes into CTA p of the cluster (its own included)
+        volatile u64* rk = cg::this_cluster().map_shared_rank(const_cast<u64*>(&s_keep[word]), lane);
+        volatile int* rf = cg::this_cluster().map_shared_rank(const_cast<int*>(&s_flag[word]), lane);
+        *rk = K;
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+        *rf = 1;
+      }
+    } else if (lane == 0) {
       s_keep[word] = K;
       __threadfence_block();
       s_flag[word] = 1;
       D2B_PROF(blockIdx.x == 0 && word < 32, 32 + word);
     }
   }
-  __syncthreads();
+  if constexpr (CL > 1) cg::this_cluster().sync();  // (also: no CTA exits while a peer may still store into it)
+  else __syncthreads();
   int kept = 0;
   for (int b = 0; b < nb; ++b) kept += __popcll(s_keep[b]);
   kept = min(kept, max_out);
-  if (!SMEM_OUT)
+  if (!SMEM_OUT && crank == 0)
     for (int j = kept + tid; j < max_out; j += kColSweepThreads) kp[j] = -1;
   return kept;
 }
