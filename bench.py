@@ -1055,7 +1055,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="d2b200", choices=["d2b200", "reference"])
     ap.add_argument("--chunks", type=int, default=4, help="image blocks run concurrently inside the graphed step")
-    ap.add_argument("--in-flight", type=int, default=3, dest="in_flight",
+    ap.add_argument("--in-flight", type=int, default=4, dest="in_flight",
                     help="graphed steps replayed concurrently on alternating streams (1 = strictly one after another)")
     ap.add_argument("--strong-in-flight", type=int, default=6, dest="strong_in_flight",
                     help="graphed steps in flight in the strong-scaling leg (small per-rank blocks: more steps overlap)")

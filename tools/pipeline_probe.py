@@ -12,7 +12,7 @@ dev = torch.device("cuda", 0)
 x = bench.to_torch(bench.make_host_inputs(16), dev=dev)
 eng = bench.make_engine()
 res = {}
-for chunks, depth, lane in ((1, 3, False), (4, 1, False), (4, 3, False), (4, 1, True), (8, 1, True), (4, 2, True), (4, 3, True), (8, 2, True), (8, 3, True), (16, 2, True)):
+for chunks, depth, lane in ((1, 3, False), (1, 4, False), (2, 2, False), (2, 3, False), (2, 4, False), (4, 1, False), (4, 2, False), (4, 3, False), (4, 4, False), (4, 6, False), (8, 2, False), (8, 3, False), (4, 3, True)):
     pipe = eng.pipeline(x, chunks=chunks, depth=depth, hbm_lane=lane)
     pipe.run(2 * depth)
     torch.cuda.synchronize()
