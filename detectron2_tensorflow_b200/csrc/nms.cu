@@ -88,7 +88,10 @@ __device__ __forceinline__ FBox filter_box(const CBox c, float kf) {
 // triangle is balanced).  8 independent warps per CTA: warp = (column group q, row half); it owns 32 rows of the
 // 64-row block and walks column blocks rb+q, rb+q+4, ...  The 64 column boxes of a block are staged in a
 // warp-private shared-memory slice (filter record, canonical box, area), so only __syncwarp is needed.
-__global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(const float4* boxes, const int32_t* counts, int n,
+#ifndef D2B_MASK_MINB
+#define D2B_MASK_MINB 4  // 64 registers; 1 (98 registers), 5 (48) and 6 (40) measured the same or slower
+#endif
+__global__ void __launch_bounds__(kMaskThreads, D2B_MASK_MINB) nms_mask_kernel(const float4* boxes, const int32_t* counts, int n,
                                                                  int W, float thr, u64* mask) {
   grid_dep_sync();
   __shared__ float4 s_flt[kMaskThreads / 32][64];  // (ylo, xlo, yhi, xhi) of the shrunk box
