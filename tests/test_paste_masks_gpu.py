@@ -37,6 +37,33 @@ def test_paste_masks_small(cuda, oracle_lib, H, W, mh, mw):
     assert tuple(e.shape) == (0, H, W)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_paste_masks_two_phase_vs_fused_adversarial_boxes(cuda, oracle_lib, seed, monkeypatch):
+    """The default path (memset + a kernel over a conservative bounding rectangle of each box) against the oracle and
+    against the one-pass kernel (D2B_PASTE_FUSED=1), on boxes that stress the rectangle: reversed (negative step),
+    outside the image, degenerate, sub-pixel, huge coordinates, NaN / inf."""
+    rng = np.random.default_rng(seed)
+    H, W, mh, mw, M = 61, 83, 28, 28, 40
+    masks = _masks(rng, M, mh, mw)
+    y0 = rng.uniform(-30, H + 10, M); x0 = rng.uniform(-30, W + 10, M)
+    boxes = np.stack([y0, x0, y0 + rng.uniform(-20, 60, M), x0 + rng.uniform(-20, 60, M)], 1).astype(np.float32)
+    boxes[0] = [40, 60, 10, 5]                 # reversed on both axes
+    boxes[1] = [-500, -500, -400, -300]        # far outside
+    boxes[2] = [3, 3, 3, 3]                    # a point
+    boxes[3] = [1e7, 2e7, 3e7, 4e7]
+    boxes[4] = [np.nan, 0, 10, 10]
+    boxes[5] = [0, 0, np.inf, 20]
+    boxes[6] = [12.25, 7.5, 12.75, 8.0]        # sub-pixel
+    boxes[7] = [0, 0, H, W]
+    want = oracle_lib.reframe_box_masks_to_image_masks(masks, boxes, (H, W), 0.5)
+    tm, tb = torch.from_numpy(masks).to(cuda), torch.from_numpy(boxes).to(cuda)
+    got = reframe_box_masks_to_image_masks(tm, tb, (H, W), 0.5).cpu().numpy()
+    monkeypatch.setenv("D2B_PASTE_FUSED", "1")
+    fused = reframe_box_masks_to_image_masks(tm, tb, (H, W), 0.5).cpu().numpy()
+    assert np.array_equal(fused, want)
+    assert np.array_equal(got, want)
+
+
 def test_paste_masks_full_image(cuda, oracle_lib):
     """100 detections of one 800x1333 image, 28x28 masks (Mask R-CNN inference shapes)."""
     rng = np.random.default_rng(5)
