@@ -146,7 +146,10 @@ __device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* s_w, u
   return before + inc - v;
 }
 
-__global__ void __launch_bounds__(kSelThreads) rpn_select_kernel(RpnArgs a, float4* seg_boxes, float* seg_scores,
+#ifndef D2B_SEL_MINB
+#define D2B_SEL_MINB 2  // A/B: 1 (104 registers) 0.197 ms at 16 images, 2 (64) 0.160, 4 (32, spills) 0.150 alone but the pipelined step 0.512 -> 0.575 ms
+#endif
+__global__ void __launch_bounds__(kSelThreads, D2B_SEL_MINB) rpn_select_kernel(RpnArgs a, float4* seg_boxes, float* seg_scores,
                                                                   int32_t* seg_count, u64* nms_in_total) {
   grid_dep_sync();
   extern __shared__ __align__(16) unsigned char s_raw_bytes[];
