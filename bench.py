@@ -612,7 +612,7 @@ def strong_scaling(hp, x, dev, world, rank, K, W, chunks, in_flight, full_step, 
     if peer:
         # NVLink peer memory: the pack kernel captured in the step graph stores the block straight into rank 0's
         # receive slot and raises a flag; rank 0's unpack kernel waits for the flags (sharding.PeerGatherPlan)
-        plans = [sharding.PeerGatherPlan(spec, layout, dev) for _ in range(in_flight)]
+        plans = [sharding.PeerGatherPlan(spec, layout, dev, timeout_ms=5000) for _ in range(in_flight)]
     else:
         plans = [sharding.GatherPlan(spec, layout, dev) for _ in range(in_flight)]
     pipe = hp.pipeline(xl, chunks=chunks_of(e - b), depth=in_flight,
@@ -648,6 +648,7 @@ def strong_scaling(hp, x, dev, world, rank, K, W, chunks, in_flight, full_step, 
             ug.replay()
         return plan.out
 
+    barrier()  # captures take different times on different ranks: start the hand-shaking steps together
     for _ in range(W):
         g0.replay()
         full = gather(g0)

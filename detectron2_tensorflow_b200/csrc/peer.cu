@@ -42,7 +42,10 @@ __global__ void __launch_bounds__(kPeerThreads) peer_copy_kernel(const __grid_co
       const unsigned long long want = epoch - (unsigned long long)a.lag;
       const unsigned long long t0 = now_ns();
       unsigned int spins = 0;
-      while (ld_flag(a.wait[tid]) < want) {
+      // once a wait has timed out the ranks are out of step for good: later launches do not wait again (one time-out
+      // per plan, not one per step), the host sees the error word
+      const bool dead = *reinterpret_cast<volatile int*>(a.err) != 0;
+      while (!dead && ld_flag(a.wait[tid]) < want) {
         if ((++spins & 63u) == 0u) {
           if (now_ns() - t0 > a.timeout_ns) {
             *a.err = 1;

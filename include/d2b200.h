@@ -733,7 +733,7 @@ D2B_API int d2b_solo_upsample(const d2b_solo_upsample_params* p, void* workspace
  *
  * d2b_peer_copy: epoch = *epoch_counter + 1.  If num_wait > 0, waits until every wait_flags[i] >=
  * epoch - wait_lag (flags live in THIS GPU's memory; a wait that exceeds timeout_ms sets *error_flag = 1
- * and the kernel goes on, so a lost peer can never hang the GPU).  Then copies every segment (src / dst are
+ * and the kernel goes on, so a lost peer can never hang the GPU; once *error_flag is set later calls do not wait at all).  Then copies every segment (src / dst are
  * device pointers of this GPU or mapped peer memory; any alignment), makes the copies visible system-wide,
  * stores `epoch` into every signal_flags[i] (peer or local memory) and writes *epoch_counter = epoch.
  * `segments`, `wait_flags` pointer values and `signal_flags` are read on the HOST at call time (they travel

@@ -68,6 +68,14 @@ def test_peer_copy_wait_signal_and_timeout(cuda):
                  timeout_ms=50)
     torch.cuda.synchronize()
     assert int(recv[2][0]) == 1 and int(recv[0][0]) == 4
+    # with the error word set, later calls do not wait again (one time-out per plan, not one per step)
+    import time
+    t0 = time.perf_counter()
+    for _ in range(20):
+        nv.peer_copy([(a.data_ptr(), c.data_ptr(), 4000)], cuda, *[t.data_ptr() for t in recv], wait_flags=[f0], wait_lag=0,
+                     timeout_ms=1000)
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t0 < 1.0 and int(recv[0][0]) == 24
 
 
 def test_peer_copy_validation(cuda):
