@@ -360,7 +360,6 @@ class PeerGatherPlan(object):
 
     def check(self):
         """Raise if a wait of this rank ever timed out (host sync)."""
-        import ctypes as C
         err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._nv.peer_copy([(self._ctr(4), err.data_ptr(), 4)], self.device, self._ctr(5), self._ctr(6), self._ctr(7))
         if int(err.item()) != 0:

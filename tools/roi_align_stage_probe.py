@@ -1,5 +1,7 @@
-import json, sys
-sys.path.insert(0, '/root/repo')
+"""Stage times of the box / mask poolers inside the 16-image step (CUDA events); used with D2B_LIB for same-box A/B of
+build variants."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, bench
 dev = torch.device('cuda', 0)
 hp = bench.make_engine()

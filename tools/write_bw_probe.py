@@ -1,4 +1,6 @@
-import torch, numpy as np, json
+"""Pure-write (fill) and copy bandwidth of the GPU on a 1.7 GB buffer: the ceiling of the write-bound kernels."""
+import json, os, sys
+import torch, numpy as np
 dev=torch.device('cuda',0)
 n=1600*800*1333
 x=torch.empty(n, dtype=torch.uint8, device=dev)
