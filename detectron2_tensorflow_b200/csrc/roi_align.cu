@@ -25,7 +25,7 @@ namespace {
 
 constexpr int kMaxSamples = 128;  // max crop rows / cols per ROI (output * sampling_ratio)
 #ifndef D2B_RA_THREADS
-#define D2B_RA_THREADS 256
+#define D2B_RA_THREADS 224  // 7 warps: 49 (98) bins = 7 (14) per warp, balanced; same-box A/B vs 256: box pooler 0.2827 -> 0.2785 ms, mask pooler 0.1004 -> 0.0984 ms
 #endif
 constexpr int kThreads = D2B_RA_THREADS;
 #ifndef D2B_RA_BINS
@@ -135,12 +135,14 @@ __device__ __forceinline__ void build_roi_frame(const RoiAlignArgs& a, long long
     if (a.L > 1) lvl = level_of(b.x, b.y, b.z, b.w, a.min_level, a.max_level, a.canon_size, a.canon_level);
     const Level L = a.lv[lvl];
     const float padf = a.pad ? 1.0f : 0.0f;
-    if (tid < ch) {
-      const float lo = b.x * L.scale + padf, hi = b.z * L.scale + padf;
-      ty[tid] = make_tap(lo, hi, tid, ch, L.H + 2 * a.pad, a.pad, L.H, a.aligned, L.W * a.C);
-    } else if (tid < ch + cw) {
-      const float lo = b.y * L.scale + padf, hi = b.w * L.scale + padf;
-      tx[tid - ch] = make_tap(lo, hi, tid - ch, cw, L.W + 2 * a.pad, a.pad, L.W, a.aligned, a.C);
+    for (int t = tid; t < ch + cw; t += kThreads) {  // (one trip unless the crop has more samples than the CTA threads)
+      if (t < ch) {
+        const float lo = b.x * L.scale + padf, hi = b.z * L.scale + padf;
+        ty[t] = make_tap(lo, hi, t, ch, L.H + 2 * a.pad, a.pad, L.H, a.aligned, L.W * a.C);
+      } else {
+        const float lo = b.y * L.scale + padf, hi = b.w * L.scale + padf;
+        tx[t - ch] = make_tap(lo, hi, t - ch, cw, L.W + 2 * a.pad, a.pad, L.W, a.aligned, a.C);
+      }
     }
     if (tid == kThreads - 1) {
       long long img = a.bidx64 ? reinterpret_cast<const long long*>(a.bidx)[roi * a.bidx_stride]
@@ -448,8 +450,7 @@ static int fill_args(const d2b_roi_align_params* p, RoiAlignArgs& a, bool backwa
   D2B_REQUIRE(p->output_h > 0 && p->output_w > 0, "output size must be positive");
   D2B_REQUIRE(p->sampling_ratio >= 0, "sampling_ratio must be >= 0");
   const int s1 = p->sampling_ratio > 0 ? p->sampling_ratio : 1;
-  D2B_REQUIRE(p->output_h * s1 <= kMaxSamples && p->output_w * s1 <= kMaxSamples &&
-                  (p->output_h + p->output_w) * s1 < kThreads,
+  D2B_REQUIRE(p->output_h * s1 <= kMaxSamples && p->output_w * s1 <= kMaxSamples,
               "output_size*sampling_ratio too large (max %d per axis)", kMaxSamples);
   if (backward) {
     D2B_REQUIRE(p->feature_dtype == D2B_DTYPE_F32 && p->out_dtype == D2B_DTYPE_F32, "backward is fp32 only");

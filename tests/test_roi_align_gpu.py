@@ -77,6 +77,19 @@ def test_single_level_roi_align_and_crop(cuda, oracle_lib):
             assert np.array_equal(got, want), (pad, aligned)
 
 
+def test_large_output_more_samples_than_cta_threads(cuda, oracle_lib):
+    """64x64 output with sampling_ratio 2: 128 + 128 crop taps per ROI, more than the CTA has threads (the tap
+    prologue loops), and 4,096 bins split over many CTAs."""
+    rng = np.random.default_rng(15)
+    img = rng.standard_normal((2, 30, 44, 8)).astype(np.float32)
+    boxes, idx = syn.rois(2, 6, seed=4, image_hw=(480, 704))
+    bi = idx[:, 0].astype(np.int32)
+    want = oracle_lib.roi_align(img, boxes, bi, (64, 64), 1 / 16., 2, True)
+    got = ROIAlign((64, 64), 1 / 16., 2, True)(torch.from_numpy(img).to(cuda), torch.from_numpy(boxes).to(cuda),
+                                               torch.from_numpy(bi).to(cuda)).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
 def test_edge_cases(cuda, oracle_lib):
     rng = np.random.default_rng(6)
     img = rng.standard_normal((2, 20, 30, 8)).astype(np.float32)
